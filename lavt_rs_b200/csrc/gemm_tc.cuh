@@ -1,0 +1,34 @@
+// Parameter block of the tcgen05 GEMM / implicit-GEMM-conv kernel (gemm_tc.cu).
+#pragma once
+#include "geom.cuh"
+#include <cuda_bf16.h>
+
+namespace lavt {
+
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2 };
+
+// out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] + resid[orow(m), n]
+struct GemmParams {
+  int M, N, K;               // logical problem (conv: M = pixels, K = taps*Cin)
+  // ---- epilogue ----
+  const float* cscale;       // [N] or nullptr
+  const float* bias;         // [N] or nullptr
+  int act;                   // GemmAct
+  const __nv_bfloat16* mul;  // [M, ldm] or nullptr (indexed by the GEMM row m)
+  int ldm;
+  const float* resid;        // [rows_out, ldo] or nullptr (indexed by the OUTPUT row)
+  float* out_f32;            // [rows_out, ldo] or nullptr
+  __nv_bfloat16* out_bf16;   // [rows_out, ldo] or nullptr
+  int ldo;
+  // ---- row map ----
+  int rowmap;                // GemmRowMap
+  WinGeom win;               // ROWMAP_WINDOW
+  // ROWMAP_CONV: A is a 4-D NHWC tensor (C, W, H, Nimg), 3x3 taps, pad 1
+  int cH, cW, cCin;          // image height/width, input channels
+  int cTH, cTW;              // tile = cTH x cTW pixels (cTH*cTW == 128)
+  int cTilesH, cTilesW;      // tiles per image
+  int taps;                  // 9 (3x3) or 1
+};
+
+}  // namespace lavt

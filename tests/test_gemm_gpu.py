@@ -1,0 +1,108 @@
+"""tcgen05 GEMM / implicit-GEMM conv (C-ABI lavt_gemm_bf16 / lavt_conv3x3_bf16) vs a plain fp32
+PyTorch evaluation of the same bf16 operands.  Tolerance: outputs are compared in fp32 against an
+fp32-accumulated reference of identical bf16 inputs, so only accumulation order and the final bf16
+rounding differ: |a-b| <= 2e-2*|b| + 2e-2*rms(b) (bf16 outputs), 1e-3 relative-rms for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(out, ref, rtol):
+    out, ref = out.float(), ref.float()
+    rms = ref.pow(2).mean().sqrt().item() + 1e-12
+    err = (out - ref).abs()
+    bound = rtol * ref.abs() + rtol * rms
+    bad = (err > bound).float().mean().item()
+    assert bad == 0.0, f"{bad*100:.4f}% elements out of tolerance; max err {err.max().item():.4e}, rms {rms:.4e}"
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from lavt_rs_b200 import _cabi
+    _cabi.check(_cabi.lib().lavt_check_device(), "lavt_check_device")
+    return _cabi
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 192), (1000, 128, 128), (4608, 1536, 512),
+                                   (77, 384, 1024)])
+def test_gemm_bias_gelu(cabi, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, bias=bias, act=cabi.ACT_GELU, out_bf16=out)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    _close(out, ref, 2e-2)
+
+
+def test_gemm_scale_mul_tanh_resid(cabi):
+    M, N, K = 513, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    cs = torch.rand(N, device="cuda", generator=g) + 0.5
+    mul = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, cscale=cs, act=cabi.ACT_TANH, mul=mul, resid=resid, out_f32=out, out_bf16=outb)
+    ref = torch.tanh((a.float() @ w.float().t()) * cs) * mul.float() + resid
+    _close(out, ref, 2e-3)
+    _close(outb, ref, 2e-2)
+
+
+@pytest.mark.parametrize("dims,window,shifted", [((2, 8, 14, 14), (8, 7, 7), True),
+                                                  ((1, 8, 10, 13), (8, 7, 7), True),
+                                                  ((1, 4, 24, 24), (8, 12, 12), True),
+                                                  ((1, 16, 14, 14), (8, 7, 7), True),
+                                                  ((2, 8, 12, 12), (8, 12, 12), False)])
+def test_gemm_window_scatter(cabi, dims, window, shifted):
+    from lavt_rs_b200.geometry import window_geometry, window_row_map
+    B, D, H, W = dims
+    C = 128
+    geom = window_geometry(B, D, H, W, window, shifted)
+    rows, _, _ = window_row_map(geom)
+    M = geom.rows()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    bias = torch.randn(C, device="cuda", generator=g)
+    x = torch.randn(geom.tokens(), C, device="cuda", generator=g)
+    out = torch.full_like(x, float("nan"))
+    cabi.gemm_bf16(a, w, bias=bias, resid=x, out_f32=out, win=geom)
+    y = a.float() @ w.float().t() + bias
+    rows = rows.cuda()
+    live = rows >= 0
+    ref = x.clone()
+    ref[rows[live]] += y[live]
+    assert not torch.isnan(out).any(), "some token rows were never written"
+    _close(out, ref, 2e-3)
+
+
+@pytest.mark.parametrize("n_img,H,W,Cin,Cout", [(2, 24, 24, 64, 128), (1, 20, 12, 128, 256), (3, 48, 48, 192, 128),
+                                                (1, 96, 96, 640, 512), (2, 15, 30, 64, 128)])
+def test_conv3x3_bn_relu(cabi, n_img, H, W, Cin, Cout):
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cin)
+    x = torch.randn(n_img, H, W, Cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    scale = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    w_taps = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.empty(n_img, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    cabi.conv3x3_bf16(x, w_taps, cscale=scale, bias=shift, act=cabi.ACT_RELU, out_bf16=out.view(-1, Cout))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-2)
+
+
+def test_gemm_rejects_bad_shapes(cabi):
+    a = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(128, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(cabi.LavtError):
+        cabi.gemm_bf16(a, w, out_bf16=out)          # K % 64 != 0
+    with pytest.raises(cabi.LavtError):
+        cabi.gemm_bf16(a.cpu(), w, out_bf16=out)    # no CPU fallback
