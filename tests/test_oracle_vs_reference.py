@@ -1,0 +1,71 @@
+"""Pin the oracle (oracle/lavt_oracle.py) against the UNMODIFIED reference modules, imported from
+/root/reference with external shims.  Runs only where the reference tree exists (the build container);
+on the GPU box the same pinning is carried by tests/golden (see test_oracle_golden.py)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import lavt_oracle as O  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")
+
+
+def _sd(bb, dec):
+    sd = {"backbone." + k: v.detach() for k, v in bb.state_dict().items()}
+    sd.update({"classifier." + k: v.detach() for k, v in dec.state_dict().items()})
+    return sd
+
+
+def _randomise_norms(mods, seed=3):
+    """init_weights leaves LN/BN at identity; perturb them so affine / running stats are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, (torch.nn.LayerNorm, torch.nn.BatchNorm2d)):
+                m.weight.data.add_(0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.data.add_(0.1 * torch.randn(m.bias.shape, generator=g))
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.add_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.add_(0.2 * torch.rand(m.running_var.shape, generator=g))
+            if isinstance(m, torch.nn.Linear) and m.bias is not None:
+                m.bias.data.add_(0.05 * torch.randn(m.bias.shape, generator=g))
+
+
+@pytest.mark.parametrize("window,T,HW,mha", [((8, 7, 7), 4, (64, 64), (1, 1, 1, 1)),
+                                             ((8, 7, 7), 16, (48, 40), (1, 1, 1, 1)),
+                                             ((8, 12, 12), 8, (96, 96), (1, 2, 4, 4)),
+                                             ((8, 12, 12), 2, (40, 52), (1, 1, 1, 1))])
+def test_backbone_and_decoder_match_reference(window, T, HW, mha):
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=window, mha=mha, depths=(2, 2, 2, 2))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=window, fusion_heads=mha)
+    x, l, m = O.synthetic_inputs(2, T, HW[0], HW[1], Nl=11)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        ref = bb(xv, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert a.shape == b.shape
+            err = (a - b).abs().max().item()
+            assert err < 2e-4, f"stage {i}: max err {err}"
+        ref_logits = dec(ref[3], ref[2], ref[1], ref[0])
+        got_logits = O.decoder_forward(sd, got[3], got[2], got[1], got[0])
+        assert (ref_logits - got_logits).abs().max().item() < 2e-4
+
+
+def test_random_state_dict_matches_reference_keys():
+    net, _ = ref_shims.build_reference("lavt_video", "tiny")
+    ref_sd = {k: v for k, v in net.state_dict().items() if not k.startswith("text_encoder.")}
+    cfg = O.OracleConfig.swin("tiny")
+    sd = O.random_state_dict(cfg)
+    skip = ("relative_position_index", "num_batches_tracked")
+    ref_keys = {k for k in ref_sd if not k.endswith(skip)}
+    assert ref_keys == set(sd.keys())
+    for k in ref_keys:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
