@@ -81,6 +81,63 @@ int lavt_gemm_bf16(const void* A, int64_t lda, const void* Wt, int64_t ldw, int3
 int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H, int32_t W, int32_t Cin,
                       const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream);
 
+/* ---- LayerNorm fused with the gathers that feed the GEMMs (fp32 rows in, bf16 and/or fp32 rows out) ---- */
+
+/* out[m,:] = LN(x[m,:]) * gamma + beta over C channels.  norm2 before the MLP (lib/video_swin_transformer.py:250),
+ * patch_embed.norm (:630), per-stage output norm{i} (:871).  C % 128 == 0. out_bf16 / out_f32 may be NULL (not both). */
+int lavt_layernorm_rows(const float* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
+                        float eps, void* out_bf16, float* out_f32, void* stream);
+
+/* LN1 + zero pad + cyclic shift + window_partition as one gather (lib/video_swin_transformer.py:218-234):
+ * out[(b*nW + w)*N + t, :] = LN(x[token(w,t)]) or 0 for a pad row.  x is (B,D,H,W,C) fp32. */
+int lavt_layernorm_window_gather(const float* x, int32_t C, const lavt_win_geom_t* geom, const float* gamma,
+                                 const float* beta, float eps, void* out_bf16, void* stream);
+
+/* PatchMerging gather + LN(4C) (lib/video_swin_transformer.py:298-308): (B,D,H,W,C) fp32 ->
+ * (B,D,ceil(H/2),ceil(W/2),4C) bf16, channel blocks ordered (0,0),(1,0),(0,1),(1,1); odd H/W zero padded. */
+int lavt_patch_merge_layernorm(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C,
+                               const float* gamma, const float* beta, float eps, void* out_bf16, void* stream);
+
+/* PatchEmbed3D im2col (lib/video_swin_transformer.py:616-628): pixels x[b,c,t,h,w] fp32 addressed through element
+ * strides (stride_b, stride_c, stride_t; rows of W contiguous floats), so both the backbone's (B,3,T,H,W) input and
+ * LAVTVideo's un-permuted (B,T,3,H,W) input (lib/_utils.py:97) are read in place ->
+ * (B*T*ceil(H/4)*ceil(W/4), 64) bf16 rows, column = c*16 + ph*4 + pw, columns 48..63 zero (GEMM K = 64). */
+int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, int64_t stride_t, int32_t B, int32_t T,
+                            int32_t H, int32_t W, void* out_bf16, void* stream);
+
+/* ---- window attention core (lib/video_swin_transformer.py:147-165) ----
+ * qkv: bf16 [B*nW*N, 3C] in window order, q already scaled by head_dim^-0.5; table: fp32 [L, nH]
+ * (relative_position_bias_table); out: bf16 [B*nW*N, C].  head_dim must be 32. */
+int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
+                          void* out_bf16, void* stream);
+
+/* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */
+/* InstanceNorm1d statistics over the n tokens of each clip: x bf16 [B,n,C] -> stats fp32 [B,2,C] = (mean, rstd). */
+int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C);
+int lavt_instnorm_stats(const void* x_bf16, int32_t B, int64_t n, int32_t C, float eps, float* stats,
+                        float* workspace, void* stream);
+/* k, v = (W l + b) * l_mask : l fp32 [B,Lin,Nl], mask fp32 [B,Nl], weights fp32 [C,Lin] -> k, v fp32 [B,Nl,C] */
+int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
+                 float* k, float* v, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream);
+/* o = softmax_words(C^-0.5 * IN(q_pre) k^T + (1e4 mask - 1e4)) v ; q_pre, o bf16 [B,n,C] */
+int lavt_pwam_attend(const void* qpre_bf16, const float* stats, const float* k, const float* v, const float* mask,
+                     void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream);
+/* out = vis * IN(lang_pre) (bf16 [B,n,C]) -- the A operand of project_mm */
+int lavt_pwam_mul_norm(const void* vis_bf16, const void* lang_bf16, const float* stats, void* out_bf16, int32_t B,
+                       int64_t n, int32_t C, void* stream);
+
+/* ---- decoder glue (lib/mask_predictor.py:56-99, lib/_utils.py:106) ---- */
+/* out NHWC bf16 [n,H,W,C1+C2] = cat[bilinear(prev [n,ph,pw,C1] -> HxW, align_corners=True), skip [n,H,W,C2]] */
+int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,
+                         void* out_bf16, int32_t n_img, int32_t H, int32_t W, void* stream);
+/* conv1_1: logits[pix, 0:2] = y[pix, :] . w[0:2, :] + b */
+int lavt_conv1x1_logits(const void* y_bf16, const float* w, const float* b, float* out, int64_t npix, int32_t C, void* stream);
+/* (n,h,w,2) fp32 -> (n,2,H,W) fp32 NCHW, bilinear align_corners=True */
+int lavt_upsample_logits(const float* in, float* out, int32_t n_img, int32_t h, int32_t w, int32_t H, int32_t W, void* stream);
+/* layout converters for the NCHW tensors of the reference's backbone / classifier API */
+int lavt_nhwc_to_nchw(const float* in, float* out, int32_t n_img, int32_t P, int32_t C, void* stream);
+int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32_t P, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,12 +77,28 @@ SIGNATURES = {
     "lavt_check_device": [],
     "lavt_gemm_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _EP, _vp],
     "lavt_conv3x3_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _EP, _vp],
+    "lavt_layernorm_rows": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp],
+    "lavt_layernorm_window_gather": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp],
+    "lavt_patch_merge_layernorm": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp],
+    "lavt_patch_embed_im2col": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "lavt_window_attention": [_vp, _vp, _i32, _i32, _WG, _vp, _vp],
+    "lavt_instnorm_stats": [_vp, _i32, _i64, _i32, _f32, _vp, _vp, _vp],
+    "lavt_pwam_kv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_pwam_attend": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
+    "lavt_pwam_mul_norm": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "lavt_upsample_concat": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp],
+    "lavt_conv1x1_logits": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "lavt_upsample_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_nhwc_to_nchw": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "lavt_nchw_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _vp],
 }
-EXPORTS = ["lavt_last_error", "lavt_abi_version", *SIGNATURES.keys()]
+EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", *SIGNATURES.keys()]
 
 
 def _declare(l: C.CDLL) -> None:
     l.lavt_abi_version.restype = C.c_int
+    l.lavt_instnorm_workspace_floats.argtypes = [_i32, _i64, _i32]
+    l.lavt_instnorm_workspace_floats.restype = C.c_int64
     for name, argtypes in SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = argtypes
@@ -162,3 +178,156 @@ def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
     e = make_epilogue(**epi)
     check(lib().lavt_conv3x3_bf16(x_nhwc.data_ptr(), Cin, n_img, H, W, Cin, w_taps.data_ptr(), Cout,
                                   C.byref(e), stream_ptr()), "lavt_conv3x3_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------
+def _c(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    _req(t, dtype, name)
+    if not t.is_contiguous():
+        raise LavtError(f"{name} must be contiguous")
+    return t
+
+
+def layernorm_rows(x: torch.Tensor, gamma, beta, *, out_bf16=None, out_f32=None, eps: float = 1e-5) -> None:
+    """x fp32 [M, C] (row pitch x.stride(0))."""
+    _req(x, torch.float32, "x")
+    M, Cn = x.shape
+    for t, dt, nm in ((out_bf16, torch.bfloat16, "out_bf16"), (out_f32, torch.float32, "out_f32")):
+        if t is not None:
+            _c(t, dt, nm)
+    check(lib().lavt_layernorm_rows(x.data_ptr(), x.stride(0), M, Cn, _c(gamma, torch.float32, "gamma").data_ptr(),
+                                    _c(beta, torch.float32, "beta").data_ptr(), eps, ptr(out_bf16), ptr(out_f32),
+                                    stream_ptr()), "lavt_layernorm_rows")
+
+
+def layernorm_window_gather(x: torch.Tensor, geom: WinGeom, gamma, beta, out_bf16: torch.Tensor, eps: float = 1e-5) -> None:
+    """x fp32 [(B*D*H*W), C] contiguous -> out bf16 [geom.rows(), C] in window order."""
+    _c(x, torch.float32, "x")
+    Cn = x.shape[-1]
+    if x.numel() != geom.tokens() * Cn or out_bf16.numel() != geom.rows() * Cn:
+        raise LavtError("window gather: tensor sizes do not match the geometry")
+    check(lib().lavt_layernorm_window_gather(x.data_ptr(), Cn, C.byref(geom), _c(gamma, torch.float32, "gamma").data_ptr(),
+                                             _c(beta, torch.float32, "beta").data_ptr(), eps,
+                                             _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+          "lavt_layernorm_window_gather")
+
+
+def patch_merge_layernorm(x: torch.Tensor, B, D, H, W, gamma, beta, out_bf16: torch.Tensor, eps: float = 1e-5) -> None:
+    _c(x, torch.float32, "x")
+    Cn = x.shape[-1]
+    check(lib().lavt_patch_merge_layernorm(x.data_ptr(), B, D, H, W, Cn, _c(gamma, torch.float32, "gamma").data_ptr(),
+                                           _c(beta, torch.float32, "beta").data_ptr(), eps,
+                                           _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+          "lavt_patch_merge_layernorm")
+
+
+def patch_embed_im2col(x: torch.Tensor, out_bf16: torch.Tensor) -> None:
+    """x fp32 (B,3,T,H,W), any batch/channel/time strides as long as each (H,W) plane is contiguous."""
+    _req(x, torch.float32, "x")
+    B, Cin, T, H, W = x.shape
+    if Cin != 3:
+        raise LavtError("patch embed expects 3 input channels")
+    if x.stride(3) != W:
+        raise LavtError("patch embed: image planes must be contiguous")
+    check(lib().lavt_patch_embed_im2col(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, T, H, W,
+                                        _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+          "lavt_patch_embed_im2col")
+
+
+def window_attention(qkv: torch.Tensor, table: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor) -> None:
+    _c(qkv, torch.bfloat16, "qkv")
+    _c(table, torch.float32, "table")
+    L, nH = table.shape
+    check(lib().lavt_window_attention(qkv.data_ptr(), table.data_ptr(), L, nH, C.byref(geom),
+                                      _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+          "lavt_window_attention")
+
+
+def instnorm_workspace_floats(B: int, n: int, Cn: int) -> int:
+    return int(lib().lavt_instnorm_workspace_floats(B, n, Cn))
+
+
+def instnorm_stats(x: torch.Tensor, stats: torch.Tensor, workspace: torch.Tensor, eps: float = 1e-5) -> None:
+    """x bf16 [B,n,C] -> stats fp32 [B,2,C] (mean, rstd)."""
+    _c(x, torch.bfloat16, "x")
+    B, n, Cn = x.shape
+    if workspace.numel() < instnorm_workspace_floats(B, n, Cn):
+        raise LavtError("instnorm_stats: workspace too small")
+    check(lib().lavt_instnorm_stats(x.data_ptr(), B, n, Cn, eps, _c(stats, torch.float32, "stats").data_ptr(),
+                                    _c(workspace, torch.float32, "workspace").data_ptr(), stream_ptr()),
+          "lavt_instnorm_stats")
+
+
+def pwam_kv(l, mask, wk, bk, wv, bv, k, v) -> None:
+    """l fp32 [B,Lin,Nl]; mask fp32 [B,Nl]; wk/wv fp32 [C,Lin]; k,v fp32 [B,Nl,C]."""
+    B, Lin, Nl = l.shape
+    Cn = wk.shape[0]
+    for t, nm in ((l, "l"), (mask, "mask"), (wk, "wk"), (bk, "bk"), (wv, "wv"), (bv, "bv"), (k, "k"), (v, "v")):
+        _c(t, torch.float32, nm)
+    check(lib().lavt_pwam_kv(l.data_ptr(), mask.data_ptr(), wk.data_ptr(), bk.data_ptr(), wv.data_ptr(), bv.data_ptr(),
+                             k.data_ptr(), v.data_ptr(), B, Nl, Lin, Cn, stream_ptr()), "lavt_pwam_kv")
+
+
+def pwam_attend(qpre, stats, k, v, mask, out, heads: int) -> None:
+    _c(qpre, torch.bfloat16, "qpre")
+    B, n, Cn = qpre.shape
+    Nl = k.shape[1]
+    check(lib().lavt_pwam_attend(qpre.data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                 _c(k, torch.float32, "k").data_ptr(), _c(v, torch.float32, "v").data_ptr(),
+                                 _c(mask, torch.float32, "mask").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
+                                 B, n, Cn, Nl, heads, stream_ptr()), "lavt_pwam_attend")
+
+
+def pwam_mul_norm(vis, lang, stats, out) -> None:
+    _c(vis, torch.bfloat16, "vis")
+    B, n, Cn = vis.shape
+    check(lib().lavt_pwam_mul_norm(vis.data_ptr(), _c(lang, torch.bfloat16, "lang").data_ptr(),
+                                   _c(stats, torch.float32, "stats").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
+                                   B, n, Cn, stream_ptr()), "lavt_pwam_mul_norm")
+
+
+def upsample_concat(prev, skip, out) -> None:
+    """prev bf16 [n,ph,pw,C1], skip bf16 [n,H,W,C2] -> out bf16 [n,H,W,C1+C2]."""
+    _c(prev, torch.bfloat16, "prev")
+    _c(skip, torch.bfloat16, "skip")
+    n, ph, pw, C1 = prev.shape
+    n2, H, W, C2 = skip.shape
+    if n != n2 or tuple(out.shape) != (n, H, W, C1 + C2):
+        raise LavtError("upsample_concat: shape mismatch")
+    check(lib().lavt_upsample_concat(prev.data_ptr(), ph, pw, C1, skip.data_ptr(), C2,
+                                     _c(out, torch.bfloat16, "out").data_ptr(), n, H, W, stream_ptr()),
+          "lavt_upsample_concat")
+
+
+def conv1x1_logits(y, w, b, out) -> None:
+    """y bf16 [npix, C]; w fp32 [2, C]; b fp32 [2]; out fp32 [npix, 2]."""
+    _c(y, torch.bfloat16, "y")
+    npix, Cn = y.shape
+    check(lib().lavt_conv1x1_logits(y.data_ptr(), _c(w, torch.float32, "w").data_ptr(), _c(b, torch.float32, "b").data_ptr(),
+                                    _c(out, torch.float32, "out").data_ptr(), npix, Cn, stream_ptr()), "lavt_conv1x1_logits")
+
+
+def upsample_logits(inp, out) -> None:
+    """inp fp32 [n,h,w,2] -> out fp32 [n,2,H,W]."""
+    n, h, w, two = inp.shape
+    n2, two2, H, W = out.shape
+    if two != 2 or two2 != 2 or n != n2:
+        raise LavtError("upsample_logits: shape mismatch")
+    check(lib().lavt_upsample_logits(_c(inp, torch.float32, "in").data_ptr(), _c(out, torch.float32, "out").data_ptr(),
+                                     n, h, w, H, W, stream_ptr()), "lavt_upsample_logits")
+
+
+def nhwc_to_nchw(inp, out) -> None:
+    """inp fp32 [n,P,C] -> out fp32 [n,C,P]."""
+    n, P, Cn = inp.shape
+    check(lib().lavt_nhwc_to_nchw(_c(inp, torch.float32, "in").data_ptr(), _c(out, torch.float32, "out").data_ptr(),
+                                  n, P, Cn, stream_ptr()), "lavt_nhwc_to_nchw")
+
+
+def nchw_to_nhwc_bf16(inp, out) -> None:
+    """inp fp32 [n,C,P] -> out bf16 [n,P,C]."""
+    n, Cn, P = inp.shape
+    check(lib().lavt_nchw_to_nhwc_bf16(_c(inp, torch.float32, "in").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
+                                       n, P, Cn, stream_ptr()), "lavt_nchw_to_nhwc_bf16")

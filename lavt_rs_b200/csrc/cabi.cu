@@ -2,6 +2,7 @@
 #include "../../include/lavt_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "kernels.cuh"
 
 #include <cstring>
 
@@ -90,6 +91,98 @@ int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H,
   p.cTilesW = (W + p.cTW - 1) / p.cTW;
   p.cTilesH = (H + p.cTH - 1) / p.cTH;
   return gemm_dispatch(x_nhwc, ldx, Wt, 9LL * Cin, p, static_cast<cudaStream_t>(stream));
+}
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static inline const __nv_bfloat16* CB(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
+static inline __nv_bfloat16* MB(void* p) { return static_cast<__nv_bfloat16*>(p); }
+
+int lavt_layernorm_rows(const float* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
+                        float eps, void* out_bf16, float* out_f32, void* stream) {
+  LnParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = ldx; p.gamma = gamma; p.beta = beta; p.out_bf16 = MB(out_bf16); p.out_f32 = out_f32;
+  p.M = M; p.C = C; p.eps = eps;
+  return ln_rows_dispatch(MODE_IDENTITY, p, S(stream));
+}
+
+int lavt_layernorm_window_gather(const float* x, int32_t C, const lavt_win_geom_t* geom, const float* gamma,
+                                 const float* beta, float eps, void* out_bf16, void* stream) {
+  LAVT_REQUIRE(geom != nullptr, "window gather: geometry is NULL");
+  LnParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.x = x; p.ldx = C; p.gamma = gamma; p.beta = beta; p.out_bf16 = MB(out_bf16);
+  p.M = 1LL * geom->B * geom->nwd * geom->nwh * geom->nww * geom->N; p.C = C; p.eps = eps;
+  return ln_rows_dispatch(MODE_WINDOW, p, S(stream));
+}
+
+int lavt_patch_merge_layernorm(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C,
+                               const float* gamma, const float* beta, float eps, void* out_bf16, void* stream) {
+  LnParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = C; p.gamma = gamma; p.beta = beta; p.out_bf16 = MB(out_bf16);
+  p.M = 1LL * B * D * ((H + 1) / 2) * ((W + 1) / 2); p.C = C; p.eps = eps;
+  p.mB = B; p.mD = D; p.mH = H; p.mW = W;
+  return ln_rows_dispatch(MODE_MERGE, p, S(stream));
+}
+
+int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, int64_t stride_t, int32_t B, int32_t T,
+                            int32_t H, int32_t W, void* out_bf16, void* stream) {
+  return im2col_patch4_dispatch(x, stride_b, stride_c, stride_t, MB(out_bf16), B, T, H, W, S(stream));
+}
+
+int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
+                          void* out_bf16, void* stream) {
+  LAVT_REQUIRE(geom != nullptr, "attention: geometry is NULL");
+  AttnParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.qkv = CB(qkv); p.table = table; p.out = MB(out_bf16); p.nH = nH; p.C = nH * 32; p.L = L;
+  return window_attn_dispatch(p, S(stream));
+}
+
+int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C) { return colstats_workspace_floats(B, n, C); }
+
+int lavt_instnorm_stats(const void* x_bf16, int32_t B, int64_t n, int32_t C, float eps, float* stats, float* workspace,
+                        void* stream) {
+  return colstats_dispatch(CB(x_bf16), stats, workspace, B, n, C, eps, S(stream));
+}
+
+int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
+                 float* k, float* v, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream) {
+  return pwam_kv_dispatch(l, mask, wk, bk, wv, bv, k, v, B, Nl, Lin, C, S(stream));
+}
+
+int lavt_pwam_attend(const void* qpre_bf16, const float* stats, const float* k, const float* v, const float* mask,
+                     void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream) {
+  return pwam_core_dispatch(CB(qpre_bf16), stats, k, v, mask, MB(o_bf16), B, n, C, Nl, heads, S(stream));
+}
+
+int lavt_pwam_mul_norm(const void* vis_bf16, const void* lang_bf16, const float* stats, void* out_bf16, int32_t B,
+                       int64_t n, int32_t C, void* stream) {
+  return pwam_mul_dispatch(CB(vis_bf16), CB(lang_bf16), stats, MB(out_bf16), B, n, C, S(stream));
+}
+
+int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,
+                         void* out_bf16, int32_t n_img, int32_t H, int32_t W, void* stream) {
+  return upsample_concat_dispatch(CB(prev_bf16), ph, pw, C1, CB(skip_bf16), C2, MB(out_bf16), n_img, H, W, S(stream));
+}
+
+int lavt_conv1x1_logits(const void* y_bf16, const float* w, const float* b, float* out, int64_t npix, int32_t C, void* stream) {
+  return conv1x1_logits_dispatch(CB(y_bf16), w, b, out, npix, C, S(stream));
+}
+
+int lavt_upsample_logits(const float* in, float* out, int32_t n_img, int32_t h, int32_t w, int32_t H, int32_t W, void* stream) {
+  return upsample_logits_dispatch(in, out, n_img, h, w, H, W, S(stream));
+}
+
+int lavt_nhwc_to_nchw(const float* in, float* out, int32_t n_img, int32_t P, int32_t C, void* stream) {
+  return nhwc_to_nchw_dispatch(in, out, n_img, P, C, S(stream));
+}
+
+int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32_t P, int32_t C, void* stream) {
+  return nchw_to_nhwc_bf16_dispatch(in, MB(out_bf16), n_img, P, C, S(stream));
 }
 
 }  // extern "C"

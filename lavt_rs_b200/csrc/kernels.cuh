@@ -1,0 +1,53 @@
+// Internal dispatch entry points (one per kernel family); called from cabi.cu.
+#pragma once
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace lavt {
+
+enum { MODE_IDENTITY = 0, MODE_WINDOW = 1, MODE_MERGE = 2 };
+
+struct LnParams {
+  const float* x;            // source rows, fp32, pitch ldx
+  long long ldx;
+  const float* gamma;        // [Cn]
+  const float* beta;         // [Cn]
+  __nv_bfloat16* out_bf16;   // [M, Cn] or nullptr
+  float* out_f32;            // [M, Cn] or nullptr
+  long long M;               // output rows
+  int C;                     // source channels per token
+  float eps;
+  WinGeom win;               // MODE_WINDOW
+  int mB, mD, mH, mW;        // MODE_MERGE: source grid (B,D,H,W)
+};
+int ln_rows_dispatch(int mode, const LnParams& p, cudaStream_t st);
+int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long sT, __nv_bfloat16* out, int B, int T, int H,
+                           int W, cudaStream_t st);
+long long colstats_workspace_floats(int B, long long n, int C);
+int colstats_dispatch(const __nv_bfloat16* x, float* stats, float* workspace, int B, long long n, int C, float eps, cudaStream_t st);
+int pwam_mul_dispatch(const __nv_bfloat16* vis, const __nv_bfloat16* lang, const float* stats, __nv_bfloat16* out, int B,
+                      long long n, int C, cudaStream_t st);
+
+struct AttnParams {
+  const __nv_bfloat16* qkv;   // [rows, 3C]: q | k | v, each [nH][32]
+  const float* table;         // [L, nH] relative_position_bias_table
+  __nv_bfloat16* out;         // [rows, C]
+  int C, nH, L;
+  WinGeom win;
+};
+int window_attn_dispatch(const AttnParams& p, cudaStream_t st);
+
+int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
+                     float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);
+int pwam_core_dispatch(const __nv_bfloat16* qpre, const float* stats, const float* k, const float* v, const float* mask,
+                       __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st);
+
+int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,
+                             __nv_bfloat16* out, int n_img, int H, int W, cudaStream_t st);
+int conv1x1_logits_dispatch(const __nv_bfloat16* y, const float* w, const float* b, float* out, long long npix, int C,
+                            cudaStream_t st);
+int upsample_logits_dispatch(const float* in, float* out, int n_img, int h, int w, int H, int W, cudaStream_t st);
+int nhwc_to_nchw_dispatch(const float* in, float* out, int n_img, int P, int C, cudaStream_t st);
+int nchw_to_nhwc_bf16_dispatch(const float* in, __nv_bfloat16* out, int n_img, int P, int C, cudaStream_t st);
+
+}  // namespace lavt

@@ -1,0 +1,307 @@
+// Bandwidth-bound row kernels: LayerNorm fused with the gathers that feed the GEMMs.
+//
+//   ln_rows<MODE>      one warp per OUTPUT row, fp32 in, two-pass statistics in registers, bf16 (and/or fp32) out
+//     MODE_IDENTITY    LN2 before the MLP (reference lib/video_swin_transformer.py:250), patch_embed.norm (:630),
+//                      per-stage output norm (:871)
+//     MODE_WINDOW      LN1 + pad + cyclic shift + window_partition as ONE gather (:218-234); pad rows -> 0
+//     MODE_MERGE       PatchMerging 2x2 gather + LN(4C) (:302-308); odd H/W padded with zeros BEFORE the norm
+//   im2col_patch4      (B,3,T,H,W) fp32 -> (tokens, 64) bf16 rows for the patch-embed GEMM (K = 3*4*4 = 48, zero padded)
+//   colstats_*         InstanceNorm1d statistics over all tokens of a clip (PWAM, :959-962, :970-973)
+//   pwam_mul           vis * InstanceNorm(lang_pre)  -> bf16 A operand of project_mm (:929-930)
+#include "kernels.cuh"
+
+namespace lavt {
+
+// NV = float4 per lane: Cn = NV * 128
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long m = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= p.M) return;
+  constexpr int Cn = NV * 128;
+  float4 v[NV];
+
+  if (MODE == MODE_MERGE) {
+    // out row m <-> (b, d, h2, w2); channel block q of 4 <-> source pixel (2*h2 + (q&1), 2*w2 + (q>>1))
+    const int H2 = (p.mH + 1) >> 1, W2 = (p.mW + 1) >> 1;
+    const int w2 = static_cast<int>(m % W2);
+    const int h2 = static_cast<int>((m / W2) % H2);
+    const long long bd = m / (static_cast<long long>(W2) * H2);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;           // column in [0, 4C)
+      const int q = col / p.C, c = col - q * p.C;
+      const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
+      if (h < p.mH && w < p.mW) {
+        const float* src = p.x + ((bd * p.mH + h) * p.mW + w) * p.ldx + c;
+        v[i] = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  } else {
+    long long row = m;
+    if (MODE == MODE_WINDOW) row = win_token(p.win, m).row;
+    if (row < 0) {   // pad row: zeros AFTER the norm (F.pad follows norm1 in the reference)
+      if (p.out_bf16) {
+        uint2* o = reinterpret_cast<uint2*>(p.out_bf16 + m * Cn);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i * 32 + lane] = make_uint2(0u, 0u);
+      }
+      if (p.out_f32) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + m * Cn);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      return;
+    }
+    const float4* src = reinterpret_cast<const float4*>(p.x + row * p.ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __ldg(src + i * 32 + lane);
+  }
+
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / Cn);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / Cn) + p.eps);
+
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (p.out_bf16)
+      reinterpret_cast<uint2*>(p.out_bf16 + m * Cn)[i * 32 + lane] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    if (p.out_f32) reinterpret_cast<float4*>(p.out_f32 + m * Cn)[i * 32 + lane] = y;
+  }
+}
+
+template <int MODE>
+static int launch_ln(const LnParams& p, int Cn, cudaStream_t st) {
+  const int warps = 8;
+  const long long blocks = (p.M + warps - 1) / warps;
+  LAVT_REQUIRE(blocks < (1LL << 31), "layernorm: too many rows");
+  dim3 grid(static_cast<unsigned>(blocks));
+  switch (Cn / 128) {
+    case 1: ln_rows_kernel<MODE, 1><<<grid, 256, 0, st>>>(p); break;
+    case 2: ln_rows_kernel<MODE, 2><<<grid, 256, 0, st>>>(p); break;
+    case 3: ln_rows_kernel<MODE, 3><<<grid, 256, 0, st>>>(p); break;
+    case 4: ln_rows_kernel<MODE, 4><<<grid, 256, 0, st>>>(p); break;
+    case 6: ln_rows_kernel<MODE, 6><<<grid, 256, 0, st>>>(p); break;
+    case 8: ln_rows_kernel<MODE, 8><<<grid, 256, 0, st>>>(p); break;
+    case 12: ln_rows_kernel<MODE, 12><<<grid, 256, 0, st>>>(p); break;
+    case 16: ln_rows_kernel<MODE, 16><<<grid, 256, 0, st>>>(p); break;
+    case 24: ln_rows_kernel<MODE, 24><<<grid, 256, 0, st>>>(p); break;
+    default:
+      set_last_error("layernorm: normalised width %d not supported (need 128 * {1,2,3,4,6,8,12,16,24})", Cn);
+      return LAVT_ERR_SHAPE;
+  }
+  LAVT_LAUNCH_CHECK("ln_rows_kernel");
+  return LAVT_OK;
+}
+
+int ln_rows_dispatch(int mode, const LnParams& p, cudaStream_t st) {
+  LAVT_REQUIRE(p.M > 0, "layernorm: empty input");
+  LAVT_REQUIRE(p.out_bf16 || p.out_f32, "layernorm: no output");
+  LAVT_REQUIRE(p.ldx % 4 == 0 && p.C % 4 == 0, "layernorm: pitch / channels must be multiples of 4");
+  const int Cn = (mode == MODE_MERGE) ? 4 * p.C : p.C;
+  LAVT_REQUIRE(Cn % 128 == 0, "layernorm: normalised width %d must be a multiple of 128", Cn);
+  if (mode == MODE_IDENTITY) return launch_ln<MODE_IDENTITY>(p, Cn, st);
+  if (mode == MODE_WINDOW) return launch_ln<MODE_WINDOW>(p, Cn, st);
+  if (mode == MODE_MERGE) return launch_ln<MODE_MERGE>(p, Cn, st);
+  set_last_error("layernorm: bad mode %d", mode);
+  return LAVT_ERR_SHAPE;
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch-embed im2col: x (B, 3, T, H, W) fp32  ->  rows (B*T*Hp*Wp, 64) bf16, col = c*16 + ph*4 + pw (48..63 = 0)
+// (Conv3d k = s = (1,4,4) == GEMM, reference lib/video_swin_transformer.py:616-628; right/bottom zero pad)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_patch4_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                            long long sB, long long sC, long long sT,
+                                                            int B, int T, int H, int W, int Hp, int Wp) {
+  // one thread per (token, c, ph): 4 consecutive pixels -> 4 bf16
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * T * Hp * Wp * 16;
+  if (idx >= total) return;
+  const int sub = static_cast<int>(idx & 15);
+  const long long tok = idx >> 4;
+  uint2 o = make_uint2(0u, 0u);
+  if (sub < 12) {
+    const int c = sub >> 2, ph = sub & 3;
+    const int wp = static_cast<int>(tok % Wp);
+    const int hp = static_cast<int>((tok / Wp) % Hp);
+    const int t = static_cast<int>((tok / (static_cast<long long>(Wp) * Hp)) % T);
+    const int b = static_cast<int>(tok / (static_cast<long long>(Wp) * Hp * T));
+    const int h = hp * 4 + ph;
+    if (h < H) {
+      const float* src = x + b * sB + c * sC + t * sT + static_cast<long long>(h) * W + wp * 4;
+      float f[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = (wp * 4 + j < W) ? __ldg(src + j) : 0.f;
+      o = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+    }
+  }
+  reinterpret_cast<uint2*>(out + tok * 64)[sub] = o;
+}
+
+int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long sT, __nv_bfloat16* out, int B, int T, int H,
+                           int W, cudaStream_t st) {
+  const int Hp = (H + 3) / 4, Wp = (W + 3) / 4;
+  const long long total = static_cast<long long>(B) * T * Hp * Wp * 16;
+  LAVT_REQUIRE(total > 0, "patch embed: empty input");
+  im2col_patch4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, out, sB, sC, sT, B, T, H, W, Hp, Wp);
+  LAVT_LAUNCH_CHECK("im2col_patch4_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm statistics per (clip, channel) over n tokens of a bf16 (B, n, C) tensor.
+// pass 1: per-chunk sums of (x - pivot) and (x - pivot)^2 (pivot = token 0 of the clip, kills the
+//         E[x^2]-E[x]^2 cancellation);  pass 2: deterministic reduction over chunks -> mean, rstd.
+// ---------------------------------------------------------------------------------------------
+constexpr int CS_ROWS_PER_BLOCK = 512;
+
+__global__ void __launch_bounds__(256) colstats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
+                                                               int n, int C, int chunks) {
+  // grid: (chunks, B).  thread -> 8 channels (one uint4); row groups stride over the chunk's rows
+  extern __shared__ float sm[];   // [rowgroups][C][2]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tpr = C / 8;                       // threads per row
+  const int rg = blockDim.x / tpr;             // row groups
+  const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  const __nv_bfloat16* base = x + static_cast<long long>(b) * n * C;
+  float pv[8], s1[8], s2[8];
+  {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(base) + tc);
+    float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    pv[0] = a.x; pv[1] = a.y; pv[2] = bb.x; pv[3] = bb.y; pv[4] = c.x; pv[5] = c.y; pv[6] = d.x; pv[7] = d.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int r0 = chunk * CS_ROWS_PER_BLOCK;
+  const int r1 = min(n, r0 + CS_ROWS_PER_BLOCK);
+  if (tr < rg) {
+    for (int r = r0 + tr; r < r1; r += rg) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C) + tc);
+      float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      float f[8] = {a.x, a.y, bb.x, bb.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = f[j] - pv[j];
+        s1[j] += t;
+        s2[j] += t * t;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[(tr * C + tc * 8 + j) * 2 + 0] = s1[j];
+      sm[(tr * C + tc * 8 + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < rg; ++g) {
+      a += sm[(g * C + c) * 2 + 0];
+      q += sm[(g * C + c) * 2 + 1];
+    }
+    float* o = part + ((static_cast<long long>(b) * chunks + chunk) * 2) * C;
+    o[c] = a;
+    o[C + c] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) colstats_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ part,
+                                                             float* __restrict__ stats, int n, int C, int chunks, float eps) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float pivot = __bfloat162float(x[static_cast<long long>(b) * n * C + c]);
+  double a = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* o = part + ((static_cast<long long>(b) * chunks + k) * 2) * C;
+    a += o[c];
+    q += o[C + c];
+  }
+  const double m1 = a / n;
+  const double var = fmax(q / n - m1 * m1, 0.0);
+  stats[(static_cast<long long>(b) * 2 + 0) * C + c] = pivot + static_cast<float>(m1);
+  stats[(static_cast<long long>(b) * 2 + 1) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+long long colstats_workspace_floats(int B, long long n, int C) {
+  const long long chunks = (n + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  return static_cast<long long>(B) * chunks * 2 * C;
+}
+
+int colstats_dispatch(const __nv_bfloat16* x, float* stats, float* workspace, int B, long long n_ll, int C, float eps, cudaStream_t st) {
+  LAVT_REQUIRE(n_ll < (1LL << 30), "instance-norm stats: too many tokens");
+  const int n = static_cast<int>(n_ll);
+  LAVT_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "instance-norm stats: C=%d unsupported", C);
+  LAVT_REQUIRE(B > 0 && n > 0, "instance-norm stats: empty input");
+  const int chunks = (n + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  const int tpr = C / 8;
+  LAVT_REQUIRE(tpr <= 256, "instance-norm stats: C too large");
+  const int rg = 256 / tpr;
+  const size_t smem = static_cast<size_t>(rg) * C * 2 * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    LAVT_CUDA(cudaFuncSetAttribute(colstats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  colstats_partial_kernel<<<dim3(chunks, B), 256, smem, st>>>(x, workspace, n, C, chunks);
+  LAVT_LAUNCH_CHECK("colstats_partial_kernel");
+  colstats_final_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(x, workspace, stats, n, C, chunks, eps);
+  LAVT_LAUNCH_CHECK("colstats_final_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = vis * (lang_pre - mean) * rstd   (bf16 in / out, stats fp32 (B,2,C))
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pwam_mul_kernel(const __nv_bfloat16* __restrict__ vis, const __nv_bfloat16* __restrict__ lang,
+                                                       const float* __restrict__ stats, __nv_bfloat16* __restrict__ out,
+                                                       long long n, int C, long long total8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = static_cast<int>(i % (C / 8));
+  const long long row = i / (C / 8);
+  const int b = static_cast<int>(row / n);
+  const float* mu = stats + (static_cast<long long>(b) * 2) * C + c8 * 8;
+  const float* rs = mu + C;
+  const uint4 uv = __ldg(reinterpret_cast<const uint4*>(vis) + i);
+  const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lang) + i);
+  const uint32_t vv[4] = {uv.x, uv.y, uv.z, uv.w}, ll[4] = {ul.x, ul.y, ul.z, ul.w};
+  uint32_t oo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_bf16x2(vv[j]), l = unpack_bf16x2(ll[j]);
+    oo[j] = pack_bf16x2(a.x * (l.x - mu[2 * j]) * rs[2 * j], a.y * (l.y - mu[2 * j + 1]) * rs[2 * j + 1]);
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+}
+
+int pwam_mul_dispatch(const __nv_bfloat16* vis, const __nv_bfloat16* lang, const float* stats, __nv_bfloat16* out, int B,
+                      long long n, int C, cudaStream_t st) {
+  LAVT_REQUIRE(C % 8 == 0, "pwam_mul: C must be a multiple of 8");
+  const long long total8 = static_cast<long long>(B) * n * (C / 8);
+  LAVT_REQUIRE(total8 > 0, "pwam_mul: empty input");
+  pwam_mul_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, st>>>(vis, lang, stats, out, n, C, total8);
+  LAVT_LAUNCH_CHECK("pwam_mul_kernel");
+  return LAVT_OK;
+}
+
+}  // namespace lavt

@@ -1,0 +1,296 @@
+"""Host-side execution engine: sequences the sm_100a kernels for each reference function.
+
+Layout in HBM
+  * residual stream  x : fp32 [B*D*H*W, C] channels-last (the reference's (B,D,H,W,C) view)
+  * GEMM operands      : bf16 rows (tokens x C), produced by the LN / gather / epilogue kernels
+  * weights            : bf16 [out, in] copies of the fp32 parameters (``PreparedWeights``), refreshed
+                         whenever a parameter's version counter changes
+Scratch buffers come from a per-device ``Workspace`` so that a steady-state forward performs no
+allocations (required for CUDA-graph capture in bench.py).
+
+No reference code path is used here; each function cites the reference function it replaces.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi as K
+from .geometry import window_geometry
+
+LAUNCHES = 0  # number of our kernel launches issued (bench.py reports it)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class Workspace:
+    """Named scratch buffers, grown on demand and reused across calls (one per device / stream user)."""
+
+    def __init__(self):
+        self._bufs: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        key = (name, dtype)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < numel or buf.device != torch.device(device):
+            buf = torch.empty(max(numel, 1), dtype=dtype, device=device)
+            self._bufs[key] = buf
+        return buf[:numel].view(*shape)
+
+    def bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._bufs.values())
+
+
+_WORKSPACES: Dict[Tuple[int, str], Workspace] = {}
+
+
+def workspace(device, tag: str = "main") -> Workspace:
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), tag)
+    if key not in _WORKSPACES:
+        _WORKSPACES[key] = Workspace()
+    return _WORKSPACES[key]
+
+
+class PreparedWeights:
+    """bf16 / folded copies of a module's parameters, rebuilt when any source tensor changes."""
+
+    def __init__(self):
+        self._cache: Dict[str, Tuple[tuple, object]] = {}
+
+    def get(self, key: str, sources: Sequence[torch.Tensor], build):
+        ver = tuple((t.data_ptr(), t._version, t.device) for t in sources)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self._cache[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._cache.clear()
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise K.LavtError(f"{what} must live on a CUDA device: the B200 path has no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin block  (reference SwinTransformerBlock3D.forward, lib/video_swin_transformer.py:253-273)
+# ------------------------------------------------------------------------------------------------
+def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shifted: bool, clamp: bool,
+               ws: Workspace, xb_out: Optional[torch.Tensor] = None) -> None:
+    """In place on the fp32 residual stream x [B*D*H*W, C].  ``blk`` is a host SwinTransformerBlock3D.
+    If ``xb_out`` is given the final value of x is also written there in bf16 (feeds PWAM's GEMMs)."""
+    n, C = x.shape
+    dev = x.device
+    geom = window_geometry(B, D, H, W, window, shifted, clamp)
+    rows = geom.rows()
+    nH = blk.num_heads
+    pw = blk.prepared
+    hd = C // nH
+
+    qkv_w = pw.get("qkv_w", [blk.attn.qkv.weight], lambda: _bf16(blk.attn.qkv.weight))
+    # q columns are scaled by head_dim^-0.5 in the epilogue: (acc + b) * s == acc * s + b * s  (:147)
+    def _qscale():
+        s = torch.ones(3 * C, device=dev, dtype=torch.float32)
+        s[:C] = hd ** -0.5
+        b = _f32(blk.attn.qkv.bias) * s if blk.attn.qkv.bias is not None else torch.zeros(3 * C, device=dev)
+        return s, b
+    qkv_s, qkv_b = pw.get("qkv_sb", [blk.attn.qkv.weight] + ([blk.attn.qkv.bias] if blk.attn.qkv.bias is not None else []), _qscale)
+    proj_w = pw.get("proj_w", [blk.attn.proj.weight], lambda: _bf16(blk.attn.proj.weight))
+    fc1_w = pw.get("fc1_w", [blk.mlp.fc1.weight], lambda: _bf16(blk.mlp.fc1.weight))
+    fc2_w = pw.get("fc2_w", [blk.mlp.fc2.weight], lambda: _bf16(blk.mlp.fc2.weight))
+    table = blk.attn.relative_position_bias_table
+
+    # --- attention half: LN1 + shift + partition gather -> qkv GEMM -> window attention -> proj GEMM + scatter + residual
+    xw = ws.get("xw", (rows, C), torch.bfloat16, dev)
+    K.layernorm_window_gather(x, geom, blk.norm1.weight, blk.norm1.bias, xw, eps=blk.norm1.eps)
+    qkv = ws.get("qkv", (rows, 3 * C), torch.bfloat16, dev)
+    K.gemm_bf16(xw, qkv_w, cscale=qkv_s, bias=qkv_b, out_bf16=qkv)
+    att = ws.get("att", (rows, C), torch.bfloat16, dev)
+    K.window_attention(qkv, table.detach(), geom, att)
+    K.gemm_bf16(att, proj_w, bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x, win=geom)
+    # --- MLP half: LN2 -> fc1 + GELU -> fc2 + residual
+    h1 = ws.get("ln2", (n, C), torch.bfloat16, dev)
+    K.layernorm_rows(x, blk.norm2.weight, blk.norm2.bias, out_bf16=h1, eps=blk.norm2.eps)
+    hid = ws.get("hid", (n, fc1_w.shape[0]), torch.bfloat16, dev)
+    K.gemm_bf16(h1, fc1_w, bias=blk.mlp.fc1.bias.detach(), act=K.ACT_GELU, out_bf16=hid)
+    K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x, out_f32=x, out_bf16=xb_out)
+    _count(7)
+
+
+# ------------------------------------------------------------------------------------------------
+# PWAM + LanguageGate  (reference PWAM.forward :919-934, SpatialImageLanguageAttention.forward :975-1009,
+# res_gate :519-525 applied at :570)
+# ------------------------------------------------------------------------------------------------
+def _conv1x1_w(conv) -> torch.Tensor:
+    return conv.weight[:, :, 0]
+
+
+def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int,
+              ws: Workspace, gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 [B*n, C] (updated in place with the gated residual), xb = bf16 copy of x, l fp32 [B,768,Nl],
+    mask fp32 [B,Nl].  Returns r (= x_residual) as fp32 [B*n, C]."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    att = fusion.image_lang_att
+    heads = att.num_heads
+    Nl = l.shape[-1]
+
+    def wprep(name, conv):
+        return pw.get(name, [conv.weight], lambda: _bf16(_conv1x1_w(conv)))
+
+    vis_w = wprep("vis_w", fusion.vis_project[0])
+    q_w = wprep("q_w", att.f_query[0])
+    W_w = wprep("W_w", att.W[0])
+    mm_w = wprep("mm_w", fusion.project_mm[0])
+    k_w = pw.get("k_w", [att.f_key[0].weight], lambda: _f32(_conv1x1_w(att.f_key[0])))
+    v_w = pw.get("v_w", [att.f_value[0].weight], lambda: _f32(_conv1x1_w(att.f_value[0])))
+
+    vis = ws.get("pw_vis", (B, n, C), torch.bfloat16, dev)
+    K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C))
+    qpre = ws.get("pw_q", (B, n, C), torch.bfloat16, dev)
+    K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_bf16=qpre.view(N_, C))
+    stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), torch.float32, dev)
+    K.instnorm_stats(qpre, stats, stw)
+    kk = ws.get("pw_k", (B, Nl, C), torch.float32, dev)
+    vv = ws.get("pw_v", (B, Nl, C), torch.float32, dev)
+    K.pwam_kv(l, mask, k_w, att.f_key[0].bias.detach(), v_w, att.f_value[0].bias.detach(), kk, vv)
+    o = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
+    K.pwam_attend(qpre, stats, kk, vv, mask, o, heads)
+    lang = qpre  # q_pre is dead: reuse its buffer for lang_pre
+    K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_bf16=lang.view(N_, C))
+    K.instnorm_stats(lang, stats, stw)
+    a2 = o  # o is dead after the W projection
+    K.pwam_mul_norm(vis, lang, stats, a2)
+    r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+    rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+    K.gemm_bf16(a2.view(N_, C), mm_w, bias=fusion.project_mm[0].bias.detach(), act=K.ACT_GELU, out_f32=r32, out_bf16=rb)
+    _count(11)
+    if res_gate is not None:
+        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1 = vis.view(N_, C)  # vis is dead
+        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
+        if gate_act != "tanh":
+            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+        _count(2)
+    return r32
+
+
+# ------------------------------------------------------------------------------------------------
+# PatchMerging (reference :289-311) and PatchEmbed3D (:616-634)
+# ------------------------------------------------------------------------------------------------
+def patch_merging(x: torch.Tensor, ds, B: int, D: int, H: int, W: int, ws: Workspace, out: torch.Tensor) -> None:
+    """x fp32 [B*D*H*W, C] -> out fp32 [B*D*ceil(H/2)*ceil(W/2), 2C]."""
+    C = x.shape[1]
+    dev = x.device
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    red_w = ds.prepared.get("red_w", [ds.reduction.weight], lambda: _bf16(ds.reduction.weight))
+    g = ws.get("merge", (B * D * H2 * W2, 4 * C), torch.bfloat16, dev)
+    K.patch_merge_layernorm(x, B, D, H, W, ds.norm.weight, ds.norm.bias, g, eps=ds.norm.eps)
+    K.gemm_bf16(g, red_w, out_f32=out)
+    _count(2)
+
+
+def patch_embed(x5: torch.Tensor, pe, ws: Workspace, out: torch.Tensor) -> Tuple[int, int]:
+    """x5 fp32 (B,3,T,H,W) strided view; out fp32 [B*T*Hp*Wp, C].  Returns (Hp, Wp)."""
+    B, _, T, H, W = x5.shape
+    dev = x5.device
+    Hp, Wp = (H + 3) // 4, (W + 3) // 4
+    C = pe.embed_dim
+
+    def _w():
+        w = pe.proj.weight.detach().reshape(C, -1).to(torch.bfloat16)     # [C, 48], col = c*16 + ph*4 + pw
+        wp = torch.zeros(C, 64, device=w.device, dtype=torch.bfloat16)
+        wp[:, : w.shape[1]] = w
+        return wp
+    pw_ = pe.prepared.get("w", [pe.proj.weight], _w)
+    cols = ws.get("pe_cols", (B * T * Hp * Wp, 64), torch.bfloat16, dev)
+    K.patch_embed_im2col(x5, cols)
+    if pe.norm is not None:
+        K.gemm_bf16(cols, pw_, bias=pe.proj.bias.detach(), out_f32=out)
+        K.layernorm_rows(out, pe.norm.weight, pe.norm.bias, out_f32=out, eps=pe.norm.eps)   # row-wise, safe in place
+        _count(3)
+    else:
+        K.gemm_bf16(cols, pw_, bias=pe.proj.bias.detach(), out_f32=out)
+        _count(2)
+    return Hp, Wp
+
+
+# ------------------------------------------------------------------------------------------------
+# SimpleDecoding (reference lib/mask_predictor.py:56-99) on NHWC bf16 feature maps
+# ------------------------------------------------------------------------------------------------
+def _bn_fold(bn):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return s.contiguous(), (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
+
+
+def _conv_taps(conv) -> torch.Tensor:
+    w = conv.weight.detach()                                    # [Cout, Cin, 3, 3]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()   # [(ky*3+kx)*Cin + ci]
+
+
+def _cbr(x_nhwc: torch.Tensor, dec, conv_name: str, bn_name: str, out: torch.Tensor) -> None:
+    conv, bn = getattr(dec, conv_name), getattr(dec, bn_name)
+    if bn.training:
+        raise K.LavtError("SimpleDecoding on the B200 path is inference-only (BatchNorm must be in eval mode)")
+    w = dec.prepared.get(conv_name, [conv.weight], lambda: _conv_taps(conv))
+    s, b = dec.prepared.get(bn_name, [bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: _bn_fold(bn))
+    K.conv3x3_bf16(x_nhwc, w, cscale=s, bias=b, act=K.ACT_RELU, out_bf16=out.view(-1, out.shape[-1]))
+    _count(1)
+
+
+def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: torch.Tensor, ws: Workspace,
+                 logits_nchw: Optional[torch.Tensor]) -> torch.Tensor:
+    """c_i bf16 NHWC [n_img, H_i, W_i, C_i]; optional logits_nchw fp32 [n_img, 2, H_1, W_1].
+    Returns the low-resolution logits as an NHWC fp32 workspace view [n_img, H_1, W_1, 2]."""
+    dev = c1.device
+    n_img = c1.shape[0]
+    hid = dec.conv1_4.weight.shape[0]
+    y = c4
+    for skip, (ca, ba, cb, bb) in ((c3, ("conv1_4", "bn1_4", "conv2_4", "bn2_4")),
+                                   (c2, ("conv1_3", "bn1_3", "conv2_3", "bn2_3")),
+                                   (c1, ("conv1_2", "bn1_2", "conv2_2", "bn2_2"))):
+        _, H, W, Cs = skip.shape
+        if y.shape[1] > H or y.shape[2] > W:
+            raise K.LavtError("decoder: coarser map is larger than the skip connection")
+        cat = ws.get("dec_cat", (n_img, H, W, y.shape[-1] + Cs), torch.bfloat16, dev)
+        K.upsample_concat(y, skip, cat)
+        t1 = ws.get("dec_t1", (n_img, H, W, hid), torch.bfloat16, dev)
+        _cbr(cat, dec, ca, ba, t1)
+        t2 = ws.get("dec_t2_%d" % H, (n_img, H, W, hid), torch.bfloat16, dev)
+        _cbr(t1, dec, cb, bb, t2)
+        y = t2
+        _count(1)
+    _, H, W, _ = y.shape
+    w11 = dec.prepared.get("w11", [dec.conv1_1.weight], lambda: _f32(dec.conv1_1.weight.reshape(2, -1)))
+    lg = ws.get("dec_logits", (n_img, H, W, 2), torch.float32, dev)
+    K.conv1x1_logits(y.view(-1, hid), w11, dec.conv1_1.bias.detach(), lg.view(-1, 2))
+    _count(1)
+    if logits_nchw is not None:
+        K.upsample_logits(lg, logits_nchw)      # same size: exact NHWC -> NCHW transposition
+        _count(1)
+    return lg

@@ -1,0 +1,100 @@
+"""Top-level LAVT modules -- B200 host side (reference lib/_utils.py:10-238).
+
+``LAVTVideo.forward(x[B,T,3,H,W], text[B,Nl], l_mask[B,Nl]) -> [B*T,2,H,W]`` and
+``LAVTOne.forward(x[B,3,H,W], text, l_mask)`` keep the reference signatures.  BERT stays the stock
+``transformers`` module (the reference's own copy is not in its tree); everything after
+``l_feats`` runs on the sm_100a kernels with NHWC bf16 hand-off between backbone and decoder.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi as K
+from .. import engine as E
+from .video_swin_transformer import _lang, _mask, _planes
+
+
+def _build_text_encoder(args):
+    from transformers import BertConfig, BertModel
+    ck = getattr(args, "ck_bert", None)
+    if ck and os.path.exists(ck):
+        enc = BertModel.from_pretrained(ck)
+    else:  # offline: BERT-base architecture, random init (weights are loaded later from the LAVT checkpoint)
+        enc = BertModel(BertConfig())
+    enc.pooler = None
+    return enc
+
+
+class _Segmenter(nn.Module):
+    video = False
+
+    def _segment(self, x5: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, size) -> torch.Tensor:
+        """x5 (B,3,T,H,W) strided view; l_feats (B,768,Nl); l_mask (B,Nl[,1])."""
+        _, nhwc = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=False, want_nhwc_bf16=True)
+        c1, c2, c3, c4 = nhwc
+        ws = E.workspace(c1.device)
+        lg = E.decoder_nhwc(self.classifier, c4, c3, c2, c1, ws, None)       # (n_img, H/4, W/4, 2) NHWC fp32
+        out = torch.empty(lg.shape[0], 2, size[0], size[1], device=lg.device, dtype=torch.float32)
+        K.upsample_logits(lg, out)                                             # bilinear x4 + NCHW (lib/_utils.py:106)
+        E._count(1)
+        return out
+
+
+class LAVT(_Segmenter):
+    """Backbone + decoder with precomputed language features (reference :10-30)."""
+
+    def __init__(self, backbone, classifier):
+        super().__init__()
+        self.backbone, self.classifier = backbone, classifier
+
+    def forward(self, x, l_feats, l_mask):
+        E.require_cuda(x, "x")
+        x5 = _planes(x).unsqueeze(2)
+        return self._segment(x5, l_feats, l_mask, x.shape[-2:])
+
+
+class LAVTOne(_Segmenter):
+    """BERT inside the model (reference :36-66)."""
+
+    def __init__(self, backbone, classifier, args):
+        super().__init__()
+        self.backbone, self.classifier = backbone, classifier
+        self.text_encoder = _build_text_encoder(args)
+        self.lazy_pred = False
+
+    def forward(self, x, text, l_mask):
+        E.require_cuda(x, "x")
+        l_feats = self.text_encoder(text, attention_mask=l_mask)[0].permute(0, 2, 1)
+        x5 = _planes(x).unsqueeze(2)
+        return self._segment(x5, l_feats, l_mask, x.shape[-2:])
+
+
+class LAVTVideo(_Segmenter):
+    """Video model (reference :76-131): x (B,T,3,H,W) -> (B*T,2,H,W)."""
+    video = True
+
+    def __init__(self, backbone, classifier, args):
+        super().__init__()
+        self.backbone, self.classifier = backbone, classifier
+        self.text_encoder = _build_text_encoder(args)
+        self.lazy_pred = False
+        self.seg_last = False
+
+    def encode_text(self, text, l_mask):
+        return self.text_encoder(text, attention_mask=l_mask)[0].permute(0, 2, 1)
+
+    def forward(self, x, text, l_mask):
+        E.require_cuda(x, "x")
+        l_feats = self.encode_text(text, l_mask)
+        return self.forward_with_lang(x, l_feats, l_mask)
+
+    def forward_with_lang(self, x, l_feats, l_mask):
+        """Hot path after BERT: x (B,T,3,H,W), l_feats (B,768,Nl), l_mask (B,Nl)."""
+        x5 = _planes(x).permute(0, 2, 1, 3, 4)     # (B,3,T,H,W) view; read in place by the im2col kernel
+        return self._segment(x5, l_feats, l_mask, x.shape[-2:])
+
+    def load_from_pretrained2d_lavt_weights(self, pretrained):
+        raise NotImplementedError("2D -> 3D checkpoint inflation (reference lib/_utils.py:133-238) is not implemented yet")

@@ -1,0 +1,51 @@
+"""SimpleDecoding mask decoder -- B200 host module (reference lib/mask_predictor.py:7-99).
+
+Parameter names match the reference (``conv{1,2}_{4,3,2}``, ``bn{1,2}_{4,3,2}``, ``conv1_1``).  The three
+upsample+concat+(conv3x3+BN+ReLU)x2 levels run as: one bandwidth kernel that writes the concatenated NHWC bf16
+conv input, and the tcgen05 implicit-GEMM convolution with eval-mode BatchNorm folded into the epilogue.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi as K
+from .. import engine as E
+
+
+class SimpleDecoding(nn.Module):
+    def __init__(self, c4_dims, args=None, factor=2):
+        super().__init__()
+        for flag in ("lazy_pred", "interpolate_before_seg", "seg_last"):
+            if getattr(args, flag, False):
+                raise NotImplementedError(f"--{flag} is not implemented on the B200 path yet")
+        self.lazy_pred = False
+        hidden = c4_dims // factor
+        c4, c3, c2, c1 = c4_dims, c4_dims // factor, c4_dims // factor ** 2, c4_dims // factor ** 3
+        for name, cin in (("1_4", c4 + c3), ("2_4", hidden), ("1_3", hidden + c2), ("2_3", hidden),
+                          ("1_2", hidden + c1), ("2_2", hidden)):
+            setattr(self, "conv" + name, nn.Conv2d(cin, hidden, 3, padding=1, bias=False))
+            setattr(self, "bn" + name, nn.BatchNorm2d(hidden))
+        self.conv1_1 = nn.Conv2d(hidden, 2, 1)
+        self.prepared = E.PreparedWeights()
+
+    def run_nhwc(self, c4, c3, c2, c1) -> torch.Tensor:
+        """NHWC bf16 maps -> logits (n_img, 2, H1, W1) fp32 NCHW."""
+        n_img, H, W, _ = c1.shape
+        logits = torch.empty(n_img, 2, H, W, device=c1.device, dtype=torch.float32)
+        E.decoder_nhwc(self, c4, c3, c2, c1, E.workspace(c1.device), logits)
+        return logits
+
+    def forward(self, x_c4, x_c3, x_c2, x_c1) -> torch.Tensor:
+        """Reference signature: four NCHW fp32 maps (coarse -> fine) -> (n_img, 2, H1, W1) logits."""
+        maps = []
+        ws = E.workspace(x_c1.device)
+        for i, t in enumerate((x_c4, x_c3, x_c2, x_c1)):
+            E.require_cuda(t, "feature map")
+            n, C, H, W = t.shape
+            t = t.detach().float().contiguous()
+            o = ws.get("dec_in_%d" % i, (n, H, W, C), torch.bfloat16, t.device)
+            K.nchw_to_nhwc_bf16(t.view(n, C, H * W), o.view(n, H * W, C))
+            E._count(1)
+            maps.append(o)
+        return self.run_nhwc(*maps)
