@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the LAVT-RS hot path on B200:  python bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): LAVT-RS forward clips/s on 8x384x384 clips, Video Swin-B, 20-word expression.
+One step = one forward of the hot path (backbone + PWAM/gate + SimpleDecoding + x4 upsample, i.e.
+``LAVTVideo.forward`` after the external BERT call) over one batch of synthetic clips per GPU.
+
+  value      whole-job clips/s, inputs resident in HBM, CUDA-graph replay of the forward, CUDA-event timed
+  e2e        same metric through the public API call ``model.forward_with_lang`` with HOST (pinned) inputs:
+             H2D of pixels / language features / mask and D2H of the full-resolution logits inside the timed region
+  roofline   the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs / CUDA-event time vs the
+             measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the oracle port of the reference forward (oracle/lavt_oracle.py) timed on this
+             box's host cores -- a reported baseline, not the target.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "LAVT-RS fwd clips/s (8x384^2)"
+T_FRAMES, IMG, NL = 8, 384, 20
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--clips-per-gpu", type=int, default=8)
+    p.add_argument("--window12", action="store_true", help="(8,12,12) windows instead of the default (8,7,7)")
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def flops_per_clip(window12: bool) -> float:
+    # BASELINE.md section 2 (measured with torch.utils.flop_counter on the reference), minus BERT (3.4 GFLOP)
+    return (2198.4e9 if window12 else 2074.8e9) - 3.4e9
+
+
+def model_args(window12: bool):
+    from lavt_rs_b200.args import default_args
+    return default_args(["--model", "lavt_video", "--swin_type", "base"] + (["--window12"] if window12 else []))
+
+
+def build_model(window12: bool, device):
+    from lavt_rs_b200.lib import segmentation
+    torch.manual_seed(0)
+    model = segmentation.lavt_video(pretrained="", args=model_args(window12))
+    # the builder's init leaves LanguageGate live (init_weights overwrites the zero init, SURVEY.md TL;DR 3.5)
+    return model.to(device).eval()
+
+
+def synth_batch(B: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T_FRAMES, 3, IMG, IMG, generator=g)
+    l = torch.randn(B, 768, NL, generator=g)
+    m = torch.zeros(B, NL, dtype=torch.int64)
+    m[:, :14] = 1
+    return x, l, m
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_forward_time(window12: bool, sd_cpu, n_runs: int, threads: int):
+    """Oracle port of the reference forward on host cores: 1 clip per run."""
+    from oracle import lavt_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig.swin("base", window12=window12, video=True)
+    x, l, m = synth_batch(1, 100)
+    times, out = [], None
+    with torch.no_grad():
+        for _ in range(n_runs):
+            t0 = time.perf_counter()
+            out = O.model_forward(sd_cpu, cfg, x, l, m)
+            times.append(time.perf_counter() - t0)
+    return times, out, (x, l, m)
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference cannot travel)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from lavt_rs_b200.lib import segmentation  # host modules only build parameters here (CPU); no kernels are run
+    torch.manual_seed(0)
+    model = segmentation.lavt_video(pretrained="", args=model_args(a.window12)).eval()
+    sd = {k: v.detach().float() for k, v in model.state_dict().items() if not k.startswith("text_encoder.")}
+    budget_s = 200.0
+    warm = min(a.warmup, 1)
+    wt, _, _ = cpu_forward_time(a.window12, sd, max(warm, 1), threads)
+    steps = max(1, min(a.steps, int(budget_s / max(wt[-1], 1e-3))))
+    times, _, _ = cpu_forward_time(a.window12, sd, steps, threads)
+    per = sum(times) / len(times)
+    v = 1.0 / per
+    sample = f"1 clip (8x384x384) per step, {steps} of {a.steps} requested steps timed after {max(warm,1)} warm-up, fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": a.gpus, "steps": steps,
+        "warmup": max(warm, 1), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LAVT-RS Video Swin-B forward, 8x384x384 clips, 20-token expression", "window": "8x12x12" if a.window12 else "8x7x7",
+                   "clips_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from lavt_rs_b200 import _cabi as K
+    from lavt_rs_b200 import engine as E
+    K.check(K.lib().lavt_check_device(), "lavt_check_device")
+
+    B = a.clips_per_gpu
+    model = build_model(a.window12, dev)
+    # two rotating host batches (pinned) and their device-resident copies
+    host = []
+    for s in range(2):
+        x, l, m = synth_batch(B, 1 + s + 10 * rank)
+        host.append((x.pin_memory(), l.pin_memory(), m.pin_memory()))
+    resident = [(x.to(dev), l.to(dev), m.to(dev)) for x, l, m in host]
+    sx, sl, sm_ = (torch.empty_like(t) for t in resident[0])     # static graph inputs
+
+    def fwd_static():
+        return model.forward_with_lang(sx, sl, sm_)
+
+    with torch.no_grad():
+        # eager warm-up (also builds bf16 weight copies, workspaces, func attributes)
+        sx.copy_(resident[0][0]); sl.copy_(resident[0][1]); sm_.copy_(resident[0][2])
+        E.LAUNCHES = 0
+        out = fwd_static()
+        launches_per_fwd = E.LAUNCHES
+        torch.cuda.synchronize()
+        graph = None
+        if not a.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fwd_static()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fwd_static()
+
+        def step_resident(i):
+            rx, rl, rm = resident[i % 2]
+            sx.copy_(rx); sl.copy_(rl); sm_.copy_(rm)       # device-to-device refresh of the static inputs (part of the step)
+            if graph is not None:
+                graph.replay()
+            else:
+                fwd_static()
+
+        host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+
+        def step_e2e(i):
+            hx, hl, hm = host[i % 2]
+            sx.copy_(hx, non_blocking=True); sl.copy_(hl, non_blocking=True); sm_.copy_(hm, non_blocking=True)
+            if graph is not None:
+                graph.replay()
+                o = out
+            else:
+                o = fwd_static()
+            host_out.copy_(o, non_blocking=True)
+
+        def timed(step_fn, steps, warmup):
+            for i in range(warmup):
+                step_fn(i)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                step_fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if dist is not None:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.barrier()
+                ms = t.item()
+            return ms
+
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ms = timed(step_resident, a.steps, max(a.warmup, 3))
+        clk = clocks.stop() if rank == 0 else None
+        ms_e2e = timed(step_e2e, a.steps, 1)
+
+        # --- roofline leg: per-launch CUDA events around the dominant kernel families (eager, same inputs) ---
+        fam = None
+        if rank == 0:
+            K.TIMER.enabled = True
+            K.TIMER.records.clear()
+            fwd_static()
+            fam = K.TIMER.summary()
+            K.TIMER.enabled = False
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_clips = B * world
+    value = total_clips * a.steps / (ms * 1e-3)
+    e2e_v = total_clips * a.steps / (ms_e2e * 1e-3)
+    pk, pk_kind = peaks()
+    g = fam.get("gemm_bf16_tc_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    at = fam.get("window_attn_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    roofline = {"kernel": "gemm_bf16_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None,
+                "launches": g["launches"], "ms_per_step": g["ms"], "alg_flops_per_step": g["flops"],
+                "attention_core": {"kernel": "window_attn_kernel", "launches": at["launches"], "ms_per_step": at["ms"],
+                                   "tflops": at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0},
+                "whole_step_tflops": flops_per_clip(a.window12) * value / world / 1e12}
+
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = host_out.numel() * host_out.element_size()
+    res = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "LAVT-RS Video Swin-B forward (hot path after BERT), 8x384x384 clips, 20-token expression",
+                   "window": "8x12x12" if a.window12 else "8x7x7", "clips_per_gpu_per_step": B, "global_clips_per_step": total_clips,
+                   "parallelism": f"clip-sharded x{world}, no collectives", "cuda_graph": graph is not None,
+                   "l2": "two rotating input batches; per-step activations (>1 GB) exceed the 126 MB L2",
+                   "flops_per_clip": flops_per_clip(a.window12)},
+        "clocks": clk,
+        "e2e": {"value": e2e_v, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches_per_fwd * a.steps,
+        "gpu_launches_per_step": launches_per_fwd,
+        "roofline": roofline,
+        "workspace_bytes": E.workspace(dev).bytes(),
+    }
+
+    if world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if not k.startswith("text_encoder.")}
+        times, ref_out, (cx, cl, cm) = cpu_forward_time(a.window12, sd, 1, threads)
+        with torch.no_grad():
+            got = model.forward_with_lang(cx.to(dev), cl.to(dev), cm.to(dev)).float().cpu()
+        rel = ((got - ref_out).norm() / ref_out.norm()).item()
+        agree = (got.argmax(1) == ref_out.argmax(1)).float().mean().item()
+        res["cpu_baseline"] = {"value": 1.0 / times[0], "unit": "clips/s", "cores": threads, "kind": "port",
+                               "sample": "1 clip (8x384x384), 1 forward, fp32, oracle port of the reference on torch CPU"}
+        res["parity_vs_oracle"] = {"logits_rel_l2": rel, "argmax_agreement": agree}
+    print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,18 +112,19 @@ int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_
                           void* out_bf16, void* stream);
 
 /* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */
-/* InstanceNorm1d statistics over the n tokens of each clip: x bf16 [B,n,C] -> stats fp32 [B,2,C] = (mean, rstd). */
+/* InstanceNorm1d statistics over the n tokens of each clip: x fp32 [B,n,C] -> stats fp32 [B,2,C] = (mean, rstd).
+ * (the pre-norm projections q_pre / lang_pre are kept in fp32: they are never tensor-core operands) */
 int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C);
-int lavt_instnorm_stats(const void* x_bf16, int32_t B, int64_t n, int32_t C, float eps, float* stats,
+int lavt_instnorm_stats(const float* x, int32_t B, int64_t n, int32_t C, float eps, float* stats,
                         float* workspace, void* stream);
 /* k, v = (W l + b) * l_mask : l fp32 [B,Lin,Nl], mask fp32 [B,Nl], weights fp32 [C,Lin] -> k, v fp32 [B,Nl,C] */
 int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                  float* k, float* v, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream);
-/* o = softmax_words(C^-0.5 * IN(q_pre) k^T + (1e4 mask - 1e4)) v ; q_pre, o bf16 [B,n,C] */
-int lavt_pwam_attend(const void* qpre_bf16, const float* stats, const float* k, const float* v, const float* mask,
+/* o = softmax_words(C^-0.5 * IN(q_pre) k^T + (1e4 mask - 1e4)) v ; q_pre fp32, o bf16 [B,n,C] */
+int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                      void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream);
-/* out = vis * IN(lang_pre) (bf16 [B,n,C]) -- the A operand of project_mm */
-int lavt_pwam_mul_norm(const void* vis_bf16, const void* lang_bf16, const float* stats, void* out_bf16, int32_t B,
+/* out = vis * IN(lang_pre) (vis, out bf16; lang_pre fp32 [B,n,C]) -- the A operand of project_mm */
+int lavt_pwam_mul_norm(const void* vis_bf16, const float* lang, const float* stats, void* out_bf16, int32_t B,
                        int64_t n, int32_t C, void* stream);
 
 /* ---- decoder glue (lib/mask_predictor.py:56-99, lib/_utils.py:106) ---- */

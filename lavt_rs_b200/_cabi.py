@@ -154,6 +154,42 @@ def make_epilogue(*, cscale=None, bias=None, act=ACT_NONE, mul=None, resid=None,
     return e
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual launches (bench.py roofline leg). Disabled by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []   # (family, flops, bytes, start_event, end_event)
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, start, family: str, flops: float, nbytes: float):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((family, flops, nbytes, start, ev))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, nb, s, e in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
+
+
+TIMER = KernelTimer()
+
+
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
     """out = epilogue(a @ w.T); a [M,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
     _req(a, torch.bfloat16, "a")
@@ -163,8 +199,10 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
     if K != K2:
         raise LavtError(f"gemm: K mismatch {K} vs {K2}")
     e = make_epilogue(**epi)
+    t0 = TIMER.begin()
     check(lib().lavt_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
                                C.byref(e), stream_ptr()), "lavt_gemm_bf16")
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N))
 
 
 def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
@@ -176,8 +214,11 @@ def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
         raise LavtError("conv: x must be contiguous NHWC")
     Cout = w_taps.shape[0]
     e = make_epilogue(**epi)
+    t0 = TIMER.begin()
     check(lib().lavt_conv3x3_bf16(x_nhwc.data_ptr(), Cin, n_img, H, W, Cin, w_taps.data_ptr(), Cout,
                                   C.byref(e), stream_ptr()), "lavt_conv3x3_bf16")
+    npix = n_img * H * W
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * npix * Cout * 9 * Cin, 2.0 * (npix * Cin + Cout * 9 * Cin + npix * Cout))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,9 +281,12 @@ def window_attention(qkv: torch.Tensor, table: torch.Tensor, geom: WinGeom, out_
     _c(qkv, torch.bfloat16, "qkv")
     _c(table, torch.float32, "table")
     L, nH = table.shape
+    t0 = TIMER.begin()
     check(lib().lavt_window_attention(qkv.data_ptr(), table.data_ptr(), L, nH, C.byref(geom),
                                       _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
           "lavt_window_attention")
+    rows = geom.rows()
+    TIMER.end(t0, "window_attn_kernel", 4.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 4)
 
 
 def instnorm_workspace_floats(B: int, n: int, Cn: int) -> int:
@@ -250,8 +294,8 @@ def instnorm_workspace_floats(B: int, n: int, Cn: int) -> int:
 
 
 def instnorm_stats(x: torch.Tensor, stats: torch.Tensor, workspace: torch.Tensor, eps: float = 1e-5) -> None:
-    """x bf16 [B,n,C] -> stats fp32 [B,2,C] (mean, rstd)."""
-    _c(x, torch.bfloat16, "x")
+    """x fp32 [B,n,C] -> stats fp32 [B,2,C] (mean, rstd)."""
+    _c(x, torch.float32, "x")
     B, n, Cn = x.shape
     if workspace.numel() < instnorm_workspace_floats(B, n, Cn):
         raise LavtError("instnorm_stats: workspace too small")
@@ -271,7 +315,7 @@ def pwam_kv(l, mask, wk, bk, wv, bv, k, v) -> None:
 
 
 def pwam_attend(qpre, stats, k, v, mask, out, heads: int) -> None:
-    _c(qpre, torch.bfloat16, "qpre")
+    _c(qpre, torch.float32, "qpre")
     B, n, Cn = qpre.shape
     Nl = k.shape[1]
     check(lib().lavt_pwam_attend(qpre.data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
@@ -283,7 +327,7 @@ def pwam_attend(qpre, stats, k, v, mask, out, heads: int) -> None:
 def pwam_mul_norm(vis, lang, stats, out) -> None:
     _c(vis, torch.bfloat16, "vis")
     B, n, Cn = vis.shape
-    check(lib().lavt_pwam_mul_norm(vis.data_ptr(), _c(lang, torch.bfloat16, "lang").data_ptr(),
+    check(lib().lavt_pwam_mul_norm(vis.data_ptr(), _c(lang, torch.float32, "lang").data_ptr(),
                                    _c(stats, torch.float32, "stats").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
                                    B, n, Cn, stream_ptr()), "lavt_pwam_mul_norm")
 

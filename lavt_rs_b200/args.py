@@ -1,0 +1,47 @@
+"""Argument namespace for the model builders.
+
+The reference reads model-structure switches straight from its argparse namespace inside ``lib/``
+(``args.swin_type``, ``args.window12``, ``args.mha``, ``args.version`` ...; reference args.py).  This
+parser declares the switches the hot path consults, with the reference's names and defaults, so
+``segmentation.lavt_video(pretrained, args)`` can be driven the same way.  Flags whose behaviour is not
+implemented on the B200 path are still declared and rejected by ``check_args`` (no silent fallback).
+"""
+from __future__ import annotations
+
+import argparse
+
+_STRUCTURE_FLAGS = [
+    # name, type/action, default, help
+    ("--model", str, "lavt_video", "lavt | lavt_one | lavt_video"),
+    ("--swin_type", str, "base", "tiny | small | base | large"),
+    ("--window12", "store_true", False, "window 12 instead of 7 (video: (8,12,12))"),
+    ("--mha", str, "", "PWAM heads per stage, e.g. 1-1-1-1"),
+    ("--fusion_drop", float, 0.0, "dropout inside PWAM (must be 0 here)"),
+    ("--version", str, "default", "default | no_gate | none"),
+    ("--fuse", str, "default", "default | simple"),
+    ("--use_checkpoint", "store_true", False, "activation checkpointing flag of the reference (affects last-stage gate)"),
+    ("--ck_bert", str, "bert-base-uncased", "BERT checkpoint directory"),
+    ("--bert_tokenizer", str, "bert-base-uncased", "tokenizer name"),
+    ("--pretrained_swin_weights", str, "", "Video-Swin checkpoint"),
+    ("--img_size", int, 480, "input size"),
+    ("--lg_act_layer", str, "tanh", "LanguageGate activation (2-D backbone)"),
+    ("--att_norm_layer_type", str, "IN", "PWAM attention norm (2-D backbone)"),
+]
+_REJECTED_BOOL_FLAGS = ["hs", "lazy_pred", "ts_pwam", "t_pwam", "t_pwam_comp", "sep_t_pwam", "seq_t_pwam",
+                        "sep_t_pwam_inner", "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "interpolate_before_seg", "seg_last"]
+
+
+def get_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="LAVT-RS B200 hot path")
+    for name, typ, default, helptext in _STRUCTURE_FLAGS:
+        if typ == "store_true":
+            p.add_argument(name, action="store_true", help=helptext)
+        else:
+            p.add_argument(name, type=typ, default=default, help=helptext)
+    for name in _REJECTED_BOOL_FLAGS:
+        p.add_argument("--" + name, action="store_true", help="declared for compatibility; rejected at model build")
+    return p
+
+
+def default_args(argv=()):
+    return get_parser().parse_args(list(argv))

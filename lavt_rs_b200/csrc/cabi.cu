@@ -144,9 +144,9 @@ int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_
 
 int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C) { return colstats_workspace_floats(B, n, C); }
 
-int lavt_instnorm_stats(const void* x_bf16, int32_t B, int64_t n, int32_t C, float eps, float* stats, float* workspace,
+int lavt_instnorm_stats(const float* x, int32_t B, int64_t n, int32_t C, float eps, float* stats, float* workspace,
                         void* stream) {
-  return colstats_dispatch(CB(x_bf16), stats, workspace, B, n, C, eps, S(stream));
+  return colstats_dispatch(x, stats, workspace, B, n, C, eps, S(stream));
 }
 
 int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
@@ -154,14 +154,14 @@ int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float
   return pwam_kv_dispatch(l, mask, wk, bk, wv, bv, k, v, B, Nl, Lin, C, S(stream));
 }
 
-int lavt_pwam_attend(const void* qpre_bf16, const float* stats, const float* k, const float* v, const float* mask,
+int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                      void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream) {
-  return pwam_core_dispatch(CB(qpre_bf16), stats, k, v, mask, MB(o_bf16), B, n, C, Nl, heads, S(stream));
+  return pwam_core_dispatch(qpre, stats, k, v, mask, MB(o_bf16), B, n, C, Nl, heads, S(stream));
 }
 
-int lavt_pwam_mul_norm(const void* vis_bf16, const void* lang_bf16, const float* stats, void* out_bf16, int32_t B,
+int lavt_pwam_mul_norm(const void* vis_bf16, const float* lang, const float* stats, void* out_bf16, int32_t B,
                        int64_t n, int32_t C, void* stream) {
-  return pwam_mul_dispatch(CB(vis_bf16), CB(lang_bf16), stats, MB(out_bf16), B, n, C, S(stream));
+  return pwam_mul_dispatch(CB(vis_bf16), lang, stats, MB(out_bf16), B, n, C, S(stream));
 }
 
 int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,

@@ -24,8 +24,8 @@ int ln_rows_dispatch(int mode, const LnParams& p, cudaStream_t st);
 int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long sT, __nv_bfloat16* out, int B, int T, int H,
                            int W, cudaStream_t st);
 long long colstats_workspace_floats(int B, long long n, int C);
-int colstats_dispatch(const __nv_bfloat16* x, float* stats, float* workspace, int B, long long n, int C, float eps, cudaStream_t st);
-int pwam_mul_dispatch(const __nv_bfloat16* vis, const __nv_bfloat16* lang, const float* stats, __nv_bfloat16* out, int B,
+int colstats_dispatch(const float* x, float* stats, float* workspace, int B, long long n, int C, float eps, cudaStream_t st);
+int pwam_mul_dispatch(const __nv_bfloat16* vis, const float* lang, const float* stats, __nv_bfloat16* out, int B,
                       long long n, int C, cudaStream_t st);
 
 struct AttnParams {
@@ -39,7 +39,7 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st);
 
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);
-int pwam_core_dispatch(const __nv_bfloat16* qpre, const float* stats, const float* k, const float* v, const float* mask,
+int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                        __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st);
 
 int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,

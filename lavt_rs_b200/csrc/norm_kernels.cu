@@ -174,42 +174,28 @@ int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long
 // ---------------------------------------------------------------------------------------------
 constexpr int CS_ROWS_PER_BLOCK = 512;
 
-__global__ void __launch_bounds__(256) colstats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
+__global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __restrict__ x, float* __restrict__ part,
                                                                int n, int C, int chunks) {
-  // grid: (chunks, B).  thread -> 8 channels (one uint4); row groups stride over the chunk's rows
+  // grid: (chunks, B).  thread -> 4 channels (one float4); row groups stride over the chunk's rows
   extern __shared__ float sm[];   // [rowgroups][C][2]
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int tpr = C / 8;                       // threads per row
+  const int tpr = C / 4;                       // threads per row
   const int rg = blockDim.x / tpr;             // row groups
   const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
-  const __nv_bfloat16* base = x + static_cast<long long>(b) * n * C;
-  float pv[8], s1[8], s2[8];
-  {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(base) + tc);
-    float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    pv[0] = a.x; pv[1] = a.y; pv[2] = bb.x; pv[3] = bb.y; pv[4] = c.x; pv[5] = c.y; pv[6] = d.x; pv[7] = d.y;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const float* base = x + static_cast<long long>(b) * n * C;
+  const float4 pv = __ldg(reinterpret_cast<const float4*>(base) + tc);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   const int r0 = chunk * CS_ROWS_PER_BLOCK;
   const int r1 = min(n, r0 + CS_ROWS_PER_BLOCK);
   if (tr < rg) {
     for (int r = r0 + tr; r < r1; r += rg) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C) + tc);
-      float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      float f[8] = {a.x, a.y, bb.x, bb.y, c.x, c.y, d.x, d.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = f[j] - pv[j];
-        s1[j] += t;
-        s2[j] += t * t;
-      }
+      const float4 u = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(r) * C) + tc);
+      const float a = u.x - pv.x, bb = u.y - pv.y, c = u.z - pv.z, d = u.w - pv.w;
+      s1.x += a; s1.y += bb; s1.z += c; s1.w += d;
+      s2.x += a * a; s2.y += bb * bb; s2.z += c * c; s2.w += d * d;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sm[(tr * C + tc * 8 + j) * 2 + 0] = s1[j];
-      sm[(tr * C + tc * 8 + j) * 2 + 1] = s2[j];
-    }
+    float* o = sm + (static_cast<long long>(tr) * C + tc * 4) * 2;
+    o[0] = s1.x; o[1] = s2.x; o[2] = s1.y; o[3] = s2.y; o[4] = s1.z; o[5] = s2.z; o[6] = s1.w; o[7] = s2.w;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -224,12 +210,12 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const __nv_bfloat
   }
 }
 
-__global__ void __launch_bounds__(256) colstats_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ part,
+__global__ void __launch_bounds__(256) colstats_final_kernel(const float* __restrict__ x, const float* __restrict__ part,
                                                              float* __restrict__ stats, int n, int C, int chunks, float eps) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float pivot = __bfloat162float(x[static_cast<long long>(b) * n * C + c]);
+  const float pivot = x[static_cast<long long>(b) * n * C + c];
   double a = 0.0, q = 0.0;
   for (int k = 0; k < chunks; ++k) {
     const float* o = part + ((static_cast<long long>(b) * chunks + k) * 2) * C;
@@ -247,21 +233,15 @@ long long colstats_workspace_floats(int B, long long n, int C) {
   return static_cast<long long>(B) * chunks * 2 * C;
 }
 
-int colstats_dispatch(const __nv_bfloat16* x, float* stats, float* workspace, int B, long long n_ll, int C, float eps, cudaStream_t st) {
+int colstats_dispatch(const float* x, float* stats, float* workspace, int B, long long n_ll, int C, float eps, cudaStream_t st) {
   LAVT_REQUIRE(n_ll < (1LL << 30), "instance-norm stats: too many tokens");
   const int n = static_cast<int>(n_ll);
-  LAVT_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "instance-norm stats: C=%d unsupported", C);
+  LAVT_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "instance-norm stats: C=%d unsupported", C);
   LAVT_REQUIRE(B > 0 && n > 0, "instance-norm stats: empty input");
   const int chunks = (n + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
-  const int tpr = C / 8;
-  LAVT_REQUIRE(tpr <= 256, "instance-norm stats: C too large");
+  const int tpr = C / 4;
   const int rg = 256 / tpr;
-  const size_t smem = static_cast<size_t>(rg) * C * 2 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    LAVT_CUDA(cudaFuncSetAttribute(colstats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  const size_t smem = static_cast<size_t>(rg) * C * 2 * sizeof(float);   // <= 8 KB
   colstats_partial_kernel<<<dim3(chunks, B), 256, smem, st>>>(x, workspace, n, C, chunks);
   LAVT_LAUNCH_CHECK("colstats_partial_kernel");
   colstats_final_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(x, workspace, stats, n, C, chunks, eps);
@@ -272,7 +252,7 @@ int colstats_dispatch(const __nv_bfloat16* x, float* stats, float* workspace, in
 // ---------------------------------------------------------------------------------------------
 // out = vis * (lang_pre - mean) * rstd   (bf16 in / out, stats fp32 (B,2,C))
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pwam_mul_kernel(const __nv_bfloat16* __restrict__ vis, const __nv_bfloat16* __restrict__ lang,
+__global__ void __launch_bounds__(256) pwam_mul_kernel(const __nv_bfloat16* __restrict__ vis, const float* __restrict__ lang,
                                                        const float* __restrict__ stats, __nv_bfloat16* __restrict__ out,
                                                        long long n, int C, long long total8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -283,18 +263,19 @@ __global__ void __launch_bounds__(256) pwam_mul_kernel(const __nv_bfloat16* __re
   const float* mu = stats + (static_cast<long long>(b) * 2) * C + c8 * 8;
   const float* rs = mu + C;
   const uint4 uv = __ldg(reinterpret_cast<const uint4*>(vis) + i);
-  const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lang) + i);
-  const uint32_t vv[4] = {uv.x, uv.y, uv.z, uv.w}, ll[4] = {ul.x, ul.y, ul.z, ul.w};
+  const float4 l0 = __ldg(reinterpret_cast<const float4*>(lang) + 2 * i), l1 = __ldg(reinterpret_cast<const float4*>(lang) + 2 * i + 1);
+  const uint32_t vv[4] = {uv.x, uv.y, uv.z, uv.w};
+  const float ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
   uint32_t oo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 a = unpack_bf16x2(vv[j]), l = unpack_bf16x2(ll[j]);
-    oo[j] = pack_bf16x2(a.x * (l.x - mu[2 * j]) * rs[2 * j], a.y * (l.y - mu[2 * j + 1]) * rs[2 * j + 1]);
+    const float2 a = unpack_bf16x2(vv[j]);
+    oo[j] = pack_bf16x2(a.x * (ll[2 * j] - mu[2 * j]) * rs[2 * j], a.y * (ll[2 * j + 1] - mu[2 * j + 1]) * rs[2 * j + 1]);
   }
   reinterpret_cast<uint4*>(out)[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
 }
 
-int pwam_mul_dispatch(const __nv_bfloat16* vis, const __nv_bfloat16* lang, const float* stats, __nv_bfloat16* out, int B,
+int pwam_mul_dispatch(const __nv_bfloat16* vis, const float* lang, const float* stats, __nv_bfloat16* out, int B,
                       long long n, int C, cudaStream_t st) {
   LAVT_REQUIRE(C % 8 == 0, "pwam_mul: C must be a multiple of 8");
   const long long total8 = static_cast<long long>(B) * n * (C / 8);

@@ -47,7 +47,7 @@ int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const f
 constexpr int PWAM_MAX_NL = 80;
 
 template <int CPL, int PIX>
-__global__ void __launch_bounds__(256) pwam_core_kernel(const __nv_bfloat16* __restrict__ qpre, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) pwam_core_kernel(const float* __restrict__ qpre, const float* __restrict__ stats,
                                                         const float* __restrict__ k, const float* __restrict__ v,
                                                         const float* __restrict__ mask, __nv_bfloat16* __restrict__ o,
                                                         long long n, int Nl, int heads, float scale) {
@@ -70,22 +70,11 @@ __global__ void __launch_bounds__(256) pwam_core_kernel(const __nv_bfloat16* __r
 #pragma unroll
   for (int pi = 0; pi < PIX; ++pi) {
     const long long pp = min(p0 + pi, n - 1);
-    const __nv_bfloat16* src = qpre + (static_cast<long long>(b) * n + pp) * C + c0;
-    if (CPL % 8 == 0) {
+    const float* src = qpre + (static_cast<long long>(b) * n + pp) * C + c0;
 #pragma unroll
-      for (int i = 0; i < CPL; i += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + i));
-        const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        q[pi][i] = a.x; q[pi][i + 1] = a.y; q[pi][i + 2] = bb.x; q[pi][i + 3] = bb.y;
-        q[pi][i + 4] = cc.x; q[pi][i + 5] = cc.y; q[pi][i + 6] = d.x; q[pi][i + 7] = d.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(src + i));
-        const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y);
-        q[pi][i] = a.x; q[pi][i + 1] = a.y; q[pi][i + 2] = bb.x; q[pi][i + 3] = bb.y;
-      }
+    for (int i = 0; i < CPL; i += 4) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(src + i));
+      q[pi][i] = u.x; q[pi][i + 1] = u.y; q[pi][i + 2] = u.z; q[pi][i + 3] = u.w;
     }
 #pragma unroll
     for (int i = 0; i < CPL; ++i) q[pi][i] = (q[pi][i] - mu[i]) * rs[i] * scale;
@@ -142,7 +131,7 @@ __global__ void __launch_bounds__(256) pwam_core_kernel(const __nv_bfloat16* __r
   }
 }
 
-int pwam_core_dispatch(const __nv_bfloat16* qpre, const float* stats, const float* k, const float* v, const float* mask,
+int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                        __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st) {
   LAVT_REQUIRE(B > 0 && n > 0, "pwam_core: empty input");
   LAVT_REQUIRE(Nl >= 1 && Nl <= 4096, "pwam_core: Nl=%d out of range", Nl);

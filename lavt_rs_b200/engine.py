@@ -169,8 +169,8 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
 
     vis = ws.get("pw_vis", (B, n, C), torch.bfloat16, dev)
     K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C))
-    qpre = ws.get("pw_q", (B, n, C), torch.bfloat16, dev)
-    K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_bf16=qpre.view(N_, C))
+    qpre = ws.get("pw_q", (B, n, C), torch.float32, dev)      # fp32: feeds InstanceNorm + SIMT attention, never an MMA operand
+    K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
     stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
     stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), torch.float32, dev)
     K.instnorm_stats(qpre, stats, stw)
@@ -180,7 +180,7 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     o = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
     K.pwam_attend(qpre, stats, kk, vv, mask, o, heads)
     lang = qpre  # q_pre is dead: reuse its buffer for lang_pre
-    K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_bf16=lang.view(N_, C))
+    K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_f32=lang.view(N_, C))
     K.instnorm_stats(lang, stats, stw)
     a2 = o  # o is dead after the W projection
     K.pwam_mul_norm(vis, lang, stats, a2)
