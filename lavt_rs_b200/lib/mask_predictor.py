@@ -39,6 +39,8 @@ class SimpleDecoding(nn.Module):
     def forward(self, x_c4, x_c3, x_c2, x_c1) -> torch.Tensor:
         """Reference signature: four NCHW fp32 maps (coarse -> fine) -> (n_img, 2, H1, W1) logits."""
         maps = []
+        for t in (x_c4, x_c3, x_c2, x_c1):
+            E.require_cuda(t, "feature map")
         ws = E.workspace(x_c1.device)
         for i, t in enumerate((x_c4, x_c3, x_c2, x_c1)):
             E.require_cuda(t, "feature map")

@@ -1,0 +1,65 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python oracle/make_golden.py
+
+For each case: seeded weights (oracle.random_state_dict -- deterministic torch.Generator streams) are loaded
+INTO the reference's own nn.Modules (MultiModalSwinTransformer3D + SimpleDecoding, imported from /root/reference
+through oracle/ref_shims.py), the reference forward is executed on seeded synthetic inputs, and its outputs are
+stored.  tests/test_oracle_golden.py replays the same seeds through the oracle (CPU) and, on the GPU box,
+tests/test_golden_gpu.py through the CUDA path -- the reference itself never travels.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import lavt_oracle as O  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+CASES = {
+    # name: (window, depths, fusion heads, B, T, H, W, Nl, stored stage outputs)
+    "w7_t4_32": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=4, H=32, W=32, Nl=20, keep=(0, 1, 2, 3)),
+    "w12_t2_48": dict(window=(8, 12, 12), depths=(2, 2, 2, 2), mha=(1, 2, 4, 8), B=2, T=2, H=48, W=48, Nl=9, keep=(1, 2, 3)),
+    "w7_t16_32x40": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=16, H=32, W=40, Nl=22, keep=(2, 3)),
+}
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def case_inputs(c):
+    cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"])
+    sd = O.random_state_dict(cfg, seed=0)
+    x, l, m = O.synthetic_inputs(c["B"], c["T"], c["H"], c["W"], Nl=c["Nl"], seed=1)
+    return cfg, sd, x, l, m
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, c in CASES.items():
+        cfg, sd, x, l, m = case_inputs(c)
+        bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"])
+        missing = bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=False)
+        assert all(k.endswith("relative_position_index") for k in missing.missing_keys) and not missing.unexpected_keys, missing
+        missing = dec.load_state_dict({k[len("classifier."):]: v for k, v in sd.items() if k.startswith("classifier.")}, strict=False)
+        assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys, missing
+        with torch.no_grad():
+            feats = bb(x.permute(0, 2, 1, 3, 4), l, m.unsqueeze(-1))          # reference forward
+            low = dec(feats[3], feats[2], feats[1], feats[0])
+            logits = F.interpolate(low, size=(c["H"], c["W"]), mode="bilinear", align_corners=True)   # lib/_utils.py:106
+        arrays = {"logits": logits.numpy(), "logits_lowres": low.numpy()}
+        for i in c["keep"]:
+            arrays[f"c{i + 1}"] = feats[i].numpy()
+        for i in range(4):
+            arrays[f"c{i + 1}_absmean"] = np.float32(feats[i].abs().mean().item())
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print(name, {k: getattr(v, "shape", v) for k, v in arrays.items()}, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/lavt_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "lavt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lavt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lavt_rs_b200.build import build_library
+    path = build_library()
+    lib = ctypes.CDLL(path)
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in lavt_b200.h but not exported"
+
+
+def test_ctypes_binding_covers_header():
+    from lavt_rs_b200 import _cabi
+    assert sorted(_cabi.EXPORTS) == _header_symbols()
+    lib = _cabi.lib()
+    assert lib.lavt_abi_version() == _cabi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    from lavt_rs_b200 import _cabi
+    assert ctypes.sizeof(_cabi.WinGeom) == 17 * 4
+    assert ctypes.sizeof(_cabi.Epilogue) == 7 * 8 + 4 * 4      # 6 data pointers + win pointer, act/ldm/ldo/_pad
+    assert _cabi.Epilogue.win.offset == 64
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    from lavt_rs_b200 import _cabi
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(_cabi.LavtError):
+        _cabi.gemm_bf16(a, a, out_bf16=torch.zeros(128, 128, dtype=torch.bfloat16))

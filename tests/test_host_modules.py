@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference model API: state-dict contract, builders, flag rejection (CPU only)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lavt_rs_b200.args import default_args  # noqa: E402
+from oracle import lavt_oracle as O  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+
+def _small_backbone(window=(8, 7, 7)):
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=window, drop_path_rate=0.0, patch_norm=True, args=None)
+    return bb, SimpleDecoding(1024, None)
+
+
+def test_state_dict_keys_match_reference_contract():
+    bb, dec = _small_backbone()
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2))
+    sd = O.random_state_dict(cfg)
+    mine = {"backbone." + k: v for k, v in bb.state_dict().items()}
+    mine.update({"classifier." + k: v for k, v in dec.state_dict().items()})
+    benign = ("relative_position_index", "num_batches_tracked")
+    assert {k for k in mine if not k.endswith(benign)} == set(sd)
+    for k, v in sd.items():
+        assert tuple(mine[k].shape) == tuple(v.shape), k
+    # the buffers the reference registers are present too (strict loading of reference checkpoints)
+    assert mine["backbone.layers.0.blocks.0.attn.relative_position_index"].shape == (392, 392)
+    assert "classifier.bn1_4.num_batches_tracked" in mine
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")
+def test_full_model_state_dict_round_trips_with_reference():
+    from lavt_rs_b200.lib import segmentation
+    ref, _ = ref_shims.build_reference("lavt_video", "base")
+    mine = segmentation.lavt_video(pretrained="", args=default_args(["--model", "lavt_video", "--swin_type", "base"]))
+    ref_sd = ref.state_dict()
+    my_sd = mine.state_dict()
+    strip = lambda d: {k for k in d if not k.startswith("text_encoder.")}
+    assert strip(ref_sd) == strip(my_sd)
+    for k in strip(ref_sd):
+        assert ref_sd[k].shape == my_sd[k].shape, k
+    mine.load_state_dict({k: v for k, v in ref_sd.items() if not k.startswith("text_encoder.")}, strict=False)
+    idx = "backbone.layers.2.blocks.5.attn.relative_position_index"
+    assert torch.equal(mine.state_dict()[idx], ref_sd[idx])
+
+
+def test_builders_reject_unimplemented_flags():
+    from lavt_rs_b200.lib import segmentation
+    for flag in ("--sep_t_pwam", "--hs", "--lazy_pred"):
+        with pytest.raises(NotImplementedError):
+            segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "base", flag]))
+    with pytest.raises(NotImplementedError):
+        segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny"]))
+
+
+def test_forward_refuses_cpu_tensors():
+    from lavt_rs_b200 import _cabi
+    bb, dec = _small_backbone()
+    with pytest.raises(_cabi.LavtError):
+        bb(torch.zeros(1, 3, 2, 32, 32), torch.zeros(1, 768, 4), torch.ones(1, 4, 1))
+    with pytest.raises(_cabi.LavtError):
+        dec(torch.zeros(1, 1024, 1, 1), torch.zeros(1, 512, 2, 2), torch.zeros(1, 256, 4, 4), torch.zeros(1, 128, 8, 8))
+
+
+def test_relative_position_index_closed_form():
+    from lavt_rs_b200.lib.video_swin_transformer import _relative_position_index
+    for window in ((8, 7, 7), (2, 3, 4), (1, 12, 12)):
+        Wd, Wh, Ww = window
+        co = torch.stack(torch.meshgrid(torch.arange(Wd), torch.arange(Wh), torch.arange(Ww), indexing="ij")).flatten(1)
+        rel = (co[:, :, None] - co[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += Wd - 1
+        rel[:, :, 1] += Wh - 1
+        rel[:, :, 2] += Ww - 1
+        rel[:, :, 0] *= (2 * Wh - 1) * (2 * Ww - 1)
+        rel[:, :, 1] *= 2 * Ww - 1
+        assert torch.equal(_relative_position_index(window), rel.sum(-1))

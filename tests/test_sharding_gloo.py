@@ -1,0 +1,50 @@
+"""N>1 host logic on CPU: clip sharding + max-over-ranks timing reduction with a world_size-2 gloo group."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lavt_rs_b200.sharding import all_slices, clip_slice, max_over_ranks  # noqa: E402
+
+
+def test_slices_partition_the_clips():
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 4, 8):
+            sl = all_slices(n, world)
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            sizes = [e - s for s, e in sl]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s, e = clip_slice(13, rank, world)
+    # each rank "processes" its clips: result = clip index squared; the union must equal the single-process result
+    mine = torch.tensor([i * i for i in range(s, e)], dtype=torch.int64)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.numel()]))
+    slowest = max_over_ranks(10.0 + rank)
+    q.put((rank, mine.tolist(), [int(t) for t in sizes], slowest))
+    dist.destroy_process_group()
+
+
+def test_world_size_two_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29511 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    merged = out[0][1] + out[1][1]
+    assert merged == [i * i for i in range(13)]
+    assert out[0][2] == [7, 6] and out[0][3] == out[1][3] == 11.0
