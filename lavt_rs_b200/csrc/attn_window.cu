@@ -1,34 +1,48 @@
 // Shifted-window attention core (reference WindowAttention3D.forward, lib/video_swin_transformer.py:147-165;
 // 2-D twin lib/backbone.py:127-138):  per (window, head)
 //     S = q k^T  (+ relative-position bias, + shifted-window mask)  ->  softmax  ->  O = P v
-// computed flash-style: the N x N score matrix never leaves registers.  q arrives pre-scaled by head_dim^-0.5
-// (folded into the qkv GEMM epilogue).  The bias is gathered from the per-head table column held in shared
-// memory through the closed form  idx(i,j) = code(i) - code(j) + const  and the -100 mask from per-token
-// region ids (geom.cuh) -- neither the (N,N) index buffer nor the (nW,N,N) mask tensor exists on the device.
+// computed flash-style: the N x N score matrix never leaves registers.  q arrives pre-scaled by
+// head_dim^-0.5 * log2(e) (folded into the qkv GEMM epilogue) so the softmax runs in base 2 with one FADD + one
+// MUFU.EX2 per score.  The bias is gathered from the per-head table column held in shared memory (pre-multiplied by
+// log2 e) through the closed form  idx(i,j) = code(i) - code(j) + const ; the -100 mask comes from per-token region
+// ids (geom.cuh) and is skipped entirely for windows that do not straddle the cyclic-shift seam -- neither the (N,N)
+// index buffer nor the (nW,N,N) mask tensor exists on the device.
 //
-// Round-1 implementation: mma.sync.m16n8k16 (bf16 -> fp32) with cp.async double-buffered K/V tiles.  head_dim
-// is 32 at every Swin stage, which makes this core exp/ALU bound rather than tensor bound (128 MMA flop per
-// exp); a tcgen05/TMEM version is the next step.
+// mma.sync.m16n8k16 (bf16 -> fp32) with cp.async double-buffered K/V tiles.  head_dim is 32 at every Swin stage,
+// which makes this core SIMT-issue bound rather than tensor bound (ncu: profiles/); the tile shapes are therefore
+// chosen to minimise padded work (N = 392 -> 5 x 80 rows/keys instead of 4 x 128 / 7 x 64).
 #include "kernels.cuh"
 
 namespace lavt {
 
 constexpr int AT_HD = 32;        // head dim
-constexpr int AT_KV = 64;        // keys per tile
+constexpr float AT_LOG2E = 1.4426950408889634f;
 
 // 16-byte chunk swizzle inside a 64-byte row so that ldmatrix (8 rows x 16 B) is bank-conflict free
 __device__ __forceinline__ int kv_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
-template <int WARPS>
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// WARPS * 16 query rows per CTA, KVT keys per K/V tile (multiple of 16)
+template <int WARPS, int KVT>
 __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParams p) {
   constexpr int BQ = WARPS * 16;
   constexpr int THREADS = WARPS * 32;
+  constexpr int NT = KVT / 8;       // n8 tiles per K/V tile
+  constexpr int KS = KVT / 16;      // k16 steps per K/V tile
   extern __shared__ __align__(16) uint8_t smem[];
   const int N = p.win.N;
-  uint8_t* ks = smem;                                   // [2][64][64 B]
-  uint8_t* vs = ks + 2 * AT_KV * 64;                    // [2][64][64 B]
-  int* info = reinterpret_cast<int*>(vs + 2 * AT_KV * 64);   // [N] code | rid << 16
-  float* tab = reinterpret_cast<float*>(info + ((N + 3) & ~3));   // [L]
+  const int Npad = (N + 7) & ~7;
+  uint8_t* ks = smem;                                             // [2][KVT][64 B]
+  uint8_t* vs = ks + 2 * KVT * 64;                                // [2][KVT][64 B]
+  uint16_t* codes = reinterpret_cast<uint16_t*>(vs + 2 * KVT * 64);   // [Npad] rel-pos code per token
+  uint8_t* rids = reinterpret_cast<uint8_t*>(codes + Npad);       // [Npad] shift region id per token
+  float* tab = reinterpret_cast<float*>(rids + Npad);             // [L] bias table column * log2(e)
+  __shared__ int s_need_mask;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -40,40 +54,55 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParam
   const __nv_bfloat16* qbase = p.qkv + row0 * ld + head * AT_HD;
   const __nv_bfloat16* kbase = qbase + p.C;
   const __nv_bfloat16* vbase = qbase + 2 * p.C;
-  const bool masked = (p.win.sd | p.win.sh | p.win.sw) != 0;
-  const int ntiles = (N + AT_KV - 1) / AT_KV;
+  const bool shifted = (p.win.sd | p.win.sh | p.win.sw) != 0;
+  const int ntiles = (N + KVT - 1) / KVT;
 
   auto load_tile = [&](int tile, int buf) {
-    // 64 keys x 4 chunks for K and V = 512 16-byte copies
-    for (int i = threadIdx.x; i < 2 * AT_KV * 4; i += THREADS) {
-      const int isv = i >= AT_KV * 4;
-      const int j = isv ? i - AT_KV * 4 : i;
+    for (int i = threadIdx.x; i < 2 * KVT * 4; i += THREADS) {
+      const int isv = i >= KVT * 4;
+      const int j = isv ? i - KVT * 4 : i;
       const int r = j >> 2, c = j & 3;
-      const int key = tile * AT_KV + r;
+      const int key = tile * KVT + r;
       const bool ok = key < N;
       const __nv_bfloat16* src = (isv ? vbase : kbase) + static_cast<long long>(ok ? key : 0) * ld + c * 8;
-      uint8_t* dst = (isv ? vs : ks) + buf * AT_KV * 64 + kv_off(r, c);
+      uint8_t* dst = (isv ? vs : ks) + buf * KVT * 64 + kv_off(r, c);
       cp_async_16(dst, src, ok);
     }
   };
 
+  if (threadIdx.x == 0) s_need_mask = 0;
   load_tile(0, 0);
   cp_async_commit();
+  __syncthreads();
 
   // per-token relative-position code and mask region (same for every head / q-tile of this window)
-  for (int i = threadIdx.x; i < N; i += THREADS) {
-    const WinTok tk = win_token(p.win, row0 + i);
-    info[i] = tk.code | (tk.rid << 16);
+  {
+    int differs = 0;
+    int rid0 = 0;
+    if (shifted) rid0 = win_token(p.win, row0).rid;
+    for (int i = threadIdx.x; i < Npad; i += THREADS) {
+      if (i < N) {
+        const WinTok tk = win_token(p.win, row0 + i);
+        codes[i] = static_cast<uint16_t>(tk.code);
+        rids[i] = static_cast<uint8_t>(tk.rid);
+        differs |= (tk.rid != rid0);
+      } else {
+        codes[i] = 0;
+        rids[i] = 0;
+      }
+    }
+    if (shifted && differs) s_need_mask = 1;     // benign race: every writer stores 1
   }
-  for (int i = threadIdx.x; i < p.L; i += THREADS) tab[i] = __ldg(p.table + static_cast<long long>(i) * p.nH + head);
+  for (int i = threadIdx.x; i < p.L; i += THREADS) tab[i] = __ldg(p.table + static_cast<long long>(i) * p.nH + head) * AT_LOG2E;
   const int rc = rel_const(p.win);
 
   // Q fragments (A operand, 16 rows x 32 d = 2 k-steps), straight from global
   uint32_t qf[2][4];
   const int qr0 = q0 + warp * 16 + g, qr1 = qr0 + 8;
+  const int qc0 = min(qr0, N - 1), qc1 = min(qr1, N - 1);
   {
-    const __nv_bfloat16* r0p = qbase + static_cast<long long>(min(qr0, N - 1)) * ld;
-    const __nv_bfloat16* r1p = qbase + static_cast<long long>(min(qr1, N - 1)) * ld;
+    const __nv_bfloat16* r0p = qbase + static_cast<long long>(qc0) * ld;
+    const __nv_bfloat16* r1p = qbase + static_cast<long long>(qc1) * ld;
 #pragma unroll
     for (int ksb = 0; ksb < 2; ++ksb) {
       qf[ksb][0] = __ldg(reinterpret_cast<const uint32_t*>(r0p + ksb * 16 + 2 * t));
@@ -82,16 +111,17 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParam
       qf[ksb][3] = __ldg(reinterpret_cast<const uint32_t*>(r1p + ksb * 16 + 8 + 2 * t));
     }
   }
-  __syncthreads();   // info / tab visible
-  const int iq0 = info[min(qr0, N - 1)], iq1 = info[min(qr1, N - 1)];
-  const int cq0 = (iq0 & 0xffff) + rc, cq1 = (iq1 & 0xffff) + rc;
-  const int rq0 = iq0 >> 16, rq1 = iq1 >> 16;
+  __syncthreads();   // codes / rids / tab / s_need_mask visible
+  const bool need_mask = s_need_mask != 0;
+  const float* tq0 = tab + (static_cast<int>(codes[qc0]) + rc);    // bias(i, j) = tq[-code(j)]
+  const float* tq1 = tab + (static_cast<int>(codes[qc1]) + rc);
+  const int rq0 = rids[qc0], rq1 = rids[qc1];
+  constexpr float MASKV = -100.0f * AT_LOG2E;
 
   float o[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  constexpr float LOG2E = 1.4426950408889634f;
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
@@ -100,59 +130,74 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParam
     cp_async_wait<1>();
     __syncthreads();
 
-    const uint8_t* kt = ks + buf * AT_KV * 64;
-    const uint8_t* vt = vs + buf * AT_KV * 64;
-    float s[8][4];
+    const uint8_t* kt = ks + buf * KVT * 64;
+    const uint8_t* vt = vs + buf * KVT * 64;
+    const int kv0 = tile * KVT;
+    // accumulators start from the relative-position bias: S = bias + q k^T
+    float s[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int nt = 0; nt < NT; ++nt) {
+      const int key = kv0 + nt * 8 + 2 * t;          // even; codes[] is zero-padded to a multiple of 8 past N
+      const int kc = min(key, Npad - 2);
+      const uint32_t cc = *reinterpret_cast<const uint32_t*>(codes + kc);
+      const int c0 = cc & 0xffff, c1 = cc >> 16;
+      s[nt][0] = tq0[-c0];
+      s[nt][1] = tq0[-c1];
+      s[nt][2] = tq1[-c0];
+      s[nt][3] = tq1[-c1];
+    }
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int key = kv0 + nt * 8 + 2 * t;
+        const int kc = min(key, Npad - 2);
+        const uint32_t rr = *reinterpret_cast<const uint16_t*>(rids + kc);
+        const int r0 = rr & 0xff, r1 = rr >> 8;
+        if (r0 != rq0) s[nt][0] += MASKV;
+        if (r1 != rq0) s[nt][1] += MASKV;
+        if (r0 != rq1) s[nt][2] += MASKV;
+        if (r1 != rq1) s[nt][3] += MASKV;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
       uint32_t kf[4];
       ldmatrix_x4(kf, kt + kv_off(nt * 8 + (lane & 7), lane >> 3));
       mma_bf16_16816(s[nt], qf[0], kf[0], kf[1]);
       mma_bf16_16816(s[nt], qf[1], kf[2], kf[3]);
     }
-    // bias + mask + key padding
-    const int kv0 = tile * AT_KV;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (kv0 + KVT > N) {          // only the last tile can contain padded keys
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = kv0 + nt * 8 + 2 * t + e;
-        if (key < N) {
-          const int ik = info[key];
-          const int ck = ik & 0xffff, rk = ik >> 16;
-          float a = s[nt][e] + tab[cq0 - ck];
-          float b = s[nt][2 + e] + tab[cq1 - ck];
-          if (masked) {
-            if (rk != rq0) a -= 100.0f;
-            if (rk != rq1) b -= 100.0f;
+        for (int e = 0; e < 2; ++e) {
+          if (kv0 + nt * 8 + 2 * t + e >= N) {
+            s[nt][e] = -INFINITY;
+            s[nt][2 + e] = -INFINITY;
           }
-          s[nt][e] = a;
-          s[nt][2 + e] = b;
-          mx0 = fmaxf(mx0, a);
-          mx1 = fmaxf(mx1, b);
-        } else {
-          s[nt][e] = -INFINITY;
-          s[nt][2 + e] = -INFINITY;
         }
       }
+    }
+    float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);
-    const float c0 = exp2f((m0 - nm0) * LOG2E), c1 = exp2f((m1 - nm1) * LOG2E);
+    const float c0 = ex2f(m0 - nm0), c1 = ex2f(m1 - nm1);
     m0 = nm0;
     m1 = nm1;
-    const float ms0 = nm0 * LOG2E, ms1 = nm1 * LOG2E;
     float rs0 = 0.f, rs1 = 0.f;
-    uint32_t pf[4][4];
+    uint32_t pf[KS][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] * LOG2E - ms0), p1 = exp2f(s[nt][1] * LOG2E - ms0);
-      const float p2 = exp2f(s[nt][2] * LOG2E - ms1), p3 = exp2f(s[nt][3] * LOG2E - ms1);
+    for (int nt = 0; nt < NT; ++nt) {
+      const float p0 = ex2f(s[nt][0] - nm0), p1 = ex2f(s[nt][1] - nm0);
+      const float p2 = ex2f(s[nt][2] - nm1), p3 = ex2f(s[nt][3] - nm1);
       rs0 += p0 + p1;
       rs1 += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -165,7 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParam
       o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1;
     }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {        // 16 keys per step
+    for (int kk = 0; kk < KS; ++kk) {       // 16 keys per step
 #pragma unroll
       for (int dp = 0; dp < 2; ++dp) {      // two d-chunks (8 each) per ldmatrix.x4
         uint32_t vf[4];
@@ -192,12 +237,13 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_kernel(const AttnParam
   }
 }
 
-template <int WARPS>
+template <int WARPS, int KVT>
 static int launch_attn(const AttnParams& p, long long nwin, cudaStream_t st) {
   const int N = p.win.N;
-  const size_t smem = 4 * AT_KV * 64 + static_cast<size_t>((N + 3) & ~3) * 4 + static_cast<size_t>(p.L) * 4;
+  const int Npad = (N + 7) & ~7;
+  const size_t smem = 4 * KVT * 64 + static_cast<size_t>(Npad) * 3 + static_cast<size_t>(p.L) * 4 + 16;
   LAVT_REQUIRE(smem <= 200 * 1024, "attention: window too large for shared memory (N=%d, L=%d)", N, p.L);
-  auto kfn = window_attn_kernel<WARPS>;
+  auto kfn = window_attn_kernel<WARPS, KVT>;
   static size_t configured = 0;
   if (smem > configured) {
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -219,8 +265,23 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
   LAVT_REQUIRE(g.N <= g.Wd * g.Wh * g.Ww, "attention: effective window larger than configured window");
   const long long nwin = 1LL * g.B * g.nwd * g.nwh * g.nww;
   LAVT_REQUIRE(nwin > 0 && nwin < 65536, "attention: window count %lld out of range", nwin);
-  if (g.N <= 64) return launch_attn<4>(p, nwin, st);
-  return launch_attn<8>(p, nwin, st);
+  // tile shape = the candidate with the least padded (query rows x keys) work
+  struct Cand { int bq, kvt; };
+  const Cand cands[4] = {{128, 64}, {80, 80}, {64, 64}, {112, 48}};
+  int best = 0;
+  long long best_work = -1;
+  for (int i = 0; i < 4; ++i) {
+    const long long qpad = 1LL * ((g.N + cands[i].bq - 1) / cands[i].bq) * cands[i].bq;
+    const long long kpad = 1LL * ((g.N + cands[i].kvt - 1) / cands[i].kvt) * cands[i].kvt;
+    const long long work = qpad * kpad;
+    if (best_work < 0 || work < best_work) { best_work = work; best = i; }
+  }
+  switch (best) {
+    case 0: return launch_attn<8, 64>(p, nwin, st);
+    case 1: return launch_attn<5, 80>(p, nwin, st);
+    case 2: return launch_attn<4, 64>(p, nwin, st);
+    default: return launch_attn<7, 48>(p, nwin, st);
+  }
 }
 
 }  // namespace lavt

@@ -8,62 +8,87 @@
 // PatchMerging.reduction (:309), PatchEmbed3D.proj (:627), the PWAM 1x1 convs (:900-973),
 // LanguageGate (:519-525) and the SimpleDecoding conv3x3+BN+ReLU stack (lib/mask_predictor.py:56-87).
 //
-// Structure (one 128 x BLOCK_N output tile per CTA, 256 threads):
-//   warp 0   : TMA producer  (one elected lane)   smem ring of STAGES x {A 128x64, B BLOCK_Nx64} bf16,
-//                                                  128-byte swizzle, mbarrier full/empty pairs
-//   warp 1   : MMA issuer    (one elected lane)   tcgen05.mma.cta_group::1.kind::f16, D in TMEM
-//   warp 2   : TMEM allocator / deallocator
-//   warps 4-7: epilogue       tcgen05.ld 32x32b -> registers -> fused math -> vectorised global stores
+// Structure: PERSISTENT, one CTA per SM, 384 threads, tiles of 128 x 128 handed out round-robin
+// (N fastest, so concurrently running CTAs share the same A rows through L2):
+//   warp 0    : TMA producer (one lane) -- smem ring of STAGES x {A 128x64, B 128x64} bf16, 128-byte swizzle,
+//               mbarrier full/empty pairs; the ring streams straight across tile boundaries
+//   warp 1    : MMA issuer (one lane)   -- tcgen05.mma.cta_group::1.kind::f16 into one of TWO TMEM accumulators
+//   warp 2    : TMEM allocator (256 columns)
+//   warps 4-7 : epilogue warpgroup 0 (even local tiles, accumulator 0)
+//   warps 8-11: epilogue warpgroup 1 (odd local tiles, accumulator 1)
+// so the epilogue of tile i (tcgen05.ld -> fused math -> global stores) overlaps the MMAs of tiles i+1, i+2.
 #include "common.cuh"
 #include "gemm_tc.cuh"
+
+#include <cstdlib>
 
 namespace lavt {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;            // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 256;
 
-template <int BN, int STAGES>
+// GEMM_BN columns per tile, GEMM_STAGES smem ring slots, EPI_WGS epilogue warpgroups (1 -> 256 threads, 2 CTAs/SM;
+// 2 -> 384 threads, 1 CTA/SM).  Two TMEM accumulators of GEMM_BN columns in every configuration.
+template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  // after the ring: barriers, tmem pointer, epilogue vectors
-  static constexpr int BAR_OFF = RING_BYTES;
-  static constexpr int VEC_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = VEC_OFF + 2 * BN * 4 + 1024 /*alignment slack*/;
+  static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = RING_BYTES;                  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int VEC_OFF = BAR_OFF + 256;               // per epilogue warpgroup: scale[BN], bias[BN]
+  static constexpr int TOTAL = VEC_OFF + EPI_WGS * 2 * GEMM_BN * 4 + 1024 /*alignment slack*/;
+  static constexpr int THREADS = 128 + 128 * EPI_WGS;
+  static constexpr int MIN_CTAS = (EPI_WGS == 1) ? 2 : 1;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exact-erf GELU (nn.GELU default): erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), 2 MUFU + ~12 FMA-pipe ops
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2_approx(-ax * ax * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+// tanh(x) = 1 - 2 / (exp(2x) + 1), abs error ~1e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);
+  return fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
+}
+
+template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS>
+__global__ void __launch_bounds__(GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::THREADS, GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::MIN_CTAS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
-  using L = GemmSmem<BN, STAGES>;
+                    const GemmParams p, const int m_tiles) {
+  using L = GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(smem + L::VEC_OFF);
-  float* s_bias = s_scale + BN;
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int mt = blockIdx.y;
-
-  // conv tile decomposition
-  int img = 0, h0 = 0, w0 = 0;
-  if (p.rowmap == ROWMAP_CONV) {
-    int tw = mt % p.cTilesW;
-    int th = (mt / p.cTilesW) % p.cTilesH;
-    img = mt / (p.cTilesW * p.cTilesH);
-    h0 = th * p.cTH;
-    w0 = tw * p.cTW;
-  }
+  const int n_tiles = p.N / GEMM_BN;
+  const int total_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
@@ -71,15 +96,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);      // one arrive per epilogue warp of the owning warpgroup
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, BN);   // BN fp32 accumulator columns (power of two >= 32)
+    tmem_alloc(tmem_ptr_smem, 2 * GEMM_BN);  // two fp32 accumulators of 128 columns
   }
   tc_fence_before();
   __syncthreads();
@@ -89,156 +117,240 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int cpb = (p.rowmap == ROWMAP_CONV) ? (p.cCin / GEMM_BK) : 1;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if (p.rowmap == ROWMAP_CONV) {
-          const int tap = kb / cpb, cc = kb - tap * cpb;
-          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
-        } else {
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
+      const bool conv = (p.rowmap == ROWMAP_CONV);
+      const int cpb = conv ? (p.cCin / GEMM_BK) : 1;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles;
+        const int n0 = (tile - mt * n_tiles) * GEMM_BN;
+        int img = 0, h0 = 0, w0 = 0;
+        if (conv) {
+          const int tw = mt % p.cTilesW;
+          const int th = (mt / p.cTilesW) % p.cTilesH;
+          img = mt / (p.cTilesW * p.cTilesH);
+          h0 = th * p.cTH;
+          w0 = tw * p.cTW;
         }
-        tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          const uint32_t ph = (it / GEMM_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (conv) {
+            const int tap = kb / cpb, cc = kb - tap * cpb;
+            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+            tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t use = static_cast<uint32_t>(lt >> 1);
+        mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
-        const uint64_t da = make_kmajor_sw128_desc(sa);
-        const uint64_t db = make_kmajor_sw128_desc(sb);
+        const uint32_t tmem_d = tmem_base + acc * GEMM_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          const uint32_t ph = (it / GEMM_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t da = make_kmajor_sw128_desc(sa);
+          const uint64_t db = make_kmajor_sw128_desc(sb);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-          umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+        umma_commit(&tmem_full_bar[acc]);      // accumulator complete
       }
-      umma_commit(tmem_full_bar);            // accumulator complete
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int et = threadIdx.x - 128;
-    for (int i = et; i < BN; i += 128) {
-      s_scale[i] = p.cscale ? p.cscale[n0 + i] : 1.0f;
-      s_bias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+    // ===================== epilogue warpgroups =====================
+    const int wg = (warp - 4) >> 2;            // epilogue warpgroup: local tiles with lt % EPI_WGS == wg
+    const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32)
+    const int et = threadIdx.x - 128 - wg * 128;
+    float* s_scale = reinterpret_cast<float*>(smem + L::VEC_OFF) + wg * 2 * GEMM_BN;
+    float* s_bias = s_scale + GEMM_BN;
+    const int r = ew * 32 + lane;              // row inside the tile
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt % EPI_WGS) != wg) continue;
+      const int acc = lt & 1;
+      const uint32_t use = static_cast<uint32_t>(lt >> 1);
+      const int mt = tile / n_tiles;
+      const int n0 = (tile - mt * n_tiles) * GEMM_BN;
 
-    const int r = ew * 32 + lane;            // row inside the tile
-    long long m = -1, orow = -1;
-    if (p.rowmap == ROWMAP_CONV) {
-      const int h = h0 + r / p.cTW, w = w0 + r % p.cTW;
-      if (h < p.cH && w < p.cW) {
-        m = (static_cast<long long>(img) * p.cH + h) * p.cW + w;
-        orow = m;
+      // previous tile's readers of s_scale / s_bias are done -> refill for this tile's columns
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+      for (int i = et; i < GEMM_BN; i += 128) {
+        s_scale[i] = p.cscale ? __ldg(p.cscale + n0 + i) : 1.0f;
+        s_bias[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.0f;
       }
-    } else {
-      const long long mm = static_cast<long long>(mt) * GEMM_BM + r;
-      if (mm < p.M) {
-        m = mm;
-        orow = (p.rowmap == ROWMAP_WINDOW) ? win_token(p.win, mm).row : mm;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+
+      long long m = -1, orow = -1;
+      if (p.rowmap == ROWMAP_CONV) {
+        const int tw = mt % p.cTilesW;
+        const int th = (mt / p.cTilesW) % p.cTilesH;
+        const int img = mt / (p.cTilesW * p.cTilesH);
+        const int h = th * p.cTH + r / p.cTW, w = tw * p.cTW + r % p.cTW;
+        if (h < p.cH && w < p.cW) {
+          m = (static_cast<long long>(img) * p.cH + h) * p.cW + w;
+          orow = m;
+        }
+      } else {
+        const long long mm = static_cast<long long>(mt) * GEMM_BM + r;
+        if (mm < p.M) {
+          m = mm;
+          orow = (p.rowmap == ROWMAP_WINDOW) ? win_token(p.win, mm).row : mm;
+        }
       }
-    }
-    const bool live = (orow >= 0);
+      const bool live = (orow >= 0);
+      const __nv_bfloat16* mul_row = (p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
+      const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
+      float* of_row = (p.out_f32 && live) ? p.out_f32 + orow * p.ldo + n0 : nullptr;
+      __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-    const __nv_bfloat16* mul_row = (p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
-    const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
-    float* of_row = (p.out_f32 && live) ? p.out_f32 + orow * p.ldo + n0 : nullptr;
-    __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
+      mbar_wait(&tmem_full_bar[acc], use & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
 
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + c * 32;
-      tmem_ld_32x32b_x32(taddr, v);          // warp-collective: executed by all lanes
-      tmem_ld_wait();
-      if (!live) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]) * s_scale[c * 32 + j] + s_bias[c * 32 + j];
-        if (p.act == ACT_GELU) x = gelu_erf(x);
-        else if (p.act == ACT_RELU) x = fmaxf(x, 0.0f);
-        else if (p.act == ACT_TANH) x = tanhf(x);
-        f[j] = x;
-      }
-      if (mul_row) {
-        const uint4* mp = reinterpret_cast<const uint4*>(mul_row + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u = __ldg(mp + q);
-          float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-          f[q * 8 + 0] *= a.x; f[q * 8 + 1] *= a.y; f[q * 8 + 2] *= b.x; f[q * 8 + 3] *= b.y;
-          f[q * 8 + 4] *= cc2.x; f[q * 8 + 5] *= cc2.y; f[q * 8 + 6] *= d.x; f[q * 8 + 7] *= d.y;
+      for (int c = 0; c < GEMM_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tbase + c * 32, v);          // warp-collective: executed by all lanes
+        tmem_ld_wait();
+        if (c == GEMM_BN / 32 - 1) {
+          // last read of this accumulator: hand it back to the MMA warp before finishing the math / stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-      }
-      if (res_row) {
-        const float4* rp = reinterpret_cast<const float4*>(res_row + c * 32);
+        if (!live) continue;
+        float f[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 u = __ldg(rp + q);
-          f[q * 4 + 0] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c * 32 + j], s_bias[c * 32 + j]);
+        if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        } else if (p.act == ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
         }
-      }
-      if (of_row) {
-        float4* op = reinterpret_cast<float4*>(of_row + c * 32);
+        if (mul_row) {
+          const uint4* mp = reinterpret_cast<const uint4*>(mul_row + c * 32);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-      }
-      if (ob_row) {
-        uint4* op = reinterpret_cast<uint4*>(ob_row + c * 32);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(mp + q);
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            f[q * 8 + 0] *= a.x; f[q * 8 + 1] *= a.y; f[q * 8 + 2] *= b.x; f[q * 8 + 3] *= b.y;
+            f[q * 8 + 4] *= cc2.x; f[q * 8 + 5] *= cc2.y; f[q * 8 + 6] *= d.x; f[q * 8 + 7] *= d.y;
+          }
+        }
+        if (res_row) {
+          const float4* rp = reinterpret_cast<const float4*>(res_row + c * 32);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          op[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                             pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+          for (int q = 0; q < 8; ++q) {
+            const float4 u = __ldg(rp + q);
+            f[q * 4 + 0] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
+          }
+        }
+        if (of_row) {
+          float4* op = reinterpret_cast<float4*>(of_row + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+        }
+        if (ob_row) {
+          uint4* op = reinterpret_cast<uint4*>(ob_row + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            op[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                               pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+        }
       }
     }
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * GEMM_BN);
   }
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
-                       cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES, int EPI_WGS>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES, EPI_WGS>;
+  auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS>;
   static bool configured = false;
-  auto kfn = gemm_bf16_tc_kernel<BN, STAGES>;
   if (!configured) {
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  dim3 grid(p.N / BN, m_tiles, 1);
-  kfn<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  const long long total = 1LL * m_tiles * (p.N / BN);
+  LAVT_REQUIRE(total < (1LL << 30), "gemm: too many tiles (%lld)", total);
+  const long long slots = 1LL * sm_count() * L::MIN_CTAS;
+  const int grid = static_cast<int>(total < slots ? total : slots);
+  kfn<<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, p, m_tiles);
   LAVT_LAUNCH_CHECK("gemm_bf16_tc_kernel");
   return LAVT_OK;
+}
+
+// 0: 128-wide tiles, 6 stages, two epilogue warpgroups, 1 CTA/SM
+// 1: 128-wide tiles, 3 stages, one epilogue warpgroup, 2 CTAs/SM
+// 2: 256-wide tiles, 4 stages, two epilogue warpgroups, 1 CTA/SM (N % 256 == 0)
+static int gemm_variant(const GemmParams& p) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("LAVT_GEMM_VARIANT");
+    forced = e ? atoi(e) : -1;
+  }
+  int v;
+  if (forced >= 0) {
+    v = forced;
+  } else {
+    // measured on B200 (tools/bench_gemm.py): 256-wide tiles halve the B-operand smem traffic per FLOP and win
+    // whenever they still fill the machine; 2 CTAs/SM wins for long K at N = 128; otherwise the 1-CTA/SM pipeline
+    const long long m_tiles = (p.rowmap == ROWMAP_CONV) ? (1LL * (p.M / (p.cH * p.cW)) * p.cTilesH * p.cTilesW)
+                                                        : ((p.M + GEMM_BM - 1) / GEMM_BM);
+    if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= sm_count() / 2) v = 2;
+    else v = (p.K >= 1024) ? 1 : 0;
+  }
+  if (v == 2 && (p.N % 256) != 0) v = 0;
+  return v;
 }
 
 int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, const GemmParams& p,
@@ -275,13 +387,14 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t strides[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {GEMM_BK, 128};
+    uint32_t box[2] = {GEMM_BK, gemm_variant(p) == 2 ? 256u : 128u};
     int rc = make_tmap_bf16(&tmB, Bw, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  LAVT_REQUIRE(m_tiles <= 65535 * 16, "gemm: too many M tiles (%d)", m_tiles);
-  if (p.K <= 2 * GEMM_BK) return launch_gemm<128, 2>(tmA, tmB, p, m_tiles, stream);
-  return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
+  const int variant = gemm_variant(p);
+  if (variant == 1) return launch_gemm<128, 3, 1>(tmA, tmB, p, m_tiles, stream);
+  if (variant == 2) return launch_gemm<256, 4, 2>(tmA, tmB, p, m_tiles, stream);
+  return launch_gemm<128, 6, 2>(tmA, tmB, p, m_tiles, stream);
 }
 
 }  // namespace lavt

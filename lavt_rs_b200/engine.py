@@ -108,10 +108,11 @@ def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shi
     hd = C // nH
 
     qkv_w = pw.get("qkv_w", [blk.attn.qkv.weight], lambda: _bf16(blk.attn.qkv.weight))
-    # q columns are scaled by head_dim^-0.5 in the epilogue: (acc + b) * s == acc * s + b * s  (:147)
+    # q columns are scaled by head_dim^-0.5 (:147) times log2(e) in the epilogue -- the attention kernel's softmax
+    # runs in base 2:  (acc + b) * s == acc * s + b * s
     def _qscale():
         s = torch.ones(3 * C, device=dev, dtype=torch.float32)
-        s[:C] = hd ** -0.5
+        s[:C] = hd ** -0.5 * 1.4426950408889634
         b = _f32(blk.attn.qkv.bias) * s if blk.attn.qkv.bias is not None else torch.zeros(3 * C, device=dev)
         return s, b
     qkv_s, qkv_b = pw.get("qkv_sb", [blk.attn.qkv.weight] + ([blk.attn.qkv.bias] if blk.attn.qkv.bias is not None else []), _qscale)
