@@ -107,9 +107,9 @@ int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, 
 
 /* ---- window attention core (lib/video_swin_transformer.py:147-165) ----
  * qkv: bf16 [B*nW*N, 3C] in window order, q already scaled by head_dim^-0.5 * log2(e) (the softmax is evaluated in
- * base 2; fold the factor into the qkv GEMM epilogue via cscale); table: fp32 [L, nH]
- * (relative_position_bias_table); out: bf16 [B*nW*N, C].  head_dim must be 32. */
-int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
+ * base 2; fold the factor into the qkv GEMM epilogue via cscale); table_t: fp32 [nH, L] = the module's
+ * relative_position_bias_table [L, nH] transposed; out: bf16 [B*nW*N, C].  head_dim must be 32. */
+int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
                           void* out_bf16, void* stream);
 
 /* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */

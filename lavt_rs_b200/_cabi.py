@@ -168,17 +168,27 @@ class KernelTimer:
         ev.record()
         return ev
 
-    def end(self, start, family: str, flops: float, nbytes: float):
+    def end(self, start, family: str, flops: float, nbytes: float, tag: str = ""):
         if start is None:
             return
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
-        self.records.append((family, flops, nbytes, start, ev))
+        self.records.append((family, flops, nbytes, start, ev, tag))
+
+    def by_tag(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, nb, s, e, tag in self.records:
+            d = out.setdefault((fam, tag), {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for fam, fl, nb, s, e in self.records:
+        for fam, fl, nb, s, e, _tag in self.records:
             d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
@@ -202,7 +212,7 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
     t0 = TIMER.begin()
     check(lib().lavt_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
                                C.byref(e), stream_ptr()), "lavt_gemm_bf16")
-    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N))
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N), f"M{M} N{N} K{K} act{e.act}")
 
 
 def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
@@ -218,7 +228,8 @@ def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
     check(lib().lavt_conv3x3_bf16(x_nhwc.data_ptr(), Cin, n_img, H, W, Cin, w_taps.data_ptr(), Cout,
                                   C.byref(e), stream_ptr()), "lavt_conv3x3_bf16")
     npix = n_img * H * W
-    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * npix * Cout * 9 * Cin, 2.0 * (npix * Cin + Cout * 9 * Cin + npix * Cout))
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * npix * Cout * 9 * Cin, 2.0 * (npix * Cin + Cout * 9 * Cin + npix * Cout),
+              f"conv {n_img}x{H}x{W} Cin{Cin} Cout{Cout}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -277,16 +288,18 @@ def patch_embed_im2col(x: torch.Tensor, out_bf16: torch.Tensor) -> None:
           "lavt_patch_embed_im2col")
 
 
-def window_attention(qkv: torch.Tensor, table: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor) -> None:
+def window_attention(qkv: torch.Tensor, table_t: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor) -> None:
+    """table_t: relative_position_bias_table transposed to [nH, L] fp32."""
     _c(qkv, torch.bfloat16, "qkv")
-    _c(table, torch.float32, "table")
-    L, nH = table.shape
+    _c(table_t, torch.float32, "table_t")
+    nH, L = table_t.shape
     t0 = TIMER.begin()
-    check(lib().lavt_window_attention(qkv.data_ptr(), table.data_ptr(), L, nH, C.byref(geom),
+    check(lib().lavt_window_attention(qkv.data_ptr(), table_t.data_ptr(), L, nH, C.byref(geom),
                                       _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
           "lavt_window_attention")
     rows = geom.rows()
-    TIMER.end(t0, "window_attn_kernel", 4.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 4)
+    TIMER.end(t0, "window_attn_kernel", 4.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 4,
+              f"rows{rows} N{geom.N} nH{nH} shift{geom.sh}")
 
 
 def instnorm_workspace_floats(B: int, n: int, Cn: int) -> int:

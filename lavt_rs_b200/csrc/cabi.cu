@@ -132,13 +132,13 @@ int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, 
   return im2col_patch4_dispatch(x, stride_b, stride_c, stride_t, MB(out_bf16), B, T, H, W, S(stream));
 }
 
-int lavt_window_attention(const void* qkv, const float* table, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
+int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
                           void* out_bf16, void* stream) {
   LAVT_REQUIRE(geom != nullptr, "attention: geometry is NULL");
   AttnParams p;
   std::memset(&p, 0, sizeof(p));
   std::memcpy(&p.win, geom, sizeof(WinGeom));
-  p.qkv = CB(qkv); p.table = table; p.out = MB(out_bf16); p.nH = nH; p.C = nH * 32; p.L = L;
+  p.qkv = CB(qkv); p.table_t = table_t; p.out = MB(out_bf16); p.nH = nH; p.C = nH * 32; p.L = L;
   return window_attn_dispatch(p, S(stream));
 }
 

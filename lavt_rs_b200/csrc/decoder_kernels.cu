@@ -73,33 +73,43 @@ int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, 
   return LAVT_OK;
 }
 
-// warp per pixel: logits[pix, o] = sum_c y[pix, c] * w[o, c] + b[o], o in {0, 1}
+// 8 lanes per pixel (4 pixels per warp): logits[pix, o] = sum_c y[pix, c] * w[o, c] + b[o], o in {0, 1}; w staged in smem
 __global__ void __launch_bounds__(256) conv1x1_logits_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w,
                                                              const float* __restrict__ b, float* __restrict__ out, long long npix,
                                                              int C) {
-  const int lane = threadIdx.x & 31;
-  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= npix) return;
+  extern __shared__ float sw[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const bool live = pix < npix;
   float a0 = 0.f, a1 = 0.f;
-  for (int c = lane * 8; c < C; c += 256) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + pix * C + c));
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  if (live) {
+    const __nv_bfloat16* row = y + pix * C;
+    for (int c = sub * 8; c < C; c += 64) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(uu[j]);
-      a0 = fmaf(f.x, __ldg(w + c + 2 * j), fmaf(f.y, __ldg(w + c + 2 * j + 1), a0));
-      a1 = fmaf(f.x, __ldg(w + C + c + 2 * j), fmaf(f.y, __ldg(w + C + c + 2 * j + 1), a1));
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(uu[j]);
+        a0 = fmaf(f.x, sw[c + 2 * j], fmaf(f.y, sw[c + 2 * j + 1], a0));
+        a1 = fmaf(f.x, sw[C + c + 2 * j], fmaf(f.y, sw[C + c + 2 * j + 1], a1));
+      }
     }
   }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  if (lane == 0) *reinterpret_cast<float2*>(out + pix * 2) = make_float2(a0 + b[0], a1 + b[1]);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (live && sub == 0) *reinterpret_cast<float2*>(out + pix * 2) = make_float2(a0 + b[0], a1 + b[1]);
 }
 
 int conv1x1_logits_dispatch(const __nv_bfloat16* y, const float* w, const float* b, float* out, long long npix, int C,
                             cudaStream_t st) {
-  LAVT_REQUIRE(npix > 0 && C % 8 == 0, "conv1x1: bad shape");
-  conv1x1_logits_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, st>>>(y, w, b, out, npix, C);
+  LAVT_REQUIRE(npix > 0 && C % 8 == 0 && C <= 4096, "conv1x1: bad shape");
+  const long long threads = npix * 8;
+  conv1x1_logits_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 2 * C * sizeof(float), st>>>(y, w, b, out, npix, C);
   LAVT_LAUNCH_CHECK("conv1x1_logits_kernel");
   return LAVT_OK;
 }

@@ -30,7 +30,7 @@ int pwam_mul_dispatch(const __nv_bfloat16* vis, const float* lang, const float* 
 
 struct AttnParams {
   const __nv_bfloat16* qkv;   // [rows, 3C]: q | k | v, each [nH][32]
-  const float* table;         // [L, nH] relative_position_bias_table
+  const float* table_t;       // [nH, L] relative_position_bias_table, transposed (coalesced per-head reads)
   __nv_bfloat16* out;         // [rows, C]
   int C, nH, L;
   WinGeom win;

@@ -172,7 +172,7 @@ int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long
 // pass 1: per-chunk sums of (x - pivot) and (x - pivot)^2 (pivot = token 0 of the clip, kills the
 //         E[x^2]-E[x]^2 cancellation);  pass 2: deterministic reduction over chunks -> mean, rstd.
 // ---------------------------------------------------------------------------------------------
-constexpr int CS_ROWS_PER_BLOCK = 512;
+constexpr int CS_ROWS_PER_BLOCK = 256;
 
 __global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __restrict__ x, float* __restrict__ part,
                                                                int n, int C, int chunks) {
@@ -188,7 +188,19 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __re
   const int r0 = chunk * CS_ROWS_PER_BLOCK;
   const int r1 = min(n, r0 + CS_ROWS_PER_BLOCK);
   if (tr < rg) {
-    for (int r = r0 + tr; r < r1; r += rg) {
+    int r = r0 + tr;
+    for (; r + 3 * rg < r1; r += 4 * rg) {      // 4 independent 16-byte loads in flight per thread
+      float4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(r + k * rg) * C) + tc);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = u[k].x - pv.x, bb = u[k].y - pv.y, c = u[k].z - pv.z, d = u[k].w - pv.w;
+        s1.x += a; s1.y += bb; s1.z += c; s1.w += d;
+        s2.x += a * a; s2.y += bb * bb; s2.z += c * c; s2.w += d * d;
+      }
+    }
+    for (; r < r1; r += rg) {
       const float4 u = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(r) * C) + tc);
       const float a = u.x - pv.x, bb = u.y - pv.y, c = u.z - pv.z, d = u.w - pv.w;
       s1.x += a; s1.y += bb; s1.z += c; s1.w += d;

@@ -8,7 +8,8 @@
 
 namespace lavt {
 
-// grid (Nl, B), block 256: smem holds the word vector l[b, :, j]; each warp produces channels c = warp, warp+8, ...
+// grid (Nl, B, ceil(2C / 64)), block 256: smem holds the word vector l[b, :, j]; each warp produces 8 of the block's 64
+// outputs (k channels first, then v channels)
 __global__ void __launch_bounds__(256) pwam_kv_kernel(const float* __restrict__ l, const float* __restrict__ mask,
                                                       const float* __restrict__ wk, const float* __restrict__ bk,
                                                       const float* __restrict__ wv, const float* __restrict__ bv,
@@ -19,7 +20,9 @@ __global__ void __launch_bounds__(256) pwam_kv_kernel(const float* __restrict__ 
   __syncthreads();
   const float m = mask[b * Nl + j];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int c = warp; c < 2 * C; c += nw) {
+  const int cbeg = blockIdx.z * 64;
+  const int cend = min(2 * C, cbeg + 64);
+  for (int c = cbeg + warp; c < cend; c += nw) {
     const bool is_v = c >= C;
     const int cc = is_v ? c - C : c;
     const float* w = (is_v ? wv : wk) + static_cast<long long>(cc) * Lin;
@@ -37,7 +40,7 @@ int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const f
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st) {
   LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0, "pwam_kv: empty input");
   LAVT_REQUIRE(Lin * sizeof(float) <= 48 * 1024, "pwam_kv: language width %d too large", Lin);
-  pwam_kv_kernel<<<dim3(Nl, B), 256, Lin * sizeof(float), st>>>(l, mask, wk, bk, wv, bv, k, v, Nl, Lin, C);
+  pwam_kv_kernel<<<dim3(Nl, B, (2 * C + 63) / 64), 256, Lin * sizeof(float), st>>>(l, mask, wk, bk, wv, bv, k, v, Nl, Lin, C);
   LAVT_LAUNCH_CHECK("pwam_kv_kernel");
   return LAVT_OK;
 }

@@ -119,7 +119,8 @@ def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shi
     proj_w = pw.get("proj_w", [blk.attn.proj.weight], lambda: _bf16(blk.attn.proj.weight))
     fc1_w = pw.get("fc1_w", [blk.mlp.fc1.weight], lambda: _bf16(blk.mlp.fc1.weight))
     fc2_w = pw.get("fc2_w", [blk.mlp.fc2.weight], lambda: _bf16(blk.mlp.fc2.weight))
-    table = blk.attn.relative_position_bias_table
+    table_t = pw.get("table_t", [blk.attn.relative_position_bias_table],
+                     lambda: _f32(blk.attn.relative_position_bias_table.t()))
 
     # --- attention half: LN1 + shift + partition gather -> qkv GEMM -> window attention -> proj GEMM + scatter + residual
     xw = ws.get("xw", (rows, C), torch.bfloat16, dev)
@@ -127,7 +128,7 @@ def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shi
     qkv = ws.get("qkv", (rows, 3 * C), torch.bfloat16, dev)
     K.gemm_bf16(xw, qkv_w, cscale=qkv_s, bias=qkv_b, out_bf16=qkv)
     att = ws.get("att", (rows, C), torch.bfloat16, dev)
-    K.window_attention(qkv, table.detach(), geom, att)
+    K.window_attention(qkv, table_t, geom, att)
     K.gemm_bf16(att, proj_w, bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x, win=geom)
     # --- MLP half: LN2 -> fc1 + GELU -> fc2 + residual
     h1 = ws.get("ln2", (n, C), torch.bfloat16, dev)
