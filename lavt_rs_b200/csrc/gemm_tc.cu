@@ -65,6 +65,17 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = fmaf(-poly, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void ldg_v8(uint32_t* r, const void* p) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // tanh(x) = 1 - 2 / (exp(2x) + 1), abs error ~1e-7
 __device__ __forceinline__ float tanh_fast(float x) {
   const float e = ex2_approx(x * 2.8853900817779268f);
@@ -227,12 +238,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float* of_row = (p.out_f32 && live) ? p.out_f32 + orow * p.ldo + n0 : nullptr;
       __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
 
-      mbar_wait(&tmem_full_bar[acc], use & 1);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
+      bool acc_ready = false;
 
 #pragma unroll 1
       for (int c = 0; c < GEMM_BN / 32; ++c) {
+        // operands that do not depend on the accumulator are requested first (for c == 0: before the MMAs finish)
+        uint32_t rr[32];
+        if (res_row) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ldg_v8(&rr[q * 8], res_row + c * 32 + q * 8);
+        }
+        if (!acc_ready) {
+          mbar_wait(&tmem_full_bar[acc], use & 1);
+          tc_fence_after();
+          acc_ready = true;
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tbase + c * 32, v);          // warp-collective: executed by all lanes
         tmem_ld_wait();
@@ -257,34 +278,39 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
         }
         if (mul_row) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mul_row + c * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = __ldg(mp + q);
-            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-            f[q * 8 + 0] *= a.x; f[q * 8 + 1] *= a.y; f[q * 8 + 2] *= b.x; f[q * 8 + 3] *= b.y;
-            f[q * 8 + 4] *= cc2.x; f[q * 8 + 5] *= cc2.y; f[q * 8 + 6] *= d.x; f[q * 8 + 7] *= d.y;
+          for (int q = 0; q < 2; ++q) {
+            uint32_t u[8];
+            ldg_v8(u, mul_row + c * 32 + q * 16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 a = unpack_bf16x2(u[j]);
+              f[q * 16 + 2 * j] *= a.x;
+              f[q * 16 + 2 * j + 1] *= a.y;
+            }
           }
         }
         if (res_row) {
-          const float4* rp = reinterpret_cast<const float4*>(res_row + c * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 u = __ldg(rp + q);
-            f[q * 4 + 0] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
-          }
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(rr[j]);
         }
         if (of_row) {
-          float4* op = reinterpret_cast<float4*>(of_row + c * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          for (int q = 0; q < 4; ++q) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(f[q * 8 + j]);
+            stg_v8(of_row + c * 32 + q * 8, u);
+          }
         }
         if (ob_row) {
-          uint4* op = reinterpret_cast<uint4*>(ob_row + c * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            op[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                               pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+          for (int q = 0; q < 2; ++q) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(f[q * 16 + 2 * j], f[q * 16 + 2 * j + 1]);
+            stg_v8(ob_row + c * 32 + q * 16, u);
+          }
         }
       }
     }
@@ -358,10 +384,13 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
   LAVT_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   LAVT_REQUIRE(p.N % 128 == 0, "gemm: N=%d must be a multiple of 128", p.N);
   LAVT_REQUIRE(p.K % GEMM_BK == 0, "gemm: K=%d must be a multiple of 64", p.K);
-  LAVT_REQUIRE(p.ldo % 8 == 0 && p.ldo >= p.N, "gemm: ldo=%d invalid for N=%d", p.ldo, p.N);
+  LAVT_REQUIRE(p.ldo % 16 == 0 && p.ldo >= p.N, "gemm: ldo=%d invalid for N=%d (need a multiple of 16)", p.ldo, p.N);
+  LAVT_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) | reinterpret_cast<uintptr_t>(p.out_bf16) |
+                reinterpret_cast<uintptr_t>(p.resid) | reinterpret_cast<uintptr_t>(p.mul)) % 32 == 0,
+               "gemm: epilogue tensors must be 32-byte aligned");
   LAVT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
   LAVT_REQUIRE(p.out_f32 || p.out_bf16, "gemm: no output buffer");
-  LAVT_REQUIRE(!p.mul || p.ldm % 8 == 0, "gemm: ldm must be a multiple of 8");
+  LAVT_REQUIRE(!p.mul || p.ldm % 16 == 0, "gemm: ldm must be a multiple of 16");
 
   CUtensorMap tmA, tmB;
   int m_tiles;
