@@ -27,14 +27,18 @@ CASES = {
     "w7_t4_32": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=4, H=32, W=32, Nl=20, keep=(0, 1, 2, 3)),
     "w12_t2_48": dict(window=(8, 12, 12), depths=(2, 2, 2, 2), mha=(1, 2, 4, 8), B=2, T=2, H=48, W=48, Nl=9, keep=(1, 2, 3)),
     "w7_t16_32x40": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=16, H=32, W=40, Nl=22, keep=(2, 3)),
+    # 2-D image backbone (lib/backbone.py): window is an int, never clamped
+    "img_w12_60x76": dict(window=(1, 12, 12), depths=(2, 2, 2, 2), mha=(1, 1, 2, 2), B=2, T=1, H=60, W=76, Nl=20, keep=(1, 2, 3),
+                          image=True),
 }
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def case_inputs(c):
-    cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"])
+    image = c.get("image", False)
+    cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"], clamp_window=not image, video=not image)
     sd = O.random_state_dict(cfg, seed=0)
-    x, l, m = O.synthetic_inputs(c["B"], c["T"], c["H"], c["W"], Nl=c["Nl"], seed=1)
+    x, l, m = O.synthetic_inputs(c["B"], c["T"], c["H"], c["W"], Nl=c["Nl"], seed=1, video=not image)
     return cfg, sd, x, l, m
 
 
@@ -42,13 +46,16 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, c in CASES.items():
         cfg, sd, x, l, m = case_inputs(c)
-        bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"])
+        if c.get("image", False):
+            bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=c["window"][1], mha=c["mha"], depths=c["depths"])
+        else:
+            bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"])
         missing = bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=False)
         assert all(k.endswith("relative_position_index") for k in missing.missing_keys) and not missing.unexpected_keys, missing
         missing = dec.load_state_dict({k[len("classifier."):]: v for k, v in sd.items() if k.startswith("classifier.")}, strict=False)
         assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys, missing
         with torch.no_grad():
-            feats = bb(x.permute(0, 2, 1, 3, 4), l, m.unsqueeze(-1))          # reference forward
+            feats = bb(x if c.get("image", False) else x.permute(0, 2, 1, 3, 4), l, m.unsqueeze(-1))   # reference forward
             low = dec(feats[3], feats[2], feats[1], feats[0])
             logits = F.interpolate(low, size=(c["H"], c["W"]), mode="bilinear", align_corners=True)   # lib/_utils.py:106
         arrays = {"logits": logits.numpy(), "logits_lowres": low.numpy()}

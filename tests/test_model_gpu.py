@@ -161,3 +161,59 @@ def test_backbone_and_model_end_to_end(small, window, T, HW, mha):
     clear = margin > 3 * (full.cpu() - ref_logits).abs().max()
     agree_clear = (full.cpu().argmax(1) == ref_logits.argmax(1))[clear].float().mean().item() if clear.any() else 1.0
     assert agree_clear >= 0.999, f"mask agreement on clear-margin pixels {agree_clear:.5f} (all pixels {agree:.5f})"
+
+
+@pytest.mark.parametrize("window,HW,mha", [(12, (96, 72), (1, 2, 2, 4)), (7, (64, 80), (1, 1, 1, 1)), (12, (40, 40), (1, 1, 1, 1))])
+def test_image_backbone_end_to_end(window, HW, mha):
+    """2-D image model (BASELINE config 1 family): never-clamped (1,w,w) windows through the same kernels."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, window, window), fusion_heads=mha, clamp_window=False, video=False)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=window,
+                                   drop_path_rate=0.0, patch_norm=True, num_heads_fusion=list(mha), args=None)
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(2, 1, HW[0], HW[1], Nl=20, video=False)
+    cap = {}
+    with torch.no_grad():
+        ref_logits = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        logits = model(x.cuda(), l.cuda(), m.cuda())
+    for i, name in enumerate(("c1", "c2", "c3", "c4")):
+        assert feats[i].shape == cap[name].shape
+        assert rel_l2(feats[i], cap[name]) < 3e-2, (name, rel_l2(feats[i], cap[name]))
+    assert logits.shape == ref_logits.shape and rel_l2(logits, ref_logits) < 3e-2
+
+
+def test_baseline_config1_image_model_full_size():
+    """BASELINE.json configs[0]: LAVT image model (Swin-B window12), batch 1, 480x480, 20-token sentence -- built through
+    the public builder (segmentation.lavt), weights = the builder's own random init, oracle on the same state dict."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib import segmentation
+    torch.manual_seed(0)
+    model = segmentation.lavt(pretrained="", args=default_args(["--model", "lavt", "--swin_type", "base", "--window12"]))
+    g = torch.Generator().manual_seed(5)
+    for mod in model.modules():          # non-trivial norm statistics / affine parameters
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.add_(0.1 * torch.randn(mod.running_mean.shape, generator=g))
+            mod.running_var.add_(0.2 * torch.rand(mod.running_var.shape, generator=g))
+    sd = {k: v.detach().float().clone() for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig.swin("base", window12=True, video=False)
+    x, l, m = O.synthetic_inputs(1, 1, 480, 480, Nl=20, video=False)
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m)
+        got = model.cuda().eval()(x.cuda(), l.cuda(), m.cuda())
+    assert got.shape == ref.shape == (1, 2, 480, 480)
+    r = rel_l2(got, ref)
+    agree = (got.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    assert r < 3e-2, f"logits rel-L2 {r:.3e}"
+    margin = (ref[:, 0] - ref[:, 1]).abs()
+    clear = margin > 3 * (got.cpu() - ref).abs().max()
+    if clear.any():
+        assert (got.cpu().argmax(1) == ref.argmax(1))[clear].float().mean().item() >= 0.999
+    print(f"config1: rel-L2 {r:.3e}, argmax agreement {agree:.5f}")

@@ -59,6 +59,23 @@ def test_backbone_and_decoder_match_reference(window, T, HW, mha):
         assert (ref_logits - got_logits).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("window,HW,mha", [(7, (64, 80), (1, 1, 1, 1)), (12, (96, 72), (1, 2, 2, 4)), (12, (40, 40), (1, 1, 1, 1))])
+def test_image_backbone_matches_reference(window, HW, mha):
+    """2-D twins (lib/backbone.py): never-clamped windows, per-call mask, (B,HW,C) token layout."""
+    bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=window, mha=mha)
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, window, window), fusion_heads=mha, clamp_window=False, video=False)
+    x, l, m = O.synthetic_inputs(2, 1, HW[0], HW[1], Nl=13, video=False)
+    with torch.no_grad():
+        ref = bb(x, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() < 2e-4, f"stage {i}"
+        assert (dec(ref[3], ref[2], ref[1], ref[0]) - O.decoder_forward(sd, got[3], got[2], got[1], got[0])).abs().max().item() < 2e-4
+
+
 def test_random_state_dict_matches_reference_keys():
     net, _ = ref_shims.build_reference("lavt_video", "tiny")
     ref_sd = {k: v for k, v in net.state_dict().items() if not k.startswith("text_encoder.")}
