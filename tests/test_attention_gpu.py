@@ -1,0 +1,63 @@
+"""Window-attention core (C-ABI lavt_window_attention) in isolation vs a plain fp32 PyTorch evaluation of the same op on
+the same bf16 q/k/v (SURVEY.md Appendix B shapes: every distinct N the kernel must support).  bias index and shift mask of
+the torch side come from the host geometry (tests/test_geometry.py pins that bit-exactly to the reference).
+Tolerance: |a-b| <= 2e-2*|b| + 2e-2*rms(b), rel-L2 <= 1e-2 (P is rounded to bf16 before P.V; fp32 accumulation)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_window_attention(qkv, table, geom):
+    """qkv bf16 [rows, 3C] (q pre-scaled by hd^-0.5*log2e); table fp32 [L, nH] -> fp32 [rows, C]"""
+    from lavt_rs_b200.geometry import rel_const, window_row_map
+    rows, C3 = qkv.shape
+    C = C3 // 3
+    nH = table.shape[1]
+    N = geom.N
+    nwin = rows // N
+    _, code, rid = window_row_map(geom)
+    code, rid = code.cuda().view(nwin, N), rid.cuda().view(nwin, N)
+    x = qkv.float().view(nwin, N, 3, nH, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0] / math.log2(math.e), x[1], x[2]
+    s = q @ k.transpose(-1, -2)
+    idx = code[0][:, None] - code[0][None, :] + rel_const(geom)
+    s = s + table[idx.reshape(-1)].view(N, N, nH).permute(2, 0, 1).unsqueeze(0)
+    if geom.sd or geom.sh or geom.sw:
+        s = s + ((rid[:, :, None] != rid[:, None, :]).float() * -100.0).unsqueeze(1)
+    return (s.softmax(-1) @ v).transpose(1, 2).reshape(rows, C)
+
+
+CASES = [  # (B, D, H, W), window, shifted, heads
+    ((1, 8, 14, 14), (8, 7, 7), True, 4), ((1, 8, 96, 96), (8, 7, 7), True, 4), ((1, 4, 24, 24), (8, 7, 7), True, 16),
+    ((1, 16, 14, 14), (8, 7, 7), True, 8), ((1, 8, 24, 24), (8, 12, 12), True, 16), ((1, 4, 48, 48), (8, 12, 12), True, 8),
+    ((1, 8, 12, 12), (8, 12, 12), True, 32), ((1, 16, 24, 24), (8, 12, 12), True, 16), ((2, 1, 30, 30), (1, 12, 12), True, 8),
+    ((2, 1, 15, 15), (1, 7, 7), True, 32), ((1, 8, 10, 10), (8, 12, 12), True, 4), ((3, 8, 14, 21), (8, 7, 7), False, 4),
+]
+
+
+@pytest.mark.parametrize("dims,window,shifted,nH", CASES)
+def test_window_attention_matches_torch(dims, window, shifted, nH):
+    from lavt_rs_b200 import _cabi as K
+    from lavt_rs_b200.geometry import window_geometry
+    B, D, H, W = dims
+    clamp = window[0] != 1
+    geom = window_geometry(B, D, H, W, window, shifted, clamp)
+    C = nH * 32
+    rows = geom.rows()
+    g = torch.Generator(device="cuda").manual_seed(rows + nH)
+    qkv = torch.randn(rows, 3 * C, device="cuda", generator=g)
+    qkv[:, :C] *= 32 ** -0.5 * math.log2(math.e) * 2.0        # scores with a few units of spread
+    qkv = qkv.bfloat16()
+    L = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    table = torch.randn(L, nH, device="cuda", generator=g)
+    out = torch.empty(rows, C, device="cuda", dtype=torch.bfloat16)
+    K.window_attention(qkv, table.t().contiguous(), geom, out)
+    ref = torch_window_attention(qkv, table, geom)
+    err = (out.float() - ref).abs()
+    rms = ref.pow(2).mean().sqrt()
+    bad = (err > 2e-2 * ref.abs() + 2e-2 * rms).float().mean().item()
+    rel = (err.norm() / ref.norm()).item()
+    assert bad < 1e-4 and rel < 1e-2, f"N={geom.N}: {bad*100:.4f}% out of tolerance, rel-L2 {rel:.3e}"
