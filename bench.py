@@ -311,7 +311,8 @@ def main():
             K.TIMER.enabled = True
             K.TIMER.records.clear()
             fwd_static()
-            fam = K.TIMER.summary()
+            _pk, _ = peaks()
+            fam = K.TIMER.summary(_pk.get("bf16_tflops_sustained", 1400.0), _pk.get("hbm_gbs", 6550.0))
             K.TIMER.enabled = False
 
     if rank != 0:
@@ -331,6 +332,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None,
                 "launches": g["launches"], "ms_per_step": g["ms"], "alg_flops_per_step": g["flops"],
+                # per launch the binding roof is max(FLOPs / tensor peak, algorithmic bytes / HBM peak): short-K Swin
+                # GEMMs (K = 128..256) are HBM-bound; this is sum(ideal) / sum(measured) over the step's launches
+                "alg_bytes_per_step": g.get("bytes"), "frac_vs_binding_roof": (g["ideal_ms"] / g["ms"]) if g["ms"] > 0 else None,
                 "attention_core": {"kernel": "window_attn_kernel", "launches": at["launches"], "ms_per_step": at["ms"],
                                    "tflops": at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0},
                 "whole_step_tflops": flops_per_clip(a.window12) * value / world / 1e12}

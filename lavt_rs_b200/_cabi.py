@@ -185,15 +185,19 @@ class KernelTimer:
             d["flops"] += fl
         return out
 
-    def summary(self):
+    def summary(self, peak_tflops: float = 0.0, peak_gbs: float = 0.0):
+        """Per kernel family: launches, total ms, algorithmic FLOPs / bytes and (given the two peaks) the sum over
+        launches of the roofline-ideal time max(flops / peak_tflops, bytes / peak_gbs)."""
         torch.cuda.synchronize()
         out = {}
         for fam, fl, nb, s, e, _tag in self.records:
-            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "ideal_ms": 0.0})
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
             d["bytes"] += nb
+            if peak_tflops > 0 and peak_gbs > 0:
+                d["ideal_ms"] += max(fl / (peak_tflops * 1e12), nb / (peak_gbs * 1e9)) * 1e3
         return out
 
 
@@ -212,7 +216,10 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
     t0 = TIMER.begin()
     check(lib().lavt_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
                                C.byref(e), stream_ptr()), "lavt_gemm_bf16")
-    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N), f"M{M} N{N} K{K} act{e.act}")
+    if t0 is not None:
+        nbytes = 2.0 * (M * K + N * K) + M * N * ((4.0 if e.out_f32 else 0.0) + (2.0 if e.out_bf16 else 0.0)
+                                                   + (4.0 if e.resid else 0.0) + (2.0 if e.mul else 0.0))
+        TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, nbytes, f"M{M} N{N} K{K} act{e.act}")
 
 
 def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:

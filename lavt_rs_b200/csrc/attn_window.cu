@@ -18,6 +18,8 @@
 // Tile shapes are chosen to minimise padded work (N = 392 -> 25 strips x 5 key tiles of 80 = 400 x 400).
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace lavt {
 
 constexpr int AT_HD = 32;        // head dim
@@ -390,6 +392,15 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
       if (strips % w == 0) { warps = w; break; }
     }
     if (strips >= 8 && strips % warps != 0) warps = 6;
+    static int env_kvt = -1, env_warps = -1;
+    if (env_kvt < 0) {
+      const char* e1 = getenv("LAVT_ATTN_KVT");
+      const char* e2 = getenv("LAVT_ATTN_WARPS");
+      env_kvt = e1 ? atoi(e1) : 0;
+      env_warps = e2 ? atoi(e2) : 0;
+    }
+    if (env_kvt == 80) best = 0; else if (env_kvt == 64) best = 1; else if (env_kvt == 48) best = 2;
+    if (env_warps > 0) warps = env_warps;
     switch (best) {
       case 0: return launch_resident<80>(p, nwin, warps, st);
       case 1: return launch_resident<64>(p, nwin, warps, st);

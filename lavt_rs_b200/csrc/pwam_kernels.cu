@@ -134,12 +134,176 @@ __global__ void __launch_bounds__(256) pwam_core_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core version (mma.sync m16n8k16, bf16 operands, fp32 accumulate) used whenever the word matrices fit in
+// shared memory: 16 pixels per warp, scores for all (padded) words at once -> exact softmax, no online rescaling.
+//   S = (IN(q_pre) * C^-0.5) k^T + (1e4 m - 1e4)      A = normalised q rows built in registers, B = k rows (ldmatrix)
+//   O = softmax(S) v                                   A = P fragments (registers), B = v rows (ldmatrix.trans)
+// NT = padded word count / 8.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) pwam_core_mma_kernel(const float* __restrict__ qpre, const float* __restrict__ stats,
+                                                            const float* __restrict__ k, const float* __restrict__ v,
+                                                            const float* __restrict__ mask, __nv_bfloat16* __restrict__ o,
+                                                            long long n, int C, int Nl, int heads, float scale) {
+  constexpr int NLP = NT * 8;
+  constexpr int KS = NT / 2;                        // k16 steps over the words for P.V
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pitch = C * 2 + 16;                     // bytes per word row (odd multiple of 16 -> conflict-free ldmatrix)
+  uint8_t* sk = smem;                               // [NLP][pitch]
+  uint8_t* sv = sk + NLP * pitch;
+  float* s_mu = reinterpret_cast<float*>(sv + NLP * pitch);    // [C]
+  float* s_rs = s_mu + C;                           // [C] rstd * scale
+  float* s_madd = s_rs + C;                         // [NLP] additive word mask (log-domain), -inf for padded words
+
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // stage k, v (fp32 -> bf16), statistics and the word mask
+  for (int i = threadIdx.x; i < NLP * (C / 2); i += blockDim.x) {
+    const int j = i / (C / 2), c = (i - j * (C / 2)) * 2;
+    float2 kk = make_float2(0.f, 0.f), vv = kk;
+    if (j < Nl) {
+      kk = __ldg(reinterpret_cast<const float2*>(k + (static_cast<long long>(b) * Nl + j) * C + c));
+      vv = __ldg(reinterpret_cast<const float2*>(v + (static_cast<long long>(b) * Nl + j) * C + c));
+    }
+    *reinterpret_cast<uint32_t*>(sk + j * pitch + c * 2) = pack_bf16x2(kk.x, kk.y);
+    *reinterpret_cast<uint32_t*>(sv + j * pitch + c * 2) = pack_bf16x2(vv.x, vv.y);
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_mu[i] = __ldg(stats + (static_cast<long long>(b) * 2) * C + i);
+    s_rs[i] = __ldg(stats + (static_cast<long long>(b) * 2 + 1) * C + i) * scale;
+  }
+  for (int i = threadIdx.x; i < NLP; i += blockDim.x) s_madd[i] = (i < Nl) ? (1e4f * __ldg(mask + b * Nl + i) - 1e4f) : -INFINITY;
+  __syncthreads();
+
+  const long long p0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * 16;
+  if (p0 >= n) return;
+  const long long r0 = min(p0 + g, n - 1), r1 = min(p0 + g + 8, n - 1);
+  const float* q0 = qpre + (static_cast<long long>(b) * n + r0) * C;
+  const float* q1 = qpre + (static_cast<long long>(b) * n + r1) * C;
+  __nv_bfloat16* o0 = o + (static_cast<long long>(b) * n + r0) * C;
+  __nv_bfloat16* o1 = o + (static_cast<long long>(b) * n + r1) * C;
+  const bool w0 = (p0 + g) < n, w1 = (p0 + g + 8) < n;
+  const int ch = C / heads;
+
+  for (int h = 0; h < heads; ++h) {
+    const int cb = h * ch;
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int kc = 0; kc < ch; kc += 16) {
+      const int c0 = cb + kc + 2 * t;
+      uint32_t a[4];
+      {
+        const float2 x00 = __ldg(reinterpret_cast<const float2*>(q0 + c0)), x01 = __ldg(reinterpret_cast<const float2*>(q0 + c0 + 8));
+        const float2 x10 = __ldg(reinterpret_cast<const float2*>(q1 + c0)), x11 = __ldg(reinterpret_cast<const float2*>(q1 + c0 + 8));
+        const float m0 = s_mu[c0], m1 = s_mu[c0 + 1], m8 = s_mu[c0 + 8], m9 = s_mu[c0 + 9];
+        const float e0 = s_rs[c0], e1 = s_rs[c0 + 1], e8 = s_rs[c0 + 8], e9 = s_rs[c0 + 9];
+        a[0] = pack_bf16x2((x00.x - m0) * e0, (x00.y - m1) * e1);
+        a[1] = pack_bf16x2((x10.x - m0) * e0, (x10.y - m1) * e1);
+        a[2] = pack_bf16x2((x01.x - m8) * e8, (x01.y - m9) * e9);
+        a[3] = pack_bf16x2((x11.x - m8) * e8, (x11.y - m9) * e9);
+      }
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t kf[4];
+        // matrices: (words np*16 + 0..7, chunk 0), (same words, chunk 1), (words +8, chunk 0), (words +8, chunk 1)
+        const int word = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int chunk = (lane >> 3) & 1;
+        ldmatrix_x4(kf, sk + word * pitch + (cb + kc + chunk * 8) * 2);
+        mma_bf16_16816(s[np * 2 + 0], a, kf[0], kf[1]);
+        mma_bf16_16816(s[np * 2 + 1], a, kf[2], kf[3]);
+      }
+    }
+    // masked softmax over the words (exact: all words are in registers)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float ma = s_madd[nt * 8 + 2 * t], mb = s_madd[nt * 8 + 2 * t + 1];
+      s[nt][0] += ma; s[nt][1] += mb; s[nt][2] += ma; s[nt][3] += mb;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pf[KS][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float p0v = __expf(s[nt][0] - mx0), p1v = __expf(s[nt][1] - mx0);
+      const float p2v = __expf(s[nt][2] - mx1), p3v = __expf(s[nt][3] - mx1);
+      l0 += p0v + p1v;
+      l1 += p2v + p3v;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0v, p1v);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2v, p3v);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    // O = P v for this head's channels, 16 channels (two n8 tiles) at a time
+    for (int oc = 0; oc < ch; oc += 16) {
+      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        uint32_t vf[4];
+        // matrices: (words kk*16 + 0..7, chan chunk 0), (words +8, chunk 0), (words 0..7, chunk 1), (words +8, chunk 1)
+        const int word = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        ldmatrix_x4_trans(vf, sv + word * pitch + (cb + oc + (lane >> 4) * 8) * 2);
+        mma_bf16_16816(acc0, pf[kk], vf[0], vf[1]);
+        mma_bf16_16816(acc1, pf[kk], vf[2], vf[3]);
+      }
+      const int c = cb + oc + 2 * t;
+      if (w0) {
+        *reinterpret_cast<uint32_t*>(o0 + c) = pack_bf16x2(acc0[0] * i0, acc0[1] * i0);
+        *reinterpret_cast<uint32_t*>(o0 + c + 8) = pack_bf16x2(acc1[0] * i0, acc1[1] * i0);
+      }
+      if (w1) {
+        *reinterpret_cast<uint32_t*>(o1 + c) = pack_bf16x2(acc0[2] * i1, acc0[3] * i1);
+        *reinterpret_cast<uint32_t*>(o1 + c + 8) = pack_bf16x2(acc1[2] * i1, acc1[3] * i1);
+      }
+    }
+  }
+}
+
+template <int NT>
+static int launch_pwam_mma(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
+                           __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, float scale, size_t smem, cudaStream_t st) {
+  auto kfn = pwam_core_mma_kernel<NT>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const long long blocks = (n + 127) / 128;
+  kfn<<<dim3(static_cast<unsigned>(blocks), B), 256, smem, st>>>(qpre, stats, k, v, mask, o, n, C, Nl, heads, scale);
+  LAVT_LAUNCH_CHECK("pwam_core_mma_kernel");
+  return LAVT_OK;
+}
+
 int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                        __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st) {
   LAVT_REQUIRE(B > 0 && n > 0, "pwam_core: empty input");
   LAVT_REQUIRE(Nl >= 1 && Nl <= 4096, "pwam_core: Nl=%d out of range", Nl);
   LAVT_REQUIRE(heads >= 1 && heads <= 32 && (32 % heads) == 0, "pwam_core: fusion heads=%d must divide 32", heads);
   const float scale = 1.0f / sqrtf(static_cast<float>(C));
+  {
+    // tensor-core path when the words fit in shared memory and the head width is MMA-friendly
+    const int nlp = Nl <= 32 ? 32 : (Nl <= 48 ? 48 : (Nl <= 80 ? 80 : (Nl <= 128 ? 128 : 0)));
+    const size_t smem = nlp ? (2 * static_cast<size_t>(nlp) * (C * 2 + 16) + 2 * C * sizeof(float) + nlp * sizeof(float)) : 0;
+    if (nlp && smem <= 160 * 1024 && (C / heads) % 16 == 0 && C % 16 == 0) {
+      switch (nlp) {
+        case 32: return launch_pwam_mma<4>(qpre, stats, k, v, mask, o, B, n, C, Nl, heads, scale, smem, st);
+        case 48: return launch_pwam_mma<6>(qpre, stats, k, v, mask, o, B, n, C, Nl, heads, scale, smem, st);
+        case 80: return launch_pwam_mma<10>(qpre, stats, k, v, mask, o, B, n, C, Nl, heads, scale, smem, st);
+        default: return launch_pwam_mma<16>(qpre, stats, k, v, mask, o, B, n, C, Nl, heads, scale, smem, st);
+      }
+    }
+  }
 #define LAVT_PWAM_CASE(cpl, pix)                                                                              \
   case cpl * 32: {                                                                                            \
     const long long warps = (n + pix - 1) / pix;                                                              \
