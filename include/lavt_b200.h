@@ -111,6 +111,10 @@ int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, 
  * relative_position_bias_table [L, nH] transposed; out: bf16 [B*nW*N, C].  head_dim must be 32. */
 int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
                           void* out_bf16, void* stream);
+/* Kernel selection for lavt_window_attention (process-wide; initial value from the LAVT_ATTN_IMPL environment variable):
+ *   0 = auto: tcgen05 / TMEM kernel for windows of <= 400 tokens, mma.sync flash kernels otherwise
+ *   1 = mma.sync kernels only.  Returns the previous setting. */
+int lavt_set_attention_impl(int32_t impl);
 
 /* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */
 /* InstanceNorm1d statistics over the n tokens of each clip: x fp32 [B,n,C] -> stats fp32 [B,2,C] = (mean, rstd).

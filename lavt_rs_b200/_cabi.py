@@ -92,13 +92,16 @@ SIGNATURES = {
     "lavt_nhwc_to_nchw": [_vp, _vp, _i32, _i32, _i32, _vp],
     "lavt_nchw_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _vp],
 }
-EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", *SIGNATURES.keys()]
+EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
+           *SIGNATURES.keys()]
 
 
 def _declare(l: C.CDLL) -> None:
     l.lavt_abi_version.restype = C.c_int
     l.lavt_instnorm_workspace_floats.argtypes = [_i32, _i64, _i32]
     l.lavt_instnorm_workspace_floats.restype = C.c_int64
+    l.lavt_set_attention_impl.argtypes = [_i32]
+    l.lavt_set_attention_impl.restype = C.c_int
     for name, argtypes in SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = argtypes
@@ -293,6 +296,12 @@ def patch_embed_im2col(x: torch.Tensor, out_bf16: torch.Tensor) -> None:
     check(lib().lavt_patch_embed_im2col(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, T, H, W,
                                         _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
           "lavt_patch_embed_im2col")
+
+
+def set_attention_impl(impl: str) -> str:
+    """'auto' (tcgen05 kernel where it applies) or 'mma' (mma.sync kernels only); returns the previous setting."""
+    prev = lib().lavt_set_attention_impl({"auto": 0, "mma": 1}[impl])
+    return "mma" if prev else "auto"
 
 
 def window_attention(qkv: torch.Tensor, table_t: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor) -> None:

@@ -368,6 +368,17 @@ static int launch_stream(const AttnParams& p, long long nwin, cudaStream_t st) {
   return LAVT_OK;
 }
 
+int attn_impl_setting(int set) {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("LAVT_ATTN_IMPL");
+    impl = (e && e[0] == 't') ? 0 : 1;   // default: mma.sync kernels until the tcgen05 kernel wins on every shape
+  }
+  const int prev = impl;
+  if (set >= 0) impl = set ? 1 : 0;
+  return prev;
+}
+
 int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
   const WinGeom& g = p.win;
   LAVT_REQUIRE(p.C == p.nH * AT_HD, "attention: head_dim must be 32 (C=%d, heads=%d)", p.C, p.nH);
@@ -378,6 +389,10 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
   const long long nwin = 1LL * g.B * g.nwd * g.nwh * g.nww;
   LAVT_REQUIRE(nwin > 0 && nwin < 65536, "attention: window count %lld out of range", nwin);
   const int N = g.N;
+  {
+    // LAVT_ATTN_IMPL=mma (or lavt_set_attention_impl(1)) forces the mma.sync kernels below
+    if (attn_impl_setting(-1) == 0 && window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
+  }
   if (N <= 512) {
     // key tile = the candidate with the least padding; warps = a divisor-friendly count of the 16-row strips
     const int kvts[3] = {80, 64, 48};

@@ -142,6 +142,8 @@ int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int3
   return window_attn_dispatch(p, S(stream));
 }
 
+int lavt_set_attention_impl(int32_t impl) { return attn_impl_setting(impl != 0 ? 1 : 0); }
+
 int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C) { return colstats_workspace_floats(B, n, C); }
 
 int lavt_instnorm_stats(const float* x, int32_t B, int64_t n, int32_t C, float eps, float* stats, float* workspace,

@@ -36,6 +36,10 @@ struct AttnParams {
   WinGeom win;
 };
 int window_attn_dispatch(const AttnParams& p, cudaStream_t st);
+// tcgen05 / TMEM variant (attn_tc.cu): windows of up to 400 tokens
+int attn_impl_setting(int set);   // set < 0: query only; returns the previous value (0 = auto, 1 = mma.sync only)
+bool window_attn_tc_supported(const AttnParams& p);
+int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st);
 
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);

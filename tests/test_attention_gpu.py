@@ -38,8 +38,9 @@ CASES = [  # (B, D, H, W), window, shifted, heads
 ]
 
 
+@pytest.mark.parametrize("impl", ["auto", "mma"])      # auto = tcgen05 kernel where it applies (N <= 400)
 @pytest.mark.parametrize("dims,window,shifted,nH", CASES)
-def test_window_attention_matches_torch(dims, window, shifted, nH):
+def test_window_attention_matches_torch(dims, window, shifted, nH, impl):
     from lavt_rs_b200 import _cabi as K
     from lavt_rs_b200.geometry import window_geometry
     B, D, H, W = dims
@@ -54,7 +55,12 @@ def test_window_attention_matches_torch(dims, window, shifted, nH):
     L = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
     table = torch.randn(L, nH, device="cuda", generator=g)
     out = torch.empty(rows, C, device="cuda", dtype=torch.bfloat16)
-    K.window_attention(qkv, table.t().contiguous(), geom, out)
+    prev = K.set_attention_impl(impl)
+    try:
+        K.window_attention(qkv, table.t().contiguous(), geom, out)
+        torch.cuda.synchronize()
+    finally:
+        K.set_attention_impl(prev)
     ref = torch_window_attention(qkv, table, geom)
     err = (out.float() - ref).abs()
     rms = ref.pow(2).mean().sqrt()
