@@ -64,6 +64,8 @@ struct AttnTcArgs {
   int stage_bytes;          // Q | K | V, each NP x 64 B
   int off_tab, off_mtab, off_negoff, off_pm, off_ps, off_bar;
   int shifted;
+  int r4, tail_rows;        // tail tile replicated x4 across the TMEM lane quadrants (see softmax warps)
+  int off_xq;               // [4][16][34] cross-quadrant partials of the replicated tail tile
   int stagger;              // phase offset (clocks) between consecutive group pipelines
   long long* trace;        // debug (LAVT_ATTN_TRACE): clock64 stamps of CTA 0, [17 events][TC_TRACE_TILES]
 };
@@ -191,31 +193,21 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // ---------------------------------------------------------------------------------------------------------------
 // softmax passes over one piece of W score columns starting at column c.
-//   tq   = shared-space byte address of table[code(i) + rc] (this thread's row): bias(i, j) = [tq + negoff4[j]]
-//   mrow = shared-space byte address of the mask-table row of this thread's region class
+//   tabq = table + code(i) + rc (this thread's row): bias(i, j) = tabq[negoff[j]],  negoff[j] = -code(j)
+//   mrow = mask-table row of this thread's region class
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void lds_v4(uint32_t addr, int* r) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-
 template <int W>
-__device__ __forceinline__ void pass1_piece(uint32_t ts, int c, int N, uint32_t tq, uint32_t negoff4, bool need_mask,
-                                            uint32_t mrow, float& m0, float& m1) {
+__device__ __forceinline__ void pass1_piece(uint32_t ts, int c, int N, const float* tabq, const int* negoff, bool need_mask,
+                                            const float* mrow, float& m0, float& m1) {
   uint32_t v[W];
   tmem_ld_w<W>(ts + c, v);
+  // plain shared-memory loads: the compiler batches the index loads ahead of the dependent gathers
+  int no[W];
+#pragma unroll
+  for (int j = 0; j < W; j += 4) *reinterpret_cast<int4*>(&no[j]) = *reinterpret_cast<const int4*>(negoff + c + j);
   float b[W];
 #pragma unroll
-  for (int j = 0; j < W; j += 4) {
-    int no[4];
-    lds_v4(negoff4 + 4 * (c + j), no);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) b[j + k] = lds_f32(tq + no[k]);
-  }
+  for (int j = 0; j < W; ++j) b[j] = tabq[no[j]];
   tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < W; j += 2) {
@@ -225,10 +217,11 @@ __device__ __forceinline__ void pass1_piece(uint32_t ts, int c, int N, uint32_t 
     v[j + 1] = __float_as_uint(a1);
   }
   if (need_mask) {
+    const float* mp = mrow + c;
 #pragma unroll
     for (int j = 0; j < W; j += 2) {
       float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
-      add2(a0, a1, lds_f32(mrow + 4 * (c + j)), lds_f32(mrow + 4 * (c + j + 1)));
+      add2(a0, a1, mp[j], mp[j + 1]);
       v[j] = __float_as_uint(a0);
       v[j + 1] = __float_as_uint(a1);
     }
@@ -266,14 +259,17 @@ __device__ __forceinline__ void pass2_piece(uint32_t ts_c, uint32_t tp, float nm
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const AttnTcArgs a) {
+window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQT, const AttnParams p,
+                      const AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment as an OFFSET (keeps the shared address space visible to the compiler: LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* tab = reinterpret_cast<float*>(smem + a.off_tab);
   float* mtab = reinterpret_cast<float*>(smem + a.off_mtab);
   int* negoff = reinterpret_cast<int*>(smem + a.off_negoff);
   float* pm = reinterpret_cast<float*>(smem + a.off_pm);       // [2][3][128] group row max (tile parity)
   float* ps = reinterpret_cast<float*>(smem + a.off_ps);       // [2][3][128] group row sum
+  float* xq = reinterpret_cast<float*>(smem + a.off_xq);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
   uint64_t* kv_full = bars;            // [2]
   uint64_t* stage_free = bars + 2;     // [2]
@@ -311,11 +307,11 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     fence_mbar_init();
   }
   if (warp == TC_TMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
-  // per-launch table: -4 * code(j) of the key tokens; zero the K / V pad rows of both stages
+  // per-launch table: -code(j) of the key tokens; zero the K / V pad rows of both stages
   for (int j = threadIdx.x; j < NP; j += blockDim.x) {
     int code = 0;
     if (j < N) code = (j / (wg.Wh * wg.Ww)) * SD + ((j / wg.Ww) % wg.Wh) * SH + j % wg.Ww;
-    negoff[j] = -4 * code;
+    negoff[j] = -code;
   }
   const int npad = (NP - N) > 0 ? (NP - N) : 1;
   for (int i = threadIdx.x; i < 2 * 2 * (NP - N) * 16; i += blockDim.x) {
@@ -333,7 +329,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   if (warp == TC_TMA_WARP) {
     // =============================== TMA producer (one thread) ===============================
     if (lane == 0) {
-      const uint32_t tx_bytes = 3u * N * 64u;
+      const uint32_t tx_bytes = 3u * N * 64u + (a.r4 ? 4u * 32u * 64u : 0u);
       for (int lu = 0; lu < nunits; ++lu) {
         const int u = u_begin + lu, s = lu & 1;
         if (lu >= 2) mbar_wait(&stage_free[s], ((lu - 2) >> 1) & 1);     // all MMAs reading unit lu-2 have retired
@@ -343,6 +339,11 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         for (int op = 0; op < 3; ++op)
           for (int b = 0; b < a.nb; ++b)
             tma_load_2d(st + op * NP * 64 + b * a.BR * 64, &tmQKV, &kv_full[s], op * p.C + head * TC_HD, win * N + b * a.BR);
+        if (a.r4) {
+          // tail query rows, one copy per TMEM lane quadrant (rows past the tensor end are zero-filled by TMA)
+          for (int qd = 0; qd < 4; ++qd)
+            tma_load_2d(st + 3 * NP * 64 + qd * 32 * 64, &tmQT, &kv_full[s], head * TC_HD, win * N + (ntiles - 1) * 128);
+        }
       }
     }
   } else if (warp >= TC_MMA_WARP0) {
@@ -367,7 +368,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         const uint64_t dv = make_sw64_desc(sq + 2 * NP * 64 + c0 * 64);
         mbar_wait(&kv_full[s], (lu >> 1) & 1);
         for (int qt = 0; qt < ntiles; ++qt, ++t) {
-          const uint64_t dq = make_sw64_desc(sq + qt * 128 * 64);
+          const uint64_t dq = make_sw64_desc((a.r4 && qt == ntiles - 1) ? sq + 3 * NP * 64 : sq + qt * 128 * 64);
           tc_fence_after();
           if (elect_one_sync()) {
             umma_bf16_ss(tmem_s, dq, dk, idesc_qk, 0);
@@ -397,7 +398,6 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
     const int c0 = tc_group_begin(NP, g), c1 = tc_group_end(NP, g);
     const uint32_t ts = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t tab_addr = smem_u32(tab), mtab_addr = smem_u32(mtab), negoff_addr = smem_u32(negoff);
     const int nW = wg.nwd * wg.nwh * wg.nww;
     const int Dp = wg.nwd * wg.wd, Hp = wg.nwh * wg.wh, Wp = wg.nww * wg.ww;
 
@@ -406,8 +406,9 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       const int lu = te / ntiles, qt = te - lu * ntiles;
       const int u = u_begin + lu;
       const int head = u / a.nwin, win = u - head * a.nwin;
-      const int i = qt * 128 + r;
-      const bool wvalid = (qt * 128 + q * 32) < N;
+      const bool rep = a.r4 && qt == ntiles - 1;            // replicated tail tile: every quadrant holds the same rows
+      const int i = rep ? qt * 128 + lane : qt * 128 + r;
+      const bool wvalid = rep || (qt * 128 + q * 32) < N;
       if (q == 0 && lane == 0) TC_TRACE(15, te);
       mbar_wait(o_full, te & 1);
       tc_fence_after();
@@ -418,7 +419,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         const float m = fmaxf(m0, fmaxf(m1, m2));
         const float w0 = ex2_ftz(m0 - m), w1 = ex2_ftz(m1 - m), w2 = ex2_ftz(m2 - m);
         const float l = w0 * psb[0] + w1 * psb[128] + w2 * psb[256];
-        const float inv = 1.0f / l;
+        const float inv = rep ? 1.0f : 1.0f / l;
         const float wgt[3] = {w0 * inv, w1 * inv, w2 * inv};
         float acc[32];
 #pragma unroll
@@ -431,7 +432,37 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = fmaf(wgt[gg], __uint_as_float(o[j]), acc[j]);
         }
-        if (i < N) {
+        if (rep) {
+          // this quadrant only saw a quarter of each group's keys: merge the four partials through shared memory
+          if (lane < a.tail_rows) {
+            float* dstq = xq + (q * 16 + lane) * 34;
+            dstq[0] = m;
+            dstq[1] = l;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dstq[2 + j] = acc[j];
+          }
+          named_bar(1 + TC_EPI_GROUP, 128);
+          if (q == 0 && lane < a.tail_rows) {
+            const float* x0 = xq + lane * 34;
+            const float mm = fmaxf(fmaxf(x0[0], x0[16 * 34]), fmaxf(x0[2 * 16 * 34], x0[3 * 16 * 34]));
+            float wq[4], ll = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              wq[k] = ex2_ftz(x0[k * 16 * 34] - mm);
+              ll = fmaf(wq[k], x0[k * 16 * 34 + 1], ll);
+            }
+            const float iv = 1.0f / ll;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = 0.f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v = fmaf(wq[k], x0[k * 16 * 34 + 2 + j], v);
+              acc[j] = v * iv;
+            }
+          }
+          named_bar(1 + TC_EPI_GROUP, 128);
+        }
+        if (i < N && (!rep || q == 0)) {
           __nv_bfloat16* dst = p.out + (static_cast<long long>(win) * N + i) * p.C + head * TC_HD;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -503,8 +534,18 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       }
 
       for (int qt = 0; qt < ntiles; ++qt, ++t) {
-        const int i = qt * 128 + r;
-        const bool wvalid = (qt * 128 + q * 32) < N;          // warp-uniform: any live query row in this warp?
+        // Tail tile with <= 16 live rows: the rows are replicated into all four lane quadrants (see the TMA producer) and
+        // quadrant q processes only a quarter of the group's keys, so the tile costs a quarter of a full one instead of
+        // leaving three of the four SM sub-partitions idle.
+        const bool rep = a.r4 && qt == ntiles - 1;
+        const int i = rep ? qt * 128 + lane : qt * 128 + r;
+        const bool wvalid = rep || (qt * 128 + q * 32) < N;   // warp-uniform: any live query row in this warp?
+        int s0 = c0, s1 = c1;
+        if (rep) {
+          const int nblk = (c1 - c0) >> 4;
+          s0 = c0 + 16 * ((q * nblk) >> 2);
+          s1 = c0 + 16 * (((q + 1) * nblk) >> 2);
+        }
         // the last group (in phase order) drains the PREVIOUS tile's accumulators before its own softmax: by then the
         // other groups' P.V of that tile were issued long ago, and no P.V of this tile ever waits for the epilogue
         if (g == TC_EPI_GROUP && t >= 1) epilogue(t - 1);
@@ -514,25 +555,33 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         if (wvalid) {
           const int ic = i < N ? i : N - 1;
           const int code_i = (ic / (wg.Wh * wg.Ww)) * SD + ((ic / wg.Ww) % wg.Wh) * SH + ic % wg.Ww;
-          const uint32_t tq = tab_addr + 4 * (code_i + a.rc);
-          uint32_t mrow = mtab_addr;
+          const float* tabq = tab + code_i + a.rc;
+          const float* mrow = mtab;
           if (need_mask) {
             const int tw = ic % wg.ww, th = (ic / wg.ww) % wg.wh, td = ic / (wg.ww * wg.wh);
             const int ci = 4 * (shift_region(wa * wg.wd + td, Dp, wg.wd, wg.sd) - rd0) +
                            2 * (shift_region(wb * wg.wh + th, Hp, wg.wh, wg.sh) - rh0) +
                            (shift_region(wc * wg.ww + tw, Wp, wg.ww, wg.sw) - rw0);
-            mrow = mtab_addr + 4 * ci * TC_MSTRIDE;
+            mrow = mtab + ci * TC_MSTRIDE;
           }
           float m0 = -INFINITY, m1 = -INFINITY;
-          int c = c0;
-          for (; c + 32 <= c1; c += 32) pass1_piece<32>(ts, c, N, tq, negoff_addr, need_mask, mrow, m0, m1);
-          if (c < c1) pass1_piece<16>(ts, c, N, tq, negoff_addr, need_mask, mrow, m0, m1);
+          int c = s0;
+          for (; c + 32 <= s1; c += 32) pass1_piece<32>(ts, c, N, tabq, negoff, need_mask, mrow, m0, m1);
+          if (c < s1) pass1_piece<16>(ts, c, N, tabq, negoff, need_mask, mrow, m0, m1);
           tmem_st_wait();
           if (q == 0 && lane == 0) TC_TRACE(9 + g, t);
-          const float m = fmaxf(m0, m1);
+          const float m = fmaxf(fmaxf(m0, m1), -1e30f);       // finite even for an empty key range (replicated tail)
           float l0 = 0.f, l1 = 0.f;
-          for (c = c0; c + 32 <= c1; c += 32) pass2_piece<32>(ts + c, ts + c0 + ((c - c0) >> 1), -m, l0, l1);
-          if (c < c1) pass2_piece<16>(ts + c, ts + c0 + ((c - c0) >> 1), -m, l0, l1);
+          for (c = s0; c + 32 <= s1; c += 32) pass2_piece<32>(ts + c, ts + c0 + ((c - c0) >> 1), -m, l0, l1);
+          if (c < s1) pass2_piece<16>(ts + c, ts + c0 + ((c - c0) >> 1), -m, l0, l1);
+          if (rep) {
+            // keys of this group owned by the other quadrants contribute nothing to these lanes: P = 0 there
+            uint32_t z[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = 0u;
+            for (c = c0; c < c1; c += 16)
+              if (c < s0 || c >= s1) tmem_st_x8(ts + c0 + ((c - c0) >> 1), z);
+          }
           tmem_st_wait();
           pm[((t & 1) * TC_GROUPS + g) * 128 + r] = m;
           ps[((t & 1) * TC_GROUPS + g) * 128 + r] = l0 + l1;
@@ -585,7 +634,17 @@ int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st) {
   a.SD = tc_stride((2 * g.Wh - 1) * a.SH, (g.Wh * g.Ww) % 32);
   a.L2 = (2 * g.Wd - 1) * a.SD;
   a.rc = (g.Wd - 1) * a.SD + (g.Wh - 1) * a.SH + (g.Ww - 1);
-  a.stage_bytes = 3 * a.NP * 64;
+  a.tail_rows = g.N - (a.ntiles - 1) * 128;
+  a.r4 = (a.ntiles >= 2 && a.tail_rows <= 16) ? 1 : 0;
+  {
+    static int no_r4 = -1;
+    if (no_r4 < 0) {
+      const char* e = getenv("LAVT_ATTN_NO_R4");
+      no_r4 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (no_r4) a.r4 = 0;
+  }
+  a.stage_bytes = 3 * a.NP * 64 + (a.r4 ? 128 * 64 : 0);
   // the last query tile reads up to 128 rows past N from the Q region: that runs into the K / V regions of the stage
   LAVT_REQUIRE(a.ntiles * 128 <= 3 * a.NP, "attention(tc): query tile overrun");
   int off = 2 * a.stage_bytes;
@@ -594,17 +653,21 @@ int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st) {
   a.off_negoff = off;     off += ((a.NP * 4 + 127) / 128) * 128;
   a.off_pm = off;         off += 2 * TC_GROUPS * 128 * 4;
   a.off_ps = off;         off += 2 * TC_GROUPS * 128 * 4;
+  a.off_xq = off;         off += a.r4 ? 4 * 16 * 34 * 4 : 0;
   a.off_bar = off;        off += 128;
   const int smem = off + 1024;
   LAVT_REQUIRE(smem <= 227 * 1024, "attention(tc): shared memory %d B exceeds the SM", smem);
   a.shifted = (g.sd | g.sh | g.sw) != 0;
 
-  CUtensorMap tm;
+  CUtensorMap tm, tm_tail;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(3 * p.C), static_cast<uint64_t>(nwin * g.N)};
     uint64_t strides[1] = {static_cast<uint64_t>(3 * p.C) * 2};
     uint32_t box[2] = {TC_HD, static_cast<uint32_t>(a.BR)};
     int rc = make_tmap_bf16(&tm, p.qkv, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    uint32_t box_t[2] = {TC_HD, 32};
+    rc = make_tmap_bf16(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   static int sms = 0;
@@ -629,7 +692,7 @@ int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st) {
   const char* trace_path = getenv("LAVT_ATTN_TRACE");
   if (trace_path) LAVT_CUDA(cudaMalloc(&a.trace, 17 * TC_TRACE_TILES * sizeof(long long)));
   if (a.trace) LAVT_CUDA(cudaMemsetAsync(a.trace, 0, 17 * TC_TRACE_TILES * sizeof(long long), st));
-  window_attn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tm, p, a);
+  window_attn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tm, tm_tail, p, a);
   LAVT_LAUNCH_CHECK("window_attn_tc_kernel");
   if (a.trace) {
     // debug only: synchronous dump of CTA 0's event clocks

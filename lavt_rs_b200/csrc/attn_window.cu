@@ -372,7 +372,7 @@ int attn_impl_setting(int set) {
   static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("LAVT_ATTN_IMPL");
-    impl = (e && e[0] == 't') ? 0 : 1;   // default: mma.sync kernels until the tcgen05 kernel wins on every shape
+    impl = (e && e[0] == 'm') ? 1 : 0;   // default: auto (tcgen05 kernel where it applies)
   }
   const int prev = impl;
   if (set >= 0) impl = set ? 1 : 0;
