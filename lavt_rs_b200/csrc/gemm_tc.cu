@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace lavt {
@@ -37,9 +38,14 @@ struct GemmSmem {
   static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = RING_BYTES;                  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
   static constexpr int VEC_OFF = BAR_OFF + 256;               // per epilogue warpgroup: scale[BN], bias[BN]
-  static constexpr int TOTAL = VEC_OFF + EPI_WGS * 2 * GEMM_BN * 4 + 1024 /*alignment slack*/;
+  static constexpr int VEC_TILE_BYTES = EPI_WGS * 2 * GEMM_BN * 4;   // per-tile scale / bias staging (fallback)
+  static constexpr int TOTAL = VEC_OFF + VEC_TILE_BYTES + 1024 /*alignment slack*/;
   static constexpr int THREADS = 128 + 128 * EPI_WGS;
   static constexpr int MIN_CTAS = (EPI_WGS == 1) ? 2 : 1;
+  // TMEM accumulator stages: all 512 columns when the CTA owns the SM (4 x 128 or 2 x 256), half of them with 2 CTAs/SM.
+  // The epilogue is bound by TMEM -> register bandwidth while the mainloop runs (~30 B/clk/SM, ncu + clock64 traces), so
+  // with short K it takes longer than the MMAs of a tile; more stages let the MMA warp run ahead instead of idling.
+  static constexpr int ACC = (MIN_CTAS == 2) ? 2 : 512 / GEMM_BN;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -52,18 +58,47 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exact-erf GELU (nn.GELU default): erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), 2 MUFU + ~12 FMA-pipe ops
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = ex2_approx(-ax * ax * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// packed fp32x2 arithmetic (sm_100): one issue slot for two elements
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// exact-erf GELU (nn.GELU default) for two values at once, no MUFU:  erf(z) = z * P(z^2) on |z| <= 3 (degree-8 minimax fit,
+// |err| <= 4e-5 including the tail beyond 3 where erf is taken as +-1 exactly; the coefficients are normalised so that
+// 3 * P(9) == 1).  Horner in packed fp32x2: 8.5 issue slots per element instead of ~18 + 2 MUFU.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = pk2(x0, x1);
+  float z0, z1;
+  upk2(mul2(x, pk2(0.70710678118654752f, 0.70710678118654752f)), z0, z1);
+  z0 = fminf(fmaxf(z0, -3.0f), 3.0f);
+  z1 = fminf(fmaxf(z1, -3.0f), 3.0f);
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t t = mul2(z, z);
+  constexpr float K = 1.0000220904f;      // 1 / (3 * P(9)) of the raw fit
+  uint64_t p = pk2(4.0742095563e-08f * K, 4.0742095563e-08f * K);
+  p = fma2(p, t, pk2(-1.9448222676e-06f * K, -1.9448222676e-06f * K));
+  p = fma2(p, t, pk2(4.1060515983e-05f * K, 4.1060515983e-05f * K));
+  p = fma2(p, t, pk2(-5.1103678896e-04f * K, -5.1103678896e-04f * K));
+  p = fma2(p, t, pk2(4.2354270142e-03f * K, 4.2354270142e-03f * K));
+  p = fma2(p, t, pk2(-2.5102860078e-02f * K, -2.5102860078e-02f * K));
+  p = fma2(p, t, pk2(1.1107933337e-01f * K, 1.1107933337e-01f * K));
+  p = fma2(p, t, pk2(-3.7531487405e-01f * K, -3.7531487405e-01f * K));
+  p = fma2(p, t, pk2(1.1282684285e+00f * K, 1.1282684285e+00f * K));
+  const uint64_t e = mul2(z, p);
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  upk2(fma2(hx, e, hx), x0, x1);
 }
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
 __device__ __forceinline__ void ldg_v8(uint32_t* r, const void* p) {
@@ -85,19 +120,23 @@ __device__ __forceinline__ float tanh_fast(float x) {
 template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS>
 __global__ void __launch_bounds__(GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::THREADS, GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::MIN_CTAS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p, const int m_tiles) {
+                    const GemmParams p, const int m_tiles, const int vec_all, long long* const trace_buf) {
   using L = GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned as an OFFSET so the compiler keeps the shared address space (LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;      // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  constexpr int ACC = L::ACC;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;      // [ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC;         // [ACC]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* const trace = (blockIdx.x == 0) ? trace_buf : nullptr;     // debug (LAVT_GEMM_TRACE): clock64 stamps of CTA 0
+#define GEMM_TRACE(ev, lt) do { if (trace && (lt) < 32) trace[(ev) * 32 + (lt)] = clock64(); } while (0)
   const int n_tiles = p.N / GEMM_BN;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
@@ -111,14 +150,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < ACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 4);      // one arrive per epilogue warp of the owning warpgroup
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, 2 * GEMM_BN);  // two fp32 accumulators of 128 columns
+    tmem_alloc(tmem_ptr_smem, ACC * GEMM_BN);  // ACC fp32 accumulators of GEMM_BN columns
+  }
+  if (vec_all) {
+    // column scale / bias of ALL N columns staged once per CTA: the epilogue never waits on global memory for them
+    float* vec = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      vec[i] = p.cscale ? __ldg(p.cscale + i) : 1.0f;
+      vec[p.N + i] = p.bias ? __ldg(p.bias + i) : 0.0f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -146,6 +193,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (kb == 0) GEMM_TRACE(5, it / num_kb);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
@@ -167,16 +215,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        const uint32_t use = static_cast<uint32_t>(lt >> 1);
+        const int acc = lt % ACC;
+        const uint32_t use = static_cast<uint32_t>(lt / ACC);
         mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
+        GEMM_TRACE(0, lt);
         const uint32_t tmem_d = tmem_base + acc * GEMM_BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0) GEMM_TRACE(1, lt);
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
           const uint64_t da = make_kmajor_sw128_desc(sa);
@@ -189,6 +239,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
         }
         umma_commit(&tmem_full_bar[acc]);      // accumulator complete
+        GEMM_TRACE(2, lt);
       }
     }
   } else if (warp >= 4) {
@@ -196,24 +247,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int wg = (warp - 4) >> 2;            // epilogue warpgroup: local tiles with lt % EPI_WGS == wg
     const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32)
     const int et = threadIdx.x - 128 - wg * 128;
-    float* s_scale = reinterpret_cast<float*>(smem + L::VEC_OFF) + wg * 2 * GEMM_BN;
-    float* s_bias = s_scale + GEMM_BN;
+    float* const vec = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    const float* s_scale = vec + wg * 2 * GEMM_BN;
+    const float* s_bias = s_scale + GEMM_BN;
     const int r = ew * 32 + lane;              // row inside the tile
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       if ((lt % EPI_WGS) != wg) continue;
-      const int acc = lt & 1;
-      const uint32_t use = static_cast<uint32_t>(lt >> 1);
+      const int acc = lt % ACC;
+      const uint32_t use = static_cast<uint32_t>(lt / ACC);
       const int mt = tile / n_tiles;
       const int n0 = (tile - mt * n_tiles) * GEMM_BN;
 
-      // previous tile's readers of s_scale / s_bias are done -> refill for this tile's columns
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-      for (int i = et; i < GEMM_BN; i += 128) {
-        s_scale[i] = p.cscale ? __ldg(p.cscale + n0 + i) : 1.0f;
-        s_bias[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.0f;
+      if (vec_all) {
+        s_scale = vec + n0;
+        s_bias = vec + p.N + n0;
+      } else {
+        // previous tile's readers of the staging vectors are done -> refill for this tile's columns
+        float* w_scale = vec + wg * 2 * GEMM_BN;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        for (int i = et; i < GEMM_BN; i += 128) {
+          w_scale[i] = p.cscale ? __ldg(p.cscale + n0 + i) : 1.0f;
+          w_scale[GEMM_BN + i] = p.bias ? __ldg(p.bias + n0 + i) : 0.0f;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
 
       long long m = -1, orow = -1;
       if (p.rowmap == ROWMAP_CONV) {
@@ -253,6 +311,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&tmem_full_bar[acc], use & 1);
           tc_fence_after();
           acc_ready = true;
+          if (ew == 0 && lane == 0) GEMM_TRACE(3, lt);
         }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tbase + c * 32, v);          // warp-collective: executed by all lanes
@@ -265,11 +324,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (!live) continue;
         float f[32];
+        {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c * 32 + j], s_bias[c * 32 + j]);
+          for (int q = 0; q < 8; ++q) {
+            const float4 sc = sc4[q], bi = bi4[q];
+            upk2(fma2(pk2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), pk2(sc.x, sc.y), pk2(bi.x, bi.y)), f[4 * q], f[4 * q + 1]);
+            upk2(fma2(pk2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), pk2(sc.z, sc.w), pk2(bi.z, bi.w)), f[4 * q + 2],
+                 f[4 * q + 3]);
+          }
+        }
         if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+          for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
         } else if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -313,6 +381,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (ew == 0 && lane == 0) GEMM_TRACE(4, lt);
     }
   }
 
@@ -320,7 +389,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * GEMM_BN);
+    tmem_dealloc(tmem_base, ACC * GEMM_BN);
   }
 }
 
@@ -341,17 +410,42 @@ template <int BN, int STAGES, int EPI_WGS>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI_WGS>;
   auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS>;
-  static bool configured = false;
-  if (!configured) {
-    LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+  // stage scale / bias of all N columns when that fits next to the operand ring (per-CTA budget: the whole SM, or half of
+  // it for the 2-CTAs/SM variant); otherwise the kernel refills a per-tile staging area
+  const int budget = (L::MIN_CTAS == 1 ? 227 * 1024 : 113 * 1024) - (L::VEC_OFF + 1024);
+  const int vec_all = (2 * p.N * 4 <= budget) ? 1 : 0;
+  const int smem = L::VEC_OFF + 1024 + (vec_all ? (2 * p.N * 4 > L::VEC_TILE_BYTES ? 2 * p.N * 4 : L::VEC_TILE_BYTES) : L::VEC_TILE_BYTES);
+  static int configured = 0;
+  if (smem > configured) {
+    LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
   const long long total = 1LL * m_tiles * (p.N / BN);
   LAVT_REQUIRE(total < (1LL << 30), "gemm: too many tiles (%lld)", total);
   const long long slots = 1LL * sm_count() * L::MIN_CTAS;
   const int grid = static_cast<int>(total < slots ? total : slots);
-  kfn<<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, p, m_tiles);
+  long long* trace = nullptr;
+  const char* trace_path = getenv("LAVT_GEMM_TRACE");
+  if (trace_path) {
+    LAVT_CUDA(cudaMalloc(&trace, 6 * 32 * sizeof(long long)));
+    LAVT_CUDA(cudaMemsetAsync(trace, 0, 6 * 32 * sizeof(long long), stream));
+  }
+  kfn<<<grid, L::THREADS, smem, stream>>>(tmA, tmB, p, m_tiles, vec_all, trace);
   LAVT_LAUNCH_CHECK("gemm_bf16_tc_kernel");
+  if (trace) {
+    // debug only: synchronous dump of CTA 0's event clocks (rows: acc free, first operands, MMAs issued, acc ready, epilogue end, first TMA)
+    long long host[6 * 32];
+    LAVT_CUDA(cudaStreamSynchronize(stream));
+    LAVT_CUDA(cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int e = 0; e < 6; ++e) {
+        for (int t = 0; t < 32; ++t) fprintf(f, "%lld ", host[e * 32 + t]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return LAVT_OK;
 }
 

@@ -41,8 +41,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -61,7 +61,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     set_last_error("TMA base pointer %p not 16-byte aligned", base);
     return LAVT_ERR_SHAPE;
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
                   gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -70,6 +70,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return LAVT_ERR_CUDA;
   }
   return LAVT_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swz);
 }
 
 const char* last_error() { return g_err; }
