@@ -328,14 +328,27 @@ def main():
     at = fam.get("window_attn_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    # DRAM bytes per launch of the dominant kernel: from the committed ncu capture of this same command
+    # (tools/ncu_r1_final.sh -> profiles/r1_dram_traffic_final.json); null if that summary is not in the tree
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_final.json")) as f:
+            tj = json.load(f)
+        if not a.window12:
+            traffic = tj["gemm_bf16_tc_kernel"]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r1_dram_traffic_final.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"kernel": "gemm_bf16_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None,
+                "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": traffic, "traffic_source": traffic_src,
+                "alg_bytes_per_launch": (g.get("bytes") / g["launches"]) if g.get("bytes") and g["launches"] else None,
                 "launches": g["launches"], "ms_per_step": g["ms"], "alg_flops_per_step": g["flops"],
                 # per launch the binding roof is max(FLOPs / tensor peak, algorithmic bytes / HBM peak): short-K Swin
                 # GEMMs (K = 128..256) are HBM-bound; this is sum(ideal) / sum(measured) over the step's launches
                 "alg_bytes_per_step": g.get("bytes"), "frac_vs_binding_roof": (g["ideal_ms"] / g["ms"]) if g["ms"] > 0 else None,
-                "attention_core": {"kernel": "window_attn_kernel", "launches": at["launches"], "ms_per_step": at["ms"],
+                "attention_core": {"kernel": "window_attn_tc_kernel (tcgen05/TMEM, windows <= 400 tokens) / window_attn_*_kernel (mma.sync)",
+                                   "impl": os.environ.get("LAVT_ATTN_IMPL", "auto"), "launches": at["launches"], "ms_per_step": at["ms"],
                                    "tflops": at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0},
                 "whole_step_tflops": flops_per_clip(a.window12) * value / world / 1e12}
 

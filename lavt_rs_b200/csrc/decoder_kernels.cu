@@ -18,55 +18,47 @@ __device__ __forceinline__ void bilinear_taps(int o, int in, int out, int& i0, i
   f = s - static_cast<float>(i0);
 }
 
-// thread per (pixel, 4 x 8 channels): the four 16-byte channel groups are independent loads in flight
+// thread per (pixel, 8-channel group): consecutive threads touch consecutive 16-byte chunks, so every load / store
+// instruction of a warp covers 512 contiguous bytes (the bilinear taps of neighbouring pixels share cache lines)
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ prev, int ph, int pw, int C1,
                                                               const __nv_bfloat16* __restrict__ skip, int C2,
                                                               __nv_bfloat16* __restrict__ out, int n_img, int H, int W) {
-  const int Ct = C1 + C2, g32 = Ct / 32;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n_img) * H * W * g32;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % g32);
-  const long long pix = idx / g32;
-  const int cbase = cg * 32;
-  const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H);
-  const long long img = pix / (static_cast<long long>(W) * H);
-  const bool same = (ph == H && pw == W);
-  int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
-  float fy = 0.f, fx = 0.f;
-  if (!same) {
+  // grid = (chunks of one output row, H, images): no 64-bit index arithmetic on the per-thread path
+  const int Ct = C1 + C2, g8 = Ct / 8;
+  const int xi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xi >= W * g8) return;
+  const int w = xi / g8;
+  const int c = (xi - w * g8) * 8;
+  const int h = blockIdx.y;
+  const long long img = blockIdx.z;
+  const long long pix = (img * H + h) * W + w;
+  uint4 r;
+  if (c >= C1) {
+    r = __ldg(reinterpret_cast<const uint4*>(skip + pix * C2 + (c - C1)));
+  } else if (ph == H && pw == W) {
+    r = __ldg(reinterpret_cast<const uint4*>(prev + pix * C1 + c));
+  } else {
+    int y0, y1, x0, x1;
+    float fy, fx;
     bilinear_taps(h, ph, H, y0, y1, fy);
     bilinear_taps(w, pw, W, x0, x1, fx);
-  }
-  const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-  const __nv_bfloat16* pbase = prev + img * ph * pw * C1;
-  uint4 r[4];
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    const __nv_bfloat16* pbase = prev + img * ph * pw * C1 + c;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y0) * pw + x0) * C1));
+    const uint4 bq = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y0) * pw + x1) * C1));
+    const uint4 cc = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y1) * pw + x0) * C1));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y1) * pw + x1) * C1));
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {bq.x, bq.y, bq.z, bq.w}, uc[4] = {cc.x, cc.y, cc.z, cc.w},
+                   ud[4] = {d.x, d.y, d.z, d.w};
+    uint32_t uo[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = cbase + k * 8;
-    if (c >= C1) {
-      r[k] = __ldg(reinterpret_cast<const uint4*>(skip + pix * C2 + (c - C1)));
-    } else if (same) {
-      r[k] = __ldg(reinterpret_cast<const uint4*>(prev + pix * C1 + c));
-    } else {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y0) * pw + x0) * C1 + c));
-      const uint4 b = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y0) * pw + x1) * C1 + c));
-      const uint4 cc = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y1) * pw + x0) * C1 + c));
-      const uint4 d = __ldg(reinterpret_cast<const uint4*>(pbase + (static_cast<long long>(y1) * pw + x1) * C1 + c));
-      const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {cc.x, cc.y, cc.z, cc.w},
-                     ud[4] = {d.x, d.y, d.z, d.w};
-      uint32_t uo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fa = unpack_bf16x2(ua[j]), fb = unpack_bf16x2(ub[j]), fc = unpack_bf16x2(uc[j]), fd = unpack_bf16x2(ud[j]);
-        uo[j] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                            w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
-      }
-      r[k] = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_bf16x2(ua[j]), fb = unpack_bf16x2(ub[j]), fc = unpack_bf16x2(uc[j]), fd = unpack_bf16x2(ud[j]);
+      uo[j] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
     }
+    r = make_uint4(uo[0], uo[1], uo[2], uo[3]);
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + pix * Ct + cbase + k * 8) = r[k];
+  *reinterpret_cast<uint4*>(out + pix * Ct + c) = r;
 }
 
 int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,
@@ -74,9 +66,9 @@ int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, 
   LAVT_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 > 0 && (C1 + C2) % 32 == 0,
                "upsample_concat: channels must be multiples of 8 and their sum a multiple of 32");
   LAVT_REQUIRE(ph <= H && pw <= W && ph > 0 && pw > 0, "upsample_concat: prev (%dx%d) larger than skip (%dx%d)", ph, pw, H, W);
-  const long long total = static_cast<long long>(n_img) * H * W * ((C1 + C2) / 32);
-  LAVT_REQUIRE(total > 0, "upsample_concat: empty input");
-  upsample_concat_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prev, ph, pw, C1, skip, C2, out, n_img, H, W);
+  LAVT_REQUIRE(n_img > 0 && n_img < 65536 && H > 0 && H < 65536 && W > 0, "upsample_concat: empty or too large input");
+  const int per_row = W * ((C1 + C2) / 8);
+  upsample_concat_kernel<<<dim3((per_row + 255) / 256, H, n_img), 256, 0, st>>>(prev, ph, pw, C1, skip, C2, out, n_img, H, W);
   LAVT_LAUNCH_CHECK("upsample_concat_kernel");
   return LAVT_OK;
 }

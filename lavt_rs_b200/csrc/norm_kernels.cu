@@ -12,37 +12,65 @@
 
 namespace lavt {
 
-// NV = float4 per lane: Cn = NV * 128
-template <int MODE, int NV>
+// NV = float4 per lane: Cn = NV * 128.  Each warp handles RPW consecutive OUTPUT rows: their loads are all in flight
+// together, and the closed-form window gather (a dozen integer divisions per row, geom.cuh::win_token) is evaluated by
+// RPW lanes in parallel and broadcast by shuffle instead of being recomputed by all 32 lanes of a one-row warp (at
+// C = 128 that index arithmetic, not memory, bounded the gather kernel).
+template <int MODE, int NV, int RPW>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
-  const long long m = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (m >= p.M) return;
+  const long long m0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (m0 >= p.M) return;
   constexpr int Cn = NV * 128;
-  float4 v[NV];
+  float4 v[RPW][NV];
+  long long myrow = -1;
+  if (MODE == MODE_WINDOW) {
+    if (lane < RPW && m0 + lane < p.M) myrow = win_token(p.win, m0 + lane).row;
+  }
+  bool live[RPW];
 
-  if (MODE == MODE_MERGE) {
-    // out row m <-> (b, d, h2, w2); channel block q of 4 <-> source pixel (2*h2 + (q&1), 2*w2 + (q>>1))
-    const int H2 = (p.mH + 1) >> 1, W2 = (p.mW + 1) >> 1;
-    const int w2 = static_cast<int>(m % W2);
-    const int h2 = static_cast<int>((m / W2) % H2);
-    const long long bd = m / (static_cast<long long>(W2) * H2);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = (i * 32 + lane) * 4;           // column in [0, 4C)
-      const int q = col / p.C, c = col - q * p.C;
-      const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
-      if (h < p.mH && w < p.mW) {
-        const float* src = p.x + ((bd * p.mH + h) * p.mW + w) * p.ldx + c;
-        v[i] = __ldg(reinterpret_cast<const float4*>(src));
-      } else {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < RPW; ++r) {
+    const long long m = m0 + r;
+    live[r] = m < p.M;
+    if (MODE == MODE_MERGE) {
+      // out row m <-> (b, d, h2, w2); channel block q of 4 <-> source pixel (2*h2 + (q&1), 2*w2 + (q>>1))
+      const int H2 = (p.mH + 1) >> 1, W2 = (p.mW + 1) >> 1;
+      const long long mm = live[r] ? m : p.M - 1;
+      const int w2 = static_cast<int>(mm % W2);
+      const int h2 = static_cast<int>((mm / W2) % H2);
+      const long long bd = mm / (static_cast<long long>(W2) * H2);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 4;           // column in [0, 4C)
+        const int q = col / p.C, c = col - q * p.C;
+        const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
+        if (h < p.mH && w < p.mW) {
+          const float* src = p.x + ((bd * p.mH + h) * p.mW + w) * p.ldx + c;
+          v[r][i] = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
+    } else {
+      long long row = live[r] ? m : p.M - 1;
+      if (MODE == MODE_WINDOW) {
+        row = __shfl_sync(0xffffffffu, myrow, r);
+        if (row < 0) live[r] = false;                  // pad row (zeros written below) or past the end
+      }
+      const float4* src = reinterpret_cast<const float4*>(p.x + (row < 0 ? 0 : row) * p.ldx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[r][i] = live[r] ? __ldg(src + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else {
-    long long row = m;
-    if (MODE == MODE_WINDOW) row = win_token(p.win, m).row;
-    if (row < 0) {   // pad row: zeros AFTER the norm (F.pad follows norm1 in the reference)
+  }
+
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const long long m = m0 + r;
+    if (m >= p.M) break;
+    if (!live[r]) {   // window pad row: zeros AFTER the norm (F.pad follows norm1 in the reference)
       if (p.out_bf16) {
         uint2* o = reinterpret_cast<uint2*>(p.out_bf16 + m * Cn);
 #pragma unroll
@@ -53,57 +81,55 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) o[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      return;
+      continue;
     }
-    const float4* src = reinterpret_cast<const float4*>(p.x + row * p.ldx);
+    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = __ldg(src + i * 32 + lane);
+    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    const float mean = warp_sum(s) * (1.0f / Cn);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / Cn) + p.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+      float4 y;
+      y.x = (v[r][i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[r][i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[r][i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[r][i].w - mean) * rstd * g.w + b.w;
+      if (p.out_bf16)
+        reinterpret_cast<uint2*>(p.out_bf16 + m * Cn)[i * 32 + lane] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+      if (p.out_f32) reinterpret_cast<float4*>(p.out_f32 + m * Cn)[i * 32 + lane] = y;
+    }
   }
+}
 
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) * (1.0f / Cn);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    ss += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / Cn) + p.eps);
-
-  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
-    float4 y;
-    y.x = (v[i].x - mean) * rstd * g.x + b.x;
-    y.y = (v[i].y - mean) * rstd * g.y + b.y;
-    y.z = (v[i].z - mean) * rstd * g.z + b.z;
-    y.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (p.out_bf16)
-      reinterpret_cast<uint2*>(p.out_bf16 + m * Cn)[i * 32 + lane] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
-    if (p.out_f32) reinterpret_cast<float4*>(p.out_f32 + m * Cn)[i * 32 + lane] = y;
-  }
+template <int MODE, int NV, int RPW>
+static void launch_ln_nv(const LnParams& p, cudaStream_t st) {
+  const int warps = 8;
+  const long long rows_per_block = static_cast<long long>(warps) * RPW;
+  const long long blocks = (p.M + rows_per_block - 1) / rows_per_block;
+  ln_rows_kernel<MODE, NV, RPW><<<dim3(static_cast<unsigned>(blocks)), 256, 0, st>>>(p);
 }
 
 template <int MODE>
 static int launch_ln(const LnParams& p, int Cn, cudaStream_t st) {
-  const int warps = 8;
-  const long long blocks = (p.M + warps - 1) / warps;
-  LAVT_REQUIRE(blocks < (1LL << 31), "layernorm: too many rows");
-  dim3 grid(static_cast<unsigned>(blocks));
-  switch (Cn / 128) {
-    case 1: ln_rows_kernel<MODE, 1><<<grid, 256, 0, st>>>(p); break;
-    case 2: ln_rows_kernel<MODE, 2><<<grid, 256, 0, st>>>(p); break;
-    case 3: ln_rows_kernel<MODE, 3><<<grid, 256, 0, st>>>(p); break;
-    case 4: ln_rows_kernel<MODE, 4><<<grid, 256, 0, st>>>(p); break;
-    case 6: ln_rows_kernel<MODE, 6><<<grid, 256, 0, st>>>(p); break;
-    case 8: ln_rows_kernel<MODE, 8><<<grid, 256, 0, st>>>(p); break;
-    case 12: ln_rows_kernel<MODE, 12><<<grid, 256, 0, st>>>(p); break;
-    case 16: ln_rows_kernel<MODE, 16><<<grid, 256, 0, st>>>(p); break;
-    case 24: ln_rows_kernel<MODE, 24><<<grid, 256, 0, st>>>(p); break;
+  LAVT_REQUIRE((p.M + 7) / 8 < (1LL << 31), "layernorm: too many rows");
+  switch (Cn / 128) {   // rows per warp chosen so that the row data of a warp stays in registers (<= 16 float4 per lane)
+    case 1: launch_ln_nv<MODE, 1, 8>(p, st); break;
+    case 2: launch_ln_nv<MODE, 2, 8>(p, st); break;
+    case 3: launch_ln_nv<MODE, 3, 4>(p, st); break;
+    case 4: launch_ln_nv<MODE, 4, 4>(p, st); break;
+    case 6: launch_ln_nv<MODE, 6, 2>(p, st); break;
+    case 8: launch_ln_nv<MODE, 8, 2>(p, st); break;
+    case 12: launch_ln_nv<MODE, 12, 1>(p, st); break;
+    case 16: launch_ln_nv<MODE, 16, 1>(p, st); break;
+    case 24: launch_ln_nv<MODE, 24, 1>(p, st); break;
     default:
       set_last_error("layernorm: normalised width %d not supported (need 128 * {1,2,3,4,6,8,12,16,24})", Cn);
       return LAVT_ERR_SHAPE;
