@@ -40,19 +40,28 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--clips-per-gpu", type=int, default=8)
     p.add_argument("--window12", action="store_true", help="(8,12,12) windows instead of the default (8,7,7)")
+    p.add_argument("--sep-t-pwam", action="store_true",
+                   help="the reference README's video configuration: SepTPWAM fusion (--sep_t_pwam --conv3d_kernel_size_t 3-3-3 "
+                        "--conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1), 3118 GFLOP per clip")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
 
+SEP_T_PWAM = False      # set from --sep-t-pwam in main()
+SEP_FLAGS = ["--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel_size_s", "1-1-1", "--w_t3x3_s1x1", "--mm_t3x3_s1x1"]
+
+
 def flops_per_clip(window12: bool) -> float:
-    # BASELINE.md section 2 (measured with torch.utils.flop_counter on the reference), minus BERT (3.4 GFLOP)
-    return (2198.4e9 if window12 else 2074.8e9) - 3.4e9
+    # BASELINE.md section 2 (measured with torch.utils.flop_counter on the reference), minus BERT (3.4 GFLOP);
+    # SepTPWAM adds four Conv3d(3,3,3) per stage: +1043.6 GFLOP (3118.4 vs 2074.8 at window 8x7x7)
+    return (2198.4e9 if window12 else 2074.8e9) - 3.4e9 + (1043.6e9 if SEP_T_PWAM else 0.0)
 
 
 def model_args(window12: bool):
     from lavt_rs_b200.args import default_args
-    return default_args(["--model", "lavt_video", "--swin_type", "base"] + (["--window12"] if window12 else []))
+    return default_args(["--model", "lavt_video", "--swin_type", "base"] + (["--window12"] if window12 else [])
+                        + (SEP_FLAGS if SEP_T_PWAM else []))
 
 
 def build_model(window12: bool, device):
@@ -124,6 +133,7 @@ def cpu_forward_time(window12: bool, sd_cpu, n_runs: int, threads: int):
     from oracle import lavt_oracle as O
     torch.set_num_threads(threads)
     cfg = O.OracleConfig.swin("base", window12=window12, video=True)
+    cfg.sep_t_pwam = SEP_T_PWAM
     x, l, m = synth_batch(1, 100)
     times, out = [], None
     with torch.no_grad():
@@ -164,7 +174,9 @@ def run_reference(a):
 
 
 def main():
+    global SEP_T_PWAM
     a = parse()
+    SEP_T_PWAM = bool(a.sep_t_pwam)
     if a.impl == "reference":
         return run_reference(a)
 
@@ -334,7 +346,7 @@ def main():
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_final.json")) as f:
             tj = json.load(f)
-        if not a.window12:
+        if not a.window12 and not SEP_T_PWAM:
             traffic = tj["gemm_bf16_tc_kernel"]["dram_bytes_per_launch"]
             traffic_src = "profiles/r1_dram_traffic_final.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
     except (OSError, KeyError, ValueError):
@@ -359,7 +371,8 @@ def main():
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "LAVT-RS Video Swin-B forward (hot path after BERT), 8x384x384 clips, 20-token expression",
-                   "window": "8x12x12" if a.window12 else "8x7x7", "clips_per_gpu_per_step": B, "global_clips_per_step": total_clips,
+                   "window": "8x12x12" if a.window12 else "8x7x7", "fusion": "SepTPWAM (README video flags)" if SEP_T_PWAM else "PWAM",
+                   "clips_per_gpu_per_step": B, "global_clips_per_step": total_clips,
                    "parallelism": f"clip-sharded x{world}, no collectives", "cuda_graph": graph is not None,
                    "l2": "two rotating input batches; per-step activations (>1 GB) exceed the 126 MB L2",
                    "flops_per_clip": flops_per_clip(a.window12)},

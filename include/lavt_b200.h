@@ -81,6 +81,14 @@ int lavt_gemm_bf16(const void* A, int64_t lda, const void* Wt, int64_t ldw, int3
 int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H, int32_t W, int32_t Cin,
                       const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream);
 
+/* 3x3x3 / pad 1 / stride 1 Conv3d as an implicit GEMM over NDHWC bf16 input (position pitch ldx >= Cin), 5-D TMA boxes:
+ *   out[pos, co] = epilogue( sum_{kz,ky,kx,ci} x[clip, d+kz-1, h+ky-1, w+kx-1, ci] * Wt[co, ((kz*3+ky)*3+kx)*Cin + ci] )
+ * Replaces the Conv3d(3,3,3) layers of SepTPWAM (temporal_vis_project / f_query_t / W_t / project_mm_t,
+ * lib/video_swin_transformer.py:1334-1336, 1376-1379, 1435-1438, 1459-1461) under the README video flags
+ * (--sep_t_pwam --conv3d_kernel_size_t 3-3-3 ...).  Requires Cin % 64 == 0, Cout % 128 == 0. */
+int lavt_conv3d_bf16(const void* x_ndhwc, int64_t ldx, int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                     const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream);
+
 /* ---- LayerNorm fused with the gathers that feed the GEMMs (fp32 rows in, bf16 and/or fp32 rows out) ---- */
 
 /* out[m,:] = LN(x[m,:]) * gamma + beta over C channels.  norm2 before the MLP (lib/video_swin_transformer.py:250),
@@ -130,6 +138,11 @@ int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, cons
                      void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream);
 /* out = vis * IN(lang_pre) (vis, out bf16; lang_pre fp32 [B,n,C]) -- the A operand of project_mm */
 int lavt_pwam_mul_norm(const void* vis_bf16, const float* lang, const float* stats, void* out_bf16, int32_t B,
+                       int64_t n, int32_t C, void* stream);
+
+/* out = InstanceNorm(a) + InstanceNorm(b) with precomputed statistics (fp32 [B,n,C]; out may alias a): SepTPWAM sums its
+ * temporal and spatial branches after their InstanceNorm3d (lib/video_swin_transformer.py:1513-1524, 1556-1561) */
+int lavt_instnorm_sum2(const float* a, const float* stats_a, const float* b, const float* stats_b, float* out, int32_t B,
                        int64_t n, int32_t C, void* stream);
 
 /* ---- decoder glue (lib/mask_predictor.py:56-99, lib/_utils.py:106) ---- */

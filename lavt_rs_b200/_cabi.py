@@ -77,6 +77,7 @@ SIGNATURES = {
     "lavt_check_device": [],
     "lavt_gemm_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _EP, _vp],
     "lavt_conv3x3_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _EP, _vp],
+    "lavt_conv3d_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _EP, _vp],
     "lavt_layernorm_rows": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp],
     "lavt_layernorm_window_gather": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp],
     "lavt_patch_merge_layernorm": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp],
@@ -86,6 +87,7 @@ SIGNATURES = {
     "lavt_pwam_kv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_pwam_attend": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_pwam_mul_norm": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "lavt_instnorm_sum2": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_upsample_concat": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp],
     "lavt_conv1x1_logits": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -242,6 +244,23 @@ def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
               f"conv {n_img}x{H}x{W} Cin{Cin} Cout{Cout}")
 
 
+def conv3d_bf16(x_ndhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:
+    """x [n_clip,D,H,W,Cin] bf16 NDHWC; w_taps [Cout, 27*Cin] bf16 (tap-major: ((kz*3+ky)*3+kx)*Cin+ci)."""
+    _req(x_ndhwc, torch.bfloat16, "x")
+    _req(w_taps, torch.bfloat16, "w_taps")
+    n_clip, D, H, W, Cin = x_ndhwc.shape
+    if not x_ndhwc.is_contiguous():
+        raise LavtError("conv3d: x must be contiguous NDHWC")
+    Cout = w_taps.shape[0]
+    e = make_epilogue(**epi)
+    t0 = TIMER.begin()
+    check(lib().lavt_conv3d_bf16(x_ndhwc.data_ptr(), Cin, n_clip, D, H, W, Cin, w_taps.data_ptr(), Cout,
+                                 C.byref(e), stream_ptr()), "lavt_conv3d_bf16")
+    npos = n_clip * D * H * W
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * npos * Cout * 27 * Cin, 2.0 * (npos * Cin + Cout * 27 * Cin + npos * Cout),
+              f"conv3d {n_clip}x{D}x{H}x{W} Cin{Cin} Cout{Cout}")
+
+
 # ------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------
@@ -359,6 +378,14 @@ def pwam_mul_norm(vis, lang, stats, out) -> None:
     check(lib().lavt_pwam_mul_norm(vis.data_ptr(), _c(lang, torch.float32, "lang").data_ptr(),
                                    _c(stats, torch.float32, "stats").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
                                    B, n, Cn, stream_ptr()), "lavt_pwam_mul_norm")
+
+
+def instnorm_sum2(a, stats_a, b, stats_b, out) -> None:
+    """out = IN(a) + IN(b); a, b, out fp32 [B,n,C]; stats fp32 [B,2,C] (mean, rstd)."""
+    B, n, Cn = a.shape
+    check(lib().lavt_instnorm_sum2(_c(a, torch.float32, "a").data_ptr(), _c(stats_a, torch.float32, "stats_a").data_ptr(),
+                                   _c(b, torch.float32, "b").data_ptr(), _c(stats_b, torch.float32, "stats_b").data_ptr(),
+                                   _c(out, torch.float32, "out").data_ptr(), B, n, Cn, stream_ptr()), "lavt_instnorm_sum2")
 
 
 def upsample_concat(prev, skip, out) -> None:

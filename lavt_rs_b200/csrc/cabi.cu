@@ -69,6 +69,19 @@ int lavt_gemm_bf16(const void* A, int64_t lda, const void* Wt, int64_t ldw, int3
   return gemm_dispatch(A, lda, Wt, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
+static void conv_pick_tile(GemmParams& p, int H, int W) {
+  // 128-pixel tile: widest power-of-two strip that wastes the least padded area
+  int best_tw = 8; long long best_area = -1;
+  for (int tw = 8; tw <= 128; tw *= 2) {
+    int th = 128 / tw;
+    long long area = 1LL * ((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
+    if (best_area < 0 || area < best_area || (area == best_area && tw > best_tw)) { best_area = area; best_tw = tw; }
+  }
+  p.cTW = best_tw; p.cTH = 128 / best_tw;
+  p.cTilesW = (W + p.cTW - 1) / p.cTW;
+  p.cTilesH = (H + p.cTH - 1) / p.cTH;
+}
+
 int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H, int32_t W, int32_t Cin,
                       const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream) {
   GemmParams p;
@@ -80,17 +93,24 @@ int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H,
   LAVT_REQUIRE(p.rowmap == ROWMAP_IDENTITY, "conv: window row map not applicable");
   p.rowmap = ROWMAP_CONV;
   p.cH = H; p.cW = W; p.cCin = Cin; p.taps = 9;
-  // 128-pixel tile: widest power-of-two strip that wastes the least padded area
-  int best_tw = 8; long long best_area = -1;
-  for (int tw = 8; tw <= 128; tw *= 2) {
-    int th = 128 / tw;
-    long long area = 1LL * ((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
-    if (best_area < 0 || area < best_area || (area == best_area && tw > best_tw)) { best_area = area; best_tw = tw; }
-  }
-  p.cTW = best_tw; p.cTH = 128 / best_tw;
-  p.cTilesW = (W + p.cTW - 1) / p.cTW;
-  p.cTilesH = (H + p.cTH - 1) / p.cTH;
+  conv_pick_tile(p, H, W);
   return gemm_dispatch(x_nhwc, ldx, Wt, 9LL * Cin, p, static_cast<cudaStream_t>(stream));
+}
+
+int lavt_conv3d_bf16(const void* x_ndhwc, int64_t ldx, int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                     const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream) {
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  LAVT_REQUIRE(n_clip > 0 && D > 0 && H > 0 && W > 0, "conv3d: empty input");
+  LAVT_REQUIRE(1LL * n_clip * D * H * W < (1LL << 31), "conv3d: too many output positions");
+  p.M = n_clip * D * H * W; p.N = Cout; p.K = 27 * Cin;
+  int rc = fill_epilogue(p, epi);
+  if (rc) return rc;
+  LAVT_REQUIRE(p.rowmap == ROWMAP_IDENTITY, "conv3d: window row map not applicable");
+  p.rowmap = ROWMAP_CONV;
+  p.cH = H; p.cW = W; p.cCin = Cin; p.taps = 27; p.cD = D;
+  conv_pick_tile(p, H, W);
+  return gemm_dispatch(x_ndhwc, ldx, Wt, 27LL * Cin, p, static_cast<cudaStream_t>(stream));
 }
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
@@ -164,6 +184,11 @@ int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, cons
 int lavt_pwam_mul_norm(const void* vis_bf16, const float* lang, const float* stats, void* out_bf16, int32_t B,
                        int64_t n, int32_t C, void* stream) {
   return pwam_mul_dispatch(CB(vis_bf16), lang, stats, MB(out_bf16), B, n, C, S(stream));
+}
+
+int lavt_instnorm_sum2(const float* a, const float* stats_a, const float* b, const float* stats_b, float* out, int32_t B,
+                       int64_t n, int32_t C, void* stream) {
+  return instnorm_sum2_dispatch(a, stats_a, b, stats_b, out, B, n, C, S(stream));
 }
 
 int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,

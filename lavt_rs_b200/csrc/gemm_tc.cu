@@ -181,11 +181,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles;
         const int n0 = (tile - mt * n_tiles) * GEMM_BN;
-        int img = 0, h0 = 0, w0 = 0;
+        int img = 0, h0 = 0, w0 = 0, d0 = 0;
         if (conv) {
           const int tw = mt % p.cTilesW;
           const int th = (mt / p.cTilesW) % p.cTilesH;
-          img = mt / (p.cTilesW * p.cTilesH);
+          img = mt / (p.cTilesW * p.cTilesH);          // 2-D: image; 3-D: clip * D + frame
+          if (p.taps == 27) {
+            d0 = img % p.cD;
+            img /= p.cD;
+          }
           h0 = th * p.cTH;
           w0 = tw * p.cTW;
         }
@@ -199,9 +203,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           if (conv) {
             const int tap = kb / cpb, cc = kb - tap * cpb;
-            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-            tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
+            if (p.taps == 27) {
+              // 3x3x3: tap = (kz * 3 + ky) * 3 + kx; frames outside the clip are zero-filled by TMA like the spatial border
+              const int dz = tap / 9 - 1, r9 = tap % 9;
+              tma_load_5d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + r9 % 3 - 1, h0 + r9 / 3 - 1, d0 + dz, img);
+            } else {
+              const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+              const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+              tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
+            }
           } else {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
           }
@@ -492,11 +502,21 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     LAVT_REQUIRE(p.cCin % GEMM_BK == 0, "conv: Cin=%d must be a multiple of 64", p.cCin);
     LAVT_REQUIRE(p.cTH * p.cTW == GEMM_BM, "conv: tile %dx%d != 128 pixels", p.cTH, p.cTW);
     LAVT_REQUIRE(p.K == p.taps * p.cCin, "conv: K mismatch");
-    const int n_img = p.M / (p.cH * p.cW);
-    uint64_t dims[4] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
-    uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH};
-    uint32_t box[4] = {GEMM_BK, (uint32_t)p.cTW, (uint32_t)p.cTH, 1};
-    int rc = make_tmap_bf16(&tmA, A, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int n_img = p.M / (p.cH * p.cW);             // 2-D: images; 3-D: clips * frames
+    int rc;
+    if (p.taps == 27) {
+      LAVT_REQUIRE(p.cD >= 1 && n_img % p.cD == 0, "conv3d: %d frames do not split into clips of %d", n_img, p.cD);
+      uint64_t dims[5] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)p.cD, (uint64_t)(n_img / p.cD)};
+      uint64_t strides[4] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH,
+                             (uint64_t)lda * 2 * p.cW * p.cH * p.cD};
+      uint32_t box[5] = {GEMM_BK, (uint32_t)p.cTW, (uint32_t)p.cTH, 1, 1};
+      rc = make_tmap_bf16(&tmA, A, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      uint64_t dims[4] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
+      uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH};
+      uint32_t box[4] = {GEMM_BK, (uint32_t)p.cTW, (uint32_t)p.cTH, 1};
+      rc = make_tmap_bf16(&tmA, A, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
     m_tiles = n_img * p.cTilesH * p.cTilesW;
   } else {

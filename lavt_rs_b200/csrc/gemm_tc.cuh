@@ -28,7 +28,8 @@ struct GemmParams {
   int cH, cW, cCin;          // image height/width, input channels
   int cTH, cTW;              // tile = cTH x cTW pixels (cTH*cTW == 128)
   int cTilesH, cTilesW;      // tiles per image
-  int taps;                  // 9 (3x3) or 1
+  int taps;                  // 9 (3x3), 27 (3x3x3) or 1
+  int cD;                    // frames per clip for the 3-D conv (A is (C, W, H, D, Nclip)); 0 / 1 = 2-D
 };
 
 }  // namespace lavt

@@ -25,6 +25,8 @@ int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long
                            int W, cudaStream_t st);
 long long colstats_workspace_floats(int B, long long n, int C);
 int colstats_dispatch(const float* x, float* stats, float* workspace, int B, long long n, int C, float eps, cudaStream_t st);
+int instnorm_sum2_dispatch(const float* a, const float* sa, const float* b, const float* sb, float* out, int B, long long n,
+                           int C, cudaStream_t st);
 int pwam_mul_dispatch(const __nv_bfloat16* vis, const float* lang, const float* stats, __nv_bfloat16* out, int B,
                       long long n, int C, cudaStream_t st);
 

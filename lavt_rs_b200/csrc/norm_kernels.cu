@@ -323,4 +323,40 @@ int pwam_mul_dispatch(const __nv_bfloat16* vis, const float* lang, const float* 
   return LAVT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// out = IN(a) + IN(b) = (a - mean_a) * rstd_a + (b - mean_b) * rstd_b   (fp32, stats (B,2,C) each; out may alias a)
+// SepTPWAM sums a temporal (3x3x3) and a spatial (1x1x1) branch AFTER their InstanceNorm3d
+// (reference lib/video_swin_transformer.py:1513-1524, 1556-1561)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) instnorm_sum2_kernel(const float* __restrict__ a, const float* __restrict__ sa,
+                                                            const float* __restrict__ b, const float* __restrict__ sb,
+                                                            float* __restrict__ out, long long n, int C, long long total4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % (C / 4));
+  const long long row = i / (C / 4);
+  const int bi = static_cast<int>(row / n);
+  const float4 ma = __ldg(reinterpret_cast<const float4*>(sa + (static_cast<long long>(bi) * 2) * C) + c4);
+  const float4 ra = __ldg(reinterpret_cast<const float4*>(sa + (static_cast<long long>(bi) * 2 + 1) * C) + c4);
+  const float4 mb = __ldg(reinterpret_cast<const float4*>(sb + (static_cast<long long>(bi) * 2) * C) + c4);
+  const float4 rb = __ldg(reinterpret_cast<const float4*>(sb + (static_cast<long long>(bi) * 2 + 1) * C) + c4);
+  const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+  float4 o;
+  o.x = (x.x - ma.x) * ra.x + (y.x - mb.x) * rb.x;
+  o.y = (x.y - ma.y) * ra.y + (y.y - mb.y) * rb.y;
+  o.z = (x.z - ma.z) * ra.z + (y.z - mb.z) * rb.z;
+  o.w = (x.w - ma.w) * ra.w + (y.w - mb.w) * rb.w;
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+int instnorm_sum2_dispatch(const float* a, const float* sa, const float* b, const float* sb, float* out, int B, long long n,
+                           int C, cudaStream_t st) {
+  LAVT_REQUIRE(C % 4 == 0, "instnorm_sum2: C must be a multiple of 4");
+  const long long total4 = static_cast<long long>(B) * n * (C / 4);
+  LAVT_REQUIRE(total4 > 0 && (total4 + 255) / 256 < (1LL << 31), "instnorm_sum2: empty or too large input");
+  instnorm_sum2_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(a, sa, b, sb, out, n, C, total4);
+  LAVT_LAUNCH_CHECK("instnorm_sum2_kernel");
+  return LAVT_OK;
+}
+
 }  // namespace lavt

@@ -202,6 +202,83 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     return r32
 
 
+def sep_t_pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, D: int,
+                    H: int, W: int, ws: Workspace, gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SepTPWAM + LanguageGate under the README video flags (reference SepTPWAM.forward :1480-1584): every projection of
+    ``pwam_gate`` is the sum of a Conv3d(3,3,3) branch (implicit GEMM over NDHWC with 5-D TMA boxes) and a Conv3d(1,1,1)
+    branch (plain GEMM).  x fp32 [B*n, C] is updated in place with the gated residual; returns r fp32 [B*n, C]."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    heads = fusion.num_heads
+    Nl = l.shape[-1]
+
+    def w333(name, conv):     # (Cout, Cin, kz, ky, kx) -> [Cout, ((kz*3+ky)*3+kx)*Cin + ci]
+        return pw.get(name, [conv.weight], lambda: _bf16(conv.weight.detach().permute(0, 2, 3, 4, 1).reshape(conv.weight.shape[0], -1)))
+
+    def w111(name, conv):
+        return pw.get(name, [conv.weight], lambda: _bf16(conv.weight.detach().reshape(conv.weight.shape[0], -1)))
+
+    def b_(conv):
+        return conv.bias.detach()
+
+    xb5 = xb.view(B, D, H, W, C)
+    t32 = ws.get("sp_t32", (N_, C), torch.float32, dev)              # temporal-branch result waiting for the spatial one
+    # ts_vis = GELU(conv333(x)) + GELU(conv111(x))                     (:1487-1503)
+    vt, vs_ = fusion.temporal_vis_project[0], fusion.spatial_vis_project[0]
+    K.conv3d_bf16(xb5, w333("vis_t", vt), bias=b_(vt), act=K.ACT_GELU, out_f32=t32)
+    vis = ws.get("pw_vis", (B, n, C), torch.bfloat16, dev)
+    K.gemm_bf16(xb, w111("vis_s", vs_), bias=b_(vs_), act=K.ACT_GELU, resid=t32, out_bf16=vis.view(N_, C))
+    # query = IN3d(conv333(x)) + IN3d(conv111(x))                      (:1512-1524)
+    qa = ws.get("pw_q", (B, n, C), torch.float32, dev)
+    qb = ws.get("sp_qb", (B, n, C), torch.float32, dev)
+    sa = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
+    sb = ws.get("sp_stats_b", (B, 2, C), torch.float32, dev)
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), torch.float32, dev)
+    qt, qs = fusion.f_query_t[0], fusion.f_query_s[0]
+    K.conv3d_bf16(xb5, w333("q_t", qt), bias=b_(qt), out_f32=qa.view(N_, C))
+    K.gemm_bf16(xb, w111("q_s", qs), bias=b_(qs), out_f32=qb.view(N_, C))
+    K.instnorm_stats(qa, sa, stw)
+    K.instnorm_stats(qb, sb, stw)
+    K.instnorm_sum2(qa, sa, qb, sb, qa)
+    ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
+    # words: k, v and the masked softmax are those of PWAM             (:1534-1553)
+    k_w = pw.get("k_w", [fusion.f_key[0].weight], lambda: _f32(_conv1x1_w(fusion.f_key[0])))
+    v_w = pw.get("v_w", [fusion.f_value[0].weight], lambda: _f32(_conv1x1_w(fusion.f_value[0])))
+    kk = ws.get("pw_k", (B, Nl, C), torch.float32, dev)
+    vv = ws.get("pw_v", (B, Nl, C), torch.float32, dev)
+    K.pwam_kv(l, mask, k_w, b_(fusion.f_key[0]), v_w, b_(fusion.f_value[0]), kk, vv)
+    o = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
+    K.pwam_attend(qa, ident, kk, vv, mask, o, heads)
+    # lang = IN3d(conv333(o)) + IN3d(conv111(o))                       (:1556-1561)
+    Wt, Ws = fusion.W_t[0], fusion.W_s[0]
+    K.conv3d_bf16(o.view(B, D, H, W, C), w333("W_t", Wt), bias=b_(Wt), out_f32=qa.view(N_, C))
+    K.gemm_bf16(o.view(N_, C), w111("W_s", Ws), bias=b_(Ws), out_f32=qb.view(N_, C))
+    K.instnorm_stats(qa, sa, stw)
+    K.instnorm_stats(qb, sb, stw)
+    K.instnorm_sum2(qa, sa, qb, sb, qa)
+    a2 = o  # o is dead after the W projections
+    K.pwam_mul_norm(vis, qa, ident, a2)
+    # r = GELU(conv333(mm)) + GELU(conv111(mm))                         (:1574-1578)
+    mt, ms = fusion.project_mm_t[0], fusion.project_mm_s[0]
+    K.conv3d_bf16(a2.view(B, D, H, W, C), w333("mm_t", mt), bias=b_(mt), act=K.ACT_GELU, out_f32=t32)
+    r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+    rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+    K.gemm_bf16(a2.view(N_, C), w111("mm_s", ms), bias=b_(ms), act=K.ACT_GELU, resid=t32, out_f32=r32, out_bf16=rb)
+    _count(19)
+    if res_gate is not None:
+        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1 = vis.view(N_, C)  # vis is dead
+        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
+        if gate_act != "tanh":
+            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+        _count(2)
+    return r32
+
+
 # ------------------------------------------------------------------------------------------------
 # PatchMerging (reference :289-311) and PatchEmbed3D (:616-634)
 # ------------------------------------------------------------------------------------------------

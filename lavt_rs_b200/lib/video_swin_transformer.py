@@ -163,6 +163,55 @@ class PWAM(nn.Module):
         return r.view(B, n, C)
 
 
+class SepTPWAM(nn.Module):
+    """Separated temporal / spatial PWAM (reference :1300-1584) in the configuration the reference README trains the
+    video models with: ``--sep_t_pwam --conv3d_kernel_size_t 3-3-3 --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1
+    --mm_t3x3_s1x1``.  Every PWAM projection is the sum of a Conv3d(3,3,3) and a Conv3d(1,1,1) branch; other kernel-size
+    / gate / fuse sub-flags of the reference are rejected (no silent fallback)."""
+
+    def __init__(self, dim, v_in_channels, l_in_channels, key_channels, value_channels, num_heads=0, dropout=0.0,
+                 conv3d_kernel_size_t=(3, 1, 1), conv3d_kernel_size_s=(1, 1, 1), w_3x3=False, mm_3x3=False, w_3=False,
+                 mm_3=False, sum_3_kernel_size=None, cat_reduce_kernel_size=None, w_t3x3_s1x1=None, mm_t3x3_s1x1=None,
+                 args=None):
+        super().__init__()
+        if tuple(conv3d_kernel_size_t) != (3, 3, 3) or tuple(conv3d_kernel_size_s) != (1, 1, 1):
+            raise NotImplementedError("SepTPWAM on the B200 path needs --conv3d_kernel_size_t 3-3-3 --conv3d_kernel_size_s 1-1-1")
+        if not (w_t3x3_s1x1 and mm_t3x3_s1x1) or w_3x3 or mm_3x3 or w_3 or mm_3 or sum_3_kernel_size or cat_reduce_kernel_size:
+            raise NotImplementedError("SepTPWAM on the B200 path needs --w_t3x3_s1x1 --mm_t3x3_s1x1 and no other W / mm / fuse flag")
+        for f in ("s_tanh_plus_1_gate_1_q", "s_tanh_plus_1_gate_1_v", "t_tanh_plus_1_gate_1_q", "t_tanh_plus_1_gate_1_v"):
+            if getattr(args, f, False):
+                raise NotImplementedError(f"--{f} is not implemented on the B200 path")
+        if dropout != 0.0:
+            raise NotImplementedError("fusion dropout > 0 is not supported on the B200 path")
+        if not (dim == v_in_channels == key_channels == value_channels):
+            raise NotImplementedError("SepTPWAM with differing channel widths is not supported on the B200 path")
+        self.num_heads = num_heads
+        c3 = dict(kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1))
+        c1 = dict(kernel_size=(1, 1, 1), stride=1, padding=0)
+        self.temporal_vis_project = nn.Sequential(nn.Conv3d(dim, dim, **c3), nn.GELU(), nn.Dropout(dropout))
+        self.spatial_vis_project = nn.Sequential(nn.Conv3d(dim, dim, **c1), nn.GELU(), nn.Dropout(dropout))
+        self.f_query_t = nn.Sequential(nn.Conv3d(v_in_channels, key_channels, **c3), nn.InstanceNorm3d(key_channels))
+        self.f_query_s = nn.Sequential(nn.Conv3d(v_in_channels, key_channels, **c1), nn.InstanceNorm3d(key_channels))
+        self.f_key = nn.Sequential(nn.Conv1d(l_in_channels, key_channels, kernel_size=1, stride=1))
+        self.f_value = nn.Sequential(nn.Conv1d(l_in_channels, value_channels, kernel_size=1, stride=1))
+        self.W_t = nn.Sequential(nn.Conv3d(value_channels, value_channels, **c3), nn.InstanceNorm3d(value_channels))
+        self.W_s = nn.Sequential(nn.Conv3d(value_channels, value_channels, **c1), nn.InstanceNorm3d(value_channels))
+        self.project_mm_t = nn.Sequential(nn.Conv3d(value_channels, value_channels, **c3), nn.GELU(), nn.Dropout(dropout))
+        self.project_mm_s = nn.Sequential(nn.Conv3d(value_channels, value_channels, **c1), nn.GELU(), nn.Dropout(dropout))
+        self.prepared = E.PreparedWeights()
+
+    def forward(self, x: torch.Tensor, l: torch.Tensor, l_mask: torch.Tensor) -> torch.Tensor:
+        """x (B,D,H,W,C); l (B,768,Nl); l_mask (B,Nl,1) -> x_residual (B,D*H*W,C)  (reference :1480-1584)."""
+        E.require_cuda(x, "x")
+        B, D, H, W, C = x.shape
+        n = D * H * W
+        xf = x.detach().float().reshape(B * n, C).contiguous()
+        xb = xf.to(torch.bfloat16)
+        r = torch.empty(B * n, C, device=x.device, dtype=torch.float32)
+        E.sep_t_pwam_gate(xf, xb, self, None, _lang(l), _mask(l_mask), B, D, H, W, E.workspace(x.device), r_f32=r)
+        return r.view(B, n, C)
+
+
 def _lang(l: torch.Tensor) -> torch.Tensor:
     return l.detach().to(torch.float32).contiguous()
 
@@ -174,8 +223,12 @@ def _mask(l_mask: torch.Tensor) -> torch.Tensor:
     return m.to(torch.float32).contiguous()
 
 
-_UNSUPPORTED_FLAGS = ("ts_pwam", "t_pwam", "t_pwam_comp", "sep_t_pwam", "seq_t_pwam", "sep_t_pwam_inner",
+_UNSUPPORTED_FLAGS = ("ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam", "sep_t_pwam_inner",
                       "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "hs", "lazy_pred")
+
+
+def _ksize(text, default):
+    return tuple(int(a) for a in str(text).split("-")) if text else default
 
 
 def check_args(args) -> None:
@@ -213,7 +266,19 @@ class MMBasicLayer(nn.Module):
                                    drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
                                    norm_layer=norm_layer, use_checkpoint=use_checkpoint)
             for i in range(depth)])
-        self.fusion = PWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop, attention=True)
+        self.sep_t_pwam = bool(getattr(args, "sep_t_pwam", False))
+        if self.sep_t_pwam:      # reference :470-479
+            self.fusion = SepTPWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop,
+                                   conv3d_kernel_size_t=_ksize(getattr(args, "conv3d_kernel_size_t", ""), (3, 1, 1)),
+                                   conv3d_kernel_size_s=_ksize(getattr(args, "conv3d_kernel_size_s", ""), (1, 1, 1)),
+                                   w_3x3=getattr(args, "w_3x3", False), mm_3x3=getattr(args, "mm_3x3", False),
+                                   w_3=getattr(args, "w_3", False), mm_3=getattr(args, "mm_3", False),
+                                   sum_3_kernel_size=getattr(args, "sum_3_kernel_size", None) or None,
+                                   cat_reduce_kernel_size=getattr(args, "cat_reduce_kernel_size", None) or None,
+                                   w_t3x3_s1x1=getattr(args, "w_t3x3_s1x1", False),
+                                   mm_t3x3_s1x1=getattr(args, "mm_t3x3_s1x1", False), args=args)
+        else:
+            self.fusion = PWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop, attention=True)
         self.has_gate = self.version == "default" and not (self.is_last_layer and use_checkpoint)
         if self.has_gate:
             self.res_gate = nn.Sequential(nn.Linear(dim, dim, bias=False), nn.ReLU(), nn.Linear(dim, dim, bias=False), nn.Tanh())
@@ -232,13 +297,19 @@ class MMBasicLayer(nn.Module):
         for i, blk in enumerate(self.blocks):
             E.swin_block(x, blk, B, D, H, W, self.window_size, blk.shifted, blk.clamp_window, ws,
                          xb_out=xb if i == self.depth - 1 else None)
+        if self.sep_t_pwam:
+            def fuse(gate):
+                E.sep_t_pwam_gate(x, xb, self.fusion, gate, l, mask, B, D, H, W, ws, r_f32=r_out)
+        else:
+            def fuse(gate):
+                E.pwam_gate(x, xb, self.fusion, gate, l, mask, B, ws, r_f32=r_out)
         if self.version == "none":      # fusion still produces the stage output; x is left untouched
-            E.pwam_gate(x, xb, self.fusion, None, l, mask, B, ws, r_f32=r_out)
+            fuse(None)
         elif self.version == "no_gate":  # ablation flag: plain residual add (tensor-container op, not a hot path)
-            E.pwam_gate(x, xb, self.fusion, None, l, mask, B, ws, r_f32=r_out)
+            fuse(None)
             x.add_(r_out)
         else:
-            E.pwam_gate(x, xb, self.fusion, self.res_gate if self.has_gate else None, l, mask, B, ws, r_f32=r_out)
+            fuse(self.res_gate if self.has_gate else None)
         if self.downsample is not None:
             H2, W2 = (H + 1) // 2, (W + 1) // 2
             nxt = ws.get("stage_x_%d" % (2 * C), (B * D * H2 * W2, 2 * C), torch.float32, dev)

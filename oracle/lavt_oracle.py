@@ -40,6 +40,8 @@ class OracleConfig:
     clamp_window: bool = True                     # 3-D backbone clamps (get_window_size); 2-D never does
     video: bool = True
     gate_act: str = "tanh"
+    sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
+                                                  # --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1
 
     @staticmethod
     def swin(swin_type: str = "base", window12: bool = False, video: bool = True, mha: str = "") -> "OracleConfig":
@@ -187,6 +189,46 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     return r
 
 
+# A7: SepTPWAM under the README video flags (lib/video_swin_transformer.py:1300-1584, forward :1480-1584):
+# every projection of PWAM becomes the SUM of a temporal Conv3d(3,3,3) branch and a spatial Conv3d(1,1,1) branch;
+# the query / W branches are each InstanceNorm3d-normalised BEFORE the sum, the vis / project_mm branches GELU'd before it.
+def _conv3d_cl(x: Tensor, sd, name: str) -> Tensor:
+    """x (B,D,H,W,Cin) channels-last; Conv3d weight (Cout,Cin,kd,kh,kw), stride 1, 'same' zero padding."""
+    w, b = sd[name + ".weight"], sd[name + ".bias"]
+    pad = tuple(k // 2 for k in w.shape[2:])
+    return F.conv3d(x.permute(0, 4, 1, 2, 3), w, b, padding=pad).permute(0, 2, 3, 4, 1)
+
+
+def _instance_norm_3d(t: Tensor) -> Tensor:
+    """InstanceNorm3d on channels-last (B,D,H,W,C): per (clip, channel) over D*H*W; biased var, eps 1e-5, no affine."""
+    B, D, H, W, C = t.shape
+    return _instance_norm_tokens(t.reshape(B, D * H * W, C)).reshape(B, D, H, W, C)
+
+
+def sep_t_pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1) -> Tensor:
+    """x (B,D,H,W,C); l (B,768,Nl); l_mask (B,Nl,1) -> x_residual (B,D*H*W,C).  ``pre`` = 'backbone.layers.{s}.fusion.'"""
+    B, D, H, W, C = x.shape
+    n = D * H * W
+    m = l_mask.to(x.dtype)
+    vis = F.gelu(_conv3d_cl(x, sd, pre + "temporal_vis_project.0")) + F.gelu(_conv3d_cl(x, sd, pre + "spatial_vis_project.0"))  # :1487-1503
+    q = _instance_norm_3d(_conv3d_cl(x, sd, pre + "f_query_t.0")) + _instance_norm_3d(_conv3d_cl(x, sd, pre + "f_query_s.0"))    # :1512-1524
+    q = q.reshape(B, n, C)
+    lt = l.transpose(1, 2)
+    k = _lin1x1(lt, sd, pre + "f_key.0") * m                                                                                 # :1534-1538
+    v = _lin1x1(lt, sd, pre + "f_value.0") * m
+    Nl = k.shape[1]
+    ch = C // heads
+    qh = q.reshape(B, n, heads, ch).transpose(1, 2)
+    kh = k.reshape(B, Nl, heads, ch).transpose(1, 2)
+    vh = v.reshape(B, Nl, heads, ch).transpose(1, 2)
+    s = (C ** -0.5) * (qh @ kh.transpose(-1, -2)) + (1e4 * m.transpose(1, 2) - 1e4).unsqueeze(1)                              # :1549-1552
+    o = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, D, H, W, C)
+    lang = _instance_norm_3d(_conv3d_cl(o, sd, pre + "W_t.0")) + _instance_norm_3d(_conv3d_cl(o, sd, pre + "W_s.0"))          # :1556-1561
+    mm = vis * lang
+    r = F.gelu(_conv3d_cl(mm, sd, pre + "project_mm_t.0")) + F.gelu(_conv3d_cl(mm, sd, pre + "project_mm_s.0"))               # :1574-1578
+    return r.reshape(B, n, C)
+
+
 def language_gate(x: Tensor, r: Tensor, sd, pre: str, act: str = "tanh") -> Tensor:
     """x + act(W2 relu(W1 r)) * r, no biases.  ``pre`` = 'backbone.layers.{s}.res_gate.'"""
     g = F.relu(r @ sd[pre + "0.weight"].t()) @ sd[pre + "2.weight"].t()
@@ -243,7 +285,10 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             if capture is not None:
                 capture[f"s{s}b{i}"] = x
         B, D, H, W, C = x.shape
-        r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
+        if cfg.sep_t_pwam:
+            r = sep_t_pwam(x, l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
+        else:
+            r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         if capture is not None:
             capture[f"s{s}.residual"] = r
         if pre + "res_gate.0.weight" in sd:
@@ -338,10 +383,21 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
             sd[bp + "attn.proj.weight"], sd[bp + "attn.proj.bias"] = tn(C, C), 0.02 * torch.randn(C, generator=g)
             sd[bp + "mlp.fc1.weight"], sd[bp + "mlp.fc1.bias"] = tn(4 * C, C), 0.02 * torch.randn(4 * C, generator=g)
             sd[bp + "mlp.fc2.weight"], sd[bp + "mlp.fc2.bias"] = tn(C, 4 * C), 0.02 * torch.randn(C, generator=g)
-        for name, cin in (("vis_project.0", C), ("image_lang_att.f_key.0", l_in), ("image_lang_att.f_query.0", C),
-                          ("image_lang_att.f_value.0", l_in), ("image_lang_att.W.0", C), ("project_mm.0", C)):
-            w, b = conv_default(C, cin, 1)
-            sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        if cfg.sep_t_pwam:
+            for name in ("temporal_vis_project.0", "f_query_t.0", "W_t.0", "project_mm_t.0"):
+                w, b = conv_default(C, C, 3, 3, 3)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+            for name in ("spatial_vis_project.0", "f_query_s.0", "W_s.0", "project_mm_s.0"):
+                w, b = conv_default(C, C, 1, 1, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+            for name in ("f_key.0", "f_value.0"):
+                w, b = conv_default(C, l_in, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        else:
+            for name, cin in (("vis_project.0", C), ("image_lang_att.f_key.0", l_in), ("image_lang_att.f_query.0", C),
+                              ("image_lang_att.f_value.0", l_in), ("image_lang_att.W.0", C), ("project_mm.0", C)):
+                w, b = conv_default(C, cin, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
         sd[pre + "res_gate.0.weight"], sd[pre + "res_gate.2.weight"] = tn(C, C), tn(C, C)
         if s < len(cfg.depths) - 1:
             sd[pre + "downsample.reduction.weight"] = tn(2 * C, 4 * C)

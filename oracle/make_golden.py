@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [case ...]
 
 For each case: seeded weights (oracle.random_state_dict -- deterministic torch.Generator streams) are loaded
 INTO the reference's own nn.Modules (MultiModalSwinTransformer3D + SimpleDecoding, imported from /root/reference
@@ -27,6 +27,10 @@ CASES = {
     "w7_t4_32": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=4, H=32, W=32, Nl=20, keep=(0, 1, 2, 3)),
     "w12_t2_48": dict(window=(8, 12, 12), depths=(2, 2, 2, 2), mha=(1, 2, 4, 8), B=2, T=2, H=48, W=48, Nl=9, keep=(1, 2, 3)),
     "w7_t16_32x40": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=16, H=32, W=40, Nl=22, keep=(2, 3)),
+    # README video configuration: SepTPWAM fusion (--sep_t_pwam --conv3d_kernel_size_t 3-3-3 --conv3d_kernel_size_s 1-1-1
+    # --w_t3x3_s1x1 --mm_t3x3_s1x1)
+    "sept_w7_t4_32": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 2, 2), B=1, T=4, H=32, W=32, Nl=20, keep=(0, 1, 2, 3),
+                          sep_t_pwam=True),
     # 2-D image backbone (lib/backbone.py): window is an int, never clamped
     "img_w12_60x76": dict(window=(1, 12, 12), depths=(2, 2, 2, 2), mha=(1, 1, 2, 2), B=2, T=1, H=60, W=76, Nl=20, keep=(1, 2, 3),
                           image=True),
@@ -36,7 +40,8 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 def case_inputs(c):
     image = c.get("image", False)
-    cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"], clamp_window=not image, video=not image)
+    cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"], clamp_window=not image, video=not image,
+                         sep_t_pwam=c.get("sep_t_pwam", False))
     sd = O.random_state_dict(cfg, seed=0)
     x, l, m = O.synthetic_inputs(c["B"], c["T"], c["H"], c["W"], Nl=c["Nl"], seed=1, video=not image)
     return cfg, sd, x, l, m
@@ -44,12 +49,16 @@ def case_inputs(c):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         cfg, sd, x, l, m = case_inputs(c)
         if c.get("image", False):
             bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=c["window"][1], mha=c["mha"], depths=c["depths"])
         else:
-            bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"])
+            bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"],
+                                                                  extra=ref_shims.SEP_T_PWAM_FLAGS if c.get("sep_t_pwam") else ())
         missing = bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=False)
         assert all(k.endswith("relative_position_index") for k in missing.missing_keys) and not missing.unexpected_keys, missing
         missing = dec.load_state_dict({k[len("classifier."):]: v for k, v in sd.items() if k.startswith("classifier.")}, strict=False)

@@ -118,13 +118,17 @@ def build_reference(model: str = "lavt_video", swin_type: str = "base", window12
     return net, args
 
 
+SEP_T_PWAM_FLAGS = ("--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel_size_s", "1-1-1",
+                    "--w_t3x3_s1x1", "--mm_t3x3_s1x1")      # the reference README's video configuration (README.md:185)
+
+
 def build_reference_backbone_small(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32), window=(8, 7, 7),
-                                   mha=(1, 1, 1, 1), seed=0):
+                                   mha=(1, 1, 1, 1), seed=0, extra=()):
     """A shallow reference video backbone + decoder for fast parity runs (same classes, fewer blocks)."""
     install_shims()
     from lib.video_swin_transformer import MultiModalSwinTransformer3D
     from lib.mask_predictor import SimpleDecoding
-    args = reference_args(["--model", "lavt_video"])
+    args = reference_args(["--model", "lavt_video", *extra])
     torch.manual_seed(seed)
     bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=embed_dim, depths=list(depths), num_heads=list(num_heads),
                                      window_size=window, drop_path_rate=0.0, patch_norm=True, out_indices=(0, 1, 2, 3),

@@ -98,6 +98,24 @@ def test_conv3x3_bn_relu(cabi, n_img, H, W, Cin, Cout):
     _close(out, ref, 2e-2)
 
 
+@pytest.mark.parametrize("n_clip,D,H,W,Cin,Cout,act", [(1, 4, 24, 24, 128, 128, 0), (2, 8, 12, 12, 256, 256, 1), (1, 8, 7, 10, 64, 128, 0),
+                                                        (1, 2, 48, 48, 128, 128, 1), (2, 3, 1, 2, 64, 128, 0)])
+def test_conv3d_333(cabi, n_clip, D, H, W, Cin, Cout, act):
+    """Conv3d(3,3,3), pad 1 (SepTPWAM branches, reference lib/video_swin_transformer.py:1334-1461) vs torch fp32 on the same
+    bf16 operands; frames / rows / columns outside the clip are zero (TMA out-of-bounds fill)."""
+    g = torch.Generator(device="cuda").manual_seed(D * H * W + Cin)
+    x = torch.randn(n_clip, D, H, W, Cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) / (27 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    w_taps = wt.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous()
+    out = torch.empty(n_clip * D * H * W, Cout, device="cuda", dtype=torch.float32)
+    cabi.conv3d_bf16(x, w_taps, bias=bias, act=cabi.ACT_GELU if act else cabi.ACT_NONE, out_f32=out)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), wt.float(), bias, padding=1)
+    if act:
+        ref = F.gelu(ref)
+    _close(out.view(n_clip, D, H, W, Cout), ref.permute(0, 2, 3, 4, 1), 2e-2)
+
+
 def test_gemm_rejects_bad_shapes(cabi):
     a = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
     w = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)

@@ -102,6 +102,44 @@ def test_pwam_and_gate(small, stage, heads, Nl):
     assert_close(xf.view(B, n, C), ref_x, what="gated x", frac=1e-2, l2=1.5e-2)
 
 
+@pytest.mark.parametrize("stage,heads,dims,Nl", [(0, 1, (2, 4, 12, 12), 20), (1, 2, (1, 8, 7, 9), 9), (2, 1, (2, 2, 4, 4), 33)])
+def test_sep_t_pwam_and_gate(stage, heads, dims, Nl):
+    """SepTPWAM (README video flags) through the reference-shaped module and the engine-level gate vs the oracle."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib.video_swin_transformer import MMBasicLayer, PatchMerging, _lang, _mask
+    from lavt_rs_b200.weights import load_reference_state_dict
+    mha = tuple(heads if i == stage else 1 for i in range(4))
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), fusion_heads=mha, sep_t_pwam=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    args = default_args(["--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel_size_s", "1-1-1", "--w_t3x3_s1x1",
+                         "--mm_t3x3_s1x1"])
+    C = 128 * 2 ** stage
+    layer = MMBasicLayer(dim=C, depth=2, num_heads=4 * 2 ** stage, window_size=(8, 7, 7), qkv_bias=True, drop_path=[0.0, 0.0],
+                         downsample=PatchMerging if stage < 3 else None, num_heads_fusion=heads, args=args)
+    load_reference_state_dict(layer, sd, f"backbone.layers.{stage}.")
+    layer = layer.cuda().eval()
+    B, D, H, W = dims
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, D, H, W, C, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.zeros(B, Nl, 1, dtype=torch.int64)
+    m[0, : max(1, Nl // 2)] = 1
+    m[-1, :] = 1
+    pre = f"backbone.layers.{stage}."
+    ref_r = O.sep_t_pwam(x, l, m, sd, pre + "fusion.", heads)
+    got_r = layer.fusion(x.cuda(), l.cuda(), m.cuda())
+    # a chain of 8 bf16 contractions (four of them K = 27 C) around four InstanceNorms and a softmax
+    assert_close(got_r, ref_r, what="sep_t_pwam residual", frac=1e-2, l2=1.5e-2)
+    n = D * H * W
+    xf = x.reshape(B * n, C).cuda().contiguous()
+    r = torch.empty_like(xf)
+    E.sep_t_pwam_gate(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate, _lang(l.cuda()), _mask(m.cuda()), B, D, H, W,
+                      E.workspace("cuda"), r_f32=r)
+    ref_x = O.language_gate(x.reshape(B, n, C), ref_r, sd, pre + "res_gate.")
+    assert_close(xf.view(B, n, C), ref_x, what="gated x", frac=1e-2, l2=1.5e-2)
+
+
 @pytest.mark.parametrize("dims", [(2, 4, 12, 12), (1, 8, 7, 9)])
 def test_patch_merging(small, dims):
     cfg, sd, bb, _ = small((8, 7, 7))

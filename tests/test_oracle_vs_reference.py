@@ -59,6 +59,31 @@ def test_backbone_and_decoder_match_reference(window, T, HW, mha):
         assert (ref_logits - got_logits).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("window,T,HW,mha", [((8, 7, 7), 4, (64, 64), (1, 1, 1, 1)), ((8, 7, 7), 8, (48, 40), (1, 2, 2, 4))])
+def test_sep_t_pwam_backbone_matches_reference(window, T, HW, mha):
+    """README video configuration: --sep_t_pwam --conv3d_kernel_size_t 3-3-3 --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1
+    --mm_t3x3_s1x1 (SepTPWAM, lib/video_swin_transformer.py:1300-1584)."""
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=window, mha=mha, depths=(2, 2, 2, 2), extra=ref_shims.SEP_T_PWAM_FLAGS)
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    assert "backbone.layers.0.fusion.W_t.0.weight" in sd and tuple(sd["backbone.layers.0.fusion.W_t.0.weight"].shape[2:]) == (3, 3, 3)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=window, fusion_heads=mha, sep_t_pwam=True)
+    x, l, m = O.synthetic_inputs(2, T, HW[0], HW[1], Nl=11)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        ref = bb(xv, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert a.shape == b.shape
+        err = (a - b).abs().max().item()
+        assert err < 2e-4, f"stage {i}: max err {err}"
+    # the oracle's random state dict carries the same keys / shapes as the reference module
+    rsd = O.random_state_dict(cfg)
+    for k, v in sd.items():
+        if k.startswith("backbone.layers.0.fusion."):
+            assert tuple(rsd[k].shape) == tuple(v.shape), k
+
+
 @pytest.mark.parametrize("window,HW,mha", [(7, (64, 80), (1, 1, 1, 1)), (12, (96, 72), (1, 2, 2, 4)), (12, (40, 40), (1, 1, 1, 1))])
 def test_image_backbone_matches_reference(window, HW, mha):
     """2-D twins (lib/backbone.py): never-clamped windows, per-call mask, (B,HW,C) token layout."""
