@@ -2,15 +2,15 @@
 """Benchmark of the LAVT-RS hot path on B200:  python bench.py --gpus N --steps K --warmup W
 
 Metric (BASELINE.json): LAVT-RS forward clips/s on 8x384x384 clips, Video Swin-B, 20-word expression.
-One step = one forward of the hot path (backbone + PWAM/gate + SimpleDecoding + x4 upsample, i.e.
-``LAVTVideo.forward`` after the external BERT call) over one batch of synthetic clips per GPU.
+One step = one ``LAVTVideo.forward(x, text ids, l_mask)`` (BERT-base text encoder + backbone + PWAM/gate + SimpleDecoding +
+x4 upsample, every layer on the sm_100a kernels) over one batch of synthetic clips per GPU.
 
   value      whole-job clips/s, inputs resident in HBM, CUDA-graph replay of the forward, CUDA-event timed
-  e2e        same metric through the public API call ``model.forward_with_lang`` with HOST (pinned) inputs:
-             H2D of pixels / language features / mask and D2H of the full-resolution logits inside the timed region
+  e2e        same metric through the public API call ``model(x, text, l_mask)`` with HOST (pinned) inputs:
+             H2D of pixels / token ids / mask and D2H of the full-resolution logits inside the timed region
   roofline   the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs / CUDA-event time vs the
              measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline / --impl reference   the oracle port of the reference forward (oracle/lavt_oracle.py) timed on this
+  cpu_baseline / --impl reference   the oracle port of the reference forward (oracle/bert_oracle.py + oracle/lavt_oracle.py) timed on this
              box's host cores -- a reported baseline, not the target.
 """
 from __future__ import annotations
@@ -53,9 +53,9 @@ SEP_FLAGS = ["--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel
 
 
 def flops_per_clip(window12: bool) -> float:
-    # BASELINE.md section 2 (measured with torch.utils.flop_counter on the reference), minus BERT (3.4 GFLOP);
+    # BASELINE.md section 2 (measured with torch.utils.flop_counter on the reference), BERT-base (3.4 GFLOP) included;
     # SepTPWAM adds four Conv3d(3,3,3) per stage: +1043.6 GFLOP (3118.4 vs 2074.8 at window 8x7x7)
-    return (2198.4e9 if window12 else 2074.8e9) - 3.4e9 + (1043.6e9 if SEP_T_PWAM else 0.0)
+    return (2198.4e9 if window12 else 2074.8e9) + (1043.6e9 if SEP_T_PWAM else 0.0)
 
 
 def model_args(window12: bool):
@@ -75,10 +75,10 @@ def build_model(window12: bool, device):
 def synth_batch(B: int, seed: int):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, T_FRAMES, 3, IMG, IMG, generator=g)
-    l = torch.randn(B, 768, NL, generator=g)
+    ids = torch.randint(1000, 5000, (B, NL), generator=g)      # token ids of a 20-word expression
     m = torch.zeros(B, NL, dtype=torch.int64)
     m[:, :14] = 1
-    return x, l, m
+    return x, ids, m
 
 
 class ClockSampler:
@@ -129,7 +129,8 @@ def peaks():
 
 
 def cpu_forward_time(window12: bool, sd_cpu, n_runs: int, threads: int):
-    """Oracle port of the reference forward on host cores: 1 clip per run."""
+    """Oracle port of the reference forward (BERT + backbone + decoder) on host cores: 1 clip per run."""
+    from oracle import bert_oracle as BO
     from oracle import lavt_oracle as O
     torch.set_num_threads(threads)
     cfg = O.OracleConfig.swin("base", window12=window12, video=True)
@@ -139,7 +140,8 @@ def cpu_forward_time(window12: bool, sd_cpu, n_runs: int, threads: int):
     with torch.no_grad():
         for _ in range(n_runs):
             t0 = time.perf_counter()
-            out = O.model_forward(sd_cpu, cfg, x, l, m)
+            l_feats = BO.bert_forward(sd_cpu, l, m).permute(0, 2, 1)        # lib/_utils.py:98-100
+            out = O.model_forward(sd_cpu, cfg, x, l_feats, m)
             times.append(time.perf_counter() - t0)
     return times, out, (x, l, m)
 
@@ -153,7 +155,7 @@ def run_reference(a):
     from lavt_rs_b200.lib import segmentation  # host modules only build parameters here (CPU); no kernels are run
     torch.manual_seed(0)
     model = segmentation.lavt_video(pretrained="", args=model_args(a.window12)).eval()
-    sd = {k: v.detach().float() for k, v in model.state_dict().items() if not k.startswith("text_encoder.")}
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
     budget_s = 200.0
     warm = min(a.warmup, 1)
     wt, _, _ = cpu_forward_time(a.window12, sd, max(warm, 1), threads)
@@ -166,8 +168,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": a.gpus, "steps": steps,
         "warmup": max(warm, 1), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LAVT-RS Video Swin-B forward, 8x384x384 clips, 20-token expression", "window": "8x12x12" if a.window12 else "8x7x7",
-                   "clips_per_step": 1},
+        "config": {"workload": "LAVT-RS Video Swin-B forward (BERT-base text encoder + backbone + decoder), 8x384x384 clips, 20-token expression",
+                   "window": "8x12x12" if a.window12 else "8x7x7", "clips_per_step": 1},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -207,7 +209,7 @@ def main():
     sx, sl, sm_ = (torch.empty_like(t) for t in resident[0])     # static graph inputs
 
     def fwd_static():
-        return model.forward_with_lang(sx, sl, sm_)
+        return model(sx, sl, sm_)          # the reference's public call: LAVTVideo.forward(x, text ids, l_mask), BERT included
 
     with torch.no_grad():
         # eager warm-up (also builds bf16 weight copies, workspaces, func attributes)
@@ -370,7 +372,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "LAVT-RS Video Swin-B forward (hot path after BERT), 8x384x384 clips, 20-token expression",
+        "config": {"workload": "LAVT-RS Video Swin-B forward (BERT-base text encoder + backbone + decoder), 8x384x384 clips, 20-token expression",
                    "window": "8x12x12" if a.window12 else "8x7x7", "fusion": "SepTPWAM (README video flags)" if SEP_T_PWAM else "PWAM",
                    "clips_per_gpu_per_step": B, "global_clips_per_step": total_clips,
                    "parallelism": f"clip-sharded x{world}, no collectives", "cuda_graph": graph is not None,
@@ -387,10 +389,10 @@ def main():
 
     if world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if not k.startswith("text_encoder.")}
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         times, ref_out, (cx, cl, cm) = cpu_forward_time(a.window12, sd, 1, threads)
         with torch.no_grad():
-            got = model.forward_with_lang(cx.to(dev), cl.to(dev), cm.to(dev)).float().cpu()
+            got = model(cx.to(dev), cl.to(dev), cm.to(dev)).float().cpu()
         rel = ((got - ref_out).norm() / ref_out.norm()).item()
         agree = (got.argmax(1) == ref_out.argmax(1)).float().mean().item()
         res["cpu_baseline"] = {"value": 1.0 / times[0], "unit": "clips/s", "cores": threads, "kind": "port",

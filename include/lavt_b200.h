@@ -145,6 +145,18 @@ int lavt_pwam_mul_norm(const void* vis_bf16, const float* lang, const float* sta
 int lavt_instnorm_sum2(const float* a, const float* stats_a, const float* b, const float* stats_b, float* out, int32_t B,
                        int64_t n, int32_t C, void* stream);
 
+/* ---- text side: BertModel(text, attention_mask)[0] (lib/_utils.py:52-54, 98-100; bert/modeling_bert.py = HF v3.0.2) ----
+ * The dense layers are lavt_gemm_bf16 calls and the LayerNorms lavt_layernorm_rows (eps 1e-12); these are the rest. */
+/* BertEmbeddings: out[b*Nl+t, :] = word[ids[b,t]] + pos[t] + type0  (fp32 rows; the embedding LayerNorm follows) */
+int lavt_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out, int32_t B, int32_t Nl,
+                    int32_t H, int32_t vocab, void* stream);
+/* BertSelfAttention core per (sentence, head), head_dim 64, Nl <= 128: softmax(q k^T + (1 - mask) * -10000) v.
+ * qkv bf16 [B*Nl, 3H] = q | k | v with q pre-scaled by 64^-0.5 * log2(e); mask fp32 [B, Nl]; out bf16 [B*Nl, H] */
+int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16, int32_t B, int32_t Nl, int32_t H, int32_t heads,
+                        void* stream);
+/* (B, Nl, C) fp32 -> (B, C, Nl) fp32: l_feats = last_hidden_state.permute(0, 2, 1) (lib/_utils.py:54) */
+int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream);
+
 /* ---- decoder glue (lib/mask_predictor.py:56-99, lib/_utils.py:106) ---- */
 /* out NHWC bf16 [n,H,W,C1+C2] = cat[bilinear(prev [n,ph,pw,C1] -> HxW, align_corners=True), skip [n,H,W,C2]] */
 int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,

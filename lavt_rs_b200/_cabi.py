@@ -88,6 +88,9 @@ SIGNATURES = {
     "lavt_pwam_attend": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_pwam_mul_norm": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_instnorm_sum2": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "lavt_bert_embed": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_bert_attention": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_rows_to_channels_first": [_vp, _vp, _i32, _i32, _i32, _vp],
     "lavt_upsample_concat": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp],
     "lavt_conv1x1_logits": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -386,6 +389,34 @@ def instnorm_sum2(a, stats_a, b, stats_b, out) -> None:
     check(lib().lavt_instnorm_sum2(_c(a, torch.float32, "a").data_ptr(), _c(stats_a, torch.float32, "stats_a").data_ptr(),
                                    _c(b, torch.float32, "b").data_ptr(), _c(stats_b, torch.float32, "stats_b").data_ptr(),
                                    _c(out, torch.float32, "out").data_ptr(), B, n, Cn, stream_ptr()), "lavt_instnorm_sum2")
+
+
+def bert_embed(ids, word, pos, type0, out) -> None:
+    """ids int64 [B,Nl]; word [V,H], pos [P,H], type0 [H] fp32 -> out fp32 [B*Nl, H]."""
+    if ids.dtype != torch.int64 or not ids.is_cuda or not ids.is_contiguous():
+        raise LavtError("bert_embed: ids must be a contiguous CUDA int64 tensor")
+    B, Nl = ids.shape
+    V, H = word.shape
+    if Nl > pos.shape[0]:
+        raise LavtError("bert_embed: sentence longer than the position table")
+    check(lib().lavt_bert_embed(ids.data_ptr(), _c(word, torch.float32, "word").data_ptr(), _c(pos, torch.float32, "pos").data_ptr(),
+                                _c(type0, torch.float32, "type0").data_ptr(), _c(out, torch.float32, "out").data_ptr(), B, Nl, H, V,
+                                stream_ptr()), "lavt_bert_embed")
+
+
+def bert_attention(qkv, mask, out, heads: int) -> None:
+    """qkv bf16 [B*Nl, 3H]; mask fp32 [B,Nl]; out bf16 [B*Nl, H]."""
+    B, Nl = mask.shape
+    H = out.shape[1]
+    check(lib().lavt_bert_attention(_c(qkv, torch.bfloat16, "qkv").data_ptr(), _c(mask, torch.float32, "mask").data_ptr(),
+                                    _c(out, torch.bfloat16, "out").data_ptr(), B, Nl, H, heads, stream_ptr()), "lavt_bert_attention")
+
+
+def rows_to_channels_first(x, out) -> None:
+    """x fp32 [B,Nl,C] -> out fp32 [B,C,Nl]."""
+    B, Nl, Cn = x.shape
+    check(lib().lavt_rows_to_channels_first(_c(x, torch.float32, "x").data_ptr(), _c(out, torch.float32, "out").data_ptr(), B, Nl, Cn,
+                                            stream_ptr()), "lavt_rows_to_channels_first")
 
 
 def upsample_concat(prev, skip, out) -> None:

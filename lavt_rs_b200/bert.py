@@ -1,0 +1,81 @@
+"""Text encoder forward on the sm_100a kernels (reference lib/_utils.py:52-54, 98-100: ``BertModel(text, attention_mask)[0]``;
+the reference's bert/ package = HF Transformers v3.0.2 modeling_bert.py).
+
+The stock ``transformers.BertModel`` stays the PARAMETER CONTAINER (its ``text_encoder.*`` state-dict keys are the reference's,
+197 keys), but its forward is not used on the GPU path: dense layers run on the tcgen05 GEMM kernel (fused bias / GELU /
+residual epilogues), LayerNorms on ``lavt_layernorm_rows`` (eps 1e-12), and the embedding gather, the per-head attention
+over the <= 128 tokens of a sentence and the final (B,Nl,C) -> (B,C,Nl) layout change on the three kernels of
+``csrc/bert_kernels.cu``.  6 + 7 * layers launches per call, no cuBLAS, no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _cabi as K
+from . import engine as E
+
+_LOG2E = 1.4426950408889634
+
+
+def _prepared(enc) -> E.PreparedWeights:
+    pw = getattr(enc, "_lavt_prepared", None)
+    if pw is None:
+        pw = E.PreparedWeights()
+        object.__setattr__(enc, "_lavt_prepared", pw)     # plain attribute: keeps state_dict() untouched
+    return pw
+
+
+def bert_forward(enc, ids: torch.Tensor, mask: torch.Tensor, out_cf: torch.Tensor = None) -> torch.Tensor:
+    """enc: transformers.BertModel (eval); ids (B,Nl) int64; mask (B,Nl) -> l_feats fp32 (B, H, Nl) (= [0].permute(0,2,1))."""
+    E.require_cuda(ids, "text")
+    if enc.training:
+        raise NotImplementedError("text-encoder dropout (training) is not implemented on the B200 path")
+    cfg = enc.config
+    H, heads, layers = cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers
+    if H // heads != 64 or H % 128 != 0:
+        raise K.LavtError("BERT on the B200 path needs head_dim 64 and hidden size % 128 == 0 (BERT-base: 768 / 12)")
+    if getattr(cfg, "hidden_act", "gelu") != "gelu":
+        raise K.LavtError("BERT on the B200 path implements the erf GELU only")
+    B, Nl = ids.shape
+    M = B * Nl
+    dev = ids.device
+    ws = E.workspace(dev)
+    pw = _prepared(enc)
+    emb = enc.embeddings
+    eps = float(cfg.layer_norm_eps)
+    ids = ids.detach().to(torch.int64).contiguous()
+    maskf = mask.detach().reshape(B, Nl).to(torch.float32).contiguous()
+
+    x = ws.get("bert_x", (M, H), torch.float32, dev)          # residual stream
+    xb = ws.get("bert_xb", (M, H), torch.bfloat16, dev)
+    type0 = pw.get("type0", [emb.token_type_embeddings.weight], lambda: emb.token_type_embeddings.weight.detach()[0].float().contiguous())
+    K.bert_embed(ids, emb.word_embeddings.weight.detach(), emb.position_embeddings.weight.detach(), type0, x)
+    K.layernorm_rows(x, emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), out_bf16=xb, out_f32=x, eps=eps)
+    qkv = ws.get("bert_qkv", (M, 3 * H), torch.bfloat16, dev)
+    ctx = ws.get("bert_ctx", (M, H), torch.bfloat16, dev)
+    hid = ws.get("bert_hid", (M, cfg.intermediate_size), torch.bfloat16, dev)
+    qs = pw.get("qscale", [], lambda: torch.cat([torch.full((H,), 64 ** -0.5 * _LOG2E), torch.ones(2 * H)]).to(dev))
+    for i, layer in enumerate(enc.encoder.layer):
+        sa, so = layer.attention.self, layer.attention.output
+        w_qkv = pw.get(f"qkv_w{i}", [sa.query.weight, sa.key.weight, sa.value.weight],
+                       lambda: torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0).detach().to(torch.bfloat16).contiguous())
+        b_qkv = pw.get(f"qkv_b{i}", [sa.query.bias, sa.key.bias, sa.value.bias],
+                       lambda: (torch.cat([sa.query.bias, sa.key.bias, sa.value.bias]).detach().float() * qs).contiguous())
+        K.gemm_bf16(xb, w_qkv, cscale=qs, bias=b_qkv, out_bf16=qkv)         # q pre-scaled by 64^-0.5 * log2(e)
+        K.bert_attention(qkv, maskf, ctx, heads)
+        w_o = pw.get(f"o_w{i}", [so.dense.weight], lambda: so.dense.weight.detach().to(torch.bfloat16).contiguous())
+        K.gemm_bf16(ctx, w_o, bias=so.dense.bias.detach(), resid=x, out_f32=x)
+        K.layernorm_rows(x, so.LayerNorm.weight.detach(), so.LayerNorm.bias.detach(), out_bf16=xb, out_f32=x, eps=eps)
+        w_1 = pw.get(f"fc1_w{i}", [layer.intermediate.dense.weight],
+                     lambda: layer.intermediate.dense.weight.detach().to(torch.bfloat16).contiguous())
+        K.gemm_bf16(xb, w_1, bias=layer.intermediate.dense.bias.detach(), act=K.ACT_GELU, out_bf16=hid)
+        w_2 = pw.get(f"fc2_w{i}", [layer.output.dense.weight], lambda: layer.output.dense.weight.detach().to(torch.bfloat16).contiguous())
+        K.gemm_bf16(hid, w_2, bias=layer.output.dense.bias.detach(), resid=x, out_f32=x)
+        K.layernorm_rows(x, layer.output.LayerNorm.weight.detach(), layer.output.LayerNorm.bias.detach(), out_bf16=xb, out_f32=x, eps=eps)
+    if out_cf is None:
+        out_cf = torch.empty(B, H, Nl, device=dev, dtype=torch.float32)
+    K.rows_to_channels_first(x.view(B, Nl, H), out_cf)
+    E._count(3 + 7 * layers)
+    return out_cf

@@ -191,6 +191,20 @@ int lavt_instnorm_sum2(const float* a, const float* stats_a, const float* b, con
   return instnorm_sum2_dispatch(a, stats_a, b, stats_b, out, B, n, C, S(stream));
 }
 
+int lavt_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out, int32_t B, int32_t Nl,
+                    int32_t H, int32_t vocab, void* stream) {
+  return bert_embed_dispatch(reinterpret_cast<const long long*>(ids), word, pos, type0, out, B, Nl, H, vocab, S(stream));
+}
+
+int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16, int32_t B, int32_t Nl, int32_t H, int32_t heads,
+                        void* stream) {
+  return bert_attention_dispatch(CB(qkv_bf16), mask, MB(out_bf16), B, Nl, H, heads, S(stream));
+}
+
+int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream) {
+  return rows_to_cf_dispatch(in, out, B, Nl, C, S(stream));
+}
+
 int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,
                          void* out_bf16, int32_t n_img, int32_t H, int32_t W, void* stream) {
   return upsample_concat_dispatch(CB(prev_bf16), ph, pw, C1, CB(skip_bf16), C2, MB(out_bf16), n_img, H, W, S(stream));

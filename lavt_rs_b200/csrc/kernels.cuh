@@ -48,6 +48,12 @@ int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const f
 int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                        __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st);
 
+int bert_embed_dispatch(const long long* ids, const float* word, const float* pos, const float* type0, float* out, int B, int Nl,
+                        int H, int vocab, cudaStream_t st);
+int bert_attention_dispatch(const __nv_bfloat16* qkv, const float* mask, __nv_bfloat16* out, int B, int Nl, int H, int heads,
+                            cudaStream_t st);
+int rows_to_cf_dispatch(const float* in, float* out, int B, int Nl, int C, cudaStream_t st);
+
 int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,
                              __nv_bfloat16* out, int n_img, int H, int W, cudaStream_t st);
 int conv1x1_logits_dispatch(const __nv_bfloat16* y, const float* w, const float* b, float* out, long long npix, int C,

@@ -1,9 +1,9 @@
 """Top-level LAVT modules -- B200 host side (reference lib/_utils.py:10-238).
 
 ``LAVTVideo.forward(x[B,T,3,H,W], text[B,Nl], l_mask[B,Nl]) -> [B*T,2,H,W]`` and
-``LAVTOne.forward(x[B,3,H,W], text, l_mask)`` keep the reference signatures.  BERT stays the stock
-``transformers`` module (the reference's own copy is not in its tree); everything after
-``l_feats`` runs on the sm_100a kernels with NHWC bf16 hand-off between backbone and decoder.
+``LAVTOne.forward(x[B,3,H,W], text, l_mask)`` keep the reference signatures.  The stock ``transformers`` BertModel is
+kept as the parameter container of ``text_encoder`` (the reference's own copy is not in its
+tree) but its forward runs on the sm_100a kernels too (``lavt_rs_b200/bert.py``); backbone and decoder hand NHWC bf16.
 """
 from __future__ import annotations
 
@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import _cabi as K
+from .. import bert as BERT
 from .. import engine as E
 from .video_swin_transformer import _lang, _mask, _planes
 
@@ -31,9 +32,27 @@ def _build_text_encoder(args):
 class _Segmenter(nn.Module):
     video = False
 
-    def _segment(self, x5: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, size) -> torch.Tensor:
+    def _encode_text_async(self, text: torch.Tensor, l_mask: torch.Tensor):
+        """Text encoder on a high-priority side stream: its ~90 small launches overlap the patch embedding and the first
+        Swin blocks (which do not read the language features).  Returns (l_feats, event that marks them valid)."""
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_text_stream", None)
+        if side is None or side.device != cur.device:
+            side = torch.cuda.Stream(device=cur.device, priority=-1)
+            object.__setattr__(self, "_text_stream", side)
+        B, Nl = text.shape
+        buf = E.workspace(text.device).get("bert_out_cf", (B, self.text_encoder.config.hidden_size, Nl), torch.float32, text.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            l_feats = BERT.bert_forward(self.text_encoder, text, l_mask, out_cf=buf)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return l_feats, ev
+
+    def _segment(self, x5: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, size, lang_ready=None) -> torch.Tensor:
         """x5 (B,3,T,H,W) strided view; l_feats (B,768,Nl); l_mask (B,Nl[,1])."""
-        _, nhwc = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=False, want_nhwc_bf16=True)
+        _, nhwc = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=False, want_nhwc_bf16=True,
+                                    lang_ready=lang_ready)
         c1, c2, c3, c4 = nhwc
         ws = E.workspace(c1.device)
         lg = E.decoder_nhwc(self.classifier, c4, c3, c2, c1, ws, None)       # (n_img, H/4, W/4, 2) NHWC fp32
@@ -67,9 +86,9 @@ class LAVTOne(_Segmenter):
 
     def forward(self, x, text, l_mask):
         E.require_cuda(x, "x")
-        l_feats = self.text_encoder(text, attention_mask=l_mask)[0].permute(0, 2, 1)
+        l_feats, ev = self._encode_text_async(text, l_mask)               # (B, 768, Nl): [0].permute(0, 2, 1) of the reference
         x5 = _planes(x).unsqueeze(2)
-        return self._segment(x5, l_feats, l_mask, x.shape[-2:])
+        return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)
 
 
 class LAVTVideo(_Segmenter):
@@ -84,12 +103,14 @@ class LAVTVideo(_Segmenter):
         self.seg_last = False
 
     def encode_text(self, text, l_mask):
-        return self.text_encoder(text, attention_mask=l_mask)[0].permute(0, 2, 1)
+        """BertModel(text, attention_mask=l_mask)[0].permute(0, 2, 1) on the sm_100a kernels (lavt_rs_b200/bert.py)."""
+        return BERT.bert_forward(self.text_encoder, text, l_mask)
 
     def forward(self, x, text, l_mask):
         E.require_cuda(x, "x")
-        l_feats = self.encode_text(text, l_mask)
-        return self.forward_with_lang(x, l_feats, l_mask)
+        l_feats, ev = self._encode_text_async(text, l_mask)
+        x5 = _planes(x).permute(0, 2, 1, 3, 4)
+        return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)
 
     def forward_with_lang(self, x, l_feats, l_mask):
         """Hot path after BERT: x (B,T,3,H,W), l_feats (B,768,Nl), l_mask (B,Nl)."""

@@ -288,7 +288,7 @@ class MMBasicLayer(nn.Module):
 
     # -- engine-level stage: works on the flat fp32 residual stream, returns (r fp32 [B*n,C], x_next, dims) --
     def run(self, x: torch.Tensor, B: int, D: int, H: int, W: int, l: torch.Tensor, mask: torch.Tensor, ws: E.Workspace,
-            r_out: torch.Tensor):
+            r_out: torch.Tensor, lang_ready=None):
         dev = x.device
         C = self.dim
         xb = ws.get("stage_xb", (B * D * H * W, C), torch.bfloat16, dev)
@@ -297,6 +297,8 @@ class MMBasicLayer(nn.Module):
         for i, blk in enumerate(self.blocks):
             E.swin_block(x, blk, B, D, H, W, self.window_size, blk.shifted, blk.clamp_window, ws,
                          xb_out=xb if i == self.depth - 1 else None)
+        if lang_ready is not None:          # first consumer of the language features
+            torch.cuda.current_stream().wait_event(lang_ready)
         if self.sep_t_pwam:
             def fuse(gate):
                 E.sep_t_pwam_gate(x, xb, self.fusion, gate, l, mask, B, D, H, W, ws, r_f32=r_out)
@@ -435,8 +437,11 @@ class MultiModalSwinTransformer3D(nn.Module):
             raise TypeError("pretrained must be a str or None")
 
     # -- engine-level forward: NHWC outputs for the fused model path ------------------------------
-    def run(self, x5: torch.Tensor, l: torch.Tensor, mask: torch.Tensor, want_nchw: bool = True, want_nhwc_bf16: bool = False):
-        """x5: (B,3,T,H,W) strided fp32 view.  Returns (list of NCHW fp32 maps or None, list of NHWC bf16 maps or None)."""
+    def run(self, x5: torch.Tensor, l: torch.Tensor, mask: torch.Tensor, want_nchw: bool = True, want_nhwc_bf16: bool = False,
+            lang_ready=None):
+        """x5: (B,3,T,H,W) strided fp32 view.  Returns (list of NCHW fp32 maps or None, list of NHWC bf16 maps or None).
+        ``lang_ready``: optional CUDA event after which ``l`` is valid (the text encoder runs on a side stream while the
+        patch embedding and the first Swin blocks -- which do not read the language features -- run on this one)."""
         dev = x5.device
         ws = E.workspace(dev)
         B, _, T, H, W = x5.shape
@@ -451,7 +456,7 @@ class MultiModalSwinTransformer3D(nn.Module):
             C = layer.dim
             n = B * D * Hc * Wc
             r = ws.get("stage_r", (n, C), torch.float32, dev)
-            x_next, H2, W2 = layer.run(x, B, D, Hc, Wc, l, mask, ws, r)
+            x_next, H2, W2 = layer.run(x, B, D, Hc, Wc, l, mask, ws, r, lang_ready=lang_ready if i == 0 else None)
             if i in self.out_indices:
                 norm = getattr(self, f"norm{i}")
                 of = ws.get("out_f32", (n, C), torch.float32, dev) if want_nchw else None

@@ -255,3 +255,28 @@ def test_baseline_config1_image_model_full_size():
     if clear.any():
         assert (got.cpu().argmax(1) == ref.argmax(1))[clear].float().mean().item() >= 0.999
     print(f"config1: rel-L2 {r:.3e}, argmax agreement {agree:.5f}")
+
+
+@pytest.mark.parametrize("layers,B,Nl", [(2, 3, 20), (12, 8, 20), (12, 2, 77)])
+def test_bert_text_encoder(layers, B, Nl):
+    """BertModel(text, attention_mask)[0].permute(0,2,1) on the sm_100a kernels vs the CPU oracle (oracle/bert_oracle.py,
+    pinned against transformers in tests/test_bert_oracle.py).  12 layers of bf16 GEMMs, each re-normalised by a LayerNorm:
+    rel-L2 <= 2e-2 on the real tokens."""
+    transformers = pytest.importorskip("transformers")
+    from oracle import bert_oracle as BO
+    from lavt_rs_b200.bert import bert_forward
+    torch.manual_seed(0)
+    enc = transformers.BertModel(transformers.BertConfig(num_hidden_layers=layers)).eval()
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1000, 5000, (B, Nl), generator=g)
+    mask = torch.zeros(B, Nl, dtype=torch.int64)
+    for b in range(B):
+        mask[b, : max(1, Nl - 2 * b - 1)] = 1
+    sd = {"text_encoder." + k: v for k, v in enc.state_dict().items()}
+    with torch.no_grad():
+        ref = BO.bert_forward(sd, ids, mask)                       # (B, Nl, H)
+        got = bert_forward(enc.cuda(), ids.cuda(), mask.cuda())   # (B, H, Nl)
+    got = got.permute(0, 2, 1).float().cpu()
+    live = mask.bool()
+    r = ((got[live] - ref[live]).norm() / ref[live].norm()).item()
+    assert r < 2e-2, f"rel-L2 {r:.3e}"

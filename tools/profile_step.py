@@ -18,16 +18,16 @@ model = bench.build_model(a.window12, dev)
 x, l, m = (t.to(dev) for t in bench.synth_batch(a.clips, 1))
 with torch.no_grad():
     for _ in range(2):
-        model.forward_with_lang(x, l, m)
+        model(x, l, m)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    model.forward_with_lang(x, l, m)
+    model(x, l, m)
     e1.record()
     torch.cuda.synchronize()
     print("eager forward ms", e0.elapsed_time(e1))
     K.TIMER.enabled = True
-    model.forward_with_lang(x, l, m)
+    model(x, l, m)
     rows = K.TIMER.by_tag()
 tot = sum(v["ms"] for v in rows.values())
 for (fam, tag), v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"]):
