@@ -117,5 +117,20 @@ class LAVTVideo(_Segmenter):
         x5 = _planes(x).permute(0, 2, 1, 3, 4)     # (B,3,T,H,W) view; read in place by the im2col kernel
         return self._segment(x5, l_feats, l_mask, x.shape[-2:])
 
+    def _load_inflated(self, pretrained, drop_fusion: bool):
+        from ..weights import inflate_lavt2d_state_dict
+        checkpoint = torch.load(pretrained, map_location="cpu")
+        sd = inflate_lavt2d_state_dict(checkpoint["model"], self.backbone.window_size, self.state_dict(), drop_fusion=drop_fusion)
+        msg = self.load_state_dict(sd, strict=False)    # not strict: the index buffers were dropped from the source dict
+        print(msg)
+        print(f"=> loaded successfully '{pretrained}'")
+        return msg
+
     def load_from_pretrained2d_lavt_weights(self, pretrained):
-        raise NotImplementedError("2D -> 3D checkpoint inflation (reference lib/_utils.py:133-238) is not implemented yet")
+        """Initialise the video model from a 2-D LAVT checkpoint (reference lib/_utils.py:133-181; train.py:575,
+        test_ytvos.py:176): patch-embed weight unsqueezed in time, bias tables resized + tiled over the temporal offsets."""
+        return self._load_inflated(pretrained, drop_fusion=False)
+
+    def load_from_pretrained2d_lavt_weights_into_a_3d_model(self, pretrained):
+        """Same, but the 2-D ``.fusion`` weights are dropped (reference lib/_utils.py:183-238)."""
+        return self._load_inflated(pretrained, drop_fusion=True)

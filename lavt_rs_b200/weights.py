@@ -20,3 +20,39 @@ def load_reference_state_dict(module: torch.nn.Module, sd: Dict[str, torch.Tenso
     unexpected = [k for k in result.unexpected_keys if not k.endswith(_BENIGN) and not k.startswith(ign)]
     if missing or unexpected:
         raise KeyError(f"state dict mismatch: missing={missing[:8]} unexpected={unexpected[:8]}")
+
+
+def inflate_lavt2d_state_dict(sd: Dict[str, torch.Tensor], window_size, current: Dict[str, torch.Tensor],
+                              drop_fusion: bool = False) -> Dict[str, torch.Tensor]:
+    """2-D LAVT checkpoint -> video model state dict (reference lib/_utils.py:133-181, :183-238 with ``drop_fusion``).
+
+    * ``relative_position_index`` / ``attn_mask`` entries are dropped (buffers are rebuilt by the modules)
+    * the patch-embedding Conv2d weight (C,3,4,4) gains a temporal axis of length 1 -> Conv3d weight (C,3,1,4,4)
+    * every 2-D bias table ((2w-1)^2, nH) is bicubically resized to the video model's (2Wh-1) x (2Ww-1) when the spatial
+      window differs, then tiled (2Wd-1) times along the leading (temporal-offset-major) axis; a head-count mismatch
+      leaves the tiled pretrained table as is (the reference prints an error and passes)
+    * ``drop_fusion``: the ``.fusion`` entries are removed (2-D PWAM vs 3-D fusion modules differ)
+    """
+    Wd, Wh, Ww = (int(w) for w in window_size)
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if "relative_position_index" in k or "attn_mask" in k:
+            continue
+        if drop_fusion and ".fusion" in k:
+            continue
+        out[k] = v
+    if "backbone.patch_embed.proj.weight" not in out:
+        raise KeyError("2-D LAVT checkpoint without backbone.patch_embed.proj.weight")
+    out["backbone.patch_embed.proj.weight"] = out["backbone.patch_embed.proj.weight"].unsqueeze(2)
+    for k in [k for k in out if "relative_position_bias_table" in k]:
+        tab = out[k]
+        L1, nH1 = tab.shape
+        nH2 = current[k].shape[1]
+        L2 = (2 * Wh - 1) * (2 * Ww - 1)
+        if nH1 == nH2 and L1 != L2:
+            S1 = int(L1 ** 0.5)
+            grid = tab.permute(1, 0).reshape(1, nH1, S1, S1)
+            grid = torch.nn.functional.interpolate(grid, size=(2 * Wh - 1, 2 * Ww - 1), mode="bicubic")
+            tab = grid.reshape(nH2, L2).permute(1, 0)
+        out[k] = tab.repeat(2 * Wd - 1, 1)
+    return out

@@ -49,6 +49,24 @@ def test_full_model_state_dict_round_trips_with_reference():
     mine.load_state_dict({k: v for k, v in ref_sd.items() if not k.startswith("text_encoder.")}, strict=False)
     idx = "backbone.layers.2.blocks.5.attn.relative_position_index"
     assert torch.equal(mine.state_dict()[idx], ref_sd[idx])
+    # method wiring of the 2-D -> video checkpoint inflation (the tensor math is pinned against the reference's own
+    # loader in tests/test_oracle_vs_reference.py): a synthetic 2-D checkpoint cut out of the video state dict
+    import contextlib
+    import io
+    import tempfile
+    sd2d = {k: v.clone() for k, v in ref_sd.items() if not k.startswith("text_encoder.")}
+    sd2d["backbone.patch_embed.proj.weight"] = sd2d["backbone.patch_embed.proj.weight"].squeeze(2)
+    tkey = "backbone.layers.1.blocks.0.attn.relative_position_bias_table"
+    for k in [k for k in sd2d if "relative_position_bias_table" in k]:
+        sd2d[k] = sd2d[k][:169] + 1.0
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "lavt2d.pth")
+        torch.save({"model": sd2d}, path)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mine.load_from_pretrained2d_lavt_weights(path)
+    got = mine.state_dict()
+    assert got["backbone.patch_embed.proj.weight"].shape == ref_sd["backbone.patch_embed.proj.weight"].shape
+    assert torch.equal(got[tkey], sd2d[tkey].repeat(15, 1))
 
 
 def test_builders_reject_unimplemented_flags():

@@ -111,3 +111,33 @@ def test_random_state_dict_matches_reference_keys():
     assert ref_keys == set(sd.keys())
     for k in ref_keys:
         assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.parametrize("into_3d", [False, True])
+def test_pretrained2d_inflation_matches_reference(tmp_path, into_3d):
+    """LAVTVideo.load_from_pretrained2d_lavt_weights[_into_a_3d_model] (reference lib/_utils.py:133-238): same resulting
+    state dict as the reference's own method, starting from a 2-D lavt_one checkpoint with window 12 -> video window (8,7,7)
+    (bicubic resize of the bias tables + temporal tiling + patch-embed unsqueeze)."""
+    ref2d, _ = ref_shims.build_reference("lavt_one", "tiny", window12=True, seed=3)
+    ckpt = tmp_path / "lavt2d.pth"
+    torch.save({"model": ref2d.state_dict()}, ckpt)
+    ref3d, _ = ref_shims.build_reference("lavt_video", "tiny", seed=4)
+    import contextlib
+    import io
+    name = "load_from_pretrained2d_lavt_weights_into_a_3d_model" if into_3d else "load_from_pretrained2d_lavt_weights"
+    with contextlib.redirect_stdout(io.StringIO()):
+        getattr(ref3d, name)(str(ckpt))
+    from lavt_rs_b200.weights import inflate_lavt2d_state_dict
+    before = {k: v.clone() for k, v in ref_shims.build_reference("lavt_video", "tiny", seed=4)[0].state_dict().items()}
+    got = inflate_lavt2d_state_dict(ref2d.state_dict(), (8, 7, 7), before, drop_fusion=into_3d)
+    want = ref3d.state_dict()
+    checked = 0
+    for k, v in got.items():
+        if k not in want or want[k].shape != v.shape:
+            continue                      # (2-D fusion keys that the video model does not have / cannot take)
+        assert torch.equal(want[k], v) or torch.allclose(want[k], v, atol=1e-6), k
+        checked += 1
+    tables = [k for k in got if "relative_position_bias_table" in k]
+    assert len(tables) == 12 and all(got[k].shape[0] == 15 * 13 * 13 for k in tables)
+    assert got["backbone.patch_embed.proj.weight"].dim() == 5 and checked > 100
+    assert into_3d == (not any(".fusion" in k for k in got))
