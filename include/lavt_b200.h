@@ -70,14 +70,14 @@ int lavt_check_device(void);
  *   qkv / proj  lib/video_swin_transformer.py:144,166 (lib/backbone.py:125,139)
  *   fc1 / fc2   :30-36          PatchMerging.reduction :309     PatchEmbed3D.proj :627
  *   PWAM vis_project / f_query / W / project_mm :900-973        LanguageGate res_gate :519-525
- * Requires N % 128 == 0, K % 64 == 0. */
+ * Requires N % 32 == 0, K % 8 == 0 (tile remainders are handled by TMA zero fill and a column guard in the epilogue). */
 int lavt_gemm_bf16(const void* A, int64_t lda, const void* Wt, int64_t ldw, int32_t M, int32_t N, int32_t K,
                    const lavt_epilogue_t* epi, void* stream);
 
 /* 3x3 / pad 1 / stride 1 convolution as an implicit GEMM over NHWC bf16 input (pixel pitch ldx >= Cin):
  *   out[pix, co] = epilogue( sum_{ky,kx,ci} x[img, h+ky-1, w+kx-1, ci] * Wt[co, (ky*3+kx)*Cin + ci] )
  * Replaces conv{1,2}_{4,3,2} + BatchNorm2d(eval, folded into cscale/bias) + ReLU of
- * SimpleDecoding.forward, lib/mask_predictor.py:56-87.  Requires Cin % 64 == 0, Cout % 128 == 0. */
+ * SimpleDecoding.forward, lib/mask_predictor.py:56-87.  Requires Cin % 8 == 0, Cout % 32 == 0. */
 int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H, int32_t W, int32_t Cin,
                       const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream);
 
@@ -85,14 +85,14 @@ int lavt_conv3x3_bf16(const void* x_nhwc, int64_t ldx, int32_t n_img, int32_t H,
  *   out[pos, co] = epilogue( sum_{kz,ky,kx,ci} x[clip, d+kz-1, h+ky-1, w+kx-1, ci] * Wt[co, ((kz*3+ky)*3+kx)*Cin + ci] )
  * Replaces the Conv3d(3,3,3) layers of SepTPWAM (temporal_vis_project / f_query_t / W_t / project_mm_t,
  * lib/video_swin_transformer.py:1334-1336, 1376-1379, 1435-1438, 1459-1461) under the README video flags
- * (--sep_t_pwam --conv3d_kernel_size_t 3-3-3 ...).  Requires Cin % 64 == 0, Cout % 128 == 0. */
+ * (--sep_t_pwam --conv3d_kernel_size_t 3-3-3 ...).  Requires Cin % 8 == 0, Cout % 32 == 0. */
 int lavt_conv3d_bf16(const void* x_ndhwc, int64_t ldx, int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin,
                      const void* Wt, int32_t Cout, const lavt_epilogue_t* epi, void* stream);
 
 /* ---- LayerNorm fused with the gathers that feed the GEMMs (fp32 rows in, bf16 and/or fp32 rows out) ---- */
 
 /* out[m,:] = LN(x[m,:]) * gamma + beta over C channels.  norm2 before the MLP (lib/video_swin_transformer.py:250),
- * patch_embed.norm (:630), per-stage output norm{i} (:871).  C % 128 == 0. out_bf16 / out_f32 may be NULL (not both). */
+ * patch_embed.norm (:630), per-stage output norm{i} (:871).  C % 4 == 0, C <= 3072. out_bf16 / out_f32 may be NULL (not both). */
 int lavt_layernorm_rows(const float* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
                         float eps, void* out_bf16, float* out_f32, void* stream);
 

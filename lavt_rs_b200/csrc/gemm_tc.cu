@@ -137,9 +137,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   long long* const trace = (blockIdx.x == 0) ? trace_buf : nullptr;     // debug (LAVT_GEMM_TRACE): clock64 stamps of CTA 0
 #define GEMM_TRACE(ev, lt) do { if (trace && (lt) < 32) trace[(ev) * 32 + (lt)] = clock64(); } while (0)
-  const int n_tiles = p.N / GEMM_BN;
+  // N and K need not be multiples of the tile: TMA zero-fills operand rows / columns past the tensor edge (so the extra
+  // accumulator columns are exact zeros and the extra K contributes nothing) and the epilogue skips columns >= N.
+  // conv: each tap spans ceil(Cin / 64) k-blocks; a block's surplus channels are zero-filled on the A side, which makes the
+  // (finite) next-tap weights the B box picks up there irrelevant.
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int total_tiles = m_tiles * n_tiles;
-  const int num_kb = p.K / GEMM_BK;
+  const int conv_cpb = (p.cCin + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = (p.rowmap == ROWMAP_CONV) ? p.taps * conv_cpb : (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -176,7 +181,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       const bool conv = (p.rowmap == ROWMAP_CONV);
-      const int cpb = conv ? (p.cCin / GEMM_BK) : 1;
+      const int cpb = conv ? conv_cpb : 1;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles;
@@ -201,8 +206,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          int bk0 = kb * GEMM_BK;                      // first K index of this block in the weight matrix
           if (conv) {
             const int tap = kb / cpb, cc = kb - tap * cpb;
+            bk0 = tap * p.cCin + cc * GEMM_BK;
             if (p.taps == 27) {
               // 3x3x3: tap = (kz * 3 + ky) * 3 + kx; frames outside the clip are zero-filled by TMA like the spatial border
               const int dz = tap / 9 - 1, r9 = tap % 9;
@@ -215,7 +222,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+          tma_load_2d(sb, &tmB, &full_bar[s], bk0, n0);
         }
       }
     }
@@ -277,8 +284,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float* w_scale = vec + wg * 2 * GEMM_BN;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         for (int i = et; i < GEMM_BN; i += 128) {
-          w_scale[i] = p.cscale ? __ldg(p.cscale + n0 + i) : 1.0f;
-          w_scale[GEMM_BN + i] = p.bias ? __ldg(p.bias + n0 + i) : 0.0f;
+          const bool in = n0 + i < p.N;
+          w_scale[i] = (p.cscale && in) ? __ldg(p.cscale + n0 + i) : 1.0f;
+          w_scale[GEMM_BN + i] = (p.bias && in) ? __ldg(p.bias + n0 + i) : 0.0f;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
       }
@@ -308,12 +316,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
       bool acc_ready = false;
+      const int nch = min(GEMM_BN / 32, (p.N - n0 + 31) / 32);      // 32-column chunks of this tile that exist (N % 32 == 0)
 
 #pragma unroll 1
       for (int c = 0; c < GEMM_BN / 32; ++c) {
         // operands that do not depend on the accumulator are requested first (for c == 0: before the MMAs finish)
         uint32_t rr[32];
-        if (res_row) {
+        if (res_row && c < nch) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) ldg_v8(&rr[q * 8], res_row + c * 32 + q * 8);
         }
@@ -332,7 +341,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (!live) continue;
+        if (!live || c >= nch) continue;
         float f[32];
         {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
@@ -430,7 +439,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const long long total = 1LL * m_tiles * (p.N / BN);
+  const long long total = 1LL * m_tiles * ((p.N + BN - 1) / BN);
   LAVT_REQUIRE(total < (1LL << 30), "gemm: too many tiles (%lld)", total);
   const long long slots = 1LL * sm_count() * L::MIN_CTAS;
   const int grid = static_cast<int>(total < slots ? total : slots);
@@ -476,7 +485,7 @@ static int gemm_variant(const GemmParams& p) {
     // whenever they still fill the machine; 2 CTAs/SM wins for long K at N = 128; otherwise the 1-CTA/SM pipeline
     const long long m_tiles = (p.rowmap == ROWMAP_CONV) ? (1LL * (p.M / (p.cH * p.cW)) * p.cTilesH * p.cTilesW)
                                                         : ((p.M + GEMM_BM - 1) / GEMM_BM);
-    if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= sm_count() / 2) v = 2;
+    if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= sm_count() / 2) v = 2;      // (partial 256-wide tiles never pay off)
     else v = (p.K >= 1024) ? 1 : 0;
   }
   if (v == 2 && (p.N % 256) != 0) v = 0;
@@ -486,8 +495,8 @@ static int gemm_variant(const GemmParams& p) {
 int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, const GemmParams& p,
                   cudaStream_t stream) {
   LAVT_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  LAVT_REQUIRE(p.N % 128 == 0, "gemm: N=%d must be a multiple of 128", p.N);
-  LAVT_REQUIRE(p.K % GEMM_BK == 0, "gemm: K=%d must be a multiple of 64", p.K);
+  LAVT_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
+  LAVT_REQUIRE(p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);
   LAVT_REQUIRE(p.ldo % 16 == 0 && p.ldo >= p.N, "gemm: ldo=%d invalid for N=%d (need a multiple of 16)", p.ldo, p.N);
   LAVT_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) | reinterpret_cast<uintptr_t>(p.out_bf16) |
                 reinterpret_cast<uintptr_t>(p.resid) | reinterpret_cast<uintptr_t>(p.mul)) % 32 == 0,
@@ -499,7 +508,7 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
   CUtensorMap tmA, tmB;
   int m_tiles;
   if (p.rowmap == ROWMAP_CONV) {
-    LAVT_REQUIRE(p.cCin % GEMM_BK == 0, "conv: Cin=%d must be a multiple of 64", p.cCin);
+    LAVT_REQUIRE(p.cCin % 8 == 0, "conv: Cin=%d must be a multiple of 8", p.cCin);
     LAVT_REQUIRE(p.cTH * p.cTW == GEMM_BM, "conv: tile %dx%d != 128 pixels", p.cTH, p.cTW);
     LAVT_REQUIRE(p.K == p.taps * p.cCin, "conv: K mismatch");
     const int n_img = p.M / (p.cH * p.cW);             // 2-D: images; 3-D: clips * frames

@@ -12,16 +12,21 @@
 
 namespace lavt {
 
-// NV = float4 per lane: Cn = NV * 128.  Each warp handles RPW consecutive OUTPUT rows: their loads are all in flight
-// together, and the closed-form window gather (a dozen integer divisions per row, geom.cuh::win_token) is evaluated by
-// RPW lanes in parallel and broadcast by shuffle instead of being recomputed by all 32 lanes of a one-row warp (at
-// C = 128 that index arithmetic, not memory, bounded the gather kernel).
+// NV = float4 slots per lane: Cn <= NV * 128 (a lane's slot i covers channels [(i*32+lane)*4, +4); slots past Cn are
+// masked, which is what Swin-T/S widths such as 96 or 192 need).  Each warp handles RPW consecutive OUTPUT rows: their
+// loads are all in flight together, and the closed-form window gather (a dozen integer divisions per row,
+// geom.cuh::win_token) is evaluated by RPW lanes in parallel and broadcast by shuffle instead of being recomputed by all
+// 32 lanes of a one-row warp (at C = 128 that index arithmetic, not memory, bounded the gather kernel).
 template <int MODE, int NV, int RPW>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const long long m0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (m0 >= p.M) return;
-  constexpr int Cn = NV * 128;
+  const int Cn = (MODE == MODE_MERGE) ? 4 * p.C : p.C;
+  const float inv_cn = 1.0f / static_cast<float>(Cn);
+  bool slot[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) slot[i] = (i * 32 + lane) * 4 < Cn;
   float4 v[RPW][NV];
   long long myrow = -1;
   if (MODE == MODE_WINDOW) {
@@ -45,7 +50,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
         const int col = (i * 32 + lane) * 4;           // column in [0, 4C)
         const int q = col / p.C, c = col - q * p.C;
         const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
-        if (h < p.mH && w < p.mW) {
+        if (slot[i] && h < p.mH && w < p.mW) {
           const float* src = p.x + ((bd * p.mH + h) * p.mW + w) * p.ldx + c;
           v[r][i] = __ldg(reinterpret_cast<const float4*>(src));
         } else {
@@ -60,7 +65,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
       }
       const float4* src = reinterpret_cast<const float4*>(p.x + (row < 0 ? 0 : row) * p.ldx);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[r][i] = live[r] ? __ldg(src + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < NV; ++i)
+        v[r][i] = (live[r] && slot[i]) ? __ldg(src + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 
@@ -71,31 +77,29 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
     const long long m = m0 + r;
     if (m >= p.M) break;
     if (!live[r]) {   // window pad row: zeros AFTER the norm (F.pad follows norm1 in the reference)
-      if (p.out_bf16) {
-        uint2* o = reinterpret_cast<uint2*>(p.out_bf16 + m * Cn);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) o[i * 32 + lane] = make_uint2(0u, 0u);
-      }
-      if (p.out_f32) {
-        float4* o = reinterpret_cast<float4*>(p.out_f32 + m * Cn);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) o[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < NV; ++i) {
+        if (!slot[i]) continue;
+        if (p.out_bf16) reinterpret_cast<uint2*>(p.out_bf16 + m * Cn)[i * 32 + lane] = make_uint2(0u, 0u);
+        if (p.out_f32) reinterpret_cast<float4*>(p.out_f32 + m * Cn)[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       continue;
     }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    const float mean = warp_sum(s) * (1.0f / Cn);
+    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);     // masked slots hold zeros
+    const float mean = warp_sum(s) * inv_cn;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      if (!slot[i]) continue;
       const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
       ss += (a * a + b * b) + (c * c + d * d);
     }
-    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / Cn) + p.eps);
+    const float rstd = rsqrtf(warp_sum(ss) * inv_cn + p.eps);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      if (!slot[i]) continue;
       const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
       float4 y;
       y.x = (v[r][i].x - mean) * rstd * g.x + b.x;
@@ -120,7 +124,7 @@ static void launch_ln_nv(const LnParams& p, cudaStream_t st) {
 template <int MODE>
 static int launch_ln(const LnParams& p, int Cn, cudaStream_t st) {
   LAVT_REQUIRE((p.M + 7) / 8 < (1LL << 31), "layernorm: too many rows");
-  switch (Cn / 128) {   // rows per warp chosen so that the row data of a warp stays in registers (<= 16 float4 per lane)
+  switch ((Cn + 127) / 128) {   // rows per warp chosen so that the row data of a warp stays in registers (<= 16 float4 per lane)
     case 1: launch_ln_nv<MODE, 1, 8>(p, st); break;
     case 2: launch_ln_nv<MODE, 2, 8>(p, st); break;
     case 3: launch_ln_nv<MODE, 3, 4>(p, st); break;
@@ -131,7 +135,7 @@ static int launch_ln(const LnParams& p, int Cn, cudaStream_t st) {
     case 16: launch_ln_nv<MODE, 16, 1>(p, st); break;
     case 24: launch_ln_nv<MODE, 24, 1>(p, st); break;
     default:
-      set_last_error("layernorm: normalised width %d not supported (need 128 * {1,2,3,4,6,8,12,16,24})", Cn);
+      set_last_error("layernorm: normalised width %d not supported (ceil(width / 128) must be in {1,2,3,4,6,8,12,16,24})", Cn);
       return LAVT_ERR_SHAPE;
   }
   LAVT_LAUNCH_CHECK("ln_rows_kernel");
@@ -143,7 +147,7 @@ int ln_rows_dispatch(int mode, const LnParams& p, cudaStream_t st) {
   LAVT_REQUIRE(p.out_bf16 || p.out_f32, "layernorm: no output");
   LAVT_REQUIRE(p.ldx % 4 == 0 && p.C % 4 == 0, "layernorm: pitch / channels must be multiples of 4");
   const int Cn = (mode == MODE_MERGE) ? 4 * p.C : p.C;
-  LAVT_REQUIRE(Cn % 128 == 0, "layernorm: normalised width %d must be a multiple of 128", Cn);
+  LAVT_REQUIRE(Cn % 4 == 0, "layernorm: normalised width %d must be a multiple of 4", Cn);
   if (mode == MODE_IDENTITY) return launch_ln<MODE_IDENTITY>(p, Cn, st);
   if (mode == MODE_WINDOW) return launch_ln<MODE_WINDOW>(p, Cn, st);
   if (mode == MODE_MERGE) return launch_ln<MODE_MERGE>(p, Cn, st);

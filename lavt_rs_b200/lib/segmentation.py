@@ -31,9 +31,9 @@ def _swin_cfg(args, kind):
     if st not in _SWIN or (kind == "video" and st == "large"):
         raise ValueError(f"unknown swin_type {st!r}")
     embed_dim, depths, heads, dpr = _SWIN[st]
-    if embed_dim % 128:
-        raise NotImplementedError(f"swin_type {st!r} (embed_dim {embed_dim}) is not supported yet: the sm_100a kernels "
-                                  "tile channels in multiples of 128 (Swin-B, the benchmark configuration)")
+    if embed_dim % 32:
+        raise NotImplementedError(f"swin_type {st!r} (embed_dim {embed_dim}): the sm_100a kernels need channel counts that "
+                                  "are multiples of 32")
     return embed_dim, list(depths), list(heads), dpr[kind]
 
 

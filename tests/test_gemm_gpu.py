@@ -116,11 +116,27 @@ def test_conv3d_333(cabi, n_clip, D, H, W, Cin, Cout, act):
     _close(out.view(n_clip, D, H, W, Cout), ref.permute(0, 2, 3, 4, 1), 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 96, 96), (777, 288, 96), (4096, 192, 384), (300, 1152, 480), (129, 32, 40)])
+def test_gemm_tile_remainders(cabi, M, N, K):
+    """N % 128 != 0, K % 64 != 0 (Swin-T/S widths): TMA zero fill past the operand edges + column guard in the epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    guard = torch.full((M + 1, N), 7.0, device="cuda")          # the row after the output must stay untouched
+    out = guard[:M]
+    cabi.gemm_bf16(a, w, bias=bias, act=cabi.ACT_GELU, resid=res, out_f32=out)
+    ref = F.gelu(a.float() @ w.float().t() + bias) + res
+    _close(out, ref, 2e-2)
+    assert (guard[M] == 7.0).all()
+
+
 def test_gemm_rejects_bad_shapes(cabi):
-    a = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
-    w = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
+    a = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
     out = torch.empty(128, 128, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(cabi.LavtError):
-        cabi.gemm_bf16(a, w, out_bf16=out)          # K % 64 != 0
+        cabi.gemm_bf16(a, w, out_bf16=out)          # K % 8 != 0 (TMA needs 16-byte row pitches)
     with pytest.raises(cabi.LavtError):
         cabi.gemm_bf16(a.cpu(), w, out_bf16=out)    # no CPU fallback

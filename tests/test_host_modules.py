@@ -74,8 +74,9 @@ def test_builders_reject_unimplemented_flags():
     for flag in ("--sep_t_pwam", "--hs", "--lazy_pred"):
         with pytest.raises(NotImplementedError):
             segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "base", flag]))
-    with pytest.raises(NotImplementedError):
-        segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny"]))
+    # Swin-T / Swin-S widths (96 channels) build: the README's video commands use --swin_type tiny
+    tiny = segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny"]))
+    assert tiny.backbone.embed_dim == 96
 
 
 def test_forward_refuses_cpu_tensors():

@@ -280,3 +280,33 @@ def test_bert_text_encoder(layers, B, Nl):
     live = mask.bool()
     r = ((got[live] - ref[live]).norm() / ref[live].norm()).item()
     assert r < 2e-2, f"rel-L2 {r:.3e}"
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_swin_tiny_width_end_to_end(sep):
+    """Swin-T / Swin-S channel widths (96, 192, 384, 768; 3-24 heads): tile remainders in the GEMM / conv kernel (N % 128,
+    K % 64, Cin % 64 != 0) and masked LayerNorm lanes, vs the oracle end to end (backbone + decoder)."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(embed_dim=96, depths=(2, 2, 2, 2), num_heads=(3, 6, 12, 24), window=(8, 7, 7), sep_t_pwam=sep)
+    sd = O.random_state_dict(cfg, seed=0)
+    args = default_args(["--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel_size_s", "1-1-1", "--w_t3x3_s1x1",
+                         "--mm_t3x3_s1x1"]) if sep else None      # the README's `--swin_type tiny` video configuration
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=96, depths=[2, 2, 2, 2], num_heads=[3, 6, 12, 24],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=args)
+    dec = SimpleDecoding(768, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(2, 4, 64, 96, Nl=20)
+    cap = {}
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.permute(0, 2, 1, 3, 4).cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        got = model._segment(x.cuda().permute(0, 2, 1, 3, 4), l.cuda(), m.cuda(), (64, 96))
+    for i in range(4):
+        assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
