@@ -26,13 +26,14 @@ _STRUCTURE_FLAGS = [
     ("--img_size", int, 480, "input size"),
     ("--lg_act_layer", str, "tanh", "LanguageGate activation (2-D backbone)"),
     ("--att_norm_layer_type", str, "IN", "PWAM attention norm (2-D backbone)"),
+    ("--hs", "store_true", False, "stage outputs = gated features E_i instead of the PWAM residuals"),
     ("--sep_t_pwam", "store_true", False, "SepTPWAM fusion: temporal Conv3d + spatial Conv3d branches, summed"),
     ("--conv3d_kernel_size_t", str, "3-1-1", "temporal-branch Conv3d kernel (B200 path: 3-3-3)"),
     ("--conv3d_kernel_size_s", str, "1-1-1", "spatial-branch Conv3d kernel (B200 path: 1-1-1)"),
     ("--w_t3x3_s1x1", "store_true", False, "SepTPWAM: W = IN(conv_t) + IN(conv_s)"),
     ("--mm_t3x3_s1x1", "store_true", False, "SepTPWAM: project_mm = GELU(conv_t) + GELU(conv_s)"),
 ]
-_REJECTED_BOOL_FLAGS = ["hs", "lazy_pred", "ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam",
+_REJECTED_BOOL_FLAGS = ["lazy_pred", "ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam",
                         "sep_t_pwam_inner", "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "interpolate_before_seg", "seg_last"]
 
 

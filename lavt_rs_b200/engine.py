@@ -343,9 +343,11 @@ def _cbr(x_nhwc: torch.Tensor, dec, conv_name: str, bn_name: str, out: torch.Ten
 
 
 def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: torch.Tensor, ws: Workspace,
-                 logits_nchw: Optional[torch.Tensor]) -> torch.Tensor:
+                 logits_nchw: Optional[torch.Tensor], feats: Optional[list] = None) -> torch.Tensor:
     """c_i bf16 NHWC [n_img, H_i, W_i, C_i]; optional logits_nchw fp32 [n_img, 2, H_1, W_1].
-    Returns the low-resolution logits as an NHWC fp32 workspace view [n_img, H_1, W_1, 2]."""
+    Returns the low-resolution logits as an NHWC fp32 workspace view [n_img, H_1, W_1, 2].
+    ``feats``: if a list, the three top-down maps after conv2_4 / conv2_3 / conv2_2 (NHWC bf16 workspace views) are
+    appended (SimpleDecoding.forward_feats, lib/mask_predictor.py:102-150)."""
     dev = c1.device
     n_img = c1.shape[0]
     hid = dec.conv1_4.weight.shape[0]
@@ -363,6 +365,8 @@ def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: 
         t2 = ws.get("dec_t2_%d" % H, (n_img, H, W, hid), torch.bfloat16, dev)
         _cbr(t1, dec, cb, bb, t2)
         y = t2
+        if feats is not None:
+            feats.append(t2)
         _count(1)
     _, H, W, _ = y.shape
     w11 = dec.prepared.get("w11", [dec.conv1_1.weight], lambda: _f32(dec.conv1_1.weight.reshape(2, -1)))

@@ -112,6 +112,18 @@ class LAVTVideo(_Segmenter):
         x5 = _planes(x).permute(0, 2, 1, 3, 4)
         return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)
 
+    def forward_feats(self, x, text, l_mask):
+        """Reference lib/_utils.py:110-131: (logits (B*T,2,H,W), decoder feature maps) -- used by test.py:155."""
+        E.require_cuda(x, "x")
+        l_feats, ev = self._encode_text_async(text, l_mask)
+        x5 = _planes(x).permute(0, 2, 1, 3, 4)
+        nchw, _ = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=True, want_nhwc_bf16=False, lang_ready=ev)
+        x_c1, x_c2, x_c3, x_c4 = nchw
+        low, feats = self.classifier.forward_feats(x_c4, x_c3, x_c2, x_c1)
+        out = torch.empty(low.shape[0], 2, x.shape[-2], x.shape[-1], device=low.device, dtype=torch.float32)
+        K.upsample_logits(low.permute(0, 2, 3, 1).contiguous(), out)
+        return out, feats
+
     def forward_with_lang(self, x, l_feats, l_mask):
         """Hot path after BERT: x (B,T,3,H,W), l_feats (B,768,Nl), l_mask (B,Nl)."""
         x5 = _planes(x).permute(0, 2, 1, 3, 4)     # (B,3,T,H,W) view; read in place by the im2col kernel

@@ -36,8 +36,21 @@ class SimpleDecoding(nn.Module):
         E.decoder_nhwc(self, c4, c3, c2, c1, E.workspace(c1.device), logits)
         return logits
 
+    def forward_feats(self, x_c4, x_c3, x_c2, x_c1):
+        """Reference lib/mask_predictor.py:102-150: (logits, [x_c4, Y3, Y2, Y1]) with the top-down maps after each
+        conv2_* + BN + ReLU as NCHW fp32 (API-compat copies of the NHWC bf16 buffers; not a hot path)."""
+        maps = self._to_nhwc(x_c4, x_c3, x_c2, x_c1)
+        n_img, H, W, _ = maps[3].shape
+        logits = torch.empty(n_img, 2, H, W, device=x_c1.device, dtype=torch.float32)
+        inter = []
+        E.decoder_nhwc(self, *maps, E.workspace(x_c1.device), logits, feats=inter)
+        return logits, [x_c4] + [t.permute(0, 3, 1, 2).float().contiguous() for t in inter]
+
     def forward(self, x_c4, x_c3, x_c2, x_c1) -> torch.Tensor:
         """Reference signature: four NCHW fp32 maps (coarse -> fine) -> (n_img, 2, H1, W1) logits."""
+        return self.run_nhwc(*self._to_nhwc(x_c4, x_c3, x_c2, x_c1))
+
+    def _to_nhwc(self, x_c4, x_c3, x_c2, x_c1):
         maps = []
         for t in (x_c4, x_c3, x_c2, x_c1):
             E.require_cuda(t, "feature map")
@@ -50,4 +63,4 @@ class SimpleDecoding(nn.Module):
             K.nchw_to_nhwc_bf16(t.view(n, C, H * W), o.view(n, H * W, C))
             E._count(1)
             maps.append(o)
-        return self.run_nhwc(*maps)
+        return maps

@@ -224,7 +224,7 @@ def _mask(l_mask: torch.Tensor) -> torch.Tensor:
 
 
 _UNSUPPORTED_FLAGS = ("ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam", "sep_t_pwam_inner",
-                      "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "hs", "lazy_pred")
+                      "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "lazy_pred")
 
 
 def _ksize(text, default):
@@ -266,6 +266,7 @@ class MMBasicLayer(nn.Module):
                                    drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
                                    norm_layer=norm_layer, use_checkpoint=use_checkpoint)
             for i in range(depth)])
+        self.hs = bool(getattr(args, "hs", False))       # stage output = gated x (E_i) instead of the residual (:579-587)
         self.sep_t_pwam = bool(getattr(args, "sep_t_pwam", False))
         if self.sep_t_pwam:      # reference :470-479
             self.fusion = SepTPWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop,
@@ -463,7 +464,8 @@ class MultiModalSwinTransformer3D(nn.Module):
                 ob = None
                 if want_nhwc_bf16:
                     ob = ws.get("out_bf16_%d" % i, (B * D, Hc, Wc, C), torch.bfloat16, dev)
-                K.layernorm_rows(r, norm.weight, norm.bias, out_bf16=ob.view(n, C) if ob is not None else None,
+                # stage output: the PWAM residual, or with --hs the gated features (x is not modified by the downsample)
+                K.layernorm_rows(x if layer.hs else r, norm.weight, norm.bias, out_bf16=ob.view(n, C) if ob is not None else None,
                                  out_f32=of, eps=norm.eps)
                 E._count(1)
                 if want_nchw:

@@ -40,6 +40,7 @@ class OracleConfig:
     clamp_window: bool = True                     # 3-D backbone clamps (get_window_size); 2-D never does
     video: bool = True
     gate_act: str = "tanh"
+    hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
     sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
                                                   # --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1
 
@@ -293,7 +294,8 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             capture[f"s{s}.residual"] = r
         if pre + "res_gate.0.weight" in sd:
             x = language_gate(x.reshape(B, D * H * W, C), r, sd, pre + "res_gate.", cfg.gate_act).reshape(B, D, H, W, C)
-        o = F.layer_norm(r.reshape(B, D, H, W, C), (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)
+        stage_out = x if cfg.hs else r.reshape(B, D, H, W, C)
+        o = F.layer_norm(stage_out, (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)
         outs.append(o.permute(0, 1, 4, 2, 3).reshape(B * D, C, H, W))      # (:869-874)
         if pre + "downsample.reduction.weight" in sd:
             x = patch_merging(x, sd, pre + "downsample.")

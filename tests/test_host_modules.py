@@ -71,7 +71,7 @@ def test_full_model_state_dict_round_trips_with_reference():
 
 def test_builders_reject_unimplemented_flags():
     from lavt_rs_b200.lib import segmentation
-    for flag in ("--sep_t_pwam", "--hs", "--lazy_pred"):
+    for flag in ("--sep_t_pwam", "--lazy_pred"):     # (--sep_t_pwam alone keeps the unsupported 3-1-1 temporal kernel)
         with pytest.raises(NotImplementedError):
             segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "base", flag]))
     # Swin-T / Swin-S widths (96 channels) build: the README's video commands use --swin_type tiny

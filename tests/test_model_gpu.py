@@ -310,3 +310,39 @@ def test_swin_tiny_width_end_to_end(sep):
     for i in range(4):
         assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_hs_stage_outputs():
+    """--hs (gated features as stage outputs) through the backbone vs the oracle."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), hs=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=default_args(["--hs"]))
+    load_reference_state_dict(bb, sd, "backbone.")
+    bb = bb.cuda().eval()
+    x, l, m = O.synthetic_inputs(1, 4, 64, 64, Nl=20)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        ref = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+        got = bb(xv.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+    for i in range(4):
+        assert rel_l2(got[i], ref[i]) < 3e-2, (i, rel_l2(got[i], ref[i]))
+
+
+def test_decoder_forward_feats(small):
+    """SimpleDecoding.forward_feats (lib/mask_predictor.py:102-150): logits + the top-down maps after each conv2_*."""
+    cfg, sd, _, dec = small((8, 7, 7))
+    g = torch.Generator().manual_seed(4)
+    n = 2
+    c1, c2, c3, c4 = (torch.randn(n, 128 * 2 ** i, 24 // 2 ** i, 16 // 2 ** i, generator=g) for i in range(4))
+    cap = {}
+    ref = O.decoder_forward(sd, c4, c3, c2, c1, capture=cap)
+    got, feats = dec.forward_feats(c4.cuda(), c3.cuda(), c2.cuda(), c1.cuda())
+    assert_close(got, ref, what="decoder logits", l2=1.5e-2, frac=1e-2)
+    assert len(feats) == 4 and feats[0].shape == c4.shape
+    for f, hw in zip(feats[1:], ((6, 4), (12, 8), (24, 16))):
+        assert tuple(f.shape) == (n, 512, hw[0], hw[1]) and f.dtype == torch.float32
+    assert_close(feats[3], cap["dec_feat"], what="Y1 (decoder feature before conv1_1)", l2=1.5e-2, frac=1e-2)

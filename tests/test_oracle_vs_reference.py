@@ -113,6 +113,21 @@ def test_random_state_dict_matches_reference_keys():
         assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
 
 
+def test_hs_backbone_matches_reference():
+    """--hs: the stage outputs are the gated features (reference MMBasicLayer.forward :579-587)."""
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=(8, 7, 7), depths=(2, 2, 2, 2), extra=("--hs",))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), hs=True)
+    x, l, m = O.synthetic_inputs(1, 4, 64, 64, Nl=11)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        ref = bb(xv, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert (a - b).abs().max().item() < 2e-4, f"stage {i}"
+
+
 @pytest.mark.parametrize("into_3d", [False, True])
 def test_pretrained2d_inflation_matches_reference(tmp_path, into_3d):
     """LAVTVideo.load_from_pretrained2d_lavt_weights[_into_a_3d_model] (reference lib/_utils.py:133-238): same resulting
