@@ -169,6 +169,44 @@ int lavt_upsample_logits(const float* in, float* out, int32_t n_img, int32_t h, 
 int lavt_nhwc_to_nchw(const float* in, float* out, int32_t n_img, int32_t P, int32_t C, void* stream);
 int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32_t P, int32_t C, void* stream);
 
+/* ================================================================================================
+ * Backward pass (training step, BASELINE config 4).  The reference differentiates its forward with autograd
+ * (train.py:330-360: loss.backward()); these are the adjoints of the forward entry points above.  Conventions: the
+ * gradient on the residual stream is fp32 [tokens, C]; gradients that feed a GEMM are bf16 rows; parameter gradients
+ * are fp32 and ACCUMULATED (+=) so that the caller zeroes them once per step (optimizer.zero_grad(), train.py:352).
+ * ================================================================================================ */
+
+/* dst[M, ldd] (+)= A[M,K] x Bt[N,K]^T with the K axis split over work items (weight gradients: dW = dY^T X has few output
+ * tiles and K = all tokens).  A = dY^T [out, tokens], Bt = X^T [in, tokens] (lavt_transpose_bf16).  b_koff shifts the K
+ * coordinate of Bt (taps of a convolution weight gradient over a zero-padded pixel axis).  Adjoint of every nn.Linear /
+ * Conv1d(k=1) / Conv2d weight on the path w.r.t. its weight. */
+int64_t lavt_gemm_splitk_workspace_floats(int32_t M, int32_t N, int32_t K);
+int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t b_koff,
+                          float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream);
+/* out[N, M] (pitch ldo) = in[M, N]^T (pitch ldi), bf16 */
+int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream);
+/* dst[n] += sum_m x[m, n]  (bias gradients); x is bf16 (is_bf16 != 0) or fp32 */
+int lavt_colsum_accumulate(const void* x, int32_t is_bf16, int64_t ldx, int64_t M, int32_t N, float* dst, void* stream);
+/* out bf16 [M, C] = x[src(m)]: src = m, or (geom != NULL) the token of window row m, pad rows -> 0.  Adjoint of the proj
+ * epilogue's window_reverse + un-shift + crop scatter (lib/video_swin_transformer.py:238-247). */
+int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream);
+/* exact-erf GELU on a saved bf16 pre-activation and its derivative (Mlp.act, lib/video_swin_transformer.py:33) */
+int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream);
+int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_t count, void* stream);
+/* LayerNorm backward, adjoints of lavt_layernorm_rows / _window_gather / lavt_patch_merge_layernorm:
+ * dx[token] = dres[token] + LN'(dy[row]) (dres may be NULL or alias dx); dgamma / dbeta accumulate. */
+int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, const float* gamma, float eps,
+                            const float* dres, float* dx, float* dgamma, float* dbeta, void* stream);
+int lavt_layernorm_window_gather_bwd(const float* x, int32_t C, const lavt_win_geom_t* geom, const void* dy_bf16, const float* gamma,
+                                     float eps, const float* dres, float* dx, float* dgamma, float* dbeta, void* stream);
+int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, const void* dy_bf16,
+                                   const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* stream);
+/* Adjoint of lavt_window_attention: qkv / out as saved by the forward, dout = gradient of out; dqkv bf16 [rows, 3C] = gradient
+ * of the UNSCALED qkv projection; dtable_t fp32 [nH, L] accumulates the relative_position_bias_table gradient (transposed).
+ * Windows of up to ~400 tokens (shared-memory resident). */
+int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
+                              const lavt_win_geom_t* geom, void* dqkv, float* dtable_t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,8 +96,20 @@ SIGNATURES = {
     "lavt_upsample_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_nhwc_to_nchw": [_vp, _vp, _i32, _i32, _i32, _vp],
     "lavt_nchw_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _vp],
+    # ---- backward pass ----
+    "lavt_gemm_bf16_splitk": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
+    "lavt_transpose_bf16": [_vp, _i64, _vp, _i64, _i64, _i32, _vp],
+    "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
+    "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
+    "lavt_gelu_fwd": [_vp, _vp, _i64, _vp],
+    "lavt_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
+    "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
+    "lavt_layernorm_window_gather_bwd": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
+    "lavt_patch_merge_layernorm_bwd": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp],
+    "lavt_window_attention_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _WG, _vp, _vp, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
+           "lavt_gemm_splitk_workspace_floats",
            *SIGNATURES.keys()]
 
 
@@ -105,6 +117,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_abi_version.restype = C.c_int
     l.lavt_instnorm_workspace_floats.argtypes = [_i32, _i64, _i32]
     l.lavt_instnorm_workspace_floats.restype = C.c_int64
+    l.lavt_gemm_splitk_workspace_floats.argtypes = [_i32, _i32, _i32]
+    l.lavt_gemm_splitk_workspace_floats.restype = C.c_int64
     l.lavt_set_attention_impl.argtypes = [_i32]
     l.lavt_set_attention_impl.restype = C.c_int
     for name, argtypes in SIGNATURES.items():
@@ -462,3 +476,109 @@ def nchw_to_nhwc_bf16(inp, out) -> None:
     n, Cn, P = inp.shape
     check(lib().lavt_nchw_to_nhwc_bf16(_c(inp, torch.float32, "in").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
                                        n, P, Cn, stream_ptr()), "lavt_nchw_to_nhwc_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# backward pass
+# ------------------------------------------------------------------------------------------------
+def splitk_workspace_floats(M: int, N: int, K: int) -> int:
+    return int(lib().lavt_gemm_splitk_workspace_floats(M, N, K))
+
+
+def gemm_bf16_splitk(a_t: torch.Tensor, b_t: torch.Tensor, dst: torch.Tensor, workspace: torch.Tensor, *, accumulate: bool = True,
+                     b_koff: int = 0, K: Optional[int] = None) -> None:
+    """dst[M, N] (+)= a_t[M, K] @ b_t[N, K].T with split-K; a_t / b_t bf16 (K-major), dst fp32 (row pitch dst.stride(0))."""
+    _req(a_t, torch.bfloat16, "a_t")
+    _req(b_t, torch.bfloat16, "b_t")
+    _req(dst, torch.float32, "dst")
+    M = a_t.shape[0]
+    N = b_t.shape[0]
+    K = int(K if K is not None else a_t.shape[1])
+    if tuple(dst.shape) != (M, N):
+        raise LavtError(f"split-K gemm: dst shape {tuple(dst.shape)} != ({M}, {N})")
+    t0 = TIMER.begin()
+    check(lib().lavt_gemm_bf16_splitk(a_t.data_ptr(), a_t.stride(0), b_t.data_ptr(), b_t.stride(0), M, N, K, b_koff,
+                                      _c(workspace, torch.float32, "workspace").data_ptr(), workspace.numel(), dst.data_ptr(),
+                                      dst.stride(0), 1 if accumulate else 0, stream_ptr()), "lavt_gemm_bf16_splitk")
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N, f"wgrad M{M} N{N} K{K}")
+
+
+def transpose_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x bf16 [M, N] -> out bf16 [N, M] (row pitches taken from the tensors)."""
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    M, N = x.shape
+    if tuple(out.shape) != (N, M):
+        raise LavtError("transpose: shape mismatch")
+    check(lib().lavt_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, N, stream_ptr()), "lavt_transpose_bf16")
+
+
+def colsum_accumulate(x: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[n] += sum_m x[m, n]; x bf16 or fp32 [M, N]."""
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise LavtError("colsum: x must be bf16 or fp32")
+    _req(x, x.dtype, "x")
+    M, N = x.shape
+    check(lib().lavt_colsum_accumulate(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), M, N,
+                                       _c(dst, torch.float32, "dst").data_ptr(), stream_ptr()), "lavt_colsum_accumulate")
+
+
+def cast_rows_bf16(x: torch.Tensor, out: torch.Tensor, geom: Optional[WinGeom] = None) -> None:
+    """out bf16 [M, C] = x fp32 rows (identity) or gathered into window order (pad rows zero)."""
+    _req(x, torch.float32, "x")
+    M, Cn = out.shape
+    check(lib().lavt_cast_rows_bf16(x.data_ptr(), x.stride(0), M, Cn, C.byref(geom) if geom is not None else None,
+                                    _c(out, torch.bfloat16, "out").data_ptr(), stream_ptr()), "lavt_cast_rows_bf16")
+
+
+def gelu_fwd(x: torch.Tensor, y: torch.Tensor) -> None:
+    check(lib().lavt_gelu_fwd(_c(x, torch.bfloat16, "x").data_ptr(), _c(y, torch.bfloat16, "y").data_ptr(), x.numel(), stream_ptr()),
+          "lavt_gelu_fwd")
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor) -> None:
+    check(lib().lavt_gelu_bwd(_c(dy, torch.bfloat16, "dy").data_ptr(), _c(x, torch.bfloat16, "x").data_ptr(),
+                              _c(dx, torch.bfloat16, "dx").data_ptr(), x.numel(), stream_ptr()), "lavt_gelu_bwd")
+
+
+def layernorm_rows_bwd(x, dy, gamma, dx, dgamma, dbeta, *, dres=None, eps: float = 1e-5) -> None:
+    """x fp32 [M, C] (LN input), dy bf16 [M, C]; dx fp32 [M, C] = (dres or 0) + LN'(dy); dgamma / dbeta fp32 [C] accumulate."""
+    _req(x, torch.float32, "x")
+    M, Cn = x.shape
+    check(lib().lavt_layernorm_rows_bwd(x.data_ptr(), x.stride(0), M, Cn, _c(dy, torch.bfloat16, "dy").data_ptr(),
+                                        _c(gamma, torch.float32, "gamma").data_ptr(), eps, ptr(dres), _c(dx, torch.float32, "dx").data_ptr(),
+                                        _c(dgamma, torch.float32, "dgamma").data_ptr(), _c(dbeta, torch.float32, "dbeta").data_ptr(),
+                                        stream_ptr()), "lavt_layernorm_rows_bwd")
+
+
+def layernorm_window_gather_bwd(x, geom: WinGeom, dy, gamma, dx, dgamma, dbeta, *, dres=None, eps: float = 1e-5) -> None:
+    """x fp32 [tokens, C]; dy bf16 [geom.rows(), C] in window order."""
+    _c(x, torch.float32, "x")
+    Cn = x.shape[-1]
+    check(lib().lavt_layernorm_window_gather_bwd(x.data_ptr(), Cn, C.byref(geom), _c(dy, torch.bfloat16, "dy").data_ptr(),
+                                                 _c(gamma, torch.float32, "gamma").data_ptr(), eps, ptr(dres),
+                                                 _c(dx, torch.float32, "dx").data_ptr(), _c(dgamma, torch.float32, "dgamma").data_ptr(),
+                                                 _c(dbeta, torch.float32, "dbeta").data_ptr(), stream_ptr()),
+          "lavt_layernorm_window_gather_bwd")
+
+
+def patch_merge_layernorm_bwd(x, B, D, H, W, dy, gamma, dx, dgamma, dbeta, eps: float = 1e-5) -> None:
+    """x fp32 [B*D*H*W, C]; dy bf16 [B*D*ceil(H/2)*ceil(W/2), 4C]; dx fp32 like x (every token written exactly once)."""
+    _c(x, torch.float32, "x")
+    Cn = x.shape[-1]
+    check(lib().lavt_patch_merge_layernorm_bwd(x.data_ptr(), B, D, H, W, Cn, _c(dy, torch.bfloat16, "dy").data_ptr(),
+                                               _c(gamma, torch.float32, "gamma").data_ptr(), eps, _c(dx, torch.float32, "dx").data_ptr(),
+                                               _c(dgamma, torch.float32, "dgamma").data_ptr(), _c(dbeta, torch.float32, "dbeta").data_ptr(),
+                                               stream_ptr()), "lavt_patch_merge_layernorm_bwd")
+
+
+def window_attention_bwd(qkv, out, dout, table_t, geom: WinGeom, dqkv, dtable_t) -> None:
+    """Adjoint of window_attention; dtable_t fp32 [nH, L] accumulates."""
+    nH, L = table_t.shape
+    t0 = TIMER.begin()
+    check(lib().lavt_window_attention_bwd(_c(qkv, torch.bfloat16, "qkv").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
+                                          _c(dout, torch.bfloat16, "dout").data_ptr(), _c(table_t, torch.float32, "table_t").data_ptr(),
+                                          L, nH, C.byref(geom), _c(dqkv, torch.bfloat16, "dqkv").data_ptr(),
+                                          ptr(dtable_t), stream_ptr()), "lavt_window_attention_bwd")
+    rows = geom.rows()
+    TIMER.end(t0, "window_attn_bwd_kernel", 12.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 8, f"rows{rows} N{geom.N} nH{nH}")

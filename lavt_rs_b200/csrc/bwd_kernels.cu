@@ -1,0 +1,375 @@
+// Bandwidth-bound kernels of the backward pass (training step, BASELINE config 4; the reference differentiates the forward
+// with autograd, train.py:330-360 -- these are the hand-written adjoints of the forward kernels in norm_kernels.cu and of the
+// GEMM epilogues):
+//   splitk_reduce     sums the split-K partials of a weight-gradient GEMM into the (accumulating) fp32 gradient
+//   transpose_bf16    [M, N] -> [N, M]: dY^T and X^T operands of  dW = dY^T X  (the tcgen05 GEMM takes K-major operands)
+//   colsum            bias gradients: dst[n] += sum_m x[m, n]
+//   cast_rows         fp32 rows -> bf16 rows, optionally gathered into window order (adjoint of the proj epilogue's
+//                     window_reverse scatter, lib/video_swin_transformer.py:238-247)
+//   gelu_fwd / bwd    exact-erf GELU on the saved pre-activation (Mlp, :30-36)
+//   ln_bwd<MODE>      LayerNorm backward fused with the adjoint of the forward gather: MODE_IDENTITY (norm2, patch_embed.norm,
+//                     norm{i}), MODE_WINDOW (norm1 + pad + roll + window_partition, :218-234), MODE_MERGE (PatchMerging
+//                     2x2 gather + LN(4C), :298-308); adds the result to the gradient on the residual stream
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+
+namespace lavt {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ part, int splits, long long count4, int ncols4,
+                                                            float* __restrict__ dst, long long ldd, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  float4 a = __ldg(part + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = __ldg(part + s * count4 + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  const long long m = i / ncols4;
+  const int n = static_cast<int>(i - m * ncols4) * 4;
+  float4* d = reinterpret_cast<float4*>(dst + m * ldd + n);
+  if (accumulate) {
+    const float4 o = *d;
+    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+  }
+  *d = a;
+}
+
+int splitk_reduce_dispatch(const float* partials, int splits, long long count, int ncols, float* dst, long long ldd, int accumulate,
+                           cudaStream_t st) {
+  LAVT_REQUIRE(count % 4 == 0 && ncols % 4 == 0 && ldd % 4 == 0, "splitk reduce: sizes must be multiples of 4");
+  const long long c4 = count / 4;
+  splitk_reduce_kernel<<<static_cast<unsigned>((c4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, c4,
+                                                                              ncols / 4, dst, ldd, accumulate);
+  LAVT_LAUNCH_CHECK("splitk_reduce_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[n, m] = in[m, n]   (64 x 64 tiles through shared memory; M, N even)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldi,
+                                                             __nv_bfloat16* __restrict__ out, long long ldo, long long M, int N) {
+  __shared__ unsigned short tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long m0 = static_cast<long long>(blockIdx.x) * 64;
+  const int n0 = blockIdx.y * 64;
+  for (int r = ty; r < 64; r += 8) {
+    uint32_t v = 0;
+    if (m0 + r < M && n0 + 2 * tx < N) v = *reinterpret_cast<const uint32_t*>(in + (m0 + r) * ldi + n0 + 2 * tx);
+    tile[r][2 * tx] = static_cast<unsigned short>(v & 0xffffu);
+    tile[r][2 * tx + 1] = static_cast<unsigned short>(v >> 16);
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    if (n0 + c < N && m0 + 2 * tx < M) {
+      const uint32_t v = static_cast<uint32_t>(tile[2 * tx][c]) | (static_cast<uint32_t>(tile[2 * tx + 1][c]) << 16);
+      *reinterpret_cast<uint32_t*>(out + static_cast<long long>(n0 + c) * ldo + m0 + 2 * tx) = v;
+    }
+  }
+}
+
+int transpose_bf16_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, long long M, int N,
+                            cudaStream_t st) {
+  LAVT_REQUIRE(M > 0 && N > 0 && M % 2 == 0 && N % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0, "transpose: sizes / pitches must be even");
+  const long long mt = (M + 63) / 64, nt = (N + 63) / 64;
+  LAVT_REQUIRE(mt < (1LL << 31) && nt < 65536, "transpose: grid too large (M=%lld, N=%d)", M, N);
+  transpose_bf16_kernel<<<dim3(static_cast<unsigned>(mt), static_cast<unsigned>(nt)), 256, 0, st>>>(in, ldi, out, ldo, M, N);
+  LAVT_LAUNCH_CHECK("transpose_bf16_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dst[n] += sum_m x[m, n]; block = 128 columns x one row chunk, 8 warps stride the rows
+template <bool BF16>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ xv, long long ldx, long long M, int N, long long rows_per_block,
+                                                     float* __restrict__ dst) {
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 128 + lane * 4;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      if (BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xv) + r * ldx + col));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xv) + r * ldx + col));
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(&red[warp][lane * 4]) = acc;
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dst + blockIdx.x * 128 + threadIdx.x, s);
+  }
+}
+
+int colsum_dispatch(const void* x, int is_bf16, long long ldx, long long M, int N, float* dst, cudaStream_t st) {
+  LAVT_REQUIRE(M > 0 && N > 0 && N % 4 == 0 && ldx % 4 == 0, "colsum: N and the pitch must be multiples of 4");
+  const int cb = (N + 127) / 128;
+  long long rb = (148 * 8 + cb - 1) / cb;
+  if (rb > (M + 63) / 64) rb = (M + 63) / 64;
+  if (rb < 1) rb = 1;
+  if (rb > 65535) rb = 65535;
+  const long long rpb = (M + rb - 1) / rb;
+  dim3 grid(cb, static_cast<unsigned>((M + rpb - 1) / rpb));
+  if (is_bf16) colsum_kernel<true><<<grid, 256, 0, st>>>(x, ldx, M, N, rpb, dst);
+  else colsum_kernel<false><<<grid, 256, 0, st>>>(x, ldx, M, N, rpb, dst);
+  LAVT_LAUNCH_CHECK("colsum_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[m, :] = bf16(x[src(m), :]);  src = identity, or the token of window row m (pad rows -> 0)
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
+                                                        long long M, int C, const WinGeom win, const int use_win) {
+  const int lane = threadIdx.x & 31;
+  const long long m0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 32;
+  if (m0 >= M) return;
+  long long myrow = m0 + lane;
+  if (use_win) myrow = (m0 + lane < M) ? win_token(win, m0 + lane).row : -1;
+  for (int r = 0; r < 32; ++r) {
+    const long long m = m0 + r;
+    if (m >= M) break;
+    const long long row = __shfl_sync(0xffffffffu, myrow, r);
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+      uint2 o = make_uint2(0u, 0u);
+      if (row >= 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c4);
+        o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+      reinterpret_cast<uint2*>(out + m * C)[c4] = o;
+    }
+  }
+}
+
+int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, cudaStream_t st) {
+  LAVT_REQUIRE(M > 0 && C % 4 == 0 && ldx % 4 == 0, "cast rows: channels / pitch must be multiples of 4");
+  WinGeom g{};
+  if (win) g = *win;
+  const long long blocks = (M + 255) / 256;
+  LAVT_REQUIRE(blocks < (1LL << 31), "cast rows: too many rows");
+  cast_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, ldx, out, M, C, g, win ? 1 : 0);
+  LAVT_LAUNCH_CHECK("cast_rows_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ out,
+                                                   long long count8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count8) return;
+  const uint4 xv = __ldg(x + i);
+  uint4 gv = make_uint4(0u, 0u, 0u, 0u);
+  if (BWD) gv = __ldg(dy + i);
+  const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_bf16x2(xs[j]);
+    float r0, r1;
+    if (BWD) {
+      const float2 d = unpack_bf16x2(gs[j]);
+      // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+      r0 = d.x * (0.5f * (1.0f + erff(a.x * 0.70710678118654752f)) + a.x * 0.3989422804014327f * __expf(-0.5f * a.x * a.x));
+      r1 = d.y * (0.5f * (1.0f + erff(a.y * 0.70710678118654752f)) + a.y * 0.3989422804014327f * __expf(-0.5f * a.y * a.y));
+    } else {
+      r0 = gelu_erf(a.x);
+      r1 = gelu_erf(a.y);
+    }
+    o[j] = pack_bf16x2(r0, r1);
+  }
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int gelu_fwd_dispatch(const __nv_bfloat16* x, __nv_bfloat16* y, long long count, cudaStream_t st) {
+  LAVT_REQUIRE(count > 0 && count % 8 == 0, "gelu: element count must be a multiple of 8");
+  const long long c8 = count / 8;
+  gelu_kernel<false><<<static_cast<unsigned>((c8 + 255) / 256), 256, 0, st>>>(nullptr, reinterpret_cast<const uint4*>(x),
+                                                                             reinterpret_cast<uint4*>(y), c8);
+  LAVT_LAUNCH_CHECK("gelu_kernel");
+  return LAVT_OK;
+}
+int gelu_bwd_dispatch(const __nv_bfloat16* dy, const __nv_bfloat16* x, __nv_bfloat16* dx, long long count, cudaStream_t st) {
+  LAVT_REQUIRE(count > 0 && count % 8 == 0, "gelu backward: element count must be a multiple of 8");
+  const long long c8 = count / 8;
+  gelu_kernel<true><<<static_cast<unsigned>((c8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x),
+                                                                            reinterpret_cast<uint4*>(dx), c8);
+  LAVT_LAUNCH_CHECK("gelu_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward.  A warp walks groups of 32 OUTPUT rows (the closed-form gathers are evaluated one row per lane and
+// broadcast); d gamma / d beta accumulate in registers over all rows of the block, are combined in shared memory and leave
+// the block as one atomicAdd per channel.
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, const long long rows_per_block) {
+  extern __shared__ float lnb_red[];      // [2 * Cn]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Cn = (MODE == MODE_MERGE) ? 4 * p.C : p.C;
+  const float inv_cn = 1.0f / static_cast<float>(Cn);
+  for (int i = threadIdx.x; i < 2 * Cn; i += blockDim.x) lnb_red[i] = 0.f;
+  __syncthreads();
+  bool slot[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) slot[i] = (i * 32 + lane) * 4 < Cn;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long b0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long b1 = (b0 + rows_per_block < p.M) ? b0 + rows_per_block : p.M;
+  const int H2 = (p.mH + 1) >> 1, W2 = (p.mW + 1) >> 1;
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+
+  for (long long m0 = b0 + warp * 32; m0 < b1; m0 += 8 * 32) {
+    long long myrow = m0 + lane;
+    if (MODE == MODE_WINDOW) myrow = (m0 + lane < b1) ? win_token(p.win, m0 + lane).row : -1;
+    for (int r = 0; r < 32; ++r) {
+      const long long m = m0 + r;
+      if (m >= b1) break;
+      const long long row = __shfl_sync(0xffffffffu, myrow, r);
+      if (row < 0) continue;                       // window pad row: produced as zeros, carries no gradient
+      float4 v[NV];
+      int w2 = 0, h2 = 0;
+      long long bd = 0;
+      if (MODE == MODE_MERGE) {
+        w2 = static_cast<int>(m % W2);
+        h2 = static_cast<int>((m / W2) % H2);
+        bd = m / (static_cast<long long>(W2) * H2);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = (i * 32 + lane) * 4;
+          const int q = col / p.C, c = col - q * p.C;
+          const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
+          v[i] = (slot[i] && h < p.mH && w < p.mW) ? __ldg(reinterpret_cast<const float4*>(p.x + ((bd * p.mH + h) * p.mW + w) * p.ldx + c))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(p.x + row * p.ldx);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = slot[i] ? __ldg(src + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) * inv_cn;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (!slot[i]) continue;
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rstd = rsqrtf(warp_sum(ss) * inv_cn + p.eps);
+      // xhat in place; gy = dy * gamma
+      float4 gy[NV];
+      float s1 = 0.f, s2 = 0.f;
+      const uint2* dy2 = reinterpret_cast<const uint2*>(p.dy + m * Cn);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (!slot[i]) { gy[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        const uint2 u = __ldg(dy2 + i * 32 + lane);
+        const float2 d01 = unpack_bf16x2(u.x), d23 = unpack_bf16x2(u.y);
+        const float4 gm = __ldg(g4 + i * 32 + lane);
+        v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+        v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+        dg[i].x += d01.x * v[i].x; dg[i].y += d01.y * v[i].y; dg[i].z += d23.x * v[i].z; dg[i].w += d23.y * v[i].w;
+        db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
+        gy[i] = make_float4(d01.x * gm.x, d01.y * gm.y, d23.x * gm.z, d23.y * gm.w);
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * v[i].x + gy[i].y * v[i].y) + (gy[i].z * v[i].z + gy[i].w * v[i].w);
+      }
+      s1 = warp_sum(s1) * inv_cn;
+      s2 = warp_sum(s2) * inv_cn;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (!slot[i]) continue;
+        float4 d;
+        d.x = rstd * (gy[i].x - s1 - v[i].x * s2);
+        d.y = rstd * (gy[i].y - s1 - v[i].y * s2);
+        d.z = rstd * (gy[i].z - s1 - v[i].z * s2);
+        d.w = rstd * (gy[i].w - s1 - v[i].w * s2);
+        long long off;
+        if (MODE == MODE_MERGE) {
+          const int col = (i * 32 + lane) * 4;
+          const int q = col / p.C, c = col - q * p.C;
+          const int h = 2 * h2 + (q & 1), w = 2 * w2 + (q >> 1);
+          if (h >= p.mH || w >= p.mW) continue;    // zero padding of an odd grid: no source token
+          off = ((bd * p.mH + h) * p.mW + w) * static_cast<long long>(p.C) + c;
+        } else {
+          off = row * static_cast<long long>(p.C) + (i * 32 + lane) * 4;
+        }
+        if (p.dres) {
+          const float4 o = *reinterpret_cast<const float4*>(p.dres + off);
+          d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w;
+        }
+        *reinterpret_cast<float4*>(p.dx + off) = d;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (!slot[i]) continue;
+    const int c = (i * 32 + lane) * 4;
+    atomicAdd(&lnb_red[c + 0], dg[i].x); atomicAdd(&lnb_red[c + 1], dg[i].y);
+    atomicAdd(&lnb_red[c + 2], dg[i].z); atomicAdd(&lnb_red[c + 3], dg[i].w);
+    atomicAdd(&lnb_red[Cn + c + 0], db[i].x); atomicAdd(&lnb_red[Cn + c + 1], db[i].y);
+    atomicAdd(&lnb_red[Cn + c + 2], db[i].z); atomicAdd(&lnb_red[Cn + c + 3], db[i].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cn; i += blockDim.x) {
+    if (p.dgamma) atomicAdd(p.dgamma + i, lnb_red[i]);
+    if (p.dbeta) atomicAdd(p.dbeta + i, lnb_red[Cn + i]);
+  }
+}
+
+template <int MODE, int NV>
+static void launch_ln_bwd_nv(const LnBwdParams& p, int Cn, cudaStream_t st) {
+  long long blocks = (p.M + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  long long rpb = (p.M + blocks - 1) / blocks;
+  rpb = (rpb + 255) / 256 * 256;
+  blocks = (p.M + rpb - 1) / rpb;
+  ln_bwd_kernel<MODE, NV><<<static_cast<unsigned>(blocks), 256, 2 * Cn * sizeof(float), st>>>(p, rpb);
+}
+
+template <int MODE>
+static int launch_ln_bwd(const LnBwdParams& p, int Cn, cudaStream_t st) {
+  switch ((Cn + 127) / 128) {
+    case 1: launch_ln_bwd_nv<MODE, 1>(p, Cn, st); break;
+    case 2: launch_ln_bwd_nv<MODE, 2>(p, Cn, st); break;
+    case 3: launch_ln_bwd_nv<MODE, 3>(p, Cn, st); break;
+    case 4: launch_ln_bwd_nv<MODE, 4>(p, Cn, st); break;
+    case 6: launch_ln_bwd_nv<MODE, 6>(p, Cn, st); break;
+    case 8: launch_ln_bwd_nv<MODE, 8>(p, Cn, st); break;
+    case 12: launch_ln_bwd_nv<MODE, 12>(p, Cn, st); break;
+    case 16: launch_ln_bwd_nv<MODE, 16>(p, Cn, st); break;
+    default:
+      set_last_error("layernorm backward: normalised width %d not supported", Cn);
+      return LAVT_ERR_SHAPE;
+  }
+  LAVT_LAUNCH_CHECK("ln_bwd_kernel");
+  return LAVT_OK;
+}
+
+int ln_bwd_dispatch(int mode, const LnBwdParams& p, cudaStream_t st) {
+  LAVT_REQUIRE(p.M > 0 && p.dy && p.dx && p.x && p.gamma, "layernorm backward: missing tensor");
+  LAVT_REQUIRE(p.ldx % 4 == 0 && p.C % 4 == 0, "layernorm backward: pitch / channels must be multiples of 4");
+  const int Cn = (mode == MODE_MERGE) ? 4 * p.C : p.C;
+  if (mode == MODE_IDENTITY) return launch_ln_bwd<MODE_IDENTITY>(p, Cn, st);
+  if (mode == MODE_WINDOW) return launch_ln_bwd<MODE_WINDOW>(p, Cn, st);
+  if (mode == MODE_MERGE) return launch_ln_bwd<MODE_MERGE>(p, Cn, st);
+  set_last_error("layernorm backward: bad mode %d", mode);
+  return LAVT_ERR_SHAPE;
+}
+
+}  // namespace lavt

@@ -226,4 +226,113 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
   return nchw_to_nhwc_bf16_dispatch(in, MB(out_bf16), n_img, P, C, S(stream));
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * backward pass (training step)
+ * ------------------------------------------------------------------------------------------------ */
+static void splitk_plan(int M, int N, int K, int* ksplit, int* kbs) {
+  const long long tiles = 1LL * ((M + 127) / 128) * ((N + 127) / 128);
+  const int num_kb = (K + 63) / 64;
+  long long want = (2 * 148 + tiles - 1) / tiles;      // ~two waves of work items
+  if (want > num_kb) want = num_kb;
+  if (want > 128) want = 128;
+  if (want < 1) want = 1;
+  *kbs = static_cast<int>((num_kb + want - 1) / want);
+  *ksplit = (num_kb + *kbs - 1) / *kbs;
+}
+
+int64_t lavt_gemm_splitk_workspace_floats(int32_t M, int32_t N, int32_t K) {
+  int ks, kbs;
+  splitk_plan(M, N, K, &ks, &kbs);
+  return 1LL * ks * M * N;
+}
+
+int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t b_koff,
+                          float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream) {
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  int ks, kbs;
+  splitk_plan(M, N, K, &ks, &kbs);
+  LAVT_REQUIRE(workspace && workspace_floats >= 1LL * ks * M * N, "split-K gemm: workspace too small (%lld < %lld floats)",
+               static_cast<long long>(workspace_floats), 1LL * ks * M * N);
+  LAVT_REQUIRE(dst != nullptr && ldd >= N, "split-K gemm: bad destination");
+  p.out_f32 = workspace;
+  p.ldo = N;
+  p.rowmap = ROWMAP_IDENTITY;
+  p.ksplit = ks;
+  p.kbs = kbs;
+  p.split_stride = 1LL * M * N;
+  p.b_koff = b_koff;
+  int rc = gemm_dispatch(A, lda, Bt, ldb, p, S(stream));
+  if (rc) return rc;
+  return splitk_reduce_dispatch(workspace, ks, 1LL * M * N, N, dst, ldd, accumulate, S(stream));
+}
+
+int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream) {
+  return transpose_bf16_dispatch(CB(in), ldi, MB(out), ldo, M, N, S(stream));
+}
+
+int lavt_colsum_accumulate(const void* x, int32_t is_bf16, int64_t ldx, int64_t M, int32_t N, float* dst, void* stream) {
+  return colsum_dispatch(x, is_bf16, ldx, M, N, dst, S(stream));
+}
+
+int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream) {
+  WinGeom g;
+  if (geom) {
+    std::memcpy(&g, geom, sizeof(g));
+    LAVT_REQUIRE(M == 1LL * g.B * g.nwd * g.nwh * g.nww * g.N, "cast rows: M does not match the window geometry");
+  }
+  return cast_rows_dispatch(x, ldx, MB(out_bf16), M, C, geom ? &g : nullptr, S(stream));
+}
+
+int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream) {
+  return gelu_fwd_dispatch(CB(x_bf16), MB(y_bf16), count, S(stream));
+}
+int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_t count, void* stream) {
+  return gelu_bwd_dispatch(CB(dy_bf16), CB(x_bf16), MB(dx_bf16), count, S(stream));
+}
+
+int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, const float* gamma, float eps,
+                            const float* dres, float* dx, float* dgamma, float* dbeta, void* stream) {
+  LnBwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = ldx; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.M = M; p.C = C; p.eps = eps;
+  return ln_bwd_dispatch(MODE_IDENTITY, p, S(stream));
+}
+
+int lavt_layernorm_window_gather_bwd(const float* x, int32_t C, const lavt_win_geom_t* geom, const void* dy_bf16, const float* gamma,
+                                     float eps, const float* dres, float* dx, float* dgamma, float* dbeta, void* stream) {
+  LAVT_REQUIRE(geom != nullptr, "window gather backward: geometry is NULL");
+  LnBwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.M = 1LL * p.win.B * p.win.nwd * p.win.nwh * p.win.nww * p.win.N; p.C = C; p.eps = eps;
+  return ln_bwd_dispatch(MODE_WINDOW, p, S(stream));
+}
+
+int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, const void* dy_bf16,
+                                   const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* stream) {
+  LnBwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = nullptr; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.M = 1LL * B * D * ((H + 1) / 2) * ((W + 1) / 2); p.C = C; p.eps = eps;
+  p.mB = B; p.mD = D; p.mH = H; p.mW = W;
+  return ln_bwd_dispatch(MODE_MERGE, p, S(stream));
+}
+
+int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
+                              const lavt_win_geom_t* geom, void* dqkv, float* dtable_t, void* stream) {
+  LAVT_REQUIRE(geom != nullptr, "attention backward: geometry is NULL");
+  AttnBwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.qkv = CB(qkv); p.out = CB(out); p.dout = CB(dout); p.table_t = table_t; p.dqkv = MB(dqkv); p.dtable_t = dtable_t;
+  p.C = nH * 32; p.nH = nH; p.L = L;
+  p.qscale = 0.17677669529663687f;      // 32^-0.5
+  LAVT_REQUIRE(L == (2 * p.win.Wd - 1) * (2 * p.win.Wh - 1) * (2 * p.win.Ww - 1), "attention backward: table length %d does not match the window", L);
+  return window_attn_bwd_dispatch(p, S(stream));
+}
+
 }  // extern "C"

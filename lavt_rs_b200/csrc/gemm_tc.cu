@@ -145,6 +145,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int total_tiles = m_tiles * n_tiles;
   const int conv_cpb = (p.cCin + GEMM_BK - 1) / GEMM_BK;
   const int num_kb = (p.rowmap == ROWMAP_CONV) ? p.taps * conv_cpb : (p.K + GEMM_BK - 1) / GEMM_BK;
+  // split-K: work item = (tile, split); every split owns at least one k-block (host guarantees (ksplit - 1) * kbs < num_kb)
+  const int nsplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int kbs = p.ksplit > 1 ? p.kbs : num_kb;
+  const int total_work = total_tiles * nsplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -183,7 +187,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool conv = (p.rowmap == ROWMAP_CONV);
       const int cpb = conv ? conv_cpb : 1;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int ks = work / total_tiles, tile = work - ks * total_tiles;
+        const int kb_lo = ks * kbs, kb_hi = min(num_kb, kb_lo + kbs);
         const int mt = tile / n_tiles;
         const int n0 = (tile - mt * n_tiles) * GEMM_BN;
         int img = 0, h0 = 0, w0 = 0, d0 = 0;
@@ -198,11 +204,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           h0 = th * p.cTH;
           w0 = tw * p.cTW;
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (kb == 0) GEMM_TRACE(5, it / num_kb);
+          if (kb == kb_lo) GEMM_TRACE(5, it / num_kb);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
@@ -222,7 +228,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], bk0, n0);
+          tma_load_2d(sb, &tmB, &full_bar[s], bk0 + p.b_koff, n0);
         }
       }
     }
@@ -231,19 +237,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
+        const int ks = work / total_tiles;
+        const int kb_lo = ks * kbs, kb_hi = min(num_kb, kb_lo + kbs);
         const int acc = lt % ACC;
         const uint32_t use = static_cast<uint32_t>(lt / ACC);
         mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         GEMM_TRACE(0, lt);
         const uint32_t tmem_d = tmem_base + acc * GEMM_BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (kb == 0) GEMM_TRACE(1, lt);
+          if (kb == kb_lo) GEMM_TRACE(1, lt);
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
           const uint64_t da = make_kmajor_sw128_desc(sa);
@@ -251,7 +259,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
           }
           umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
         }
@@ -269,8 +277,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float* s_bias = s_scale + GEMM_BN;
     const int r = ew * 32 + lane;              // row inside the tile
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
       if ((lt % EPI_WGS) != wg) continue;
+      const int ks = work / total_tiles, tile = work - ks * total_tiles;
       const int acc = lt % ACC;
       const uint32_t use = static_cast<uint32_t>(lt / ACC);
       const int mt = tile / n_tiles;
@@ -311,7 +320,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool live = (orow >= 0);
       const __nv_bfloat16* mul_row = (p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
       const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
-      float* of_row = (p.out_f32 && live) ? p.out_f32 + orow * p.ldo + n0 : nullptr;
+      float* of_row = (p.out_f32 && live) ? p.out_f32 + ks * p.split_stride + orow * p.ldo + n0 : nullptr;
       __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
 
       const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
@@ -439,7 +448,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const long long total = 1LL * m_tiles * ((p.N + BN - 1) / BN);
+  const long long total = 1LL * m_tiles * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   LAVT_REQUIRE(total < (1LL << 30), "gemm: too many tiles (%lld)", total);
   const long long slots = 1LL * sm_count() * L::MIN_CTAS;
   const int grid = static_cast<int>(total < slots ? total : slots);

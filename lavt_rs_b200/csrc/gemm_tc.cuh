@@ -30,6 +30,13 @@ struct GemmParams {
   int cTilesH, cTilesW;      // tiles per image
   int taps;                  // 9 (3x3), 27 (3x3x3) or 1
   int cD;                    // frames per clip for the 3-D conv (A is (C, W, H, D, Nclip)); 0 / 1 = 2-D
+  // ---- split-K (weight gradients: few output tiles, very long K) ----
+  int ksplit;                // 0 / 1 = off; s > 1: work item = (tile, split); split ks accumulates k-blocks [ks*kbs, (ks+1)*kbs)
+  int kbs;                   // k-blocks per split
+  long long split_stride;    // out_f32 of split ks = out_f32 + ks * split_stride (partials, reduced by splitk_reduce)
+  int b_koff;                // added to the K coordinate of the B operand (conv weight gradient: tap offset in the padded pixel axis)
 };
+int splitk_reduce_dispatch(const float* partials, int splits, long long count, int ncols, float* dst, long long ldd, int accumulate,
+                           cudaStream_t st);
 
 }  // namespace lavt

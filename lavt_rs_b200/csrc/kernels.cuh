@@ -43,6 +43,43 @@ int attn_impl_setting(int set);   // set < 0: query only; returns the previous v
 bool window_attn_tc_supported(const AttnParams& p);
 int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st);
 
+// ---- backward pass (training step) ----
+struct AttnBwdParams {
+  const __nv_bfloat16* qkv;    // [rows, 3C] saved by the forward (q pre-scaled by hd^-0.5 * log2 e)
+  const __nv_bfloat16* out;    // [rows, C]  forward output O
+  const __nv_bfloat16* dout;   // [rows, C]  gradient of O
+  const float* table_t;        // [nH, L]
+  __nv_bfloat16* dqkv;         // [rows, 3C] gradient of the UNSCALED qkv projection output
+  float* dtable_t;             // [nH, L] accumulated (+=), or nullptr
+  int C, nH, L;
+  float qscale;                // hd^-0.5
+  WinGeom win;
+};
+int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st);
+
+struct LnBwdParams {
+  const float* x;              // LN input rows (fp32, pitch ldx), gathered like the forward
+  long long ldx;
+  const __nv_bfloat16* dy;     // [M, Cn] gradient of the LN output, in OUTPUT-row order
+  const float* gamma;          // [Cn]
+  const float* dres;           // [tokens, C] gradient already flowing on the residual stream (added), or nullptr
+  float* dx;                   // [tokens, C] result (may alias dres)
+  float* dgamma;               // [Cn] accumulated (+=)
+  float* dbeta;                // [Cn] accumulated (+=)
+  long long M;                 // output rows
+  int C;
+  float eps;
+  WinGeom win;                 // MODE_WINDOW
+  int mB, mD, mH, mW;          // MODE_MERGE
+};
+int ln_bwd_dispatch(int mode, const LnBwdParams& p, cudaStream_t st);
+int transpose_bf16_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, long long M, int N,
+                            cudaStream_t st);
+int colsum_dispatch(const void* x, int is_bf16, long long ldx, long long M, int N, float* dst, cudaStream_t st);
+int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, cudaStream_t st);
+int gelu_fwd_dispatch(const __nv_bfloat16* x, __nv_bfloat16* y, long long count, cudaStream_t st);
+int gelu_bwd_dispatch(const __nv_bfloat16* dy, const __nv_bfloat16* x, __nv_bfloat16* dx, long long count, cudaStream_t st);
+
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);
 int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
