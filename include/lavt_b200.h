@@ -177,8 +177,8 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
  * ================================================================================================ */
 
 /* dst[M, ldd] (+)= A[M,K] x Bt[N,K]^T with the K axis split over work items (weight gradients: dW = dY^T X has few output
- * tiles and K = all tokens).  A = dY^T [out, tokens], Bt = X^T [in, tokens] (lavt_transpose_bf16).  b_koff shifts the K
- * coordinate of Bt (taps of a convolution weight gradient over a zero-padded pixel axis).  Adjoint of every nn.Linear /
+ * tiles and K = all tokens).  A = dY^T [out, tokens], Bt = X^T [in, tokens] (lavt_transpose_bf16).  b_koff (a multiple of 8)
+ * shifts the K coordinate of Bt (taps of a convolution weight gradient over a zero-padded pixel axis).  Adjoint of every nn.Linear /
  * Conv1d(k=1) / Conv2d weight on the path w.r.t. its weight. */
 int64_t lavt_gemm_splitk_workspace_floats(int32_t M, int32_t N, int32_t K);
 int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t b_koff,
@@ -195,7 +195,7 @@ int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream)
 int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_t count, void* stream);
 /* LayerNorm backward, adjoints of lavt_layernorm_rows / _window_gather / lavt_patch_merge_layernorm:
  * dx[token] = dres[token] + LN'(dy[row]) (dres may be NULL or alias dx); dgamma / dbeta accumulate. */
-int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, const float* gamma, float eps,
+int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, int64_t lddy, const float* gamma, float eps,
                             const float* dres, float* dx, float* dgamma, float* dbeta, void* stream);
 int lavt_layernorm_window_gather_bwd(const float* x, int32_t C, const lavt_win_geom_t* geom, const void* dy_bf16, const float* gamma,
                                      float eps, const float* dres, float* dx, float* dgamma, float* dbeta, void* stream);
@@ -206,6 +206,65 @@ int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t
  * Windows of up to ~400 tokens (shared-memory resident). */
 int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
                               const lavt_win_geom_t* geom, void* dqkv, float* dtable_t, void* stream);
+
+/* ---- PWAM + LanguageGate backward (adjoints of lavt_pwam_* above; reference lib/video_swin_transformer.py:919-1009, 519-525) ---- */
+/* Per pixel: recompute q^ = IN(q_pre) and the masked word softmax P, dP = dO v^T, dS = P (dP - sum P dP).  Outputs:
+ * dqhat fp32 [B,n,C] = C^-0.5 dS k; qs bf16 [B*n, C] = C^-0.5 q^; p_bd / ds_bd bf16 [B*n, B*heads*NlPad]: row (b, pixel) carries
+ * P / dS of fusion head h in columns (b*heads + h)*NlPad + j and zeros elsewhere, so that dv = p_bd^T dO and dk = ds_bd^T qs
+ * are ordinary weight-gradient GEMMs (lavt_gemm_bf16_splitk); sums fp32 [B,2,C] += (sum_n dqhat, sum_n dqhat * q^). */
+int lavt_pwam_attend_bwd(const float* qpre, const float* stats, const float* k, const float* v, const float* mask, const void* do_bf16,
+                         float* dqhat, void* qs_bf16, void* p_bd, void* ds_bd, float* sums, int32_t B, int64_t n, int32_t C, int32_t Nl,
+                         int32_t NlPad, int32_t heads, void* stream);
+/* a2 = vis * IN(lang_pre), vis = GELU(vis_pre): dvispre bf16 = da2 * IN(lang_pre) * GELU'(vis_pre); sums [B,2,C] += the
+ * InstanceNorm reductions of g = da2 * vis (sum g, sum g * lang) */
+int lavt_pwam_mul_norm_bwd(const void* da2, const void* vis, const void* vispre, const float* langpre, const float* stats, void* dvispre,
+                           float* sums, int32_t B, int64_t n, int32_t C, void* stream);
+/* InstanceNorm backward from the reductions: out bf16 = rstd * (g - S1/n - x^ S2/n); g = g_f32, or ga * gb (bf16) if g_f32 is NULL */
+int lavt_instnorm_bwd(const float* g_f32, const void* ga_bf16, const void* gb_bf16, const float* xpre, const float* stats, const float* sums,
+                      void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream);
+/* Adjoint of lavt_pwam_kv: dkbuf / dvbuf fp32 [B*heads*NlPad, C] (the GEMM outputs above) -> dwk, dbk, dwv, dbv, dl (all +=) */
+int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv, float* dwk,
+                     float* dbk, float* dwv, float* dbv, float* dl, int32_t B, int32_t Nl, int32_t NlPad, int32_t Lin, int32_t C,
+                     int32_t heads, void* stream);
+/* Elementwise pieces of the LanguageGate x' = x + tanh(relu(r G0^T) G2^T) * r and of GELU with fp32 sides (count % 8 == 0):
+ *   mode 0: out_f32 = f + tanh(a) * b                             (forward: a = gate pre-activation, b = r, f = x)
+ *   mode 1: out_bf16 = f * b * (1 - tanh(a)^2); out_f32 = f2 + f * tanh(a)   (f = dx', f2 = gradient of r so far or NULL)
+ *   mode 2: out_bf16 = a * [b > 0]                                (ReLU backward: a = dg1, b = g1)
+ *   mode 3: out_bf16 = GELU(a), out_f32 = the same                (a = bf16 pre-activation)
+ *   mode 4: out_bf16 = f * GELU'(a)                               (f = fp32 gradient) */
+int lavt_gate_elementwise(int32_t mode, const void* a_bf16, const void* b_bf16, const float* f, const float* f2, void* out_bf16,
+                          float* out_f32, int64_t count, void* stream);
+
+/* ---- SimpleDecoding in training mode + loss (lib/mask_predictor.py:56-99 with BatchNorm2d batch statistics; losses.py:7-11) ---- */
+/* t bf16 [npix, C] = relu((z - mean) * rstd * gamma + beta); z fp32 conv output, stats fp32 [2, C] = (mean, rstd) over all pixels
+ * (lavt_instnorm_stats with B = 1) */
+int lavt_bn_relu_apply(const float* z, const float* stats, const float* gamma, const float* beta, void* t_bf16, int64_t npix, int32_t C,
+                       void* stream);
+/* BatchNorm + ReLU backward, two phases around the (optionally cross-GPU) reduction: sums fp32 [2, C] += (sum dy, sum dy * z^) with
+ * dy = dt * [t > 0] (these are d beta, d gamma); then dz bf16 = gamma * rstd * (dy - sums[0]/n_stat - z^ sums[1]/n_stat) */
+int lavt_bn_relu_bwd_reduce(const void* dt_bf16, const void* t_bf16, const float* z, const float* stats, float* sums, int64_t npix, int32_t C,
+                            void* stream);
+int lavt_bn_relu_bwd_apply(const void* dt_bf16, const void* t_bf16, const float* z, const float* stats, const float* gamma, const float* sums,
+                           void* dz_bf16, int64_t npix, int64_t n_stat, int32_t C, void* stream);
+/* NHWC bf16 [n,H,W,C] (pixel pitch ldi) -> [C, ldo] with column (img*(H+2) + h+1)*Wp + w+1 - dshift (Wp >= W+2, a multiple of 8;
+ * dshift in {-1,0,1}); the caller zeroes the buffer (borders).  In this layout tap (ky,kx) of a 3x3 conv is the column offset
+ * (ky-1)*Wp + (kx-1): the conv weight gradient is nine lavt_gemm_bf16_splitk calls, A = dz^T (dshift 0), Bt = the copy of x^T
+ * written with dshift = kx-1, b_koff = (ky-1)*Wp (TMA needs 16-byte aligned inner coordinates, hence the three shifted copies). */
+int lavt_nhwc_pad_transpose(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                            int32_t Wp, int32_t dshift, void* stream);
+/* adjoint of the upsample half of lavt_upsample_concat: dprev bf16 [n,ph,pw,C1] from dcat bf16 [n,H,W,Ct] (channels 0..C1) */
+int lavt_upsample_concat_bwd(const void* dcat_bf16, int32_t Ct, void* dprev_bf16, int32_t ph, int32_t pw, int32_t C1, int32_t n_img, int32_t H,
+                             int32_t W, void* stream);
+/* adjoint of lavt_conv1x1_logits: dy bf16 [npix, C]; dw fp32 [2, C] and db fp32 [2] accumulate */
+int lavt_conv1x1_logits_bwd(const float* dlogits, const void* y_bf16, const float* w, void* dy_bf16, float* dw, float* db, int64_t npix,
+                            int32_t C, void* stream);
+/* adjoint of lavt_upsample_logits: dout fp32 (n,2,H,W) -> din fp32 (n,h,w,2) */
+int lavt_upsample_logits_bwd(const float* dout, float* din, int32_t n_img, int32_t h, int32_t w, int32_t H, int32_t W, void* stream);
+/* weighted 2-class cross-entropy over logits fp32 (n,2,H,W) and target int64 (n,H,W) (losses.py:7-11: weights 0.9 / 1.1).
+ * phase 0: acc[0] += sum w[t] * nll, acc[1] += sum w[t] (loss = acc[0] / acc[1]);
+ * phase 1: dlogits = gscale * w[t] * (softmax - onehot) / acc[1] */
+int lavt_cross_entropy(const float* logits, const int64_t* target, float w0, float w1, float* acc, float* dlogits, float gscale, int32_t n_img,
+                       int32_t H, int32_t W, int32_t phase, void* stream);
 
 #ifdef __cplusplus
 }

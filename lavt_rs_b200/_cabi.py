@@ -103,10 +103,23 @@ SIGNATURES = {
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
     "lavt_gelu_fwd": [_vp, _vp, _i64, _vp],
     "lavt_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
-    "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
+    "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
     "lavt_layernorm_window_gather_bwd": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
     "lavt_patch_merge_layernorm_bwd": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp],
     "lavt_window_attention_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _WG, _vp, _vp, _vp],
+    "lavt_pwam_attend_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
+    "lavt_pwam_mul_norm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "lavt_instnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "lavt_pwam_kv_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_gate_elementwise": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "lavt_bn_relu_apply": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "lavt_bn_relu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "lavt_bn_relu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
+    "lavt_nhwc_pad_transpose": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_upsample_concat_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_conv1x1_logits_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "lavt_upsample_logits_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_cross_entropy": [_vp, _vp, _f32, _f32, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
            "lavt_gemm_splitk_workspace_floats",
@@ -545,7 +558,8 @@ def layernorm_rows_bwd(x, dy, gamma, dx, dgamma, dbeta, *, dres=None, eps: float
     """x fp32 [M, C] (LN input), dy bf16 [M, C]; dx fp32 [M, C] = (dres or 0) + LN'(dy); dgamma / dbeta fp32 [C] accumulate."""
     _req(x, torch.float32, "x")
     M, Cn = x.shape
-    check(lib().lavt_layernorm_rows_bwd(x.data_ptr(), x.stride(0), M, Cn, _c(dy, torch.bfloat16, "dy").data_ptr(),
+    _req(dy, torch.bfloat16, "dy")
+    check(lib().lavt_layernorm_rows_bwd(x.data_ptr(), x.stride(0), M, Cn, dy.data_ptr(), dy.stride(0),
                                         _c(gamma, torch.float32, "gamma").data_ptr(), eps, ptr(dres), _c(dx, torch.float32, "dx").data_ptr(),
                                         _c(dgamma, torch.float32, "dgamma").data_ptr(), _c(dbeta, torch.float32, "dbeta").data_ptr(),
                                         stream_ptr()), "lavt_layernorm_rows_bwd")
@@ -582,3 +596,114 @@ def window_attention_bwd(qkv, out, dout, table_t, geom: WinGeom, dqkv, dtable_t)
                                           ptr(dtable_t), stream_ptr()), "lavt_window_attention_bwd")
     rows = geom.rows()
     TIMER.end(t0, "window_attn_bwd_kernel", 12.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 8, f"rows{rows} N{geom.N} nH{nH}")
+
+
+def pwam_attend_bwd(qpre, stats, k, v, mask, do, dqhat, qs, p_bd, ds_bd, sums, heads: int, nl_pad: int) -> None:
+    B, n, Cn = qpre.shape
+    Nl = k.shape[1]
+    if tuple(p_bd.shape) != (B * n, B * heads * nl_pad) or tuple(ds_bd.shape) != tuple(p_bd.shape):
+        raise LavtError("pwam_attend_bwd: block-diagonal buffers have the wrong shape")
+    check(lib().lavt_pwam_attend_bwd(_c(qpre, torch.float32, "qpre").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                     _c(k, torch.float32, "k").data_ptr(), _c(v, torch.float32, "v").data_ptr(),
+                                     _c(mask, torch.float32, "mask").data_ptr(), _c(do, torch.bfloat16, "do").data_ptr(),
+                                     _c(dqhat, torch.float32, "dqhat").data_ptr(), _c(qs, torch.bfloat16, "qs").data_ptr(),
+                                     _c(p_bd, torch.bfloat16, "p_bd").data_ptr(), _c(ds_bd, torch.bfloat16, "ds_bd").data_ptr(),
+                                     _c(sums, torch.float32, "sums").data_ptr(), B, n, Cn, Nl, nl_pad, heads, stream_ptr()),
+          "lavt_pwam_attend_bwd")
+
+
+def pwam_mul_norm_bwd(da2, vis, vispre, langpre, stats, dvispre, sums) -> None:
+    B, n, Cn = langpre.shape
+    check(lib().lavt_pwam_mul_norm_bwd(_c(da2, torch.bfloat16, "da2").data_ptr(), _c(vis, torch.bfloat16, "vis").data_ptr(),
+                                       _c(vispre, torch.bfloat16, "vispre").data_ptr(), _c(langpre, torch.float32, "langpre").data_ptr(),
+                                       _c(stats, torch.float32, "stats").data_ptr(), _c(dvispre, torch.bfloat16, "dvispre").data_ptr(),
+                                       _c(sums, torch.float32, "sums").data_ptr(), B, n, Cn, stream_ptr()), "lavt_pwam_mul_norm_bwd")
+
+
+def instnorm_bwd(xpre, stats, sums, out, *, g_f32=None, ga=None, gb=None) -> None:
+    B, n, Cn = xpre.shape
+    check(lib().lavt_instnorm_bwd(ptr(g_f32), ptr(ga), ptr(gb), _c(xpre, torch.float32, "xpre").data_ptr(),
+                                  _c(stats, torch.float32, "stats").data_ptr(), _c(sums, torch.float32, "sums").data_ptr(),
+                                  _c(out, torch.bfloat16, "out").data_ptr(), B, n, Cn, stream_ptr()), "lavt_instnorm_bwd")
+
+
+def pwam_kv_bwd(dkbuf, dvbuf, mask, l, wk, wv, dwk, dbk, dwv, dbv, dl, heads: int, nl_pad: int) -> None:
+    B, Lin, Nl = l.shape
+    Cn = wk.shape[0]
+    check(lib().lavt_pwam_kv_bwd(_c(dkbuf, torch.float32, "dkbuf").data_ptr(), _c(dvbuf, torch.float32, "dvbuf").data_ptr(),
+                                 _c(mask, torch.float32, "mask").data_ptr(), _c(l, torch.float32, "l").data_ptr(),
+                                 _c(wk, torch.float32, "wk").data_ptr(), _c(wv, torch.float32, "wv").data_ptr(), ptr(dwk), ptr(dbk),
+                                 ptr(dwv), ptr(dbv), ptr(dl), B, Nl, nl_pad, Lin, Cn, heads, stream_ptr()), "lavt_pwam_kv_bwd")
+
+
+def gate_elementwise(mode: int, a, b=None, f=None, f2=None, out_bf16=None, out_f32=None) -> None:
+    check(lib().lavt_gate_elementwise(mode, _c(a, torch.bfloat16, "a").data_ptr(), ptr(b), ptr(f), ptr(f2), ptr(out_bf16), ptr(out_f32),
+                                      a.numel(), stream_ptr()), "lavt_gate_elementwise")
+
+
+# ---- SimpleDecoding (training mode), final upsample and loss ----
+def bn_relu_apply(z, stats, gamma, beta, t) -> None:
+    """z fp32 [npix, C]; stats fp32 [2, C] (mean, rstd); t bf16 [npix, C]."""
+    npix, Cn = z.shape
+    check(lib().lavt_bn_relu_apply(_c(z, torch.float32, "z").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                   _c(gamma, torch.float32, "gamma").data_ptr(), _c(beta, torch.float32, "beta").data_ptr(),
+                                   _c(t, torch.bfloat16, "t").data_ptr(), npix, Cn, stream_ptr()), "lavt_bn_relu_apply")
+
+
+def bn_relu_bwd_reduce(dt, t, z, stats, sums) -> None:
+    npix, Cn = z.shape
+    check(lib().lavt_bn_relu_bwd_reduce(_c(dt, torch.bfloat16, "dt").data_ptr(), _c(t, torch.bfloat16, "t").data_ptr(),
+                                        _c(z, torch.float32, "z").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                        _c(sums, torch.float32, "sums").data_ptr(), npix, Cn, stream_ptr()), "lavt_bn_relu_bwd_reduce")
+
+
+def bn_relu_bwd_apply(dt, t, z, stats, gamma, sums, dz, n_stat: int) -> None:
+    npix, Cn = z.shape
+    check(lib().lavt_bn_relu_bwd_apply(_c(dt, torch.bfloat16, "dt").data_ptr(), _c(t, torch.bfloat16, "t").data_ptr(),
+                                       _c(z, torch.float32, "z").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                       _c(gamma, torch.float32, "gamma").data_ptr(), _c(sums, torch.float32, "sums").data_ptr(),
+                                       _c(dz, torch.bfloat16, "dz").data_ptr(), npix, n_stat, Cn, stream_ptr()), "lavt_bn_relu_bwd_apply")
+
+
+def nhwc_pad_transpose(x_nhwc, out, wp: int, dshift: int = 0) -> None:
+    """x bf16 [n,H,W,C] (last dim contiguous, pixel pitch x.stride(2)) -> out bf16 [C, >= n*(H+2)*wp], pre-zeroed by the caller;
+    pixel (img,h,w) lands in column (img*(H+2) + h+1)*wp + w+1 - dshift."""
+    _req(x_nhwc, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    n, H, W, Cn = x_nhwc.shape
+    check(lib().lavt_nhwc_pad_transpose(x_nhwc.data_ptr(), x_nhwc.stride(2), out.data_ptr(), out.stride(0),
+                                        n, H, W, Cn, wp, dshift, stream_ptr()), "lavt_nhwc_pad_transpose")
+
+
+def upsample_concat_bwd(dcat, dprev) -> None:
+    """dcat bf16 [n,H,W,Ct] -> dprev bf16 [n,ph,pw,C1] (gradient of the upsampled first C1 channels)."""
+    n, H, W, Ct = dcat.shape
+    n2, ph, pw, C1 = dprev.shape
+    check(lib().lavt_upsample_concat_bwd(_c(dcat, torch.bfloat16, "dcat").data_ptr(), Ct, _c(dprev, torch.bfloat16, "dprev").data_ptr(),
+                                         ph, pw, C1, n, H, W, stream_ptr()), "lavt_upsample_concat_bwd")
+
+
+def conv1x1_logits_bwd(dlogits, y, w, dy, dw, db) -> None:
+    npix, Cn = y.shape
+    check(lib().lavt_conv1x1_logits_bwd(_c(dlogits, torch.float32, "dlogits").data_ptr(), _c(y, torch.bfloat16, "y").data_ptr(),
+                                        _c(w, torch.float32, "w").data_ptr(), _c(dy, torch.bfloat16, "dy").data_ptr(),
+                                        _c(dw, torch.float32, "dw").data_ptr(), _c(db, torch.float32, "db").data_ptr(), npix, Cn,
+                                        stream_ptr()), "lavt_conv1x1_logits_bwd")
+
+
+def upsample_logits_bwd(dout, din) -> None:
+    """dout fp32 [n,2,H,W] -> din fp32 [n,h,w,2]."""
+    n, _, H, W = dout.shape
+    n2, h, w, _ = din.shape
+    check(lib().lavt_upsample_logits_bwd(_c(dout, torch.float32, "dout").data_ptr(), _c(din, torch.float32, "din").data_ptr(), n, h, w, H, W,
+                                         stream_ptr()), "lavt_upsample_logits_bwd")
+
+
+def cross_entropy(logits, target, acc, dlogits=None, *, w0: float = 0.9, w1: float = 1.1, gscale: float = 1.0, phase: int = 0) -> None:
+    """logits fp32 [n,2,H,W]; target int64 [n,H,W]; acc fp32 [2] (sum w*nll, sum w)."""
+    n, two, H, W = logits.shape
+    if target.dtype != torch.int64 or not target.is_cuda or not target.is_contiguous():
+        raise LavtError("cross_entropy: target must be a contiguous CUDA int64 tensor")
+    check(lib().lavt_cross_entropy(_c(logits, torch.float32, "logits").data_ptr(), target.data_ptr(), w0, w1,
+                                   _c(acc, torch.float32, "acc").data_ptr(), ptr(dlogits), gscale, n, H, W, phase, stream_ptr()),
+          "lavt_cross_entropy")

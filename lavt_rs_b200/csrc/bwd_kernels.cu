@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, const 
       // xhat in place; gy = dy * gamma
       float4 gy[NV];
       float s1 = 0.f, s2 = 0.f;
-      const uint2* dy2 = reinterpret_cast<const uint2*>(p.dy + m * Cn);
+      const uint2* dy2 = reinterpret_cast<const uint2*>(p.dy + m * p.lddy);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (!slot[i]) { gy[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
@@ -363,7 +363,7 @@ static int launch_ln_bwd(const LnBwdParams& p, int Cn, cudaStream_t st) {
 
 int ln_bwd_dispatch(int mode, const LnBwdParams& p, cudaStream_t st) {
   LAVT_REQUIRE(p.M > 0 && p.dy && p.dx && p.x && p.gamma, "layernorm backward: missing tensor");
-  LAVT_REQUIRE(p.ldx % 4 == 0 && p.C % 4 == 0, "layernorm backward: pitch / channels must be multiples of 4");
+  LAVT_REQUIRE(p.ldx % 4 == 0 && p.C % 4 == 0 && p.lddy % 4 == 0, "layernorm backward: pitch / channels must be multiples of 4");
   const int Cn = (mode == MODE_MERGE) ? 4 * p.C : p.C;
   if (mode == MODE_IDENTITY) return launch_ln_bwd<MODE_IDENTITY>(p, Cn, st);
   if (mode == MODE_WINDOW) return launch_ln_bwd<MODE_WINDOW>(p, Cn, st);

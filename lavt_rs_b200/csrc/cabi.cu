@@ -256,6 +256,7 @@ int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ld
   LAVT_REQUIRE(workspace && workspace_floats >= 1LL * ks * M * N, "split-K gemm: workspace too small (%lld < %lld floats)",
                static_cast<long long>(workspace_floats), 1LL * ks * M * N);
   LAVT_REQUIRE(dst != nullptr && ldd >= N, "split-K gemm: bad destination");
+  LAVT_REQUIRE(b_koff % 8 == 0, "split-K gemm: b_koff=%d must be a multiple of 8 elements (TMA needs a 16-byte aligned inner coordinate)", b_koff);
   p.out_f32 = workspace;
   p.ldo = N;
   p.rowmap = ROWMAP_IDENTITY;
@@ -292,11 +293,11 @@ int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_
   return gelu_bwd_dispatch(CB(dy_bf16), CB(x_bf16), MB(dx_bf16), count, S(stream));
 }
 
-int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, const float* gamma, float eps,
+int lavt_layernorm_rows_bwd(const float* x, int64_t ldx, int64_t M, int32_t C, const void* dy_bf16, int64_t lddy, const float* gamma, float eps,
                             const float* dres, float* dx, float* dgamma, float* dbeta, void* stream) {
   LnBwdParams p;
   std::memset(&p, 0, sizeof(p));
-  p.x = x; p.ldx = ldx; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.x = x; p.ldx = ldx; p.dy = CB(dy_bf16); p.lddy = lddy; p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
   p.M = M; p.C = C; p.eps = eps;
   return ln_bwd_dispatch(MODE_IDENTITY, p, S(stream));
 }
@@ -307,7 +308,7 @@ int lavt_layernorm_window_gather_bwd(const float* x, int32_t C, const lavt_win_g
   LnBwdParams p;
   std::memset(&p, 0, sizeof(p));
   std::memcpy(&p.win, geom, sizeof(WinGeom));
-  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.lddy = C; p.gamma = gamma; p.dres = dres; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
   p.M = 1LL * p.win.B * p.win.nwd * p.win.nwh * p.win.nww * p.win.N; p.C = C; p.eps = eps;
   return ln_bwd_dispatch(MODE_WINDOW, p, S(stream));
 }
@@ -316,7 +317,7 @@ int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t
                                    const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* stream) {
   LnBwdParams p;
   std::memset(&p, 0, sizeof(p));
-  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.gamma = gamma; p.dres = nullptr; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.x = x; p.ldx = C; p.dy = CB(dy_bf16); p.lddy = 4 * C; p.gamma = gamma; p.dres = nullptr; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
   p.M = 1LL * B * D * ((H + 1) / 2) * ((W + 1) / 2); p.C = C; p.eps = eps;
   p.mB = B; p.mD = D; p.mH = H; p.mW = W;
   return ln_bwd_dispatch(MODE_MERGE, p, S(stream));
@@ -333,6 +334,62 @@ int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout
   p.qscale = 0.17677669529663687f;      // 32^-0.5
   LAVT_REQUIRE(L == (2 * p.win.Wd - 1) * (2 * p.win.Wh - 1) * (2 * p.win.Ww - 1), "attention backward: table length %d does not match the window", L);
   return window_attn_bwd_dispatch(p, S(stream));
+}
+
+int lavt_pwam_attend_bwd(const float* qpre, const float* stats, const float* k, const float* v, const float* mask, const void* do_bf16,
+                         float* dqhat, void* qs_bf16, void* p_bd, void* ds_bd, float* sums, int32_t B, int64_t n, int32_t C, int32_t Nl,
+                         int32_t NlPad, int32_t heads, void* stream) {
+  return pwam_attend_bwd_dispatch(qpre, stats, k, v, mask, CB(do_bf16), dqhat, MB(qs_bf16), MB(p_bd), MB(ds_bd), sums, B, n, C, Nl, NlPad,
+                                  heads, S(stream));
+}
+int lavt_pwam_mul_norm_bwd(const void* da2, const void* vis, const void* vispre, const float* langpre, const float* stats, void* dvispre,
+                           float* sums, int32_t B, int64_t n, int32_t C, void* stream) {
+  return pwam_mul_bwd_dispatch(CB(da2), CB(vis), CB(vispre), langpre, stats, MB(dvispre), sums, B, n, C, S(stream));
+}
+int lavt_instnorm_bwd(const float* g_f32, const void* ga_bf16, const void* gb_bf16, const float* xpre, const float* stats, const float* sums,
+                      void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream) {
+  return instnorm_bwd_dispatch(g_f32, CB(ga_bf16), CB(gb_bf16), xpre, stats, sums, MB(out_bf16), B, n, C, S(stream));
+}
+int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv, float* dwk,
+                     float* dbk, float* dwv, float* dbv, float* dl, int32_t B, int32_t Nl, int32_t NlPad, int32_t Lin, int32_t C,
+                     int32_t heads, void* stream) {
+  return pwam_kv_bwd_dispatch(dkbuf, dvbuf, mask, l, wk, wv, dwk, dbk, dwv, dbv, dl, B, Nl, NlPad, Lin, C, heads, S(stream));
+}
+int lavt_gate_elementwise(int32_t mode, const void* a_bf16, const void* b_bf16, const float* f, const float* f2, void* out_bf16,
+                          float* out_f32, int64_t count, void* stream) {
+  return gate_elem_dispatch(mode, CB(a_bf16), CB(b_bf16), f, f2, MB(out_bf16), out_f32, count, S(stream));
+}
+
+int lavt_bn_relu_apply(const float* z, const float* stats, const float* gamma, const float* beta, void* t_bf16, int64_t npix, int32_t C,
+                       void* stream) {
+  return bn_relu_apply_dispatch(z, stats, gamma, beta, MB(t_bf16), npix, C, S(stream));
+}
+int lavt_bn_relu_bwd_reduce(const void* dt_bf16, const void* t_bf16, const float* z, const float* stats, float* sums, int64_t npix, int32_t C,
+                            void* stream) {
+  return bn_relu_bwd_dispatch(CB(dt_bf16), CB(t_bf16), z, stats, nullptr, sums, nullptr, npix, npix, C, 0, S(stream));
+}
+int lavt_bn_relu_bwd_apply(const void* dt_bf16, const void* t_bf16, const float* z, const float* stats, const float* gamma, const float* sums,
+                           void* dz_bf16, int64_t npix, int64_t n_stat, int32_t C, void* stream) {
+  return bn_relu_bwd_dispatch(CB(dt_bf16), CB(t_bf16), z, stats, gamma, const_cast<float*>(sums), MB(dz_bf16), npix, n_stat, C, 1, S(stream));
+}
+int lavt_nhwc_pad_transpose(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                            int32_t Wp, int32_t dshift, void* stream) {
+  return nhwc_pad_transpose_dispatch(CB(in_bf16), ldi, MB(out_bf16), ldo, n_img, H, W, C, Wp, dshift, S(stream));
+}
+int lavt_upsample_concat_bwd(const void* dcat_bf16, int32_t Ct, void* dprev_bf16, int32_t ph, int32_t pw, int32_t C1, int32_t n_img, int32_t H,
+                             int32_t W, void* stream) {
+  return upsample_concat_bwd_dispatch(CB(dcat_bf16), Ct, MB(dprev_bf16), ph, pw, C1, n_img, H, W, S(stream));
+}
+int lavt_conv1x1_logits_bwd(const float* dlogits, const void* y_bf16, const float* w, void* dy_bf16, float* dw, float* db, int64_t npix,
+                            int32_t C, void* stream) {
+  return conv1x1_logits_bwd_dispatch(dlogits, CB(y_bf16), w, MB(dy_bf16), dw, db, npix, C, S(stream));
+}
+int lavt_upsample_logits_bwd(const float* dout, float* din, int32_t n_img, int32_t h, int32_t w, int32_t H, int32_t W, void* stream) {
+  return upsample_logits_bwd_dispatch(dout, din, n_img, h, w, H, W, S(stream));
+}
+int lavt_cross_entropy(const float* logits, const int64_t* target, float w0, float w1, float* acc, float* dlogits, float gscale, int32_t n_img,
+                       int32_t H, int32_t W, int32_t phase, void* stream) {
+  return ce_loss_dispatch(logits, reinterpret_cast<const long long*>(target), w0, w1, acc, dlogits, gscale, n_img, H, W, phase, S(stream));
 }
 
 }  // extern "C"

@@ -60,7 +60,8 @@ int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st);
 struct LnBwdParams {
   const float* x;              // LN input rows (fp32, pitch ldx), gathered like the forward
   long long ldx;
-  const __nv_bfloat16* dy;     // [M, Cn] gradient of the LN output, in OUTPUT-row order
+  const __nv_bfloat16* dy;     // [M, Cn] gradient of the LN output, in OUTPUT-row order (row pitch lddy)
+  long long lddy;
   const float* gamma;          // [Cn]
   const float* dres;           // [tokens, C] gradient already flowing on the residual stream (added), or nullptr
   float* dx;                   // [tokens, C] result (may alias dres)
@@ -79,6 +80,32 @@ int colsum_dispatch(const void* x, int is_bf16, long long ldx, long long M, int 
 int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, cudaStream_t st);
 int gelu_fwd_dispatch(const __nv_bfloat16* x, __nv_bfloat16* y, long long count, cudaStream_t st);
 int gelu_bwd_dispatch(const __nv_bfloat16* dy, const __nv_bfloat16* x, __nv_bfloat16* dx, long long count, cudaStream_t st);
+
+int bn_relu_apply_dispatch(const float* z, const float* stats, const float* gamma, const float* beta, __nv_bfloat16* t, long long npix,
+                           int C, cudaStream_t st);
+int bn_relu_bwd_dispatch(const __nv_bfloat16* dt, const __nv_bfloat16* t, const float* z, const float* stats, const float* gamma,
+                         float* sums, __nv_bfloat16* dz, long long npix, long long n_stat, int C, int phase, cudaStream_t st);
+int nhwc_pad_transpose_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, int n_img, int H, int W, int C,
+                                int Wp, int dshift, cudaStream_t st);
+int upsample_concat_bwd_dispatch(const __nv_bfloat16* dcat, int Ct, __nv_bfloat16* dprev, int ph, int pw, int C1, int n_img, int H, int W,
+                                 cudaStream_t st);
+int conv1x1_logits_bwd_dispatch(const float* dlog, const __nv_bfloat16* y, const float* w, __nv_bfloat16* dy, float* dw, float* db,
+                                long long npix, int C, cudaStream_t st);
+int upsample_logits_bwd_dispatch(const float* dout, float* din, int n_img, int h, int w, int H, int W, cudaStream_t st);
+int ce_loss_dispatch(const float* logits, const long long* target, float w0, float w1, float* acc, float* dlogits, float gscale, int n_img,
+                     int H, int W, int phase, cudaStream_t st);
+int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
+                             const __nv_bfloat16* dO, float* dqhat, __nv_bfloat16* qs_out, __nv_bfloat16* P_bd, __nv_bfloat16* dS_bd,
+                             float* sums, int B, long long n, int C, int Nl, int NlPad, int heads, cudaStream_t st);
+int pwam_mul_bwd_dispatch(const __nv_bfloat16* da2, const __nv_bfloat16* vis, const __nv_bfloat16* vispre, const float* langpre,
+                          const float* stats, __nv_bfloat16* dvispre, float* sums, int B, long long n, int C, cudaStream_t st);
+int instnorm_bwd_dispatch(const float* g32, const __nv_bfloat16* ga, const __nv_bfloat16* gb, const float* xpre, const float* stats,
+                          const float* sums, __nv_bfloat16* out, int B, long long n, int C, cudaStream_t st);
+int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv,
+                         float* dwk, float* dbk, float* dwv, float* dbv, float* dl, int B, int Nl, int NlPad, int Lin, int C, int heads,
+                         cudaStream_t st);
+int gate_elem_dispatch(int mode, const __nv_bfloat16* a, const __nv_bfloat16* b, const float* f, const float* f2, __nv_bfloat16* out_bf16,
+                       float* out_f32, long long count, cudaStream_t st);
 
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);

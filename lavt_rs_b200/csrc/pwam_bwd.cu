@@ -1,0 +1,432 @@
+// Backward of PWAM + LanguageGate (reference PWAM.forward lib/video_swin_transformer.py:919-934,
+// SpatialImageLanguageAttention.forward :975-1009, res_gate :519-525 applied at :570; differentiated by autograd in the
+// reference, train.py:330-360).  The dense parts (1x1 convs, gate linears) go through the tcgen05 GEMM (dgrad) and the split-K
+// GEMM (wgrad); these kernels are the adjoints of everything in between:
+//   pwam_attend_bwd   per pixel: recompute q^ = IN(q_pre), the masked softmax over words and dP = dO v^T; emits d q^, the bf16
+//                     rows of P and dS (block-diagonal over clips / fusion heads) that turn dk = dS^T q^ and dv = P^T dO into
+//                     ordinary weight-gradient GEMMs, and the two InstanceNorm reductions sum(dq^), sum(dq^ q^)
+//   pwam_mul_bwd      a2 = vis * IN(lang_pre): d vis_pre (through GELU') and the InstanceNorm reductions of lang
+//   instnorm_bwd      d x_pre = rstd (g - mean g - x^ mean(g x^)) from the accumulated reductions
+//   pwam_kv_bwd       k, v = (W l + b) * mask: dW, db, d l
+//   gate kernels      x' = x + tanh(.) * r: elementwise adjoints (tanh', relu mask), GELU with an fp32 copy / fp32 gradient in
+#include "kernels.cuh"
+
+namespace lavt {
+
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One warp per pixel (grid-strided); lane owns CPL = C / 32 contiguous channels, each fusion head's channels sit in a group
+// of 32 / heads lanes (same layout as pwam_core_kernel).  Per-warp shared memory: s, P, dP, dS for heads x NlPad words.
+template <int CPL>
+__global__ void __launch_bounds__(256) pwam_attend_bwd_kernel(const float* __restrict__ qpre, const float* __restrict__ stats,
+                                                              const float* __restrict__ k, const float* __restrict__ v,
+                                                              const float* __restrict__ mask, const __nv_bfloat16* __restrict__ dO,
+                                                              float* __restrict__ dqhat, __nv_bfloat16* __restrict__ qs_out,
+                                                              __nv_bfloat16* __restrict__ P_bd, __nv_bfloat16* __restrict__ dS_bd,
+                                                              float* __restrict__ sums, int B, long long n, int Nl, int NlPad, int heads,
+                                                              float scale) {
+  extern __shared__ float pab_smem[];
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int HW = heads * NlPad;
+  float* sS = pab_smem + warp * 4 * HW;
+  float* sP = sS + HW;
+  float* sdP = sP + HW;
+  float* sdS = sdP + HW;
+  for (int i = lane; i < 4 * HW; i += 32) sS[i] = 0.f;
+  __syncwarp();
+  const int gl = 32 / heads;
+  const int myhead = lane / gl;
+  const bool leader = (lane % gl) == 0;
+  const int c0 = lane * CPL;
+  const int Wd = B * HW;
+  float mu[CPL], rs[CPL], s1[CPL], s2[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    mu[i] = __ldg(stats + (static_cast<long long>(b) * 2) * C + c0 + i);
+    rs[i] = __ldg(stats + (static_cast<long long>(b) * 2 + 1) * C + c0 + i);
+    s1[i] = 0.f;
+    s2[i] = 0.f;
+  }
+  const float* kb = k + static_cast<long long>(b) * Nl * C + c0;
+  const float* vb = v + static_cast<long long>(b) * Nl * C + c0;
+  const float* mb = mask + b * Nl;
+  float* hs = sS + myhead * NlPad;
+  float* hp = sP + myhead * NlPad;
+  float* hdp = sdP + myhead * NlPad;
+  float* hds = sdS + myhead * NlPad;
+  const long long total_warps = static_cast<long long>(gridDim.x) * 8;
+  for (long long p = static_cast<long long>(blockIdx.x) * 8 + warp; p < n; p += total_warps) {
+    const long long row = static_cast<long long>(b) * n + p;
+    float qh[CPL], d[CPL], dq[CPL];
+    {
+      const float* src = qpre + row * C + c0;
+      const __nv_bfloat16* dsrc = dO + row * C + c0;
+#pragma unroll
+      for (int i = 0; i < CPL; i += 4) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(src + i));
+        qh[i] = (u.x - mu[i]) * rs[i]; qh[i + 1] = (u.y - mu[i + 1]) * rs[i + 1];
+        qh[i + 2] = (u.z - mu[i + 2]) * rs[i + 2]; qh[i + 3] = (u.w - mu[i + 3]) * rs[i + 3];
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(dsrc + i));
+        const float2 a = unpack_bf16x2(w.x), c = unpack_bf16x2(w.y);
+        d[i] = a.x; d[i + 1] = a.y; d[i + 2] = c.x; d[i + 3] = c.y;
+        dq[i] = dq[i + 1] = dq[i + 2] = dq[i + 3] = 0.f;
+      }
+    }
+    // pass 1: scores (kept in shared memory), running max / denominator per head
+    float mx = -INFINITY, den = 0.f;
+    for (int j = 0; j < Nl; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; i += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * C + i));
+        s = fmaf(qh[i], a.x, s); s = fmaf(qh[i + 1], a.y, s); s = fmaf(qh[i + 2], a.z, s); s = fmaf(qh[i + 3], a.w, s);
+      }
+      for (int off = gl >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      s = s * scale + (1e4f * __ldg(mb + j) - 1e4f);
+      if (leader) hs[j] = s;
+      const float nm = fmaxf(mx, s);
+      den = den * __expf(mx - nm) + __expf(s - nm);
+      mx = nm;
+    }
+    __syncwarp();
+    const float inv = 1.0f / den;
+    // pass 2: P, dP = dO . v_j, D = sum_j P dP
+    float Dsum = 0.f;
+    for (int j = 0; j < Nl; ++j) {
+      float dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; i += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * C + i));
+        dp = fmaf(d[i], a.x, dp); dp = fmaf(d[i + 1], a.y, dp); dp = fmaf(d[i + 2], a.z, dp); dp = fmaf(d[i + 3], a.w, dp);
+      }
+      for (int off = gl >> 1; off > 0; off >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, off);
+      const float pj = __expf(hs[j] - mx) * inv;
+      Dsum = fmaf(pj, dp, Dsum);
+      if (leader) { hp[j] = pj; hdp[j] = dp; }
+    }
+    __syncwarp();
+    // pass 3: dS = P (dP - D), d q^ = scale * dS k
+    for (int j = 0; j < Nl; ++j) {
+      const float ds = hp[j] * (hdp[j] - Dsum);
+      if (leader) hds[j] = ds;
+#pragma unroll
+      for (int i = 0; i < CPL; i += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * C + i));
+        dq[i] = fmaf(ds, a.x, dq[i]); dq[i + 1] = fmaf(ds, a.y, dq[i + 1]);
+        dq[i + 2] = fmaf(ds, a.z, dq[i + 2]); dq[i + 3] = fmaf(ds, a.w, dq[i + 3]);
+      }
+    }
+    __syncwarp();
+    {
+      float* dst = dqhat + row * C + c0;
+      __nv_bfloat16* qdst = qs_out + row * C + c0;
+#pragma unroll
+      for (int i = 0; i < CPL; i += 4) {
+        float4 o = make_float4(dq[i] * scale, dq[i + 1] * scale, dq[i + 2] * scale, dq[i + 3] * scale);
+        *reinterpret_cast<float4*>(dst + i) = o;
+        s1[i] += o.x; s1[i + 1] += o.y; s1[i + 2] += o.z; s1[i + 3] += o.w;
+        s2[i] = fmaf(o.x, qh[i], s2[i]); s2[i + 1] = fmaf(o.y, qh[i + 1], s2[i + 1]);
+        s2[i + 2] = fmaf(o.z, qh[i + 2], s2[i + 2]); s2[i + 3] = fmaf(o.w, qh[i + 3], s2[i + 3]);
+        *reinterpret_cast<uint2*>(qdst + i) = make_uint2(pack_bf16x2(qh[i] * scale, qh[i + 1] * scale), pack_bf16x2(qh[i + 2] * scale, qh[i + 3] * scale));
+      }
+    }
+    // block-diagonal rows: columns of clip b carry P / dS, all other clips zero
+    for (int c2 = lane * 2; c2 < Wd; c2 += 64) {
+      const int blk = c2 / HW, w = c2 - blk * HW;
+      uint32_t pv = 0u, zv = 0u;
+      if (blk == b) {
+        pv = pack_bf16x2(sP[w], sP[w + 1]);
+        zv = pack_bf16x2(sdS[w], sdS[w + 1]);
+      }
+      *reinterpret_cast<uint32_t*>(P_bd + row * Wd + c2) = pv;
+      *reinterpret_cast<uint32_t*>(dS_bd + row * Wd + c2) = zv;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    atomicAdd(sums + (static_cast<long long>(b) * 2) * C + c0 + i, s1[i]);
+    atomicAdd(sums + (static_cast<long long>(b) * 2 + 1) * C + c0 + i, s2[i]);
+  }
+}
+
+int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
+                             const __nv_bfloat16* dO, float* dqhat, __nv_bfloat16* qs_out, __nv_bfloat16* P_bd, __nv_bfloat16* dS_bd,
+                             float* sums, int B, long long n, int C, int Nl, int NlPad, int heads, cudaStream_t st) {
+  LAVT_REQUIRE(B > 0 && n > 0 && Nl > 0, "pwam backward: empty input");
+  LAVT_REQUIRE(heads >= 1 && heads <= 32 && (32 % heads) == 0, "pwam backward: fusion heads=%d must divide 32", heads);
+  LAVT_REQUIRE(NlPad >= Nl && NlPad % 8 == 0, "pwam backward: padded word count %d invalid for %d words", NlPad, Nl);
+  const float scale = 1.0f / sqrtf(static_cast<float>(C));
+  const size_t smem = static_cast<size_t>(8) * 4 * heads * NlPad * sizeof(float);
+  LAVT_REQUIRE(smem <= 200 * 1024, "pwam backward: %d heads x %d words do not fit in shared memory", heads, NlPad);
+  long long gx = (n + 7) / 8;
+  if (gx > 148 * 2) gx = 148 * 2;
+  dim3 grid(static_cast<unsigned>(gx), B);
+#define LAVT_PAB_CASE(cpl)                                                                                             \
+  case cpl * 32: {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                              \
+      LAVT_CUDA(cudaFuncSetAttribute(pwam_attend_bwd_kernel<cpl>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    pwam_attend_bwd_kernel<cpl><<<grid, 256, smem, st>>>(qpre, stats, k, v, mask, dO, dqhat, qs_out, P_bd, dS_bd, sums, B, n, Nl, NlPad, \
+                                                         heads, scale);                                                \
+    break;                                                                                                             \
+  }
+  switch (C) {
+    LAVT_PAB_CASE(4)
+    LAVT_PAB_CASE(8)
+    LAVT_PAB_CASE(16)
+    LAVT_PAB_CASE(32)
+    default:
+      set_last_error("pwam backward: C=%d unsupported (need 128/256/512/1024)", C);
+      return LAVT_ERR_SHAPE;
+  }
+#undef LAVT_PAB_CASE
+  LAVT_LAUNCH_CHECK("pwam_attend_bwd_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a2 = vis * IN(lang_pre), vis = GELU(vis_pre):  d vis_pre = da2 * lang * GELU'(vis_pre);  g = da2 * vis is the gradient of lang,
+// whose InstanceNorm reductions sum(g), sum(g * lang) accumulate into sums [B,2,C].  grid (chunks of 256 rows, B).
+__global__ void __launch_bounds__(256) pwam_mul_bwd_kernel(const __nv_bfloat16* __restrict__ da2, const __nv_bfloat16* __restrict__ vis,
+                                                           const __nv_bfloat16* __restrict__ vispre, const float* __restrict__ langpre,
+                                                           const float* __restrict__ stats, __nv_bfloat16* __restrict__ dvispre,
+                                                           float* __restrict__ sums, int n, int C) {
+  extern __shared__ float pmb_sm[];       // [rg][C][2]
+  const int b = blockIdx.y;
+  const int tpr = C / 4, rg = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2) * C) + tc);
+  const float4 rs = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2 + 1) * C) + tc);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const int r0 = blockIdx.x * 256, r1 = min(n, r0 + 256);
+  if (tr < rg) {
+    for (int r = r0 + tr; r < r1; r += rg) {
+      const long long e = (static_cast<long long>(b) * n + r) * C + tc * 4;
+      const uint2 ua = __ldg(reinterpret_cast<const uint2*>(da2 + e)), uv = __ldg(reinterpret_cast<const uint2*>(vis + e));
+      const uint2 up = __ldg(reinterpret_cast<const uint2*>(vispre + e));
+      const float4 lp = __ldg(reinterpret_cast<const float4*>(langpre + e));
+      const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), v0 = unpack_bf16x2(uv.x), v1 = unpack_bf16x2(uv.y);
+      const float2 p0 = unpack_bf16x2(up.x), p1 = unpack_bf16x2(up.y);
+      const float l0 = (lp.x - mu.x) * rs.x, l1 = (lp.y - mu.y) * rs.y, l2 = (lp.z - mu.z) * rs.z, l3 = (lp.w - mu.w) * rs.w;
+      const float g0 = a0.x * v0.x, g1 = a0.y * v0.y, g2 = a1.x * v1.x, g3 = a1.y * v1.y;
+      s1.x += g0; s1.y += g1; s1.z += g2; s1.w += g3;
+      s2.x += g0 * l0; s2.y += g1 * l1; s2.z += g2 * l2; s2.w += g3 * l3;
+      *reinterpret_cast<uint2*>(dvispre + e) = make_uint2(pack_bf16x2(a0.x * l0 * gelu_grad(p0.x), a0.y * l1 * gelu_grad(p0.y)),
+                                                          pack_bf16x2(a1.x * l2 * gelu_grad(p1.x), a1.y * l3 * gelu_grad(p1.y)));
+    }
+    float* o = pmb_sm + (static_cast<long long>(tr) * C + tc * 4) * 2;
+    o[0] = s1.x; o[1] = s2.x; o[2] = s1.y; o[3] = s2.y; o[4] = s1.z; o[5] = s2.z; o[6] = s1.w; o[7] = s2.w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < rg; ++g) {
+      a += pmb_sm[(g * C + c) * 2 + 0];
+      q += pmb_sm[(g * C + c) * 2 + 1];
+    }
+    atomicAdd(sums + (static_cast<long long>(b) * 2) * C + c, a);
+    atomicAdd(sums + (static_cast<long long>(b) * 2 + 1) * C + c, q);
+  }
+}
+
+int pwam_mul_bwd_dispatch(const __nv_bfloat16* da2, const __nv_bfloat16* vis, const __nv_bfloat16* vispre, const float* langpre,
+                          const float* stats, __nv_bfloat16* dvispre, float* sums, int B, long long n, int C, cudaStream_t st) {
+  LAVT_REQUIRE(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "pwam mul backward: C=%d unsupported (need 128/256/512/1024)", C);
+  LAVT_REQUIRE(B > 0 && n > 0 && n < (1LL << 30), "pwam mul backward: bad sizes");
+  const int rg = 256 / (C / 4);
+  pwam_mul_bwd_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), B), 256, static_cast<size_t>(rg) * C * 2 * sizeof(float), st>>>(
+      da2, vis, vispre, langpre, stats, dvispre, sums, static_cast<int>(n), C);
+  LAVT_LAUNCH_CHECK("pwam_mul_bwd_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// InstanceNorm backward from the accumulated reductions: out = rstd * (g - S1/n - x^ * S2/n); g = g_f32, or ga * gb (bf16)
+__global__ void __launch_bounds__(256) instnorm_bwd_kernel(const float* __restrict__ g32, const __nv_bfloat16* __restrict__ ga,
+                                                           const __nv_bfloat16* __restrict__ gb, const float* __restrict__ xpre,
+                                                           const float* __restrict__ stats, const float* __restrict__ sums,
+                                                           __nv_bfloat16* __restrict__ out, long long n, int C, long long total4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % (C / 4));
+  const long long row = i / (C / 4);
+  const int b = static_cast<int>(row / n);
+  const float inv_n = 1.0f / static_cast<float>(n);
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2) * C) + c4);
+  const float4 rs = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2 + 1) * C) + c4);
+  const float4 S1 = __ldg(reinterpret_cast<const float4*>(sums + (static_cast<long long>(b) * 2) * C) + c4);
+  const float4 S2 = __ldg(reinterpret_cast<const float4*>(sums + (static_cast<long long>(b) * 2 + 1) * C) + c4);
+  const float4 x = __ldg(reinterpret_cast<const float4*>(xpre) + i);
+  float4 g;
+  if (g32) {
+    g = __ldg(reinterpret_cast<const float4*>(g32) + i);
+  } else {
+    const uint2 ua = __ldg(reinterpret_cast<const uint2*>(ga) + i), ub = __ldg(reinterpret_cast<const uint2*>(gb) + i);
+    const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), b0 = unpack_bf16x2(ub.x), b1 = unpack_bf16x2(ub.y);
+    g = make_float4(a0.x * b0.x, a0.y * b0.y, a1.x * b1.x, a1.y * b1.y);
+  }
+  const float h0 = (x.x - mu.x) * rs.x, h1 = (x.y - mu.y) * rs.y, h2 = (x.z - mu.z) * rs.z, h3 = (x.w - mu.w) * rs.w;
+  const float o0 = rs.x * (g.x - S1.x * inv_n - h0 * S2.x * inv_n), o1 = rs.y * (g.y - S1.y * inv_n - h1 * S2.y * inv_n);
+  const float o2 = rs.z * (g.z - S1.z * inv_n - h2 * S2.z * inv_n), o3 = rs.w * (g.w - S1.w * inv_n - h3 * S2.w * inv_n);
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+}
+
+int instnorm_bwd_dispatch(const float* g32, const __nv_bfloat16* ga, const __nv_bfloat16* gb, const float* xpre, const float* stats,
+                          const float* sums, __nv_bfloat16* out, int B, long long n, int C, cudaStream_t st) {
+  LAVT_REQUIRE(C % 4 == 0 && B > 0 && n > 0, "instance-norm backward: bad sizes");
+  LAVT_REQUIRE(g32 || (ga && gb), "instance-norm backward: no gradient input");
+  const long long total4 = static_cast<long long>(B) * n * (C / 4);
+  instnorm_bwd_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(g32, ga, gb, xpre, stats, sums, out, n, C, total4);
+  LAVT_LAUNCH_CHECK("instnorm_bwd_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k, v = (W l + b) * mask.  dkbuf / dvbuf fp32 [(b * heads + h) * NlPad + j, C]: the row of head h = channel's head is the valid one.
+// grid.x covers C * Lin weight elements (both matrices), then B * Lin * Nl language elements.
+__global__ void __launch_bounds__(256) pwam_kv_bwd_kernel(const float* __restrict__ dkbuf, const float* __restrict__ dvbuf,
+                                                          const float* __restrict__ mask, const float* __restrict__ l,
+                                                          const float* __restrict__ wk, const float* __restrict__ wv,
+                                                          float* __restrict__ dwk, float* __restrict__ dbk, float* __restrict__ dwv,
+                                                          float* __restrict__ dbv, float* __restrict__ dl, int B, int Nl, int NlPad,
+                                                          int Lin, int C, int heads) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nW = static_cast<long long>(C) * Lin;
+  const int ch = C / heads;
+  if (idx < nW) {
+    const int c = static_cast<int>(idx / Lin), i = static_cast<int>(idx - static_cast<long long>(c) * Lin);
+    const int h = c / ch;
+    float ak = 0.f, av = 0.f, bk = 0.f, bv = 0.f;
+    for (int b = 0; b < B; ++b) {
+      for (int j = 0; j < Nl; ++j) {
+        const float m = __ldg(mask + b * Nl + j);
+        if (m == 0.f) continue;
+        const long long r = (static_cast<long long>(b) * heads + h) * NlPad + j;
+        const float gk = __ldg(dkbuf + r * C + c) * m, gv = __ldg(dvbuf + r * C + c) * m;
+        const float lv = __ldg(l + (static_cast<long long>(b) * Lin + i) * Nl + j);
+        ak = fmaf(gk, lv, ak);
+        av = fmaf(gv, lv, av);
+        bk += gk;
+        bv += gv;
+      }
+    }
+    if (dwk) dwk[idx] += ak;
+    if (dwv) dwv[idx] += av;
+    if (i == 0) {
+      if (dbk) dbk[c] += bk;
+      if (dbv) dbv[c] += bv;
+    }
+    return;
+  }
+  const long long e = idx - nW;
+  if (!dl || e >= static_cast<long long>(B) * Lin * Nl) return;
+  const int j = static_cast<int>(e % Nl);
+  const int i = static_cast<int>((e / Nl) % Lin);
+  const int b = static_cast<int>(e / (static_cast<long long>(Nl) * Lin));
+  const float m = __ldg(mask + b * Nl + j);
+  float acc = 0.f;
+  if (m != 0.f) {
+    for (int c = 0; c < C; ++c) {
+      const long long r = (static_cast<long long>(b) * heads + c / ch) * NlPad + j;
+      acc = fmaf(__ldg(dkbuf + r * C + c), __ldg(wk + static_cast<long long>(c) * Lin + i), acc);
+      acc = fmaf(__ldg(dvbuf + r * C + c), __ldg(wv + static_cast<long long>(c) * Lin + i), acc);
+    }
+  }
+  dl[e] += acc * m;
+}
+
+int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv,
+                         float* dwk, float* dbk, float* dwv, float* dbv, float* dl, int B, int Nl, int NlPad, int Lin, int C, int heads,
+                         cudaStream_t st) {
+  LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0 && heads > 0 && C % heads == 0, "pwam kv backward: bad sizes");
+  const long long total = static_cast<long long>(C) * Lin + static_cast<long long>(B) * Lin * Nl;
+  pwam_kv_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dkbuf, dvbuf, mask, l, wk, wv, dwk, dbk, dwv, dbv, dl, B,
+                                                                              Nl, NlPad, Lin, C, heads);
+  LAVT_LAUNCH_CHECK("pwam_kv_bwd_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LanguageGate elementwise pieces (x' = x + g2 * r, g2 = tanh(g1 G2^T), g1 = relu(r G0^T)); 8 elements per thread
+// (the tanh PRE-activation is what is saved: 1 - tanh^2 recomputed from a bf16-rounded tanh output loses all precision near
+//  saturation)
+// mode 0: out_f32 = x + tanh(a) * r                                     (forward; a = gate pre-activation, b = r, f = x)
+// mode 1: out_bf16 = f * r * (1 - tanh(a)^2);  out_f32 = f2 + f * tanh(a)  (f = dx', f2 = gradient of r so far or NULL)
+// mode 2: out_bf16 = a * [b > 0]                                         (relu backward; a = dg1, b = g1)
+// mode 3: out_bf16 = GELU(a), out_f32 = the same in fp32                 (forward with fp32 copy; a = pre-activation)
+// mode 4: out_bf16 = f * GELU'(a)                                        (GELU backward with an fp32 gradient)
+template <int MODE>
+__global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ f,
+                                                        const float4* __restrict__ f2, uint4* __restrict__ out_bf16,
+                                                        float4* __restrict__ out_f32, long long count8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count8) return;
+  float av[8], bv[8], fv[8], gv[8], ob[8], of[8];
+  {
+    const uint4 u = __ldg(a + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w[j]); av[2 * j] = t.x; av[2 * j + 1] = t.y; }
+  }
+  if (MODE <= 2) {
+    const uint4 u = __ldg(b + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w[j]); bv[2 * j] = t.x; bv[2 * j + 1] = t.y; }
+  }
+  if (MODE == 0 || MODE == 1 || MODE == 4) {
+    const float4 x0 = __ldg(f + 2 * i), x1 = __ldg(f + 2 * i + 1);
+    fv[0] = x0.x; fv[1] = x0.y; fv[2] = x0.z; fv[3] = x0.w; fv[4] = x1.x; fv[5] = x1.y; fv[6] = x1.z; fv[7] = x1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+  if (MODE == 1 && f2) {
+    const float4 x0 = __ldg(f2 + 2 * i), x1 = __ldg(f2 + 2 * i + 1);
+    gv[0] = x0.x; gv[1] = x0.y; gv[2] = x0.z; gv[3] = x0.w; gv[4] = x1.x; gv[5] = x1.y; gv[6] = x1.z; gv[7] = x1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ob[j] = 0.f;
+    of[j] = 0.f;
+    if (MODE == 0) of[j] = fv[j] + tanhf(av[j]) * bv[j];
+    if (MODE == 1) { const float t = tanhf(av[j]); ob[j] = fv[j] * bv[j] * (1.0f - t * t); of[j] = gv[j] + fv[j] * t; }
+    if (MODE == 2) ob[j] = bv[j] > 0.f ? av[j] : 0.f;
+    if (MODE == 3) { ob[j] = gelu_erf(av[j]); of[j] = ob[j]; }
+    if (MODE == 4) ob[j] = fv[j] * gelu_grad(av[j]);
+  }
+  if (MODE != 0) out_bf16[i] = make_uint4(pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]), pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
+  if (MODE == 0 || MODE == 1 || MODE == 3) {
+    out_f32[2 * i] = make_float4(of[0], of[1], of[2], of[3]);
+    out_f32[2 * i + 1] = make_float4(of[4], of[5], of[6], of[7]);
+  }
+}
+
+int gate_elem_dispatch(int mode, const __nv_bfloat16* a, const __nv_bfloat16* b, const float* f, const float* f2, __nv_bfloat16* out_bf16,
+                       float* out_f32, long long count, cudaStream_t st) {
+  LAVT_REQUIRE(count > 0 && count % 8 == 0, "gate kernels: element count must be a multiple of 8");
+  const long long c8 = count / 8;
+  const unsigned grid = static_cast<unsigned>((c8 + 255) / 256);
+  const uint4* a4 = reinterpret_cast<const uint4*>(a);
+  const uint4* b4 = reinterpret_cast<const uint4*>(b);
+  const float4* f4 = reinterpret_cast<const float4*>(f);
+  const float4* g4 = reinterpret_cast<const float4*>(f2);
+  uint4* ob = reinterpret_cast<uint4*>(out_bf16);
+  float4* of = reinterpret_cast<float4*>(out_f32);
+  switch (mode) {
+    case 0: LAVT_REQUIRE(a && b && f && out_f32, "gate apply: missing tensor"); gate_elem_kernel<0><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 1: LAVT_REQUIRE(a && b && f && out_bf16 && out_f32, "gate backward: missing tensor"); gate_elem_kernel<1><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 2: LAVT_REQUIRE(a && b && out_bf16, "relu backward: missing tensor"); gate_elem_kernel<2><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 3: LAVT_REQUIRE(a && out_bf16 && out_f32, "gelu forward: missing tensor"); gate_elem_kernel<3><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 4: LAVT_REQUIRE(a && f && out_bf16, "gelu backward: missing tensor"); gate_elem_kernel<4><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    default: set_last_error("gate kernels: bad mode %d", mode); return LAVT_ERR_SHAPE;
+  }
+  LAVT_LAUNCH_CHECK("gate_elem_kernel");
+  return LAVT_OK;
+}
+
+}  // namespace lavt

@@ -27,11 +27,13 @@ from .geometry import window_geometry
 
 
 class GradStore:
-    """fp32 accumulation buffers for parameter gradients (zeroed at creation = ``optimizer.zero_grad()``, train.py:352)."""
+    """fp32 accumulation buffers for parameter gradients (zeroed at creation = ``optimizer.zero_grad()``, train.py:352).
+    Some kernels accumulate in the layout of the engine's prepared operand rather than the parameter's; those buffers carry
+    a function that maps them back to the parameter's shape when the gradients are handed over."""
 
     def __init__(self):
         self._g: Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]] = {}
-        self._table_t: Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]] = {}
+        self._alt: Dict[Tuple[int, str], Tuple[torch.nn.Parameter, torch.Tensor, object]] = {}
 
     def of(self, param: torch.Tensor) -> torch.Tensor:
         """Accumulation buffer with the parameter's shape."""
@@ -41,20 +43,38 @@ class GradStore:
             self._g[id(param)] = hit
         return hit[1]
 
+    def _alt_buf(self, param, kind: str, shape, back) -> torch.Tensor:
+        hit = self._alt.get((id(param), kind))
+        if hit is None:
+            hit = (param, torch.zeros(shape, device=param.device, dtype=torch.float32), back)
+            self._alt[(id(param), kind)] = hit
+        return hit[1]
+
     def table_t(self, param: torch.Tensor) -> torch.Tensor:
         """relative_position_bias_table is [L, nH]; the attention kernels work on its transpose [nH, L]."""
-        hit = self._table_t.get(id(param))
-        if hit is None:
-            hit = (param, torch.zeros(param.shape[1], param.shape[0], device=param.device, dtype=torch.float32))
-            self._table_t[id(param)] = hit
-        return hit[1]
+        return self._alt_buf(param, "table_t", (param.shape[1], param.shape[0]), lambda b: b.t())
+
+    def conv_taps(self, param: torch.Tensor) -> torch.Tensor:
+        """Conv2d weight [Cout, Cin, 3, 3] accumulated tap-major [Cout, (ky*3+kx)*Cin + ci] (the implicit-GEMM operand layout)."""
+        Cout, Cin, kh, kw = param.shape
+        return self._alt_buf(param, "taps", (Cout, kh * kw * Cin), lambda b: b.view(Cout, kh, kw, Cin).permute(0, 3, 1, 2))
+
+    def padded_cols(self, param: torch.Tensor, cols: int) -> torch.Tensor:
+        """Weight flattened to [out, in] with the input axis zero-padded to ``cols`` (patch-embed GEMM, K = 48 -> 64)."""
+        out = param.shape[0]
+        kin = param.numel() // out
+        return self._alt_buf(param, "pad%d" % cols, (out, cols), lambda b: b[:, :kin].reshape(param.shape))
+
+    def _fold(self) -> None:
+        for param, buf, back in self._alt.values():
+            self.of(param).add_(back(buf))
+        self._alt.clear()
 
     def finalize(self) -> None:
         """Hand the accumulated gradients to ``param.grad`` (added to an existing ``.grad`` like autograd does).  Tensor-container
         bookkeeping, not a hot path."""
         with torch.no_grad():
-            for param, buf in self._table_t.values():
-                self.of(param).add_(buf.t())
+            self._fold()
             for param, buf in self._g.values():
                 if not param.requires_grad:
                     continue
@@ -64,18 +84,18 @@ class GradStore:
                 else:
                     param.grad.add_(g)
         self._g.clear()
-        self._table_t.clear()
+
+    def buffers(self) -> List[Tuple[torch.nn.Parameter, torch.Tensor]]:
+        """(parameter, fp32 gradient buffer) pairs after folding the alternate layouts (gradient all-reduce, tests)."""
+        with torch.no_grad():
+            self._fold()
+        return list(self._g.values())
 
     def named(self, module: torch.nn.Module) -> Dict[str, torch.Tensor]:
-        """name -> gradient buffer (after folding the transposed tables) for tests."""
-        out = {}
-        for name, prm in module.named_parameters():
-            if id(prm) in self._g or id(prm) in self._table_t:
-                g = self.of(prm).clone()
-                if id(prm) in self._table_t:
-                    g += self._table_t[id(prm)][1].t()
-                out[name] = g
-        return out
+        """name -> gradient buffer for tests."""
+        with torch.no_grad():
+            self._fold()
+        return {name: self._g[id(prm)][1] for name, prm in module.named_parameters() if id(prm) in self._g}
 
 
 def _pad8(n: int) -> int:
@@ -235,3 +255,349 @@ def patch_merging_bwd(ds, saved, dout: torch.Tensor, grads: GradStore, ws: Works
     K.patch_merge_layernorm_bwd(x, B, D, H, W, dg, ds.norm.weight, dx, grads.of(ds.norm.weight), grads.of(ds.norm.bias), eps=ds.norm.eps)
     _count(2)
     return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# PWAM + LanguageGate  (reference PWAM.forward :919-934, SpatialImageLanguageAttention.forward :975-1009, res_gate :519-525)
+# ------------------------------------------------------------------------------------------------
+def _nl_pad(Nl: int) -> int:
+    return (Nl + 7) // 8 * 8
+
+
+def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace):
+    """x fp32 [B*n, C] (not modified), xb = its bf16 copy, l fp32 [B,768,Nl], mask fp32 [B,Nl].
+    Returns (r fp32 [B*n, C] = x_residual, x' fp32 = gated x or None without a gate, saved)."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    att = fusion.image_lang_att
+    heads = att.num_heads
+    Nl = l.shape[-1]
+    bf, f32 = torch.bfloat16, torch.float32
+
+    def wprep(name, conv):
+        return pw.get(name, [conv.weight], lambda: _bf16(conv.weight[:, :, 0]))
+    vis_w, q_w, W_w, mm_w = (wprep("vis_w", fusion.vis_project[0]), wprep("q_w", att.f_query[0]), wprep("W_w", att.W[0]),
+                             wprep("mm_w", fusion.project_mm[0]))
+    k_w = pw.get("k_w", [att.f_key[0].weight], lambda: _f32(att.f_key[0].weight[:, :, 0]))
+    v_w = pw.get("v_w", [att.f_value[0].weight], lambda: _f32(att.f_value[0].weight[:, :, 0]))
+
+    vispre = torch.empty(N_, C, device=dev, dtype=bf)
+    K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), out_bf16=vispre)
+    vis = torch.empty(B, n, C, device=dev, dtype=bf)
+    K.gelu_fwd(vispre, vis)
+    qpre = torch.empty(B, n, C, device=dev, dtype=f32)
+    K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
+    stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), f32, dev)
+    K.instnorm_stats(qpre, stats_q, stw)
+    kk = torch.empty(B, Nl, C, device=dev, dtype=f32)
+    vv = torch.empty(B, Nl, C, device=dev, dtype=f32)
+    K.pwam_kv(l, mask, k_w, att.f_key[0].bias.detach(), v_w, att.f_value[0].bias.detach(), kk, vv)
+    o = torch.empty(B, n, C, device=dev, dtype=bf)
+    K.pwam_attend(qpre, stats_q, kk, vv, mask, o, heads)
+    langpre = torch.empty(B, n, C, device=dev, dtype=f32)
+    K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_f32=langpre.view(N_, C))
+    stats_l = torch.empty(B, 2, C, device=dev, dtype=f32)
+    K.instnorm_stats(langpre, stats_l, stw)
+    a2 = torch.empty(B, n, C, device=dev, dtype=bf)
+    K.pwam_mul_norm(vis, langpre, stats_l, a2)
+    rpre = torch.empty(N_, C, device=dev, dtype=bf)
+    K.gemm_bf16(a2.view(N_, C), mm_w, bias=fusion.project_mm[0].bias.detach(), out_bf16=rpre)
+    rb = torch.empty(N_, C, device=dev, dtype=bf)
+    r32 = torch.empty(N_, C, device=dev, dtype=f32)
+    K.gate_elementwise(3, rpre, out_bf16=rb, out_f32=r32)
+    _count(13)
+    g1 = g2 = xg = None
+    if res_gate is not None:
+        g0w = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2w = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1 = torch.empty(N_, C, device=dev, dtype=bf)
+        K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
+        g2 = torch.empty(N_, C, device=dev, dtype=bf)
+        K.gemm_bf16(g1, g2w, out_bf16=g2)       # PRE-activation of the tanh (saved); tanh is applied by the elementwise kernel
+        xg = torch.empty(N_, C, device=dev, dtype=f32)
+        K.gate_elementwise(0, g2, rb, f=x, out_f32=xg)
+        _count(3)
+    saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
+                 a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w)
+    return r32, xg, saved
+
+
+def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: Optional[torch.Tensor], grads: GradStore, ws: Workspace,
+                  dl: torch.Tensor) -> torch.Tensor:
+    """dr_out fp32 [B*n, C]: gradient of r from the stage-output path (or None); dxg fp32: gradient of the gated x' (or None when the
+    gate output is unused, e.g. the last stage).  ``dl`` fp32 [B,768,Nl] accumulates the gradient of the language features.
+    Returns dx fp32 [B*n, C], the gradient of the stage features x (dxg is reused in place when given)."""
+    s = saved
+    B, heads = s["B"], s["heads"]
+    xb = s["xb"]
+    N_, C = xb.shape
+    n = N_ // B
+    dev = xb.device
+    bf, f32 = torch.bfloat16, torch.float32
+    pw = fusion.prepared
+    att = fusion.image_lang_att
+    Nl = s["l"].shape[-1]
+    nlp = _nl_pad(Nl)
+    dr = dr_out
+    if res_gate is not None and dxg is not None:
+        dg2pre = ws.get("bw_pw_a", (N_, C), bf, dev)
+        if dr is None:
+            dr = ws.get("bw_pw_dr", (N_, C), f32, dev)
+            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
+        else:
+            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
+        dg1 = ws.get("bw_pw_b", (N_, C), bf, dev)
+        linear_bwd(dg2pre, s["g1"], res_gate[2].weight, None, grads, ws, pw, "g2", dx_bf16=dg1)
+        K.gate_elementwise(2, dg1, s["g1"], out_bf16=dg1)
+        linear_bwd(dg1, s["rb"], res_gate[0].weight, None, grads, ws, pw, "g0", dx_f32=dr, dx_resid=dr)
+        _count(2)
+    if dr is None:
+        raise K.LavtError("pwam backward: neither the stage output nor the gated features carry a gradient")
+    drpre = ws.get("bw_pw_a", (N_, C), bf, dev)
+    K.gate_elementwise(4, s["rpre"], f=dr, out_bf16=drpre)
+    da2 = ws.get("bw_pw_b", (N_, C), bf, dev)
+    linear_bwd(drpre, s["a2"].view(N_, C), fusion.project_mm[0].weight, fusion.project_mm[0].bias, grads, ws, pw, "mm", dx_bf16=da2)
+    sums = torch.zeros(2, B, 2, C, device=dev, dtype=f32)
+    dvispre = ws.get("bw_pw_c", (N_, C), bf, dev)
+    K.pwam_mul_norm_bwd(da2, s["vis"], s["vispre"], s["langpre"], s["stats_l"], dvispre, sums[0])
+    dlangpre = ws.get("bw_pw_a", (N_, C), bf, dev)
+    K.instnorm_bwd(s["langpre"], s["stats_l"], sums[0], dlangpre, ga=da2, gb=s["vis"].view(N_, C))
+    do = ws.get("bw_pw_b", (N_, C), bf, dev)
+    linear_bwd(dlangpre, s["o"].view(N_, C), att.W[0].weight, att.W[0].bias, grads, ws, pw, "W", dx_bf16=do)
+    # pixel-word attention core
+    Wd = B * heads * nlp
+    dqhat = ws.get("bw_pw_dq", (B, n, C), f32, dev)
+    qs = ws.get("bw_pw_a", (N_, C), bf, dev)
+    p_bd = ws.get("bw_pw_pbd", (N_, Wd), bf, dev)
+    ds_bd = ws.get("bw_pw_dsbd", (N_, Wd), bf, dev)
+    K.pwam_attend_bwd(s["qpre"], s["stats_q"], s["kk"], s["vv"], s["mask"], do, dqhat, qs, p_bd, ds_bd, sums[1], heads, nlp)
+    dkv = torch.empty(2, Wd, C, device=dev, dtype=f32)
+    for buf, dy_rows, x_rows in ((dkv[0], ds_bd, qs), (dkv[1], p_bd, do)):      # dk = dS^T (C^-0.5 q^), dv = P^T dO
+        dy_t = _transposed(ws, "bw_dyT", dy_rows)
+        x_t = _transposed(ws, "bw_xT", x_rows)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Wd, C, dy_t.shape[1]),), f32, dev)
+        K.gemm_bf16_splitk(dy_t, x_t, buf, part, accumulate=False)
+    fk, fv = att.f_key[0], att.f_value[0]
+    K.pwam_kv_bwd(dkv[0], dkv[1], s["mask"], s["l"], s["k_w"], s["v_w"],
+                  grads.of(fk.weight) if fk.weight.requires_grad else None, grads.of(fk.bias) if fk.bias.requires_grad else None,
+                  grads.of(fv.weight) if fv.weight.requires_grad else None, grads.of(fv.bias) if fv.bias.requires_grad else None,
+                  dl, heads, nlp)
+    dqpre = ws.get("bw_pw_b", (N_, C), bf, dev)
+    K.instnorm_bwd(s["qpre"], s["stats_q"], sums[1], dqpre, g_f32=dqhat)
+    # both projections of x: dx (+)= dvispre Wvis + dqpre Wq
+    if dxg is not None:
+        dx = dxg
+        first_resid = dx
+    else:
+        dx = torch.empty(N_, C, device=dev, dtype=f32)
+        first_resid = None
+    x_t = linear_bwd(dvispre, xb, fusion.vis_project[0].weight, fusion.vis_project[0].bias, grads, ws, pw, "vis", dx_f32=dx,
+                     dx_resid=first_resid)
+    linear_bwd(dqpre, xb, att.f_query[0].weight, att.f_query[0].bias, grads, ws, pw, "q", dx_f32=dx, dx_resid=dx, x_t=x_t)
+    _count(16)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# PatchEmbed3D (reference :616-634) and the per-stage output norm (:869-874)
+# ------------------------------------------------------------------------------------------------
+def patch_embed_fwd(x5: torch.Tensor, pe, ws: Workspace):
+    """x5 fp32 (B,3,T,H,W) strided view -> (x fp32 [B*T*Hp*Wp, C], Hp, Wp, saved)."""
+    B, _, T, H, W = x5.shape
+    dev = x5.device
+    Hp, Wp = (H + 3) // 4, (W + 3) // 4
+    C = pe.embed_dim
+    n = B * T * Hp * Wp
+
+    def _w():
+        w = pe.proj.weight.detach().reshape(C, -1).to(torch.bfloat16)
+        wp = torch.zeros(C, 64, device=w.device, dtype=torch.bfloat16)
+        wp[:, : w.shape[1]] = w
+        return wp
+    pw_ = pe.prepared.get("w", [pe.proj.weight], _w)
+    cols = torch.empty(n, 64, device=dev, dtype=torch.bfloat16)
+    K.patch_embed_im2col(x5, cols)
+    ypre = torch.empty(n, C, device=dev, dtype=torch.float32)
+    K.gemm_bf16(cols, pw_, bias=pe.proj.bias.detach(), out_f32=ypre)
+    if pe.norm is None:
+        _count(2)
+        return ypre, Hp, Wp, (cols, None)
+    x = torch.empty(n, C, device=dev, dtype=torch.float32)
+    K.layernorm_rows(ypre, pe.norm.weight, pe.norm.bias, out_f32=x, eps=pe.norm.eps)
+    _count(3)
+    return x, Hp, Wp, (cols, ypre)
+
+
+def patch_embed_bwd(pe, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace) -> None:
+    """dx fp32 [n, C]: gradient of the patch-embedding output (the pixels need no gradient)."""
+    cols, ypre = saved
+    if not any(p.requires_grad for p in pe.parameters()):
+        return
+    n, C = dx.shape
+    dev = dx.device
+    dyb = ws.get("bw_dyb", (n, C), torch.bfloat16, dev)
+    K.cast_rows_bf16(dx, dyb)
+    if ypre is not None:
+        dpre = ws.get("bw_pe_dpre", (n, C), torch.float32, dev)
+        K.layernorm_rows_bwd(ypre, dyb, pe.norm.weight, dpre, grads.of(pe.norm.weight), grads.of(pe.norm.bias), eps=pe.norm.eps)
+        K.cast_rows_bf16(dpre, dyb)
+        _count(2)
+    if pe.proj.weight.requires_grad:
+        dy_t = _transposed(ws, "bw_dyT", dyb)
+        x_t = _transposed(ws, "bw_xT", cols)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(C, 64, dy_t.shape[1]),), torch.float32, dev)
+        K.gemm_bf16_splitk(dy_t, x_t, grads.padded_cols(pe.proj.weight, 64), part, accumulate=True)
+        _count(4)
+    if pe.proj.bias is not None and pe.proj.bias.requires_grad:
+        K.colsum_accumulate(dyb, grads.of(pe.proj.bias))
+        _count(1)
+    _count(1)
+
+
+# ------------------------------------------------------------------------------------------------
+# SimpleDecoding in training mode (reference lib/mask_predictor.py:56-99, BatchNorm2d batch statistics / SyncBatchNorm train.py:589)
+# ------------------------------------------------------------------------------------------------
+def _world():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def _cbr_fwd(x_nhwc: torch.Tensor, dec, conv_name: str, bn_name: str, ws: Workspace, sync_bn: bool):
+    conv, bn = getattr(dec, conv_name), getattr(dec, bn_name)
+    n, H, W, Cin = x_nhwc.shape
+    dev = x_nhwc.device
+    hid = conv.weight.shape[0]
+    npix = n * H * W
+    w = dec.prepared.get(conv_name, [conv.weight], lambda: E._conv_taps(conv))
+    z = torch.empty(npix, hid, device=dev, dtype=torch.float32)
+    K.conv3x3_bf16(x_nhwc, w, out_f32=z)
+    stats = torch.empty(1, 2, hid, device=dev, dtype=torch.float32)
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(1, npix, hid),), torch.float32, dev)
+    K.instnorm_stats(z.view(1, npix, hid), stats, stw, eps=bn.eps)
+    n_stat = npix
+    dist = _world() if sync_bn else None
+    with torch.no_grad():       # [C]-sized bookkeeping: cross-GPU statistics and the running buffers
+        if dist is not None:
+            mean = stats[0, 0]
+            ex2 = 1.0 / stats[0, 1] ** 2 - bn.eps + mean * mean
+            both = torch.stack([mean, ex2])
+            dist.all_reduce(both)
+            both /= dist.get_world_size()
+            n_stat = npix * dist.get_world_size()
+            stats[0, 0] = both[0]
+            stats[0, 1] = torch.rsqrt((both[1] - both[0] * both[0]).clamp_min(0) + bn.eps)
+        if bn.track_running_stats:
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            var = 1.0 / stats[0, 1] ** 2 - bn.eps
+            bn.running_mean.mul_(1 - mom).add_(stats[0, 0], alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var * (n_stat / max(n_stat - 1, 1)), alpha=mom)
+            bn.num_batches_tracked += 1
+    t = torch.empty(n, H, W, hid, device=dev, dtype=torch.bfloat16)
+    K.bn_relu_apply(z, stats.view(2, hid), bn.weight, bn.bias, t.view(npix, hid))
+    _count(4)
+    return t, (x_nhwc, z, stats.view(2, hid), t, n_stat, conv_name, bn_name)
+
+
+def _cbr_bwd(dec, saved, dt: torch.Tensor, grads: GradStore, ws: Workspace, sync_bn: bool, dx_out: Optional[torch.Tensor]) -> None:
+    """dt bf16 [npix, hid] = gradient of the ReLU output; writes the input gradient (bf16 NHWC) into ``dx_out`` if given."""
+    x_nhwc, z, stats, t, n_stat, conv_name, bn_name = saved
+    conv, bn = getattr(dec, conv_name), getattr(dec, bn_name)
+    n, H, W, Cin = x_nhwc.shape
+    dev = z.device
+    npix, hid = z.shape
+    sums = torch.zeros(2, hid, device=dev, dtype=torch.float32)
+    K.bn_relu_bwd_reduce(dt, t.view(npix, hid), z, stats, sums)
+    with torch.no_grad():
+        dist = _world() if sync_bn else None
+        if dist is not None:
+            dist.all_reduce(sums)
+        if bn.weight.requires_grad:
+            grads.of(bn.weight).add_(sums[1])       # note: with SyncBN every rank holds the GLOBAL sum; the later gradient
+        if bn.bias.requires_grad:                   # all-reduce averages, which reproduces SyncBatchNorm's DDP semantics
+            grads.of(bn.bias).add_(sums[0])
+    dz = ws.get("bw_dz", (n, H, W, hid), torch.bfloat16, dev)
+    K.bn_relu_bwd_apply(dt, t.view(npix, hid), z, stats, bn.weight, sums, dz.view(npix, hid), n_stat)
+    _count(2)
+    if conv.weight.requires_grad:
+        # dW[co, tap, ci] = sum_p dz^T[co, p] x^T[ci, p + (ky-1)*Wp + (kx-1)] over the zero-padded pixel axis (rows of Wp = W+2 rounded
+        # up to 8 columns): the row part of the offset is a 16-byte aligned TMA coordinate, the +-1 part a pre-shifted copy of x^T
+        Wp = _pad8(W + 2)
+        Kp = n * (H + 2) * Wp
+        dz_t = ws.get("bw_dzT", (hid, Kp), torch.bfloat16, dev)
+        dz_t.zero_()
+        K.nhwc_pad_transpose(dz, dz_t, Wp, 0)
+        x_t = ws.get("bw_cxT", (3, Cin, Kp), torch.bfloat16, dev)
+        x_t.zero_()
+        for kx in range(3):
+            K.nhwc_pad_transpose(x_nhwc, x_t[kx], Wp, kx - 1)
+        gbuf = grads.conv_taps(conv.weight)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(hid, Cin, Kp),), torch.float32, dev)
+        for tap in range(9):
+            ky, kx = tap // 3, tap % 3
+            K.gemm_bf16_splitk(dz_t, x_t[kx], gbuf[:, tap * Cin:(tap + 1) * Cin], part, accumulate=True, b_koff=(ky - 1) * Wp)
+        _count(6 + 18)
+    if dx_out is not None:
+        def _wT():
+            wgt = conv.weight.detach()                         # [Cout, Cin, 3, 3] -> [Cin, ((2-ky)*3 + (2-kx))*Cout + co]
+            return wgt.flip(2, 3).permute(1, 2, 3, 0).reshape(wgt.shape[1], -1).to(torch.bfloat16).contiguous()
+        w_t = dec.prepared.get(conv_name + "_wT", [conv.weight], _wT)
+        K.conv3x3_bf16(dz, w_t, out_bf16=dx_out.view(npix, Cin))
+        _count(1)
+
+
+def decoder_fwd(dec, c4, c3, c2, c1, ws: Workspace, sync_bn: bool = False):
+    """NHWC bf16 maps (coarse -> fine) -> (low-resolution logits fp32 [n, H1, W1, 2], saved)."""
+    dev = c1.device
+    n_img = c1.shape[0]
+    hid = dec.conv1_4.weight.shape[0]
+    y = c4
+    levels = []
+    for skip, (ca, ba, cb, bb) in ((c3, ("conv1_4", "bn1_4", "conv2_4", "bn2_4")), (c2, ("conv1_3", "bn1_3", "conv2_3", "bn2_3")),
+                                   (c1, ("conv1_2", "bn1_2", "conv2_2", "bn2_2"))):
+        _, H, W, Cs = skip.shape
+        if y.shape[1] > H or y.shape[2] > W:
+            raise K.LavtError("decoder: coarser map is larger than the skip connection")
+        cat = torch.empty(n_img, H, W, y.shape[-1] + Cs, device=dev, dtype=torch.bfloat16)
+        K.upsample_concat(y, skip, cat)
+        t1, s1 = _cbr_fwd(cat, dec, ca, ba, ws, sync_bn)
+        t2, s2 = _cbr_fwd(t1, dec, cb, bb, ws, sync_bn)
+        levels.append((tuple(y.shape), s1, s2))
+        y = t2
+        _count(1)
+    _, H, W, _ = y.shape
+    w11 = dec.prepared.get("w11", [dec.conv1_1.weight], lambda: _f32(dec.conv1_1.weight.reshape(2, -1)))
+    lg = torch.empty(n_img, H, W, 2, device=dev, dtype=torch.float32)
+    K.conv1x1_logits(y.view(-1, hid), w11, dec.conv1_1.bias.detach(), lg.view(-1, 2))
+    _count(1)
+    return lg, (levels, y, w11)
+
+
+def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, sync_bn: bool = False):
+    """dlg fp32 [n, H1, W1, 2] -> gradients of (c4, c3, c2, c1) as bf16 row views [n*H_i*W_i, C_i] (c3..c1 are column slices of the
+    concatenated-input gradient, i.e. have a row pitch larger than C_i)."""
+    levels, y, w11 = saved
+    dev = dlg.device
+    hid = y.shape[-1]
+    npix = y.shape[0] * y.shape[1] * y.shape[2]
+    dy = ws.get("bw_dec_dy", (npix, hid), torch.bfloat16, dev)
+    K.conv1x1_logits_bwd(dlg.view(-1, 2), y.view(-1, hid), w11, dy, grads.of(dec.conv1_1.weight).view(2, hid), grads.of(dec.conv1_1.bias))
+    _count(1)
+    dskips = []
+    for li in (2, 1, 0):
+        yshape, s1, s2 = levels[li]
+        cat = s1[0]
+        n, H, W, Ct = cat.shape
+        dt1 = ws.get("bw_dec_dt1", (n * H * W, hid), torch.bfloat16, dev)
+        _cbr_bwd(dec, s2, dy, grads, ws, sync_bn, dt1.view(n, H, W, hid))
+        dcat = torch.empty(n, H, W, Ct, device=dev, dtype=torch.bfloat16)
+        _cbr_bwd(dec, s1, dt1, grads, ws, sync_bn, dcat)
+        C1 = yshape[-1]
+        dskips.append(dcat.view(n * H * W, Ct)[:, C1:])
+        dprev = torch.empty(yshape, device=dev, dtype=torch.bfloat16)
+        K.upsample_concat_bwd(dcat, dprev)
+        _count(1)
+        dy = dprev.view(-1, C1)
+    return (dy, dskips[2], dskips[1], dskips[0])       # dc4, dc3, dc2, dc1

@@ -1,0 +1,188 @@
+"""Training step of the video model on the sm_100a kernels (BASELINE config 4: fwd+bwd, gradient all-reduce over NCCL).
+
+Mirrors the inner loop of the reference's ``train_one_epoch_*`` (train.py:330-360, 398-460):
+
+    output = model(image, text, l_mask); loss = criterion(output, target); optimizer.zero_grad(); loss.backward()
+
+* ``segment_forward_backward`` runs the hot path after the text encoder: forward with saved activations, the reference's
+  [0.9, 1.1]-weighted cross-entropy (losses.py:7-11) and the hand-written backward, leaving fp32 gradients in a
+  ``GradStore`` and returning the gradient of the language features.
+* ``SegmentFunction`` exposes the same computation to autograd (``model(x, text, mask)`` in ``model.train()`` mode returns
+  logits whose ``.backward()`` drives the kernels), so that the reference's training loop runs unchanged.
+* ``allreduce_gradients`` is the one collective of the path: bucketed NCCL all-reduce of the parameter gradients
+  (replaces DistributedDataParallel, train.py:590-593).
+
+Not implemented in training mode (raise, no fallback): stochastic depth > 0, --hs / --version variants, SepTPWAM, the 2-D
+image models, windows above ~400 tokens (8x12x12).  The text encoder's own backward runs through the stock ``transformers``
+module under autograd (SURVEY.md section 8f-2 marks the text side as the next row, not the hot path).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _cabi as K
+from . import engine as E
+from . import train_engine as T
+
+
+def _check_trainable(model) -> None:
+    bb = model.backbone
+    for layer in bb.layers:
+        if layer.hs or layer.sep_t_pwam or layer.version != "default":
+            raise NotImplementedError("training on the B200 path supports the default PWAM + LanguageGate configuration only")
+        for blk in layer.blocks:
+            if blk.drop_path_rate > 0:
+                raise NotImplementedError("stochastic depth > 0 is not implemented on the B200 training path (build with drop_path_rate=0)")
+    if tuple(bb.out_indices) != (0, 1, 2, 3):
+        raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
+
+
+def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, sync_bn: bool = False):
+    """Forward of the hot path with saved activations.  x (B,T,3,H,W) fp32; l_feats (B,768,Nl); l_mask (B,Nl[,1]).
+    Returns (logits fp32 (B*T,2,H,W), tape)."""
+    from .lib.video_swin_transformer import _lang, _mask, _planes
+    _check_trainable(model)
+    E.require_cuda(x, "x")
+    bb, dec = model.backbone, model.classifier
+    dev = x.device
+    ws = E.workspace(dev)
+    l = _lang(l_feats)
+    mask = _mask(l_mask)
+    x5 = _planes(x).permute(0, 2, 1, 3, 4)
+    B, _, D, H, W = x5.shape
+    feat, Hc, Wc, pe_saved = T.patch_embed_fwd(x5, bb.patch_embed, ws)
+    stages = []
+    maps = []
+    for i, layer in enumerate(bb.layers):
+        C = layer.dim
+        n = B * D * Hc * Wc
+        xb = torch.empty(n, C, device=dev, dtype=torch.bfloat16)
+        blocks = []
+        for bi, blk in enumerate(layer.blocks):
+            feat, sv = T.swin_block_fwd(feat, blk, B, D, Hc, Wc, layer.window_size, blk.shifted, blk.clamp_window, ws,
+                                        xb_out=xb if bi == layer.depth - 1 else None)
+            blocks.append(sv)
+        last = layer.downsample is None
+        gate = layer.res_gate if (layer.has_gate and not last) else None      # the last stage's gated features are unused (:570-587)
+        r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
+        norm = getattr(bb, f"norm{i}")
+        ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
+        K.layernorm_rows(r32, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
+        E._count(1)
+        maps.append(ob)
+        merge_saved = None
+        if not last:
+            src = xg if xg is not None else feat
+            feat, merge_saved = T.patch_merging_fwd(src, layer.downsample, B, D, Hc, Wc, ws)
+        stages.append((blocks, pw_saved, r32, merge_saved, gate is not None))
+        if not last:
+            Hc, Wc = (Hc + 1) // 2, (Wc + 1) // 2
+    c1, c2, c3, c4 = maps
+    lg, dec_saved = T.decoder_fwd(dec, c4, c3, c2, c1, ws, sync_bn)
+    logits = torch.empty(lg.shape[0], 2, x.shape[-2], x.shape[-1], device=dev, dtype=torch.float32)
+    K.upsample_logits(lg, logits)
+    E._count(1)
+    tape = dict(pe=pe_saved, stages=stages, dec=dec_saved, lg_shape=tuple(lg.shape), l=l, sync_bn=sync_bn)
+    return logits, tape
+
+
+def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> torch.Tensor:
+    """dlogits fp32 (B*T,2,H,W) -> parameter gradients in ``grads``; returns the gradient of l_feats (B,768,Nl)."""
+    bb, dec = model.backbone, model.classifier
+    dev = dlogits.device
+    ws = E.workspace(dev)
+    sync_bn = tape["sync_bn"]
+    dlg = torch.empty(tape["lg_shape"], device=dev, dtype=torch.float32)
+    K.upsample_logits_bwd(dlogits.contiguous(), dlg)
+    E._count(1)
+    dcs = T.decoder_bwd(dec, tape["dec"], dlg, grads, ws, sync_bn)      # (dc4, dc3, dc2, dc1)
+    dl = torch.zeros_like(tape["l"])
+    dx_next: Optional[torch.Tensor] = None
+    for i in range(len(bb.layers) - 1, -1, -1):
+        layer = bb.layers[i]
+        blocks, pw_saved, r32, merge_saved, has_gate = tape["stages"][i]
+        norm = getattr(bb, f"norm{i}")
+        dr = torch.empty_like(r32)
+        K.layernorm_rows_bwd(r32, dcs[3 - i], norm.weight, dr, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
+        E._count(1)
+        dxg = None
+        if merge_saved is not None:
+            dxg = T.patch_merging_bwd(layer.downsample, merge_saved, dx_next, grads, ws)
+        if has_gate:
+            dx = T.pwam_gate_bwd(layer.fusion, layer.res_gate, pw_saved, dr, dxg, grads, ws, dl)
+        else:
+            # no gate on this stage: x feeds the next stage directly, so dxg is the residual-stream gradient itself
+            dx = T.pwam_gate_bwd(layer.fusion, None, pw_saved, dr, dxg, grads, ws, dl)
+        for bi in range(layer.depth - 1, -1, -1):
+            dx = T.swin_block_bwd(layer.blocks[bi], blocks[bi], dx, grads, ws)
+        dx_next = dx
+    T.patch_embed_bwd(bb.patch_embed, tape["pe"], dx_next, grads, ws)
+    return dl
+
+
+def segment_forward_backward(model, x, l_feats, l_mask, target: torch.Tensor, grads: T.GradStore, sync_bn: bool = False,
+                             loss_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One fused fwd + loss + bwd of the hot path.  target int64 (B*T,H,W) in {0,1}.  Returns (loss as a 0-d CUDA tensor, dl_feats)."""
+    logits, tape = segment_forward(model, x, l_feats, l_mask, sync_bn)
+    acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+    K.cross_entropy(logits, target, acc, phase=0)
+    dlogits = torch.empty_like(logits)
+    K.cross_entropy(logits, target, acc, dlogits, gscale=loss_scale, phase=1)
+    E._count(2)
+    dl = segment_backward(model, tape, dlogits, grads)
+    return acc[0] / acc[1], dl
+
+
+class SegmentFunction(torch.autograd.Function):
+    """autograd bridge: logits = SegmentFunction.apply(x, l_feats, l_mask, model, sync_bn).  backward() runs the sm_100a backward,
+    ACCUMULATES the parameter gradients into ``param.grad`` as a side effect (the parameters are not autograd inputs of this
+    node -- there are 450 of them and the kernels never see autograd) and returns the gradient of ``l_feats`` so that the text
+    encoder's autograd graph continues."""
+
+    @staticmethod
+    def forward(ctx, x, l_feats, l_mask, model, sync_bn):
+        logits, tape = segment_forward(model, x.detach(), l_feats.detach(), l_mask, sync_bn)
+        ctx.tape, ctx.model = tape, model
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = T.GradStore()
+        dl = segment_backward(ctx.model, ctx.tape, dlogits.float(), grads)
+        grads.finalize()
+        ctx.tape = None
+        return None, dl, None, None, None
+
+
+def allreduce_gradients(params: List[torch.nn.Parameter], bucket_mb: int = 64) -> None:
+    """Bucketed average of ``param.grad`` over the ranks (NCCL over NVLink; replaces DDP's reducer, train.py:590-593)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    bucket: List[torch.Tensor] = []
+    size = 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+
+    for p in params:
+        if p.grad is None:
+            continue
+        bucket.append(p.grad)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= bucket_mb << 20:
+            flush()
+    flush()

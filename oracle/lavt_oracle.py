@@ -307,10 +307,25 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
 # --------------------------------------------------------------------------------------------
 # A6: SimpleDecoding (lib/mask_predictor.py:56-99), eval-mode BatchNorm
 # --------------------------------------------------------------------------------------------
-def _cbr(x: Tensor, sd, conv: str, bn: str) -> Tensor:
-    x = F.conv2d(x, sd[f"classifier.{conv}.weight"], padding=1)
-    x = F.batch_norm(x, sd[f"classifier.{bn}.running_mean"], sd[f"classifier.{bn}.running_var"],
-                     sd[f"classifier.{bn}.weight"], sd[f"classifier.{bn}.bias"], False, 0.0, 1e-5)
+def _q_bf16(t: Tensor) -> Tensor:
+    """Straight-through bf16 rounding (forward: round to bf16; backward: identity).  Used ONLY by the gradient-parity tests: the
+    gradient of a ReLU network is discontinuous in its inputs (an operand error of relative size eps flips ~eps of the ReLU masks and
+    moves the gradient by ~sqrt(eps) in rel-L2), so a bf16 kernel can only be compared with an oracle that rounds the operands of
+    the ReLU-producing contractions at the same points (conv inputs / weights are bf16 in the kernels, accumulation is fp32)."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _cbr(x: Tensor, sd, conv: str, bn: str, train_bn: bool = False, emulate_bf16: bool = False) -> Tensor:
+    w = sd[f"classifier.{conv}.weight"]
+    if emulate_bf16:
+        x, w = _q_bf16(x), _q_bf16(w)
+    x = F.conv2d(x, w, padding=1)
+    if train_bn:     # model.train(): batch statistics (the running buffers are updated on clones: the oracle stays functional)
+        x = F.batch_norm(x, sd[f"classifier.{bn}.running_mean"].clone(), sd[f"classifier.{bn}.running_var"].clone(),
+                         sd[f"classifier.{bn}.weight"], sd[f"classifier.{bn}.bias"], True, 0.1, 1e-5)
+    else:
+        x = F.batch_norm(x, sd[f"classifier.{bn}.running_mean"], sd[f"classifier.{bn}.running_var"],
+                         sd[f"classifier.{bn}.weight"], sd[f"classifier.{bn}.bias"], False, 0.0, 1e-5)
     return F.relu(x)
 
 
@@ -320,19 +335,28 @@ def _up_to(x: Tensor, ref: Tensor) -> Tensor:
     return x
 
 
-def decoder_forward(sd, x_c4, x_c3, x_c2, x_c1, capture: Optional[dict] = None) -> Tensor:
+def decoder_forward(sd, x_c4, x_c3, x_c2, x_c1, capture: Optional[dict] = None, train_bn: bool = False,
+                    emulate_bf16: bool = False) -> Tensor:
+    tb, eb = train_bn, emulate_bf16
+    q = _q_bf16 if eb else (lambda t: t)      # the kernels hand bf16 maps from level to level
     y = torch.cat([_up_to(x_c4, x_c3), x_c3], 1)
-    y = _cbr(_cbr(y, sd, "conv1_4", "bn1_4"), sd, "conv2_4", "bn2_4")
+    y = q(_cbr(_cbr(y, sd, "conv1_4", "bn1_4", tb, eb), sd, "conv2_4", "bn2_4", tb, eb))
     y = torch.cat([_up_to(y, x_c2), x_c2], 1)
-    y = _cbr(_cbr(y, sd, "conv1_3", "bn1_3"), sd, "conv2_3", "bn2_3")
+    y = q(_cbr(_cbr(y, sd, "conv1_3", "bn1_3", tb, eb), sd, "conv2_3", "bn2_3", tb, eb))
     y = torch.cat([_up_to(y, x_c1), x_c1], 1)
-    y = _cbr(_cbr(y, sd, "conv1_2", "bn1_2"), sd, "conv2_2", "bn2_2")
+    y = q(_cbr(_cbr(y, sd, "conv1_2", "bn1_2", tb, eb), sd, "conv2_2", "bn2_2", tb, eb))
     if capture is not None:
         capture["dec_feat"] = y
     return F.conv2d(y, sd["classifier.conv1_1.weight"], sd["classifier.conv1_1.bias"])
 
 
-def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Tensor, capture: Optional[dict] = None) -> Tensor:
+def weighted_cross_entropy(logits: Tensor, target: Tensor) -> Tensor:
+    """losses.py:7-11: F.cross_entropy with class weights [0.9, 1.1] (mean normalised by the summed weights)."""
+    return F.cross_entropy(logits, target, weight=torch.tensor([0.9, 1.1], dtype=logits.dtype))
+
+
+def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Tensor, capture: Optional[dict] = None,
+                  train_bn: bool = False) -> Tensor:
     """LAVTVideo.forward / LAVTOne.forward minus the (external) BERT call (lib/_utils.py:86-108, 42-63).
     x (B,T,3,H,W) for video, (B,3,H,W) for image; l_feats (B,768,Nl); l_mask (B,Nl) -> logits (B*T,2,H,W)."""
     if cfg.video:
@@ -341,7 +365,7 @@ def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Ten
     c1, c2, c3, c4 = backbone_forward(sd, cfg, x, l_feats, l_mask.unsqueeze(-1), capture)
     if capture is not None:
         capture.update(c1=c1, c2=c2, c3=c3, c4=c4)
-    logits = decoder_forward(sd, c4, c3, c2, c1, capture)
+    logits = decoder_forward(sd, c4, c3, c2, c1, capture, train_bn)
     if capture is not None:
         capture["logits_lowres"] = logits
     return F.interpolate(logits, size=size, mode="bilinear", align_corners=True)
