@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""Training-step benchmark (BASELINE config 4): LAVT-RS Video Swin-B, fwd + weighted CE + bwd in bf16 on the sm_100a kernels,
+4 clips (8x384x384) per GPU, gradient all-reduce over NCCL at N > 1.
+
+    python tools/bench_train.py --steps 5 --warmup 2
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/bench_train.py --gpus 2
+
+One step = what the reference's ``train_one_epoch_ytvos`` does per iteration up to the optimizer (train.py:430-470):
+``optimizer.zero_grad(); output = model(image, text, l_mask); loss = criterion(output, target); loss.backward()`` plus DDP's
+gradient all-reduce.  The text encoder runs as the stock ``transformers`` module under autograd (its input gradient comes from the
+kernels); DropPath is disabled.  Prints one JSON line (same keys as bench.py where they apply).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench as B0  # noqa: E402  (shared helpers: synthetic batch, clocks, peaks)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--clips-per-gpu", type=int, default=4)
+    p.add_argument("--frozen-text", action="store_true", help="do not backpropagate into the text encoder")
+    p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
+    a = p.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from lavt_rs_b200 import _cabi as K
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    from lavt_rs_b200 import training as TR
+    K.check(K.lib().lavt_check_device(), "lavt_check_device")
+
+    model = B0.build_model(False, dev).train()
+    for layer in model.backbone.layers:
+        for blk in layer.blocks:
+            blk.drop_path_rate = 0.0
+    text = model.text_encoder
+    text.eval()          # BERT dropout off: the timed work is identical, the numbers reproducible
+    for prm in text.parameters():
+        prm.requires_grad_(not a.frozen_text)
+    params = [prm for prm in model.parameters() if prm.requires_grad]
+
+    Bc = a.clips_per_gpu
+    batches = []
+    for s in range(2):
+        x, ids, m = B0.synth_batch(Bc, 1 + s + 10 * rank)
+        g = torch.Generator().manual_seed(77 + s + 10 * rank)
+        tgt = torch.randint(0, 2, (Bc * B0.T_FRAMES, B0.IMG, B0.IMG), generator=g)
+        batches.append((x.to(dev), ids.to(dev), m.to(dev), tgt.to(dev)))
+
+    state = {}
+
+    def step(i):
+        x, ids, m, tgt = batches[i % 2]
+        for prm in params:
+            prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
+        l_feats = text(ids, attention_mask=m)[0].permute(0, 2, 1)             # lib/_utils.py:98-100
+        grads = T.GradStore()
+        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1)
+        grads.finalize()
+        if not a.frozen_text:
+            l_feats.backward(dl)
+        TR.allreduce_gradients(params)
+        state["loss"] = loss
+
+    def timed(steps, warmup):
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    E.LAUNCHES = 0
+    step(0)
+    torch.cuda.synchronize()
+    launches = E.LAUNCHES
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    clocks = B0.ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(a.steps, max(a.warmup, 3))
+    clk = clocks.stop() if rank == 0 else None
+
+    fam = None
+    if rank == 0:
+        K.TIMER.enabled = True
+        K.TIMER.records.clear()
+        step(0)
+        pk, pk_kind = B0.peaks()
+        fam = K.TIMER.summary(pk.get("bf16_tflops_sustained", 1400.0), pk.get("hbm_gbs", 6550.0))
+        K.TIMER.enabled = False
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total = Bc * world
+    value = total * a.steps / (ms * 1e-3)
+    flops_clip = 3.0 * (2074.8e9 - 3.4e9)          # forward + input gradients + weight gradients of every contraction
+    g = fam.get("gemm_bf16_tc_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    ab = fam.get("window_attn_bwd_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    af = fam.get("window_attn_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    res = {
+        "metric": "LAVT-RS train step clips/s (fwd+bwd, 8x384^2)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "LAVT-RS Video Swin-B training step: BERT-base + backbone + decoder forward, [0.9,1.1]-weighted CE, backward, "
+                               "gradient all-reduce; 8x384x384 clips, 20-token expression, window 8x7x7, DropPath off, no optimizer update",
+                   "clips_per_gpu_per_step": Bc, "global_clips_per_step": total,
+                   "parallelism": f"data-parallel x{world}" + (", NCCL gradient all-reduce + SyncBN statistics" if world > 1 else ""),
+                   "text_encoder": "frozen" if a.frozen_text else "transformers BertModel under autograd (fp32)",
+                   "l2": "two rotating batches; saved activations (> 10 GB) exceed the 126 MB L2", "flops_per_clip": flops_clip},
+        "clocks": clk, "loss": float(state["loss"].item()), "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
+        "peak_memory_bytes": peak_mem,
+        "roofline": {"kernel": "gemm_bf16_tc_kernel (forward GEMMs / convs, input-gradient GEMMs / convs, split-K weight-gradient GEMMs)",
+                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None, "launches": g["launches"], "ms_per_step": g["ms"],
+                     "alg_flops_per_step": g["flops"],
+                     "attention_bwd": {"kernel": "window_attn_bwd_kernel (mma.sync)", "launches": ab["launches"], "ms_per_step": ab["ms"],
+                                       "tflops": ab["flops"] / (ab["ms"] * 1e-3) / 1e12 if ab["ms"] > 0 else 0.0},
+                     "attention_fwd": {"launches": af["launches"], "ms_per_step": af["ms"]},
+                     "whole_step_tflops": flops_clip * value / world / 1e12},
+    }
+    if a.cpu_baseline and world == 1:
+        from oracle import lavt_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        cfg = O.OracleConfig.swin("base", window12=False, video=True)
+        sd = {k: v.detach().float().cpu().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in model.state_dict().items()}
+        x, ids, m = B0.synth_batch(1, 100)
+        tgt = torch.randint(0, 2, (B0.T_FRAMES, B0.IMG, B0.IMG))
+        l = torch.randn(1, 768, B0.NL)
+        t0 = time.perf_counter()
+        out = O.model_forward(sd, cfg, x, l, m, train_bn=True)
+        O.weighted_cross_entropy(out, tgt).backward()
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "1 clip (8x384x384), 1 fwd+bwd after BERT, fp32, autograd through the oracle port on torch CPU"}
+    print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
