@@ -48,3 +48,34 @@ def test_world_size_two_gloo():
     merged = out[0][1] + out[1][1]
     assert merged == [i * i for i in range(13)]
     assert out[0][2] == [7, 6] and out[0][3] == out[1][3] == 11.0
+
+
+def _grad_worker(rank, world, port, q):
+    """training.allreduce_gradients: bucketed average of param.grad over the ranks (the one collective of the training path)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lavt_rs_b200.training import allreduce_gradients
+    g = torch.Generator().manual_seed(5)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (2, 2, 2), (300000,), (11,))]
+    base = [torch.randn(p.shape, generator=g) for p in params]
+    for p, b in zip(params, base):
+        p.grad = b * (rank + 1)            # rank r holds (r + 1) * base -> the average is 1.5 * base for two ranks
+    params[2].grad = None                   # a parameter without gradient (frozen / dead) is skipped, not all-reduced
+    allreduce_gradients(params, bucket_mb=1)        # 1 MiB buckets: the 300 000-element tensor forces several flushes
+    ok = all(torch.allclose(p.grad, 1.5 * b, rtol=1e-6, atol=1e-6) for p, b in zip(params, base) if p.grad is not None)
+    q.put((rank, ok, params[2].grad is None))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31511 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and none_kept for _, ok, none_kept in out)
