@@ -116,14 +116,16 @@ def main():
     ms = timed(a.steps, max(a.warmup, 3))
     clk = clocks.stop() if rank == 0 else None
 
+    # roofline leg: per-launch CUDA events on rank 0; EVERY rank runs the step (it contains collectives)
     fam = None
+    K.TIMER.enabled = rank == 0
+    K.TIMER.records.clear()
+    step(0)
+    torch.cuda.synchronize()
     if rank == 0:
-        K.TIMER.enabled = True
-        K.TIMER.records.clear()
-        step(0)
         pk, pk_kind = B0.peaks()
         fam = K.TIMER.summary(pk.get("bf16_tflops_sustained", 1400.0), pk.get("hbm_gbs", 6550.0))
-        K.TIMER.enabled = False
+    K.TIMER.enabled = False
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
