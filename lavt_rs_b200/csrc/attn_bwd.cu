@@ -9,9 +9,10 @@
 //
 // One persistent CTA walks (head, window) units; Q, K, V, dO of the unit live in shared memory (cp.async, 64-byte rows with
 // the xor chunk swizzle of attn_window.cu).  Main loop: a warp OWNS a 16-key tile (dK, dV accumulate in registers across
-// all query blocks; S^T = K Q^T and dP^T = V dO^T make P^T / dZ^T come out of the MMA already in A-fragment layout), dQ^T =
-// K^T dZ^T uses movmatrix to turn the dZ^T accumulator into a B fragment and is reduced across warps with shared-memory
-// fp32 atomics, as is the relative-position-bias gradient (one table copy per CTA, flushed when the head changes).
+// all query blocks; S^T = K Q^T and dP^T = V dO^T make P^T / dZ^T come out of the MMA already in A-fragment layout); a second
+// pass with a warp owning 16 QUERY rows recomputes S / dP / dZ and accumulates dQ in registers (a first version reduced dQ^T =
+// K^T dZ^T across the key-owning warps with shared fp32 atomics: 36 ms per training step vs the recomputation's cost).  The
+// relative-position-bias gradient accumulates in one table copy per CTA (shared atomics), flushed when the head changes.
 #include "kernels.cuh"
 
 namespace lavt {
@@ -20,7 +21,6 @@ constexpr int AB_HD = 32;
 constexpr float AB_LOG2E = 1.4426950408889634f;
 constexpr float AB_MASKV = -100.0f * AB_LOG2E;
 constexpr int AB_WARPS = 16;
-constexpr int AB_DQ_PITCH = 36;      // floats per dQ row: (hd = g, query = 2t) atomics of a warp hit 32 distinct banks
 
 __device__ __forceinline__ int ab_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ float ab_ex2(float x) {
@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
   uint8_t* sK = sQ + NP * 64;
   uint8_t* sV = sK + NP * 64;
   uint8_t* sD = sV + NP * 64;
-  float* sdQ = reinterpret_cast<float*>(sD + NP * 64);               // [NP][36]
-  AbTok* tok = reinterpret_cast<AbTok*>(sdQ + NP * AB_DQ_PITCH);    // [NP]
+  AbTok* tok = reinterpret_cast<AbTok*>(sD + NP * 64);               // [NP]
   float* tab = reinterpret_cast<float*>(tok + NP);                   // [L]  table * log2 e of the current head
   float* dtab = tab + L;                                             // [L]  gradient accumulator of the current head
+  int* work_ctr = reinterpret_cast<int*>(dtab + L);                  // dynamic work-list cursor of the current unit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
     const int head = u / nwin, win = u - head * nwin;
     const long long row0 = static_cast<long long>(win) * N;
     __syncthreads();                                       // previous unit finished with every buffer
+    if (threadIdx.x == 0) *work_ctr = 0;
     if (head != cur_head) {
       if (cur_head >= 0 && p.dtable_t)
         for (int i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(p.dtable_t + static_cast<long long>(cur_head) * L + i, dtab[i]);
@@ -85,7 +86,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
       cp_async_16(ab_smem + which * NP * 64 + ab_off(row, ch), src, in);
     }
     cp_async_commit();
-    for (int i = threadIdx.x; i < NP * AB_DQ_PITCH; i += blockDim.x) sdQ[i] = 0.f;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
       AbTok a;
       a.code = 0; a.rid = -1; a.lse = 0.f; a.delta = 0.f;
@@ -168,18 +168,24 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
       }
     }
     __syncthreads();
-    // ---- main pass: warp owns a 16-key tile
-    for (int jt = warp; jt < NP / 16; jt += AB_WARPS) {
+    // ---- main pass (items 0 .. T-1: a warp owns a 16-key tile) and pass 2 (items T .. 2T-1: a warp owns 16 query rows) share one
+    //      dynamically scheduled work list: the two passes are independent of each other, and T = 25 tiles over 16 warps would
+    //      otherwise idle 7 warps for half of each pass (ncu: barrier was the second largest stall reason)
+    const int T = NP / 16;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(work_ctr, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= 2 * T) break;
+      if (item < T) {
+      const int jt = item;
       const int j0 = jt * 16;
-      uint32_t kA[2][4], vA[2][4], kT[2][4];
+      uint32_t kA[2][4], vA[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         ldmatrix_x4(kA[ks], sK + ab_off(j0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
         ldmatrix_x4(vA[ks], sV + ab_off(j0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
       }
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)   // A = K^T: rows = head-dim 16*mt.., k = the 16 keys
-        ldmatrix_x4_trans(kT[mt], sK + ab_off(j0 + (lane & 7) + (lane >> 4) * 8, 2 * mt + ((lane >> 3) & 1)));
       const AbTok k0 = tok[j0 + g], k1 = tok[j0 + g + 8];
       const bool kv0 = j0 + g < N, kv1 = j0 + g + 8 < N;
       float dK[4][4], dV[4][4];
@@ -240,22 +246,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
           mma_bf16_16816(dK[dpair * 2 + 0], aZ, bf[0], bf[1]);
           mma_bf16_16816(dK[dpair * 2 + 1], aZ, bf[2], bf[3]);
         }
-        // dQ^T[hd, query] += K^T[hd, key] dZ^T[key, query]
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t b0 = movmatrix_trans(pZ[h][0]), b1 = movmatrix_trans(pZ[h][1]);
-          const int i = qb * 16 + h * 8 + 2 * t;
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16_16816(c, kT[mt], b0, b1);
-            float* d0 = sdQ + i * AB_DQ_PITCH + mt * 16 + g;
-            atomicAdd(d0, c[0]);
-            atomicAdd(d0 + AB_DQ_PITCH, c[1]);
-            atomicAdd(d0 + 8, c[2]);
-            atomicAdd(d0 + AB_DQ_PITCH + 8, c[3]);
-          }
-        }
       }
       // dy_k = dZ^T q' / log2 e  (q' = y_q hd^-0.5 log2 e),  dy_v = P^T dO
 #pragma unroll
@@ -269,13 +259,73 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
           *reinterpret_cast<uint32_t*>(dst + 2 * C + nt * 8) = pack_bf16x2(dV[nt][2 * r], dV[nt][2 * r + 1]);
         }
       }
-    }
-    __syncthreads();
-    // ---- dy_q = hd^-0.5 dZ K
-    for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
-      const int row = i >> 4, c2 = (i & 15) * 2;
-      const float* s = sdQ + row * AB_DQ_PITCH + c2;
-      *reinterpret_cast<uint32_t*>(p.dqkv + (row0 + row) * (3 * C) + head * AB_HD + c2) = pack_bf16x2(s[0] * p.qscale, s[1] * p.qscale);
+      } else {
+      // ---- pass 2: dy_q = hd^-0.5 dZ K with a warp OWNING 16 query rows (S, dP, dZ recomputed; dQ accumulates in registers --
+      //      reducing dQ across the key-owning warps of the main pass with shared fp32 atomics cost more than this recomputation)
+      const int qt = item - T;
+      const int i0 = qt * 16;
+      uint32_t qf[2][4], df[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        ldmatrix_x4(qf[ks], sQ + ab_off(i0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
+        ldmatrix_x4(df[ks], sD + ab_off(i0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
+      }
+      const AbTok q0 = tok[i0 + g], q1 = tok[i0 + g + 8];
+      const float* tq0 = tab + q0.code + rc;
+      const float* tq1 = tab + q1.code + rc;
+      float dQ[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dQ[a][b] = 0.f;
+      for (int jb = 0; jb < NP / 16; ++jb) {
+        uint32_t aZ[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j0 = jb * 16 + h * 8;
+          uint32_t kf[4], vf[4];
+          ldmatrix_x4(kf, sK + ab_off(j0 + (lane & 7), lane >> 3));
+          ldmatrix_x4(vf, sV + ab_off(j0 + (lane & 7), lane >> 3));
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(s, qf[0], kf[0], kf[1]);
+          mma_bf16_16816(s, qf[1], kf[2], kf[3]);
+          mma_bf16_16816(dp, df[0], vf[0], vf[1]);
+          mma_bf16_16816(dp, df[1], vf[2], vf[3]);
+          float zv[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = j0 + 2 * t + e;
+            const AbTok kj = tok[j];
+            const bool ok = j < N;
+            float z0 = s[e] + tq0[-kj.code] - q0.lse, z1 = s[2 + e] + tq1[-kj.code] - q1.lse;
+            if (need_mask) {
+              if (kj.rid != q0.rid) z0 += AB_MASKV;
+              if (kj.rid != q1.rid) z1 += AB_MASKV;
+            }
+            zv[e] = ok ? ab_ex2(z0) * (dp[e] - q0.delta) : 0.f;
+            zv[2 + e] = ok ? ab_ex2(z1) * (dp[2 + e] - q1.delta) : 0.f;
+          }
+          aZ[2 * h] = pack_bf16x2(zv[0], zv[1]);
+          aZ[2 * h + 1] = pack_bf16x2(zv[2], zv[3]);
+        }
+#pragma unroll
+        for (int dpair = 0; dpair < 2; ++dpair) {
+          uint32_t bf[4];
+          ldmatrix_x4_trans(bf, sK + ab_off(jb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dpair * 2 + (lane >> 4)));
+          mma_bf16_16816(dQ[dpair * 2 + 0], aZ, bf[0], bf[1]);
+          mma_bf16_16816(dQ[dpair * 2 + 1], aZ, bf[2], bf[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = i0 + g + 8 * r;
+        if (i >= N) continue;
+        __nv_bfloat16* dst = p.dqkv + (row0 + i) * (3 * C) + head * AB_HD + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(dQ[nt][2 * r] * p.qscale, dQ[nt][2 * r + 1] * p.qscale);
+      }
+      }
     }
   }
   __syncthreads();
@@ -288,8 +338,7 @@ int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st) {
   LAVT_REQUIRE(p.C == p.nH * AB_HD, "attention backward: head_dim must be 32 (C=%d, heads=%d)", p.C, p.nH);
   LAVT_REQUIRE(w.N > 0 && w.N == w.wd * w.wh * w.ww, "attention backward: bad window geometry");
   const int NP = (w.N + 15) / 16 * 16;
-  const size_t smem = static_cast<size_t>(NP) * 64 * 4 + static_cast<size_t>(NP) * AB_DQ_PITCH * 4 + static_cast<size_t>(NP) * sizeof(AbTok) +
-                      static_cast<size_t>(p.L) * 8;
+  const size_t smem = static_cast<size_t>(NP) * 64 * 4 + static_cast<size_t>(NP) * sizeof(AbTok) + static_cast<size_t>(p.L) * 8 + 16;
   LAVT_REQUIRE(smem <= 227 * 1024, "attention backward: window of %d tokens (table %d) needs %zu B of shared memory; windows above ~400 "
                "tokens (8x12x12) are not supported by the training path yet", w.N, p.L, smem);
   static size_t configured = 0;
