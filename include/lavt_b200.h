@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LAVT_ABI_VERSION 1
+#define LAVT_ABI_VERSION 2
 
 #define LAVT_ERR_SHAPE 1
 #define LAVT_ERR_CUDA 2
@@ -43,7 +43,7 @@ typedef struct lavt_win_geom {
 } lavt_win_geom_t;
 
 /* Fused GEMM epilogue:
- *   out[orow(m), n] = act(acc[m,n] * cscale[n] + bias[n]) * mul[m,n] + resid[orow(m), n]
+ *   out[orow(m), n] = act(acc[m,n] * cscale[n] + bias[n]) * mul[m,n] * rscale[orow(m) / rscale_rows] + resid[orow(m), n]
  * orow = m, or (win != NULL) the token row that window-row m maps back to (window_reverse +
  * reverse cyclic shift + crop, lib/video_swin_transformer.py:238-247); pad rows are dropped. */
 typedef struct lavt_epilogue {
@@ -58,6 +58,10 @@ typedef struct lavt_epilogue {
   int32_t ldo;           /* row pitch of resid / out (elements) */
   int32_t _pad;
   const lavt_win_geom_t* win; /* HOST pointer or NULL */
+  const float* rscale;   /* fp32 per-sample scale of the whole branch, or NULL: DropPath in training (timm drop_path as used at
+                            lib/video_swin_transformer.py:266,271: 0 or 1/keep_prob per clip); sample = output row / rscale_rows */
+  int32_t rscale_rows;
+  int32_t _pad2;
 } lavt_epilogue_t;
 
 const char* lavt_last_error(void);
@@ -190,6 +194,9 @@ int lavt_colsum_accumulate(const void* x, int32_t is_bf16, int64_t ldx, int64_t 
 /* out bf16 [M, C] = x[src(m)]: src = m, or (geom != NULL) the token of window row m, pad rows -> 0.  Adjoint of the proj
  * epilogue's window_reverse + un-shift + crop scatter (lib/video_swin_transformer.py:238-247). */
 int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream);
+/* same with a per-sample scale: out = x[src(m)] * rscale[src(m) / rscale_rows] (adjoint of the epilogue's rscale: DropPath backward) */
+int lavt_cast_rows_scaled_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
+                               int32_t rscale_rows, void* out_bf16, void* stream);
 /* exact-erf GELU on a saved bf16 pre-activation and its derivative (Mlp.act, lib/video_swin_transformer.py:33) */
 int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream);
 int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_t count, void* stream);
@@ -265,6 +272,23 @@ int lavt_upsample_logits_bwd(const float* dout, float* din, int32_t n_img, int32
  * phase 1: dlogits = gscale * w[t] * (softmax - onehot) / acc[1] */
 int lavt_cross_entropy(const float* logits, const int64_t* target, float w0, float w1, float* acc, float* dlogits, float gscale, int32_t n_img,
                        int32_t H, int32_t W, int32_t phase, void* stream);
+
+/* ---- optimizer (train.py:688-699: torch.optim.AdamW over the reference's parameter groups + polynomial LR decay) ---- */
+typedef struct lavt_adamw_tensor {
+  float* p;          /* parameter (fp32, updated in place) */
+  const float* g;    /* gradient */
+  float* m;          /* exp_avg */
+  float* v;          /* exp_avg_sq */
+  float* vmax;       /* max_exp_avg_sq (AMSGrad) or NULL */
+  int64_t n;         /* elements */
+  float bc1, bc2;    /* bias corrections 1 - beta_k^step of THIS tensor (torch keeps one step counter per parameter) */
+} lavt_adamw_tensor_t;
+/* elements handled per thread block; block_prefix[i] = sum_{j<i} ceil(n_j / chunk), n_blocks = block_prefix[n_tensors] */
+int lavt_adamw_chunk_elems(void);
+/* One AdamW step for all tensors of a parameter group in one launch (table / prefix are DEVICE arrays).  torch.optim.AdamW
+ * semantics: p *= 1 - lr*wd; m, v moment updates; p -= lr/bc1 * m / (sqrt(v or vmax)/sqrt(bc2) + eps), bc_k = 1 - beta_k^step. */
+int lavt_adamw_step(const lavt_adamw_tensor_t* table_dev, const int32_t* block_prefix_dev, int32_t n_tensors, int32_t n_blocks,
+                    float lr, double beta1, double beta2, float eps, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

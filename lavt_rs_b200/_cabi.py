@@ -38,6 +38,7 @@ class Epilogue(C.Structure):
         ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
         ("ldo", C.c_int32), ("_pad", C.c_int32),
         ("win", C.POINTER(WinGeom)),
+        ("rscale", C.c_void_p), ("rscale_rows", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -66,7 +67,7 @@ def lib() -> C.CDLL:
     return l
 
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 _EP = C.POINTER(Epilogue)
@@ -101,6 +102,7 @@ SIGNATURES = {
     "lavt_transpose_bf16": [_vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
+    "lavt_cast_rows_scaled_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _i32, _vp, _vp],
     "lavt_gelu_fwd": [_vp, _vp, _i64, _vp],
     "lavt_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
@@ -120,9 +122,10 @@ SIGNATURES = {
     "lavt_conv1x1_logits_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_cross_entropy": [_vp, _vp, _f32, _f32, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
-           "lavt_gemm_splitk_workspace_floats",
+           "lavt_gemm_splitk_workspace_floats", "lavt_adamw_chunk_elems",
            *SIGNATURES.keys()]
 
 
@@ -132,6 +135,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_instnorm_workspace_floats.restype = C.c_int64
     l.lavt_gemm_splitk_workspace_floats.argtypes = [_i32, _i32, _i32]
     l.lavt_gemm_splitk_workspace_floats.restype = C.c_int64
+    l.lavt_adamw_chunk_elems.argtypes = []
+    l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
     l.lavt_set_attention_impl.restype = C.c_int
     for name, argtypes in SIGNATURES.items():
@@ -164,7 +169,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def make_epilogue(*, cscale=None, bias=None, act=ACT_NONE, mul=None, resid=None,
-                  out_f32=None, out_bf16=None, ldo=None, win: Optional[WinGeom] = None) -> Epilogue:
+                  out_f32=None, out_bf16=None, ldo=None, win: Optional[WinGeom] = None, rscale=None, rscale_rows: int = 0) -> Epilogue:
     e = Epilogue()
     for name, t in (("cscale", cscale), ("bias", bias), ("resid", resid), ("out_f32", out_f32)):
         if t is not None:
@@ -186,6 +191,11 @@ def make_epilogue(*, cscale=None, bias=None, act=ACT_NONE, mul=None, resid=None,
         if t is not None and t.stride(-2) != e.ldo:
             raise LavtError("resid / out_f32 / out_bf16 must share one row pitch")
     e.win = C.pointer(win) if win is not None else None
+    if rscale is not None:
+        _req(rscale, torch.float32, "rscale")
+        if rscale_rows <= 0:
+            raise LavtError("rscale needs rscale_rows > 0")
+        e.rscale, e.rscale_rows = rscale.data_ptr(), int(rscale_rows)
     return e
 
 
@@ -536,12 +546,15 @@ def colsum_accumulate(x: torch.Tensor, dst: torch.Tensor) -> None:
                                        _c(dst, torch.float32, "dst").data_ptr(), stream_ptr()), "lavt_colsum_accumulate")
 
 
-def cast_rows_bf16(x: torch.Tensor, out: torch.Tensor, geom: Optional[WinGeom] = None) -> None:
-    """out bf16 [M, C] = x fp32 rows (identity) or gathered into window order (pad rows zero)."""
+def cast_rows_bf16(x: torch.Tensor, out: torch.Tensor, geom: Optional[WinGeom] = None, rscale: Optional[torch.Tensor] = None,
+                   rscale_rows: int = 0) -> None:
+    """out bf16 [M, C] = x fp32 rows (identity) or gathered into window order (pad rows zero), optionally times a per-sample scale
+    rscale[source row // rscale_rows] (DropPath backward)."""
     _req(x, torch.float32, "x")
     M, Cn = out.shape
-    check(lib().lavt_cast_rows_bf16(x.data_ptr(), x.stride(0), M, Cn, C.byref(geom) if geom is not None else None,
-                                    _c(out, torch.bfloat16, "out").data_ptr(), stream_ptr()), "lavt_cast_rows_bf16")
+    check(lib().lavt_cast_rows_scaled_bf16(x.data_ptr(), x.stride(0), M, Cn, C.byref(geom) if geom is not None else None,
+                                           ptr(rscale), int(rscale_rows), _c(out, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+          "lavt_cast_rows_scaled_bf16")
 
 
 def gelu_fwd(x: torch.Tensor, y: torch.Tensor) -> None:

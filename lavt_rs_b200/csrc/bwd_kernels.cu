@@ -129,7 +129,8 @@ int colsum_dispatch(const void* x, int is_bf16, long long ldx, long long M, int 
 // ---------------------------------------------------------------------------------------------
 // out[m, :] = bf16(x[src(m), :]);  src = identity, or the token of window row m (pad rows -> 0)
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
-                                                        long long M, int C, const WinGeom win, const int use_win) {
+                                                        long long M, int C, const WinGeom win, const int use_win,
+                                                        const float* __restrict__ rscale, const int rs_rows) {
   const int lane = threadIdx.x & 31;
   const long long m0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 32;
   if (m0 >= M) return;
@@ -139,24 +140,26 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
     const long long m = m0 + r;
     if (m >= M) break;
     const long long row = __shfl_sync(0xffffffffu, myrow, r);
+    const float sc = (rscale && row >= 0) ? __ldg(rscale + row / rs_rows) : 1.0f;
     for (int c4 = lane; c4 < C / 4; c4 += 32) {
       uint2 o = make_uint2(0u, 0u);
       if (row >= 0) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c4);
-        o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        o = make_uint2(pack_bf16x2(v.x * sc, v.y * sc), pack_bf16x2(v.z * sc, v.w * sc));
       }
       reinterpret_cast<uint2*>(out + m * C)[c4] = o;
     }
   }
 }
 
-int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, cudaStream_t st) {
+int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, const float* rscale,
+                       int rs_rows, cudaStream_t st) {
   LAVT_REQUIRE(M > 0 && C % 4 == 0 && ldx % 4 == 0, "cast rows: channels / pitch must be multiples of 4");
   WinGeom g{};
   if (win) g = *win;
   const long long blocks = (M + 255) / 256;
   LAVT_REQUIRE(blocks < (1LL << 31), "cast rows: too many rows");
-  cast_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, ldx, out, M, C, g, win ? 1 : 0);
+  cast_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, ldx, out, M, C, g, win ? 1 : 0, rscale, rs_rows);
   LAVT_LAUNCH_CHECK("cast_rows_kernel");
   return LAVT_OK;
 }

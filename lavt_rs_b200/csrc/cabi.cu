@@ -24,6 +24,9 @@ static int fill_epilogue(GemmParams& p, const lavt_epilogue_t* e) {
   p.out_f32 = e->out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(e->out_bf16);
   p.ldo = e->ldo;
+  p.rscale = e->rscale;
+  p.rs_rows = e->rscale_rows;
+  LAVT_REQUIRE(!e->rscale || e->rscale_rows > 0, "epilogue: rscale needs rscale_rows > 0");
   LAVT_REQUIRE(e->act >= 0 && e->act <= 3, "bad activation id %d", e->act);
   if (e->win) {
     p.rowmap = ROWMAP_WINDOW;
@@ -277,13 +280,18 @@ int lavt_colsum_accumulate(const void* x, int32_t is_bf16, int64_t ldx, int64_t 
   return colsum_dispatch(x, is_bf16, ldx, M, N, dst, S(stream));
 }
 
-int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream) {
+int lavt_cast_rows_scaled_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
+                               int32_t rscale_rows, void* out_bf16, void* stream) {
   WinGeom g;
   if (geom) {
     std::memcpy(&g, geom, sizeof(g));
     LAVT_REQUIRE(M == 1LL * g.B * g.nwd * g.nwh * g.nww * g.N, "cast rows: M does not match the window geometry");
   }
-  return cast_rows_dispatch(x, ldx, MB(out_bf16), M, C, geom ? &g : nullptr, S(stream));
+  LAVT_REQUIRE(!rscale || rscale_rows > 0, "cast rows: rscale needs rscale_rows > 0");
+  return cast_rows_dispatch(x, ldx, MB(out_bf16), M, C, geom ? &g : nullptr, rscale, rscale_rows, S(stream));
+}
+int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream) {
+  return lavt_cast_rows_scaled_bf16(x, ldx, M, C, geom, nullptr, 0, out_bf16, stream);
 }
 
 int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream) {

@@ -318,6 +318,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       const bool live = (orow >= 0);
+      const float row_scale = (p.rscale && live) ? __ldg(p.rscale + orow / p.rs_rows) : 1.0f;
       const __nv_bfloat16* mul_row = (p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
       const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
       float* of_row = (p.out_f32 && live) ? p.out_f32 + ks * p.split_stride + orow * p.ldo + n0 : nullptr;
@@ -385,6 +386,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               f[q * 16 + 2 * j + 1] *= a.y;
             }
           }
+        }
+        if (p.rscale) {       // DropPath: the whole branch of a dropped sample is scaled (0 or 1 / keep_prob) before the shortcut add
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= row_scale;
         }
         if (res_row) {
 #pragma unroll

@@ -8,7 +8,7 @@ namespace lavt {
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
 enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2 };
 
-// out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] + resid[orow(m), n]
+// out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] * rscale[orow(m) / rs_rows] + resid[orow(m), n]
 struct GemmParams {
   int M, N, K;               // logical problem (conv: M = pixels, K = taps*Cin)
   // ---- epilogue ----
@@ -21,6 +21,8 @@ struct GemmParams {
   float* out_f32;            // [rows_out, ldo] or nullptr
   __nv_bfloat16* out_bf16;   // [rows_out, ldo] or nullptr
   int ldo;
+  const float* rscale;       // per-sample scale of the branch (stochastic depth in training), indexed by output row / rs_rows; or nullptr
+  int rs_rows;
   // ---- row map ----
   int rowmap;                // GemmRowMap
   WinGeom win;               // ROWMAP_WINDOW

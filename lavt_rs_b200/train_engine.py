@@ -145,10 +145,20 @@ def linear_bwd(dy: torch.Tensor, x: Optional[torch.Tensor], weight: torch.Tensor
 # ------------------------------------------------------------------------------------------------
 # Swin block  (reference SwinTransformerBlock3D.forward, lib/video_swin_transformer.py:214-273)
 # ------------------------------------------------------------------------------------------------
+def draw_drop_path(rate: float, B: int, device) -> Optional[torch.Tensor]:
+    """timm DropPath as the reference uses it (lib/video_swin_transformer.py:210, 266, 271): one Bernoulli(keep) draw per sample,
+    scaled by 1 / keep.  Returns the fp32 [B] branch scale, or None when the rate is 0."""
+    if rate <= 0.0:
+        return None
+    keep = 1.0 - rate
+    return torch.empty(B, device=device, dtype=torch.float32).bernoulli_(keep).div_(keep)
+
+
 def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shifted: bool, clamp: bool, ws: Workspace,
-                   xb_out: Optional[torch.Tensor] = None):
+                   xb_out: Optional[torch.Tensor] = None, drop_scales=None):
     """x fp32 [B*D*H*W, C] (not modified) -> (x_out, saved).  Same kernels as ``engine.swin_block`` except that fc1 stores
-    its pre-activation (GELU runs as its own kernel) and nothing is overwritten."""
+    its pre-activation (GELU runs as its own kernel) and nothing is overwritten.  ``drop_scales`` = (attention-branch scale,
+    MLP-branch scale), fp32 [B] each or None (stochastic depth; drawn here from the block's rate when not given)."""
     n, C = x.shape
     dev = x.device
     geom = window_geometry(B, D, H, W, window, shifted, clamp)
@@ -169,6 +179,11 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     fc2_w = pw.get("fc2_w", [blk.mlp.fc2.weight], lambda: _bf16(blk.mlp.fc2.weight))
     table_t = pw.get("table_t", [blk.attn.relative_position_bias_table], lambda: _f32(blk.attn.relative_position_bias_table.t()))
     hidden = fc1_w.shape[0]
+    if drop_scales is None:
+        rate = float(getattr(blk, "drop_path_rate", 0.0)) if blk.training else 0.0
+        drop_scales = (draw_drop_path(rate, B, dev), draw_drop_path(rate, B, dev))      # two independent draws, like the two DropPath calls
+    s_attn, s_mlp = drop_scales
+    tok = D * H * W
 
     xw = torch.empty(rows, C, device=dev, dtype=torch.bfloat16)
     K.layernorm_window_gather(x, geom, blk.norm1.weight, blk.norm1.bias, xw, eps=blk.norm1.eps)
@@ -177,7 +192,7 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     att = torch.empty(rows, C, device=dev, dtype=torch.bfloat16)
     K.window_attention(qkv, table_t, geom, att)
     x1 = torch.empty_like(x)
-    K.gemm_bf16(att, proj_w, bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x1, win=geom)
+    K.gemm_bf16(att, proj_w, bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x1, win=geom, rscale=s_attn, rscale_rows=tok)
     h1 = torch.empty(n, C, device=dev, dtype=torch.bfloat16)
     K.layernorm_rows(x1, blk.norm2.weight, blk.norm2.bias, out_bf16=h1, eps=blk.norm2.eps)
     hpre = torch.empty(n, hidden, device=dev, dtype=torch.bfloat16)
@@ -185,14 +200,14 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     hid = torch.empty(n, hidden, device=dev, dtype=torch.bfloat16)
     K.gelu_fwd(hpre, hid)
     x2 = torch.empty_like(x)
-    K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x1, out_f32=x2, out_bf16=xb_out)
+    K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x1, out_f32=x2, out_bf16=xb_out, rscale=s_mlp, rscale_rows=tok)
     _count(8)
-    return x2, (x, xw, qkv, att, x1, h1, hpre, hid, geom, table_t)
+    return x2, (x, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok)
 
 
 def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace) -> torch.Tensor:
     """dx fp32 [n, C] = gradient of the block output; updated IN PLACE to the gradient of the block input and returned."""
-    x0, xw, qkv, att, x1, h1, hpre, hid, geom, table_t = saved
+    x0, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok = saved
     n, C = x0.shape
     dev = x0.device
     rows = geom.rows()
@@ -200,7 +215,7 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
     pw = blk.prepared
     # ---- MLP half: x2 = x1 + fc2(GELU(fc1(LN2(x1))))
     dyb = ws.get("bw_dyb", (n, C), torch.bfloat16, dev)
-    K.cast_rows_bf16(dx, dyb)
+    K.cast_rows_bf16(dx, dyb, rscale=s_mlp, rscale_rows=tok)         # DropPath: the branch sees the gradient times its sample's scale
     dhid = ws.get("bw_dhid", (n, hidden), torch.bfloat16, dev)
     linear_bwd(dyb, hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, grads, ws, pw, "fc2", dx_bf16=dhid)
     K.gelu_bwd(dhid, hpre, dhid)
@@ -210,7 +225,7 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
                          eps=blk.norm2.eps)
     # ---- attention half: x1 = x0 + scatter(proj(attn(qkv(gather(LN1(x0))))))
     dyw = ws.get("bw_dyw", (rows, C), torch.bfloat16, dev)
-    K.cast_rows_bf16(dx, dyw, geom)
+    K.cast_rows_bf16(dx, dyw, geom, rscale=s_attn, rscale_rows=tok)
     datt = ws.get("bw_datt", (rows, C), torch.bfloat16, dev)
     linear_bwd(dyw, att, blk.attn.proj.weight, blk.attn.proj.bias, grads, ws, pw, "proj", dx_bf16=datt)
     dqkv = ws.get("bw_dqkv", (rows, 3 * C), torch.bfloat16, dev)

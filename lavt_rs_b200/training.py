@@ -12,7 +12,8 @@ Mirrors the inner loop of the reference's ``train_one_epoch_*`` (train.py:330-36
 * ``allreduce_gradients`` is the one collective of the path: bucketed NCCL all-reduce of the parameter gradients
   (replaces DistributedDataParallel, train.py:590-593).
 
-Not implemented in training mode (raise, no fallback): stochastic depth > 0, --hs / --version variants, SepTPWAM, the 2-D
+Stochastic depth (DropPath) runs as a per-sample scale inside the proj / fc2 GEMM epilogues.  Not implemented in training mode
+(raise, no fallback): --hs / --version variants, SepTPWAM, the 2-D
 image models, windows above ~400 tokens (8x12x12).  The text encoder's own backward runs through the stock ``transformers``
 module under autograd (SURVEY.md section 8f-2 marks the text side as the next row, not the hot path).
 """
@@ -32,9 +33,6 @@ def _check_trainable(model) -> None:
     for layer in bb.layers:
         if layer.hs or layer.sep_t_pwam or layer.version != "default":
             raise NotImplementedError("training on the B200 path supports the default PWAM + LanguageGate configuration only")
-        for blk in layer.blocks:
-            if blk.drop_path_rate > 0:
-                raise NotImplementedError("stochastic depth > 0 is not implemented on the B200 training path (build with drop_path_rate=0)")
     if tuple(bb.out_indices) != (0, 1, 2, 3):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
 

@@ -107,7 +107,7 @@ def rel_const(window_cfg) -> int:
 # A1: attention half of a Swin block (forward_part1 + WindowAttention3D, :137-168, :214-248)
 # --------------------------------------------------------------------------------------------
 def swin_attention_half(x: Tensor, sd: Dict[str, Tensor], pre: str, num_heads: int, window, shifted: bool,
-                        clamp: bool = True, return_parts: bool = False):
+                        clamp: bool = True, return_parts: bool = False, branch_scale: Optional[Tensor] = None):
     """x (B,D,H,W,C) -> x + Attn(LN1(x)).  ``pre`` = 'backbone.layers.{s}.blocks.{i}.'"""
     B, D, H, W, C = x.shape
     shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
@@ -133,6 +133,8 @@ def swin_attention_half(x: Tensor, sd: Dict[str, Tensor], pre: str, num_heads: i
     o = (p @ v).transpose(1, 2).reshape(B * nW, N, C)
     y = o @ sd[pre + "attn.proj.weight"].t() + sd[pre + "attn.proj.bias"]
     y = y.reshape(B, nW * N, C)
+    if branch_scale is not None:       # DropPath in training (:266): per-sample 0 or 1 / keep_prob on the whole branch
+        y = y * branch_scale.reshape(B, 1, 1)
     out = x.reshape(B, D * H * W, C).clone()
     vi = valid.reshape(-1)
     out[:, src.reshape(-1)[vi]] += y[:, vi]                                            # window_reverse + un-roll + crop
@@ -143,11 +145,14 @@ def swin_attention_half(x: Tensor, sd: Dict[str, Tensor], pre: str, num_heads: i
 
 
 # A2: MLP half (:250-251, :30-36)
-def swin_mlp_half(x: Tensor, sd, pre: str) -> Tensor:
+def swin_mlp_half(x: Tensor, sd, pre: str, branch_scale: Optional[Tensor] = None) -> Tensor:
     C = x.shape[-1]
     h = F.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
     h = F.gelu(h @ sd[pre + "mlp.fc1.weight"].t() + sd[pre + "mlp.fc1.bias"])
-    return x + h @ sd[pre + "mlp.fc2.weight"].t() + sd[pre + "mlp.fc2.bias"]
+    y = h @ sd[pre + "mlp.fc2.weight"].t() + sd[pre + "mlp.fc2.bias"]
+    if branch_scale is not None:       # DropPath (:271)
+        y = y * branch_scale.reshape(-1, *([1] * (y.dim() - 1)))
+    return x + y
 
 
 # --------------------------------------------------------------------------------------------

@@ -182,6 +182,40 @@ def test_swin_block_backward(stage, shifted, dims):
     check_grads(grads.named(blk), pg_ref, f"swin block stage {stage} shifted={shifted}")
 
 
+def test_swin_block_drop_path():
+    """Stochastic depth (timm DropPath, reference :266/:271): per-sample branch scale inside the GEMM epilogues and its adjoint."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    window = (8, 7, 7)
+    cfg, sd, bb = _block_setup(window)
+    B, D, H, W, C, nH = 3, 4, 14, 10, 128, 4
+    blk = bb.layers[0].blocks[1]
+    pre = "backbone.layers.0.blocks.1."
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, D, H, W, C, generator=g)
+    gout = torch.randn(B, D, H, W, C, generator=g)
+    s_attn = torch.tensor([1 / 0.7, 0.0, 1 / 0.7])
+    s_mlp = torch.tensor([0.0, 1 / 0.7, 1 / 0.7])
+
+    def fn(sd2, xx):
+        return O.swin_mlp_half(O.swin_attention_half(xx, sd2, pre, nH, window, True, branch_scale=s_attn), sd2, pre, branch_scale=s_mlp)
+    (dx_ref,), pg_ref = _oracle_grads(fn, sd, pre, [x], gout)
+    ws = E.workspace("cuda")
+    grads = T.GradStore()
+    out, saved = T.swin_block_fwd(x.cuda().reshape(-1, C).contiguous(), blk, B, D, H, W, window, True, True, ws,
+                                  drop_scales=(s_attn.cuda(), s_mlp.cuda()))
+    assert rel_l2(out, fn(sd, x).reshape(-1, C)) < 1e-2
+    dx = T.swin_block_bwd(blk, saved, gout.cuda().reshape(-1, C).contiguous(), grads, ws)
+    assert rel_l2(dx, dx_ref.reshape(-1, C)) < GRAD_L2
+    check_grads(grads.named(blk), pg_ref, "swin block with DropPath")
+    # the drawn scales take the two values of timm's DropPath
+    blk.drop_path_rate = 0.25
+    s = T.draw_drop_path(0.25, 4096, "cuda")
+    vals = torch.unique(s).tolist()
+    assert all(min(abs(v), abs(v - 1 / 0.75)) < 1e-6 for v in vals) and abs((s > 0).float().mean().item() - 0.75) < 0.05
+    blk.drop_path_rate = 0.0
+
+
 def test_patch_merging_backward():
     from lavt_rs_b200 import engine as E
     from lavt_rs_b200 import train_engine as T
@@ -424,3 +458,36 @@ def test_model_training_step():
     for name, prm in (("backbone.layers.2.blocks.1.mlp.fc1.weight", bb.layers[2].blocks[1].mlp.fc1.weight),
                       ("classifier.conv2_3.weight", dec.conv2_3.weight), ("backbone.patch_embed.proj.weight", bb.patch_embed.proj.weight)):
         assert rel_l2(prm.grad, got[name].reshape(prm.shape)) < 3e-2, name      # same kernels, same inputs: both routes agree
+
+
+def test_fused_adamw_matches_torch():
+    """lavt_adamw_step (one launch per parameter group) vs torch.optim.AdamW over three steps, with the reference's group structure
+    (a no-decay group, default groups, train.py:615-692), odd sizes / unaligned views, AMSGrad on and off, and a LambdaLR schedule."""
+    from lavt_rs_b200.optim import FusedAdamW, poly_lr_lambda
+    g = torch.Generator().manual_seed(9)
+    for amsgrad in (False, True):
+        shapes = [(128, 64), (77,), (3, 5, 7), (4096 * 3 + 5,), (1,), (512, 1, 3, 3)]
+        big = torch.randn(1000, generator=g).cuda()
+        ours = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes] + [torch.nn.Parameter(big[3:3 + 500].clone())]
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+
+        def groups(ps):
+            return [{"params": ps[:2], "weight_decay": 0.0}, {"params": ps[2:5]}, {"params": ps[5:]}]
+        o1 = FusedAdamW(groups(ours), lr=5e-3, weight_decay=1e-2, amsgrad=amsgrad)
+        o2 = torch.optim.AdamW(groups(ref), lr=5e-3, weight_decay=1e-2, amsgrad=amsgrad)
+        s1 = torch.optim.lr_scheduler.LambdaLR(o1, poly_lr_lambda(10))
+        s2 = torch.optim.lr_scheduler.LambdaLR(o2, poly_lr_lambda(10))
+        for it in range(3):
+            for a, b in zip(ours, ref):
+                gr = torch.randn(a.shape, generator=g).cuda()
+                a.grad, b.grad = gr.clone(), gr.clone()
+            if it == 1:
+                ours[1].grad = None
+                ref[1].grad = None           # a parameter without gradient is skipped
+            o1.step(); o2.step(); s1.step(); s2.step()
+        torch.cuda.synchronize()
+        for a, b in zip(ours, ref):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (amsgrad, a.shape, (a - b).abs().max().item())
+        st1, st2 = o1.state_dict()["state"], o2.state_dict()["state"]
+        assert set(st1[0].keys()) == set(st2[0].keys())
+        assert torch.allclose(st1[3]["exp_avg_sq"], st2[3]["exp_avg_sq"], rtol=1e-5, atol=1e-9)

@@ -34,8 +34,10 @@ def test_ctypes_binding_covers_header():
 def test_struct_layouts_match_header():
     from lavt_rs_b200 import _cabi
     assert ctypes.sizeof(_cabi.WinGeom) == 17 * 4
-    assert ctypes.sizeof(_cabi.Epilogue) == 7 * 8 + 4 * 4      # 6 data pointers + win pointer, act/ldm/ldo/_pad
-    assert _cabi.Epilogue.win.offset == 64
+    assert ctypes.sizeof(_cabi.Epilogue) == 8 * 8 + 6 * 4      # 6 data pointers + win + rscale pointers, act/ldm/ldo/_pad/rscale_rows/_pad2
+    assert _cabi.Epilogue.win.offset == 64 and _cabi.Epilogue.rscale.offset == 72 and _cabi.Epilogue.rscale_rows.offset == 80
+    from lavt_rs_b200.optim import _Tensor
+    assert ctypes.sizeof(_Tensor) == 56                         # lavt_adamw_tensor_t: 5 pointers, int64 n, two floats
 
 
 def test_no_cpu_fallback():

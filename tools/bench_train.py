@@ -33,6 +33,8 @@ def main():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--clips-per-gpu", type=int, default=4)
     p.add_argument("--frozen-text", action="store_true", help="do not backpropagate into the text encoder")
+    p.add_argument("--optimizer", action="store_true", help="include the AdamW update (FusedAdamW over the reference's parameter groups, "
+                                                            "poly LR) in the timed step")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
     a = p.parse_args()
 
@@ -62,6 +64,12 @@ def main():
         prm.requires_grad_(not a.frozen_text)
     params = [prm for prm in model.parameters() if prm.requires_grad]
 
+    opt = sched = None
+    if a.optimizer:
+        from lavt_rs_b200.optim import FusedAdamW, poly_lr_lambda, reference_param_groups
+        opt = FusedAdamW(reference_param_groups(model, "encoder-10"), lr=5e-5, weight_decay=1e-2, amsgrad=True)    # args.py defaults
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, poly_lr_lambda(100000))
+
     Bc = a.clips_per_gpu
     batches = []
     for s in range(2):
@@ -83,6 +91,9 @@ def main():
         if not a.frozen_text:
             l_feats.backward(dl)
         TR.allreduce_gradients(params)
+        if opt is not None:
+            opt.step()
+            sched.step()
         state["loss"] = loss
 
     def timed(steps, warmup):
