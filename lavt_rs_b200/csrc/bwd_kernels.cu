@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
 
 int transpose_bf16_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, long long M, int N,
                             cudaStream_t st) {
-  LAVT_REQUIRE(M > 0 && N > 0 && M % 2 == 0 && N % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0, "transpose: sizes / pitches must be even");
+  LAVT_REQUIRE(M > 0 && N > 0 && N % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0, "transpose: N and the pitches must be even");
+  // the kernel stores pairs along M: an odd M writes one extra (zero) element, which must fall inside the row pitch
+  LAVT_REQUIRE(M % 2 == 0 || ldo > M, "transpose: odd M=%lld needs an output pitch > M (got %lld)", M, ldo);
   const long long mt = (M + 63) / 64, nt = (N + 63) / 64;
   LAVT_REQUIRE(mt < (1LL << 31) && nt < 65536, "transpose: grid too large (M=%lld, N=%d)", M, N);
   transpose_bf16_kernel<<<dim3(static_cast<unsigned>(mt), static_cast<unsigned>(nt)), 256, 0, st>>>(in, ldi, out, ldo, M, N);

@@ -32,6 +32,10 @@ def _build_text_encoder(args):
 class _Segmenter(nn.Module):
     video = False
 
+    def _train_mode(self) -> bool:
+        """model.train() with autograd on: the call is part of a training step (reference train.py:330-360)."""
+        return self.training and torch.is_grad_enabled()
+
     def _encode_text_async(self, text: torch.Tensor, l_mask: torch.Tensor):
         """Text encoder on a high-priority side stream: its ~90 small launches overlap the patch embedding and the first
         Swin blocks (which do not read the language features).  Returns (l_feats, event that marks them valid)."""
@@ -71,6 +75,9 @@ class LAVT(_Segmenter):
 
     def forward(self, x, l_feats, l_mask):
         E.require_cuda(x, "x")
+        if self._train_mode():
+            from ..training import train_forward
+            return train_forward(self, x, l_feats, l_mask)
         x5 = _planes(x).unsqueeze(2)
         return self._segment(x5, l_feats, l_mask, x.shape[-2:])
 
@@ -86,6 +93,9 @@ class LAVTOne(_Segmenter):
 
     def forward(self, x, text, l_mask):
         E.require_cuda(x, "x")
+        if self._train_mode():
+            from ..training import train_forward
+            return train_forward(self, x, text, l_mask)
         l_feats, ev = self._encode_text_async(text, l_mask)               # (B, 768, Nl): [0].permute(0, 2, 1) of the reference
         x5 = _planes(x).unsqueeze(2)
         return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)
@@ -108,6 +118,9 @@ class LAVTVideo(_Segmenter):
 
     def forward(self, x, text, l_mask):
         E.require_cuda(x, "x")
+        if self._train_mode():          # training step: saved activations + hand-written backward behind autograd
+            from ..training import train_forward
+            return train_forward(self, x, text, l_mask)
         l_feats, ev = self._encode_text_async(text, l_mask)
         x5 = _planes(x).permute(0, 2, 1, 3, 4)
         return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)

@@ -13,8 +13,8 @@ Mirrors the inner loop of the reference's ``train_one_epoch_*`` (train.py:330-36
   (replaces DistributedDataParallel, train.py:590-593).
 
 Stochastic depth (DropPath) runs as a per-sample scale inside the proj / fc2 GEMM epilogues.  Not implemented in training mode
-(raise, no fallback): --hs / --version variants, SepTPWAM, the 2-D
-image models, windows above ~400 tokens (8x12x12).  The text encoder's own backward runs through the stock ``transformers``
+(raise, no fallback): --hs / --version variants, SepTPWAM, windows above ~400 tokens (8x12x12).  The 2-D image models
+(lavt / lavt_one) train through the same code with one frame per clip.  The text encoder's own backward runs through the stock ``transformers``
 module under autograd (SURVEY.md section 8f-2 marks the text side as the next row, not the hot path).
 """
 from __future__ import annotations
@@ -38,7 +38,7 @@ def _check_trainable(model) -> None:
 
 
 def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, sync_bn: bool = False):
-    """Forward of the hot path with saved activations.  x (B,T,3,H,W) fp32; l_feats (B,768,Nl); l_mask (B,Nl[,1]).
+    """Forward of the hot path with saved activations.  x (B,T,3,H,W) fp32 (video) or (B,3,H,W) (image); l_feats (B,768,Nl); l_mask (B,Nl[,1]).
     Returns (logits fp32 (B*T,2,H,W), tape)."""
     from .lib.video_swin_transformer import _lang, _mask, _planes
     _check_trainable(model)
@@ -48,7 +48,8 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
     ws = E.workspace(dev)
     l = _lang(l_feats)
     mask = _mask(l_mask)
-    x5 = _planes(x).permute(0, 2, 1, 3, 4)
+    # video: (B,T,3,H,W) -> (B,3,T,H,W) view; image models (lavt / lavt_one): (B,3,H,W) -> one frame, windows (1,w,w) never clamped
+    x5 = _planes(x).permute(0, 2, 1, 3, 4) if x.dim() == 5 else _planes(x).unsqueeze(2)
     B, _, D, H, W = x5.shape
     feat, Hc, Wc, pe_saved = T.patch_embed_fwd(x5, bb.patch_embed, ws)
     stages = []
@@ -140,7 +141,9 @@ class SegmentFunction(torch.autograd.Function):
     encoder's autograd graph continues."""
 
     @staticmethod
-    def forward(ctx, x, l_feats, l_mask, model, sync_bn):
+    def forward(ctx, x, l_feats, l_mask, model, sync_bn, anchor=None):
+        # ``anchor``: any tensor with requires_grad=True.  It keeps this node in the autograd graph when neither the pixels nor the
+        # language features require grad (frozen or precomputed text features): the parameters are not autograd inputs here.
         logits, tape = segment_forward(model, x.detach(), l_feats.detach(), l_mask, sync_bn)
         ctx.tape, ctx.model = tape, model
         return logits
@@ -151,7 +154,7 @@ class SegmentFunction(torch.autograd.Function):
         dl = segment_backward(ctx.model, ctx.tape, dlogits.float(), grads)
         grads.finalize()
         ctx.tape = None
-        return None, dl, None, None, None
+        return None, dl, None, None, None, None
 
 
 def allreduce_gradients(params: List[torch.nn.Parameter], bucket_mb: int = 64) -> None:
@@ -184,3 +187,19 @@ def allreduce_gradients(params: List[torch.nn.Parameter], bucket_mb: int = 64) -
         if size >= bucket_mb << 20:
             flush()
     flush()
+
+
+def uses_sync_bn(model) -> bool:
+    """True if the decoder's BatchNorm layers were converted with nn.SyncBatchNorm.convert_sync_batchnorm (train.py:589)."""
+    return any(isinstance(m, torch.nn.SyncBatchNorm) for m in model.classifier.modules())
+
+
+def train_forward(model, x, text, l_mask):
+    """``model(x, text, l_mask)`` in training mode (reference lib/_utils.py:86-108 under autograd): the text encoder runs as the stock
+    transformers module under autograd, everything after it through ``SegmentFunction``."""
+    if hasattr(model, "text_encoder"):
+        l_feats = model.text_encoder(text, attention_mask=l_mask)[0].permute(0, 2, 1)      # (B, 768, Nl)
+    else:
+        l_feats = text                                                                      # LAVT: precomputed language features
+    anchor = torch.zeros((), device=x.device, requires_grad=True)
+    return SegmentFunction.apply(x, l_feats, l_mask, model, uses_sync_bn(model), anchor)

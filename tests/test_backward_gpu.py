@@ -491,3 +491,61 @@ def test_fused_adamw_matches_torch():
         st1, st2 = o1.state_dict()["state"], o2.state_dict()["state"]
         assert set(st1[0].keys()) == set(st2[0].keys())
         assert torch.allclose(st1[3]["exp_avg_sq"], st2[3]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
+def test_image_model_training_through_public_api(tmp_path):
+    """2-D LAVT (windows (1,7,7), never clamped) in ``model.train()``: ``model(x, l_feats, l_mask)`` -> criterion -> ``backward()`` ->
+    FusedAdamW step -> checkpoint round trip in the reference's format; gradients vs autograd through the oracle (direction / scale)."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.optim import FusedAdamW, poly_lr_lambda, reference_param_groups
+    from lavt_rs_b200.checkpoint import resume_checkpoint, save_checkpoint
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=None)
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    g = torch.Generator().manual_seed(41)
+    B, H, W, Nl = 3, 160, 128, 15
+    x = torch.randn(B, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    m[1, 9:] = 0
+    target = torch.randint(0, 2, (B, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, l, m, train_bn=True), target)
+    loss_ref.backward()
+
+    opt = FusedAdamW(reference_param_groups(model), lr=1e-4, weight_decay=1e-2, amsgrad=True)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, poly_lr_lambda(100))
+    out = model(x.cuda(), l.cuda(), m.cuda())                       # training mode: autograd-connected logits
+    assert out.requires_grad and out.shape == (B, 2, H, W)
+    loss = torch.nn.functional.cross_entropy(out, target.cuda(), weight=torch.tensor([0.9, 1.1], device="cuda"))
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    opt.zero_grad()
+    loss.backward()
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    check_direction(got, ref, "2-D training step")
+    before = bb.layers[1].blocks[0].mlp.fc1.weight.detach().clone()
+    opt.step()
+    sched.step()
+    assert not torch.equal(before, bb.layers[1].blocks[0].mlp.fc1.weight)
+    # eval mode still runs the inference path, without autograd
+    model.eval()
+    with torch.no_grad():
+        assert not model(x.cuda(), l.cuda(), m.cuda()).requires_grad
+    # checkpoint round trip (train.py:752-762 format)
+    path = os.path.join(tmp_path, "models", "checkpoint_00.pth")
+    save_checkpoint(path, model, opt, sched, epoch=0, args={"lr": 1e-4})
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "epoch", "args", "lr_scheduler"} and set(ck["model"]) == set(model.state_dict())
+    with torch.no_grad():
+        bb.layers[1].blocks[0].mlp.fc1.weight.zero_()
+    assert resume_checkpoint(path, model, opt, sched) == 0
+    assert bb.layers[1].blocks[0].mlp.fc1.weight.abs().sum().item() > 0
