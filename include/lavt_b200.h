@@ -187,6 +187,11 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
 int64_t lavt_gemm_splitk_workspace_floats(int32_t M, int32_t N, int32_t K);
 int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t b_koff,
                           float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream);
+/* dst[n_out, n_in] (+)= dy[tokens, n_out]^T x[tokens, n_in] straight from the ROW-MAJOR activations: TMA boxes of 64 tokens x 64
+ * channels land in shared memory as MN-major tcgen05 operands, so no transposed copies are made (split-K over the token axis,
+ * workspace as for lavt_gemm_bf16_splitk with M = n_out, N = n_in, K = tokens).  n_out % 8 == 0, n_in % 32 == 0. */
+int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t tokens, int32_t n_out, int32_t n_in,
+                         float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream);
 /* out[N, M] (pitch ldo) = in[M, N]^T (pitch ldi), bf16 */
 int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream);
 /* dst[n] += sum_m x[m, n]  (bias gradients); x is bf16 (is_bf16 != 0) or fp32 */

@@ -99,6 +99,7 @@ SIGNATURES = {
     "lavt_nchw_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _vp],
     # ---- backward pass ----
     "lavt_gemm_bf16_splitk": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
+    "lavt_gemm_bf16_wgrad": [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
     "lavt_transpose_bf16": [_vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
@@ -524,6 +525,23 @@ def gemm_bf16_splitk(a_t: torch.Tensor, b_t: torch.Tensor, dst: torch.Tensor, wo
                                       _c(workspace, torch.float32, "workspace").data_ptr(), workspace.numel(), dst.data_ptr(),
                                       dst.stride(0), 1 if accumulate else 0, stream_ptr()), "lavt_gemm_bf16_splitk")
     TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N, f"wgrad M{M} N{N} K{K}")
+
+
+def gemm_bf16_wgrad(dy: torch.Tensor, x: torch.Tensor, dst: torch.Tensor, workspace: torch.Tensor, *, accumulate: bool = True) -> None:
+    """dst[out, in] (+)= dy[tokens, out].T @ x[tokens, in] from the row-major activations (MN-major tcgen05 operands, split-K)."""
+    _req(dy, torch.bfloat16, "dy")
+    _req(x, torch.bfloat16, "x")
+    _req(dst, torch.float32, "dst")
+    tokens, n_out = dy.shape
+    n_in = x.shape[1]
+    if x.shape[0] != tokens or tuple(dst.shape) != (n_out, n_in):
+        raise LavtError("wgrad gemm: shape mismatch")
+    t0 = TIMER.begin()
+    check(lib().lavt_gemm_bf16_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), tokens, n_out, n_in,
+                                     _c(workspace, torch.float32, "workspace").data_ptr(), workspace.numel(), dst.data_ptr(),
+                                     dst.stride(0), 1 if accumulate else 0, stream_ptr()), "lavt_gemm_bf16_wgrad")
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * tokens * n_out * n_in, 2.0 * tokens * (n_out + n_in) + 4.0 * n_out * n_in,
+              f"wgrad-mn tokens{tokens} out{n_out} in{n_in}")
 
 
 def transpose_bf16(x: torch.Tensor, out: torch.Tensor) -> None:

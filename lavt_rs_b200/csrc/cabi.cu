@@ -272,6 +272,29 @@ int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ld
   return splitk_reduce_dispatch(workspace, ks, 1LL * M * N, N, dst, ldd, accumulate, S(stream));
 }
 
+int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t tokens, int32_t n_out, int32_t n_in,
+                         float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream) {
+  LAVT_REQUIRE(tokens > 0 && tokens < (1LL << 31), "wgrad gemm: token count out of range");
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = n_out; p.N = n_in; p.K = static_cast<int>(tokens);
+  int ks, kbs;
+  splitk_plan(p.M, p.N, p.K, &ks, &kbs);
+  LAVT_REQUIRE(workspace && workspace_floats >= 1LL * ks * p.M * p.N, "wgrad gemm: workspace too small (%lld < %lld floats)",
+               static_cast<long long>(workspace_floats), 1LL * ks * p.M * p.N);
+  LAVT_REQUIRE(dst != nullptr && ldd >= n_in, "wgrad gemm: bad destination");
+  p.out_f32 = workspace;
+  p.ldo = p.N;
+  p.rowmap = ROWMAP_IDENTITY;
+  p.ksplit = ks;
+  p.kbs = kbs;
+  p.split_stride = 1LL * p.M * p.N;
+  p.mnmajor = 1;
+  int rc = gemm_dispatch(dy, lddy, x, ldx, p, S(stream));
+  if (rc) return rc;
+  return splitk_reduce_dispatch(workspace, ks, 1LL * p.M * p.N, p.N, dst, ldd, accumulate, S(stream));
+}
+
 int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream) {
   return transpose_bf16_dispatch(CB(in), ldi, MB(out), ldo, M, N, S(stream));
 }

@@ -228,6 +228,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand, 128-byte swizzle: the tile is stored k-row by k-row, each row = 64 consecutive MN elements (128 B), rows at
+// 128 B pitch (one TMA box of 64 k x 64 mn = 8 KB); canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements:
+//   SBO = 1024 B between groups of 8 k-rows, LBO = byte distance between consecutive 64-element MN atoms (= one 8 KB box here).
+// One tcgen05.mma (K = 16) consumes two 8-row groups: advance the start address by 2048 B per k-step.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> f32, A and B both K-major.
 //   bits [4,6) D format (1 = f32); [7,10) A format (1 = bf16); [10,13) B format (1 = bf16)
 //   bit 15 / 16: A / B major (0 = K); [17,23) N >> 3; [24,29) M >> 4

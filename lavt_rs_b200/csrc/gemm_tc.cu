@@ -225,6 +225,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
               tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
             }
+          } else if (p.mnmajor) {
+            // operands stored [K, MN] row-major: boxes of 64 k-rows x 64 MN elements, one 8 KB box per 64-wide MN atom
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], mt * GEMM_BM + j * 64, kb * GEMM_BK);
+#pragma unroll
+            for (int j = 0; j < GEMM_BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * GEMM_BK + p.b_koff);
+            continue;
           } else {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
           }
@@ -235,7 +242,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
+      constexpr uint32_t idesc_k = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
+      const uint32_t idesc = p.mnmajor ? (idesc_k | (1u << 15) | (1u << 16)) : idesc_k;      // bits 15 / 16: A / B are MN-major
       int it = 0, lt = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
         const int ks = work / total_tiles;
@@ -254,12 +262,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (kb == kb_lo) GEMM_TRACE(1, lt);
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
-          const uint64_t da = make_kmajor_sw128_desc(sa);
-          const uint64_t db = make_kmajor_sw128_desc(sb);
+          if (p.mnmajor) {
+            const uint64_t da = make_mnmajor_sw128_desc(sa, 8192);
+            const uint64_t db = make_mnmajor_sw128_desc(sb, 8192);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // 16 k-rows of 128 B = 2048 bytes per k-step: +128 in (addr >> 4) units
+              umma_bf16_ss(tmem_d, da + 128 * k, db + 128 * k, idesc, ((kb - kb_lo) | k) != 0);
+            }
+          } else {
+            const uint64_t da = make_kmajor_sw128_desc(sa);
+            const uint64_t db = make_kmajor_sw128_desc(sb);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
+              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+            }
           }
           umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
         }
@@ -510,7 +528,8 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
                   cudaStream_t stream) {
   LAVT_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   LAVT_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
-  LAVT_REQUIRE(p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);
+  LAVT_REQUIRE(p.mnmajor || p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);
+  LAVT_REQUIRE(!p.mnmajor || (p.M % 8 == 0 && p.rowmap == ROWMAP_IDENTITY), "gemm (MN-major operands): M=%d must be a multiple of 8", p.M);
   LAVT_REQUIRE(p.ldo % 16 == 0 && p.ldo >= p.N, "gemm: ldo=%d invalid for N=%d (need a multiple of 16)", p.ldo, p.N);
   LAVT_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) | reinterpret_cast<uintptr_t>(p.out_bf16) |
                 reinterpret_cast<uintptr_t>(p.resid) | reinterpret_cast<uintptr_t>(p.mul)) % 32 == 0,
@@ -542,6 +561,16 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     }
     if (rc) return rc;
     m_tiles = n_img * p.cTilesH * p.cTilesW;
+  } else if (p.mnmajor) {
+    // A stored [K, M] row-major, B stored [K, N] row-major: 64 x 64 boxes (inner = 64 MN elements = one 128-byte swizzle row)
+    uint64_t dimsA[2] = {(uint64_t)p.M, (uint64_t)p.K}, dimsB[2] = {(uint64_t)p.N, (uint64_t)p.K};
+    uint64_t sA[1] = {(uint64_t)lda * 2}, sB[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {64, GEMM_BK};
+    int rc = make_tmap_bf16(&tmA, A, 2, dimsA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB, Bw, 2, dimsB, sB, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   } else {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
     uint64_t strides[1] = {(uint64_t)lda * 2};
@@ -550,7 +579,7 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     if (rc) return rc;
     m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   }
-  {
+  if (!p.mnmajor) {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t strides[1] = {(uint64_t)ldb * 2};
     uint32_t box[2] = {GEMM_BK, gemm_variant(p) == 2 ? 256u : 128u};

@@ -36,6 +36,8 @@ struct GemmParams {
   int ksplit;                // 0 / 1 = off; s > 1: work item = (tile, split); split ks accumulates k-blocks [ks*kbs, (ks+1)*kbs)
   int kbs;                   // k-blocks per split
   long long split_stride;    // out_f32 of split ks = out_f32 + ks * split_stride (partials, reduced by splitk_reduce)
+  int mnmajor;               // 1: both operands are stored [K, M] / [K, N] row-major (dW = dY^T X straight from the row-major activations):
+                             //    TMA boxes of 64 k-rows x 64 MN-elements, MN-major shared-memory descriptors, no transposed copies
   int b_koff;                // added to the K coordinate of the B operand (conv weight gradient: tap offset in the padded pixel axis)
 };
 int splitk_reduce_dispatch(const float* partials, int splits, long long count, int ncols, float* dst, long long ldd, int accumulate,

@@ -5,7 +5,7 @@ The reference trains with autograd over PyTorch ops (train.py:330-360: ``loss.ba
 ``*_bwd`` that sequences the backward kernels of ``include/lavt_b200.h``:
 
   * activation gradients of a Linear / Conv1d(k=1):  dX = dY W        -> ``lavt_gemm_bf16`` with the transposed bf16 weight
-  * weight gradients:                                 dW += dY^T X     -> ``lavt_transpose_bf16`` x 2 + ``lavt_gemm_bf16_splitk``
+  * weight gradients:                                 dW += dY^T X     -> ``lavt_gemm_bf16_wgrad`` (MN-major operands, split-K)
   * bias gradients:                                   db += colsum dY  -> ``lavt_colsum_accumulate``
   * LayerNorm (+ window gather / PatchMerging gather) -> ``lavt_layernorm_*_bwd``
   * window attention                                  -> ``lavt_window_attention_bwd``
@@ -119,19 +119,16 @@ def linear_bwd(dy: torch.Tensor, x: Optional[torch.Tensor], weight: torch.Tensor
                **dx_epi) -> Optional[torch.Tensor]:
     """Adjoint of y = x W^T + b for bf16 rows dy [M, out], x [M, in]; ``weight`` is the [out, in(,1)] parameter.
     dW += dy^T x, db += colsum(dy); if a dx buffer is given: dx = dy W (through the GEMM epilogue options in ``dx_epi``).
-    Returns the transposed x operand so that a caller with several consumers of the same x can reuse it."""
+    (``x_t`` is accepted for callers written against the transposed-operand version and ignored.)"""
     M, Nout = dy.shape
     w2 = weight.view(weight.shape[0], -1) if weight.dim() != 2 else weight
     Kin = w2.shape[1]
     dev = dy.device
     if weight.requires_grad:
-        dy_t = _transposed(ws, "bw_dyT", dy)
-        if x_t is None:
-            x_t = _transposed(ws, "bw_xT", x)
-        wsf = K.splitk_workspace_floats(Nout, Kin, dy_t.shape[1])
-        part = ws.get("bw_splitk", (wsf,), torch.float32, dev)
-        K.gemm_bf16_splitk(dy_t, x_t, grads.of(weight).view(Nout, Kin), part, accumulate=True)
-        _count(4)
+        # dW += dy^T x straight from the row-major rows: 64-token x 64-channel TMA boxes are MN-major tcgen05 operands
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Nout, Kin, M),), torch.float32, dev)
+        K.gemm_bf16_wgrad(dy, x, grads.of(weight).view(Nout, Kin), part, accumulate=True)
+        _count(2)
     if bias is not None and bias.requires_grad:
         K.colsum_accumulate(dy, grads.of(bias))
         _count(1)
@@ -391,10 +388,8 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     K.pwam_attend_bwd(s["qpre"], s["stats_q"], s["kk"], s["vv"], s["mask"], do, dqhat, qs, p_bd, ds_bd, sums[1], heads, nlp)
     dkv = torch.empty(2, Wd, C, device=dev, dtype=f32)
     for buf, dy_rows, x_rows in ((dkv[0], ds_bd, qs), (dkv[1], p_bd, do)):      # dk = dS^T (C^-0.5 q^), dv = P^T dO
-        dy_t = _transposed(ws, "bw_dyT", dy_rows)
-        x_t = _transposed(ws, "bw_xT", x_rows)
-        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Wd, C, dy_t.shape[1]),), f32, dev)
-        K.gemm_bf16_splitk(dy_t, x_t, buf, part, accumulate=False)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Wd, C, N_),), f32, dev)
+        K.gemm_bf16_wgrad(dy_rows, x_rows, buf, part, accumulate=False)
     fk, fv = att.f_key[0], att.f_value[0]
     K.pwam_kv_bwd(dkv[0], dkv[1], s["mask"], s["l"], s["k_w"], s["v_w"],
                   grads.of(fk.weight) if fk.weight.requires_grad else None, grads.of(fk.bias) if fk.bias.requires_grad else None,
@@ -461,11 +456,9 @@ def patch_embed_bwd(pe, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
         K.cast_rows_bf16(dpre, dyb)
         _count(2)
     if pe.proj.weight.requires_grad:
-        dy_t = _transposed(ws, "bw_dyT", dyb)
-        x_t = _transposed(ws, "bw_xT", cols)
-        part = ws.get("bw_splitk", (K.splitk_workspace_floats(C, 64, dy_t.shape[1]),), torch.float32, dev)
-        K.gemm_bf16_splitk(dy_t, x_t, grads.padded_cols(pe.proj.weight, 64), part, accumulate=True)
-        _count(4)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(C, 64, n),), torch.float32, dev)
+        K.gemm_bf16_wgrad(dyb, cols, grads.padded_cols(pe.proj.weight, 64), part, accumulate=True)
+        _count(2)
     if pe.proj.bias is not None and pe.proj.bias.requires_grad:
         K.colsum_accumulate(dyb, grads.of(pe.proj.bias))
         _count(1)

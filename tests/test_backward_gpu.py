@@ -77,7 +77,7 @@ def check_direction(got: dict, ref: dict, what: str, min_cos: float = 0.95):
 def test_transpose_colsum_splitk():
     from lavt_rs_b200 import _cabi as K
     g = torch.Generator().manual_seed(0)
-    for M, N, Kin in ((1000, 96, 64), (4104, 384, 128), (392 * 9, 512, 2048)):
+    for M, N, Kin in ((1000, 96, 64), (4104, 384, 128), (392 * 9, 512, 2048), (3 * 148, 128, 128)):
         dy = torch.randn(M, N, generator=g).cuda().to(torch.bfloat16)
         x = torch.randn(M, Kin, generator=g).cuda().to(torch.bfloat16)
         M8 = (M + 7) // 8 * 8
@@ -92,6 +92,10 @@ def test_transpose_colsum_splitk():
         K.gemm_bf16_splitk(dyt, xt, dst, part, accumulate=True)
         ref = dy.float().t() @ x.float() + 0.5
         assert rel_l2(dst, ref) < 2e-3, (M, N, Kin, rel_l2(dst, ref))
+        # the same product straight from the row-major operands (MN-major tcgen05 descriptors, no transposed copies)
+        dst2 = torch.full((N, Kin), 0.5, device="cuda")
+        K.gemm_bf16_wgrad(dy, x, dst2, torch.empty(K.splitk_workspace_floats(N, Kin, M), device="cuda"), accumulate=True)
+        assert rel_l2(dst2, ref) < 2e-3, ("mn-major", M, N, Kin, rel_l2(dst2, ref))
         cs = torch.ones(N, device="cuda")
         K.colsum_accumulate(dy, cs)
         assert rel_l2(cs, dy.float().sum(0) + 1) < 1e-3
