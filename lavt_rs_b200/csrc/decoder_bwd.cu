@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloa
 
 int bn_relu_bwd_dispatch(const __nv_bfloat16* dt, const __nv_bfloat16* t, const float* z, const float* stats, const float* gamma,
                          float* sums, __nv_bfloat16* dz, long long npix, long long n_stat, int C, int phase, cudaStream_t st) {
-  LAVT_REQUIRE(npix > 0 && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "bn backward: C=%d unsupported", C);
+  LAVT_REQUIRE(npix > 0 && C % 4 == 0 && C <= 1024, "bn backward: C=%d unsupported", C);
   if (phase == 0) {
     const int rg = 256 / (C / 4);
     bn_relu_bwd_reduce_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, static_cast<size_t>(rg) * C * 2 * sizeof(float), st>>>(
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) conv1x1_logits_bwd_kernel(const float* __
 
 int conv1x1_logits_bwd_dispatch(const float* dlog, const __nv_bfloat16* y, const float* w, __nv_bfloat16* dy, float* dw, float* db,
                                 long long npix, int C, cudaStream_t st) {
-  LAVT_REQUIRE(npix > 0 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "conv1x1 backward: C=%d unsupported", C);
+  LAVT_REQUIRE(npix > 0 && C % 8 == 0 && C <= 2048, "conv1x1 backward: C=%d unsupported", C);
   conv1x1_logits_bwd_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 2 * C * sizeof(float), st>>>(dlog, y, w, dy, dw, db, npix, C);
   LAVT_LAUNCH_CHECK("conv1x1_logits_bwd_kernel");
   return LAVT_OK;

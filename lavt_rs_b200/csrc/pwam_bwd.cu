@@ -17,6 +17,45 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// CPL consecutive elements per lane: 128-bit accesses when CPL is a multiple of 4 (C = 128 .. 1024), scalar otherwise (the Swin-T/S
+// widths 96 / 192: CPL = 3 / 6)
+template <int CPL>
+__device__ __forceinline__ void ld_f32(float (&o)[CPL], const float* __restrict__ p) {
+  if constexpr (CPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < CPL; i += 4) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(p + i));
+      o[i] = u.x; o[i + 1] = u.y; o[i + 2] = u.z; o[i + 3] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) o[i] = __ldg(p + i);
+  }
+}
+template <int CPL>
+__device__ __forceinline__ void ld_bf16(float (&o)[CPL], const __nv_bfloat16* __restrict__ p) {
+  if constexpr (CPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < CPL; i += 4) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + i));
+      const float2 a = unpack_bf16x2(w.x), c = unpack_bf16x2(w.y);
+      o[i] = a.x; o[i + 1] = a.y; o[i + 2] = c.x; o[i + 3] = c.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) o[i] = __bfloat162float(p[i]);
+  }
+}
+template <int CPL>
+__device__ __forceinline__ float dot_row(const float (&a)[CPL], const float* __restrict__ p) {
+  float k[CPL];
+  ld_f32<CPL>(k, p);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) s = fmaf(a[i], k[i], s);
+  return s;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // One warp per pixel (grid-strided); lane owns CPL = C / 32 contiguous channels, each fusion head's channels sit in a group
 // of 32 / heads lanes (same layout as pwam_core_kernel).  Per-warp shared memory: s, P, dP, dS for heads x NlPad words.
@@ -63,29 +102,17 @@ __global__ void __launch_bounds__(256) pwam_attend_bwd_kernel(const float* __res
   for (long long p = static_cast<long long>(blockIdx.x) * 8 + warp; p < n; p += total_warps) {
     const long long row = static_cast<long long>(b) * n + p;
     float qh[CPL], d[CPL], dq[CPL];
-    {
-      const float* src = qpre + row * C + c0;
-      const __nv_bfloat16* dsrc = dO + row * C + c0;
+    ld_f32<CPL>(qh, qpre + row * C + c0);
+    ld_bf16<CPL>(d, dO + row * C + c0);
 #pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(src + i));
-        qh[i] = (u.x - mu[i]) * rs[i]; qh[i + 1] = (u.y - mu[i + 1]) * rs[i + 1];
-        qh[i + 2] = (u.z - mu[i + 2]) * rs[i + 2]; qh[i + 3] = (u.w - mu[i + 3]) * rs[i + 3];
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(dsrc + i));
-        const float2 a = unpack_bf16x2(w.x), c = unpack_bf16x2(w.y);
-        d[i] = a.x; d[i + 1] = a.y; d[i + 2] = c.x; d[i + 3] = c.y;
-        dq[i] = dq[i + 1] = dq[i + 2] = dq[i + 3] = 0.f;
-      }
+    for (int i = 0; i < CPL; ++i) {
+      qh[i] = (qh[i] - mu[i]) * rs[i];
+      dq[i] = 0.f;
     }
     // pass 1: scores (kept in shared memory), running max / denominator per head
     float mx = -INFINITY, den = 0.f;
     for (int j = 0; j < Nl; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * C + i));
-        s = fmaf(qh[i], a.x, s); s = fmaf(qh[i + 1], a.y, s); s = fmaf(qh[i + 2], a.z, s); s = fmaf(qh[i + 3], a.w, s);
-      }
+      float s = dot_row<CPL>(qh, kb + static_cast<long long>(j) * C);
       for (int off = gl >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
       s = s * scale + (1e4f * __ldg(mb + j) - 1e4f);
       if (leader) hs[j] = s;
@@ -98,12 +125,7 @@ __global__ void __launch_bounds__(256) pwam_attend_bwd_kernel(const float* __res
     // pass 2: P, dP = dO . v_j, D = sum_j P dP
     float Dsum = 0.f;
     for (int j = 0; j < Nl; ++j) {
-      float dp = 0.f;
-#pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * C + i));
-        dp = fmaf(d[i], a.x, dp); dp = fmaf(d[i + 1], a.y, dp); dp = fmaf(d[i + 2], a.z, dp); dp = fmaf(d[i + 3], a.w, dp);
-      }
+      float dp = dot_row<CPL>(d, vb + static_cast<long long>(j) * C);
       for (int off = gl >> 1; off > 0; off >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, off);
       const float pj = __expf(hs[j] - mx) * inv;
       Dsum = fmaf(pj, dp, Dsum);
@@ -114,25 +136,34 @@ __global__ void __launch_bounds__(256) pwam_attend_bwd_kernel(const float* __res
     for (int j = 0; j < Nl; ++j) {
       const float ds = hp[j] * (hdp[j] - Dsum);
       if (leader) hds[j] = ds;
+      float kk[CPL];
+      ld_f32<CPL>(kk, kb + static_cast<long long>(j) * C);
 #pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * C + i));
-        dq[i] = fmaf(ds, a.x, dq[i]); dq[i + 1] = fmaf(ds, a.y, dq[i + 1]);
-        dq[i + 2] = fmaf(ds, a.z, dq[i + 2]); dq[i + 3] = fmaf(ds, a.w, dq[i + 3]);
-      }
+      for (int i = 0; i < CPL; ++i) dq[i] = fmaf(ds, kk[i], dq[i]);
     }
     __syncwarp();
     {
       float* dst = dqhat + row * C + c0;
       __nv_bfloat16* qdst = qs_out + row * C + c0;
 #pragma unroll
-      for (int i = 0; i < CPL; i += 4) {
-        float4 o = make_float4(dq[i] * scale, dq[i + 1] * scale, dq[i + 2] * scale, dq[i + 3] * scale);
-        *reinterpret_cast<float4*>(dst + i) = o;
-        s1[i] += o.x; s1[i + 1] += o.y; s1[i + 2] += o.z; s1[i + 3] += o.w;
-        s2[i] = fmaf(o.x, qh[i], s2[i]); s2[i + 1] = fmaf(o.y, qh[i + 1], s2[i + 1]);
-        s2[i + 2] = fmaf(o.z, qh[i + 2], s2[i + 2]); s2[i + 3] = fmaf(o.w, qh[i + 3], s2[i + 3]);
-        *reinterpret_cast<uint2*>(qdst + i) = make_uint2(pack_bf16x2(qh[i] * scale, qh[i + 1] * scale), pack_bf16x2(qh[i + 2] * scale, qh[i + 3] * scale));
+      for (int i = 0; i < CPL; ++i) {
+        const float o = dq[i] * scale;
+        dq[i] = o;
+        s1[i] += o;
+        s2[i] = fmaf(o, qh[i], s2[i]);
+      }
+      if constexpr (CPL % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < CPL; i += 4) {
+          *reinterpret_cast<float4*>(dst + i) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+          *reinterpret_cast<uint2*>(qdst + i) = make_uint2(pack_bf16x2(qh[i] * scale, qh[i + 1] * scale), pack_bf16x2(qh[i + 2] * scale, qh[i + 3] * scale));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          dst[i] = dq[i];
+          qdst[i] = __float2bfloat16(qh[i] * scale);
+        }
       }
     }
     // block-diagonal rows: columns of clip b carry P / dS, all other clips zero
@@ -176,12 +207,16 @@ int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float*
     break;                                                                                                             \
   }
   switch (C) {
+    LAVT_PAB_CASE(3)
     LAVT_PAB_CASE(4)
+    LAVT_PAB_CASE(6)
     LAVT_PAB_CASE(8)
+    LAVT_PAB_CASE(12)
     LAVT_PAB_CASE(16)
+    LAVT_PAB_CASE(24)
     LAVT_PAB_CASE(32)
     default:
-      set_last_error("pwam backward: C=%d unsupported (need 128/256/512/1024)", C);
+      set_last_error("pwam backward: C=%d unsupported (need 96/128/192/256/384/512/768/1024)", C);
       return LAVT_ERR_SHAPE;
   }
 #undef LAVT_PAB_CASE
@@ -236,7 +271,7 @@ __global__ void __launch_bounds__(256) pwam_mul_bwd_kernel(const __nv_bfloat16* 
 
 int pwam_mul_bwd_dispatch(const __nv_bfloat16* da2, const __nv_bfloat16* vis, const __nv_bfloat16* vispre, const float* langpre,
                           const float* stats, __nv_bfloat16* dvispre, float* sums, int B, long long n, int C, cudaStream_t st) {
-  LAVT_REQUIRE(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "pwam mul backward: C=%d unsupported (need 128/256/512/1024)", C);
+  LAVT_REQUIRE(C % 4 == 0 && C <= 1024, "pwam mul backward: C=%d unsupported (need a multiple of 4 up to 1024)", C);
   LAVT_REQUIRE(B > 0 && n > 0 && n < (1LL << 30), "pwam mul backward: bad sizes");
   const int rg = 256 / (C / 4);
   pwam_mul_bwd_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), B), 256, static_cast<size_t>(rg) * C * 2 * sizeof(float), st>>>(

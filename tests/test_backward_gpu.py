@@ -553,3 +553,46 @@ def test_image_model_training_through_public_api(tmp_path):
         bb.layers[1].blocks[0].mlp.fc1.weight.zero_()
     assert resume_checkpoint(path, model, opt, sched) == 0
     assert bb.layers[1].blocks[0].mlp.fc1.weight.abs().sum().item() > 0
+
+
+def test_swin_tiny_width_training_step():
+    """Swin-T / Swin-S widths (96, 192, 384, 768; 3-24 heads; decoder width 384) through the whole training step with stochastic
+    depth off: tile remainders in the dgrad / wgrad GEMMs, masked LayerNorm-backward lanes, scalar PWAM-backward lanes."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    cfg = O.OracleConfig(embed_dim=96, depths=(2, 2, 2, 2), num_heads=(3, 6, 12, 24), window=(8, 7, 7))
+    sd = O.random_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(51)
+    for s in range(3):
+        C = 96 * 2 ** s
+        for k in ("0", "2"):
+            sd[f"backbone.layers.{s}.res_gate.{k}.weight"] = torch.randn(C, C, generator=g) * C ** -0.5
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=96, depths=[2, 2, 2, 2], num_heads=[3, 6, 12, 24],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=None)
+    dec = SimpleDecoding(768, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    B, Tn, H, W, Nl = 2, 4, 64, 96, 20
+    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    m[1, 14:] = 0
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    lr = l.clone().requires_grad_()
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, lr, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, dl = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    check_direction(got, ref, "Swin-T width training step")
+    c, ratio = cos_and_ratio(dl, lr.grad)
+    assert c > 0.95 and 0.85 < ratio < 1.18, ("dl", c, ratio)
