@@ -234,6 +234,9 @@ int lavt_pwam_mul_norm_bwd(const void* da2, const void* vis, const void* vispre,
 /* InstanceNorm backward from the reductions: out bf16 = rstd * (g - S1/n - x^ S2/n); g = g_f32, or ga * gb (bf16) if g_f32 is NULL */
 int lavt_instnorm_bwd(const float* g_f32, const void* ga_bf16, const void* gb_bf16, const float* xpre, const float* stats, const float* sums,
                       void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream);
+/* InstanceNorm reductions of an fp32 gradient: sums [B,2,C] += (sum_n g, sum_n g * IN(xpre)) -- SepTPWAM's summed branches */
+int lavt_instnorm_bwd_reduce(const float* g, const float* xpre, const float* stats, float* sums, int32_t B, int64_t n, int32_t C,
+                             void* stream);
 /* Adjoint of lavt_pwam_kv: dkbuf / dvbuf fp32 [B*heads*NlPad, C] (the GEMM outputs above) -> dwk, dbk, dwv, dbv, dl (all +=) */
 int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv, float* dwk,
                      float* dbk, float* dwv, float* dbv, float* dl, int32_t B, int32_t Nl, int32_t NlPad, int32_t Lin, int32_t C,
@@ -243,7 +246,8 @@ int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, 
  *   mode 1: out_bf16 = f * b * (1 - tanh(a)^2); out_f32 = f2 + f * tanh(a)   (f = dx', f2 = gradient of r so far or NULL)
  *   mode 2: out_bf16 = a * [b > 0]                                (ReLU backward: a = dg1, b = g1)
  *   mode 3: out_bf16 = GELU(a), out_f32 = the same                (a = bf16 pre-activation)
- *   mode 4: out_bf16 = f * GELU'(a)                               (f = fp32 gradient) */
+ *   mode 4: out_bf16 = f * GELU'(a)                               (f = fp32 gradient)
+ *   mode 5: out_bf16 = out_f32 = GELU(a) + f                      (SepTPWAM: sum of the temporal and spatial GELU'd branches) */
 int lavt_gate_elementwise(int32_t mode, const void* a_bf16, const void* b_bf16, const float* f, const float* f2, void* out_bf16,
                           float* out_f32, int64_t count, void* stream);
 
@@ -261,9 +265,11 @@ int lavt_bn_relu_bwd_apply(const void* dt_bf16, const void* t_bf16, const float*
 /* NHWC bf16 [n,H,W,C] (pixel pitch ldi) -> [C, ldo] with column (img*(H+2) + h+1)*Wp + w+1 - dshift (Wp >= W+2, a multiple of 8;
  * dshift in {-1,0,1}); the caller zeroes the buffer (borders).  In this layout tap (ky,kx) of a 3x3 conv is the column offset
  * (ky-1)*Wp + (kx-1): the conv weight gradient is nine lavt_gemm_bf16_splitk calls, A = dz^T (dshift 0), Bt = the copy of x^T
- * written with dshift = kx-1, b_koff = (ky-1)*Wp (TMA needs 16-byte aligned inner coordinates, hence the three shifted copies). */
+ * written with dshift = kx-1, b_koff = (ky-1)*Wp (TMA needs 16-byte aligned inner coordinates, hence the three shifted copies).
+ * D > 0: the n_img frames are clips of D frames, each clip padded with a zero frame on either side (frame index -> clip*(D+2) + d+1):
+ * the 27 taps of a Conv3d(3,3,3) weight gradient (SepTPWAM) add (kz-1)*(H+2)*Wp to b_koff.  D = 0: 2-D. */
 int lavt_nhwc_pad_transpose(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t n_img, int32_t H, int32_t W, int32_t C,
-                            int32_t Wp, int32_t dshift, void* stream);
+                            int32_t Wp, int32_t dshift, int32_t D, void* stream);
 /* adjoint of the upsample half of lavt_upsample_concat: dprev bf16 [n,ph,pw,C1] from dcat bf16 [n,H,W,Ct] (channels 0..C1) */
 int lavt_upsample_concat_bwd(const void* dcat_bf16, int32_t Ct, void* dprev_bf16, int32_t ph, int32_t pw, int32_t C1, int32_t n_img, int32_t H,
                              int32_t W, void* stream);

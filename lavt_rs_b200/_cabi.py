@@ -118,7 +118,8 @@ SIGNATURES = {
     "lavt_bn_relu_apply": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_bn_relu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_bn_relu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
-    "lavt_nhwc_pad_transpose": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_nhwc_pad_transpose": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_instnorm_bwd_reduce": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_upsample_concat_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_conv1x1_logits_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -696,14 +697,23 @@ def bn_relu_bwd_apply(dt, t, z, stats, gamma, sums, dz, n_stat: int) -> None:
                                        _c(dz, torch.bfloat16, "dz").data_ptr(), npix, n_stat, Cn, stream_ptr()), "lavt_bn_relu_bwd_apply")
 
 
-def nhwc_pad_transpose(x_nhwc, out, wp: int, dshift: int = 0) -> None:
+def instnorm_bwd_reduce(g, xpre, stats, sums) -> None:
+    """sums fp32 [B,2,C] += (sum_n g, sum_n g * IN(xpre)); g, xpre fp32 [B,n,C]."""
+    B, n, Cn = xpre.shape
+    check(lib().lavt_instnorm_bwd_reduce(_c(g, torch.float32, "g").data_ptr(), _c(xpre, torch.float32, "xpre").data_ptr(),
+                                         _c(stats, torch.float32, "stats").data_ptr(), _c(sums, torch.float32, "sums").data_ptr(),
+                                         B, n, Cn, stream_ptr()), "lavt_instnorm_bwd_reduce")
+
+
+def nhwc_pad_transpose(x_nhwc, out, wp: int, dshift: int = 0, frames_per_clip: int = 0) -> None:
     """x bf16 [n,H,W,C] (last dim contiguous, pixel pitch x.stride(2)) -> out bf16 [C, >= n*(H+2)*wp], pre-zeroed by the caller;
-    pixel (img,h,w) lands in column (img*(H+2) + h+1)*wp + w+1 - dshift."""
+    pixel (img,h,w) lands in column (img*(H+2) + h+1)*wp + w+1 - dshift; with frames_per_clip = D > 0 the images are frames of clips that
+    get a zero frame on either side (img -> clip*(D+2) + d+1)."""
     _req(x_nhwc, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
     n, H, W, Cn = x_nhwc.shape
     check(lib().lavt_nhwc_pad_transpose(x_nhwc.data_ptr(), x_nhwc.stride(2), out.data_ptr(), out.stride(0),
-                                        n, H, W, Cn, wp, dshift, stream_ptr()), "lavt_nhwc_pad_transpose")
+                                        n, H, W, Cn, wp, dshift, frames_per_clip, stream_ptr()), "lavt_nhwc_pad_transpose")
 
 
 def upsample_concat_bwd(dcat, dprev) -> None:

@@ -381,6 +381,10 @@ int lavt_instnorm_bwd(const float* g_f32, const void* ga_bf16, const void* gb_bf
                       void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream) {
   return instnorm_bwd_dispatch(g_f32, CB(ga_bf16), CB(gb_bf16), xpre, stats, sums, MB(out_bf16), B, n, C, S(stream));
 }
+int lavt_instnorm_bwd_reduce(const float* g, const float* xpre, const float* stats, float* sums, int32_t B, int64_t n, int32_t C,
+                             void* stream) {
+  return instnorm_bwd_reduce_dispatch(g, xpre, stats, sums, B, n, C, S(stream));
+}
 int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv, float* dwk,
                      float* dbk, float* dwv, float* dbv, float* dl, int32_t B, int32_t Nl, int32_t NlPad, int32_t Lin, int32_t C,
                      int32_t heads, void* stream) {
@@ -404,8 +408,8 @@ int lavt_bn_relu_bwd_apply(const void* dt_bf16, const void* t_bf16, const float*
   return bn_relu_bwd_dispatch(CB(dt_bf16), CB(t_bf16), z, stats, gamma, const_cast<float*>(sums), MB(dz_bf16), npix, n_stat, C, 1, S(stream));
 }
 int lavt_nhwc_pad_transpose(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t n_img, int32_t H, int32_t W, int32_t C,
-                            int32_t Wp, int32_t dshift, void* stream) {
-  return nhwc_pad_transpose_dispatch(CB(in_bf16), ldi, MB(out_bf16), ldo, n_img, H, W, C, Wp, dshift, S(stream));
+                            int32_t Wp, int32_t dshift, int32_t D, void* stream) {
+  return nhwc_pad_transpose_dispatch(CB(in_bf16), ldi, MB(out_bf16), ldo, n_img, H, W, C, Wp, dshift, D, S(stream));
 }
 int lavt_upsample_concat_bwd(const void* dcat_bf16, int32_t Ct, void* dprev_bf16, int32_t ph, int32_t pw, int32_t C1, int32_t n_img, int32_t H,
                              int32_t W, void* stream) {

@@ -120,7 +120,7 @@ int bn_relu_bwd_dispatch(const __nv_bfloat16* dt, const __nv_bfloat16* t, const 
 // out[c, p' - dshift] = in[(img,h,w), c],  p' = (img*(H+2) + h+1)*Wp + w+1   (64 pixels x 64 channels per block through smem)
 __global__ void __launch_bounds__(256) nhwc_pad_transpose_kernel(const __nv_bfloat16* __restrict__ in, long long ldi,
                                                                  __nv_bfloat16* __restrict__ out, long long ldo, long long npix, int C, int H,
-                                                                 int W, int Wp, int dshift) {
+                                                                 int W, int Wp, int dshift, int D) {
   __shared__ unsigned short tile[64][66];
   __shared__ long long dcol[64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) nhwc_pad_transpose_kernel(const __nv_bflo
     long long d = -1;
     if (m < npix) {
       const int w = static_cast<int>(m % W), h = static_cast<int>((m / W) % H);
-      const long long img = m / (static_cast<long long>(W) * H);
+      long long img = m / (static_cast<long long>(W) * H);
+      if (D > 0) img = (img / D) * (D + 2) + img % D + 1;      // 3-D: frames of a clip padded with one zero frame on either side
       d = (img * (H + 2) + h + 1) * Wp + w + 1 - dshift;
     }
     dcol[threadIdx.x] = d;
@@ -156,13 +157,14 @@ __global__ void __launch_bounds__(256) nhwc_pad_transpose_kernel(const __nv_bflo
 }
 
 int nhwc_pad_transpose_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, int n_img, int H, int W, int C,
-                                int Wp, int dshift, cudaStream_t st) {
+                                int Wp, int dshift, int D, cudaStream_t st) {
   const long long npix = 1LL * n_img * H * W;
   LAVT_REQUIRE(npix > 0 && C % 2 == 0 && ldi % 2 == 0, "pad transpose: bad sizes");
   LAVT_REQUIRE(Wp >= W + 2 && dshift >= -1 && dshift <= 1, "pad transpose: padded width %d / shift %d invalid", Wp, dshift);
-  LAVT_REQUIRE(ldo >= 1LL * n_img * (H + 2) * Wp, "pad transpose: output pitch too small");
+  LAVT_REQUIRE(D == 0 || n_img % D == 0, "pad transpose: %d frames do not split into clips of %d", n_img, D);
+  LAVT_REQUIRE(ldo >= 1LL * (D > 0 ? n_img / D * (D + 2) : n_img) * (H + 2) * Wp, "pad transpose: output pitch too small");
   nhwc_pad_transpose_kernel<<<dim3(static_cast<unsigned>((npix + 63) / 64), static_cast<unsigned>((C + 63) / 64)), 256, 0, st>>>(
-      in, ldi, out, ldo, npix, C, H, W, Wp, dshift);
+      in, ldi, out, ldo, npix, C, H, W, Wp, dshift, D);
   LAVT_LAUNCH_CHECK("nhwc_pad_transpose_kernel");
   return LAVT_OK;
 }

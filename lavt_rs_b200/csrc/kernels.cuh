@@ -87,7 +87,7 @@ int bn_relu_apply_dispatch(const float* z, const float* stats, const float* gamm
 int bn_relu_bwd_dispatch(const __nv_bfloat16* dt, const __nv_bfloat16* t, const float* z, const float* stats, const float* gamma,
                          float* sums, __nv_bfloat16* dz, long long npix, long long n_stat, int C, int phase, cudaStream_t st);
 int nhwc_pad_transpose_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat16* out, long long ldo, int n_img, int H, int W, int C,
-                                int Wp, int dshift, cudaStream_t st);
+                                int Wp, int dshift, int D, cudaStream_t st);
 int upsample_concat_bwd_dispatch(const __nv_bfloat16* dcat, int Ct, __nv_bfloat16* dprev, int ph, int pw, int C1, int n_img, int H, int W,
                                  cudaStream_t st);
 int conv1x1_logits_bwd_dispatch(const float* dlog, const __nv_bfloat16* y, const float* w, __nv_bfloat16* dy, float* dw, float* db,
@@ -102,6 +102,8 @@ int pwam_mul_bwd_dispatch(const __nv_bfloat16* da2, const __nv_bfloat16* vis, co
                           const float* stats, __nv_bfloat16* dvispre, float* sums, int B, long long n, int C, cudaStream_t st);
 int instnorm_bwd_dispatch(const float* g32, const __nv_bfloat16* ga, const __nv_bfloat16* gb, const float* xpre, const float* stats,
                           const float* sums, __nv_bfloat16* out, int B, long long n, int C, cudaStream_t st);
+int instnorm_bwd_reduce_dispatch(const float* g, const float* xpre, const float* stats, float* sums, int B, long long n, int C,
+                                 cudaStream_t st);
 int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv,
                          float* dwk, float* dbk, float* dwv, float* dbv, float* dl, int B, int Nl, int NlPad, int Lin, int C, int heads,
                          cudaStream_t st);

@@ -281,6 +281,53 @@ int pwam_mul_bwd_dispatch(const __nv_bfloat16* da2, const __nv_bfloat16* vis, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// InstanceNorm reductions of an fp32 gradient g w.r.t. x^ = IN(x_pre): sums [B,2,C] += (sum_n g, sum_n g * x^).  SepTPWAM sums two
+// InstanceNorm'd branches (lib/video_swin_transformer.py:1512-1524, 1556-1561): the same g flows into both, each needs its own
+// reductions.  grid (chunks of 256 rows, B).
+__global__ void __launch_bounds__(256) instnorm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ xpre,
+                                                                  const float* __restrict__ stats, float* __restrict__ sums, int n, int C) {
+  extern __shared__ float ibr_sm[];       // [rg][C][2]
+  const int b = blockIdx.y;
+  const int tpr = C / 4, rg = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const int r0 = blockIdx.x * 256, r1 = min(n, r0 + 256);
+  if (tr < rg) {
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2) * C) + tc);
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<long long>(b) * 2 + 1) * C) + tc);
+    for (int r = r0 + tr; r < r1; r += rg) {
+      const long long e = (static_cast<long long>(b) * n + r) * C + tc * 4;
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + e)), x = __ldg(reinterpret_cast<const float4*>(xpre + e));
+      s1.x += gv.x; s1.y += gv.y; s1.z += gv.z; s1.w += gv.w;
+      s2.x += gv.x * (x.x - mu.x) * rs.x; s2.y += gv.y * (x.y - mu.y) * rs.y;
+      s2.z += gv.z * (x.z - mu.z) * rs.z; s2.w += gv.w * (x.w - mu.w) * rs.w;
+    }
+    float* o = ibr_sm + (static_cast<long long>(tr) * C + tc * 4) * 2;
+    o[0] = s1.x; o[1] = s2.x; o[2] = s1.y; o[3] = s2.y; o[4] = s1.z; o[5] = s2.z; o[6] = s1.w; o[7] = s2.w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < rg; ++k) {
+      a += ibr_sm[(k * C + c) * 2 + 0];
+      q += ibr_sm[(k * C + c) * 2 + 1];
+    }
+    atomicAdd(sums + (static_cast<long long>(b) * 2) * C + c, a);
+    atomicAdd(sums + (static_cast<long long>(b) * 2 + 1) * C + c, q);
+  }
+}
+
+int instnorm_bwd_reduce_dispatch(const float* g, const float* xpre, const float* stats, float* sums, int B, long long n, int C,
+                                 cudaStream_t st) {
+  LAVT_REQUIRE(C % 4 == 0 && C <= 1024 && B > 0 && n > 0 && n < (1LL << 30), "instance-norm backward reduce: bad sizes");
+  const int rg = 256 / (C / 4);
+  instnorm_bwd_reduce_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), B), 256, static_cast<size_t>(rg) * C * 2 * sizeof(float), st>>>(
+      g, xpre, stats, sums, static_cast<int>(n), C);
+  LAVT_LAUNCH_CHECK("instnorm_bwd_reduce_kernel");
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // InstanceNorm backward from the accumulated reductions: out = rstd * (g - S1/n - x^ * S2/n); g = g_f32, or ga * gb (bf16)
 __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const float* __restrict__ g32, const __nv_bfloat16* __restrict__ ga,
                                                            const __nv_bfloat16* __restrict__ gb, const float* __restrict__ xpre,
@@ -395,6 +442,7 @@ int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* ma
 // mode 2: out_bf16 = a * [b > 0]                                         (relu backward; a = dg1, b = g1)
 // mode 3: out_bf16 = GELU(a), out_f32 = the same in fp32                 (forward with fp32 copy; a = pre-activation)
 // mode 4: out_bf16 = f * GELU'(a)                                        (GELU backward with an fp32 gradient)
+// mode 5: out_bf16 = out_f32 = GELU(a) + f                               (SepTPWAM: sum of the two GELU'd branches)
 template <int MODE>
 __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ f,
                                                         const float4* __restrict__ f2, uint4* __restrict__ out_bf16,
@@ -414,7 +462,7 @@ __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w[j]); bv[2 * j] = t.x; bv[2 * j + 1] = t.y; }
   }
-  if (MODE == 0 || MODE == 1 || MODE == 4) {
+  if (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5) {
     const float4 x0 = __ldg(f + 2 * i), x1 = __ldg(f + 2 * i + 1);
     fv[0] = x0.x; fv[1] = x0.y; fv[2] = x0.z; fv[3] = x0.w; fv[4] = x1.x; fv[5] = x1.y; fv[6] = x1.z; fv[7] = x1.w;
   }
@@ -433,9 +481,10 @@ __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict_
     if (MODE == 2) ob[j] = bv[j] > 0.f ? av[j] : 0.f;
     if (MODE == 3) { ob[j] = gelu_erf(av[j]); of[j] = ob[j]; }
     if (MODE == 4) ob[j] = fv[j] * gelu_grad(av[j]);
+    if (MODE == 5) { ob[j] = gelu_erf(av[j]) + fv[j]; of[j] = ob[j]; }
   }
   if (MODE != 0) out_bf16[i] = make_uint4(pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]), pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
-  if (MODE == 0 || MODE == 1 || MODE == 3) {
+  if (MODE == 0 || MODE == 1 || MODE == 3 || MODE == 5) {
     out_f32[2 * i] = make_float4(of[0], of[1], of[2], of[3]);
     out_f32[2 * i + 1] = make_float4(of[4], of[5], of[6], of[7]);
   }
@@ -458,6 +507,7 @@ int gate_elem_dispatch(int mode, const __nv_bfloat16* a, const __nv_bfloat16* b,
     case 2: LAVT_REQUIRE(a && b && out_bf16, "relu backward: missing tensor"); gate_elem_kernel<2><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     case 3: LAVT_REQUIRE(a && out_bf16 && out_f32, "gelu forward: missing tensor"); gate_elem_kernel<3><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     case 4: LAVT_REQUIRE(a && f && out_bf16, "gelu backward: missing tensor"); gate_elem_kernel<4><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 5: LAVT_REQUIRE(a && f && out_bf16 && out_f32, "gelu sum: missing tensor"); gate_elem_kernel<5><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     default: set_last_error("gate kernels: bad mode %d", mode); return LAVT_ERR_SHAPE;
   }
   LAVT_LAUNCH_CHECK("gate_elem_kernel");

@@ -55,9 +55,16 @@ class GradStore:
         return self._alt_buf(param, "table_t", (param.shape[1], param.shape[0]), lambda b: b.t())
 
     def conv_taps(self, param: torch.Tensor) -> torch.Tensor:
-        """Conv2d weight [Cout, Cin, 3, 3] accumulated tap-major [Cout, (ky*3+kx)*Cin + ci] (the implicit-GEMM operand layout)."""
-        Cout, Cin, kh, kw = param.shape
-        return self._alt_buf(param, "taps", (Cout, kh * kw * Cin), lambda b: b.view(Cout, kh, kw, Cin).permute(0, 3, 1, 2))
+        """Conv2d / Conv3d weight [Cout, Cin, (kd,) kh, kw] accumulated tap-major [Cout, tap*Cin + ci] (the implicit-GEMM operand
+        layout, tap = (kz*3 + ky)*3 + kx or ky*3 + kx)."""
+        Cout, Cin = param.shape[:2]
+        ks = tuple(param.shape[2:])
+        taps = 1
+        for k in ks:
+            taps *= k
+        nd = len(ks)
+        perm = (0, nd + 1) + tuple(range(1, nd + 1))
+        return self._alt_buf(param, "taps", (Cout, taps * Cin), lambda b: b.view(Cout, *ks, Cin).permute(*perm))
 
     def padded_cols(self, param: torch.Tensor, cols: int) -> torch.Tensor:
         """Weight flattened to [out, in] with the input axis zero-padded to ``cols`` (patch-embed GEMM, K = 48 -> 64)."""
@@ -609,3 +616,227 @@ def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, 
         _count(1)
         dy = dprev.view(-1, C1)
     return (dy, dskips[2], dskips[1], dskips[0])       # dc4, dc3, dc2, dc1
+
+
+# ------------------------------------------------------------------------------------------------
+# SepTPWAM + LanguageGate under the README video flags (reference SepTPWAM.forward :1480-1584): every PWAM projection is the sum of
+# a Conv3d(3,3,3) branch and a Conv3d(1,1,1) branch
+# ------------------------------------------------------------------------------------------------
+def conv3d_bwd(dy: torch.Tensor, x5: torch.Tensor, conv, grads: GradStore, ws: Workspace, prepared: E.PreparedWeights, key: str, *,
+               dx_bf16: Optional[torch.Tensor] = None, dx_f32: Optional[torch.Tensor] = None, dx_resid: Optional[torch.Tensor] = None) -> None:
+    """Adjoint of y = Conv3d_333(x) + b (stride 1, zero padding 1).  dy bf16 [B*D*H*W, Cout]; x5 bf16 [B,D,H,W,Cin].
+    dW: 27 split-K GEMMs over the zero-padded transposed layouts (see ``_cbr_bwd``; frames get a zero frame on either side);
+    dx = the same implicit-GEMM convolution with flipped taps and Cin <-> Cout."""
+    B, D, H, W, Cin = x5.shape
+    Cout = conv.weight.shape[0]
+    dev = dy.device
+    npos = B * D * H * W
+    if conv.weight.requires_grad:
+        Wp = _pad8(W + 2)
+        Kp = B * (D + 2) * (H + 2) * Wp
+        dz_t = ws.get("bw_dzT", (Cout, Kp), torch.bfloat16, dev)
+        dz_t.zero_()
+        K.nhwc_pad_transpose(dy.view(B * D, H, W, Cout), dz_t, Wp, 0, frames_per_clip=D)
+        x_t = ws.get("bw_cxT", (3, Cin, Kp), torch.bfloat16, dev)
+        x_t.zero_()
+        for kx in range(3):
+            K.nhwc_pad_transpose(x5.view(B * D, H, W, Cin), x_t[kx], Wp, kx - 1, frames_per_clip=D)
+        gbuf = grads.conv_taps(conv.weight)
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Cout, Cin, Kp),), torch.float32, dev)
+        for tap in range(27):
+            kz, ky, kx = tap // 9, (tap // 3) % 3, tap % 3
+            K.gemm_bf16_splitk(dz_t, x_t[kx], gbuf[:, tap * Cin:(tap + 1) * Cin], part, accumulate=True,
+                               b_koff=(kz - 1) * (H + 2) * Wp + (ky - 1) * Wp)
+        _count(6 + 54)
+    if conv.bias is not None and conv.bias.requires_grad:
+        K.colsum_accumulate(dy, grads.of(conv.bias))
+        _count(1)
+    if dx_bf16 is not None or dx_f32 is not None:
+        def _wT():
+            wgt = conv.weight.detach()      # [Cout, Cin, 3, 3, 3] -> [Cin, flipped tap * Cout + co]
+            return wgt.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(wgt.shape[1], -1).to(torch.bfloat16).contiguous()
+        w_t = prepared.get(key + "_wT", [conv.weight], _wT)
+        K.conv3d_bf16(dy.view(B, D, H, W, Cout), w_t, out_bf16=dx_bf16, out_f32=dx_f32, resid=dx_resid)
+        _count(1)
+
+
+def sep_t_pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, D: int, H: int,
+                        W: int, ws: Workspace):
+    """Training twin of ``engine.sep_t_pwam_gate``: returns (r fp32 [B*n, C], gated x or None, saved)."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    heads = fusion.num_heads
+    Nl = l.shape[-1]
+    bf, f32 = torch.bfloat16, torch.float32
+
+    def w333(name, conv):
+        return pw.get(name, [conv.weight], lambda: _bf16(conv.weight.detach().permute(0, 2, 3, 4, 1).reshape(conv.weight.shape[0], -1)))
+
+    def w111(name, conv):
+        return pw.get(name, [conv.weight], lambda: _bf16(conv.weight.detach().reshape(conv.weight.shape[0], -1)))
+
+    def b_(conv):
+        return conv.bias.detach()
+
+    def rows(dtype):
+        return torch.empty(N_, C, device=dev, dtype=dtype)
+    xb5 = xb.view(B, D, H, W, C)
+    t32 = ws.get("sp_t32", (N_, C), f32, dev)
+    scr32 = ws.get("sp_scr32", (N_, C), f32, dev)
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), f32, dev)
+    ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
+    # ts_vis = GELU(conv333(x)) + GELU(conv111(x))
+    vt, vs_ = fusion.temporal_vis_project[0], fusion.spatial_vis_project[0]
+    vt_pre, vs_pre, vis = rows(bf), rows(bf), rows(bf)
+    K.conv3d_bf16(xb5, w333("vis_t", vt), bias=b_(vt), out_bf16=vt_pre)
+    K.gemm_bf16(xb, w111("vis_s", vs_), bias=b_(vs_), out_bf16=vs_pre)
+    K.gate_elementwise(3, vt_pre, out_bf16=vis, out_f32=t32)
+    K.gate_elementwise(5, vs_pre, f=t32, out_bf16=vis, out_f32=scr32)
+    # query = IN3d(conv333(x)) + IN3d(conv111(x))
+    qt, qs_ = fusion.f_query_t[0], fusion.f_query_s[0]
+    qa, qb, qhat = (torch.empty(B, n, C, device=dev, dtype=f32) for _ in range(3))
+    sa_q, sb_q = (torch.empty(B, 2, C, device=dev, dtype=f32) for _ in range(2))
+    K.conv3d_bf16(xb5, w333("q_t", qt), bias=b_(qt), out_f32=qa.view(N_, C))
+    K.gemm_bf16(xb, w111("q_s", qs_), bias=b_(qs_), out_f32=qb.view(N_, C))
+    K.instnorm_stats(qa, sa_q, stw)
+    K.instnorm_stats(qb, sb_q, stw)
+    K.instnorm_sum2(qa, sa_q, qb, sb_q, qhat)
+    k_w = pw.get("k_w", [fusion.f_key[0].weight], lambda: _f32(fusion.f_key[0].weight[:, :, 0]))
+    v_w = pw.get("v_w", [fusion.f_value[0].weight], lambda: _f32(fusion.f_value[0].weight[:, :, 0]))
+    kk = torch.empty(B, Nl, C, device=dev, dtype=f32)
+    vv = torch.empty(B, Nl, C, device=dev, dtype=f32)
+    K.pwam_kv(l, mask, k_w, b_(fusion.f_key[0]), v_w, b_(fusion.f_value[0]), kk, vv)
+    o = torch.empty(B, n, C, device=dev, dtype=bf)
+    K.pwam_attend(qhat, ident, kk, vv, mask, o, heads)
+    # lang = IN3d(conv333(o)) + IN3d(conv111(o))
+    Wt, Ws = fusion.W_t[0], fusion.W_s[0]
+    la, lb, lang = (torch.empty(B, n, C, device=dev, dtype=f32) for _ in range(3))
+    sa_l, sb_l = (torch.empty(B, 2, C, device=dev, dtype=f32) for _ in range(2))
+    K.conv3d_bf16(o.view(B, D, H, W, C), w333("W_t", Wt), bias=b_(Wt), out_f32=la.view(N_, C))
+    K.gemm_bf16(o.view(N_, C), w111("W_s", Ws), bias=b_(Ws), out_f32=lb.view(N_, C))
+    K.instnorm_stats(la, sa_l, stw)
+    K.instnorm_stats(lb, sb_l, stw)
+    K.instnorm_sum2(la, sa_l, lb, sb_l, lang)
+    a2 = torch.empty(B, n, C, device=dev, dtype=bf)
+    K.pwam_mul_norm(vis.view(B, n, C), lang, ident, a2)
+    # r = GELU(conv333(mm)) + GELU(conv111(mm))
+    mt, ms = fusion.project_mm_t[0], fusion.project_mm_s[0]
+    rt_pre, rs_pre, rb = rows(bf), rows(bf), rows(bf)
+    r32 = rows(f32)
+    K.conv3d_bf16(a2.view(B, D, H, W, C), w333("mm_t", mt), bias=b_(mt), out_bf16=rt_pre)
+    K.gemm_bf16(a2.view(N_, C), w111("mm_s", ms), bias=b_(ms), out_bf16=rs_pre)
+    K.gate_elementwise(3, rt_pre, out_bf16=rb, out_f32=t32)
+    K.gate_elementwise(5, rs_pre, f=t32, out_bf16=rb, out_f32=r32)
+    _count(27)
+    g1 = g2 = xg = None
+    if res_gate is not None:
+        g0w = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2w = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1, g2 = rows(bf), rows(bf)
+        K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
+        K.gemm_bf16(g1, g2w, out_bf16=g2)
+        xg = rows(f32)
+        K.gate_elementwise(0, g2, rb, f=x, out_f32=xg)
+        _count(3)
+    saved = dict(xb=xb, vt_pre=vt_pre, vs_pre=vs_pre, vis=vis, qa=qa, qb=qb, qhat=qhat, sa_q=sa_q, sb_q=sb_q, kk=kk, vv=vv, o=o, la=la,
+                 lb=lb, lang=lang, sa_l=sa_l, sb_l=sb_l, a2=a2, rt_pre=rt_pre, rs_pre=rs_pre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B,
+                 dims=(D, H, W), heads=heads, k_w=k_w, v_w=v_w, ident=ident)
+    return r32, xg, saved
+
+
+def sep_t_pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: Optional[torch.Tensor], grads: GradStore,
+                        ws: Workspace, dl: torch.Tensor) -> torch.Tensor:
+    """Adjoint of ``sep_t_pwam_gate_fwd`` (same contract as ``pwam_gate_bwd``)."""
+    s = saved
+    B, heads = s["B"], s["heads"]
+    D, H, W = s["dims"]
+    xb = s["xb"]
+    N_, C = xb.shape
+    n = N_ // B
+    dev = xb.device
+    bf, f32 = torch.bfloat16, torch.float32
+    pw = fusion.prepared
+    ident = s["ident"]
+    Nl = s["l"].shape[-1]
+    nlp = _nl_pad(Nl)
+
+    def wsb(name, dtype=bf):
+        return ws.get("bw_sp_" + name, (N_, C), dtype, dev)
+    dr = dr_out
+    if res_gate is not None and dxg is not None:
+        dg2pre = wsb("a")
+        if dr is None:
+            dr = wsb("dr", f32)
+            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
+        else:
+            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
+        dg1 = wsb("b")
+        linear_bwd(dg2pre, s["g1"], res_gate[2].weight, None, grads, ws, pw, "g2", dx_bf16=dg1)
+        K.gate_elementwise(2, dg1, s["g1"], out_bf16=dg1)
+        linear_bwd(dg1, s["rb"], res_gate[0].weight, None, grads, ws, pw, "g0", dx_f32=dr, dx_resid=dr)
+        _count(2)
+    if dr is None:
+        raise K.LavtError("SepTPWAM backward: neither the stage output nor the gated features carry a gradient")
+    a2 = s["a2"].view(N_, C)
+    o = s["o"].view(N_, C)
+    vis = s["vis"]
+    # r = GELU(rt_pre) + GELU(rs_pre)
+    drt, drs = wsb("a"), wsb("b")
+    K.gate_elementwise(4, s["rt_pre"], f=dr, out_bf16=drt)
+    K.gate_elementwise(4, s["rs_pre"], f=dr, out_bf16=drs)
+    acc32 = wsb("acc32", f32)
+    da2 = wsb("c")
+    mt, ms = fusion.project_mm_t[0], fusion.project_mm_s[0]
+    linear_bwd(drs, a2, ms.weight, ms.bias, grads, ws, pw, "mm_s", dx_f32=acc32)
+    conv3d_bwd(drt, a2.view(B, D, H, W, C), mt, grads, ws, pw, "mm_t", dx_bf16=da2, dx_resid=acc32)
+    # a2 = vis * (IN(la) + IN(lb)),  vis = GELU(vt_pre) + GELU(vs_pre)
+    sums = torch.zeros(6, B, 2, C, device=dev, dtype=f32)
+    scratch, dvt, dvs = wsb("a"), wsb("d"), wsb("e")
+    K.pwam_mul_norm_bwd(da2, vis, s["vt_pre"], s["la"], s["sa_l"], scratch, sums[0])        # reductions of the temporal branch
+    K.pwam_mul_norm_bwd(da2, vis, s["vt_pre"], s["lb"], s["sb_l"], scratch, sums[1])        # ... of the spatial branch
+    K.pwam_mul_norm_bwd(da2, vis, s["vt_pre"], s["lang"], ident, dvt, sums[2])              # d vt_pre = da2 * lang * GELU'(vt_pre)
+    K.pwam_mul_norm_bwd(da2, vis, s["vs_pre"], s["lang"], ident, dvs, sums[3])
+    dla, dlb = wsb("a"), wsb("b")
+    K.instnorm_bwd(s["la"], s["sa_l"], sums[0], dla, ga=da2, gb=vis)
+    K.instnorm_bwd(s["lb"], s["sb_l"], sums[1], dlb, ga=da2, gb=vis)
+    Wt, Ws = fusion.W_t[0], fusion.W_s[0]
+    do = wsb("c")
+    linear_bwd(dlb, o, Ws.weight, Ws.bias, grads, ws, pw, "W_s", dx_f32=acc32)
+    conv3d_bwd(dla, o.view(B, D, H, W, C), Wt, grads, ws, pw, "W_t", dx_bf16=do, dx_resid=acc32)
+    # pixel-word attention core on q^ = IN(qa) + IN(qb)
+    Wd = B * heads * nlp
+    dqhat = ws.get("bw_pw_dq", (B, n, C), f32, dev)
+    qs = wsb("a")
+    p_bd = ws.get("bw_pw_pbd", (N_, Wd), bf, dev)
+    ds_bd = ws.get("bw_pw_dsbd", (N_, Wd), bf, dev)
+    K.pwam_attend_bwd(s["qhat"], ident, s["kk"], s["vv"], s["mask"], do, dqhat, qs, p_bd, ds_bd, sums[2], heads, nlp)
+    dkv = torch.empty(2, Wd, C, device=dev, dtype=f32)
+    for buf, dy_rows, x_rows in ((dkv[0], ds_bd, qs), (dkv[1], p_bd, do)):
+        part = ws.get("bw_splitk", (K.splitk_workspace_floats(Wd, C, N_),), f32, dev)
+        K.gemm_bf16_wgrad(dy_rows, x_rows, buf, part, accumulate=False)
+    fk, fv = fusion.f_key[0], fusion.f_value[0]
+    K.pwam_kv_bwd(dkv[0], dkv[1], s["mask"], s["l"], s["k_w"], s["v_w"],
+                  grads.of(fk.weight) if fk.weight.requires_grad else None, grads.of(fk.bias) if fk.bias.requires_grad else None,
+                  grads.of(fv.weight) if fv.weight.requires_grad else None, grads.of(fv.bias) if fv.bias.requires_grad else None,
+                  dl, heads, nlp)
+    K.instnorm_bwd_reduce(dqhat, s["qa"], s["sa_q"], sums[4])
+    K.instnorm_bwd_reduce(dqhat, s["qb"], s["sb_q"], sums[5])
+    dqa, dqb = wsb("b"), wsb("c")
+    K.instnorm_bwd(s["qa"], s["sa_q"], sums[4], dqa, g_f32=dqhat)
+    K.instnorm_bwd(s["qb"], s["sb_q"], sums[5], dqb, g_f32=dqhat)
+    # the four projections of x
+    if dxg is not None:
+        dx, first = dxg, dxg
+    else:
+        dx, first = torch.empty(N_, C, device=dev, dtype=f32), None
+    vt, vs_ = fusion.temporal_vis_project[0], fusion.spatial_vis_project[0]
+    qt, qs_ = fusion.f_query_t[0], fusion.f_query_s[0]
+    xb5 = xb.view(B, D, H, W, C)
+    linear_bwd(dvs, xb, vs_.weight, vs_.bias, grads, ws, pw, "vis_s", dx_f32=dx, dx_resid=first)
+    linear_bwd(dqb, xb, qs_.weight, qs_.bias, grads, ws, pw, "q_s", dx_f32=dx, dx_resid=dx)
+    conv3d_bwd(dvt, xb5, vt, grads, ws, pw, "vis_t", dx_f32=dx, dx_resid=dx)
+    conv3d_bwd(dqa, xb5, qt, grads, ws, pw, "q_t", dx_f32=dx, dx_resid=dx)
+    _count(24)
+    return dx

@@ -13,7 +13,7 @@ Mirrors the inner loop of the reference's ``train_one_epoch_*`` (train.py:330-36
   (replaces DistributedDataParallel, train.py:590-593).
 
 Stochastic depth (DropPath) runs as a per-sample scale inside the proj / fc2 GEMM epilogues.  Not implemented in training mode
-(raise, no fallback): --hs / --version variants, SepTPWAM, windows above ~400 tokens (8x12x12).  The 2-D image models
+(raise, no fallback): --hs / --version variants, windows above ~400 tokens (8x12x12).  The 2-D image models
 (lavt / lavt_one) train through the same code with one frame per clip.  The text encoder's own backward runs through the stock ``transformers``
 module under autograd (SURVEY.md section 8f-2 marks the text side as the next row, not the hot path).
 """
@@ -31,8 +31,8 @@ from . import train_engine as T
 def _check_trainable(model) -> None:
     bb = model.backbone
     for layer in bb.layers:
-        if layer.hs or layer.sep_t_pwam or layer.version != "default":
-            raise NotImplementedError("training on the B200 path supports the default PWAM + LanguageGate configuration only")
+        if layer.hs or layer.version != "default":
+            raise NotImplementedError("training on the B200 path supports PWAM / SepTPWAM with the default LanguageGate (no --hs / --version)")
     if tuple(bb.out_indices) != (0, 1, 2, 3):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
 
@@ -65,7 +65,10 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
             blocks.append(sv)
         last = layer.downsample is None
         gate = layer.res_gate if (layer.has_gate and not last) else None      # the last stage's gated features are unused (:570-587)
-        r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
+        if layer.sep_t_pwam:
+            r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
+        else:
+            r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
         norm = getattr(bb, f"norm{i}")
         ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
         K.layernorm_rows(r32, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
@@ -109,11 +112,9 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
         dxg = None
         if merge_saved is not None:
             dxg = T.patch_merging_bwd(layer.downsample, merge_saved, dx_next, grads, ws)
-        if has_gate:
-            dx = T.pwam_gate_bwd(layer.fusion, layer.res_gate, pw_saved, dr, dxg, grads, ws, dl)
-        else:
-            # no gate on this stage: x feeds the next stage directly, so dxg is the residual-stream gradient itself
-            dx = T.pwam_gate_bwd(layer.fusion, None, pw_saved, dr, dxg, grads, ws, dl)
+        fuse_bwd = T.sep_t_pwam_gate_bwd if layer.sep_t_pwam else T.pwam_gate_bwd
+        # without a gate on this stage x feeds the next stage directly, so dxg is the residual-stream gradient itself
+        dx = fuse_bwd(layer.fusion, layer.res_gate if has_gate else None, pw_saved, dr, dxg, grads, ws, dl)
         for bi in range(layer.depth - 1, -1, -1):
             dx = T.swin_block_bwd(layer.blocks[bi], blocks[bi], dx, grads, ws)
         dx_next = dx

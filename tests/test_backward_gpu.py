@@ -596,3 +596,100 @@ def test_swin_tiny_width_training_step():
     check_direction(got, ref, "Swin-T width training step")
     c, ratio = cos_and_ratio(dl, lr.grad)
     assert c > 0.95 and 0.85 < ratio < 1.18, ("dl", c, ratio)
+
+
+SEP_FLAGS = ["--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d_kernel_size_s", "1-1-1", "--w_t3x3_s1x1", "--mm_t3x3_s1x1"]
+
+
+def _sep_setup(embed=128, heads=(4, 8, 16, 32)):
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(embed_dim=embed, depths=(2, 2, 2, 2), num_heads=heads, window=(8, 7, 7), sep_t_pwam=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=embed, depths=[2, 2, 2, 2], num_heads=list(heads), window_size=(8, 7, 7),
+                                     drop_path_rate=0.0, patch_norm=True, args=default_args(SEP_FLAGS))
+    load_reference_state_dict(bb, sd, "backbone.")
+    return cfg, sd, bb.cuda().train()
+
+
+@pytest.mark.parametrize("stage,gate", [(0, True), (2, False)])
+def test_sep_t_pwam_gate_backward(stage, gate):
+    """SepTPWAM under the README video flags (Conv3d(3,3,3) + Conv3d(1,1,1) branches, summed InstanceNorms) + LanguageGate:
+    every gradient vs autograd through the oracle."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    cfg, sd, bb = _sep_setup()
+    layer = bb.layers[stage]
+    C = 128 * 2 ** stage
+    B, D, H, W, Nl = 2, 4, 9, 10, 17
+    n = D * H * W
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(B, D, H, W, C, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl, 1)
+    m[0, Nl - 4:] = 0
+    gr = torch.randn(B, n, C, generator=g)
+    gx = torch.randn(B, n, C, generator=g)
+    pre = f"backbone.layers.{stage}."
+    sd = dict(sd)
+    for k in ("res_gate.0.weight", "res_gate.2.weight"):
+        sd[pre + k] = torch.randn(C, C, generator=g) * C ** -0.5
+    with torch.no_grad():
+        layer.res_gate[0].weight.copy_(sd[pre + "res_gate.0.weight"])
+        layer.res_gate[2].weight.copy_(sd[pre + "res_gate.2.weight"])
+
+    def fn(sd2, xx, ll):
+        r = O.sep_t_pwam(xx, ll, m, sd2, pre + "fusion.", 1)
+        if not gate:
+            return r
+        return torch.cat([r, O.language_gate(xx.reshape(B, n, C), r, sd2, pre + "res_gate.")], 0)
+    gout = torch.cat([gr, gx], 0) if gate else gr
+    (dx_ref, dl_ref), pg_ref = _oracle_grads(fn, sd, pre, [x, l], gout)
+    pg_ref = {k: v for k, v in pg_ref.items() if k.startswith("fusion.") or (gate and k.startswith("res_gate."))}
+    ws = E.workspace("cuda")
+    grads = T.GradStore()
+    xf = x.cuda().reshape(-1, C).contiguous()
+    r32, xg, saved = T.sep_t_pwam_gate_fwd(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate if gate else None, l.cuda(),
+                                           m.squeeze(-1).cuda(), B, D, H, W, ws)
+    ref = fn(sd, x, l)
+    assert rel_l2(r32, ref[:B].reshape(-1, C)) < 1.5e-2
+    dl = torch.zeros(B, 768, Nl, device="cuda")
+    dx = T.sep_t_pwam_gate_bwd(layer.fusion, layer.res_gate if gate else None, saved, gr.cuda().reshape(-1, C).contiguous(),
+                               gx.cuda().reshape(-1, C).contiguous() if gate else None, grads, ws, dl)
+    torch.cuda.synchronize()
+    assert rel_l2(dx, dx_ref.reshape(-1, C)) < GRAD_L2, ("dx", rel_l2(dx, dx_ref.reshape(-1, C)))
+    assert rel_l2(dl, dl_ref) < GRAD_L2, ("dl", rel_l2(dl, dl_ref))
+    check_grads(grads.named(layer), pg_ref, f"SepTPWAM stage {stage}")
+
+
+def test_sep_t_pwam_tiny_training_step():
+    """The README's video configuration (--swin_type tiny widths + SepTPWAM flags) through one whole training step."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    cfg, sd, bb = _sep_setup(96, (3, 6, 12, 24))
+    dec = SimpleDecoding(768, None)
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    g = torch.Generator().manual_seed(71)
+    B, Tn, H, W, Nl = 2, 4, 64, 96, 20
+    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    m[0, 15:] = 0
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    lr = l.clone().requires_grad_()
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, lr, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, dl = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    # the reference zero-initialises the gates: their gradients are exactly zero on both sides and carry no direction
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None and "res_gate" not in k}
+    check_direction(got, ref, "SepTPWAM tiny training step")

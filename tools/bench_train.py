@@ -35,6 +35,7 @@ def main():
     p.add_argument("--frozen-text", action="store_true", help="do not backpropagate into the text encoder")
     p.add_argument("--optimizer", action="store_true", help="include the AdamW update (FusedAdamW over the reference's parameter groups, "
                                                             "poly LR) in the timed step")
+    p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
     a = p.parse_args()
 
@@ -54,6 +55,7 @@ def main():
     from lavt_rs_b200 import training as TR
     K.check(K.lib().lavt_check_device(), "lavt_check_device")
 
+    B0.SEP_T_PWAM = bool(a.sep_t_pwam)
     model = B0.build_model(False, dev).train()
     for layer in model.backbone.layers:
         for blk in layer.blocks:
@@ -144,7 +146,7 @@ def main():
 
     total = Bc * world
     value = total * a.steps / (ms * 1e-3)
-    flops_clip = 3.0 * (2074.8e9 - 3.4e9)          # forward + input gradients + weight gradients of every contraction
+    flops_clip = 3.0 * (2074.8e9 - 3.4e9 + (1043.6e9 if a.sep_t_pwam else 0.0))          # forward + input gradients + weight gradients of every contraction
     g = fam.get("gemm_bf16_tc_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
     ab = fam.get("window_attn_bwd_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
     af = fam.get("window_attn_kernel", {"launches": 0, "ms": 0.0, "flops": 0.0})
