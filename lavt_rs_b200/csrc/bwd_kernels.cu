@@ -213,11 +213,14 @@ int gelu_bwd_dispatch(const __nv_bfloat16* dy, const __nv_bfloat16* x, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm backward.  A warp walks groups of 32 OUTPUT rows (the closed-form gathers are evaluated one row per lane and
+// LayerNorm backward.  A warp walks groups of LNB_G OUTPUT rows (the closed-form gathers are evaluated one row per lane and
 // broadcast); d gamma / d beta accumulate in registers over all rows of the block, are combined in shared memory and leave
-// the block as one atomicAdd per channel.
+// the block as one atomicAdd per channel.  Each row is a chain of three dependent global round trips and four warp reductions,
+// so throughput comes from resident warps: small row groups (many blocks) and, for widths up to 512, two blocks per SM
+// (the first version -- 32-row groups, one 254-register block per SM -- ran at 1/7 of the HBM rate: 156 us for 18 432 x 512).
+constexpr int LNB_G = 8;
 template <int MODE, int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, const long long rows_per_block) {
+__global__ void __launch_bounds__(256, (NV <= 4) ? 2 : 1) ln_bwd_kernel(const LnBwdParams p, const long long rows_per_block) {
   extern __shared__ float lnb_red[];      // [2 * Cn]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Cn = (MODE == MODE_MERGE) ? 4 * p.C : p.C;
@@ -235,10 +238,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, const 
   const int H2 = (p.mH + 1) >> 1, W2 = (p.mW + 1) >> 1;
   const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
 
-  for (long long m0 = b0 + warp * 32; m0 < b1; m0 += 8 * 32) {
+  for (long long m0 = b0 + warp * LNB_G; m0 < b1; m0 += 8 * LNB_G) {
     long long myrow = m0 + lane;
-    if (MODE == MODE_WINDOW) myrow = (m0 + lane < b1) ? win_token(p.win, m0 + lane).row : -1;
-    for (int r = 0; r < 32; ++r) {
+    if (MODE == MODE_WINDOW) myrow = (lane < LNB_G && m0 + lane < b1) ? win_token(p.win, m0 + lane).row : -1;
+#pragma unroll 1
+    for (int r = 0; r < LNB_G; ++r) {
       const long long m = m0 + r;
       if (m >= b1) break;
       const long long row = __shfl_sync(0xffffffffu, myrow, r);
@@ -339,10 +343,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, const 
 
 template <int MODE, int NV>
 static void launch_ln_bwd_nv(const LnBwdParams& p, int Cn, cudaStream_t st) {
-  long long blocks = (p.M + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  constexpr int ROWS = 8 * LNB_G;                 // rows per block iteration
+  long long blocks = (p.M + ROWS - 1) / ROWS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   long long rpb = (p.M + blocks - 1) / blocks;
-  rpb = (rpb + 255) / 256 * 256;
+  rpb = (rpb + ROWS - 1) / ROWS * ROWS;
   blocks = (p.M + rpb - 1) / rpb;
   ln_bwd_kernel<MODE, NV><<<static_cast<unsigned>(blocks), 256, 2 * Cn * sizeof(float), st>>>(p, rpb);
 }

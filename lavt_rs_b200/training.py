@@ -31,8 +31,8 @@ from . import train_engine as T
 def _check_trainable(model) -> None:
     bb = model.backbone
     for layer in bb.layers:
-        if layer.hs or layer.version != "default":
-            raise NotImplementedError("training on the B200 path supports PWAM / SepTPWAM with the default LanguageGate (no --hs / --version)")
+        if layer.version != "default":
+            raise NotImplementedError("training on the B200 path supports PWAM / SepTPWAM with the default LanguageGate (no --version ablations)")
     if tuple(bb.out_indices) != (0, 1, 2, 3):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
 
@@ -64,21 +64,23 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
                                         xb_out=xb if bi == layer.depth - 1 else None)
             blocks.append(sv)
         last = layer.downsample is None
-        gate = layer.res_gate if (layer.has_gate and not last) else None      # the last stage's gated features are unused (:570-587)
+        # the last stage's gated features are unused (:570-587) unless --hs makes them the stage output (:579-587)
+        gate = layer.res_gate if (layer.has_gate and (not last or layer.hs)) else None
         if layer.sep_t_pwam:
             r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
         else:
             r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
         norm = getattr(bb, f"norm{i}")
         ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
-        K.layernorm_rows(r32, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
+        out_src = ((xg if xg is not None else feat) if layer.hs else r32)      # --hs: stage output = gated features instead of the residual
+        K.layernorm_rows(out_src, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
         E._count(1)
         maps.append(ob)
         merge_saved = None
         if not last:
             src = xg if xg is not None else feat
             feat, merge_saved = T.patch_merging_fwd(src, layer.downsample, B, D, Hc, Wc, ws)
-        stages.append((blocks, pw_saved, r32, merge_saved, gate is not None))
+        stages.append((blocks, pw_saved, out_src, merge_saved, gate is not None, bool(layer.hs)))
         if not last:
             Hc, Wc = (Hc + 1) // 2, (Wc + 1) // 2
     c1, c2, c3, c4 = maps
@@ -104,17 +106,28 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
     dx_next: Optional[torch.Tensor] = None
     for i in range(len(bb.layers) - 1, -1, -1):
         layer = bb.layers[i]
-        blocks, pw_saved, r32, merge_saved, has_gate = tape["stages"][i]
+        blocks, pw_saved, out_src, merge_saved, has_gate, hs = tape["stages"][i]
         norm = getattr(bb, f"norm{i}")
-        dr = torch.empty_like(r32)
-        K.layernorm_rows_bwd(r32, dcs[3 - i], norm.weight, dr, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
-        E._count(1)
         dxg = None
         if merge_saved is not None:
             dxg = T.patch_merging_bwd(layer.downsample, merge_saved, dx_next, grads, ws)
-        fuse_bwd = T.sep_t_pwam_gate_bwd if layer.sep_t_pwam else T.pwam_gate_bwd
-        # without a gate on this stage x feeds the next stage directly, so dxg is the residual-stream gradient itself
-        dx = fuse_bwd(layer.fusion, layer.res_gate if has_gate else None, pw_saved, dr, dxg, grads, ws, dl)
+        if hs:      # the stage output is the gated x': its gradient joins the one coming back through PatchMerging
+            dr = None
+            if dxg is None:
+                dxg = torch.empty_like(out_src)
+                K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dxg, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
+            else:
+                K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dxg, grads.of(norm.weight), grads.of(norm.bias), dres=dxg, eps=norm.eps)
+        else:
+            dr = torch.empty_like(out_src)
+            K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dr, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
+        E._count(1)
+        if dr is None and not has_gate:
+            dx = dxg        # --hs without a gate: x' = x and the fusion output is unused (no gradient for its parameters)
+        else:
+            fuse_bwd = T.sep_t_pwam_gate_bwd if layer.sep_t_pwam else T.pwam_gate_bwd
+            # without a gate on this stage x feeds the next stage directly, so dxg is the residual-stream gradient itself
+            dx = fuse_bwd(layer.fusion, layer.res_gate if has_gate else None, pw_saved, dr, dxg, grads, ws, dl)
         for bi in range(layer.depth - 1, -1, -1):
             dx = T.swin_block_bwd(layer.blocks[bi], blocks[bi], dx, grads, ws)
         dx_next = dx

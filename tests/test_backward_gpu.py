@@ -693,3 +693,44 @@ def test_sep_t_pwam_tiny_training_step():
     # the reference zero-initialises the gates: their gradients are exactly zero on both sides and carry no direction
     ref = {k: v.grad for k, v in leaf.items() if v.grad is not None and "res_gate" not in k}
     check_direction(got, ref, "SepTPWAM tiny training step")
+
+
+def test_hs_training_step():
+    """--hs (stage output = gated features E_i instead of the PWAM residual, reference :579-587): the decoder gradient enters the
+    residual stream through the gate, including at the last stage."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), hs=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(81)
+    for s in range(4):
+        C = 128 * 2 ** s
+        for k in ("0", "2"):
+            sd[f"backbone.layers.{s}.res_gate.{k}.weight"] = torch.randn(C, C, generator=g) * C ** -0.5
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=default_args(["--hs"]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    B, Tn, H, W, Nl = 2, 4, 96, 64, 12
+    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, l, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, _ = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    assert any(k.startswith("backbone.layers.3.res_gate") for k in ref), "with --hs the last stage's gate is live"
+    check_direction(got, ref, "--hs training step")
