@@ -233,11 +233,15 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
  * backward pass (training step)
  * ------------------------------------------------------------------------------------------------ */
 static void splitk_plan(int M, int N, int K, int* ksplit, int* kbs) {
-  const long long tiles = 1LL * ((M + 127) / 128) * ((N + 127) / 128);
+  // One wave of work items: (tile, split) pairs should fill the CTA slots of the variant gemm_variant() will pick, not overflow
+  // them (tiles x 5 = 320 items on 296 slots ran as two waves, the second one 8 % full: ncu showed the tensor pipe at 30 %).
   const int num_kb = (K + 63) / 64;
-  long long want = (2 * 148 + tiles - 1) / tiles;      // ~two waves of work items
+  const bool wide = (N % 256) == 0;                       // 128 x 256 tiles, one CTA per SM
+  const long long tiles = 1LL * ((M + 127) / 128) * (wide ? N / 256 : (N + 127) / 128);
+  const long long slots = wide ? 148 : (K >= 1024 ? 296 : 148);
+  long long want = slots / tiles;
   if (want > num_kb) want = num_kb;
-  if (want > 128) want = 128;
+  if (want > 64) want = 64;
   if (want < 1) want = 1;
   *kbs = static_cast<int>((num_kb + want - 1) / want);
   *ksplit = (num_kb + *kbs - 1) / *kbs;

@@ -517,7 +517,8 @@ static int gemm_variant(const GemmParams& p) {
     // whenever they still fill the machine; 2 CTAs/SM wins for long K at N = 128; otherwise the 1-CTA/SM pipeline
     const long long m_tiles = (p.rowmap == ROWMAP_CONV) ? (1LL * (p.M / (p.cH * p.cW)) * p.cTilesH * p.cTilesW)
                                                         : ((p.M + GEMM_BM - 1) / GEMM_BM);
-    if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= sm_count() / 2) v = 2;      // (partial 256-wide tiles never pay off)
+    const long long splits = p.ksplit > 1 ? p.ksplit : 1;                         // split-K work items fill the machine too
+    if ((p.N % 256) == 0 && m_tiles * splits * (p.N / 256) >= sm_count() / 2) v = 2;      // (partial 256-wide tiles never pay off)
     else v = (p.K >= 1024) ? 1 : 0;
   }
   if (v == 2 && (p.N % 256) != 0) v = 0;

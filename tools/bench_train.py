@@ -36,6 +36,7 @@ def main():
     p.add_argument("--optimizer", action="store_true", help="include the AdamW update (FusedAdamW over the reference's parameter groups, "
                                                             "poly LR) in the timed step")
     p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
+    p.add_argument("--by-tag", action="store_true", help="print the CUDA-event time of every GEMM / attention shape of one step to stderr")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
     a = p.parse_args()
 
@@ -138,6 +139,9 @@ def main():
     if rank == 0:
         pk, pk_kind = B0.peaks()
         fam = K.TIMER.summary(pk.get("bf16_tflops_sustained", 1400.0), pk.get("hbm_gbs", 6550.0))
+        if a.by_tag:
+            for (f_, tag), d in sorted(K.TIMER.by_tag().items(), key=lambda kv: -kv[1]["ms"]):
+                print(f"{d['ms']:8.3f} ms  x{d['launches']:3d}  {d['flops'] / max(d['ms'], 1e-9) / 1e9:7.0f} TFLOP/s  {f_}  {tag}", file=sys.stderr)
     K.TIMER.enabled = False
     if rank != 0:
         if dist is not None:
