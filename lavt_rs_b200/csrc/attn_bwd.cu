@@ -12,7 +12,8 @@
 // all query blocks; S^T = K Q^T and dP^T = V dO^T make P^T / dZ^T come out of the MMA already in A-fragment layout); a second
 // pass with a warp owning 16 QUERY rows recomputes S / dP / dZ and accumulates dQ in registers (a first version reduced dQ^T =
 // K^T dZ^T across the key-owning warps with shared fp32 atomics: 36 ms per training step vs the recomputation's cost).  The
-// relative-position-bias gradient accumulates in one table copy per CTA (shared atomics), flushed when the head changes.
+// relative-position-bias gradient accumulates per unit in fixed point (scale from a per-unit bound) with native integer shared atomics (fp32 shared
+// atomics are CAS loops) and per CTA in an fp32 table copy that is flushed when the head changes.
 #include "kernels.cuh"
 
 namespace lavt {
@@ -51,7 +52,9 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
   AbTok* tok = reinterpret_cast<AbTok*>(sD + NP * 64);               // [NP]
   float* tab = reinterpret_cast<float*>(tok + NP);                   // [L]  table * log2 e of the current head
   float* dtab = tab + L;                                             // [L]  gradient accumulator of the current head
-  int* work_ctr = reinterpret_cast<int*>(dtab + L);                  // dynamic work-list cursor of the current unit
+  int* itab = reinterpret_cast<int*>(dtab + L);                      // [L]  this unit's table gradient in 16.16 fixed point (below)
+  int* work_ctr = itab + L;                                          // dynamic work-list cursor of the current unit
+  int* umax = work_ctr + 1;                                          // [2] bit patterns of max |dO|, max |V| of the current unit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -61,12 +64,18 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
   const int u_begin = static_cast<int>(1LL * units * blockIdx.x / gridDim.x);
   const int u_end = static_cast<int>(1LL * units * (blockIdx.x + 1) / gridDim.x);
   int cur_head = -1;
+  // Shared-memory fp32 atomicAdd compiles to an LDS / FADD / ATOMS.CAST.SPIN retry loop (ncu source page: those loops were the top
+  // stall sites, and neighbouring lanes hit the SAME table entry); only 32-bit integer ATOMS.ADD is native.  The per-unit table
+  // gradient is therefore accumulated in fixed point and folded into the fp32 table after each unit.  The scale is chosen per unit
+  // from a rigorous bound: |dZ| <= |dP| + |delta| <= 64 max|dO| max|V| and an entry receives at most N terms, so
+  // scale = 2^30 / (64 N max|dO| max|V|) cannot overflow int32 and keeps ~1e-7 of the bound as resolution (order-independent sums).
+  for (int i = threadIdx.x; i < L; i += blockDim.x) itab[i] = 0;
 
   for (int u = u_begin; u < u_end; ++u) {
     const int head = u / nwin, win = u - head * nwin;
     const long long row0 = static_cast<long long>(win) * N;
     __syncthreads();                                       // previous unit finished with every buffer
-    if (threadIdx.x == 0) *work_ctr = 0;
+    if (threadIdx.x == 0) { *work_ctr = 0; umax[0] = 0; umax[1] = 0; }
     if (head != cur_head) {
       if (cur_head >= 0 && p.dtable_t)
         for (int i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(p.dtable_t + static_cast<long long>(cur_head) * L + i, dtab[i]);
@@ -98,6 +107,27 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
     }
     cp_async_wait<0>();
     __syncthreads();
+    // ---- unit maxima of |dO| and |V| for the fixed-point scale of the table gradient
+    {
+      float mdo = 0.f, mv = 0.f;
+      for (int i = threadIdx.x; i < N * 4; i += blockDim.x) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sD + ab_off(i >> 2, i & 3));
+        const uint4 b = *reinterpret_cast<const uint4*>(sV + ab_off(i >> 2, i & 3));
+        const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16x2(aa[j]), y = unpack_bf16x2(bb[j]);
+          mdo = fmaxf(mdo, fmaxf(fabsf(x.x), fabsf(x.y)));
+          mv = fmaxf(mv, fmaxf(fabsf(y.x), fabsf(y.y)));
+        }
+      }
+      mdo = warp_max(mdo);
+      mv = warp_max(mv);
+      if (lane == 0) {       // non-negative floats order like their bit patterns
+        atomicMax(umax, __float_as_int(mdo));
+        atomicMax(umax + 1, __float_as_int(mv));
+      }
+    }
     // ---- delta_i = dO_i . O_i  (O from global: 64 contiguous bytes per row)
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       const uint4* o4 = reinterpret_cast<const uint4*>(p.out + (row0 + i) * C + head * AB_HD);
@@ -172,6 +202,8 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
     //      dynamically scheduled work list: the two passes are independent of each other, and T = 25 tiles over 16 warps would
     //      otherwise idle 7 warps for half of each pass (ncu: barrier was the second largest stall reason)
     const int T = NP / 16;
+    const float ubound = 64.0f * static_cast<float>(N) * __int_as_float(umax[0]) * __int_as_float(umax[1]);
+    const float fix = (ubound > 0.f && isfinite(ubound)) ? 1073741824.0f / ubound : 1.0f;
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(work_ctr, 1);
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
               const float dz = pr * (dp[2 * r + e] - qi.delta);
               pv[2 * r + e] = pr;
               zv[2 * r + e] = dz;
-              if (ok && p.dtable_t) atomicAdd(dtab + idx, dz);
+              if (ok && p.dtable_t) atomicAdd(itab + idx, __float2int_rn(dz * fix));
             }
           }
           pP[h][0] = pack_bf16x2(pv[0], pv[1]);
@@ -327,6 +359,12 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
       }
       }
     }
+    __syncthreads();
+    if (p.dtable_t)
+      for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        dtab[i] += static_cast<float>(itab[i]) / fix;
+        itab[i] = 0;
+      }
   }
   __syncthreads();
   if (cur_head >= 0 && p.dtable_t)
@@ -338,7 +376,7 @@ int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st) {
   LAVT_REQUIRE(p.C == p.nH * AB_HD, "attention backward: head_dim must be 32 (C=%d, heads=%d)", p.C, p.nH);
   LAVT_REQUIRE(w.N > 0 && w.N == w.wd * w.wh * w.ww, "attention backward: bad window geometry");
   const int NP = (w.N + 15) / 16 * 16;
-  const size_t smem = static_cast<size_t>(NP) * 64 * 4 + static_cast<size_t>(NP) * sizeof(AbTok) + static_cast<size_t>(p.L) * 8 + 16;
+  const size_t smem = static_cast<size_t>(NP) * 64 * 4 + static_cast<size_t>(NP) * sizeof(AbTok) + static_cast<size_t>(p.L) * 12 + 32;
   LAVT_REQUIRE(smem <= 227 * 1024, "attention backward: window of %d tokens (table %d) needs %zu B of shared memory; windows above ~400 "
                "tokens (8x12x12) are not supported by the training path yet", w.N, p.L, smem);
   static size_t configured = 0;
