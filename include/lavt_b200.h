@@ -301,6 +301,16 @@ int lavt_adamw_chunk_elems(void);
 int lavt_adamw_step(const lavt_adamw_tensor_t* table_dev, const int32_t* block_prefix_dev, int32_t n_tensors, int32_t n_blocks,
                     float lr, double beta1, double beta2, float eps, float weight_decay, void* stream);
 
+/* ---- input / output edges of the inference scripts ---- */
+/* T.ToTensor() + T.Normalize(mean, std) (train.py:54-60): uint8 HWC frames [n,H,W,3] (already resized) -> fp32 [n,3,H,W];
+ * mean3_host / std3_host are HOST arrays of 3 floats */
+int lavt_normalize_u8(const uint8_t* frames_hwc, float* out_nchw, int32_t n_img, int32_t H, int32_t W, const float* mean3_host,
+                      const float* std3_host, void* stream);
+/* F.interpolate(logits, (out_h, out_w), bilinear, align_corners=True).argmax(1) * 255 (test_ytvos.py:249-253, 274-279):
+ * fp32 [n,2,H,W] -> uint8 [n,out_h,out_w] */
+int lavt_logits_to_mask(const float* logits_nchw, uint8_t* mask, int32_t n_img, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

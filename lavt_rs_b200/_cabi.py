@@ -124,6 +124,8 @@ SIGNATURES = {
     "lavt_conv1x1_logits_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_cross_entropy": [_vp, _vp, _f32, _f32, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_normalize_u8": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "lavt_logits_to_mask": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
@@ -748,3 +750,33 @@ def cross_entropy(logits, target, acc, dlogits=None, *, w0: float = 0.9, w1: flo
     check(lib().lavt_cross_entropy(_c(logits, torch.float32, "logits").data_ptr(), target.data_ptr(), w0, w1,
                                    _c(acc, torch.float32, "acc").data_ptr(), ptr(dlogits), gscale, n, H, W, phase, stream_ptr()),
           "lavt_cross_entropy")
+
+
+# ---- input / output edges ----
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def normalize_u8(frames: torch.Tensor, out: Optional[torch.Tensor] = None, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """T.ToTensor() + T.Normalize (reference train.py:54-60): uint8 CUDA frames [n,H,W,3] -> fp32 [n,3,H,W]."""
+    if frames.dtype != torch.uint8 or not frames.is_cuda or not frames.is_contiguous() or frames.shape[-1] != 3:
+        raise LavtError("normalize_u8: frames must be a contiguous CUDA uint8 tensor [n,H,W,3]")
+    n, H, W, _ = frames.shape
+    if out is None:
+        out = torch.empty(n, 3, H, W, device=frames.device, dtype=torch.float32)
+    m, s_ = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(lib().lavt_normalize_u8(frames.data_ptr(), _c(out, torch.float32, "out").data_ptr(), n, H, W, C.cast(m, C.c_void_p),
+                                  C.cast(s_, C.c_void_p), stream_ptr()), "lavt_normalize_u8")
+    return out
+
+
+def logits_to_mask(logits: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(logits, size, 'bilinear', align_corners=True).argmax(1) as the 0 / 255 uint8 image the reference saves
+    (test_ytvos.py:249-253, 274-279): logits fp32 [n,2,H,W] -> uint8 [n,oh,ow]."""
+    n, two, H, W = logits.shape
+    if two != 2:
+        raise LavtError("logits_to_mask: expects 2 classes")
+    oh, ow = int(size[0]), int(size[1])
+    out = torch.empty(n, oh, ow, device=logits.device, dtype=torch.uint8)
+    check(lib().lavt_logits_to_mask(_c(logits, torch.float32, "logits").data_ptr(), out.data_ptr(), n, H, W, oh, ow, stream_ptr()),
+          "lavt_logits_to_mask")
+    return out

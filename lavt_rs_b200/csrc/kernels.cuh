@@ -95,6 +95,8 @@ int conv1x1_logits_bwd_dispatch(const float* dlog, const __nv_bfloat16* y, const
 int upsample_logits_bwd_dispatch(const float* dout, float* din, int n_img, int h, int w, int H, int W, cudaStream_t st);
 int ce_loss_dispatch(const float* logits, const long long* target, float w0, float w1, float* acc, float* dlogits, float gscale, int n_img,
                      int H, int W, int phase, cudaStream_t st);
+int normalize_u8_dispatch(const uint8_t* in, float* out, int n_img, int H, int W, const float* mean, const float* stdv, cudaStream_t st);
+int logits_to_mask_dispatch(const float* logits, uint8_t* mask, int n_img, int H, int W, int oh, int ow, cudaStream_t st);
 int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                              const __nv_bfloat16* dO, float* dqhat, __nv_bfloat16* qs_out, __nv_bfloat16* P_bd, __nv_bfloat16* dS_bd,
                              float* sums, int B, long long n, int C, int Nl, int NlPad, int heads, cudaStream_t st);

@@ -346,3 +346,20 @@ def test_decoder_forward_feats(small):
     for f, hw in zip(feats[1:], ((6, 4), (12, 8), (24, 16))):
         assert tuple(f.shape) == (n, 512, hw[0], hw[1]) and f.dtype == torch.float32
     assert_close(feats[3], cap["dec_feat"], what="Y1 (decoder feature before conv1_1)", l2=1.5e-2, frac=1e-2)
+
+
+def test_io_edges():
+    """ToTensor + Normalize of uint8 frames and interpolate-to-original-size + argmax of the logits (train.py:54-60, test_ytvos.py:249-279)."""
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (5, 48, 64, 3), generator=g, dtype=torch.uint8)
+    ref = (frames.permute(0, 3, 1, 2).float() / 255.0 - torch.tensor(K.IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(K.IMAGENET_STD).view(1, 3, 1, 1)
+    got = K.normalize_u8(frames.cuda())
+    assert torch.allclose(got.cpu(), ref, atol=1e-6, rtol=1e-6)
+    logits = torch.randn(3, 2, 96, 80, generator=g)
+    for size in ((96, 80), (217, 333), (50, 41)):
+        up = torch.nn.functional.interpolate(logits, size=size, mode="bilinear", align_corners=True)
+        want = (up.argmax(1) * 255).to(torch.uint8)
+        got = K.logits_to_mask(logits.cuda(), size).cpu()
+        margin = (up[:, 1] - up[:, 0]).abs()
+        assert got.shape == want.shape and ((got == want) | (margin < 1e-5)).all()      # identical except at numerical ties
