@@ -31,8 +31,8 @@ from . import train_engine as T
 def _check_trainable(model) -> None:
     bb = model.backbone
     for layer in bb.layers:
-        if layer.version != "default":
-            raise NotImplementedError("training on the B200 path supports PWAM / SepTPWAM with the default LanguageGate (no --version ablations)")
+        if layer.version not in ("default", "no_gate", "none"):
+            raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
     if tuple(bb.out_indices) != (0, 1, 2, 3):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
 
@@ -70,6 +70,10 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
             r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
         else:
             r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
+        if layer.version == "no_gate" and (not last or layer.hs):       # ablation: plain residual add x' = x + r (:570-575)
+            xg = torch.empty_like(r32)
+            K.gate_elementwise(6, pw_saved["rb"], f=feat, f2=r32, out_f32=xg)
+            E._count(1)
         norm = getattr(bb, f"norm{i}")
         ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
         out_src = ((xg if xg is not None else feat) if layer.hs else r32)      # --hs: stage output = gated features instead of the residual
@@ -80,7 +84,7 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
         if not last:
             src = xg if xg is not None else feat
             feat, merge_saved = T.patch_merging_fwd(src, layer.downsample, B, D, Hc, Wc, ws)
-        stages.append((blocks, pw_saved, out_src, merge_saved, gate is not None, bool(layer.hs)))
+        stages.append((blocks, pw_saved, out_src, merge_saved, gate is not None, bool(layer.hs), layer.version == "no_gate" and xg is not None))
         if not last:
             Hc, Wc = (Hc + 1) // 2, (Wc + 1) // 2
     c1, c2, c3, c4 = maps
@@ -106,7 +110,7 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
     dx_next: Optional[torch.Tensor] = None
     for i in range(len(bb.layers) - 1, -1, -1):
         layer = bb.layers[i]
-        blocks, pw_saved, out_src, merge_saved, has_gate, hs = tape["stages"][i]
+        blocks, pw_saved, out_src, merge_saved, has_gate, hs, plain_add = tape["stages"][i]
         norm = getattr(bb, f"norm{i}")
         dxg = None
         if merge_saved is not None:
@@ -122,6 +126,12 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
             dr = torch.empty_like(out_src)
             K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dr, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
         E._count(1)
+        if plain_add and dxg is not None:      # x' = x + r: the gradient of x' reaches r as well as x
+            if dr is None:
+                dr = dxg.clone()
+            else:
+                K.gate_elementwise(6, pw_saved["rb"], f=dr, f2=dxg, out_f32=dr)
+            E._count(1)
         if dr is None and not has_gate:
             dx = dxg        # --hs without a gate: x' = x and the fusion output is unused (no gradient for its parameters)
         else:

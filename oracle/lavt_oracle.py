@@ -41,6 +41,7 @@ class OracleConfig:
     video: bool = True
     gate_act: str = "tanh"
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
+    version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
     sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
                                                   # --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1
 
@@ -297,7 +298,9 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         if capture is not None:
             capture[f"s{s}.residual"] = r
-        if pre + "res_gate.0.weight" in sd:
+        if cfg.version == "no_gate":
+            x = x + r.reshape(B, D, H, W, C)
+        elif cfg.version == "default" and pre + "res_gate.0.weight" in sd:
             x = language_gate(x.reshape(B, D * H * W, C), r, sd, pre + "res_gate.", cfg.gate_act).reshape(B, D, H, W, C)
         stage_out = x if cfg.hs else r.reshape(B, D, H, W, C)
         o = F.layer_norm(stage_out, (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)

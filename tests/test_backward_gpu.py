@@ -734,3 +734,38 @@ def test_hs_training_step():
     ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
     assert any(k.startswith("backbone.layers.3.res_gate") for k in ref), "with --hs the last stage's gate is live"
     check_direction(got, ref, "--hs training step")
+
+
+@pytest.mark.parametrize("version", ["no_gate", "none"])
+def test_version_ablation_training_step(version):
+    """--version no_gate (x' = x + r) / none (x' = x): reference lib/video_swin_transformer.py:561-575."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), version=version)
+    sd = {k: v for k, v in O.random_state_dict(cfg, seed=0).items() if "res_gate" not in k}
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=default_args(["--version", version]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    g = torch.Generator().manual_seed(91)
+    B, Tn, H, W, Nl = 2, 4, 64, 96, 10
+    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, l, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, _ = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    check_direction(got, {k: v.grad for k, v in leaf.items() if v.grad is not None}, f"--version {version} training step")

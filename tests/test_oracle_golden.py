@@ -27,3 +27,25 @@ def test_oracle_reproduces_reference_outputs(name):
         if key in gold:
             assert np.abs(cap[key].numpy() - gold[key]).max() < 2e-4, key
         assert abs(cap[key].abs().mean().item() - float(gold[key + "_absmean"])) < 1e-4
+
+
+def test_oracle_autograd_reproduces_reference_training_step():
+    """Golden training step of the UNMODIFIED reference (oracle/make_golden_train.py): loss, d l_feats, the norm of every parameter
+    gradient and ten complete gradient tensors vs autograd through the oracle."""
+    from oracle.make_golden_train import TRAIN_CASES, train_case_inputs
+    for name, c in TRAIN_CASES.items():
+        gold = np.load(os.path.join(OUT, name + ".npz"))
+        cfg, sd, x, l, m, target = train_case_inputs(c)
+        leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        lr = l.clone().requires_grad_()
+        loss = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, lr, m, train_bn=True), target)
+        loss.backward()
+        assert abs(loss.item() - float(gold["loss"])) < 1e-5
+        assert np.abs(lr.grad.numpy() - gold["dl"]).max() < 1e-6 + 2e-3 * np.abs(gold["dl"]).max()
+        for k, nrm in zip(gold["names"], gold["norms"]):
+            g = leaf[str(k)].grad
+            assert g is not None and abs(g.norm().item() - float(nrm)) < 5e-3 * float(nrm) + 1e-8, k
+        for key in gold.files:
+            if key.startswith("g:"):
+                a, b = leaf[key[2:]].grad.numpy(), gold[key]
+                assert np.linalg.norm(a - b) < 5e-3 * np.linalg.norm(b) + 1e-9, key

@@ -156,3 +156,45 @@ def test_pretrained2d_inflation_matches_reference(tmp_path, into_3d):
     assert len(tables) == 12 and all(got[k].shape[0] == 15 * 13 * 13 for k in tables)
     assert got["backbone.patch_embed.proj.weight"].dim() == 5 and checked > 100
     assert into_3d == (not any(".fusion" in k for k in got))
+
+
+@pytest.mark.parametrize("extra,cfg_kw", [((), {}), (("--version", "no_gate"), {"version": "no_gate"}), (("--version", "none"), {"version": "none"}),
+                                          (("--hs",), {"hs": True})])
+def test_training_gradients_match_reference_autograd(extra, cfg_kw):
+    """The GRADIENT oracle (autograd through oracle/lavt_oracle.py with train-mode BatchNorm and the [0.9, 1.1]-weighted cross-entropy)
+    pinned against autograd through the unmodified reference modules in train() mode: loss, d l_feats and every parameter gradient.
+    This is what tests/test_backward_gpu.py holds the sm_100a backward kernels to."""
+    import torch.nn.functional as F
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=(8, 7, 7), depths=(2, 2, 2, 2), extra=extra)
+    _randomise_norms([bb, dec])
+    g = torch.Generator().manual_seed(5)
+    for layer in bb.layers:          # the reference zero-initialises the gates: give them signal
+        if hasattr(layer, "res_gate"):
+            for k in (0, 2):
+                layer.res_gate[k].weight.data.copy_(torch.randn(layer.res_gate[k].weight.shape, generator=g) * layer.res_gate[k].weight.shape[0] ** -0.5)
+    sd = {k: v.clone() for k, v in _sd(bb, dec).items()}
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), **cfg_kw)
+    x, l, m = O.synthetic_inputs(2, 4, 64, 48, Nl=9)
+    target = torch.randint(0, 2, (8, 64, 48), generator=g)
+    bb.train()
+    dec.train()
+    lr_ = l.clone().requires_grad_()
+    feats = bb(x.permute(0, 2, 1, 3, 4), lr_, m.unsqueeze(-1))
+    out = F.interpolate(dec(feats[3], feats[2], feats[1], feats[0]), size=(64, 48), mode="bilinear", align_corners=True)
+    loss_ref = F.cross_entropy(out, target, weight=torch.tensor([0.9, 1.1]))
+    loss_ref.backward()
+    ref = {"backbone." + k: p.grad for k, p in bb.named_parameters() if p.grad is not None}
+    ref.update({"classifier." + k: p.grad for k, p in dec.named_parameters() if p.grad is not None})
+
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    lo = l.clone().requires_grad_()
+    loss = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, lo, m, train_bn=True), target)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    assert (lo.grad - lr_.grad).abs().max().item() < 1e-6 + 1e-3 * lr_.grad.abs().max().item()
+    got = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    assert set(got) == set(ref), set(got) ^ set(ref)
+    for k, r in ref.items():
+        err = (got[k] - r).norm().item() / (r.norm().item() + 1e-12)
+        # fp32 on both sides; different op order (index-math gathers vs roll / partition copies) leaves ~1e-3 on the deepest tensors
+        assert err < 5e-3 or (got[k] - r).abs().max().item() < 1e-7, (k, err)
