@@ -137,6 +137,11 @@ int lavt_instnorm_stats(const float* x, int32_t B, int64_t n, int32_t C, float e
 /* k, v = (W l + b) * l_mask : l fp32 [B,Lin,Nl], mask fp32 [B,Nl], weights fp32 [C,Lin] -> k, v fp32 [B,Nl,C] */
 int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                  float* k, float* v, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream);
+/* LangProject of the --fuse simple ablation (lib/video_swin_transformer.py:1012-1039): per clip, masked mean of the word features ->
+ * Linear(Lin -> C) -> ReLU -> Linear(C -> C).  l fp32 [B,Lin,Nl], mask fp32 [B,Nl], w0 [C,Lin], w2 [C,C].  The sentence vector is
+ * written as stats fp32 [B,2,C] = (-lang, 1): lavt_pwam_mul_norm over an all-zero lang tensor then yields vis * lang. */
+int lavt_lang_project(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* b2, float* stats,
+                      int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream);
 /* o = softmax_words(C^-0.5 * IN(q_pre) k^T + (1e4 mask - 1e4)) v ; q_pre fp32, o bf16 [B,n,C] */
 int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                      void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
     "lavt_window_attention": [_vp, _vp, _i32, _i32, _WG, _vp, _vp],
     "lavt_instnorm_stats": [_vp, _i32, _i64, _i32, _f32, _vp, _vp, _vp],
     "lavt_pwam_kv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_lang_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_pwam_attend": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_pwam_mul_norm": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_instnorm_sum2": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
@@ -404,6 +405,16 @@ def pwam_kv(l, mask, wk, bk, wv, bv, k, v) -> None:
         _c(t, torch.float32, nm)
     check(lib().lavt_pwam_kv(l.data_ptr(), mask.data_ptr(), wk.data_ptr(), bk.data_ptr(), wv.data_ptr(), bv.data_ptr(),
                              k.data_ptr(), v.data_ptr(), B, Nl, Lin, Cn, stream_ptr()), "lavt_pwam_kv")
+
+
+def lang_project(l, mask, w0, b0, w2, b2, stats) -> None:
+    """--fuse simple: stats fp32 [B,2,C] = (-LangProject(l, mask), 1); l fp32 [B,Lin,Nl], mask fp32 [B,Nl]."""
+    B, Lin, Nl = l.shape
+    Cn = w0.shape[0]
+    for t, nm in ((l, "l"), (mask, "mask"), (w0, "w0"), (b0, "b0"), (w2, "w2"), (b2, "b2"), (stats, "stats")):
+        _c(t, torch.float32, nm)
+    check(lib().lavt_lang_project(l.data_ptr(), mask.data_ptr(), w0.data_ptr(), b0.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                  stats.data_ptr(), B, Nl, Lin, Cn, stream_ptr()), "lavt_lang_project")
 
 
 def pwam_attend(qpre, stats, k, v, mask, out, heads: int) -> None:

@@ -179,6 +179,11 @@ int lavt_pwam_kv(const float* l, const float* mask, const float* wk, const float
   return pwam_kv_dispatch(l, mask, wk, bk, wv, bv, k, v, B, Nl, Lin, C, S(stream));
 }
 
+int lavt_lang_project(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* b2, float* stats,
+                      int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream) {
+  return lang_project_dispatch(l, mask, w0, b0, w2, b2, stats, B, Nl, Lin, C, S(stream));
+}
+
 int lavt_pwam_attend(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                      void* o_bf16, int32_t B, int64_t n, int32_t C, int32_t Nl, int32_t heads, void* stream) {
   return pwam_core_dispatch(qpre, stats, k, v, mask, MB(o_bf16), B, n, C, Nl, heads, S(stream));

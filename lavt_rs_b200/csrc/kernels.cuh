@@ -114,6 +114,8 @@ int gate_elem_dispatch(int mode, const __nv_bfloat16* a, const __nv_bfloat16* b,
 
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st);
+int lang_project_dispatch(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* b2,
+                          float* stats, int B, int Nl, int Lin, int C, cudaStream_t st);
 int pwam_core_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                        __nv_bfloat16* o, int B, long long n, int C, int Nl, int heads, cudaStream_t st);
 

@@ -135,6 +135,54 @@ __global__ void __launch_bounds__(256) pwam_core_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LangProject (reference lib/video_swin_transformer.py:1012-1039, the --fuse simple ablation): per clip, masked mean of the word
+// features -> Linear(768 -> C) -> ReLU -> Linear(C -> C).  One CTA per clip; the result is written NEGATED as the "mean" row of an
+// InstanceNorm statistics block (mean = -lang, rstd = 1) so that pwam_mul over an all-zero lang_pre tensor yields vis * lang.
+__global__ void __launch_bounds__(256) lang_project_kernel(const float* __restrict__ l, const float* __restrict__ mask,
+                                                           const float* __restrict__ w0, const float* __restrict__ b0,
+                                                           const float* __restrict__ w2, const float* __restrict__ b2,
+                                                           float* __restrict__ stats, int Nl, int Lin, int C) {
+  extern __shared__ float lp_sm[];      // [Lin] pooled sentence vector, [C] hidden
+  float* pooled = lp_sm;
+  float* hid = lp_sm + Lin;
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int j = 0; j < Nl; ++j) cnt += mask[b * Nl + j];
+  for (int i = threadIdx.x; i < Lin; i += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Nl; ++j) s += l[(static_cast<long long>(b) * Lin + i) * Nl + j] * mask[b * Nl + j];
+    pooled[i] = s / cnt;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < Lin; i += 32) acc = fmaf(__ldg(w0 + static_cast<long long>(c) * Lin + i), pooled[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) hid[c] = fmaxf(acc + b0[c], 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * C + i), hid[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      stats[(static_cast<long long>(b) * 2) * C + c] = -(acc + b2[c]);
+      stats[(static_cast<long long>(b) * 2 + 1) * C + c] = 1.0f;
+    }
+  }
+}
+
+int lang_project_dispatch(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* b2,
+                          float* stats, int B, int Nl, int Lin, int C, cudaStream_t st) {
+  LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0, "lang_project: empty input");
+  const size_t smem = static_cast<size_t>(Lin + C) * sizeof(float);
+  LAVT_REQUIRE(smem <= 48 * 1024, "lang_project: widths %d + %d too large", Lin, C);
+  lang_project_kernel<<<B, 256, smem, st>>>(l, mask, w0, b0, w2, b2, stats, Nl, Lin, C);
+  LAVT_LAUNCH_CHECK("lang_project_kernel");
+  return LAVT_OK;
+}
+
 // Tensor-core version (mma.sync m16n8k16, bf16 operands, fp32 accumulate) used whenever the word matrices fit in
 // shared memory: 16 pixels per warp, scores for all (padded) words at once -> exact softmax, no online rescaling.
 //   S = (IN(q_pre) * C^-0.5) k^T + (1e4 m - 1e4)      A = normalised q rows built in registers, B = k rows (ldmatrix)

@@ -156,11 +156,37 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     dev = x.device
     pw = fusion.prepared
     att = fusion.image_lang_att
-    heads = att.num_heads
     Nl = l.shape[-1]
 
     def wprep(name, conv):
         return pw.get(name, [conv.weight], lambda: _bf16(_conv1x1_w(conv)))
+
+    if not fusion.attention:
+        # --fuse simple (reference :916-917, :929-930): lang = LangProject(mean-pooled words), one vector per clip
+        vis = ws.get("pw_vis", (B, n, C), torch.bfloat16, dev)
+        K.gemm_bf16(xb, wprep("vis_w", fusion.vis_project[0]), bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C))
+        stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
+        pr = att.project
+        K.lang_project(l, mask, _f32(pr[0].weight), _f32(pr[0].bias), _f32(pr[2].weight), _f32(pr[2].bias), stats)
+        zeros = pw.get("zeros_%d_%d" % (B, n), [], lambda: torch.zeros(B, n, C, device=dev, dtype=torch.float32))
+        a2 = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
+        K.pwam_mul_norm(vis, zeros, stats, a2)          # vis * (0 - (-lang)) * 1
+        r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+        rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+        K.gemm_bf16(a2.view(N_, C), wprep("mm_w", fusion.project_mm[0]), bias=fusion.project_mm[0].bias.detach(), act=K.ACT_GELU, out_f32=r32,
+                    out_bf16=rb)
+        _count(4)
+        if res_gate is not None:
+            g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+            g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+            g1 = vis.view(N_, C)
+            K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
+            if gate_act != "tanh":
+                raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+            K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+            _count(2)
+        return r32
+    heads = att.num_heads
 
     vis_w = wprep("vis_w", fusion.vis_project[0])
     q_w = wprep("q_w", att.f_query[0])

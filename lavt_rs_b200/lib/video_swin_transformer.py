@@ -135,20 +135,32 @@ class SpatialImageLanguageAttention(nn.Module):
         self.W = nn.Sequential(nn.Conv1d(value_channels, self.out_channels, 1), nn.InstanceNorm1d(self.out_channels))
 
 
+class LangProject(nn.Module):
+    """Mean-pooled sentence vector -> Linear -> ReLU -> Linear (reference :1012-1039; the --fuse simple ablation)."""
+
+    def __init__(self, l_in_channels, l_out_channels):
+        super().__init__()
+        self.l_in_channels, self.l_out_channels = l_in_channels, l_out_channels
+        self.project = nn.Sequential(nn.Linear(l_in_channels, l_out_channels), nn.ReLU(), nn.Linear(l_out_channels, l_out_channels))
+
+
 class PWAM(nn.Module):
-    """Pixel-word attention module (reference :889-934)."""
+    """Pixel-word attention module (reference :889-934); ``attention=False`` = the --fuse simple ablation (LangProject)."""
 
     def __init__(self, dim, v_in_channels, l_in_channels, key_channels, value_channels, num_heads=0, dropout=0.0,
                  attention=True):
         super().__init__()
-        if not attention:
-            raise NotImplementedError("--fuse simple (LangProject) is not implemented on the B200 path")
         if dropout != 0.0:
             raise NotImplementedError("fusion dropout > 0 is not supported on the B200 path")
         self.attention = attention
         self.vis_project = nn.Sequential(nn.Conv1d(dim, dim, 1, 1), nn.GELU(), nn.Dropout(dropout))
-        self.image_lang_att = SpatialImageLanguageAttention(v_in_channels, l_in_channels, key_channels, value_channels,
-                                                            out_channels=value_channels, num_heads=num_heads)
+        if attention:
+            self.image_lang_att = SpatialImageLanguageAttention(v_in_channels, l_in_channels, key_channels, value_channels,
+                                                                out_channels=value_channels, num_heads=num_heads)
+        else:
+            if dim != value_channels:
+                raise NotImplementedError("--fuse simple with differing channel widths is not supported on the B200 path")
+            self.image_lang_att = LangProject(l_in_channels, value_channels)
         self.project_mm = nn.Sequential(nn.Conv1d(value_channels, value_channels, 1, 1), nn.GELU(), nn.Dropout(dropout))
         self.prepared = E.PreparedWeights()
 
@@ -238,8 +250,10 @@ def check_args(args) -> None:
     for f in _UNSUPPORTED_FLAGS:
         if getattr(args, f, False):
             raise NotImplementedError(f"--{f} is not implemented on the B200 path yet (SURVEY.md section 8f)")
-    if getattr(args, "fuse", "default") not in ("default", ""):
-        raise NotImplementedError("--fuse simple is not implemented on the B200 path")
+    if getattr(args, "fuse", "default") not in ("default", "", "simple"):
+        raise ValueError(f"unknown --fuse {args.fuse}")
+    if getattr(args, "fuse", "default") == "simple" and getattr(args, "sep_t_pwam", False):
+        raise NotImplementedError("--fuse simple together with --sep_t_pwam is not implemented on the B200 path")
     if getattr(args, "version", "default") not in ("default", "no_gate", "none"):
         raise ValueError(f"unknown --version {args.version}")
 
@@ -279,7 +293,8 @@ class MMBasicLayer(nn.Module):
                                    w_t3x3_s1x1=getattr(args, "w_t3x3_s1x1", False),
                                    mm_t3x3_s1x1=getattr(args, "mm_t3x3_s1x1", False), args=args)
         else:
-            self.fusion = PWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop, attention=True)
+            self.fusion = PWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop,
+                               attention=getattr(args, "fuse", "default") != "simple")      # reference :502-511
         self.has_gate = self.version == "default" and not (self.is_last_layer and use_checkpoint)
         if self.has_gate:
             self.res_gate = nn.Sequential(nn.Linear(dim, dim, bias=False), nn.ReLU(), nn.Linear(dim, dim, bias=False), nn.Tanh())

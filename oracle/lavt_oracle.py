@@ -41,6 +41,7 @@ class OracleConfig:
     video: bool = True
     gate_act: str = "tanh"
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
+    fuse_simple: bool = False                     # --fuse simple: LangProject (mean-pooled sentence vector) instead of pixel-word attention
     version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
     sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
                                                   # --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1
@@ -170,12 +171,22 @@ def _instance_norm_tokens(t: Tensor) -> Tensor:
     return (t - mu) / torch.sqrt(var + 1e-5)
 
 
+def lang_project(l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
+    """LangProject (:1012-1039): masked mean of the word features -> Linear -> ReLU -> Linear.  l (B,768,Nl), l_mask (B,Nl,1) -> (B,1,C)."""
+    m = l_mask.to(l.dtype).transpose(1, 2)                              # (B, 1, Nl)
+    s = (l * m).sum(-1) / m.sum(-1)                                     # (B, 768)
+    h = F.relu(s @ sd[pre + "project.0.weight"].t() + sd[pre + "project.0.bias"])
+    return (h @ sd[pre + "project.2.weight"].t() + sd[pre + "project.2.bias"]).unsqueeze(1)
+
+
 def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, return_parts: bool = False):
     """x (B,n,C); l (B,768,Nl); l_mask (B,Nl,1) -> x_residual (B,n,C).  ``pre`` = 'backbone.layers.{s}.fusion.'"""
     B, n, C = x.shape
     m = l_mask.to(x.dtype)                                              # (B, Nl, 1)
     vis = F.gelu(_lin1x1(x, sd, pre + "vis_project.0"))
     a = pre + "image_lang_att."
+    if a + "project.0.weight" in sd:                                    # --fuse simple (:916-917, 929-930): broadcast sentence vector
+        return F.gelu(_lin1x1(vis * lang_project(l, l_mask, sd, a), sd, pre + "project_mm.0"))
     q = _instance_norm_tokens(_lin1x1(x, sd, a + "f_query.0"))          # (B, n, C)
     lt = l.transpose(1, 2)                                              # (B, Nl, 768)
     k = _lin1x1(lt, sd, a + "f_key.0") * m                              # (B, Nl, C)
@@ -427,6 +438,13 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
             for name in ("f_key.0", "f_value.0"):
                 w, b = conv_default(C, l_in, 1)
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        elif cfg.fuse_simple:
+            for name in ("vis_project.0", "project_mm.0"):
+                w, b = conv_default(C, C, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+            for name, cin in (("project.0", l_in), ("project.2", C)):
+                w, b = conv_default(C, cin)
+                sd[f"{pre}fusion.image_lang_att.{name}.weight"], sd[f"{pre}fusion.image_lang_att.{name}.bias"] = w, b
         else:
             for name, cin in (("vis_project.0", C), ("image_lang_att.f_key.0", l_in), ("image_lang_att.f_query.0", C),
                               ("image_lang_att.f_value.0", l_in), ("image_lang_att.W.0", C), ("project_mm.0", C)):

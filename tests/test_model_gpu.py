@@ -363,3 +363,29 @@ def test_io_edges():
         got = K.logits_to_mask(logits.cuda(), size).cpu()
         margin = (up[:, 1] - up[:, 0]).abs()
         assert got.shape == want.shape and ((got == want) | (margin < 1e-5)).all()      # identical except at numerical ties
+
+
+def test_fuse_simple_end_to_end():
+    """--fuse simple (LangProject fusion, reference :916-917, 1012-1039): backbone + decoder vs the oracle."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), fuse_simple=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=default_args(["--fuse", "simple"]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(2, 4, 64, 96, Nl=20)
+    cap = {}
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.permute(0, 2, 1, 3, 4).cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        got = model._segment(x.cuda().permute(0, 2, 1, 3, 4), l.cuda(), m.cuda(), (64, 96))
+    for i in range(4):
+        assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)

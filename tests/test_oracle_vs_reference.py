@@ -198,3 +198,20 @@ def test_training_gradients_match_reference_autograd(extra, cfg_kw):
         err = (got[k] - r).norm().item() / (r.norm().item() + 1e-12)
         # fp32 on both sides; different op order (index-math gathers vs roll / partition copies) leaves ~1e-3 on the deepest tensors
         assert err < 5e-3 or (got[k] - r).abs().max().item() < 1e-7, (k, err)
+
+
+def test_fuse_simple_matches_reference():
+    """--fuse simple: PWAM with LangProject (mean-pooled sentence vector) instead of pixel-word attention (:916-917, 1012-1039)."""
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=(8, 7, 7), depths=(2, 2, 2, 2), extra=("--fuse", "simple"))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    assert "backbone.layers.0.fusion.image_lang_att.project.0.weight" in sd
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), fuse_simple=True)
+    assert set(O.random_state_dict(cfg)) - {k for k in sd} == set()
+    x, l, m = O.synthetic_inputs(2, 4, 64, 48, Nl=9)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        ref = bb(xv, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert (a - b).abs().max().item() < 2e-4, i
