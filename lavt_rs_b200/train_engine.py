@@ -77,12 +77,18 @@ class GradStore:
             self.of(param).add_(back(buf))
         self._alt.clear()
 
-    def finalize(self) -> None:
-        """Hand the accumulated gradients to ``param.grad`` (added to an existing ``.grad`` like autograd does).  Tensor-container
-        bookkeeping, not a hot path."""
+    def finalize(self, only=None) -> List[torch.nn.Parameter]:
+        """Hand the accumulated gradients to ``param.grad`` (added to an existing ``.grad`` like autograd does) and forget them.
+        ``only``: restrict to these parameters (a finished stage whose gradients can already be all-reduced while the backward of
+        the earlier stages runs).  Returns the parameters that received a gradient.  Tensor-container bookkeeping, not a hot path."""
+        keep = None if only is None else {id(p) for p in only}
+        done = []
         with torch.no_grad():
-            self._fold()
-            for param, buf in self._g.values():
+            for key in [k for k in self._alt if keep is None or k[0] in keep]:
+                param, buf, back = self._alt.pop(key)
+                self.of(param).add_(back(buf))
+            for pid in [k for k in self._g if keep is None or k in keep]:
+                param, buf = self._g.pop(pid)
                 if not param.requires_grad:
                     continue
                 g = buf.to(param.dtype)
@@ -90,7 +96,8 @@ class GradStore:
                     param.grad = g
                 else:
                     param.grad.add_(g)
-        self._g.clear()
+                done.append(param)
+        return done
 
     def buffers(self) -> List[Tuple[torch.nn.Parameter, torch.Tensor]]:
         """(parameter, fp32 gradient buffer) pairs after folding the alternate layouts (gradient all-reduce, tests)."""

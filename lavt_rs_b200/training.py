@@ -98,8 +98,10 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
     return logits, tape
 
 
-def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> torch.Tensor:
-    """dlogits fp32 (B*T,2,H,W) -> parameter gradients in ``grads``; returns the gradient of l_feats (B,768,Nl)."""
+def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_ready=None) -> torch.Tensor:
+    """dlogits fp32 (B*T,2,H,W) -> parameter gradients in ``grads``; returns the gradient of l_feats (B,768,Nl).
+    ``on_ready(params)`` is called as soon as the gradients of a group of parameters are complete (decoder, then each stage from the
+    last to the first, then the patch embedding) so that their all-reduce can overlap the rest of the backward (``GradReducer``)."""
     bb, dec = model.backbone, model.classifier
     dev = dlogits.device
     ws = E.workspace(dev)
@@ -108,6 +110,8 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
     K.upsample_logits_bwd(dlogits.contiguous(), dlg)
     E._count(1)
     dcs = T.decoder_bwd(dec, tape["dec"], dlg, grads, ws, sync_bn)      # (dc4, dc3, dc2, dc1)
+    if on_ready is not None:
+        on_ready(list(dec.parameters()))
     dl = torch.zeros_like(tape["l"])
     dx_next: Optional[torch.Tensor] = None
     for i in range(len(bb.layers) - 1, -1, -1):
@@ -143,12 +147,16 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore) -> 
         for bi in range(layer.depth - 1, -1, -1):
             dx = T.swin_block_bwd(layer.blocks[bi], blocks[bi], dx, grads, ws)
         dx_next = dx
+        if on_ready is not None:
+            on_ready(list(layer.parameters()) + list(norm.parameters()))
     T.patch_embed_bwd(bb.patch_embed, tape["pe"], dx_next, grads, ws)
+    if on_ready is not None:
+        on_ready(list(bb.patch_embed.parameters()))
     return dl
 
 
 def segment_forward_backward(model, x, l_feats, l_mask, target: torch.Tensor, grads: T.GradStore, sync_bn: bool = False,
-                             loss_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+                             loss_scale: float = 1.0, on_ready=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """One fused fwd + loss + bwd of the hot path.  target int64 (B*T,H,W) in {0,1}.  Returns (loss as a 0-d CUDA tensor, dl_feats)."""
     logits, tape = segment_forward(model, x, l_feats, l_mask, sync_bn)
     acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
@@ -156,7 +164,7 @@ def segment_forward_backward(model, x, l_feats, l_mask, target: torch.Tensor, gr
     dlogits = torch.empty_like(logits)
     K.cross_entropy(logits, target, acc, dlogits, gscale=loss_scale, phase=1)
     E._count(2)
-    dl = segment_backward(model, tape, dlogits, grads)
+    dl = segment_backward(model, tape, dlogits, grads, on_ready)
     return acc[0] / acc[1], dl
 
 
@@ -181,6 +189,53 @@ class SegmentFunction(torch.autograd.Function):
         grads.finalize()
         ctx.tape = None
         return None, dl, None, None, None, None
+
+
+class GradReducer:
+    """Gradient all-reduce driven by ``segment_backward``'s ``on_ready`` callback: each finished parameter group (decoder, stages last
+    to first, patch embedding, text encoder) is handed to ``param.grad`` and flattened into one bucket.
+
+    ``overlap=False`` (default): the buckets are all-reduced when ``wait()`` is called at the end of the backward.
+    ``overlap=True``: every bucket's all-reduce is launched asynchronously (NCCL's own stream) as soon as the group is finished, so it
+    runs under the backward kernels of the earlier stages.  Measured back to back on 2 x B200: 96.7 ms per step overlapped vs 97.4 ms
+    after the backward (1 GPU: 91.7 ms) -- within noise, i.e. the 226 M-gradient all-reduce over NVLink is not what the extra 5-6 ms of
+    the multi-GPU step are made of (SyncBN's 24 small blocking reductions and per-step skew are); kept as an option.
+    With one rank everything is a no-op except the hand-over to ``param.grad``."""
+
+    def __init__(self, overlap: bool = False):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.overlap = overlap
+        self.pending = []
+
+    def ready(self, grads: T.GradStore):
+        def _cb(params):
+            self.reduce(grads.finalize(only=params))
+        return _cb
+
+    def reduce(self, params) -> None:
+        gs = [p.grad for p in params if p.grad is not None]
+        if self.dist is None or not gs:
+            return
+        if not self.overlap:
+            self.pending.append((None, None, gs))
+            return
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        self.pending.append((self.dist.all_reduce(flat, async_op=True), flat, gs))
+
+    def wait(self) -> None:
+        for handle, flat, gs in self.pending:
+            if handle is None:
+                flat = torch.cat([g.reshape(-1) for g in gs])
+                self.dist.all_reduce(flat)
+            else:
+                handle.wait()
+            flat /= self.dist.get_world_size()
+            off = 0
+            for g in gs:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.pending = []
 
 
 def allreduce_gradients(params: List[torch.nn.Parameter], bucket_mb: int = 64) -> None:

@@ -79,3 +79,39 @@ def test_gradient_allreduce_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok and none_kept for _, ok, none_kept in out)
+
+
+def _reducer_worker(rank, world, port, q):
+    """training.GradReducer: per-group asynchronous all-reduce (what segment_backward's on_ready callback drives)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lavt_rs_b200.training import GradReducer
+    from lavt_rs_b200.train_engine import GradStore
+    g = torch.Generator().manual_seed(6)
+    groups = [[torch.nn.Parameter(torch.zeros(s)) for s in shapes] for shapes in (((4, 3), (5,)), ((7, 2, 2),), ((1,), (9, 9)))]
+    base = [[torch.randn(p.shape, generator=g) for p in grp] for grp in groups]
+    store = GradStore()
+    red = GradReducer(overlap=(rank >= 0) and bool(os.environ.get("LAVT_TEST_OVERLAP", "1") == "1"))
+    cb = red.ready(store)
+    for grp, bs in zip(groups, base):
+        for p, b in zip(grp, bs):
+            store.of(p).add_(b * (rank + 1))
+        cb(grp)                              # group finished: hand over + start its all-reduce
+    red.wait()
+    ok = all(torch.allclose(p.grad, 1.5 * b, rtol=1e-6, atol=1e-6) for grp, bs in zip(groups, base) for p, b in zip(grp, bs))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradient_reducer_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33511 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in out)

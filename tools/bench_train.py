@@ -36,6 +36,7 @@ def main():
     p.add_argument("--optimizer", action="store_true", help="include the AdamW update (FusedAdamW over the reference's parameter groups, "
                                                             "poly LR) in the timed step")
     p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
+    p.add_argument("--overlap-allreduce", action="store_true", help="launch each stage's gradient all-reduce under the rest of the backward")
     p.add_argument("--by-tag", action="store_true", help="print the CUDA-event time of every GEMM / attention shape of one step to stderr")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
     a = p.parse_args()
@@ -89,11 +90,13 @@ def main():
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
         l_feats = text(ids, attention_mask=m)[0].permute(0, 2, 1)             # lib/_utils.py:98-100
         grads = T.GradStore()
-        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1)
+        reducer = TR.GradReducer(overlap=a.overlap_allreduce)
+        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
         grads.finalize()
         if not a.frozen_text:
             l_feats.backward(dl)
-        TR.allreduce_gradients(params)
+            reducer.reduce([prm for prm in text.parameters() if prm.requires_grad])
+        reducer.wait()
         if opt is not None:
             opt.step()
             sched.step()
@@ -163,7 +166,7 @@ def main():
         "config": {"workload": "LAVT-RS Video Swin-B training step: BERT-base + backbone + decoder forward, [0.9,1.1]-weighted CE, backward, "
                                "gradient all-reduce; 8x384x384 clips, 20-token expression, window 8x7x7, DropPath off, no optimizer update",
                    "clips_per_gpu_per_step": Bc, "global_clips_per_step": total,
-                   "parallelism": f"data-parallel x{world}" + (", NCCL gradient all-reduce + SyncBN statistics" if world > 1 else ""),
+                   "parallelism": f"data-parallel x{world}" + ((", NCCL gradient all-reduce (" + ("per stage, under the backward" if a.overlap_allreduce else "after the backward") + ") + SyncBN statistics") if world > 1 else ""),
                    "text_encoder": "frozen" if a.frozen_text else "transformers BertModel under autograd (fp32)",
                    "l2": "two rotating batches; saved activations (> 10 GB) exceed the 126 MB L2", "flops_per_clip": flops_clip},
         "clocks": clk, "loss": float(state["loss"].item()), "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
