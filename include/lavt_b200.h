@@ -123,6 +123,11 @@ int lavt_patch_embed_im2col(const float* x, int64_t stride_b, int64_t stride_c, 
  * relative_position_bias_table [L, nH] transposed; out: bf16 [B*nW*N, C].  head_dim must be 32. */
 int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom,
                           void* out_bf16, void* stream);
+/* Same, and lse fp32 [B*nW*N, nH] = log2-sum-exp2 of every score row (what the backward needs besides qkv and out; written by the
+ * tcgen05 kernel only -- lavt_window_attention_has_lse tells whether this geometry gets it: 1 / 0). */
+int lavt_window_attention_lse(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom, void* out_bf16,
+                              float* lse, void* stream);
+int lavt_window_attention_has_lse(const lavt_win_geom_t* geom, int32_t L, int32_t nH);
 /* Kernel selection for lavt_window_attention (process-wide; initial value from the LAVT_ATTN_IMPL environment variable):
  *   0 = auto: tcgen05 / TMEM kernel for windows of <= 400 tokens, mma.sync flash kernels otherwise
  *   1 = mma.sync kernels only.  Returns the previous setting. */
@@ -220,9 +225,10 @@ int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t
                                    const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* stream);
 /* Adjoint of lavt_window_attention: qkv / out as saved by the forward, dout = gradient of out; dqkv bf16 [rows, 3C] = gradient
  * of the UNSCALED qkv projection; dtable_t fp32 [nH, L] accumulates the relative_position_bias_table gradient (transposed).
+ * lse: the row statistics saved by lavt_window_attention_lse, or NULL (then they are recomputed in a first pass).
  * Windows of up to ~400 tokens (shared-memory resident). */
 int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
-                              const lavt_win_geom_t* geom, void* dqkv, float* dtable_t, void* stream);
+                              const lavt_win_geom_t* geom, const float* lse, void* dqkv, float* dtable_t, void* stream);
 
 /* ---- PWAM + LanguageGate backward (adjoints of lavt_pwam_* above; reference lib/video_swin_transformer.py:919-1009, 519-525) ---- */
 /* Per pixel: recompute q^ = IN(q_pre) and the masked word softmax P, dP = dO v^T, dS = P (dP - sum P dP).  Outputs:

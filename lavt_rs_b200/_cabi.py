@@ -84,6 +84,7 @@ SIGNATURES = {
     "lavt_patch_merge_layernorm": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp],
     "lavt_patch_embed_im2col": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "lavt_window_attention": [_vp, _vp, _i32, _i32, _WG, _vp, _vp],
+    "lavt_window_attention_lse": [_vp, _vp, _i32, _i32, _WG, _vp, _vp, _vp],
     "lavt_instnorm_stats": [_vp, _i32, _i64, _i32, _f32, _vp, _vp, _vp],
     "lavt_pwam_kv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_lang_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
@@ -110,7 +111,7 @@ SIGNATURES = {
     "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
     "lavt_layernorm_window_gather_bwd": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
     "lavt_patch_merge_layernorm_bwd": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp],
-    "lavt_window_attention_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _WG, _vp, _vp, _vp],
+    "lavt_window_attention_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _WG, _vp, _vp, _vp, _vp],
     "lavt_pwam_attend_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
     "lavt_pwam_mul_norm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_instnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
@@ -130,7 +131,7 @@ SIGNATURES = {
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
-           "lavt_gemm_splitk_workspace_floats", "lavt_adamw_chunk_elems",
+           "lavt_gemm_splitk_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
 
@@ -140,6 +141,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_instnorm_workspace_floats.restype = C.c_int64
     l.lavt_gemm_splitk_workspace_floats.argtypes = [_i32, _i32, _i32]
     l.lavt_gemm_splitk_workspace_floats.restype = C.c_int64
+    l.lavt_window_attention_has_lse.argtypes = [_WG, _i32, _i32]
+    l.lavt_window_attention_has_lse.restype = C.c_int
     l.lavt_adamw_chunk_elems.argtypes = []
     l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
@@ -368,15 +371,26 @@ def set_attention_impl(impl: str) -> str:
     return "mma" if prev else "auto"
 
 
-def window_attention(qkv: torch.Tensor, table_t: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor) -> None:
-    """table_t: relative_position_bias_table transposed to [nH, L] fp32."""
+def window_attention_has_lse(table_t: torch.Tensor, geom: WinGeom) -> bool:
+    """True if window_attention can also write the per-row log-sum-exp for this geometry (tcgen05 kernel)."""
+    nH, L = table_t.shape
+    return bool(lib().lavt_window_attention_has_lse(C.byref(geom), L, nH))
+
+
+def window_attention(qkv: torch.Tensor, table_t: torch.Tensor, geom: WinGeom, out_bf16: torch.Tensor, lse: Optional[torch.Tensor] = None) -> None:
+    """table_t: relative_position_bias_table transposed to [nH, L] fp32; lse: optional fp32 [rows, nH] row statistics (training)."""
     _c(qkv, torch.bfloat16, "qkv")
     _c(table_t, torch.float32, "table_t")
     nH, L = table_t.shape
     t0 = TIMER.begin()
-    check(lib().lavt_window_attention(qkv.data_ptr(), table_t.data_ptr(), L, nH, C.byref(geom),
-                                      _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
-          "lavt_window_attention")
+    if lse is None:
+        check(lib().lavt_window_attention(qkv.data_ptr(), table_t.data_ptr(), L, nH, C.byref(geom),
+                                          _c(out_bf16, torch.bfloat16, "out").data_ptr(), stream_ptr()),
+              "lavt_window_attention")
+    else:
+        check(lib().lavt_window_attention_lse(qkv.data_ptr(), table_t.data_ptr(), L, nH, C.byref(geom),
+                                              _c(out_bf16, torch.bfloat16, "out").data_ptr(), _c(lse, torch.float32, "lse").data_ptr(),
+                                              stream_ptr()), "lavt_window_attention_lse")
     rows = geom.rows()
     TIMER.end(t0, "window_attn_kernel", 4.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 4,
               f"rows{rows} N{geom.N} nH{nH} shift{geom.sh}")
@@ -631,13 +645,13 @@ def patch_merge_layernorm_bwd(x, B, D, H, W, dy, gamma, dx, dgamma, dbeta, eps: 
                                                stream_ptr()), "lavt_patch_merge_layernorm_bwd")
 
 
-def window_attention_bwd(qkv, out, dout, table_t, geom: WinGeom, dqkv, dtable_t) -> None:
-    """Adjoint of window_attention; dtable_t fp32 [nH, L] accumulates."""
+def window_attention_bwd(qkv, out, dout, table_t, geom: WinGeom, dqkv, dtable_t, lse=None) -> None:
+    """Adjoint of window_attention; dtable_t fp32 [nH, L] accumulates; lse = the forward's row statistics or None (recomputed)."""
     nH, L = table_t.shape
     t0 = TIMER.begin()
     check(lib().lavt_window_attention_bwd(_c(qkv, torch.bfloat16, "qkv").data_ptr(), _c(out, torch.bfloat16, "out").data_ptr(),
                                           _c(dout, torch.bfloat16, "dout").data_ptr(), _c(table_t, torch.float32, "table_t").data_ptr(),
-                                          L, nH, C.byref(geom), _c(dqkv, torch.bfloat16, "dqkv").data_ptr(),
+                                          L, nH, C.byref(geom), ptr(lse), _c(dqkv, torch.bfloat16, "dqkv").data_ptr(),
                                           ptr(dtable_t), stream_ptr()), "lavt_window_attention_bwd")
     rows = geom.rows()
     TIMER.end(t0, "window_attn_bwd_kernel", 12.0 * rows * geom.N * nH * 32, 2.0 * rows * nH * 32 * 8, f"rows{rows} N{geom.N} nH{nH}")

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
         const WinTok w = win_token(p.win, row0 + i);
         a.code = w.code;
         a.rid = w.rid;
+        if (p.lse) a.lse = __ldg(p.lse + (row0 + i) * p.nH + head);      // saved by the forward kernel: pass 0 is skipped
       }
       tok[i] = a;
     }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
       tok[i].delta = acc;
     }
     // ---- pass 0: log2-sum-exp2 of every score row (warp = 16 query rows, all keys)
-    for (int qt = warp; qt < NP / 16; qt += AB_WARPS) {
+    for (int qt = warp; qt < (p.lse ? 0 : NP / 16); qt += AB_WARPS) {
       const int i0 = qt * 16;
       uint32_t qf[2][4];
 #pragma unroll

@@ -421,6 +421,8 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const float l = w0 * psb[0] + w1 * psb[128] + w2 * psb[256];
         const float inv = rep ? 1.0f : 1.0f / l;
         const float wgt[3] = {w0 * inv, w1 * inv, w2 * inv};
+        float lse_val = 0.f;                                // row statistic for the backward pass (base 2, like the scores)
+        if (p.lse) lse_val = m + __log2f(l);
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = 0.f;
@@ -452,6 +454,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
               ll = fmaf(wq[k], x0[k * 16 * 34 + 1], ll);
             }
             const float iv = 1.0f / ll;
+            if (p.lse) lse_val = mm + __log2f(ll);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float v = 0.f;
@@ -463,6 +466,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           named_bar(1 + TC_EPI_GROUP, 128);
         }
         if (i < N && (!rep || q == 0)) {
+          if (p.lse) p.lse[(static_cast<long long>(win) * N + i) * p.nH + head] = lse_val;
           __nv_bfloat16* dst = p.out + (static_cast<long long>(win) * N + i) * p.C + head * TC_HD;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {

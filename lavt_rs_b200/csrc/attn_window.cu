@@ -393,6 +393,7 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
     // LAVT_ATTN_IMPL=mma (or lavt_set_attention_impl(1)) forces the mma.sync kernels below
     if (attn_impl_setting(-1) == 0 && window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
   }
+  LAVT_REQUIRE(p.lse == nullptr, "attention: row statistics (lse) are produced by the tcgen05 kernel only (N=%d)", N);
   if (N <= 512) {
     // key tile = the candidate with the least padding; warps = a divisor-friendly count of the 16-row strips
     const int kvts[3] = {80, 64, 48};

@@ -165,6 +165,25 @@ int lavt_window_attention(const void* qkv, const float* table_t, int32_t L, int3
   return window_attn_dispatch(p, S(stream));
 }
 
+int lavt_window_attention_lse(const void* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom, void* out_bf16,
+                              float* lse, void* stream) {
+  LAVT_REQUIRE(geom != nullptr, "attention: geometry is NULL");
+  AttnParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.qkv = CB(qkv); p.table_t = table_t; p.out = MB(out_bf16); p.nH = nH; p.C = nH * 32; p.L = L; p.lse = lse;
+  return window_attn_dispatch(p, S(stream));
+}
+
+int lavt_window_attention_has_lse(const lavt_win_geom_t* geom, int32_t L, int32_t nH) {
+  if (geom == nullptr) return 0;
+  AttnParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::memcpy(&p.win, geom, sizeof(WinGeom));
+  p.nH = nH; p.C = nH * 32; p.L = L;
+  return (attn_impl_setting(-1) == 0 && window_attn_tc_supported(p)) ? 1 : 0;
+}
+
 int lavt_set_attention_impl(int32_t impl) { return attn_impl_setting(impl != 0 ? 1 : 0); }
 
 int64_t lavt_instnorm_workspace_floats(int32_t B, int64_t n, int32_t C) { return colstats_workspace_floats(B, n, C); }
@@ -364,12 +383,12 @@ int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t
 }
 
 int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
-                              const lavt_win_geom_t* geom, void* dqkv, float* dtable_t, void* stream) {
+                              const lavt_win_geom_t* geom, const float* lse, void* dqkv, float* dtable_t, void* stream) {
   LAVT_REQUIRE(geom != nullptr, "attention backward: geometry is NULL");
   AttnBwdParams p;
   std::memset(&p, 0, sizeof(p));
   std::memcpy(&p.win, geom, sizeof(WinGeom));
-  p.qkv = CB(qkv); p.out = CB(out); p.dout = CB(dout); p.table_t = table_t; p.dqkv = MB(dqkv); p.dtable_t = dtable_t;
+  p.qkv = CB(qkv); p.out = CB(out); p.dout = CB(dout); p.table_t = table_t; p.dqkv = MB(dqkv); p.dtable_t = dtable_t; p.lse = lse;
   p.C = nH * 32; p.nH = nH; p.L = L;
   p.qscale = 0.17677669529663687f;      // 32^-0.5
   LAVT_REQUIRE(L == (2 * p.win.Wd - 1) * (2 * p.win.Wh - 1) * (2 * p.win.Ww - 1), "attention backward: table length %d does not match the window", L);

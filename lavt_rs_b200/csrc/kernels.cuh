@@ -36,6 +36,7 @@ struct AttnParams {
   __nv_bfloat16* out;         // [rows, C]
   int C, nH, L;
   WinGeom win;
+  float* lse;                 // [rows, nH] log2-sum-exp2 of every score row, or nullptr (training: saved for the backward; tcgen05 kernel only)
 };
 int window_attn_dispatch(const AttnParams& p, cudaStream_t st);
 // tcgen05 / TMEM variant (attn_tc.cu): windows of up to 400 tokens
@@ -51,6 +52,7 @@ struct AttnBwdParams {
   const float* table_t;        // [nH, L]
   __nv_bfloat16* dqkv;         // [rows, 3C] gradient of the UNSCALED qkv projection output
   float* dtable_t;             // [nH, L] accumulated (+=), or nullptr
+  const float* lse;            // [rows, nH] row statistics saved by the forward kernel, or nullptr (recomputed in a first pass)
   int C, nH, L;
   float qscale;                // hd^-0.5
   WinGeom win;

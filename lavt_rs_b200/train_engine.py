@@ -201,7 +201,9 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     qkv = torch.empty(rows, 3 * C, device=dev, dtype=torch.bfloat16)
     K.gemm_bf16(xw, qkv_w, cscale=qkv_s, bias=qkv_b, out_bf16=qkv)
     att = torch.empty(rows, C, device=dev, dtype=torch.bfloat16)
-    K.window_attention(qkv, table_t, geom, att)
+    # row log-sum-exp of the scores, saved for the backward when the tcgen05 kernel runs (else the backward recomputes it)
+    lse = torch.empty(rows, nH, device=dev, dtype=torch.float32) if K.window_attention_has_lse(table_t, geom) else None
+    K.window_attention(qkv, table_t, geom, att, lse=lse)
     x1 = torch.empty_like(x)
     K.gemm_bf16(att, proj_w, bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x1, win=geom, rscale=s_attn, rscale_rows=tok)
     h1 = torch.empty(n, C, device=dev, dtype=torch.bfloat16)
@@ -213,12 +215,12 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     x2 = torch.empty_like(x)
     K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x1, out_f32=x2, out_bf16=xb_out, rscale=s_mlp, rscale_rows=tok)
     _count(8)
-    return x2, (x, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok)
+    return x2, (x, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok, lse)
 
 
 def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace) -> torch.Tensor:
     """dx fp32 [n, C] = gradient of the block output; updated IN PLACE to the gradient of the block input and returned."""
-    x0, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok = saved
+    x0, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok, lse = saved
     n, C = x0.shape
     dev = x0.device
     rows = geom.rows()
@@ -241,7 +243,7 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
     linear_bwd(dyw, att, blk.attn.proj.weight, blk.attn.proj.bias, grads, ws, pw, "proj", dx_bf16=datt)
     dqkv = ws.get("bw_dqkv", (rows, 3 * C), torch.bfloat16, dev)
     tbl = blk.attn.relative_position_bias_table
-    K.window_attention_bwd(qkv, att, datt, table_t, geom, dqkv, grads.table_t(tbl) if tbl.requires_grad else None)
+    K.window_attention_bwd(qkv, att, datt, table_t, geom, dqkv, grads.table_t(tbl) if tbl.requires_grad else None, lse=lse)
     dxw = ws.get("bw_dxw", (rows, C), torch.bfloat16, dev)
     linear_bwd(dqkv, xw, blk.attn.qkv.weight, blk.attn.qkv.bias, grads, ws, pw, "qkv", dx_bf16=dxw)
     K.layernorm_window_gather_bwd(x0, geom, dxw, blk.norm1.weight, dx, grads.of(blk.norm1.weight), grads.of(blk.norm1.bias),

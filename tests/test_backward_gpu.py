@@ -184,6 +184,13 @@ def test_swin_block_backward(stage, shifted, dims):
     torch.cuda.synchronize()
     assert rel_l2(dx, dx_ref.reshape(-1, C)) < GRAD_L2, ("dx", rel_l2(dx, dx_ref.reshape(-1, C)))
     check_grads(grads.named(blk), pg_ref, f"swin block stage {stage} shifted={shifted}")
+    # the forward kernel saved the row log-sum-exp for the attention backward; without it the backward recomputes it in a first pass
+    assert saved[-1] is not None and saved[-1].shape == (saved[8].rows(), nH)
+    grads2 = T.GradStore()
+    dx2 = T.swin_block_bwd(blk, saved[:-1] + (None,), gout.cuda().reshape(-1, C).contiguous(), grads2, ws)
+    assert rel_l2(dx2, dx) < 5e-3
+    n1, n2 = grads.named(blk), grads2.named(blk)
+    assert all(rel_l2(n2[k], n1[k]) < 5e-3 for k in ("attn.qkv.weight", "attn.relative_position_bias_table"))
 
 
 def test_swin_block_drop_path():
