@@ -284,3 +284,28 @@ def train_forward(model, x, text, l_mask):
         l_feats = text                                                                      # LAVT: precomputed language features
     anchor = torch.zeros((), device=x.device, requires_grad=True)
     return SegmentFunction.apply(x, l_feats, l_mask, model, uses_sync_bn(model), anchor)
+
+
+class GraphedTextEncoder(torch.nn.Module):
+    """The text encoder's forward AND backward as two CUDA graphs (``torch.cuda.make_graphed_callables``): BERT-base on 4 x 20
+    tokens is ~600 tiny kernels in each direction, i.e. launch-bound (4.8 + 3.9 ms eager vs the GPU time of a few hundred
+    microseconds).  Shapes are static per (batch, sentence length); parameters stay ordinary autograd leaves."""
+
+    class _Wrap(torch.nn.Module):
+        def __init__(self, enc):
+            super().__init__()
+            self.enc = enc
+
+        def forward(self, ids, mask):
+            return self.enc(ids, attention_mask=mask)[0]          # last_hidden_state (B, Nl, 768)
+
+    def __init__(self, text_encoder, sample_ids: torch.Tensor, sample_mask: torch.Tensor):
+        super().__init__()
+        self.wrap = self._Wrap(text_encoder)
+        self.graphed = torch.cuda.make_graphed_callables(self.wrap, (sample_ids, sample_mask))
+        self.shape = tuple(sample_ids.shape)
+
+    def forward(self, ids, mask):
+        if tuple(ids.shape) != self.shape:
+            raise ValueError(f"GraphedTextEncoder was captured for token ids of shape {self.shape}, got {tuple(ids.shape)}")
+        return self.graphed(ids, mask).permute(0, 2, 1)           # (B, 768, Nl) = lib/_utils.py:98-100

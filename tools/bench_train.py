@@ -37,6 +37,8 @@ def main():
                                                             "poly LR) in the timed step")
     p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
     p.add_argument("--overlap-allreduce", action="store_true", help="launch each stage's gradient all-reduce under the rest of the backward")
+    p.add_argument("--eager-text", action="store_true", help="run the text encoder eagerly instead of as CUDA graphs")
+    p.add_argument("--phases", action="store_true", help="print CUDA-event times of the phases of one step to stderr")
     p.add_argument("--by-tag", action="store_true", help="print the CUDA-event time of every GEMM / attention shape of one step to stderr")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's fwd+bwd of one clip on the host cores (~1 min, 14 GB)")
     a = p.parse_args()
@@ -83,12 +85,15 @@ def main():
         batches.append((x.to(dev), ids.to(dev), m.to(dev), tgt.to(dev)))
 
     state = {}
+    text_fn = lambda ids, m: text(ids, attention_mask=m)[0].permute(0, 2, 1)             # noqa: E731  lib/_utils.py:98-100
+    if not a.eager_text and not a.frozen_text:
+        text_fn = TR.GraphedTextEncoder(text, batches[0][1], batches[0][2])
 
     def step(i):
         x, ids, m, tgt = batches[i % 2]
         for prm in params:
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
-        l_feats = text(ids, attention_mask=m)[0].permute(0, 2, 1)             # lib/_utils.py:98-100
+        l_feats = text_fn(ids, m)
         grads = T.GradStore()
         reducer = TR.GradReducer(overlap=a.overlap_allreduce)
         loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
@@ -122,6 +127,46 @@ def main():
             ms = t.item()
         return ms
 
+    if a.phases and rank == 0:
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        for _ in range(3):
+            step(0)
+        x, ids, m, tgt = batches[0]
+        for prm in params:
+            prm.grad = None
+        marks = [("start", ev())]
+        l_feats = text_fn(ids, m)
+        marks.append(("text encoder forward (torch)", ev()))
+        logits, tape = TR.segment_forward(model, x, l_feats.detach(), m, sync_bn=False)
+        marks.append(("segment forward (saved activations)", ev()))
+        acc = torch.zeros(2, device=dev)
+        K.cross_entropy(logits, tgt, acc, phase=0)
+        dlog = torch.empty_like(logits)
+        K.cross_entropy(logits, tgt, acc, dlog, phase=1)
+        marks.append(("weighted cross-entropy fwd + bwd", ev()))
+        grads = T.GradStore()
+        stage_marks = []
+        dl = TR.segment_backward(model, tape, dlog, grads, on_ready=lambda ps: stage_marks.append(ev()))
+        marks.append(("segment backward", ev()))
+        grads.finalize()
+        marks.append(("hand gradients to param.grad", ev()))
+        if not a.frozen_text:
+            l_feats.backward(dl)
+        marks.append(("text encoder backward (torch autograd)", ev()))
+        if opt is not None:
+            opt.step()
+        marks.append(("FusedAdamW", ev()))
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(marks, marks[1:]):
+            print(f"{e0.elapsed_time(e1):8.2f} ms  {n1}", file=sys.stderr)
+        names = ["decoder backward", "stage 3 backward", "stage 2 backward", "stage 1 backward", "stage 0 backward", "patch embed backward"]
+        prev = marks[3][1]
+        for nm, e in zip(names, stage_marks):
+            print(f"    {prev.elapsed_time(e):8.2f} ms  {nm}", file=sys.stderr)
+            prev = e
     E.LAUNCHES = 0
     step(0)
     torch.cuda.synchronize()
@@ -167,7 +212,7 @@ def main():
                                "gradient all-reduce; 8x384x384 clips, 20-token expression, window 8x7x7, DropPath off, no optimizer update",
                    "clips_per_gpu_per_step": Bc, "global_clips_per_step": total,
                    "parallelism": f"data-parallel x{world}" + ((", NCCL gradient all-reduce (" + ("per stage, under the backward" if a.overlap_allreduce else "after the backward") + ") + SyncBN statistics") if world > 1 else ""),
-                   "text_encoder": "frozen" if a.frozen_text else "transformers BertModel under autograd (fp32)",
+                   "text_encoder": "frozen" if a.frozen_text else ("transformers BertModel under autograd (fp32)" + ("" if a.eager_text else ", forward and backward replayed as CUDA graphs")),
                    "l2": "two rotating batches; saved activations (> 10 GB) exceed the 126 MB L2", "flops_per_clip": flops_clip},
         "clocks": clk, "loss": float(state["loss"].item()), "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
         "peak_memory_bytes": peak_mem,
