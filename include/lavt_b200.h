@@ -202,6 +202,14 @@ int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ld
  * workspace as for lavt_gemm_bf16_splitk with M = n_out, N = n_in, K = tokens).  n_out % 8 == 0, n_in % 32 == 0. */
 int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t tokens, int32_t n_out, int32_t n_in,
                          float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream);
+/* conv3x3 (pad 1, stride 1) WEIGHT gradient in one launch, no im2col and no padded / transposed copies:
+ *   dw_taps[co, (ky*3+kx)*Cin + ci] (+)= sum_{img,h,w} dz[img,h,w,co] * x[img,h+ky-1,w+kx-1,ci]
+ * dz, x: NHWC bf16 (contiguous).  Both operands are 4-D TMA boxes of 64 channels x (TH x TW = 64 pixels) that land in shared memory as
+ * MN-major tcgen05 operands; the tap is a coordinate offset of the x box and the zero padding is TMA's out-of-bounds fill.  Split-K
+ * over the pixel tiles.  Cin % 64 == 0.  Adjoint of lavt_conv3x3_bf16 w.r.t. its weights (lib/mask_predictor.py:56-87). */
+int64_t lavt_conv3x3_wgrad_workspace_floats(int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+int lavt_conv3x3_wgrad(const void* dz_nhwc, const void* x_nhwc, int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                       float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream);
 /* out[N, M] (pitch ldo) = in[M, N]^T (pitch ldi), bf16 */
 int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream);
 /* dst[n] += sum_m x[m, n]  (bias gradients); x is bf16 (is_bf16 != 0) or fp32 */

@@ -102,6 +102,7 @@ SIGNATURES = {
     # ---- backward pass ----
     "lavt_gemm_bf16_splitk": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
     "lavt_gemm_bf16_wgrad": [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
+    "lavt_conv3x3_wgrad": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp],
     "lavt_transpose_bf16": [_vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
@@ -131,7 +132,7 @@ SIGNATURES = {
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
-           "lavt_gemm_splitk_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
+           "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
 
@@ -143,6 +144,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_gemm_splitk_workspace_floats.restype = C.c_int64
     l.lavt_window_attention_has_lse.argtypes = [_WG, _i32, _i32]
     l.lavt_window_attention_has_lse.restype = C.c_int
+    l.lavt_conv3x3_wgrad_workspace_floats.argtypes = [_i32, _i32, _i32, _i32, _i32]
+    l.lavt_conv3x3_wgrad_workspace_floats.restype = C.c_int64
     l.lavt_adamw_chunk_elems.argtypes = []
     l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
@@ -570,6 +573,26 @@ def gemm_bf16_wgrad(dy: torch.Tensor, x: torch.Tensor, dst: torch.Tensor, worksp
                                      dst.stride(0), 1 if accumulate else 0, stream_ptr()), "lavt_gemm_bf16_wgrad")
     TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * tokens * n_out * n_in, 2.0 * tokens * (n_out + n_in) + 4.0 * n_out * n_in,
               f"wgrad-mn tokens{tokens} out{n_out} in{n_in}")
+
+
+def conv3x3_wgrad_workspace_floats(n_img: int, H: int, W: int, Cin: int, Cout: int) -> int:
+    return int(lib().lavt_conv3x3_wgrad_workspace_floats(n_img, H, W, Cin, Cout))
+
+
+def conv3x3_wgrad(dz_nhwc: torch.Tensor, x_nhwc: torch.Tensor, dw_taps: torch.Tensor, workspace: torch.Tensor, *, accumulate: bool = True) -> None:
+    """dw_taps fp32 [Cout, 9*Cin] (+)= conv3x3 weight gradient from dz bf16 [n,H,W,Cout] and x bf16 [n,H,W,Cin] (both contiguous NHWC)."""
+    _c(dz_nhwc, torch.bfloat16, "dz")
+    _c(x_nhwc, torch.bfloat16, "x")
+    n, H, W, Cout = dz_nhwc.shape
+    Cin = x_nhwc.shape[-1]
+    if tuple(x_nhwc.shape[:3]) != (n, H, W) or tuple(dw_taps.shape) != (Cout, 9 * Cin):
+        raise LavtError("conv3x3_wgrad: shape mismatch")
+    t0 = TIMER.begin()
+    check(lib().lavt_conv3x3_wgrad(dz_nhwc.data_ptr(), x_nhwc.data_ptr(), n, H, W, Cin, Cout, _c(workspace, torch.float32, "workspace").data_ptr(),
+                                   workspace.numel(), _c(dw_taps, torch.float32, "dw_taps").data_ptr(), 1 if accumulate else 0, stream_ptr()),
+          "lavt_conv3x3_wgrad")
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * n * H * W * Cout * 9 * Cin, 2.0 * n * H * W * (Cout + Cin) + 4.0 * Cout * 9 * Cin,
+              f"conv-wgrad {n}x{H}x{W} Cin{Cin} Cout{Cout}")
 
 
 def transpose_bf16(x: torch.Tensor, out: torch.Tensor) -> None:

@@ -144,7 +144,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int total_tiles = m_tiles * n_tiles;
   const int conv_cpb = (p.cCin + GEMM_BK - 1) / GEMM_BK;
-  const int num_kb = (p.rowmap == ROWMAP_CONV) ? p.taps * conv_cpb : (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = (p.rowmap == ROWMAP_CONV) ? p.taps * conv_cpb
+                     : (p.rowmap == ROWMAP_WGCONV) ? (p.K / GEMM_BK) : (p.K + GEMM_BK - 1) / GEMM_BK;
   // split-K: work item = (tile, split); every split owns at least one k-block (host guarantees (ksplit - 1) * kbs < num_kb)
   const int nsplit = p.ksplit > 1 ? p.ksplit : 1;
   const int kbs = p.ksplit > 1 ? p.kbs : num_kb;
@@ -225,6 +226,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
               tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
             }
+          } else if (p.rowmap == ROWMAP_WGCONV) {
+            // conv weight gradient: k-block = one 64-pixel tile of one image; A = dz channels, B = x channels shifted by the tap
+            const int tw = kb % p.cTilesW;
+            const int th = (kb / p.cTilesW) % p.cTilesH;
+            const int im = kb / (p.cTilesW * p.cTilesH);
+            const int ph0 = th * p.cTH, pw0 = tw * p.cTW;
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_4d(sa + j * 8192, &tmA, &full_bar[s], mt * GEMM_BM + j * 64, pw0, ph0, im);
+#pragma unroll
+            for (int j = 0; j < GEMM_BN / 64; ++j) {
+              const int col = n0 + j * 64;                       // column of C = tap * Cin + ci (Cin % 64 == 0: an atom never straddles taps)
+              int tap = col / p.cCin, ci0 = col - tap * p.cCin;
+              if (tap >= 9) { tap = 8; ci0 = p.cCin; }           // past N: channel coordinate out of bounds -> zero fill
+              tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], ci0, pw0 + tap % 3 - 1, ph0 + tap / 3 - 1, im);
+            }
+            continue;
           } else if (p.mnmajor) {
             // operands stored [K, MN] row-major: boxes of 64 k-rows x 64 MN elements, one 8 KB box per 64-wide MN atom
 #pragma unroll
@@ -530,7 +547,8 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
   LAVT_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   LAVT_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
   LAVT_REQUIRE(p.mnmajor || p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);
-  LAVT_REQUIRE(!p.mnmajor || (p.M % 8 == 0 && p.rowmap == ROWMAP_IDENTITY), "gemm (MN-major operands): M=%d must be a multiple of 8", p.M);
+  LAVT_REQUIRE(!p.mnmajor || (p.M % 8 == 0 && (p.rowmap == ROWMAP_IDENTITY || p.rowmap == ROWMAP_WGCONV)),
+               "gemm (MN-major operands): M=%d must be a multiple of 8", p.M);
   LAVT_REQUIRE(p.ldo % 16 == 0 && p.ldo >= p.N, "gemm: ldo=%d invalid for N=%d (need a multiple of 16)", p.ldo, p.N);
   LAVT_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) | reinterpret_cast<uintptr_t>(p.out_bf16) |
                 reinterpret_cast<uintptr_t>(p.resid) | reinterpret_cast<uintptr_t>(p.mul)) % 32 == 0,
@@ -562,6 +580,19 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     }
     if (rc) return rc;
     m_tiles = n_img * p.cTilesH * p.cTilesW;
+  } else if (p.rowmap == ROWMAP_WGCONV) {
+    LAVT_REQUIRE(p.mnmajor == 1 && p.cCin % 64 == 0 && p.cTH * p.cTW == 64 && p.N == 9 * p.cCin, "conv wgrad: bad configuration");
+    const int n_img = p.K / (p.cTilesH * p.cTilesW * 64);
+    uint64_t dimsA[4] = {(uint64_t)p.M, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
+    uint64_t sA[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH};
+    uint64_t dimsB[4] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
+    uint64_t sB[3] = {(uint64_t)ldb * 2, (uint64_t)ldb * 2 * p.cW, (uint64_t)ldb * 2 * p.cW * p.cH};
+    uint32_t box[4] = {64, (uint32_t)p.cTW, (uint32_t)p.cTH, 1};
+    int rc = make_tmap_bf16(&tmA, A, 4, dimsA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB, Bw, 4, dimsB, sB, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   } else if (p.mnmajor) {
     // A stored [K, M] row-major, B stored [K, N] row-major: 64 x 64 boxes (inner = 64 MN elements = one 128-byte swizzle row)
     uint64_t dimsA[2] = {(uint64_t)p.M, (uint64_t)p.K}, dimsB[2] = {(uint64_t)p.N, (uint64_t)p.K};

@@ -6,7 +6,7 @@
 namespace lavt {
 
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
-enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2 };
+enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2, ROWMAP_WGCONV = 3 };
 
 // out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] * rscale[orow(m) / rs_rows] + resid[orow(m), n]
 struct GemmParams {
@@ -36,6 +36,9 @@ struct GemmParams {
   int ksplit;                // 0 / 1 = off; s > 1: work item = (tile, split); split ks accumulates k-blocks [ks*kbs, (ks+1)*kbs)
   int kbs;                   // k-blocks per split
   long long split_stride;    // out_f32 of split ks = out_f32 + ks * split_stride (partials, reduced by splitk_reduce)
+  // ROWMAP_WGCONV (conv3x3 WEIGHT gradient, with mnmajor = 1): C[co, tap*Cin + ci] = sum_pixels dz[pix, co] * x[pix + tap, ci].  A = dz
+  // and B = x are 4-D NHWC tensor maps (C, W, H, Nimg); a k-block is a cTH x cTW = 64-pixel tile, the tap is a coordinate offset of
+  // the B box and the zero padding is TMA's out-of-bounds fill -- no im2col, no padded or transposed copies.  M = Cout, N = 9*Cin.
   int mnmajor;               // 1: both operands are stored [K, M] / [K, N] row-major (dW = dY^T X straight from the row-major activations):
                              //    TMA boxes of 64 k-rows x 64 MN-elements, MN-major shared-memory descriptors, no transposed copies
   int b_koff;                // added to the K coordinate of the B operand (conv weight gradient: tap offset in the padded pixel axis)

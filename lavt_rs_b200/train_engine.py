@@ -545,8 +545,15 @@ def _cbr_bwd(dec, saved, dt: torch.Tensor, grads: GradStore, ws: Workspace, sync
     dz = ws.get("bw_dz", (n, H, W, hid), torch.bfloat16, dev)
     K.bn_relu_bwd_apply(dt, t.view(npix, hid), z, stats, bn.weight, sums, dz.view(npix, hid), n_stat)
     _count(2)
-    if conv.weight.requires_grad:
-        # dW[co, tap, ci] = sum_p dz^T[co, p] x^T[ci, p + (ky-1)*Wp + (kx-1)] over the zero-padded pixel axis (rows of Wp = W+2 rounded
+    if conv.weight.requires_grad and Cin % 64 == 0:
+        # one launch: dz and x are read in place through 4-D TMA boxes (64 channels x 64 pixels = MN-major tcgen05 operands), the tap
+        # is a coordinate offset of the x box, the zero padding TMA's out-of-bounds fill
+        part = ws.get("bw_splitk", (K.conv3x3_wgrad_workspace_floats(n, H, W, Cin, hid),), torch.float32, dev)
+        K.conv3x3_wgrad(dz, x_nhwc, grads.conv_taps(conv.weight), part, accumulate=True)
+        _count(2)
+    elif conv.weight.requires_grad:
+        # channel counts that are not a multiple of 64 (Swin-T/S decoders): nine split-K GEMMs over zero-padded transposed layouts.
+        # dW[co, tap, ci] = sum_p dz^T[co, p] x^T[ci, p + (ky-1)*Wp + (kx-1)] over the padded pixel axis (rows of Wp = W+2 rounded
         # up to 8 columns): the row part of the offset is a 16-byte aligned TMA coordinate, the +-1 part a pre-shifted copy of x^T
         Wp = _pad8(W + 2)
         Kp = n * (H + 2) * Wp
