@@ -210,6 +210,10 @@ int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ld
 int64_t lavt_conv3x3_wgrad_workspace_floats(int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
 int lavt_conv3x3_wgrad(const void* dz_nhwc, const void* x_nhwc, int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                        float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream);
+/* the same for Conv3d(3,3,3): dw_taps[co, ((kz*3+ky)*3+kx)*Cin + ci] over NDHWC operands, 5-D TMA boxes (SepTPWAM, adjoint of lavt_conv3d_bf16) */
+int64_t lavt_conv3d_wgrad_workspace_floats(int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+int lavt_conv3d_wgrad(const void* dz_ndhwc, const void* x_ndhwc, int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                      float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream);
 /* out[N, M] (pitch ldo) = in[M, N]^T (pitch ldi), bf16 */
 int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream);
 /* dst[n] += sum_m x[m, n]  (bias gradients); x is bf16 (is_bf16 != 0) or fp32 */

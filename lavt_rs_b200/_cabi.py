@@ -103,6 +103,7 @@ SIGNATURES = {
     "lavt_gemm_bf16_splitk": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
     "lavt_gemm_bf16_wgrad": [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
     "lavt_conv3x3_wgrad": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp],
+    "lavt_conv3d_wgrad": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp],
     "lavt_transpose_bf16": [_vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
@@ -132,7 +133,7 @@ SIGNATURES = {
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
-           "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
+           "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
 
@@ -146,6 +147,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_window_attention_has_lse.restype = C.c_int
     l.lavt_conv3x3_wgrad_workspace_floats.argtypes = [_i32, _i32, _i32, _i32, _i32]
     l.lavt_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    l.lavt_conv3d_wgrad_workspace_floats.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32]
+    l.lavt_conv3d_wgrad_workspace_floats.restype = C.c_int64
     l.lavt_adamw_chunk_elems.argtypes = []
     l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
@@ -593,6 +596,24 @@ def conv3x3_wgrad(dz_nhwc: torch.Tensor, x_nhwc: torch.Tensor, dw_taps: torch.Te
           "lavt_conv3x3_wgrad")
     TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * n * H * W * Cout * 9 * Cin, 2.0 * n * H * W * (Cout + Cin) + 4.0 * Cout * 9 * Cin,
               f"conv-wgrad {n}x{H}x{W} Cin{Cin} Cout{Cout}")
+
+
+def conv3d_wgrad(dz_ndhwc: torch.Tensor, x_ndhwc: torch.Tensor, dw_taps: torch.Tensor, ws_get, *, accumulate: bool = True) -> None:
+    """dw_taps fp32 [Cout, 27*Cin] (+)= Conv3d(3,3,3) weight gradient from dz bf16 [B,D,H,W,Cout] and x bf16 [B,D,H,W,Cin] (contiguous);
+    ``ws_get(n_floats)`` returns an fp32 workspace tensor of at least that many elements."""
+    _c(dz_ndhwc, torch.bfloat16, "dz")
+    _c(x_ndhwc, torch.bfloat16, "x")
+    B, D, H, W, Cout = dz_ndhwc.shape
+    Cin = x_ndhwc.shape[-1]
+    if tuple(x_ndhwc.shape[:4]) != (B, D, H, W) or tuple(dw_taps.shape) != (Cout, 27 * Cin):
+        raise LavtError("conv3d_wgrad: shape mismatch")
+    workspace = ws_get(int(lib().lavt_conv3d_wgrad_workspace_floats(B, D, H, W, Cin, Cout)))
+    t0 = TIMER.begin()
+    check(lib().lavt_conv3d_wgrad(dz_ndhwc.data_ptr(), x_ndhwc.data_ptr(), B, D, H, W, Cin, Cout, _c(workspace, torch.float32, "workspace").data_ptr(),
+                                  workspace.numel(), _c(dw_taps, torch.float32, "dw_taps").data_ptr(), 1 if accumulate else 0, stream_ptr()),
+          "lavt_conv3d_wgrad")
+    TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * B * D * H * W * Cout * 27 * Cin, 2.0 * B * D * H * W * (Cout + Cin) + 4.0 * Cout * 27 * Cin,
+              f"conv3d-wgrad {B}x{D}x{H}x{W} Cin{Cin} Cout{Cout}")
 
 
 def transpose_bf16(x: torch.Tensor, out: torch.Tensor) -> None:

@@ -323,25 +323,7 @@ int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ld
   return splitk_reduce_dispatch(workspace, ks, 1LL * p.M * p.N, p.N, dst, ldd, accumulate, S(stream));
 }
 
-int64_t lavt_conv3x3_wgrad_workspace_floats(int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
-  int tw = 8; long long best = -1;
-  for (int t = 1; t <= 64; t *= 2) {
-    const int th = 64 / t;
-    const long long area = 1LL * ((H + th - 1) / th) * th * ((W + t - 1) / t) * t;
-    if (best < 0 || area < best || (area == best && t > tw)) { best = area; tw = t; }
-  }
-  const int th = 64 / tw;
-  const long long K = 1LL * n_img * ((H + th - 1) / th) * ((W + tw - 1) / tw) * 64;
-  int ks, kbs;
-  splitk_plan(Cout, 9 * Cin, static_cast<int>(K), &ks, &kbs);
-  return 1LL * ks * Cout * 9 * Cin;
-}
-
-int lavt_conv3x3_wgrad(const void* dz_nhwc, const void* x_nhwc, int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                       float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream) {
-  LAVT_REQUIRE(n_img > 0 && H > 0 && W > 0 && Cin % 64 == 0 && Cout % 8 == 0, "conv wgrad: need Cin %% 64 == 0 and Cout %% 8 == 0 (Cin=%d, Cout=%d)", Cin, Cout);
-  GemmParams p;
-  std::memset(&p, 0, sizeof(p));
+static void wgrad_tile(GemmParams& p, int H, int W) {
   int tw = 8; long long best = -1;
   for (int t = 1; t <= 64; t *= 2) {          // 64-pixel tile with the least padded area
     const int th = 64 / t;
@@ -351,21 +333,51 @@ int lavt_conv3x3_wgrad(const void* dz_nhwc, const void* x_nhwc, int32_t n_img, i
   p.cTW = tw; p.cTH = 64 / tw;
   p.cTilesW = (W + p.cTW - 1) / p.cTW;
   p.cTilesH = (H + p.cTH - 1) / p.cTH;
-  p.cH = H; p.cW = W; p.cCin = Cin; p.taps = 9;
-  const long long K = 1LL * n_img * p.cTilesH * p.cTilesW * 64;
+  p.cH = H; p.cW = W;
+}
+
+static int conv_wgrad_impl(const void* dz, const void* x, int n_frames, int D, int H, int W, int Cin, int Cout, int taps, float* workspace,
+                           int64_t workspace_floats, float* dw_taps, int accumulate, void* stream, int64_t* need_only) {
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  wgrad_tile(p, H, W);
+  p.cCin = Cin; p.taps = taps; p.cD = D;
+  const long long K = 1LL * n_frames * p.cTilesH * p.cTilesW * 64;
   LAVT_REQUIRE(K < (1LL << 31), "conv wgrad: too many pixels");
-  p.M = Cout; p.N = 9 * Cin; p.K = static_cast<int>(K);
+  p.M = Cout; p.N = taps * Cin; p.K = static_cast<int>(K);
   int ks, kbs;
   splitk_plan(p.M, p.N, p.K, &ks, &kbs);
+  if (need_only) { *need_only = 1LL * ks * p.M * p.N; return LAVT_OK; }
+  LAVT_REQUIRE(n_frames > 0 && H > 0 && W > 0 && Cin % 64 == 0 && Cout % 8 == 0, "conv wgrad: need Cin %% 64 == 0 and Cout %% 8 == 0 (Cin=%d, Cout=%d)", Cin, Cout);
   LAVT_REQUIRE(workspace && workspace_floats >= 1LL * ks * p.M * p.N, "conv wgrad: workspace too small");
   p.out_f32 = workspace;
   p.ldo = p.N;
   p.rowmap = ROWMAP_WGCONV;
   p.mnmajor = 1;
   p.ksplit = ks; p.kbs = kbs; p.split_stride = 1LL * p.M * p.N;
-  int rc = gemm_dispatch(dz_nhwc, Cout, x_nhwc, Cin, p, S(stream));
+  int rc = gemm_dispatch(dz, Cout, x, Cin, p, S(stream));
   if (rc) return rc;
   return splitk_reduce_dispatch(workspace, ks, 1LL * p.M * p.N, p.N, dw_taps, p.N, accumulate, S(stream));
+}
+
+int64_t lavt_conv3x3_wgrad_workspace_floats(int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+  int64_t need = 0;
+  conv_wgrad_impl(nullptr, nullptr, n_img, 0, H, W, Cin, Cout, 9, nullptr, 0, nullptr, 0, nullptr, &need);
+  return need;
+}
+int lavt_conv3x3_wgrad(const void* dz_nhwc, const void* x_nhwc, int32_t n_img, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                       float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream) {
+  return conv_wgrad_impl(dz_nhwc, x_nhwc, n_img, 0, H, W, Cin, Cout, 9, workspace, workspace_floats, dw_taps, accumulate, stream, nullptr);
+}
+int64_t lavt_conv3d_wgrad_workspace_floats(int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+  int64_t need = 0;
+  conv_wgrad_impl(nullptr, nullptr, n_clip * D, D, H, W, Cin, Cout, 27, nullptr, 0, nullptr, 0, nullptr, &need);
+  return need;
+}
+int lavt_conv3d_wgrad(const void* dz_ndhwc, const void* x_ndhwc, int32_t n_clip, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                      float* workspace, int64_t workspace_floats, float* dw_taps, int32_t accumulate, void* stream) {
+  LAVT_REQUIRE(D >= 1, "conv3d wgrad: D must be >= 1");
+  return conv_wgrad_impl(dz_ndhwc, x_ndhwc, n_clip * D, D, H, W, Cin, Cout, 27, workspace, workspace_floats, dw_taps, accumulate, stream, nullptr);
 }
 
 int lavt_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int32_t N, void* stream) {

@@ -227,19 +227,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
             }
           } else if (p.rowmap == ROWMAP_WGCONV) {
-            // conv weight gradient: k-block = one 64-pixel tile of one image; A = dz channels, B = x channels shifted by the tap
+            // conv weight gradient: k-block = one 64-pixel tile of one image / frame; A = dz channels, B = x channels shifted by the tap
             const int tw = kb % p.cTilesW;
             const int th = (kb / p.cTilesW) % p.cTilesH;
-            const int im = kb / (p.cTilesW * p.cTilesH);
+            int im = kb / (p.cTilesW * p.cTilesH);
             const int ph0 = th * p.cTH, pw0 = tw * p.cTW;
+            int fr = 0;
+            if (p.taps == 27) { fr = im % p.cD; im /= p.cD; }     // 3-D: im = clip, fr = frame
 #pragma unroll
-            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_4d(sa + j * 8192, &tmA, &full_bar[s], mt * GEMM_BM + j * 64, pw0, ph0, im);
+            for (int j = 0; j < GEMM_BM / 64; ++j) {
+              if (p.taps == 27) tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], mt * GEMM_BM + j * 64, pw0, ph0, fr, im);
+              else tma_load_4d(sa + j * 8192, &tmA, &full_bar[s], mt * GEMM_BM + j * 64, pw0, ph0, im);
+            }
 #pragma unroll
             for (int j = 0; j < GEMM_BN / 64; ++j) {
               const int col = n0 + j * 64;                       // column of C = tap * Cin + ci (Cin % 64 == 0: an atom never straddles taps)
               int tap = col / p.cCin, ci0 = col - tap * p.cCin;
-              if (tap >= 9) { tap = 8; ci0 = p.cCin; }           // past N: channel coordinate out of bounds -> zero fill
-              tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], ci0, pw0 + tap % 3 - 1, ph0 + tap / 3 - 1, im);
+              if (tap >= p.taps) { tap = p.taps - 1; ci0 = p.cCin; }   // past N: channel coordinate out of bounds -> zero fill
+              if (p.taps == 27) {
+                const int r9 = tap % 9;
+                tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], ci0, pw0 + r9 % 3 - 1, ph0 + r9 / 3 - 1, fr + tap / 9 - 1, im);
+              } else {
+                tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], ci0, pw0 + tap % 3 - 1, ph0 + tap / 3 - 1, im);
+              }
             }
             continue;
           } else if (p.mnmajor) {
@@ -581,16 +591,29 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     if (rc) return rc;
     m_tiles = n_img * p.cTilesH * p.cTilesW;
   } else if (p.rowmap == ROWMAP_WGCONV) {
-    LAVT_REQUIRE(p.mnmajor == 1 && p.cCin % 64 == 0 && p.cTH * p.cTW == 64 && p.N == 9 * p.cCin, "conv wgrad: bad configuration");
-    const int n_img = p.K / (p.cTilesH * p.cTilesW * 64);
-    uint64_t dimsA[4] = {(uint64_t)p.M, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
-    uint64_t sA[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH};
-    uint64_t dimsB[4] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
-    uint64_t sB[3] = {(uint64_t)ldb * 2, (uint64_t)ldb * 2 * p.cW, (uint64_t)ldb * 2 * p.cW * p.cH};
-    uint32_t box[4] = {64, (uint32_t)p.cTW, (uint32_t)p.cTH, 1};
-    int rc = make_tmap_bf16(&tmA, A, 4, dimsA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tmB, Bw, 4, dimsB, sB, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    LAVT_REQUIRE(p.mnmajor == 1 && p.cCin % 64 == 0 && p.cTH * p.cTW == 64 && (p.taps == 9 || p.taps == 27) && p.N == p.taps * p.cCin,
+                 "conv wgrad: bad configuration");
+    const int n_img = p.K / (p.cTilesH * p.cTilesW * 64);          // 2-D: images; 3-D: clips * frames
+    uint32_t box[5] = {64, (uint32_t)p.cTW, (uint32_t)p.cTH, 1, 1};
+    int rc;
+    if (p.taps == 27) {
+      LAVT_REQUIRE(p.cD >= 1 && n_img % p.cD == 0, "conv3d wgrad: %d frames do not split into clips of %d", n_img, p.cD);
+      uint64_t dimsA[5] = {(uint64_t)p.M, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)p.cD, (uint64_t)(n_img / p.cD)};
+      uint64_t sA[4] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH, (uint64_t)lda * 2 * p.cW * p.cH * p.cD};
+      uint64_t dimsB[5] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)p.cD, (uint64_t)(n_img / p.cD)};
+      uint64_t sB[4] = {(uint64_t)ldb * 2, (uint64_t)ldb * 2 * p.cW, (uint64_t)ldb * 2 * p.cW * p.cH, (uint64_t)ldb * 2 * p.cW * p.cH * p.cD};
+      rc = make_tmap_bf16(&tmA, A, 5, dimsA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tmap_bf16(&tmB, Bw, 5, dimsB, sB, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      uint64_t dimsA[4] = {(uint64_t)p.M, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
+      uint64_t sA[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * p.cW, (uint64_t)lda * 2 * p.cW * p.cH};
+      uint64_t dimsB[4] = {(uint64_t)p.cCin, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)n_img};
+      uint64_t sB[3] = {(uint64_t)ldb * 2, (uint64_t)ldb * 2 * p.cW, (uint64_t)ldb * 2 * p.cW * p.cH};
+      rc = make_tmap_bf16(&tmA, A, 4, dimsA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tmap_bf16(&tmB, Bw, 4, dimsB, sB, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
     m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   } else if (p.mnmajor) {

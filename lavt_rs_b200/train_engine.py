@@ -647,7 +647,12 @@ def conv3d_bwd(dy: torch.Tensor, x5: torch.Tensor, conv, grads: GradStore, ws: W
     Cout = conv.weight.shape[0]
     dev = dy.device
     npos = B * D * H * W
-    if conv.weight.requires_grad:
+    if conv.weight.requires_grad and Cin % 64 == 0:
+        # one launch over 5-D TMA boxes (64 channels x 64 pixels of one frame), taps = box offsets, padding = out-of-bounds fill
+        K.conv3d_wgrad(dy.view(B, D, H, W, Cout), x5, grads.conv_taps(conv.weight),
+                       lambda nfl: ws.get("bw_splitk", (nfl,), torch.float32, dev), accumulate=True)
+        _count(2)
+    elif conv.weight.requires_grad:
         Wp = _pad8(W + 2)
         Kp = B * (D + 2) * (H + 2) * Wp
         dz_t = ws.get("bw_dzT", (Cout, Kp), torch.bfloat16, dev)
