@@ -776,3 +776,31 @@ def test_version_ablation_training_step(version):
     got = {"backbone." + k: v for k, v in grads.named(bb).items()}
     got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
     check_direction(got, {k: v.grad for k, v in leaf.items() if v.grad is not None}, f"--version {version} training step")
+
+
+def test_conv_weight_gradient_tma():
+    """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
+    from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""
+    import torch.nn.functional as F
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(13)
+    for n, H, W, Cin, Cout in ((3, 12, 10, 512, 512), (2, 24, 24, 640, 512), (4, 7, 9, 1536, 512), (1, 5, 3, 64, 128)):
+        x = torch.randn(n, Cin, H, W, generator=g).to(torch.bfloat16)
+        dz = torch.randn(n, Cout, H, W, generator=g).to(torch.bfloat16)
+        w = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+        F.conv2d(x.float(), w, padding=1).backward(dz.float())
+        ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)
+        dw = torch.full((Cout, 9 * Cin), 0.25, device="cuda")
+        ws = torch.empty(K.conv3x3_wgrad_workspace_floats(n, H, W, Cin, Cout), device="cuda")
+        K.conv3x3_wgrad(dz.permute(0, 2, 3, 1).contiguous().cuda(), x.permute(0, 2, 3, 1).contiguous().cuda(), dw, ws, accumulate=True)
+        assert rel_l2(dw - 0.25, ref) < 1e-4, (n, H, W, Cin, Cout, rel_l2(dw - 0.25, ref))
+    for B, D, H, W, Cin, Cout in ((2, 4, 6, 5, 128, 128), (1, 3, 9, 10, 64, 256)):
+        x = torch.randn(B, Cin, D, H, W, generator=g).to(torch.bfloat16)
+        dz = torch.randn(B, Cout, D, H, W, generator=g).to(torch.bfloat16)
+        w = torch.zeros(Cout, Cin, 3, 3, 3, requires_grad=True)
+        F.conv3d(x.float(), w, padding=1).backward(dz.float())
+        ref = w.grad.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin)
+        dw = torch.zeros(Cout, 27 * Cin, device="cuda")
+        K.conv3d_wgrad(dz.permute(0, 2, 3, 4, 1).contiguous().cuda(), x.permute(0, 2, 3, 4, 1).contiguous().cuda(), dw,
+                       lambda nfl: torch.empty(nfl, device="cuda"), accumulate=True)
+        assert rel_l2(dw, ref) < 1e-4, (B, D, H, W, Cin, Cout, rel_l2(dw, ref))
