@@ -31,15 +31,34 @@ class GradStore:
     Some kernels accumulate in the layout of the engine's prepared operand rather than the parameter's; those buffers carry
     a function that maps them back to the parameter's shape when the gradients are handed over."""
 
-    def __init__(self):
+    def __init__(self, params=None):
+        """``params``: the parameters that will receive gradients.  Their buffers are then views of ONE zero-filled allocation
+        (one memset per step instead of ~450 tiny fill kernels: the ncu launch list of a step showed 1 354 FillFunctor launches)."""
         self._g: Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]] = {}
         self._alt: Dict[Tuple[int, str], Tuple[torch.nn.Parameter, torch.Tensor, object]] = {}
+        self._slots: Dict[int, Tuple[int, torch.nn.Parameter]] = {}
+        self._flat: Dict[torch.device, torch.Tensor] = {}
+        if params is not None:
+            sizes: Dict[torch.device, int] = {}
+            for p in params:
+                if not p.requires_grad or id(p) in self._slots or not p.is_cuda:
+                    continue
+                off = sizes.get(p.device, 0)
+                self._slots[id(p)] = (off, p)
+                sizes[p.device] = off + (p.numel() + 7) // 8 * 8          # 32-byte aligned slots (float4 / TMA friendly)
+            for dev, total in sizes.items():
+                self._flat[dev] = torch.zeros(total, device=dev, dtype=torch.float32)
 
     def of(self, param: torch.Tensor) -> torch.Tensor:
         """Accumulation buffer with the parameter's shape."""
         hit = self._g.get(id(param))
         if hit is None:
-            hit = (param, torch.zeros(param.shape, device=param.device, dtype=torch.float32))
+            slot = self._slots.get(id(param))
+            if slot is not None:
+                buf = self._flat[param.device][slot[0]:slot[0] + param.numel()].view(param.shape)
+            else:
+                buf = torch.zeros(param.shape, device=param.device, dtype=torch.float32)
+            hit = (param, buf)
             self._g[id(param)] = hit
         return hit[1]
 

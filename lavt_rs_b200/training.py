@@ -184,7 +184,7 @@ class SegmentFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        grads = T.GradStore()
+        grads = T.GradStore(ctx.model.parameters())
         dl = segment_backward(ctx.model, ctx.tape, dlogits.float(), grads)
         grads.finalize()
         ctx.tape = None

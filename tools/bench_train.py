@@ -94,7 +94,7 @@ def main():
         for prm in params:
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
         l_feats = text_fn(ids, m)
-        grads = T.GradStore()
+        grads = T.GradStore(params)
         reducer = TR.GradReducer(overlap=a.overlap_allreduce)
         loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
         grads.finalize()
