@@ -37,6 +37,8 @@ def main():
                                                             "poly LR) in the timed step")
     p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
     p.add_argument("--overlap-allreduce", action="store_true", help="launch each stage's gradient all-reduce under the rest of the backward")
+    p.add_argument("--graph", action="store_true", help="capture forward + loss + backward of the hot path (everything after the text encoder) "
+                                                        "in one CUDA graph (1 GPU only: SyncBN / gradient collectives stay eager)")
     p.add_argument("--eager-text", action="store_true", help="run the text encoder eagerly instead of as CUDA graphs")
     p.add_argument("--phases", action="store_true", help="print CUDA-event times of the phases of one step to stderr")
     p.add_argument("--by-tag", action="store_true", help="print the CUDA-event time of every GEMM / attention shape of one step to stderr")
@@ -89,7 +91,53 @@ def main():
     if not a.eager_text and not a.frozen_text:
         text_fn = TR.GraphedTextEncoder(text, batches[0][1], batches[0][2])
 
+    graph_state = {}
+
+    def build_graph():
+        """Static-input CUDA graph of segment_forward_backward: ~1000 short launches replayed without Python / launch gaps."""
+        x0, ids0, m0, tgt0 = batches[0]
+        gs = graph_state
+        gs["x"], gs["m"], gs["tgt"] = x0.clone(), m0.clone(), tgt0.clone()
+        gs["l"] = torch.zeros(x0.shape[0], 768, ids0.shape[1], device=dev)
+        seg_params = [prm for prm in list(model.backbone.parameters()) + list(model.classifier.parameters()) if prm.requires_grad]
+        for prm in seg_params:
+            prm.grad = None
+        for mod in model.modules():           # bf16 weight copies must be (re)built INSIDE the capture so that every replay refreshes them
+            if hasattr(mod, "prepared"):
+                mod.prepared.clear()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):         # one eager pass on the capture stream: workspaces, function attributes
+            TR.segment_forward_backward(model, gs["x"], gs["l"], gs["m"], gs["tgt"], T.GradStore(seg_params))
+        torch.cuda.current_stream().wait_stream(side)
+        for mod in model.modules():
+            if hasattr(mod, "prepared"):
+                mod.prepared.clear()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            grads = T.GradStore(seg_params)
+            gs["loss"], gs["dl"] = TR.segment_forward_backward(model, gs["x"], gs["l"], gs["m"], gs["tgt"], grads)
+            grads.finalize()                  # param.grad = views of the graph-owned flat buffer (zeroed by the captured memset)
+        gs["graph"] = g
+
+    def step_graph(i):
+        x, ids, m, tgt = batches[i % 2]
+        gs = graph_state
+        for prm in text.parameters():
+            prm.grad = None
+        l_feats = text_fn(ids, m)
+        gs["x"].copy_(x); gs["m"].copy_(m); gs["tgt"].copy_(tgt); gs["l"].copy_(l_feats.detach())
+        gs["graph"].replay()
+        if not a.frozen_text:
+            l_feats.backward(gs["dl"])
+        if opt is not None:
+            opt.step()
+            sched.step()
+        state["loss"] = gs["loss"]
+
     def step(i):
+        if graph_state.get("graph") is not None and not K.TIMER.enabled:
+            return step_graph(i)
         x, ids, m, tgt = batches[i % 2]
         for prm in params:
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
@@ -171,6 +219,10 @@ def main():
     step(0)
     torch.cuda.synchronize()
     launches = E.LAUNCHES
+    if a.graph:
+        if world > 1:
+            raise SystemExit("--graph is a 1-GPU option")
+        build_graph()
     peak_mem = torch.cuda.max_memory_allocated(dev)
     clocks = B0.ClockSampler(local)
     if rank == 0:
@@ -213,7 +265,7 @@ def main():
                    "clips_per_gpu_per_step": Bc, "global_clips_per_step": total,
                    "parallelism": f"data-parallel x{world}" + ((", NCCL gradient all-reduce (" + ("per stage, under the backward" if a.overlap_allreduce else "after the backward") + ") + SyncBN statistics") if world > 1 else ""),
                    "text_encoder": "frozen" if a.frozen_text else ("transformers BertModel under autograd (fp32)" + ("" if a.eager_text else ", forward and backward replayed as CUDA graphs")),
-                   "l2": "two rotating batches; saved activations (> 10 GB) exceed the 126 MB L2", "flops_per_clip": flops_clip},
+                   "cuda_graph": bool(a.graph), "l2": "two rotating batches; saved activations (> 10 GB) exceed the 126 MB L2", "flops_per_clip": flops_clip},
         "clocks": clk, "loss": float(state["loss"].item()), "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
         "peak_memory_bytes": peak_mem,
         "roofline": {"kernel": "gemm_bf16_tc_kernel (forward GEMMs / convs, input-gradient GEMMs / convs, split-K weight-gradient GEMMs)",
