@@ -335,6 +335,15 @@ int lavt_normalize_u8(const uint8_t* frames_hwc, float* out_nchw, int32_t n_img,
 int lavt_logits_to_mask(const float* logits_nchw, uint8_t* mask, int32_t n_img, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
                         void* stream);
 
+/* ---- GA-CD fusion (lib/bcam.py:78-127; the --gacd ablation of the 2-D image backbone, lib/backbone.py:578-582) ----
+ * Everything after mm_gen: xm fp32 [B,n,C] = relu(Linear(ls * x)), lang_stats = the (-ls, 1) block written by lavt_lang_project.
+ * One query vector per image, so the collection / diffusion attentions reduce to per-token dot products with u_c = Wc^T q, u_d = Wd^T q,
+ * a softmax over the tokens and out[n] = xm[n] + sigmoid(s_d[n]) (Wv sum_n softmax(s_c)[n] xm[n] + bv).  Weights fp32 [C,C] / [C]. */
+int64_t lavt_gacd_workspace_floats(int32_t B, int64_t n, int32_t C);
+int lavt_gacd_fuse(const float* xm, const float* lang_stats, const float* wq, const float* bq, const float* wc, const float* bc,
+                   const float* wd, const float* bd, const float* wv, const float* bv, float* workspace, float* out_f32,
+                   void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

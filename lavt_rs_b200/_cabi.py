@@ -130,10 +130,11 @@ SIGNATURES = {
     "lavt_cross_entropy": [_vp, _vp, _f32, _f32, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp],
     "lavt_normalize_u8": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "lavt_logits_to_mask": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_gacd_fuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
-           "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
+           "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
 
@@ -149,6 +150,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_conv3x3_wgrad_workspace_floats.restype = C.c_int64
     l.lavt_conv3d_wgrad_workspace_floats.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32]
     l.lavt_conv3d_wgrad_workspace_floats.restype = C.c_int64
+    l.lavt_gacd_workspace_floats.argtypes = [_i32, _i64, _i32]
+    l.lavt_gacd_workspace_floats.restype = C.c_int64
     l.lavt_adamw_chunk_elems.argtypes = []
     l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
@@ -849,3 +852,14 @@ def logits_to_mask(logits: torch.Tensor, size) -> torch.Tensor:
     check(lib().lavt_logits_to_mask(_c(logits, torch.float32, "logits").data_ptr(), out.data_ptr(), n, H, W, oh, ow, stream_ptr()),
           "lavt_logits_to_mask")
     return out
+
+
+def gacd_fuse(xm, lang_stats, wq, bq, wc, bc, wd, bd, wv, bv, ws_get, out_f32=None, out_bf16=None) -> None:
+    """GA-CD after mm_gen: xm fp32 [B,n,C]; weights fp32; ``ws_get(n_floats)`` returns an fp32 workspace."""
+    B, n, Cn = xm.shape
+    work = ws_get(int(lib().lavt_gacd_workspace_floats(B, n, Cn)))
+    for t, nm in ((xm, "xm"), (lang_stats, "lang_stats"), (wq, "wq"), (bq, "bq"), (wc, "wc"), (bc, "bc"), (wd, "wd"), (bd, "bd"), (wv, "wv"), (bv, "bv")):
+        _c(t, torch.float32, nm)
+    check(lib().lavt_gacd_fuse(xm.data_ptr(), lang_stats.data_ptr(), wq.data_ptr(), bq.data_ptr(), wc.data_ptr(), bc.data_ptr(), wd.data_ptr(),
+                               bd.data_ptr(), wv.data_ptr(), bv.data_ptr(), _c(work, torch.float32, "workspace").data_ptr(), ptr(out_f32),
+                               ptr(out_bf16), B, n, Cn, stream_ptr()), "lavt_gacd_fuse")

@@ -151,6 +151,8 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
               ws: Workspace, gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x fp32 [B*n, C] (updated in place with the gated residual), xb = bf16 copy of x, l fp32 [B,768,Nl],
     mask fp32 [B,Nl].  Returns r (= x_residual) as fp32 [B*n, C]."""
+    if getattr(fusion, "kind", "pwam") == "gacd":
+        return gacd_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
     N_, C = x.shape
     n = N_ // B
     dev = x.device
@@ -220,6 +222,41 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
         g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
         g1 = vis.view(N_, C)  # vis is dead
+        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
+        if gate_act != "tanh":
+            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+        _count(2)
+    return r32
+
+
+def gacd_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace,
+              gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GA-CD fusion (reference lib/bcam.py:78-127, --gacd) + LanguageGate; same contract as ``pwam_gate``."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
+    pr = fusion.lang_gen.project
+    K.lang_project(l, mask, _f32(pr[0].weight), _f32(pr[0].bias), _f32(pr[2].weight), _f32(pr[2].bias), stats)      # (-ls, 1)
+    zeros = pw.get("zeros_%d_%d" % (B, n), [], lambda: torch.zeros(B, n, C, device=dev, dtype=torch.float32))
+    a = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
+    K.pwam_mul_norm(xb.view(B, n, C), zeros, stats, a)                                        # ls * x
+    xm = ws.get("pw_q", (B, n, C), torch.float32, dev)
+    mm = fusion.mm_gen[0]
+    K.gemm_bf16(a.view(N_, C), pw.get("mm_w", [mm.weight], lambda: _bf16(mm.weight)), bias=mm.bias.detach(), act=K.ACT_RELU,
+                out_f32=xm.view(N_, C))
+    r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+    rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+    K.gacd_fuse(xm, stats, _f32(fusion.query.weight), _f32(fusion.query.bias), _f32(fusion.key_c.weight), _f32(fusion.key_c.bias),
+                _f32(fusion.key_d.weight), _f32(fusion.key_d.bias), _f32(fusion.value.weight), _f32(fusion.value.bias),
+                lambda nfl: ws.get("gacd_ws", (nfl,), torch.float32, dev), out_f32=r32, out_bf16=rb)
+    _count(7)
+    if res_gate is not None:
+        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1 = a.view(N_, C)           # the ls * x operand is dead
         K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
         if gate_act != "tanh":
             raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")

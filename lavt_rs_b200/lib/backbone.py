@@ -14,7 +14,7 @@ import torch.nn as nn
 from .. import engine as E
 from . import video_swin_transformer as V
 
-_REJECTED = ("bcam", "gacd", "efn")
+_REJECTED = ("bcam", "efn")
 
 
 def _check_2d_args(args) -> None:
@@ -28,6 +28,32 @@ def _check_2d_args(args) -> None:
         raise NotImplementedError("only the tanh LanguageGate is implemented on the B200 path")
     if getattr(args, "att_norm_layer_type", "IN") != "IN":
         raise NotImplementedError("only InstanceNorm PWAM attention norms are implemented on the B200 path")
+
+
+class GACD(nn.Module):
+    """GA-CD fusion parameters (reference lib/bcam.py:78-127; --gacd).  forward(x (B,n,C), l (B,768,Nl), l_mask (B,Nl,1)) -> (B,n,C)."""
+    kind = "gacd"
+
+    def __init__(self, dim, v_in_channels, l_in_channels, num_heads=0):
+        super().__init__()
+        if dim != v_in_channels:
+            raise NotImplementedError("GA-CD with differing channel widths is not supported on the B200 path")
+        self.k, self.dim = num_heads, dim
+        self.lang_gen = V.LangProject(l_in_channels, v_in_channels)
+        self.mm_gen = nn.Sequential(nn.Linear(v_in_channels, dim), nn.ReLU())
+        self.query = nn.Linear(dim, dim)
+        self.key_c = nn.Linear(v_in_channels, dim)
+        self.key_d = nn.Linear(v_in_channels, dim)
+        self.value = nn.Linear(v_in_channels, dim)
+        self.prepared = E.PreparedWeights()
+
+    def forward(self, x: torch.Tensor, l: torch.Tensor, l_mask: torch.Tensor) -> torch.Tensor:
+        E.require_cuda(x, "x")
+        B, n, C = x.shape
+        xf = x.detach().float().reshape(B * n, C).contiguous()
+        r = torch.empty(B * n, C, device=x.device, dtype=torch.float32)
+        E.gacd_gate(xf, xf.to(torch.bfloat16), self, None, V._lang(l), V._mask(l_mask), B, E.workspace(x.device), r_f32=r)
+        return r.view(B, n, C)
 
 
 class PatchEmbed(nn.Module):
@@ -63,6 +89,8 @@ class MMBasicLayer(V.MMBasicLayer):
                          mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
                          drop_path=drop_path, norm_layer=norm_layer, downsample=downsample, use_checkpoint=False,
                          num_heads_fusion=num_heads_fusion, fusion_drop=fusion_drop, args=args)
+        if getattr(args, "gacd", False):      # reference lib/backbone.py:578-582
+            self.fusion = GACD(dim, dim, 768, num_heads=num_heads_fusion)
         for blk in self.blocks:
             blk.clamp_window = False          # the 2-D reference always pads to a full window and always shifts
         self.use_checkpoint = use_checkpoint

@@ -41,6 +41,7 @@ class OracleConfig:
     video: bool = True
     gate_act: str = "tanh"
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
+    gacd: bool = False                            # --gacd (2-D image backbone): GA-CD fusion of lib/bcam.py:78-127 instead of PWAM
     fuse_simple: bool = False                     # --fuse simple: LangProject (mean-pooled sentence vector) instead of pixel-word attention
     version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
     sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
@@ -207,6 +208,23 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     return r
 
 
+def gacd(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
+    """GA-CD fusion (lib/bcam.py:78-127, the --gacd ablation of the 2-D backbone): sentence vector ls = LangProject(l); xm = relu(Linear(ls * x));
+    one query vector per image q = Linear(ls); collection A_c = softmax_n(q . key_c(xm) dim^-0.5), diffusion A_d = sigmoid(q . key_d(xm) dim^-0.5);
+    out = xm + A_d * (A_c @ value(xm)).  x (B,n,C); l (B,768,Nl); l_mask (B,Nl,1) -> (B,n,C).  ``pre`` = 'backbone.layers.{s}.fusion.'"""
+    C = x.shape[-1]
+
+    def lin(t, name):
+        return t @ sd[pre + name + ".weight"].t() + sd[pre + name + ".bias"]
+    ls = lang_project(l, l_mask, sd, pre + "lang_gen.")                # (B, 1, C)
+    xm = F.relu(lin(ls * x, "mm_gen.0"))                                # (B, n, C)
+    q = lin(ls, "query")                                                # (B, 1, C)
+    a_c = (q @ lin(xm, "key_c").transpose(1, 2) * C ** -0.5).softmax(-1)           # (B, 1, n)
+    a_d = torch.sigmoid(q @ lin(xm, "key_d").transpose(1, 2) * C ** -0.5)          # (B, 1, n)
+    f_col = a_c @ lin(xm, "value")                                      # (B, 1, C)
+    return xm + a_d.transpose(1, 2) @ f_col
+
+
 # A7: SepTPWAM under the README video flags (lib/video_swin_transformer.py:1300-1584, forward :1480-1584):
 # every projection of PWAM becomes the SUM of a temporal Conv3d(3,3,3) branch and a spatial Conv3d(1,1,1) branch;
 # the query / W branches are each InstanceNorm3d-normalised BEFORE the sum, the vis / project_mm branches GELU'd before it.
@@ -303,7 +321,9 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             if capture is not None:
                 capture[f"s{s}b{i}"] = x
         B, D, H, W, C = x.shape
-        if cfg.sep_t_pwam:
+        if cfg.gacd:
+            r = gacd(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
+        elif cfg.sep_t_pwam:
             r = sep_t_pwam(x, l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         else:
             r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
@@ -437,6 +457,11 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
             for name in ("f_key.0", "f_value.0"):
                 w, b = conv_default(C, l_in, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        elif cfg.gacd:
+            for name, cin in (("lang_gen.project.0", l_in), ("lang_gen.project.2", C), ("mm_gen.0", C), ("query", C), ("key_c", C), ("key_d", C),
+                              ("value", C)):
+                w, b = conv_default(C, cin)
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
         elif cfg.fuse_simple:
             for name in ("vis_project.0", "project_mm.0"):

@@ -141,12 +141,12 @@ def build_reference_backbone_small(embed_dim=128, depths=(2, 2, 2, 2), num_heads
 
 
 def build_reference_image_backbone_small(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32), window=7,
-                                         mha=(1, 1, 1, 1), seed=0):
+                                         mha=(1, 1, 1, 1), seed=0, extra=()):
     """A shallow reference 2-D (image) backbone + decoder: lib/backbone.py MultiModalSwinTransformer."""
     install_shims()
     from lib.backbone import MultiModalSwinTransformer
     from lib.mask_predictor import SimpleDecoding
-    args = reference_args(["--model", "lavt_one"])
+    args = reference_args(["--model", "lavt_one", *extra])
     torch.manual_seed(seed)
     bb = MultiModalSwinTransformer(embed_dim=embed_dim, depths=list(depths), num_heads=list(num_heads), window_size=window,
                                    ape=False, drop_path_rate=0.0, patch_norm=True, out_indices=(0, 1, 2, 3),

@@ -389,3 +389,35 @@ def test_fuse_simple_end_to_end():
     for i in range(4):
         assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_gacd_image_model_end_to_end():
+    """--gacd (GA-CD fusion, reference lib/bcam.py:78-127) in the 2-D image backbone: stage outputs + logits vs the oracle."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, gacd=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=default_args(["--gacd"]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(2, 1, 96, 160, Nl=20, video=False)
+    cap = {}
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        got = model(x.cuda(), l.cuda(), m.cuda())
+        # the module on its own, reference signature
+        C = 256
+        xs = torch.randn(2, 777, C, generator=torch.Generator().manual_seed(4))
+        r_ref = O.gacd(xs, l, m.unsqueeze(-1), sd, "backbone.layers.1.fusion.")
+        r_got = bb.layers[1].fusion(xs.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+    assert rel_l2(r_got, r_ref) < 1.5e-2, rel_l2(r_got, r_ref)
+    for i in range(4):
+        assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)

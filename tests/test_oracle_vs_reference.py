@@ -215,3 +215,19 @@ def test_fuse_simple_matches_reference():
         got = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
     for i, (a, b) in enumerate(zip(got, ref)):
         assert (a - b).abs().max().item() < 2e-4, i
+
+
+def test_gacd_image_backbone_matches_reference():
+    """--gacd: GA-CD fusion (lib/bcam.py:78-127) in the 2-D image backbone (lib/backbone.py:578-582)."""
+    bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=7, depths=(2, 2, 2, 2), extra=("--gacd",))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    assert "backbone.layers.0.fusion.key_d.weight" in sd
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, gacd=True)
+    assert {k for k in O.random_state_dict(cfg) if "fusion" in k} == {k for k in sd if "fusion" in k}
+    x, l, m = O.synthetic_inputs(2, 1, 64, 80, Nl=11, video=False)
+    with torch.no_grad():
+        ref = bb(x, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 2e-4, i
