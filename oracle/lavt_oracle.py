@@ -41,6 +41,7 @@ class OracleConfig:
     video: bool = True
     gate_act: str = "tanh"
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
+    bcam: bool = False                            # --bcam (2-D image backbone, 480 x 480 inputs only): BCAM fusion of lib/bcam.py:8-75
     gacd: bool = False                            # --gacd (2-D image backbone): GA-CD fusion of lib/bcam.py:78-127 instead of PWAM
     fuse_simple: bool = False                     # --fuse simple: LangProject (mean-pooled sentence vector) instead of pixel-word attention
     version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
@@ -208,6 +209,23 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     return r
 
 
+def bcam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
+    """BCAM fusion (lib/bcam.py:8-75, the --bcam ablation of the 2-D backbone; from BRINet): vision-guided linguistic attention (pixel-word
+    softmax without scaling, keys = values = reduced word features) followed by a language-guided visual attention whose n x n map comes
+    from a Linear(dim -> hw) on tanh features -- so the module only exists for n = hw (480 x 480 inputs).  x (B,n,C) -> (B,n,C)."""
+    def lin(t, name):
+        return t @ sd[pre + name + ".weight"].t() + sd[pre + name + ".bias"]
+    lr = lin(l.transpose(1, 2), "lang_reduce")                           # (B, Nl, C)
+    m = l_mask.to(x.dtype).transpose(1, 2)                               # (B, 1, Nl)
+    sim = (F.relu(lin(x, "vis_1.0")) @ lr.transpose(1, 2) + (1e4 * m - 1e4)).softmax(-1)
+    out = sim @ lr                                                       # (B, n, C)
+    a = torch.tanh(lin(out, "out_1") + lin(F.relu(lin(x, "vis_2.0")), "vis_2_2"))
+    rel = lin(a, "a_proj").softmax(-1)                                   # (B, n, hw = n)
+    out2 = rel @ F.relu(lin(x, "vis_3.0"))
+    out3 = F.relu(lin(torch.cat([out2, out], -1), "out3_proj.0"))
+    return out3 + F.relu(lin(x, "vis_4.0"))
+
+
 def gacd(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
     """GA-CD fusion (lib/bcam.py:78-127, the --gacd ablation of the 2-D backbone): sentence vector ls = LangProject(l); xm = relu(Linear(ls * x));
     one query vector per image q = Linear(ls); collection A_c = softmax_n(q . key_c(xm) dim^-0.5), diffusion A_d = sigmoid(q . key_d(xm) dim^-0.5);
@@ -321,7 +339,9 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             if capture is not None:
                 capture[f"s{s}b{i}"] = x
         B, D, H, W, C = x.shape
-        if cfg.gacd:
+        if cfg.bcam:
+            r = bcam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
+        elif cfg.gacd:
             r = gacd(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
         elif cfg.sep_t_pwam:
             r = sep_t_pwam(x, l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
@@ -457,6 +477,12 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
             for name in ("f_key.0", "f_value.0"):
                 w, b = conv_default(C, l_in, 1)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        elif cfg.bcam:
+            hw = {128: 120 * 120, 256: 60 * 60, 512: 30 * 30, 1024: 15 * 15}[C]          # lib/bcam.py:12-19
+            for name, cout, cin in (("lang_reduce", C, l_in), ("vis_1.0", C, C), ("vis_2.0", C, C), ("vis_3.0", C, C), ("vis_4.0", C, C),
+                                    ("out_1", C, C), ("vis_2_2", C, C), ("a_proj", hw, C), ("out3_proj.0", C, 2 * C)):
+                w, b = conv_default(cout, cin)
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
         elif cfg.gacd:
             for name, cin in (("lang_gen.project.0", l_in), ("lang_gen.project.2", C), ("mm_gen.0", C), ("query", C), ("key_c", C), ("key_d", C),

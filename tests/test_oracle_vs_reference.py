@@ -231,3 +231,18 @@ def test_gacd_image_backbone_matches_reference():
         got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
     for i, (a, b) in enumerate(zip(got, ref)):
         assert a.shape == b.shape and (a - b).abs().max().item() < 2e-4, i
+
+
+def test_bcam_image_backbone_matches_reference():
+    """--bcam: BCAM fusion (lib/bcam.py:8-75) in the 2-D image backbone; its Linear(dim -> hw) pins the input to 480 x 480."""
+    bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=7, depths=(2, 2, 2, 2), extra=("--bcam",))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, bcam=True)
+    assert {k for k in O.random_state_dict(cfg) if "fusion" in k} == {k for k in sd if "fusion" in k}
+    x, l, m = O.synthetic_inputs(1, 1, 480, 480, Nl=9, video=False)
+    with torch.no_grad():
+        ref = bb(x, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 5e-4, (i, (a - b).abs().max().item())
