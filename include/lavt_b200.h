@@ -344,6 +344,20 @@ int lavt_gacd_fuse(const float* xm, const float* lang_stats, const float* wq, co
                    const float* wd, const float* bd, const float* wv, const float* bv, float* workspace, float* out_f32,
                    void* out_bf16, int32_t B, int64_t n, int32_t C, void* stream);
 
+/* ---- BCAM fusion (lib/bcam.py:8-75; the --bcam ablation of the 2-D image backbone, lib/backbone.py:573-577) ----
+ * All contractions of the module are lavt_gemm_bf16 calls; these are the kernels between them.
+ * lavt_bcam_words: lr = lang_reduce(l^T) (lib/bcam.py:47): l fp32 [B,Lin,Nl], w fp32 [C,Lin] -> lr bf16 [B,Nlp,C] (rows >= Nl zero) and
+ *   its transpose lrT bf16 [B,C,Nlp] (the K-major operands of sim = q lr^T and out = sim lr, :52-56).
+ * lavt_bcam_softmax_rows: p[r, 0:cols] = softmax(s[r, 0:cols] + (1e4 mask[r / rows_per_mask, :] - 1e4)) as bf16, p[r, cols:ldp] = 0
+ *   (mask may be NULL): the word softmax (:54-55) and the hw x hw relation map (:62); cols <= 16384.
+ * lavt_bcam_transpose_pad: in bf16 [B*n, ldi] (C channels) -> out bf16 [B, C, ldo], columns n..ldo zero: query3 as the K-major
+ *   operand of out2 = rel_map query3 (:63-64). */
+int lavt_bcam_words(const float* l, const float* w, const float* bias, void* lr_bf16, void* lrT_bf16, int32_t B, int32_t Nl, int32_t Nlp,
+                    int32_t Lin, int32_t C, void* stream);
+int lavt_bcam_softmax_rows(const float* s, int64_t lds, const float* mask, int64_t rows_per_mask, void* p_bf16, int64_t ldp, int64_t rows,
+                           int32_t cols, void* stream);
+int lavt_bcam_transpose_pad(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t B, int64_t n, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

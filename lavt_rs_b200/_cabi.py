@@ -132,6 +132,9 @@ SIGNATURES = {
     "lavt_logits_to_mask": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_gacd_fuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
+    "lavt_bcam_words": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_bcam_softmax_rows": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp],
+    "lavt_bcam_transpose_pad": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
            "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
@@ -863,3 +866,40 @@ def gacd_fuse(xm, lang_stats, wq, bq, wc, bc, wd, bd, wv, bv, ws_get, out_f32=No
     check(lib().lavt_gacd_fuse(xm.data_ptr(), lang_stats.data_ptr(), wq.data_ptr(), bq.data_ptr(), wc.data_ptr(), bc.data_ptr(), wd.data_ptr(),
                                bd.data_ptr(), wv.data_ptr(), bv.data_ptr(), _c(work, torch.float32, "workspace").data_ptr(), ptr(out_f32),
                                ptr(out_bf16), B, n, Cn, stream_ptr()), "lavt_gacd_fuse")
+
+
+def bcam_words(l: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, lr: torch.Tensor, lrT: torch.Tensor) -> None:
+    """lr = lang_reduce(l^T) (reference lib/bcam.py:47): l fp32 [B,Lin,Nl], w fp32 [C,Lin] -> lr bf16 [B,Nlp,C] (pad rows zero), lrT bf16 [B,C,Nlp]."""
+    B, Lin, Nl = l.shape
+    _, Nlp, Cn = lr.shape
+    if tuple(lrT.shape) != (B, Cn, Nlp) or tuple(w.shape) != (Cn, Lin):
+        raise LavtError("bcam_words: shape mismatch")
+    check(lib().lavt_bcam_words(_c(l, torch.float32, "l").data_ptr(), _c(w, torch.float32, "w").data_ptr(), _c(bias, torch.float32, "bias").data_ptr(),
+                                _c(lr, torch.bfloat16, "lr").data_ptr(), _c(lrT, torch.bfloat16, "lrT").data_ptr(), B, Nl, Nlp, Lin, Cn, stream_ptr()),
+          "lavt_bcam_words")
+
+
+def bcam_softmax_rows(s: torch.Tensor, cols: int, p: torch.Tensor, mask: Optional[torch.Tensor] = None, rows_per_mask: int = 0) -> None:
+    """p[r, :cols] = softmax(s[r, :cols] + (1e4 mask - 1e4)) in bf16, p[r, cols:] = 0; s fp32 [rows, lds], p bf16 [rows, ldp], mask fp32 [*, cols]."""
+    _req(s, torch.float32, "s")
+    _req(p, torch.bfloat16, "p")
+    rows = s.shape[0]
+    if p.shape[0] != rows or s.stride(1) != 1 or p.stride(1) != 1 or s.shape[1] < cols or p.shape[1] < cols:
+        raise LavtError("bcam_softmax_rows: shape mismatch")
+    if mask is not None:
+        _c(mask, torch.float32, "mask")
+        if mask.shape[-1] != cols or rows_per_mask <= 0 or mask.numel() // cols * rows_per_mask < rows:
+            raise LavtError("bcam_softmax_rows: mask shape mismatch")
+    check(lib().lavt_bcam_softmax_rows(s.data_ptr(), s.stride(0), ptr(mask), int(rows_per_mask), p.data_ptr(), p.stride(0), rows, int(cols),
+                                       stream_ptr()), "lavt_bcam_softmax_rows")
+
+
+def bcam_transpose_pad(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x bf16 [B*n, C] (row pitch x.stride(0)) -> out bf16 [B, C, ldo >= n], columns n.. zero."""
+    _req(x, torch.bfloat16, "x")
+    B, Cn, ldo = out.shape
+    n = x.shape[0] // B
+    if x.shape[0] != B * n or x.shape[1] != Cn or x.stride(1) != 1 or ldo < n:
+        raise LavtError("bcam_transpose_pad: shape mismatch")
+    check(lib().lavt_bcam_transpose_pad(x.data_ptr(), x.stride(0), _c(out, torch.bfloat16, "out").data_ptr(), ldo, B, n, Cn, stream_ptr()),
+          "lavt_bcam_transpose_pad")

@@ -28,7 +28,7 @@ _STRUCTURE_FLAGS = [
     ("--att_norm_layer_type", str, "IN", "PWAM attention norm (2-D backbone)"),
     ("--hs", "store_true", False, "stage outputs = gated features E_i instead of the PWAM residuals"),
     ("--gacd", "store_true", False, "2-D image backbone: GA-CD fusion (lib/bcam.py) instead of PWAM"),
-    ("--bcam", "store_true", False, "2-D image backbone: BCAM fusion (lib/bcam.py) -- rejected at build time (not implemented)"),
+    ("--bcam", "store_true", False, "2-D image backbone: BCAM fusion (lib/bcam.py) instead of PWAM; 480 x 480 inputs only, inference"),
     ("--efn", "store_true", False, "2-D image backbone: EFN fusion (lib/bcam.py) -- rejected at build time (not implemented)"),
     ("--sep_t_pwam", "store_true", False, "SepTPWAM fusion: temporal Conv3d + spatial Conv3d branches, summed"),
     ("--conv3d_kernel_size_t", str, "3-1-1", "temporal-branch Conv3d kernel (B200 path: 3-3-3)"),

@@ -153,6 +153,8 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     mask fp32 [B,Nl].  Returns r (= x_residual) as fp32 [B*n, C]."""
     if getattr(fusion, "kind", "pwam") == "gacd":
         return gacd_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
+    if getattr(fusion, "kind", "pwam") == "bcam":
+        return bcam_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
     N_, C = x.shape
     n = N_ // B
     dev = x.device
@@ -261,6 +263,84 @@ def gacd_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         if gate_act != "tanh":
             raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
         K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+        _count(2)
+    return r32
+
+
+def bcam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace,
+              gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BCAM fusion (reference lib/bcam.py:43-75, --bcam) + LanguageGate; same contract as ``pwam_gate``.  Eleven tcgen05 GEMMs with
+    the three ``csrc/bcam_kernels.cu`` kernels between them; sums of two Linear layers run as one GEMM over row-concatenated operands
+    (one [n, 3C] buffer holds out2 | out | query2, so cat[out2, out] and [out | query2] are column windows of it, never copies).
+    The hw x hw relation map (:61-62) is materialised once as fp32 logits and once as bf16 probabilities (1.2 GB at 120 x 120)."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    if n != fusion.hw:
+        raise K.LavtError(f"BCAM: a_proj maps to {fusion.hw} positions but the feature map has {n} (the reference pins --bcam to 480 x 480 inputs)")
+    pw = fusion.prepared
+    Nl = l.shape[-1]
+    Nlp = (Nl + 31) // 32 * 32           # N granule of the sim GEMM (also a K granule of the out GEMM)
+    hwp = (n + 31) // 32 * 32            # N granule of a_proj
+    hw8 = (n + 7) // 8 * 8               # K granule of rel_map @ query3
+
+    def wb(name, lin):
+        return pw.get(name, [lin.weight], lambda: _bf16(lin.weight))
+
+    def b_(lin):
+        return lin.bias.detach()
+
+    lr = ws.get("bc_lr", (B, Nlp, C), torch.bfloat16, dev)
+    lrT = ws.get("bc_lrT", (B, C, Nlp), torch.bfloat16, dev)
+    K.bcam_words(l, _f32(fusion.lang_reduce.weight), _f32(fusion.lang_reduce.bias), lr, lrT)
+    # VLAM (:51-56): sim = softmax(relu(vis_1 x) lr^T + mask), out = sim lr
+    q = ws.get("pw_vis", (N_, C), torch.bfloat16, dev)
+    K.gemm_bf16(xb, wb("v1_w", fusion.vis_1[0]), bias=b_(fusion.vis_1[0]), act=K.ACT_RELU, out_bf16=q)
+    sim = ws.get("bc_sim", (N_, Nlp), torch.float32, dev)
+    for b in range(B):
+        K.gemm_bf16(q[b * n:(b + 1) * n], lr[b], out_f32=sim[b * n:(b + 1) * n])
+    simp = ws.get("bc_simp", (N_, Nlp), torch.bfloat16, dev)
+    K.bcam_softmax_rows(sim, Nl, simp, mask=mask, rows_per_mask=n)
+    cat = ws.get("bc_cat", (N_, 3 * C), torch.bfloat16, dev)        # out2 | out | query2
+    for b in range(B):
+        K.gemm_bf16(simp[b * n:(b + 1) * n], lrT[b], out_bf16=cat[b * n:(b + 1) * n, C:2 * C])
+    # LVAM (:59-64): A = tanh(out_1(out) + vis_2_2(relu(vis_2 x))); rel_map = softmax(a_proj(A)); out2 = rel_map relu(vis_3 x)
+    K.gemm_bf16(xb, wb("v2_w", fusion.vis_2[0]), bias=b_(fusion.vis_2[0]), act=K.ACT_RELU, out_bf16=cat[:, 2 * C:])
+    w_a = pw.get("a_w", [fusion.out_1.weight, fusion.vis_2_2.weight], lambda: _bf16(torch.cat([fusion.out_1.weight, fusion.vis_2_2.weight], 1)))
+    b_a = pw.get("a_b", [fusion.out_1.bias, fusion.vis_2_2.bias], lambda: _f32(fusion.out_1.bias + fusion.vis_2_2.bias))
+    a = ws.get("pw_o", (N_, C), torch.bfloat16, dev)
+    K.gemm_bf16(cat[:, C:], w_a, bias=b_a, act=K.ACT_TANH, out_bf16=a)
+
+    def _aproj():
+        w = torch.zeros(hwp, C, device=dev, dtype=torch.bfloat16)
+        w[:n] = fusion.a_proj.weight.detach()
+        bb = torch.zeros(hwp, device=dev, dtype=torch.float32)
+        bb[:n] = fusion.a_proj.bias.detach()
+        return w, bb
+    ap_w, ap_b = pw.get("ap", [fusion.a_proj.weight, fusion.a_proj.bias], _aproj)
+    logits = ws.get("bc_logits", (N_, hwp), torch.float32, dev)
+    K.gemm_bf16(a, ap_w, bias=ap_b, out_f32=logits)
+    rel = ws.get("bc_rel", (N_, hwp), torch.bfloat16, dev)
+    K.bcam_softmax_rows(logits, n, rel)
+    K.gemm_bf16(xb, wb("v3_w", fusion.vis_3[0]), bias=b_(fusion.vis_3[0]), act=K.ACT_RELU, out_bf16=q)         # query is dead: query3
+    q3T = ws.get("bc_q3T", (B, C, hw8), torch.bfloat16, dev)
+    K.bcam_transpose_pad(q, q3T)
+    for b in range(B):
+        K.gemm_bf16(rel[b * n:(b + 1) * n, :hw8], q3T[b], out_bf16=cat[b * n:(b + 1) * n, :C])
+    # out3 = relu(out3_proj(cat[out2, out])) + relu(vis_4 x)  (:65-71)
+    q4 = ws.get("pw_q", (N_, C), torch.float32, dev)
+    K.gemm_bf16(xb, wb("v4_w", fusion.vis_4[0]), bias=b_(fusion.vis_4[0]), act=K.ACT_RELU, out_f32=q4)
+    r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+    rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+    K.gemm_bf16(cat[:, :2 * C], wb("o3_w", fusion.out3_proj[0]), bias=b_(fusion.out3_proj[0]), act=K.ACT_RELU, resid=q4, out_f32=r32, out_bf16=rb)
+    _count(11 + 3 * B)
+    if res_gate is not None:
+        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=q)
+        if gate_act != "tanh":
+            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+        K.gemm_bf16(q, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
         _count(2)
     return r32
 

@@ -14,7 +14,7 @@ import torch.nn as nn
 from .. import engine as E
 from . import video_swin_transformer as V
 
-_REJECTED = ("bcam", "efn")
+_REJECTED = ("efn",)
 
 
 def _check_2d_args(args) -> None:
@@ -56,6 +56,39 @@ class GACD(nn.Module):
         return r.view(B, n, C)
 
 
+class BCAM(nn.Module):
+    """BCAM fusion parameters (reference lib/bcam.py:8-75; --bcam, from BRINet).  forward(x (B,hw,C), l (B,768,Nl), l_mask (B,Nl,1)) -> (B,hw,C).
+    ``a_proj`` is a Linear(dim -> hw) with hw tied to the width as in the reference (:11-18), i.e. to the feature maps of a 480 x 480 input."""
+    kind = "bcam"
+    HW = {128: 120 * 120, 256: 60 * 60, 512: 30 * 30, 1024: 15 * 15}
+
+    def __init__(self, dim, v_in_channels, l_in_channels):
+        super().__init__()
+        if dim not in self.HW:
+            raise NotImplementedError(f"BCAM is defined for widths {sorted(self.HW)} only (reference lib/bcam.py:11-18), got {dim}")
+        if dim != v_in_channels:
+            raise NotImplementedError("BCAM with differing channel widths is not supported on the B200 path")
+        self.dim, self.hw = dim, self.HW[dim]
+        self.lang_reduce = nn.Linear(l_in_channels, dim)
+        self.vis_1 = nn.Sequential(nn.Linear(v_in_channels, dim), nn.ReLU())
+        self.vis_2 = nn.Sequential(nn.Linear(v_in_channels, dim), nn.ReLU())
+        self.vis_3 = nn.Sequential(nn.Linear(v_in_channels, dim), nn.ReLU())
+        self.vis_4 = nn.Sequential(nn.Linear(v_in_channels, dim), nn.ReLU())
+        self.out_1 = nn.Linear(dim, dim)
+        self.vis_2_2 = nn.Linear(dim, dim)
+        self.a_proj = nn.Linear(dim, self.hw)
+        self.out3_proj = nn.Sequential(nn.Linear(2 * dim, dim), nn.ReLU())
+        self.prepared = E.PreparedWeights()
+
+    def forward(self, x: torch.Tensor, l: torch.Tensor, l_mask: torch.Tensor) -> torch.Tensor:
+        E.require_cuda(x, "x")
+        B, n, C = x.shape
+        xf = x.detach().float().reshape(B * n, C).contiguous()
+        r = torch.empty(B * n, C, device=x.device, dtype=torch.float32)
+        E.bcam_gate(xf, xf.to(torch.bfloat16), self, None, V._lang(l), V._mask(l_mask), B, E.workspace(x.device), r_f32=r)
+        return r.view(B, n, C)
+
+
 class PatchEmbed(nn.Module):
     """Conv2d(k = s = 4) + LN (reference :291-331)."""
 
@@ -89,7 +122,9 @@ class MMBasicLayer(V.MMBasicLayer):
                          mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
                          drop_path=drop_path, norm_layer=norm_layer, downsample=downsample, use_checkpoint=False,
                          num_heads_fusion=num_heads_fusion, fusion_drop=fusion_drop, args=args)
-        if getattr(args, "gacd", False):      # reference lib/backbone.py:578-582
+        if getattr(args, "bcam", False):      # reference lib/backbone.py:573-577 (checked before --gacd there too)
+            self.fusion = BCAM(dim, dim, 768)
+        elif getattr(args, "gacd", False):    # reference lib/backbone.py:578-582
             self.fusion = GACD(dim, dim, 768, num_heads=num_heads_fusion)
         for blk in self.blocks:
             blk.clamp_window = False          # the 2-D reference always pads to a full window and always shifts

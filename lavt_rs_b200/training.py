@@ -31,8 +31,8 @@ from . import train_engine as T
 def _check_trainable(model) -> None:
     bb = model.backbone
     for layer in bb.layers:
-        if getattr(layer.fusion, "kind", "pwam") == "gacd":
-            raise NotImplementedError("--gacd is inference-only on the B200 path")
+        if getattr(layer.fusion, "kind", "pwam") in ("gacd", "bcam"):
+            raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
         if not layer.sep_t_pwam and not layer.fusion.attention:
             raise NotImplementedError("--fuse simple is inference-only on the B200 path")
         if layer.version not in ("default", "no_gate", "none"):

@@ -79,6 +79,23 @@ def test_builders_reject_unimplemented_flags():
     assert tiny.backbone.embed_dim == 96
 
 
+def test_bcam_gacd_backbone_state_dicts_match_oracle_contract():
+    """--bcam / --gacd (reference lib/backbone.py:573-582): the 2-D backbone registers the reference's fusion parameters; --efn is refused."""
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    for flag in ("bcam", "gacd"):
+        bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                       num_heads_fusion=[1, 1, 1, 1], args=default_args(["--" + flag]))
+        cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, **{flag: True})
+        sd = {k[len("backbone."):]: v for k, v in O.random_state_dict(cfg).items() if k.startswith("backbone.")}
+        mine = {k: v for k, v in bb.state_dict().items() if not k.endswith("relative_position_index")}
+        assert set(mine) == set(sd), flag
+        for k, v in sd.items():
+            assert tuple(mine[k].shape) == tuple(v.shape), k
+    assert bb.layers[0].fusion.kind == "gacd"
+    with pytest.raises(NotImplementedError):
+        MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, args=default_args(["--efn"]))
+
+
 def test_forward_refuses_cpu_tensors():
     from lavt_rs_b200 import _cabi
     bb, dec = _small_backbone()

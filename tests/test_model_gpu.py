@@ -421,3 +421,69 @@ def test_gacd_image_model_end_to_end():
     for i in range(4):
         assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_bcam_kernels_vs_torch():
+    """csrc/bcam_kernels.cu on their own (reference lib/bcam.py:47, :54-55 / :62, :63-64), ragged sizes: pad rows / columns must be exact zeros."""
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(3)
+    B, Nl, Nlp, Lin, C = 2, 21, 32, 768, 96
+    l = torch.randn(B, Lin, Nl, generator=g).cuda()
+    w = (torch.randn(C, Lin, generator=g) * 0.05).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    lr = torch.full((B, Nlp, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    lrT = torch.full((B, C, Nlp), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.bcam_words(l, w, bias, lr, lrT)
+    ref = l.transpose(1, 2) @ w.t() + bias
+    assert_close(lr[:, :Nl], ref, what="bcam_words")
+    assert torch.equal(lr.transpose(1, 2), lrT) and lr[:, Nl:].abs().max().item() == 0.0
+    for rows, cols, ld, with_mask in ((37, 21, 32, True), (19, 225, 256, False), (5, 14400, 14400, False), (3, 3600, 3616, False)):
+        s_ = torch.randn(rows, ld, generator=g).cuda() * 3
+        m = (torch.rand(2, cols, generator=g) > 0.3).float().cuda() if with_mask else None
+        p_ = torch.full((rows, ld), 7.0, device="cuda", dtype=torch.bfloat16)
+        rpm = (rows + 1) // 2
+        K.bcam_softmax_rows(s_, cols, p_, mask=m, rows_per_mask=rpm if with_mask else 0)
+        z = s_[:, :cols]
+        if with_mask:
+            z = z + (1e4 * m[torch.arange(rows, device="cuda") // rpm] - 1e4)
+        assert (p_[:, :cols].float() - z.softmax(-1)).abs().max().item() < 4e-3 * z.softmax(-1).max().item() + 1e-6, (rows, cols)
+        assert ld == cols or p_[:, cols:].abs().max().item() == 0.0
+    x = torch.randn(2 * 225, 64, generator=g).cuda().to(torch.bfloat16)
+    out = torch.full((2, 64, 232), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.bcam_transpose_pad(x, out)
+    assert torch.equal(out[:, :, :225], x.view(2, 225, 64).transpose(1, 2)) and out[:, :, 225:].abs().max().item() == 0.0
+
+
+def test_bcam_image_model_end_to_end():
+    """--bcam (BCAM fusion, reference lib/bcam.py:8-75) in the 2-D image backbone at its only input size, 480 x 480 (a_proj is a
+    Linear(dim -> hw)): stage outputs + logits vs the oracle; the module on its own with a batch of 2 at the ragged hw = 15 x 15 stage."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, bcam=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=default_args(["--bcam"]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(1, 1, 480, 480, Nl=20, video=False)
+    cap = {}
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        got = model(x.cuda(), l.cuda(), m.cuda())
+        _, l2, m2 = O.synthetic_inputs(2, 1, 32, 32, Nl=11, video=False)
+        for stage, C, hw in ((3, 1024, 225), (2, 512, 900)):
+            xs = torch.randn(2, hw, C, generator=torch.Generator().manual_seed(4))
+            r_ref = O.bcam(xs, l2, m2.unsqueeze(-1), sd, f"backbone.layers.{stage}.fusion.")
+            r_got = bb.layers[stage].fusion(xs.cuda(), l2.cuda(), m2.unsqueeze(-1).cuda())
+            assert rel_l2(r_got, r_ref) < 1.5e-2, (stage, rel_l2(r_got, r_ref))
+        with pytest.raises(RuntimeError):          # a feature map that a_proj does not match is refused, not truncated
+            bb.layers[3].fusion(torch.randn(1, 144, 1024).cuda(), l2[:1].cuda(), m2[:1].unsqueeze(-1).cuda())
+    for i in range(4):
+        assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
