@@ -42,6 +42,7 @@ class OracleConfig:
     gate_act: str = "tanh"
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
     bcam: bool = False                            # --bcam (2-D image backbone, 480 x 480 inputs only): BCAM fusion of lib/bcam.py:8-75
+    efn: bool = False                             # --efn (2-D image backbone): EFN fusion of lib/bcam.py:160-269 (co-attention over pooled pixels)
     gacd: bool = False                            # --gacd (2-D image backbone): GA-CD fusion of lib/bcam.py:78-127 instead of PWAM
     fuse_simple: bool = False                     # --fuse simple: LangProject (mean-pooled sentence vector) instead of pixel-word attention
     version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
@@ -226,6 +227,40 @@ def bcam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
     return out3 + F.relu(lin(x, "vis_4.0"))
 
 
+def efn(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
+    """EFN fusion (lib/bcam.py:160-269, the --efn ablation of the 2-D backbone).  M = gelu(Conv1d(cat[x, masked-mean sentence vector]));
+    lang = gelu(Conv1d(l)) * mask; L = softmax_words(C^-0.5 M lang + pad mask) lang^T (:172-194).  EFNAttention (:236-269): q = IN(Conv1d(M)),
+    k = IN(Conv1d(L)), both 2 x 2 average-pooled when hw > 225 (the token axis is read as a square image); sim = C^-0.5 q k^T;
+    Lp = softmax_rows(sim) k, Mp = softmax_cols(sim)^T q; out = IN(Conv1d(k = 3, pad 1, over the flattened token axis)(cat[Lp, Mp])),
+    bilinearly upsampled x 2 (align_corners False) when pooled.  x (B,n,C); l (B,768,Nl); l_mask (B,Nl,1) -> (B,n,C)."""
+    B, n, C = x.shape
+    m = l_mask.to(x.dtype)                                               # (B, Nl, 1)
+    lt = l.transpose(1, 2)                                               # (B, Nl, 768)
+    sent = (lt * m).sum(1, keepdim=True) / m.sum(1, keepdim=True)        # (B, 1, 768)
+    M = F.gelu(_lin1x1(torch.cat([x, sent.expand(B, n, -1)], -1), sd, pre + "project.0"))
+    lang = F.gelu(_lin1x1(lt, sd, pre + "lang_project.0")) * m           # (B, Nl, C)
+    score = (C ** -0.5) * (M @ lang.transpose(1, 2)) + (1e4 * m.transpose(1, 2) - 1e4)
+    L = score.softmax(-1) @ lang                                         # (B, n, C)
+    a = pre + "image_lang_att."
+    q = _instance_norm_tokens(_lin1x1(M, sd, a + "f_query.0"))
+    k = _instance_norm_tokens(_lin1x1(L, sd, a + "f_key.0"))
+    pooled = n > 225
+    h = int(n ** 0.5)
+    if pooled:
+        def pool(t):
+            return F.avg_pool2d(t.transpose(1, 2).reshape(B, C, h, h), 2).reshape(B, C, n // 4).transpose(1, 2)
+        q, k = pool(q), pool(k)
+    sim = (C ** -0.5) * (q @ k.transpose(1, 2))                          # (B, n', n')
+    Lp = sim.softmax(-1) @ k
+    Mp = sim.softmax(-2).transpose(1, 2) @ q
+    cat = torch.cat([Lp, Mp], -1).transpose(1, 2)                        # (B, 2C, n')
+    out = F.conv1d(cat, sd[a + "W.0.weight"], sd[a + "W.0.bias"], padding=1)
+    out = _instance_norm_tokens(out.transpose(1, 2)).transpose(1, 2)     # (B, C, n')
+    if pooled:
+        out = F.interpolate(out.reshape(B, C, h // 2, h // 2), scale_factor=2, mode="bilinear").reshape(B, C, n)
+    return out.transpose(1, 2)
+
+
 def gacd(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
     """GA-CD fusion (lib/bcam.py:78-127, the --gacd ablation of the 2-D backbone): sentence vector ls = LangProject(l); xm = relu(Linear(ls * x));
     one query vector per image q = Linear(ls); collection A_c = softmax_n(q . key_c(xm) dim^-0.5), diffusion A_d = sigmoid(q . key_d(xm) dim^-0.5);
@@ -343,6 +378,8 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             r = bcam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
         elif cfg.gacd:
             r = gacd(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
+        elif cfg.efn:
+            r = efn(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
         elif cfg.sep_t_pwam:
             r = sep_t_pwam(x, l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         else:
@@ -488,6 +525,11 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
             for name, cin in (("lang_gen.project.0", l_in), ("lang_gen.project.2", C), ("mm_gen.0", C), ("query", C), ("key_c", C), ("key_d", C),
                               ("value", C)):
                 w, b = conv_default(C, cin)
+                sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+        elif cfg.efn:
+            for name, shape in (("project.0", (C, C + l_in, 1)), ("lang_project.0", (C, l_in, 1)), ("image_lang_att.f_key.0", (C, C, 1)),
+                                ("image_lang_att.f_query.0", (C, C, 1)), ("image_lang_att.W.0", (C, 2 * C, 3))):
+                w, b = conv_default(*shape)
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
         elif cfg.fuse_simple:
             for name in ("vis_project.0", "project_mm.0"):

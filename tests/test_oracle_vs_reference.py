@@ -246,3 +246,23 @@ def test_bcam_image_backbone_matches_reference():
         got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
     for i, (a, b) in enumerate(zip(got, ref)):
         assert a.shape == b.shape and (a - b).abs().max().item() < 5e-4, (i, (a - b).abs().max().item())
+
+
+def test_efn_image_backbone_matches_reference():
+    """--efn: EFN fusion (lib/bcam.py:160-269) in the 2-D image backbone; 480 x 480 so that stages 0-2 pool (square maps of 120, 60, 30) and
+    stage 3 (15 x 15 = 225 tokens) does not."""
+    bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=7, depths=(2, 2, 2, 2), extra=("--efn",))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, efn=True)
+    assert {k for k in O.random_state_dict(cfg) if "fusion" in k} == {k for k in sd if "fusion" in k}
+    for k, v in O.random_state_dict(cfg).items():
+        assert "fusion" not in k or v.shape == sd[k].shape, k
+    x, l, m = O.synthetic_inputs(1, 1, 480, 480, Nl=9, video=False)
+    with torch.no_grad():
+        ref = bb(x, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+    # at random init the co-attention maps are almost uniform, so Lp / Mp barely vary over the tokens and the closing InstanceNorm
+    # amplifies fp32 summation-order noise (the restatement contracts (B, n, C) rows, the reference (B, C, n) planes): 2e-3 on O(1) values
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 2e-3, (i, (a - b).abs().max().item())
