@@ -348,15 +348,38 @@ int lavt_gacd_fuse(const float* xm, const float* lang_stats, const float* wq, co
  * All contractions of the module are lavt_gemm_bf16 calls; these are the kernels between them.
  * lavt_bcam_words: lr = lang_reduce(l^T) (lib/bcam.py:47): l fp32 [B,Lin,Nl], w fp32 [C,Lin] -> lr bf16 [B,Nlp,C] (rows >= Nl zero) and
  *   its transpose lrT bf16 [B,C,Nlp] (the K-major operands of sim = q lr^T and out = sim lr, :52-56).
+ *   With act = LAVT_ACT_GELU and mask fp32 [B,Nl] (else LAVT_ACT_NONE / NULL) the same kernel is EFN's lang = gelu(lang_project(l)) * l_mask
+ *   (lib/bcam.py:186-187).
  * lavt_bcam_softmax_rows: p[r, 0:cols] = softmax(s[r, 0:cols] + (1e4 mask[r / rows_per_mask, :] - 1e4)) as bf16, p[r, cols:ldp] = 0
  *   (mask may be NULL): the word softmax (:54-55) and the hw x hw relation map (:62); cols <= 16384.
  * lavt_bcam_transpose_pad: in bf16 [B*n, ldi] (C channels) -> out bf16 [B, C, ldo], columns n..ldo zero: query3 as the K-major
  *   operand of out2 = rel_map query3 (:63-64). */
-int lavt_bcam_words(const float* l, const float* w, const float* bias, void* lr_bf16, void* lrT_bf16, int32_t B, int32_t Nl, int32_t Nlp,
-                    int32_t Lin, int32_t C, void* stream);
+int lavt_bcam_words(const float* l, const float* w, const float* bias, const float* mask, int32_t act, void* lr_bf16, void* lrT_bf16,
+                    int32_t B, int32_t Nl, int32_t Nlp, int32_t Lin, int32_t C, void* stream);
 int lavt_bcam_softmax_rows(const float* s, int64_t lds, const float* mask, int64_t rows_per_mask, void* p_bf16, int64_t ldp, int64_t rows,
                            int32_t cols, void* stream);
 int lavt_bcam_transpose_pad(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t B, int64_t n, int32_t C, void* stream);
+
+/* ---- EFN fusion (lib/bcam.py:160-269; the --efn ablation of the 2-D image backbone, lib/backbone.py:583-588) ----
+ * The contractions are lavt_gemm_bf16 calls (the k = 3 Conv1d of EFNAttention.W, :231-233, as three row-shifted accumulating GEMMs; the
+ * dim = -2 softmax of :255 as the row softmax of the transposed product); word side / softmaxes / K-major copies are the lavt_bcam_* kernels.
+ * lavt_efn_sentence_bias: sb fp32 [B,C] = bias + w sent, sent = masked mean of l fp32 [B,Lin,Nl] (:179-180), w fp32 [C,Lin] with row pitch
+ *   ldw: the language half of project's Conv1d over cat[x, sentence] (:183-185) as a per-image bias of the GEMM over x.
+ * lavt_efn_norm_pool: out bf16 [B, rows_out, C] = AvgPool2d(2) (pool != 0; n = h*h tokens as a square image, :243-249) of the InstanceNorm of
+ *   pre fp32 [B,n,C] with stats fp32 [B,2,C] = (mean, rstd) from lavt_instnorm_stats; rows beyond the n/4 (or n) produced are zero.
+ * lavt_efn_norm_upsample: out (fp32 and / or bf16) [B,n,C] = nn.Upsample(scale_factor=2, bilinear) (up != 0, :263-266) of the InstanceNorm of
+ *   pre fp32 [B, n/4, C]; up == 0: the InstanceNorm alone.
+ * lavt_efn_word_attend: k_pre fp32 [B*n, C] = f_key(L), L = softmax_words(score + (1e4 mask - 1e4)) lang^T (:189-194, :241), evaluated as
+ *   sum_j p[i, j] g[b, j, :] with g fp32 [B, g_rows, C] = f_key(lang^T) (bias included) and score fp32 [B*n, lds]: everything stays fp32
+ *   because the few words carry all of the token-to-token variation and an InstanceNorm follows.  Nl <= 128. */
+int lavt_efn_word_attend(const float* score, int64_t lds, const float* mask, const float* g, int64_t g_rows, float* out, int32_t B, int64_t n,
+                         int32_t Nl, int32_t C, void* stream);
+int lavt_efn_sentence_bias(const float* l, const float* mask, const float* w, int64_t ldw, const float* bias, float* sb, int32_t B, int32_t Nl,
+                           int32_t Lin, int32_t C, void* stream);
+int lavt_efn_norm_pool(const float* pre, const float* stats, void* out_bf16, int32_t B, int64_t n, int32_t h, int32_t pool, int64_t rows_out,
+                       int32_t C, void* stream);
+int lavt_efn_norm_upsample(const float* pre, const float* stats, float* out_f32, void* out_bf16, int32_t B, int64_t n, int32_t h, int32_t up,
+                           int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -132,7 +132,11 @@ SIGNATURES = {
     "lavt_logits_to_mask": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "lavt_gacd_fuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_adamw_step": [_vp, _vp, _i32, _i32, _f32, C.c_double, C.c_double, _f32, _f32, _vp],
-    "lavt_bcam_words": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_bcam_words": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "lavt_efn_sentence_bias": [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_efn_word_attend": [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i64, _i32, _i32, _vp],
+    "lavt_efn_norm_pool": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp],
+    "lavt_efn_norm_upsample": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_bcam_softmax_rows": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_bcam_transpose_pad": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp],
 }
@@ -868,13 +872,16 @@ def gacd_fuse(xm, lang_stats, wq, bq, wc, bc, wd, bd, wv, bv, ws_get, out_f32=No
                                ptr(out_bf16), B, n, Cn, stream_ptr()), "lavt_gacd_fuse")
 
 
-def bcam_words(l: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, lr: torch.Tensor, lrT: torch.Tensor) -> None:
-    """lr = lang_reduce(l^T) (reference lib/bcam.py:47): l fp32 [B,Lin,Nl], w fp32 [C,Lin] -> lr bf16 [B,Nlp,C] (pad rows zero), lrT bf16 [B,C,Nlp]."""
+def bcam_words(l: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, lr: torch.Tensor, lrT: torch.Tensor, mask: Optional[torch.Tensor] = None,
+               act: int = ACT_NONE) -> None:
+    """lr = lang_reduce(l^T) (reference lib/bcam.py:47): l fp32 [B,Lin,Nl], w fp32 [C,Lin] -> lr bf16 [B,Nlp,C] (pad rows zero), lrT bf16 [B,C,Nlp].
+    With ``act=ACT_GELU`` and ``mask`` fp32 [B,Nl]: EFN's lang = gelu(lang_project(l)) * l_mask (:186-187)."""
     B, Lin, Nl = l.shape
     _, Nlp, Cn = lr.shape
     if tuple(lrT.shape) != (B, Cn, Nlp) or tuple(w.shape) != (Cn, Lin):
         raise LavtError("bcam_words: shape mismatch")
     check(lib().lavt_bcam_words(_c(l, torch.float32, "l").data_ptr(), _c(w, torch.float32, "w").data_ptr(), _c(bias, torch.float32, "bias").data_ptr(),
+                                _c(mask, torch.float32, "mask").data_ptr() if mask is not None else None, int(act),
                                 _c(lr, torch.bfloat16, "lr").data_ptr(), _c(lrT, torch.bfloat16, "lrT").data_ptr(), B, Nl, Nlp, Lin, Cn, stream_ptr()),
           "lavt_bcam_words")
 
@@ -903,3 +910,51 @@ def bcam_transpose_pad(x: torch.Tensor, out: torch.Tensor) -> None:
         raise LavtError("bcam_transpose_pad: shape mismatch")
     check(lib().lavt_bcam_transpose_pad(x.data_ptr(), x.stride(0), _c(out, torch.bfloat16, "out").data_ptr(), ldo, B, n, Cn, stream_ptr()),
           "lavt_bcam_transpose_pad")
+
+
+def efn_sentence_bias(l: torch.Tensor, mask: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, sb: torch.Tensor) -> None:
+    """sb fp32 [B,C] = bias + w @ masked-mean(l) (reference lib/bcam.py:179-185); l fp32 [B,Lin,Nl], mask fp32 [B,Nl], w fp32 [C,Lin] (row pitch free)."""
+    B, Lin, Nl = l.shape
+    _req(w, torch.float32, "w")
+    Cn = w.shape[0]
+    if w.shape[1] != Lin or tuple(sb.shape) != (B, Cn) or tuple(mask.shape) != (B, Nl):
+        raise LavtError("efn_sentence_bias: shape mismatch")
+    check(lib().lavt_efn_sentence_bias(_c(l, torch.float32, "l").data_ptr(), _c(mask, torch.float32, "mask").data_ptr(), w.data_ptr(), w.stride(0),
+                                       _c(bias, torch.float32, "bias").data_ptr(), _c(sb, torch.float32, "sb").data_ptr(), B, Nl, Lin, Cn,
+                                       stream_ptr()), "lavt_efn_sentence_bias")
+
+
+def efn_norm_pool(pre: torch.Tensor, stats: torch.Tensor, out: torch.Tensor, h: int, pool: bool) -> None:
+    """out bf16 [B, rows_out, C] = (2 x 2 average pool of) InstanceNorm(pre fp32 [B,n,C]) with stats fp32 [B,2,C]; surplus rows zero."""
+    B, n, Cn = pre.shape
+    if out.shape[0] != B or out.shape[2] != Cn:
+        raise LavtError("efn_norm_pool: shape mismatch")
+    check(lib().lavt_efn_norm_pool(_c(pre, torch.float32, "pre").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(),
+                                   _c(out, torch.bfloat16, "out").data_ptr(), B, n, int(h), 1 if pool else 0, out.shape[1], Cn, stream_ptr()),
+          "lavt_efn_norm_pool")
+
+
+def efn_norm_upsample(pre: torch.Tensor, stats: torch.Tensor, n: int, h: int, up: bool, out_f32=None, out_bf16=None) -> None:
+    """out [B*n, C] = (bilinear x 2, align_corners False, of) InstanceNorm(pre fp32 [B, n/4 or n, C])."""
+    B, n_in, Cn = pre.shape
+    if n_in != (n // 4 if up else n):
+        raise LavtError("efn_norm_upsample: shape mismatch")
+    for t, dt, nm in ((out_f32, torch.float32, "out_f32"), (out_bf16, torch.bfloat16, "out_bf16")):
+        if t is not None:
+            _c(t, dt, nm)
+            if t.numel() != B * n * Cn:
+                raise LavtError("efn_norm_upsample: output size mismatch")
+    check(lib().lavt_efn_norm_upsample(_c(pre, torch.float32, "pre").data_ptr(), _c(stats, torch.float32, "stats").data_ptr(), ptr(out_f32),
+                                       ptr(out_bf16), B, n, int(h), 1 if up else 0, Cn, stream_ptr()), "lavt_efn_norm_upsample")
+
+
+def efn_word_attend(score: torch.Tensor, mask: torch.Tensor, g: torch.Tensor, out: torch.Tensor) -> None:
+    """out fp32 [B*n, C] = softmax(score[:, :Nl] + (1e4 mask - 1e4)) @ g[b]; score fp32 [B*n, lds], mask fp32 [B,Nl], g fp32 [B, g_rows >= Nl, C]."""
+    _req(score, torch.float32, "score")
+    B, Nl = mask.shape
+    rows = score.shape[0]
+    Cn = g.shape[2]
+    if rows % B or g.shape[0] != B or g.shape[1] < Nl or score.shape[1] < Nl or tuple(out.shape) != (rows, Cn):
+        raise LavtError("efn_word_attend: shape mismatch")
+    check(lib().lavt_efn_word_attend(score.data_ptr(), score.stride(0), _c(mask, torch.float32, "mask").data_ptr(), _c(g, torch.float32, "g").data_ptr(),
+                                     g.shape[1], _c(out, torch.float32, "out").data_ptr(), B, rows // B, Nl, Cn, stream_ptr()), "lavt_efn_word_attend")

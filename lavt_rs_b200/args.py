@@ -29,7 +29,7 @@ _STRUCTURE_FLAGS = [
     ("--hs", "store_true", False, "stage outputs = gated features E_i instead of the PWAM residuals"),
     ("--gacd", "store_true", False, "2-D image backbone: GA-CD fusion (lib/bcam.py) instead of PWAM"),
     ("--bcam", "store_true", False, "2-D image backbone: BCAM fusion (lib/bcam.py) instead of PWAM; 480 x 480 inputs only, inference"),
-    ("--efn", "store_true", False, "2-D image backbone: EFN fusion (lib/bcam.py) -- rejected at build time (not implemented)"),
+    ("--efn", "store_true", False, "2-D image backbone: EFN fusion (lib/bcam.py) instead of PWAM; square feature maps, inference"),
     ("--sep_t_pwam", "store_true", False, "SepTPWAM fusion: temporal Conv3d + spatial Conv3d branches, summed"),
     ("--conv3d_kernel_size_t", str, "3-1-1", "temporal-branch Conv3d kernel (B200 path: 3-3-3)"),
     ("--conv3d_kernel_size_s", str, "1-1-1", "spatial-branch Conv3d kernel (B200 path: 1-1-1)"),

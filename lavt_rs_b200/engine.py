@@ -155,6 +155,8 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         return gacd_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
     if getattr(fusion, "kind", "pwam") == "bcam":
         return bcam_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
+    if getattr(fusion, "kind", "pwam") == "efn":
+        return efn_gate(x, xb, fusion, res_gate, l, mask, B, ws, gate_act=gate_act, r_f32=r_f32)
     N_, C = x.shape
     n = N_ // B
     dev = x.device
@@ -341,6 +343,101 @@ def bcam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         if gate_act != "tanh":
             raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
         K.gemm_bf16(q, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
+        _count(2)
+    return r32
+
+
+def efn_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace,
+             gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EFN fusion (reference lib/bcam.py:172-269, --efn) + LanguageGate; same contract as ``pwam_gate``.  The token axis is read as a square
+    image (h = sqrt(n)) and 2 x 2 pooled when n > 225, as in the reference; the co-attention maps are (n/4)^2 at most (3600^2 at 480 x 480)."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    h = int(round(n ** 0.5))
+    pooled = n > 225                         # (:243)
+    if h * h != n or (pooled and h % 2):
+        raise K.LavtError(f"EFN: {n} tokens are not a square (even-sided when pooled) feature map (reference lib/bcam.py:239-249)")
+    pw = fusion.prepared
+    att = fusion.image_lang_att
+    Nl = l.shape[-1]
+    Nlp = (Nl + 31) // 32 * 32
+    n2 = n // 4 if pooled else n             # co-attention positions
+    n2p = (n2 + 31) // 32 * 32
+    scale = C ** -0.5
+
+    def cs(N):
+        return pw.get("cs_%d" % N, [], lambda: torch.full((N,), scale, device=dev, dtype=torch.float32))
+
+    # M = gelu(project(cat[x, sentence])) (:179-185): the sentence half of the Conv1d is a per-image bias
+    pj = fusion.project[0]
+    sb = ws.get("ef_sb", (B, C), torch.float32, dev)
+    K.efn_sentence_bias(l, mask, pw.get("pj_wl", [pj.weight], lambda: _f32(pj.weight[:, C:, 0])), _f32(pj.bias), sb)
+    wx = pw.get("pj_wx", [pj.weight], lambda: _bf16(pj.weight[:, :C, 0]))
+    M = ws.get("pw_vis", (N_, C), torch.bfloat16, dev)
+    for b in range(B):
+        K.gemm_bf16(xb[b * n:(b + 1) * n], wx, bias=sb[b], act=K.ACT_GELU, out_bf16=M[b * n:(b + 1) * n])
+    # lang = gelu(lang_project(l)) * mask; L = softmax(C^-0.5 M lang + pad mask) lang^T (:186-194)
+    lp = fusion.lang_project[0]
+    lang = ws.get("bc_lr", (B, Nlp, C), torch.bfloat16, dev)
+    langT = ws.get("bc_lrT", (B, C, Nlp), torch.bfloat16, dev)
+    K.bcam_words(l, pw.get("lp_w", [lp.weight], lambda: _f32(lp.weight[:, :, 0])), _f32(lp.bias), lang, langT, mask=mask, act=K.ACT_GELU)
+    sim = ws.get("bc_sim", (N_, Nlp), torch.float32, dev)
+    for b in range(B):
+        K.gemm_bf16(M[b * n:(b + 1) * n], lang[b], cscale=cs(Nlp), out_f32=sim[b * n:(b + 1) * n])
+    # f_key(L) = sum_j p_j f_key(lang_j): the key side stays fp32 up to its InstanceNorm (see csrc/bcam_kernels.cu: efn_word_attend_kernel)
+    fk = att.f_key[0]
+    G = ws.get("ef_G", (B, Nlp, C), torch.float32, dev)
+    K.gemm_bf16(lang.view(B * Nlp, C), pw.get("fk_w", [fk.weight], lambda: _bf16(_conv1x1_w(fk))), bias=fk.bias.detach(), out_f32=G.view(B * Nlp, C))
+    # EFNAttention (:236-269): q = pool(IN(f_query M)), k = pool(IN(f_key L))
+    stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), torch.float32, dev)
+    stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
+    pre = ws.get("pw_q", (B, n, C), torch.float32, dev)
+    qk = []
+    for name in ("fq", "fk"):
+        if name == "fq":
+            conv = att.f_query[0]
+            K.gemm_bf16(M, pw.get("fq_w", [conv.weight], lambda: _bf16(_conv1x1_w(conv))), bias=conv.bias.detach(), out_f32=pre.view(N_, C))
+        else:
+            K.efn_word_attend(sim, mask, G, pre.view(N_, C))
+        K.instnorm_stats(pre, stats, stw)
+        t = ws.get("ef_" + name, (B, n2p, C), torch.bfloat16, dev)
+        K.efn_norm_pool(pre, stats, t, h, pooled)
+        qk.append(t)
+    q, k = qk
+    qT = ws.get("ef_qT", (B, C, n2p), torch.bfloat16, dev)
+    kT = ws.get("ef_kT", (B, C, n2p), torch.bfloat16, dev)
+    K.bcam_transpose_pad(q.view(B * n2p, C), qT)
+    K.bcam_transpose_pad(k.view(B * n2p, C), kT)
+    logits = ws.get("bc_logits", (n2, n2p), torch.float32, dev)
+    prob = ws.get("bc_rel", (n2, n2p), torch.bfloat16, dev)
+    cat = ws.get("bc_cat", (B, n2, 2 * C), torch.bfloat16, dev)            # Lp | Mp
+    for b in range(B):
+        # Lp = softmax_rows(sim) k ; Mp = softmax_cols(sim)^T q = softmax_rows(sim^T) q   (:251-258)
+        for a_, w_, vT, col in ((q, k, kT, 0), (k, q, qT, C)):
+            K.gemm_bf16(a_[b, :n2], w_[b], cscale=cs(n2p), out_f32=logits)
+            K.bcam_softmax_rows(logits, n2, prob)
+            K.gemm_bf16(prob, vT[b], out_bf16=cat[b, :, col:col + C])
+    # W: Conv1d(2C -> C, k = 3, pad 1) over the flattened token axis = centre tap + two row-shifted accumulations; then IN (+ upsample)
+    Wc = att.W[0]
+    taps = pw.get("W_taps", [Wc.weight], lambda: [_bf16(Wc.weight[:, :, t]) for t in range(3)])
+    o = ws.get("pw_q", (B, n2, C), torch.float32, dev)                     # q / k pre-activations are dead
+    for b in range(B):
+        K.gemm_bf16(cat[b], taps[1], bias=Wc.bias.detach(), out_f32=o[b])
+        K.gemm_bf16(cat[b, :n2 - 1], taps[0], resid=o[b, 1:], out_f32=o[b, 1:])          # out[i] += W[:, :, 0] cat[i - 1]
+        K.gemm_bf16(cat[b, 1:], taps[2], resid=o[b, :n2 - 1], out_f32=o[b, :n2 - 1])      # out[i] += W[:, :, 2] cat[i + 1]
+    K.instnorm_stats(o, stats, stw)
+    r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
+    rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
+    K.efn_norm_upsample(o, stats, n, h, pooled, out_f32=r32, out_bf16=rb)
+    _count(13 + 11 * B)
+    if res_gate is not None:
+        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=M)
+        if gate_act != "tanh":
+            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
+        K.gemm_bf16(M, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
         _count(2)
     return r32
 

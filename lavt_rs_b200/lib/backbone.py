@@ -14,7 +14,7 @@ import torch.nn as nn
 from .. import engine as E
 from . import video_swin_transformer as V
 
-_REJECTED = ("efn",)
+_REJECTED = ()
 
 
 def _check_2d_args(args) -> None:
@@ -89,6 +89,41 @@ class BCAM(nn.Module):
         return r.view(B, n, C)
 
 
+class EFNAttention(nn.Module):
+    """Parameter container of the reference's EFNAttention (lib/bcam.py:207-233); the math runs in ``engine.efn_gate``."""
+
+    def __init__(self, in_channels, key_channels):
+        super().__init__()
+        self.in_channels, self.key_channels = in_channels, key_channels
+        self.f_key = nn.Sequential(nn.Conv1d(in_channels, key_channels, kernel_size=1, stride=1), nn.InstanceNorm1d(key_channels))
+        self.f_query = nn.Sequential(nn.Conv1d(in_channels, key_channels, kernel_size=1, stride=1), nn.InstanceNorm1d(key_channels))
+        self.W = nn.Sequential(nn.Conv1d(2 * in_channels, in_channels, kernel_size=3, stride=1, padding=1), nn.InstanceNorm1d(in_channels))
+
+
+class EFN(nn.Module):
+    """EFN fusion parameters (reference lib/bcam.py:160-204; --efn).  forward(x (B,hw,C), l (B,768,Nl), l_mask (B,Nl,1)) -> (B,hw,C);
+    hw must be a square map (the reference reshapes the token axis to sqrt(hw) x sqrt(hw) and pools it when hw > 225)."""
+    kind = "efn"
+
+    def __init__(self, dim, v_in_channels, l_in_channels):
+        super().__init__()
+        if dim != v_in_channels:
+            raise NotImplementedError("EFN with differing channel widths is not supported on the B200 path")
+        self.dim = dim
+        self.project = nn.Sequential(nn.Conv1d(v_in_channels + l_in_channels, dim, 1, 1), nn.GELU())
+        self.lang_project = nn.Sequential(nn.Conv1d(l_in_channels, dim, 1, 1), nn.GELU())
+        self.image_lang_att = EFNAttention(in_channels=dim, key_channels=dim)
+        self.prepared = E.PreparedWeights()
+
+    def forward(self, x: torch.Tensor, l: torch.Tensor, l_mask: torch.Tensor) -> torch.Tensor:
+        E.require_cuda(x, "x")
+        B, n, C = x.shape
+        xf = x.detach().float().reshape(B * n, C).contiguous()
+        r = torch.empty(B * n, C, device=x.device, dtype=torch.float32)
+        E.efn_gate(xf, xf.to(torch.bfloat16), self, None, V._lang(l), V._mask(l_mask), B, E.workspace(x.device), r_f32=r)
+        return r.view(B, n, C)
+
+
 class PatchEmbed(nn.Module):
     """Conv2d(k = s = 4) + LN (reference :291-331)."""
 
@@ -126,6 +161,8 @@ class MMBasicLayer(V.MMBasicLayer):
             self.fusion = BCAM(dim, dim, 768)
         elif getattr(args, "gacd", False):    # reference lib/backbone.py:578-582
             self.fusion = GACD(dim, dim, 768, num_heads=num_heads_fusion)
+        elif getattr(args, "efn", False):     # reference lib/backbone.py:583-588
+            self.fusion = EFN(dim, dim, 768)
         for blk in self.blocks:
             blk.clamp_window = False          # the 2-D reference always pads to a full window and always shifts
         self.use_checkpoint = use_checkpoint

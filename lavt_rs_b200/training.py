@@ -31,7 +31,7 @@ from . import train_engine as T
 def _check_trainable(model) -> None:
     bb = model.backbone
     for layer in bb.layers:
-        if getattr(layer.fusion, "kind", "pwam") in ("gacd", "bcam"):
+        if getattr(layer.fusion, "kind", "pwam") in ("gacd", "bcam", "efn"):
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
         if not layer.sep_t_pwam and not layer.fusion.attention:
             raise NotImplementedError("--fuse simple is inference-only on the B200 path")

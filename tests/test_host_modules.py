@@ -80,9 +80,9 @@ def test_builders_reject_unimplemented_flags():
 
 
 def test_bcam_gacd_backbone_state_dicts_match_oracle_contract():
-    """--bcam / --gacd (reference lib/backbone.py:573-582): the 2-D backbone registers the reference's fusion parameters; --efn is refused."""
+    """--bcam / --efn / --gacd (reference lib/backbone.py:573-588): the 2-D backbone registers the reference's fusion parameters."""
     from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
-    for flag in ("bcam", "gacd"):
+    for flag in ("bcam", "efn", "gacd"):
         bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
                                        num_heads_fusion=[1, 1, 1, 1], args=default_args(["--" + flag]))
         cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, **{flag: True})
@@ -92,8 +92,6 @@ def test_bcam_gacd_backbone_state_dicts_match_oracle_contract():
         for k, v in sd.items():
             assert tuple(mine[k].shape) == tuple(v.shape), k
     assert bb.layers[0].fusion.kind == "gacd"
-    with pytest.raises(NotImplementedError):
-        MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, args=default_args(["--efn"]))
 
 
 def test_forward_refuses_cpu_tensors():

@@ -487,3 +487,92 @@ def test_bcam_image_model_end_to_end():
     for i in range(4):
         assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_efn_kernels_vs_torch():
+    """EFN's own kernels (reference lib/bcam.py:179-187, :240-249, :263-266) against torch on ragged sizes."""
+    import torch.nn.functional as F
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(5)
+    B, Nl, Lin, C = 2, 13, 768, 96
+    l = torch.randn(B, Lin, Nl, generator=g).cuda()
+    m = torch.zeros(B, Nl).cuda()
+    m[0, :9] = 1
+    m[1, :4] = 1
+    wfull = (torch.randn(C, C + Lin, generator=g) * 0.05).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    sb = torch.empty(B, C, device="cuda")
+    K.efn_sentence_bias(l, m, wfull[:, C:], bias, sb)                      # strided weight view: row pitch C + Lin
+    sent = (l * m[:, None]).sum(-1) / m.sum(-1, keepdim=True)
+    assert (sb - (sent @ wfull[:, C:].t() + bias)).abs().max().item() < 1e-4
+    lr = torch.empty(B, 32, C, device="cuda", dtype=torch.bfloat16)
+    lrT = torch.empty(B, C, 32, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(C, Lin, generator=g) * 0.05).cuda()
+    K.bcam_words(l, w, bias, lr, lrT, mask=m, act=K.ACT_GELU)
+    assert_close(lr[:, :Nl], F.gelu(l.transpose(1, 2) @ w.t() + bias) * m[..., None], what="efn words")
+    assert torch.equal(lr.transpose(1, 2), lrT) and lr[:, Nl:].abs().max().item() == 0.0
+    score = torch.randn(B * 37, 32, generator=g).cuda()
+    G = torch.randn(B, 32, C, generator=g).cuda()
+    kp = torch.empty(B * 37, C, device="cuda")
+    K.efn_word_attend(score, m, G, kp)
+    pr = (score[:, :Nl].view(B, 37, Nl) + (1e4 * m - 1e4)[:, None]).softmax(-1)
+    assert (kp.view(B, 37, C) - pr @ G[:, :Nl]).abs().max().item() < 1e-4
+    for h, pool in ((6, True), (15, False), (30, True)):
+        n = h * h
+        pre = torch.randn(B, n, C, generator=g).cuda() * 2 + 0.5
+        mu, var = pre.mean(1), pre.var(1, unbiased=False)
+        stats = torch.stack([mu, (var + 1e-5).rsqrt()], 1).contiguous()
+        normed = (pre - mu[:, None]) * stats[:, 1][:, None]
+        n2 = n // 4 if pool else n
+        rows = (n2 + 31) // 32 * 32
+        out = torch.full((B, rows, C), 7.0, device="cuda", dtype=torch.bfloat16)
+        K.efn_norm_pool(pre, stats, out, h, pool)
+        ref = F.avg_pool2d(normed.transpose(1, 2).reshape(B, C, h, h), 2).reshape(B, C, n2).transpose(1, 2) if pool else normed
+        assert (out[:, :n2].float() - ref).abs().max().item() < 2e-2 and (rows == n2 or out[:, n2:].abs().max().item() == 0.0)
+        small = torch.randn(B, n2, C, generator=g).cuda() * 2 + 0.5
+        mu, var = small.mean(1), small.var(1, unbiased=False)
+        stats = torch.stack([mu, (var + 1e-5).rsqrt()], 1).contiguous()
+        normed = (small - mu[:, None]) * stats[:, 1][:, None]
+        of = torch.empty(B * n, C, device="cuda")
+        ob = torch.empty(B * n, C, device="cuda", dtype=torch.bfloat16)
+        K.efn_norm_upsample(small, stats, n, h, pool, out_f32=of, out_bf16=ob)
+        ref = (F.interpolate(normed.transpose(1, 2).reshape(B, C, h // 2, h // 2), scale_factor=2, mode="bilinear").reshape(B, C, n).transpose(1, 2)
+               if pool else normed).reshape(B * n, C)
+        assert (of - ref).abs().max().item() < 1e-4 and (ob.float() - ref).abs().max().item() < 3e-2, (h, pool)
+
+
+def test_efn_image_model_end_to_end():
+    """--efn (EFN fusion, reference lib/bcam.py:160-269) in the 2-D image backbone at 480 x 480 (pooled co-attention at stages 0-2, plain at the
+    15 x 15 stage): stage outputs + logits vs the oracle; the module on its own with a batch of 2, pooled and not."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, efn=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=default_args(["--efn"]))
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(1, 1, 480, 480, Nl=20, video=False)
+    cap = {}
+    with torch.no_grad():
+        ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        got = model(x.cuda(), l.cuda(), m.cuda())
+        _, l2, m2 = O.synthetic_inputs(2, 1, 32, 32, Nl=11, video=False)
+        errs = {}
+        for stage, C, hw in ((3, 1024, 225), (2, 512, 900), (1, 256, 144)):
+            xs = torch.randn(2, hw, C, generator=torch.Generator().manual_seed(4))
+            r_ref = O.efn(xs, l2, m2.unsqueeze(-1), sd, f"backbone.layers.{stage}.fusion.")
+            r_got = bb.layers[stage].fusion(xs.cuda(), l2.cuda(), m2.unsqueeze(-1).cuda())
+            errs[stage] = rel_l2(r_got, r_ref)
+        with pytest.raises(RuntimeError):          # not a square map
+            bb.layers[3].fusion(torch.randn(1, 200, 1024).cuda(), l2[:1].cuda(), m2[:1].unsqueeze(-1).cuda())
+    stage_errs = [rel_l2(feats[i], cap[f"c{i + 1}"]) for i in range(4)]
+    assert max(errs.values()) < 2e-2, errs
+    assert max(stage_errs) < 3e-2, stage_errs
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
