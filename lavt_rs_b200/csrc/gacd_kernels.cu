@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(256) gacd_apply_kernel(const float4* __restric
 
 using namespace lavt;
 
+static inline long long al4(long long v) { return (v + 3) / 4 * 4; }
+
 extern "C" int64_t lavt_gacd_workspace_floats(int32_t B, int64_t n, int32_t C) {
   const int64_t chunks = (n + GACD_ROWS - 1) / GACD_ROWS;
-  return 1LL * B * 2 * C + 2LL * B + 2LL * B * n + 2LL * B * chunks + 1LL * B * chunks * C + 1LL * B * C;
+  // every segment starts on a 16-byte boundary (float4 reads of the partial sums / f_col): sizes rounded up to 4 floats
+  return al4(1LL * B * 2 * C) + al4(2LL * B) + al4(2LL * B * n) + 2 * al4(1LL * B * chunks) + al4(1LL * B * chunks * C) + al4(1LL * B * C);
 }
 
 // Everything of GA-CD after mm_gen: xm fp32 [B,n,C] -> out (fp32 and / or bf16) [B,n,C]
@@ -179,12 +182,12 @@ extern "C" int lavt_gacd_fuse(const float* xm, const float* lang_stats, const fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunks = static_cast<int>((n + GACD_ROWS - 1) / GACD_ROWS);
   float* u = workspace;
-  float* k0 = u + 1LL * B * 2 * C;
-  float* scores = k0 + 2LL * B;
-  float* pm = scores + 2LL * B * n;
-  float* ps = pm + 1LL * B * chunks;
-  float* px = ps + 1LL * B * chunks;
-  float* fcol = px + 1LL * B * chunks * C;
+  float* k0 = u + al4(1LL * B * 2 * C);
+  float* scores = k0 + al4(2LL * B);
+  float* pm = scores + al4(2LL * B * n);
+  float* ps = pm + al4(1LL * B * chunks);
+  float* px = ps + al4(1LL * B * chunks);
+  float* fcol = px + al4(1LL * B * chunks * C);
   gacd_vec_kernel<<<B, 256, 2 * C * sizeof(float), st>>>(lang_stats, wq, bq, wc, bc, wd, bd, u, k0, C);
   LAVT_LAUNCH_CHECK("gacd_vec_kernel");
   const size_t smem = (GACD_ROWS + 8 + 8 * static_cast<size_t>(C)) * sizeof(float);

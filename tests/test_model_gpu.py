@@ -417,7 +417,11 @@ def test_gacd_image_model_end_to_end():
         xs = torch.randn(2, 777, C, generator=torch.Generator().manual_seed(4))
         r_ref = O.gacd(xs, l, m.unsqueeze(-1), sd, "backbone.layers.1.fusion.")
         r_got = bb.layers[1].fusion(xs.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        # a single image with an odd chunk count: the workspace segments must stay 16-byte aligned (batch 1 at 480 x 480 used to fault)
+        r1_ref = O.gacd(xs[:1, :515], l[:1], m[:1].unsqueeze(-1), sd, "backbone.layers.1.fusion.")
+        r1_got = bb.layers[1].fusion(xs[:1, :515].cuda(), l[:1].cuda(), m[:1].unsqueeze(-1).cuda())
     assert rel_l2(r_got, r_ref) < 1.5e-2, rel_l2(r_got, r_ref)
+    assert rel_l2(r1_got, r1_ref) < 1.5e-2, rel_l2(r1_got, r1_ref)
     for i in range(4):
         assert rel_l2(feats[i], cap[f"c{i + 1}"]) < 3e-2, (i, rel_l2(feats[i], cap[f"c{i + 1}"]))
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
