@@ -2,7 +2,7 @@
 // With one query vector per image the "attention" collapses to vector algebra, so nothing of size n x n or n x C x C is formed:
 //     ls   = LangProject(l)                                  (lavt_lang_project)
 //     xm   = relu(Linear(ls * x))                            (lavt_pwam_mul_norm trick + tcgen05 GEMM with ReLU epilogue)
-//     q    = Wq ls + bq ;  u_c = Wc^T q, k_c = bc . q ;  u_d = Wd^T q, k_d = bd . q                 gacd_vec_kernel (per image)
+//     q    = Wq ls + bq ;  u_c = Wc^T q, k_c = bc . q ;  u_d = Wd^T q, k_d = bd . q                 gacd_query_kernel, gacd_vec_kernel
 //     s_c[n] = (xm[n] . u_c + k_c) C^-0.5 ,  s_d[n] likewise; per-block softmax partials of s_c       gacd_scores_kernel
 //     xbar = sum_n softmax(s_c)[n] xm[n] ;  f_col = Wv xbar + bv     (sum_n A_c = 1 folds value's bias)  gacd_finish_kernel
 //     out[n] = xm[n] + sigmoid(s_d[n]) f_col                                                             gacd_apply_kernel
@@ -11,38 +11,58 @@
 
 namespace lavt {
 
-__global__ void __launch_bounds__(256) gacd_vec_kernel(const float* __restrict__ stats, const float* __restrict__ wq, const float* __restrict__ bq,
-                                                       const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ wd,
-                                                       const float* __restrict__ bd, float* __restrict__ u, float* __restrict__ k0, int C) {
-  extern __shared__ float gv_sm[];          // ls[C], q[C]
-  float* ls = gv_sm;
-  float* q = gv_sm + C;
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) ls[c] = -stats[(static_cast<long long>(b) * 2) * C + c];   // lang_project stores -ls
+// q[b, o] = Wq[o, :] . ls[b] + bq[o]: one warp per output row, 8 rows per CTA, grid (C / 8, B).  (These per-image mat-vecs ran in one CTA
+// per image at first: 0.5 ms per launch at C = 1024, profiles/r1_ncu_launches_image_gacd.txt.)
+__global__ void __launch_bounds__(256) gacd_query_kernel(const float* __restrict__ stats, const float* __restrict__ wq, const float* __restrict__ bq,
+                                                         float* __restrict__ q, int C) {
+  extern __shared__ float gv_sm[];          // ls[C]
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) gv_sm[c] = -stats[(static_cast<long long>(b) * 2) * C + c];   // lang_project stores -ls
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < C; o += nw) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wq + static_cast<long long>(o) * C + c), ls[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) q[o] = acc + bq[o];
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= C) return;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wq + static_cast<long long>(o) * C + c), gv_sm[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) q[static_cast<long long>(b) * C + o] = acc + bq[o];
+}
+
+// u_c = Wc^T q, u_d = Wd^T q (column sums: thread x = column, thread y = one eighth of the rows), k_c = bc . q, k_d = bd . q.
+// grid (C / 32, B), block (32, 8)
+__global__ void __launch_bounds__(256) gacd_vec_kernel(const float* __restrict__ q, const float* __restrict__ wc, const float* __restrict__ bc,
+                                                       const float* __restrict__ wd, const float* __restrict__ bd, float* __restrict__ u,
+                                                       float* __restrict__ k0, int C) {
+  extern __shared__ float gv_sm[];          // q[C], part[2][8][32]
+  float* qs = gv_sm;
+  float* part = gv_sm + C;
+  const int b = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  for (int c = tid; c < C; c += 256) qs[c] = q[static_cast<long long>(b) * C + c];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float ac = 0.f, ad = 0.f;
-    for (int o = 0; o < C; ++o) {
-      ac = fmaf(__ldg(wc + static_cast<long long>(o) * C + c), q[o], ac);
-      ad = fmaf(__ldg(wd + static_cast<long long>(o) * C + c), q[o], ad);
+  const int c = blockIdx.x * 32 + tx;
+  float ac = 0.f, ad = 0.f;
+  if (c < C) {
+    for (int o = ty; o < C; o += 8) {
+      ac = fmaf(__ldg(wc + static_cast<long long>(o) * C + c), qs[o], ac);
+      ad = fmaf(__ldg(wd + static_cast<long long>(o) * C + c), qs[o], ad);
     }
-    u[(static_cast<long long>(b) * 2) * C + c] = ac;
-    u[(static_cast<long long>(b) * 2 + 1) * C + c] = ad;
   }
-  if (warp == 0) {
+  part[ty * 32 + tx] = ac;
+  part[256 + ty * 32 + tx] = ad;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float sc = 0.f, sd = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) { sc += part[y * 32 + tx]; sd += part[256 + y * 32 + tx]; }
+    u[(static_cast<long long>(b) * 2) * C + c] = sc;
+    u[(static_cast<long long>(b) * 2 + 1) * C + c] = sd;
+  }
+  if (blockIdx.x == 0 && ty == 1) {
     float kc = 0.f, kd = 0.f;
-    for (int o = lane; o < C; o += 32) { kc = fmaf(bc[o], q[o], kc); kd = fmaf(bd[o], q[o], kd); }
+    for (int o = tx; o < C; o += 32) { kc = fmaf(bc[o], qs[o], kc); kd = fmaf(bd[o], qs[o], kd); }
     kc = warp_sum(kc);
     kd = warp_sum(kd);
-    if (lane == 0) { k0[b * 2] = kc; k0[b * 2 + 1] = kd; }
+    if (tx == 0) { k0[b * 2] = kc; k0[b * 2 + 1] = kd; }
   }
 }
 
@@ -120,12 +140,12 @@ __global__ void __launch_bounds__(256) gacd_scores_kernel(const float* __restric
   }
 }
 
-// grid B: merge the block partials, f_col = Wv xbar + bv
+// grid (C / 8, B): every CTA merges the block partials into xbar (chunks * C L2 reads), then one warp per row of f_col = Wv xbar + bv
 __global__ void __launch_bounds__(256) gacd_finish_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ px,
                                                           const float* __restrict__ wv, const float* __restrict__ bv, float* __restrict__ fcol,
                                                           int chunks, int C) {
   extern __shared__ float gf_sm[];            // xbar[C]
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   float M = -INFINITY;
   for (int k = 0; k < chunks; ++k) M = fmaxf(M, pm[b * chunks + k]);
   float S = 0.f;
@@ -136,13 +156,13 @@ __global__ void __launch_bounds__(256) gacd_finish_kernel(const float* __restric
     gf_sm[c] = a / S;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < C; o += nw) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wv + static_cast<long long>(o) * C + c), gf_sm[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) fcol[static_cast<long long>(b) * C + o] = acc + bv[o];
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= C) return;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wv + static_cast<long long>(o) * C + c), gf_sm[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) fcol[static_cast<long long>(b) * C + o] = acc + bv[o];
 }
 
 __global__ void __launch_bounds__(256) gacd_apply_kernel(const float4* __restrict__ xm, const float* __restrict__ scores, const float* __restrict__ fcol,
@@ -170,7 +190,7 @@ static inline long long al4(long long v) { return (v + 3) / 4 * 4; }
 extern "C" int64_t lavt_gacd_workspace_floats(int32_t B, int64_t n, int32_t C) {
   const int64_t chunks = (n + GACD_ROWS - 1) / GACD_ROWS;
   // every segment starts on a 16-byte boundary (float4 reads of the partial sums / f_col): sizes rounded up to 4 floats
-  return al4(1LL * B * 2 * C) + al4(2LL * B) + al4(2LL * B * n) + 2 * al4(1LL * B * chunks) + al4(1LL * B * chunks * C) + al4(1LL * B * C);
+  return al4(1LL * B * 2 * C) + al4(2LL * B) + al4(2LL * B * n) + 2 * al4(1LL * B * chunks) + al4(1LL * B * chunks * C) + 2 * al4(1LL * B * C);
 }
 
 // Everything of GA-CD after mm_gen: xm fp32 [B,n,C] -> out (fp32 and / or bf16) [B,n,C]
@@ -188,7 +208,11 @@ extern "C" int lavt_gacd_fuse(const float* xm, const float* lang_stats, const fl
   float* ps = pm + al4(1LL * B * chunks);
   float* px = ps + al4(1LL * B * chunks);
   float* fcol = px + al4(1LL * B * chunks * C);
-  gacd_vec_kernel<<<B, 256, 2 * C * sizeof(float), st>>>(lang_stats, wq, bq, wc, bc, wd, bd, u, k0, C);
+  float* q = fcol + al4(1LL * B * C);
+  LAVT_REQUIRE(B < 65536, "gacd: batch %d too large", B);
+  gacd_query_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), st>>>(lang_stats, wq, bq, q, C);
+  LAVT_LAUNCH_CHECK("gacd_query_kernel");
+  gacd_vec_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), (C + 512) * sizeof(float), st>>>(q, wc, bc, wd, bd, u, k0, C);
   LAVT_LAUNCH_CHECK("gacd_vec_kernel");
   const size_t smem = (GACD_ROWS + 8 + 8 * static_cast<size_t>(C)) * sizeof(float);
   static bool configured = false;
@@ -198,7 +222,7 @@ extern "C" int lavt_gacd_fuse(const float* xm, const float* lang_stats, const fl
   }
   gacd_scores_kernel<<<dim3(chunks, B), 256, smem, st>>>(xm, u, k0, scores, pm, ps, px, static_cast<int>(n), C, 1.0f / sqrtf(static_cast<float>(C)));
   LAVT_LAUNCH_CHECK("gacd_scores_kernel");
-  gacd_finish_kernel<<<B, 256, C * sizeof(float), st>>>(pm, ps, px, wv, bv, fcol, chunks, C);
+  gacd_finish_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), st>>>(pm, ps, px, wv, bv, fcol, chunks, C);
   LAVT_LAUNCH_CHECK("gacd_finish_kernel");
   const long long total4 = 1LL * B * n * (C / 4);
   gacd_apply_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(xm), scores, fcol,

@@ -136,50 +136,65 @@ __global__ void __launch_bounds__(256) pwam_core_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------------------------------------------------------
 // LangProject (reference lib/video_swin_transformer.py:1012-1039, the --fuse simple ablation): per clip, masked mean of the word
-// features -> Linear(768 -> C) -> ReLU -> Linear(C -> C).  One CTA per clip; the result is written NEGATED as the "mean" row of an
-// InstanceNorm statistics block (mean = -lang, rstd = 1) so that pwam_mul over an all-zero lang_pre tensor yields vis * lang.
-__global__ void __launch_bounds__(256) lang_project_kernel(const float* __restrict__ l, const float* __restrict__ mask,
-                                                           const float* __restrict__ w0, const float* __restrict__ b0,
-                                                           const float* __restrict__ w2, const float* __restrict__ b2,
-                                                           float* __restrict__ stats, int Nl, int Lin, int C) {
-  extern __shared__ float lp_sm[];      // [Lin] pooled sentence vector, [C] hidden
-  float* pooled = lp_sm;
-  float* hid = lp_sm + Lin;
-  const int b = blockIdx.x;
+// features -> Linear(768 -> C) -> ReLU -> Linear(C -> C).  The result is written NEGATED as the "mean" row of an InstanceNorm
+// statistics block (mean = -lang, rstd = 1) so that pwam_mul over an all-zero lang_pre tensor yields vis * lang.
+// Two mat-vec launches with one warp per output row and 8 rows per CTA, grid (C / 8, B) (a single CTA per clip took 0.27 ms at C = 1024:
+// profiles/r1_ncu_launches_image_gacd.txt); the hidden vector travels in the block's second row, which the second launch's successor
+// then sets to ones.
+__global__ void __launch_bounds__(256) lang_project_hidden_kernel(const float* __restrict__ l, const float* __restrict__ mask,
+                                                                  const float* __restrict__ w0, const float* __restrict__ b0,
+                                                                  float* __restrict__ stats, int Nl, int Lin, int C) {
+  extern __shared__ float lp_sm[];      // [Lin] pooled sentence vector (recomputed by every CTA: Lin * Nl L2 reads)
+  const int b = blockIdx.y;
   float cnt = 0.f;
   for (int j = 0; j < Nl; ++j) cnt += mask[b * Nl + j];
   for (int i = threadIdx.x; i < Lin; i += blockDim.x) {
     float s = 0.f;
     for (int j = 0; j < Nl; ++j) s += l[(static_cast<long long>(b) * Lin + i) * Nl + j] * mask[b * Nl + j];
-    pooled[i] = s / cnt;
+    lp_sm[i] = s / cnt;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nw) {
-    float acc = 0.f;
-    for (int i = lane; i < Lin; i += 32) acc = fmaf(__ldg(w0 + static_cast<long long>(c) * Lin + i), pooled[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) hid[c] = fmaxf(acc + b0[c], 0.f);
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int i = lane; i < Lin; i += 32) acc = fmaf(__ldg(w0 + static_cast<long long>(c) * Lin + i), lp_sm[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) stats[(static_cast<long long>(b) * 2 + 1) * C + c] = fmaxf(acc + b0[c], 0.f);      // hidden vector, parked in row 1
+}
+
+__global__ void __launch_bounds__(256) lang_project_out_kernel(const float* __restrict__ w2, const float* __restrict__ b2,
+                                                               float* __restrict__ stats, int C) {
+  extern __shared__ float lp_sm[];      // [C] hidden
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) lp_sm[i] = stats[(static_cast<long long>(b) * 2 + 1) * C + i];
   __syncthreads();
-  for (int c = warp; c < C; c += nw) {
-    float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * C + i), hid[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      stats[(static_cast<long long>(b) * 2) * C + c] = -(acc + b2[c]);
-      stats[(static_cast<long long>(b) * 2 + 1) * C + c] = 1.0f;
-    }
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * C + i), lp_sm[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) stats[(static_cast<long long>(b) * 2) * C + c] = -(acc + b2[c]);
+}
+
+__global__ void __launch_bounds__(256) lang_project_ones_kernel(float* __restrict__ stats, int C, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over B * C
+  if (i < total) stats[(static_cast<long long>(i / C) * 2 + 1) * C + i % C] = 1.0f;
 }
 
 int lang_project_dispatch(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* b2,
                           float* stats, int B, int Nl, int Lin, int C, cudaStream_t st) {
-  LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0, "lang_project: empty input");
-  const size_t smem = static_cast<size_t>(Lin + C) * sizeof(float);
-  LAVT_REQUIRE(smem <= 48 * 1024, "lang_project: widths %d + %d too large", Lin, C);
-  lang_project_kernel<<<B, 256, smem, st>>>(l, mask, w0, b0, w2, b2, stats, Nl, Lin, C);
-  LAVT_LAUNCH_CHECK("lang_project_kernel");
+  LAVT_REQUIRE(B > 0 && B < 65536 && Nl > 0 && Lin > 0 && C > 0, "lang_project: empty input");
+  LAVT_REQUIRE(static_cast<size_t>(Lin) * sizeof(float) <= 48 * 1024 && static_cast<size_t>(C) * sizeof(float) <= 48 * 1024,
+               "lang_project: widths %d / %d too large", Lin, C);
+  const dim3 grid((C + 7) / 8, B);
+  lang_project_hidden_kernel<<<grid, 256, static_cast<size_t>(Lin) * sizeof(float), st>>>(l, mask, w0, b0, stats, Nl, Lin, C);
+  LAVT_LAUNCH_CHECK("lang_project_hidden_kernel");
+  lang_project_out_kernel<<<grid, 256, static_cast<size_t>(C) * sizeof(float), st>>>(w2, b2, stats, C);
+  LAVT_LAUNCH_CHECK("lang_project_out_kernel");
+  lang_project_ones_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(stats, C, B * C);
+  LAVT_LAUNCH_CHECK("lang_project_ones_kernel");
   return LAVT_OK;
 }
 

@@ -181,7 +181,7 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
         K.gemm_bf16(a2.view(N_, C), wprep("mm_w", fusion.project_mm[0]), bias=fusion.project_mm[0].bias.detach(), act=K.ACT_GELU, out_f32=r32,
                     out_bf16=rb)
-        _count(4)
+        _count(6)
         if res_gate is not None:
             g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
             g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
@@ -256,7 +256,7 @@ def gacd_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     K.gacd_fuse(xm, stats, _f32(fusion.query.weight), _f32(fusion.query.bias), _f32(fusion.key_c.weight), _f32(fusion.key_c.bias),
                 _f32(fusion.key_d.weight), _f32(fusion.key_d.bias), _f32(fusion.value.weight), _f32(fusion.value.bias),
                 lambda nfl: ws.get("gacd_ws", (nfl,), torch.float32, dev), out_f32=r32, out_bf16=rb)
-    _count(7)
+    _count(10)
     if res_gate is not None:
         g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
         g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
