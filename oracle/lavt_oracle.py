@@ -40,6 +40,8 @@ class OracleConfig:
     clamp_window: bool = True                     # 3-D backbone clamps (get_window_size); 2-D never does
     video: bool = True
     gate_act: str = "tanh"
+    lazy_pred: bool = False                       # --lazy_pred: stage outputs = features BEFORE fusion (V_i, :556-558), stages 1-3 only
+                                                  # (lib/segmentation.py:184-185); the decoder stops at 1/8 scale (lib/mask_predictor.py:32,77)
     hs: bool = False                              # --hs: stage output = gated x (E_i) instead of the PWAM residual (:579-587)
     bcam: bool = False                            # --bcam (2-D image backbone, 480 x 480 inputs only): BCAM fusion of lib/bcam.py:8-75
     efn: bool = False                             # --efn (2-D image backbone): EFN fusion of lib/bcam.py:160-269 (co-attention over pooled pixels)
@@ -374,6 +376,7 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             if capture is not None:
                 capture[f"s{s}b{i}"] = x
         B, D, H, W, C = x.shape
+        x_pre = x                                                          # V_i (:556-558)
         if cfg.bcam:
             r = bcam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
         elif cfg.gacd:
@@ -390,9 +393,10 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             x = x + r.reshape(B, D, H, W, C)
         elif cfg.version == "default" and pre + "res_gate.0.weight" in sd:
             x = language_gate(x.reshape(B, D * H * W, C), r, sd, pre + "res_gate.", cfg.gate_act).reshape(B, D, H, W, C)
-        stage_out = x if cfg.hs else r.reshape(B, D, H, W, C)
-        o = F.layer_norm(stage_out, (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)
-        outs.append(o.permute(0, 1, 4, 2, 3).reshape(B * D, C, H, W))      # (:869-874)
+        stage_out = x if cfg.hs else (x_pre if cfg.lazy_pred else r.reshape(B, D, H, W, C))          # (:579-587)
+        if f"backbone.norm{s}.weight" in sd:                               # out_indices (lazy_pred: 1, 2, 3)
+            o = F.layer_norm(stage_out, (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)
+            outs.append(o.permute(0, 1, 4, 2, 3).reshape(B * D, C, H, W))      # (:869-874)
         if pre + "downsample.reduction.weight" in sd:
             x = patch_merging(x, sd, pre + "downsample.")
             if capture is not None:
@@ -439,8 +443,9 @@ def decoder_forward(sd, x_c4, x_c3, x_c2, x_c1, capture: Optional[dict] = None, 
     y = q(_cbr(_cbr(y, sd, "conv1_4", "bn1_4", tb, eb), sd, "conv2_4", "bn2_4", tb, eb))
     y = torch.cat([_up_to(y, x_c2), x_c2], 1)
     y = q(_cbr(_cbr(y, sd, "conv1_3", "bn1_3", tb, eb), sd, "conv2_3", "bn2_3", tb, eb))
-    y = torch.cat([_up_to(y, x_c1), x_c1], 1)
-    y = q(_cbr(_cbr(y, sd, "conv1_2", "bn1_2", tb, eb), sd, "conv2_2", "bn2_2", tb, eb))
+    if x_c1 is not None:                       # --lazy_pred stops at 1/8 scale (lib/mask_predictor.py:77)
+        y = torch.cat([_up_to(y, x_c1), x_c1], 1)
+        y = q(_cbr(_cbr(y, sd, "conv1_2", "bn1_2", tb, eb), sd, "conv2_2", "bn2_2", tb, eb))
     if capture is not None:
         capture["dec_feat"] = y
     return F.conv2d(y, sd["classifier.conv1_1.weight"], sd["classifier.conv1_1.bias"])
@@ -458,7 +463,8 @@ def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Ten
     if cfg.video:
         x = x.permute(0, 2, 1, 3, 4)
     size = x.shape[-2:]
-    c1, c2, c3, c4 = backbone_forward(sd, cfg, x, l_feats, l_mask.unsqueeze(-1), capture)
+    feats = backbone_forward(sd, cfg, x, l_feats, l_mask.unsqueeze(-1), capture)
+    c1, c2, c3, c4 = feats if len(feats) == 4 else (None, *feats)        # lib/_utils.py:55-59, 101-105
     if capture is not None:
         capture.update(c1=c1, c2=c2, c3=c3, c4=c4)
     logits = decoder_forward(sd, c4, c3, c2, c1, capture, train_bn)
@@ -547,9 +553,11 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
         if s < len(cfg.depths) - 1:
             sd[pre + "downsample.reduction.weight"] = tn(2 * C, 4 * C)
             ln(pre + "downsample.norm", 4 * C)
-        ln(f"backbone.norm{s}", C)
+        if s > 0 or not cfg.lazy_pred:
+            ln(f"backbone.norm{s}", C)
     hid = 8 * C0 // 2
-    for name, cin in (("1_4", 8 * C0 + 4 * C0), ("2_4", hid), ("1_3", hid + 2 * C0), ("2_3", hid), ("1_2", hid + C0), ("2_2", hid)):
+    levels = (("1_4", 8 * C0 + 4 * C0), ("2_4", hid), ("1_3", hid + 2 * C0), ("2_3", hid), ("1_2", hid + C0), ("2_2", hid))
+    for name, cin in (levels[:4] if cfg.lazy_pred else levels):
         sd[f"classifier.conv{name}.weight"] = conv_default(hid, cin, 3, 3)[0]
         sd[f"classifier.bn{name}.weight"] = 1 + 0.1 * torch.randn(hid, generator=g)
         sd[f"classifier.bn{name}.bias"] = 0.1 * torch.randn(hid, generator=g)

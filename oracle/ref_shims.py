@@ -123,7 +123,7 @@ SEP_T_PWAM_FLAGS = ("--sep_t_pwam", "--conv3d_kernel_size_t", "3-3-3", "--conv3d
 
 
 def build_reference_backbone_small(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32), window=(8, 7, 7),
-                                   mha=(1, 1, 1, 1), seed=0, extra=()):
+                                   mha=(1, 1, 1, 1), seed=0, extra=(), out_indices=(0, 1, 2, 3)):
     """A shallow reference video backbone + decoder for fast parity runs (same classes, fewer blocks)."""
     install_shims()
     from lib.video_swin_transformer import MultiModalSwinTransformer3D
@@ -131,7 +131,7 @@ def build_reference_backbone_small(embed_dim=128, depths=(2, 2, 2, 2), num_heads
     args = reference_args(["--model", "lavt_video", *extra])
     torch.manual_seed(seed)
     bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=embed_dim, depths=list(depths), num_heads=list(num_heads),
-                                     window_size=window, drop_path_rate=0.0, patch_norm=True, out_indices=(0, 1, 2, 3),
+                                     window_size=window, drop_path_rate=0.0, patch_norm=True, out_indices=tuple(out_indices),
                                      use_checkpoint=False, num_heads_fusion=list(mha), fusion_drop=0.0, args=args)
     bb.init_weights()
     dec = SimpleDecoding(8 * embed_dim, args)

@@ -266,3 +266,27 @@ def test_efn_image_backbone_matches_reference():
     # amplifies fp32 summation-order noise (the restatement contracts (B, n, C) rows, the reference (B, C, n) planes): 2e-3 on O(1) values
     for i, (a, b) in enumerate(zip(got, ref)):
         assert a.shape == b.shape and (a - b).abs().max().item() < 2e-3, (i, (a - b).abs().max().item())
+
+
+def test_lazy_pred_model_matches_reference():
+    """--lazy_pred (reference lib/video_swin_transformer.py:556-558, 586-587; lib/mask_predictor.py:32, 77; lib/_utils.py:101-107): stage
+    outputs are the features BEFORE fusion at stages 1-3 and the decoder stops at 1/8 scale; whole video model without the text encoder."""
+    import torch.nn.functional as F
+    bb, dec, _ = ref_shims.build_reference_backbone_small(window=(8, 7, 7), depths=(2, 2, 2, 2), extra=("--lazy_pred",), out_indices=(1, 2, 3))
+    _randomise_norms([bb, dec])
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), lazy_pred=True)
+    mine = O.random_state_dict(cfg)
+    benign = ("relative_position_index", "num_batches_tracked")          # buffers the oracle derives in closed form / does not need
+    assert set(mine) == {k for k in sd if not k.endswith(benign)} and all(mine[k].shape == sd[k].shape for k in mine)
+    x, l, m = O.synthetic_inputs(1, 4, 64, 64, Nl=11)
+    xv = x.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        c2, c3, c4 = bb(xv, l, m.unsqueeze(-1))
+        ref = F.interpolate(dec(c4, c3, c2, None), size=(64, 64), mode="bilinear", align_corners=True)
+        feats = O.backbone_forward(sd, cfg, xv, l, m.unsqueeze(-1))
+        got = O.model_forward(sd, cfg, x, l, m)
+    assert len(feats) == 3
+    for i, (a, b) in enumerate(zip(feats, (c2, c3, c4))):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 2e-4, f"stage {i + 1}"
+    assert got.shape == ref.shape == (4, 2, 64, 64) and (got - ref).abs().max().item() < 2e-4
