@@ -27,6 +27,7 @@ _STRUCTURE_FLAGS = [
     ("--lg_act_layer", str, "tanh", "LanguageGate activation (2-D backbone)"),
     ("--att_norm_layer_type", str, "IN", "PWAM attention norm (2-D backbone)"),
     ("--hs", "store_true", False, "stage outputs = gated features E_i instead of the PWAM residuals"),
+    ("--lazy_pred", "store_true", False, "stage outputs = features before fusion at stages 1-3; decoder stops at 1/8 scale (inference)"),
     ("--gacd", "store_true", False, "2-D image backbone: GA-CD fusion (lib/bcam.py) instead of PWAM"),
     ("--bcam", "store_true", False, "2-D image backbone: BCAM fusion (lib/bcam.py) instead of PWAM; 480 x 480 inputs only, inference"),
     ("--efn", "store_true", False, "2-D image backbone: EFN fusion (lib/bcam.py) instead of PWAM; square feature maps, inference"),
@@ -36,7 +37,7 @@ _STRUCTURE_FLAGS = [
     ("--w_t3x3_s1x1", "store_true", False, "SepTPWAM: W = IN(conv_t) + IN(conv_s)"),
     ("--mm_t3x3_s1x1", "store_true", False, "SepTPWAM: project_mm = GELU(conv_t) + GELU(conv_s)"),
 ]
-_REJECTED_BOOL_FLAGS = ["lazy_pred", "ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam",
+_REJECTED_BOOL_FLAGS = ["ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam",
                         "sep_t_pwam_inner", "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "interpolate_before_seg", "seg_last"]
 
 

@@ -584,17 +584,21 @@ def _cbr(x_nhwc: torch.Tensor, dec, conv_name: str, bn_name: str, out: torch.Ten
 
 def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: torch.Tensor, ws: Workspace,
                  logits_nchw: Optional[torch.Tensor], feats: Optional[list] = None) -> torch.Tensor:
-    """c_i bf16 NHWC [n_img, H_i, W_i, C_i]; optional logits_nchw fp32 [n_img, 2, H_1, W_1].
+    """c_i bf16 NHWC [n_img, H_i, W_i, C_i] (c1 = None under --lazy_pred); optional logits_nchw fp32 [n_img, 2, H_1, W_1].
     Returns the low-resolution logits as an NHWC fp32 workspace view [n_img, H_1, W_1, 2].
     ``feats``: if a list, the three top-down maps after conv2_4 / conv2_3 / conv2_2 (NHWC bf16 workspace views) are
     appended (SimpleDecoding.forward_feats, lib/mask_predictor.py:102-150)."""
-    dev = c1.device
-    n_img = c1.shape[0]
+    dev = c4.device
+    n_img = c4.shape[0]
     hid = dec.conv1_4.weight.shape[0]
     y = c4
+    if (c1 is None) != bool(getattr(dec, "lazy_pred", False)):
+        raise K.LavtError("decoder: the 1/4-scale map is omitted exactly when the decoder was built with --lazy_pred")
     for skip, (ca, ba, cb, bb) in ((c3, ("conv1_4", "bn1_4", "conv2_4", "bn2_4")),
                                    (c2, ("conv1_3", "bn1_3", "conv2_3", "bn2_3")),
                                    (c1, ("conv1_2", "bn1_2", "conv2_2", "bn2_2"))):
+        if skip is None:                      # --lazy_pred: no 1/4-scale level (reference lib/mask_predictor.py:77)
+            continue
         _, H, W, Cs = skip.shape
         if y.shape[1] > H or y.shape[2] > W:
             raise K.LavtError("decoder: coarser map is larger than the skip connection")

@@ -57,11 +57,11 @@ class _Segmenter(nn.Module):
         """x5 (B,3,T,H,W) strided view; l_feats (B,768,Nl); l_mask (B,Nl[,1])."""
         _, nhwc = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=False, want_nhwc_bf16=True,
                                     lang_ready=lang_ready)
-        c1, c2, c3, c4 = nhwc
-        ws = E.workspace(c1.device)
-        lg = E.decoder_nhwc(self.classifier, c4, c3, c2, c1, ws, None)       # (n_img, H/4, W/4, 2) NHWC fp32
+        c1, c2, c3, c4 = nhwc if len(nhwc) == 4 else (None, *nhwc)              # --lazy_pred: three maps (lib/_utils.py:101-105)
+        ws = E.workspace(c4.device)
+        lg = E.decoder_nhwc(self.classifier, c4, c3, c2, c1, ws, None)       # (n_img, H/4, W/4, 2) NHWC fp32 (H/8 under --lazy_pred)
         out = torch.empty(lg.shape[0], 2, size[0], size[1], device=lg.device, dtype=torch.float32)
-        K.upsample_logits(lg, out)                                             # bilinear x4 + NCHW (lib/_utils.py:106)
+        K.upsample_logits(lg, out)                                             # bilinear x4 (x8) + NCHW (lib/_utils.py:106)
         E._count(1)
         return out
 
@@ -89,7 +89,7 @@ class LAVTOne(_Segmenter):
         super().__init__()
         self.backbone, self.classifier = backbone, classifier
         self.text_encoder = _build_text_encoder(args)
-        self.lazy_pred = False
+        self.lazy_pred = bool(getattr(args, "lazy_pred", False))
 
     def forward(self, x, text, l_mask):
         E.require_cuda(x, "x")
@@ -109,7 +109,7 @@ class LAVTVideo(_Segmenter):
         super().__init__()
         self.backbone, self.classifier = backbone, classifier
         self.text_encoder = _build_text_encoder(args)
-        self.lazy_pred = False
+        self.lazy_pred = bool(getattr(args, "lazy_pred", False))
         self.seg_last = False
 
     def encode_text(self, text, l_mask):

@@ -174,7 +174,13 @@ class MMBasicLayer(V.MMBasicLayer):
         ws = E.workspace(x.device)
         xf = x.detach().float().reshape(B * L, C).contiguous().clone()
         r = torch.empty(B * L, C, device=x.device, dtype=torch.float32)
-        nxt, H2, W2 = self.run(xf, B, 1, H, W, V._lang(l), V._mask(l_mask), ws, r)
+        v_i = torch.empty_like(r) if self.lazy_pred else None           # V_i (reference :662-664); API-compat copy, not the hot path
+        nxt, H2, W2 = self.run(xf, B, 1, H, W, V._lang(l), V._mask(l_mask), ws, r,
+                               pre_fusion=(lambda t: v_i.copy_(t)) if self.lazy_pred else None)
+        if self.hs:
+            r = xf                          # the gated stream (reference :678-681)
+        elif self.lazy_pred:
+            r = v_i
         return r.view(B, L, C), H, W, nxt.view(B, H2 * W2, -1).clone(), H2, W2
 
 

@@ -16,34 +16,35 @@ from .. import engine as E
 class SimpleDecoding(nn.Module):
     def __init__(self, c4_dims, args=None, factor=2):
         super().__init__()
-        for flag in ("lazy_pred", "interpolate_before_seg", "seg_last"):
+        for flag in ("interpolate_before_seg", "seg_last"):
             if getattr(args, flag, False):
                 raise NotImplementedError(f"--{flag} is not implemented on the B200 path yet")
-        self.lazy_pred = False
+        self.lazy_pred = bool(getattr(args, "lazy_pred", False))      # no 1/4-scale level (reference :32, :77): logits at 1/8 scale
         hidden = c4_dims // factor
         c4, c3, c2, c1 = c4_dims, c4_dims // factor, c4_dims // factor ** 2, c4_dims // factor ** 3
-        for name, cin in (("1_4", c4 + c3), ("2_4", hidden), ("1_3", hidden + c2), ("2_3", hidden),
-                          ("1_2", hidden + c1), ("2_2", hidden)):
+        levels = (("1_4", c4 + c3), ("2_4", hidden), ("1_3", hidden + c2), ("2_3", hidden), ("1_2", hidden + c1), ("2_2", hidden))
+        for name, cin in (levels[:4] if self.lazy_pred else levels):
             setattr(self, "conv" + name, nn.Conv2d(cin, hidden, 3, padding=1, bias=False))
             setattr(self, "bn" + name, nn.BatchNorm2d(hidden))
         self.conv1_1 = nn.Conv2d(hidden, 2, 1)
         self.prepared = E.PreparedWeights()
 
     def run_nhwc(self, c4, c3, c2, c1) -> torch.Tensor:
-        """NHWC bf16 maps -> logits (n_img, 2, H1, W1) fp32 NCHW."""
-        n_img, H, W, _ = c1.shape
-        logits = torch.empty(n_img, 2, H, W, device=c1.device, dtype=torch.float32)
-        E.decoder_nhwc(self, c4, c3, c2, c1, E.workspace(c1.device), logits)
+        """NHWC bf16 maps -> logits (n_img, 2, H1, W1) fp32 NCHW (H2, W2 and c1 = None under --lazy_pred)."""
+        fine = c2 if self.lazy_pred else c1
+        n_img, H, W, _ = fine.shape
+        logits = torch.empty(n_img, 2, H, W, device=fine.device, dtype=torch.float32)
+        E.decoder_nhwc(self, c4, c3, c2, None if self.lazy_pred else c1, E.workspace(fine.device), logits)
         return logits
 
     def forward_feats(self, x_c4, x_c3, x_c2, x_c1):
         """Reference lib/mask_predictor.py:102-150: (logits, [x_c4, Y3, Y2, Y1]) with the top-down maps after each
         conv2_* + BN + ReLU as NCHW fp32 (API-compat copies of the NHWC bf16 buffers; not a hot path)."""
         maps = self._to_nhwc(x_c4, x_c3, x_c2, x_c1)
-        n_img, H, W, _ = maps[3].shape
-        logits = torch.empty(n_img, 2, H, W, device=x_c1.device, dtype=torch.float32)
+        n_img, H, W, _ = (maps[2] if self.lazy_pred else maps[3]).shape
+        logits = torch.empty(n_img, 2, H, W, device=x_c4.device, dtype=torch.float32)
         inter = []
-        E.decoder_nhwc(self, *maps, E.workspace(x_c1.device), logits, feats=inter)
+        E.decoder_nhwc(self, *maps, E.workspace(x_c4.device), logits, feats=inter)
         return logits, [x_c4] + [t.permute(0, 3, 1, 2).float().contiguous() for t in inter]
 
     def forward(self, x_c4, x_c3, x_c2, x_c1) -> torch.Tensor:
@@ -51,12 +52,19 @@ class SimpleDecoding(nn.Module):
         return self.run_nhwc(*self._to_nhwc(x_c4, x_c3, x_c2, x_c1))
 
     def _to_nhwc(self, x_c4, x_c3, x_c2, x_c1):
-        maps = []
+        if self.lazy_pred:
+            x_c1 = None                     # the reference ignores it too (lib/_utils.py:57-58, 103-104 pass None)
+        elif x_c1 is None:
+            raise K.LavtError("SimpleDecoding: x_c1 is required unless the model was built with --lazy_pred")
         for t in (x_c4, x_c3, x_c2, x_c1):
-            E.require_cuda(t, "feature map")
-        ws = E.workspace(x_c1.device)
+            if t is not None:
+                E.require_cuda(t, "feature map")
+        maps = []
+        ws = E.workspace(x_c4.device)
         for i, t in enumerate((x_c4, x_c3, x_c2, x_c1)):
-            E.require_cuda(t, "feature map")
+            if t is None:
+                maps.append(None)
+                continue
             n, C, H, W = t.shape
             t = t.detach().float().contiguous()
             o = ws.get("dec_in_%d" % i, (n, H, W, C), torch.bfloat16, t.device)

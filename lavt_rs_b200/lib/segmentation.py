@@ -26,6 +26,11 @@ def _fusion_heads(args):
     return [int(a) for a in mha.split("-")] if mha else [1, 1, 1, 1]
 
 
+def _out_indices(args):
+    """--lazy_pred drops the 1/4-scale stage from the decoder's inputs (reference :116-118, :183-185)."""
+    return (1, 2, 3) if getattr(args, "lazy_pred", False) else (0, 1, 2, 3)
+
+
 def _swin_cfg(args, kind):
     st = getattr(args, "swin_type", "base")
     if st not in _SWIN or (kind == "video" and st == "large"):
@@ -43,7 +48,7 @@ def lavt_video(pretrained="", args=None):
     w = 12 if getattr(args, "window12", False) else 7
     backbone = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=embed_dim, depths=depths, num_heads=heads,
                                            window_size=(8, w, w), drop_path_rate=dpr, patch_norm=True,
-                                           out_indices=(0, 1, 2, 3), use_checkpoint=getattr(args, "use_checkpoint", False),
+                                           out_indices=_out_indices(args), use_checkpoint=getattr(args, "use_checkpoint", False),
                                            num_heads_fusion=_fusion_heads(args),
                                            fusion_drop=getattr(args, "fusion_drop", 0.0), args=args)
     backbone.init_weights(pretrained=pretrained if pretrained else None)
@@ -56,7 +61,7 @@ def _image_backbone(pretrained, args):
     embed_dim, depths, heads, dpr = _swin_cfg(args, "image")
     w = 12 if (getattr(args, "window12", False) or "window12" in (pretrained or "")) else 7
     backbone = MultiModalSwinTransformer(embed_dim=embed_dim, depths=depths, num_heads=heads, window_size=w,
-                                         drop_path_rate=dpr, patch_norm=True, out_indices=(0, 1, 2, 3),
+                                         drop_path_rate=dpr, patch_norm=True, out_indices=_out_indices(args),
                                          use_checkpoint=False, num_heads_fusion=_fusion_heads(args),
                                          fusion_drop=getattr(args, "fusion_drop", 0.0), args=args)
     backbone.init_weights(pretrained=pretrained if pretrained else None)

@@ -236,7 +236,7 @@ def _mask(l_mask: torch.Tensor) -> torch.Tensor:
 
 
 _UNSUPPORTED_FLAGS = ("ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam", "sep_t_pwam_inner",
-                      "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "lazy_pred")
+                      "sep_seq_t_pwam", "sep_seq_t_pwam_inner")
 
 
 def _ksize(text, default):
@@ -281,6 +281,8 @@ class MMBasicLayer(nn.Module):
                                    norm_layer=norm_layer, use_checkpoint=use_checkpoint)
             for i in range(depth)])
         self.hs = bool(getattr(args, "hs", False))       # stage output = gated x (E_i) instead of the residual (:579-587)
+        # --lazy_pred: stage output = features BEFORE fusion (V_i, :556-558); --hs wins when both are set (x_out is overwritten, :579-581)
+        self.lazy_pred = bool(getattr(args, "lazy_pred", False)) and not self.hs
         self.sep_t_pwam = bool(getattr(args, "sep_t_pwam", False))
         if self.sep_t_pwam:      # reference :470-479
             self.fusion = SepTPWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop,
@@ -304,7 +306,9 @@ class MMBasicLayer(nn.Module):
 
     # -- engine-level stage: works on the flat fp32 residual stream, returns (r fp32 [B*n,C], x_next, dims) --
     def run(self, x: torch.Tensor, B: int, D: int, H: int, W: int, l: torch.Tensor, mask: torch.Tensor, ws: E.Workspace,
-            r_out: torch.Tensor, lang_ready=None):
+            r_out: torch.Tensor, lang_ready=None, pre_fusion=None):
+        """``pre_fusion``: optional callable invoked with the fp32 stream right after the Swin blocks (--lazy_pred reads V_i there,
+        before the LanguageGate updates the stream in place)."""
         dev = x.device
         C = self.dim
         xb = ws.get("stage_xb", (B * D * H * W, C), torch.bfloat16, dev)
@@ -313,6 +317,8 @@ class MMBasicLayer(nn.Module):
         for i, blk in enumerate(self.blocks):
             E.swin_block(x, blk, B, D, H, W, self.window_size, blk.shifted, blk.clamp_window, ws,
                          xb_out=xb if i == self.depth - 1 else None)
+        if pre_fusion is not None:
+            pre_fusion(x)
         if lang_ready is not None:          # first consumer of the language features
             torch.cuda.current_stream().wait_event(lang_ready)
         if self.sep_t_pwam:
@@ -342,7 +348,13 @@ class MMBasicLayer(nn.Module):
         ws = E.workspace(x.device)
         xf = x.detach().float().permute(0, 2, 3, 4, 1).reshape(B * D * H * W, C).contiguous()
         r = torch.empty(B * D * H * W, C, device=x.device, dtype=torch.float32)
-        nxt, H2, W2 = self.run(xf, B, D, H, W, _lang(l), _mask(l_mask), ws, r)
+        v_i = torch.empty_like(r) if self.lazy_pred else None           # V_i (:556-558); API-compat copy, not the hot path
+        nxt, H2, W2 = self.run(xf, B, D, H, W, _lang(l), _mask(l_mask), ws, r,
+                               pre_fusion=(lambda t: v_i.copy_(t)) if self.lazy_pred else None)
+        if self.hs:
+            r = xf                          # the gated stream E_i (:579-581); xf is this call's private copy
+        elif self.lazy_pred:
+            r = v_i
         r5 = r.view(B, D, H, W, C).permute(0, 4, 1, 2, 3)
         n5 = nxt.view(B, D, H2, W2, -1).permute(0, 4, 1, 2, 3).clone()
         return r5, n5
@@ -472,16 +484,14 @@ class MultiModalSwinTransformer3D(nn.Module):
             C = layer.dim
             n = B * D * Hc * Wc
             r = ws.get("stage_r", (n, C), torch.float32, dev)
-            x_next, H2, W2 = layer.run(x, B, D, Hc, Wc, l, mask, ws, r, lang_ready=lang_ready if i == 0 else None)
-            if i in self.out_indices:
+
+            def emit(src, i=i, n=n, C=C, Hc=Hc, Wc=Wc):
                 norm = getattr(self, f"norm{i}")
                 of = ws.get("out_f32", (n, C), torch.float32, dev) if want_nchw else None
                 ob = None
                 if want_nhwc_bf16:
                     ob = ws.get("out_bf16_%d" % i, (B * D, Hc, Wc, C), torch.bfloat16, dev)
-                # stage output: the PWAM residual, or with --hs the gated features (x is not modified by the downsample)
-                K.layernorm_rows(x if layer.hs else r, norm.weight, norm.bias, out_bf16=ob.view(n, C) if ob is not None else None,
-                                 out_f32=of, eps=norm.eps)
+                K.layernorm_rows(src, norm.weight, norm.bias, out_bf16=ob.view(n, C) if ob is not None else None, out_f32=of, eps=norm.eps)
                 E._count(1)
                 if want_nchw:
                     o = torch.empty(B * D, C, Hc, Wc, device=dev, dtype=torch.float32)
@@ -490,6 +500,13 @@ class MultiModalSwinTransformer3D(nn.Module):
                     nchw.append(o)
                 if want_nhwc_bf16:
                     nhwc.append(ob)
+            out_here = i in self.out_indices
+            early = out_here and getattr(layer, "lazy_pred", False)          # V_i must be read before the gate rewrites the stream
+            x_next, H2, W2 = layer.run(x, B, D, Hc, Wc, l, mask, ws, r, lang_ready=lang_ready if i == 0 else None,
+                                       pre_fusion=emit if early else None)
+            if out_here and not early:
+                # stage output: the PWAM residual, or with --hs the gated features (x is not modified by the downsample)
+                emit(x if layer.hs else r)
             x, Hc, Wc = x_next, H2, W2
         return (nchw if want_nchw else None), (nhwc if want_nhwc_bf16 else None)
 

@@ -71,7 +71,7 @@ def test_full_model_state_dict_round_trips_with_reference():
 
 def test_builders_reject_unimplemented_flags():
     from lavt_rs_b200.lib import segmentation
-    for flag in ("--sep_t_pwam", "--lazy_pred"):     # (--sep_t_pwam alone keeps the unsupported 3-1-1 temporal kernel)
+    for flag in ("--sep_t_pwam", "--seg_last"):      # (--sep_t_pwam alone keeps the unsupported 3-1-1 temporal kernel)
         with pytest.raises(NotImplementedError):
             segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "base", flag]))
     # Swin-T / Swin-S widths (96 channels) build: the README's video commands use --swin_type tiny
@@ -92,6 +92,18 @@ def test_bcam_gacd_backbone_state_dicts_match_oracle_contract():
         for k, v in sd.items():
             assert tuple(mine[k].shape) == tuple(v.shape), k
     assert bb.layers[0].fusion.kind == "gacd"
+
+
+def test_lazy_pred_state_dict_matches_oracle_contract():
+    """--lazy_pred (reference lib/segmentation.py:183-185, lib/mask_predictor.py:32): no backbone.norm0, no 1/4-scale decoder level."""
+    from lavt_rs_b200.lib import segmentation
+    m = segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny", "--lazy_pred"]))
+    assert m.backbone.out_indices == (1, 2, 3) and m.lazy_pred and m.classifier.lazy_pred and m.backbone.layers[0].lazy_pred
+    cfg = O.OracleConfig(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), lazy_pred=True)
+    sd = O.random_state_dict(cfg)
+    mine = {k for k in m.state_dict() if not k.startswith("text_encoder.") and not k.endswith(("relative_position_index", "num_batches_tracked"))}
+    assert mine == set(sd)
+    assert "backbone.norm0.weight" not in mine and "classifier.conv1_2.weight" not in mine
 
 
 def test_forward_refuses_cpu_tensors():

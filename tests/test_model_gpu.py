@@ -580,3 +580,48 @@ def test_efn_image_model_end_to_end():
     assert max(errs.values()) < 2e-2, errs
     assert max(stage_errs) < 3e-2, stage_errs
     assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_lazy_pred_video_and_image_models():
+    """--lazy_pred (reference lib/video_swin_transformer.py:556-558 / lib/backbone.py:662-664, lib/mask_predictor.py:77, lib/_utils.py:101-107):
+    features before fusion at stages 1-3 + a decoder that stops at 1/8 scale, through the backbone API (three NCHW maps), the decoder API
+    (x_c1 = None, like the reference) and the fused model path, video and 2-D image, vs the oracle; the layer API returns V_i."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    args = default_args(["--lazy_pred"])
+    for video in (True, False):
+        window = (8, 7, 7) if video else (1, 7, 7)
+        cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=window, clamp_window=video, video=video, lazy_pred=True)
+        sd = O.random_state_dict(cfg, seed=0)
+        kw = dict(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], drop_path_rate=0.0, patch_norm=True, out_indices=(1, 2, 3), args=args)
+        bb = (MultiModalSwinTransformer3D(patch_size=(1, 4, 4), window_size=window, **kw) if video
+              else MultiModalSwinTransformer(window_size=7, num_heads_fusion=[1, 1, 1, 1], **kw))
+        dec = SimpleDecoding(1024, args)
+        load_reference_state_dict(bb, sd, "backbone.")
+        load_reference_state_dict(dec, sd, "classifier.")
+        bb, dec = bb.cuda().eval(), dec.cuda().eval()
+        x, l, m = O.synthetic_inputs(1, 4, 64, 96, Nl=20, video=video)
+        xin = x.permute(0, 2, 1, 3, 4) if video else x
+        cap = {}
+        with torch.no_grad():
+            ref = O.model_forward(sd, cfg, x, l, m, capture=cap)
+            feats = bb(xin.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+            low = dec(feats[2], feats[1], feats[0], None)
+            assert len(feats) == 3 and low.shape[-2:] == (8, 12)
+            for i in range(3):
+                assert rel_l2(feats[i], cap[f"c{i + 2}"]) < 3e-2, (video, i, rel_l2(feats[i], cap[f"c{i + 2}"]))
+            assert rel_l2(low, cap["logits_lowres"]) < 3e-2, (video, rel_l2(low, cap["logits_lowres"]))
+            if not video:
+                got = LAVT(bb, dec).cuda().eval()(x.cuda(), l.cuda(), m.cuda())
+                assert got.shape == ref.shape and rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+                # layer API (reference MMBasicLayer.forward): first return value = the features before fusion
+                xs = torch.randn(1, 12 * 8, 256, generator=torch.Generator().manual_seed(2)).cuda()
+                v_i = bb.layers[1](xs, 8, 12, l.cuda(), m.unsqueeze(-1).cuda())[0]
+                blocks_only = xs.clone().view(1, 1, 8, 12, 256)
+                for blk in bb.layers[1].blocks:
+                    blocks_only = blk(blocks_only)
+                assert rel_l2(v_i, blocks_only.reshape(1, 96, 256)) < 1e-3
