@@ -34,6 +34,15 @@ CASES = {
     # 2-D image backbone (lib/backbone.py): window is an int, never clamped
     "img_w12_60x76": dict(window=(1, 12, 12), depths=(2, 2, 2, 2), mha=(1, 1, 2, 2), B=2, T=1, H=60, W=76, Nl=20, keep=(1, 2, 3),
                           image=True),
+    # fusion ablations of lib/bcam.py in the 2-D image backbone (flags = the reference's own CLI flags) and --lazy_pred
+    "img_efn_128": dict(window=(1, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=1, H=128, W=128, Nl=20, keep=(1, 2, 3), image=True,
+                        flags=("--efn",)),                      # 32 x 32 and 16 x 16 maps are pooled (hw > 225), 8 x 8 and 4 x 4 are not
+    "img_gacd_64x96": dict(window=(1, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=2, T=1, H=64, W=96, Nl=20, keep=(1, 2, 3), image=True,
+                           flags=("--gacd",)),
+    "img_bcam_480": dict(window=(1, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=1, H=480, W=480, Nl=20, keep=(), image=True,
+                         flags=("--bcam",), store_logits=False),   # a_proj pins BCAM to 480 x 480; only the 1/4-scale logits are stored
+    "lazy_w7_t4_64": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=4, H=64, W=64, Nl=20, keep=(1, 2, 3),
+                          flags=("--lazy_pred",)),
 }
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -41,7 +50,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 def case_inputs(c):
     image = c.get("image", False)
     cfg = O.OracleConfig(depths=c["depths"], window=c["window"], fusion_heads=c["mha"], clamp_window=not image, video=not image,
-                         sep_t_pwam=c.get("sep_t_pwam", False))
+                         sep_t_pwam=c.get("sep_t_pwam", False), **{f[2:]: True for f in c.get("flags", ())})
     sd = O.random_state_dict(cfg, seed=0)
     x, l, m = O.synthetic_inputs(c["B"], c["T"], c["H"], c["W"], Nl=c["Nl"], seed=1, video=not image)
     return cfg, sd, x, l, m
@@ -54,24 +63,31 @@ def main():
         if only and name not in only:
             continue
         cfg, sd, x, l, m = case_inputs(c)
+        flags = tuple(c.get("flags", ()))
+        lazy = "--lazy_pred" in flags
         if c.get("image", False):
-            bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=c["window"][1], mha=c["mha"], depths=c["depths"])
+            bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=c["window"][1], mha=c["mha"], depths=c["depths"], extra=flags)
         else:
             bb, dec, _ = ref_shims.build_reference_backbone_small(window=c["window"], mha=c["mha"], depths=c["depths"],
-                                                                  extra=ref_shims.SEP_T_PWAM_FLAGS if c.get("sep_t_pwam") else ())
+                                                                  extra=(ref_shims.SEP_T_PWAM_FLAGS if c.get("sep_t_pwam") else ()) + flags,
+                                                                  out_indices=(1, 2, 3) if lazy else (0, 1, 2, 3))
         missing = bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=False)
         assert all(k.endswith("relative_position_index") for k in missing.missing_keys) and not missing.unexpected_keys, missing
         missing = dec.load_state_dict({k[len("classifier."):]: v for k, v in sd.items() if k.startswith("classifier.")}, strict=False)
         assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys, missing
         with torch.no_grad():
             feats = bb(x if c.get("image", False) else x.permute(0, 2, 1, 3, 4), l, m.unsqueeze(-1))   # reference forward
+            feats = ((None,) + tuple(feats)) if lazy else tuple(feats)                                   # lib/_utils.py:101-105
             low = dec(feats[3], feats[2], feats[1], feats[0])
             logits = F.interpolate(low, size=(c["H"], c["W"]), mode="bilinear", align_corners=True)   # lib/_utils.py:106
-        arrays = {"logits": logits.numpy(), "logits_lowres": low.numpy()}
+        arrays = {"logits_lowres": low.numpy()}
+        if c.get("store_logits", True):
+            arrays["logits"] = logits.numpy()
         for i in c["keep"]:
             arrays[f"c{i + 1}"] = feats[i].numpy()
         for i in range(4):
-            arrays[f"c{i + 1}_absmean"] = np.float32(feats[i].abs().mean().item())
+            if feats[i] is not None:
+                arrays[f"c{i + 1}_absmean"] = np.float32(feats[i].abs().mean().item())
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **arrays)
         print(name, {k: getattr(v, "shape", v) for k, v in arrays.items()}, os.path.getsize(path) // 1024, "KiB")

@@ -20,13 +20,18 @@ def test_oracle_reproduces_reference_outputs(name):
     cap = {}
     with torch.no_grad():
         logits = O.model_forward(sd, cfg, x, l, m, capture=cap)
-    assert np.abs(logits.numpy() - gold["logits"]).max() < 2e-4
-    assert np.abs(cap["logits_lowres"].numpy() - gold["logits_lowres"]).max() < 2e-4
+    # EFN ends in an InstanceNorm over nearly uniform co-attention averages at random init: fp32 summation order shows at 2e-3 (see
+    # tests/test_oracle_vs_reference.py::test_efn_image_backbone_matches_reference)
+    tol = 2e-3 if "--efn" in CASES[name].get("flags", ()) else 2e-4
+    if "logits" in gold:
+        assert np.abs(logits.numpy() - gold["logits"]).max() < tol
+    assert np.abs(cap["logits_lowres"].numpy() - gold["logits_lowres"]).max() < tol
     for i in range(4):
         key = f"c{i + 1}"
         if key in gold:
-            assert np.abs(cap[key].numpy() - gold[key]).max() < 2e-4, key
-        assert abs(cap[key].abs().mean().item() - float(gold[key + "_absmean"])) < 1e-4
+            assert np.abs(cap[key].numpy() - gold[key]).max() < tol, key
+        if key + "_absmean" in gold:
+            assert abs(cap[key].abs().mean().item() - float(gold[key + "_absmean"])) < 1e-4
 
 
 def test_oracle_autograd_reproduces_reference_training_step():
