@@ -290,3 +290,40 @@ def test_lazy_pred_model_matches_reference():
     for i, (a, b) in enumerate(zip(feats, (c2, c3, c4))):
         assert a.shape == b.shape and (a - b).abs().max().item() < 2e-4, f"stage {i + 1}"
     assert got.shape == ref.shape == (4, 2, 64, 64) and (got - ref).abs().max().item() < 2e-4
+
+
+def test_vlt_head_matches_reference(monkeypatch):
+    """oracle/vlt_oracle.py vs the unmodified reference VLTFuseAndClassify (lib/vlt.py:12-199) in eval mode, on CPU.  The reference's
+    vlt_concat_coords builds its coordinate grids on the hard-coded device string 'cuda:<index>' (:268); only torch.arange's device
+    argument is redirected here, the reference code itself runs untouched."""
+    ref_shims.install_shims()
+    from lib.vlt import VLTFuseAndClassify
+    from oracle import vlt_oracle as VO
+    real_arange = torch.arange
+
+    def arange_on_cpu(*a, **kw):
+        if isinstance(kw.get("device"), str) and kw["device"].startswith("cuda"):
+            kw["device"] = "cpu"
+        return real_arange(*a, **kw)
+    monkeypatch.setattr(torch, "arange", arange_on_cpu)
+    args = ref_shims.reference_args(["--model", "lavt_vlt", "--img_size", "128"])
+    torch.manual_seed(0)
+    head = VLTFuseAndClassify(d_model=256, nhead=8, d_hid=256, nlayers=2, args=args).eval()
+    _randomise_norms([head])
+    g = torch.Generator().manual_seed(7)
+    for m in head.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.add_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.add_(0.2 * torch.rand(m.running_var.shape, generator=g))
+    sd = {k: v.detach() for k, v in head.state_dict().items()}
+    B, Nl = 2, 11
+    c4, c3, c2 = (torch.randn(B, 1024, 4, 4, generator=g), torch.randn(B, 512, 8, 8, generator=g), torch.randn(B, 256, 16, 16, generator=g))
+    l = torch.randn(B, 768, Nl, generator=g)
+    mask = torch.zeros(B, Nl, 1)
+    mask[0, :8] = 1
+    mask[1, :5] = 1
+    with torch.no_grad():
+        ref = head(c4, c3, c2, l, mask)
+        got = VO.vlt_fuse_and_classify(sd, c4, c3, c2, l, mask)
+    assert got.shape == ref.shape == (B, 2, 64, 64)
+    assert (got - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item()), (got - ref).abs().max().item()
