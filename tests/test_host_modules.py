@@ -106,6 +106,17 @@ def test_lazy_pred_state_dict_matches_oracle_contract():
     assert "backbone.norm0.weight" not in mine and "classifier.conv1_2.weight" not in mine
 
 
+def test_inference_only_variants_refuse_training():
+    """The lib/bcam.py fusions and --lazy_pred have no hand-written backward: the training entry point must refuse them up front."""
+    from lavt_rs_b200 import training
+    from lavt_rs_b200.lib import segmentation
+    for flag in ("--bcam", "--efn", "--gacd", "--lazy_pred"):
+        m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", flag]))
+        with pytest.raises(NotImplementedError):
+            training._check_trainable(m)
+    training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
+
+
 def test_forward_refuses_cpu_tensors():
     from lavt_rs_b200 import _cabi
     bb, dec = _small_backbone()
