@@ -18,7 +18,9 @@ import torch
 from . import _cabi as K
 
 
-def reference_param_groups(model, lang_enc_params: str = "encoder-10") -> List[dict]:
+def reference_param_groups(model, lang_enc_params: str = "encoder-10", bert_model=None) -> List[dict]:
+    """``bert_model``: the separate text encoder of the non-integrated ``lavt`` model (train.py:624-633): when the model has no
+    ``text_encoder`` of its own, the first 10 encoder layers of ``bert_model`` form the fourth group, as in the reference."""
     no_decay, decay = [], []
     for name, prm in model.backbone.named_parameters():
         (no_decay if ("norm" in name or "absolute_pos_embed" in name or "relative_position_bias_table" in name) else decay).append(prm)
@@ -40,11 +42,21 @@ def reference_param_groups(model, lang_enc_params: str = "encoder-10") -> List[d
             groups.append({"params": [p for p in enc.encoder.parameters() if p.requires_grad]})
         else:
             raise ValueError(f"unknown --lang_enc_params {lang_enc_params}")
+    elif bert_model is not None:
+        groups.append({"params": [p for i in range(10) for p in bert_model.encoder.layer[i].parameters() if p.requires_grad]})
     return groups
 
 
 def poly_lr_lambda(total_iters: int):
     return lambda it: (1 - it / total_iters) ** 0.9
+
+
+def _bump_versions(tensors) -> None:
+    """Advance the autograd version counter of tensors that were written outside of PyTorch (no kernel launch)."""
+    try:
+        torch._C._autograd._unsafe_set_version_counter(tuple(tensors), tuple(t._version + 1 for t in tensors))
+    except (AttributeError, TypeError):          # older / newer torch without the batched setter: a real (cheap) in-place op
+        torch._foreach_add_(list(tensors), 0.0)
 
 
 class _Tensor(C.Structure):
@@ -78,8 +90,15 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     if group["amsgrad"]:
                         st["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                step_no = int(st["step"].item())            # CPU scalar: torch keeps one step counter per parameter
+                # torch.optim.AdamW keeps one step counter per parameter: a Python int in checkpoints written by torch 1.x (the
+                # reference's era), a tensor today -- and load_state_dict may have moved it to the GPU.  Normalise to a CPU
+                # scalar tensor so that .item() never synchronises the device.
+                s_old = st["step"]
+                step_no = int(s_old.item() if torch.is_tensor(s_old) else s_old) + 1
+                if torch.is_tensor(s_old) and not s_old.is_cuda:
+                    s_old.fill_(float(step_no))
+                else:
+                    st["step"] = torch.tensor(float(step_no), dtype=torch.float32)
                 e = _Tensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                             st["max_exp_avg_sq"].data_ptr() if group["amsgrad"] else None, p.numel(),
                             1.0 - b1 ** step_no, 1.0 - b2 ** step_no)
@@ -93,4 +112,7 @@ class FusedAdamW(torch.optim.Optimizer):
             K.check(K.lib().lavt_adamw_step(tab.data_ptr(), pre.data_ptr(), n, blocks, float(group["lr"]), float(b1), float(b2),
                                             float(group["eps"]), float(group["weight_decay"]), K.stream_ptr()), "lavt_adamw_step")
             self._host[gi] = (tab, pre, [g for _, g in entries])      # lifetime: until the next step of this group
+            # the kernel wrote the parameters through raw pointers: bump their autograd version counters so that every cache keyed on
+            # (data_ptr, _version) -- engine.PreparedWeights' bf16 / folded copies -- is rebuilt before the next forward
+            _bump_versions(live)
         return loss

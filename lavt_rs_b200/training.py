@@ -186,7 +186,10 @@ class SegmentFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        grads = T.GradStore(ctx.model.parameters())
+        # gradients are produced for the backbone and the classifier only: the text encoder's ~110 M parameters get theirs from
+        # autograd through d l_feats, so they need no slot (and no 440 MB memset) here
+        m = ctx.model
+        grads = T.GradStore(list(m.backbone.parameters()) + list(m.classifier.parameters()))
         dl = segment_backward(ctx.model, ctx.tape, dlogits.float(), grads)
         grads.finalize()
         ctx.tape = None

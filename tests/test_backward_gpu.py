@@ -504,6 +504,36 @@ def test_fused_adamw_matches_torch():
         assert torch.allclose(st1[3]["exp_avg_sq"], st2[3]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
 
 
+def test_fused_adamw_resumes_from_torch_adamw_state():
+    """Optimizer state written by torch.optim.AdamW -- with the step counter as a Python int (torch 1.x checkpoints, the reference's
+    era), a CPU tensor, or a CUDA tensor (what older load_state_dict produced) -- resumes in FusedAdamW and continues identically."""
+    from lavt_rs_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(11)
+    for kind in ("int", "cpu", "cuda"):
+        ref = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in [(64, 32), (19,)]]
+        o2 = torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-2)
+        grads = [[torch.randn(p.shape, generator=g).cuda() for p in ref] for _ in range(4)]
+        for it in range(2):
+            for p, gr in zip(ref, grads[it]):
+                p.grad = gr.clone()
+            o2.step()
+        ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+        sd = o2.state_dict()
+        for st in sd["state"].values():
+            stp = int(st["step"].item()) if torch.is_tensor(st["step"]) else int(st["step"])
+            st["step"] = stp if kind == "int" else torch.tensor(float(stp), device=kind)
+        o1 = FusedAdamW(ours, lr=1e-3, weight_decay=1e-2)
+        o1.load_state_dict(sd)
+        for it in range(2, 4):
+            for p, q, gr in zip(ref, ours, grads[it]):
+                p.grad, q.grad = gr.clone(), gr.clone()
+            o2.step(); o1.step()
+        for st in o1.state.values():
+            assert torch.is_tensor(st["step"]) and not st["step"].is_cuda and int(st["step"].item()) == 4
+        for a, b in zip(ours, ref):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (kind, (a - b).abs().max().item())
+
+
 def test_image_model_training_through_public_api(tmp_path):
     """2-D LAVT (windows (1,7,7), never clamped) in ``model.train()``: ``model(x, l_feats, l_mask)`` -> criterion -> ``backward()`` ->
     FusedAdamW step -> checkpoint round trip in the reference's format; gradients vs autograd through the oracle (direction / scale)."""
@@ -544,13 +574,27 @@ def test_image_model_training_through_public_api(tmp_path):
     ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
     check_direction(got, ref, "2-D training step")
     before = bb.layers[1].blocks[0].mlp.fc1.weight.detach().clone()
+    with torch.no_grad():
+        model.eval()
+        out_before = model(x.cuda(), l.cuda(), m.cuda()).clone()
+        model.train()
     opt.step()
     sched.step()
     assert not torch.equal(before, bb.layers[1].blocks[0].mlp.fc1.weight)
     # eval mode still runs the inference path, without autograd
     model.eval()
     with torch.no_grad():
-        assert not model(x.cuda(), l.cuda(), m.cuda()).requires_grad
+        out_after = model(x.cuda(), l.cuda(), m.cuda()).clone()
+        assert not out_after.requires_grad
+        # the optimizer kernel writes the fp32 masters through raw pointers: the cached bf16 / folded operand copies must follow
+        # (version counters bumped in FusedAdamW.step) -- the forward after the step uses the NEW weights ...
+        assert (out_after - out_before).abs().max().item() > 1e-4, "forward after optimizer.step() still uses the step-0 weights"
+        # ... and equals a forward with every prepared-operand cache rebuilt from scratch
+        for mod in model.modules():
+            if hasattr(mod, "prepared"):
+                mod.prepared.clear()
+        out_fresh = model(x.cuda(), l.cuda(), m.cuda())
+        assert torch.equal(out_after, out_fresh), (out_after - out_fresh).abs().max().item()
     # checkpoint round trip (train.py:752-762 format)
     path = os.path.join(tmp_path, "models", "checkpoint_00.pth")
     save_checkpoint(path, model, opt, sched, epoch=0, args={"lr": 1e-4})
