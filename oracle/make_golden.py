@@ -43,8 +43,23 @@ CASES = {
                          flags=("--bcam",), store_logits=False),   # a_proj pins BCAM to 480 x 480; only the 1/4-scale logits are stored
     "lazy_w7_t4_64": dict(window=(8, 7, 7), depths=(2, 2, 2, 2), mha=(1, 1, 1, 1), B=1, T=4, H=64, W=64, Nl=20, keep=(1, 2, 3),
                           flags=("--lazy_pred",)),
+    # BASELINE.json configs[1] / configs[2] at their REAL size: Video Swin-B depths 2-2-18-2, one clip of 8 x 384 x 384, 20 words, window
+    # (8,7,7) and --window12.  The full tensors are 60 MB, so strided slices (``subsample`` below) + per-tensor statistics are stored.
+    "full_w7_t8_384": dict(window=(8, 7, 7), depths=(2, 2, 18, 2), mha=(1, 1, 1, 1), B=1, T=8, H=384, W=384, Nl=20, keep=(0, 1, 2, 3),
+                           sub=True),
+    "full_w12_t8_384": dict(window=(8, 12, 12), depths=(2, 2, 18, 2), mha=(1, 1, 1, 1), B=1, T=8, H=384, W=384, Nl=20, keep=(0, 1, 2, 3),
+                            sub=True),
 }
 OUT = os.path.join(ROOT, "tests", "golden")
+
+# strided slices stored for the full-size cases: (channel stride, spatial stride) per tensor
+SUB = {"c1": (32, 4), "c2": (32, 2), "c3": (32, 1), "c4": (16, 1), "logits": (1, 4), "logits_lowres": (1, 2)}
+
+
+def subsample(key: str, t):
+    """The slice of tensor ``key`` ([frames, C, H, W]) that a ``sub=True`` golden case stores."""
+    cs, ss = SUB[key]
+    return t[:, ::cs, ::ss, ::ss]
 
 
 def case_inputs(c):
@@ -80,11 +95,23 @@ def main():
             feats = ((None,) + tuple(feats)) if lazy else tuple(feats)                                   # lib/_utils.py:101-105
             low = dec(feats[3], feats[2], feats[1], feats[0])
             logits = F.interpolate(low, size=(c["H"], c["W"]), mode="bilinear", align_corners=True)   # lib/_utils.py:106
-        arrays = {"logits_lowres": low.numpy()}
+        sub = (lambda k, t: subsample(k, t)) if c.get("sub") else (lambda k, t: t)
+        arrays = {"logits_lowres": sub("logits_lowres", low).numpy()}
         if c.get("store_logits", True):
-            arrays["logits"] = logits.numpy()
+            arrays["logits"] = sub("logits", logits).numpy()
         for i in c["keep"]:
-            arrays[f"c{i + 1}"] = feats[i].numpy()
+            arrays[f"c{i + 1}"] = sub(f"c{i + 1}", feats[i]).numpy()
+        if c.get("sub"):
+            # whole-tensor statistics of what was not stored: L2 norm of every tensor, the thresholded mask (bit-packed) and the
+            # fp32 logit margin quantised to int8 are what the mask-agreement checks need
+            arrays["logits_norm"] = np.float32(logits.norm().item())
+            arrays["mask_bits"] = np.packbits((logits[:, 1] > logits[:, 0]).numpy())
+            margin = (logits[:, 1] - logits[:, 0]).numpy()
+            step = float(margin.std()) / 32.0                      # int8 steps of std/32: fine where it matters (around zero)
+            arrays["margin_step"] = np.float32(step)
+            arrays["margin_q"] = np.clip(np.rint(margin / step), -127, 127).astype(np.int8)
+            for i in range(4):
+                arrays[f"c{i + 1}_norm"] = np.float32(feats[i].norm().item())
         for i in range(4):
             if feats[i] is not None:
                 arrays[f"c{i + 1}_absmean"] = np.float32(feats[i].abs().mean().item())
