@@ -129,8 +129,10 @@ int lavt_window_attention_lse(const void* qkv, const float* table_t, int32_t L, 
                               float* lse, void* stream);
 int lavt_window_attention_has_lse(const lavt_win_geom_t* geom, int32_t L, int32_t nH);
 /* Kernel selection for lavt_window_attention (process-wide; initial value from the LAVT_ATTN_IMPL environment variable):
- *   0 = auto: tcgen05 / TMEM kernel for windows of <= 400 tokens, mma.sync flash kernels otherwise
- *   1 = mma.sync kernels only.  Returns the previous setting. */
+ *   0 = auto: one-pass key-chunked tcgen05 / TMEM kernel (attn_tc2.cu) for windows of up to 1152 tokens
+ *   1 = mma.sync kernels only
+ *   2 = prefer the two-pass tcgen05 kernel (attn_tc.cu) for windows of <= 400 tokens
+ *   3 = attn_tc2.cu (same as auto).  Returns the previous setting. */
 int lavt_set_attention_impl(int32_t impl);
 
 /* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */

@@ -382,9 +382,11 @@ def patch_embed_im2col(x: torch.Tensor, out_bf16: torch.Tensor) -> None:
 
 
 def set_attention_impl(impl: str) -> str:
-    """'auto' (tcgen05 kernel where it applies) or 'mma' (mma.sync kernels only); returns the previous setting."""
-    prev = lib().lavt_set_attention_impl({"auto": 0, "mma": 1}[impl])
-    return "mma" if prev else "auto"
+    """'auto' (tcgen05 kernels: the one-pass chunked kernel for every window size), 'tc1' (prefer the two-pass tcgen05 kernel for
+    windows of <= 400 tokens), 'tc2' (= auto today) or 'mma' (mma.sync kernels only); returns the previous setting."""
+    names = ["auto", "mma", "tc1", "tc2"]
+    prev = lib().lavt_set_attention_impl(names.index(impl))
+    return names[prev] if 0 <= prev < len(names) else "auto"
 
 
 def window_attention_has_lse(table_t: torch.Tensor, geom: WinGeom) -> bool:

@@ -372,10 +372,11 @@ int attn_impl_setting(int set) {
   static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("LAVT_ATTN_IMPL");
-    impl = (e && e[0] == 'm') ? 1 : 0;   // default: auto (tcgen05 kernel where it applies)
+    // default: auto (tcgen05 kernels where they apply); "mma" = mma.sync only, "tc1" / "tc2" = prefer the first / second generation
+    impl = !e ? 0 : e[0] == 'm' ? 1 : (e[0] == 't' && e[1] == 'c' && e[2] == '1') ? 2 : (e[0] == 't' && e[1] == 'c' && e[2] == '2') ? 3 : 0;
   }
   const int prev = impl;
-  if (set >= 0) impl = set ? 1 : 0;
+  if (set >= 0) impl = set <= 3 ? set : 0;
   return prev;
 }
 
@@ -391,7 +392,13 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
   const int N = g.N;
   {
     // LAVT_ATTN_IMPL=mma (or lavt_set_attention_impl(1)) forces the mma.sync kernels below
-    if (attn_impl_setting(-1) == 0 && window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
+    const int impl = attn_impl_setting(-1);
+    if (impl != 1) {
+      // auto: the one-pass chunked kernel (attn_tc2.cu, any window up to 1152 tokens); tc1 keeps the two-pass kernel (<= 400 tokens)
+      if (impl != 2 && window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
+      if (window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
+      if (window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
+    }
   }
   LAVT_REQUIRE(p.lse == nullptr, "attention: row statistics (lse) are produced by the tcgen05 kernel only (N=%d)", N);
   if (N <= 512) {

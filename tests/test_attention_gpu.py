@@ -38,7 +38,8 @@ CASES = [  # (B, D, H, W), window, shifted, heads
 ]
 
 
-@pytest.mark.parametrize("impl", ["auto", "mma"])      # auto = tcgen05 kernel where it applies (N <= 400)
+# auto / tc2 = one-pass chunked tcgen05 kernel (every N); tc1 = two-pass tcgen05 kernel where it applies (N <= 400); mma = mma.sync
+@pytest.mark.parametrize("impl", ["auto", "tc1", "mma"])
 @pytest.mark.parametrize("dims,window,shifted,nH", CASES)
 def test_window_attention_matches_torch(dims, window, shifted, nH, impl):
     from lavt_rs_b200 import _cabi as K
@@ -67,3 +68,51 @@ def test_window_attention_matches_torch(dims, window, shifted, nH, impl):
     bad = (err > 2e-2 * ref.abs() + 2e-2 * rms).float().mean().item()
     rel = (err.norm() / ref.norm()).item()
     assert bad < 1e-4 and rel < 1e-2, f"N={geom.N}: {bad*100:.4f}% out of tolerance, rel-L2 {rel:.3e}"
+
+
+@pytest.mark.parametrize("dims,window,nH", [((1, 8, 14, 14), (8, 7, 7), 4), ((1, 8, 24, 24), (8, 12, 12), 4), ((1, 4, 24, 24), (8, 7, 7), 4),
+                                            ((1, 8, 10, 10), (8, 12, 12), 4)])
+@pytest.mark.parametrize("pattern", ["ramp", "spike", "late_rows"])
+def test_one_pass_softmax_slow_path(dims, window, nH, pattern):
+    """The one-pass kernel keeps the running maximum of the FIRST piece of a row and only re-bases when a later piece overflows
+    sum 2^(s - m) <= 2^20.  These inputs force that slow path: scores that grow by hundreds of units along the key axis ('ramp'),
+    a single huge key in the last chunk ('spike': rescale of the P columns already written AND of the O accumulator in TMEM), and
+    rows whose maximum moves only for part of a warp ('late_rows')."""
+    from lavt_rs_b200 import _cabi as K
+    from lavt_rs_b200.geometry import window_geometry
+    B, D, H, W = dims
+    geom = window_geometry(B, D, H, W, window, True, True)
+    C = nH * 32
+    rows, N = geom.rows(), geom.N
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(rows, 3 * C, device="cuda", generator=g)
+    qkv[:, :C] *= 32 ** -0.5 * math.log2(math.e)
+    t = torch.arange(rows, device="cuda") % N
+    # feature 0 of q / k carries the forced score: s_ij += q_i0 * k_j0
+    if pattern == "ramp":
+        qkv[:, 0] = 4.0
+        qkv[:, C] = (t.float() / N) * 150.0                 # + up to 600 log2-units from the first to the last key
+    elif pattern == "spike":
+        qkv[:, 0] = 4.0
+        qkv[:, C] = torch.where(t == N - 3, 120.0, 0.0)
+    else:
+        qkv[:, 0] = torch.where(t % 5 == 0, 4.0, 0.0)       # only every fifth query row sees the ramp
+        qkv[:, C] = (t.float() / N) * 100.0
+    qkv = qkv.bfloat16()
+    L = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    table = torch.randn(L, nH, device="cuda", generator=g)
+    out = torch.empty(rows, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(rows, nH, device="cuda", dtype=torch.float32)
+    prev = K.set_attention_impl("tc2")
+    try:
+        K.window_attention(qkv, table.t().contiguous(), geom, out, lse=lse)
+        torch.cuda.synchronize()
+    finally:
+        K.set_attention_impl(prev)
+    ref = torch_window_attention(qkv, table, geom)
+    err = (out.float() - ref).abs()
+    rms = ref.pow(2).mean().sqrt()
+    bad = (err > 2e-2 * ref.abs() + 2e-2 * rms).float().mean().item()
+    rel = (err.norm() / ref.norm()).item()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert bad < 1e-4 and rel < 1e-2, f"{pattern} N={N}: {bad*100:.4f}% out of tolerance, rel-L2 {rel:.3e}"

@@ -518,7 +518,8 @@ def test_fused_adamw_resumes_from_torch_adamw_state():
                 p.grad = gr.clone()
             o2.step()
         ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
-        sd = o2.state_dict()
+        import copy
+        sd = copy.deepcopy(o2.state_dict())          # state_dict() hands out the optimizer's own tensors: edit a copy
         for st in sd["state"].values():
             stp = int(st["step"].item()) if torch.is_tensor(st["step"]) else int(st["step"])
             st["step"] = stp if kind == "int" else torch.tensor(float(stp), device=kind)
