@@ -55,6 +55,7 @@ struct AttnTc2Args {
   int off_q, off_tab, off_cf, off_negoff, off_pm, off_ps, off_xq, off_bar;
   int shifted;
   int r4, tail_rows;
+  int mode;                 // 0 generic pieces, 1 runs of 7 keys (56-column pieces), 2 runs of 12 keys (48-column pieces)
 };
 
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
@@ -63,11 +64,45 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+// W consecutive columns as the fewest power-of-two transfers (any even W)
+template <int W>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (W >= 32) { tmem_ld_x32(taddr, r); if constexpr (W > 32) tmem_ld_n<W - 32>(taddr + 32, r + 32); }
+  else if constexpr (W >= 16) { tmem_ld_x16(taddr, r); if constexpr (W > 16) tmem_ld_n<W - 16>(taddr + 16, r + 16); }
+  else if constexpr (W >= 8) { tmem_ld_x8(taddr, r); if constexpr (W > 8) tmem_ld_n<W - 8>(taddr + 8, r + 8); }
+  else if constexpr (W >= 4) { tmem_ld_x4(taddr, r); if constexpr (W > 4) tmem_ld_n<W - 4>(taddr + 4, r + 4); }
+  else { static_assert(W == 2, "unsupported TMEM transfer width"); tmem_ld_x2(taddr, r); }
+}
+template <int W>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  if constexpr (W >= 32) { tmem_st_x32(taddr, r); if constexpr (W > 32) tmem_st_n<W - 32>(taddr + 32, r + 32); }
+  else if constexpr (W >= 16) { tmem_st_x16(taddr, r); if constexpr (W > 16) tmem_st_n<W - 16>(taddr + 16, r + 16); }
+  else if constexpr (W >= 8) { tmem_st_x8(taddr, r); if constexpr (W > 8) tmem_st_n<W - 8>(taddr + 8, r + 8); }
+  else if constexpr (W >= 4) { tmem_st_x4(taddr, r); if constexpr (W > 4) tmem_st_n<W - 4>(taddr + 4, r + 4); }
+  else { static_assert(W == 2, "unsupported TMEM transfer width"); tmem_st_x2(taddr, r); }
+}
 
 // per-row state of the one-pass softmax
 struct T2Row {
-  const float* tabq;     // table + code(i) + rc : bias(i, j) = tabq[negoff[j]]
-  const int* negoff;
+  const float* tabq;     // table + code(i) + rc : bias(i, j) = tabq[-code(j)]
+  const int* negoff;     // generic pieces: -code(j) per key
+  const int* runcode;    // run pieces: code(first key of the run) per run of Ww consecutive keys
   const float* cf;       // per-key region class of this window (floats), or nullptr when the window needs no mask
   float cif;             // region class of this row
   int N;
@@ -75,22 +110,11 @@ struct T2Row {
   bool first;
 };
 
-// One piece of W score columns: chunk column c (TMEM address ts_buf + c), global key index gc.
+// Softmax of one piece whose W scores s[] already hold q.k + bias: mask, padding, running maximum, exp2, row sum, bf16 P -> TMEM.
+//   chunk column c (TMEM address ts_buf + c), global key index gc
 //   o_acc / pv_done / pv_parity / tmem_o: the group's O accumulator already holds earlier chunks of this tile (slow path rescales it)
 template <int W>
-__device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& r, bool o_acc, uint64_t* pv_done, uint32_t pv_parity,
-                                         uint32_t tmem_o) {
-  uint32_t v[W];
-  tmem_ld_w<W>(ts_buf + c, v);
-  int no[W];
-#pragma unroll
-  for (int j = 0; j < W; j += 4) *reinterpret_cast<int4*>(&no[j]) = *reinterpret_cast<const int4*>(r.negoff + gc + j);
-  float s[W];
-#pragma unroll
-  for (int j = 0; j < W; ++j) s[j] = r.tabq[no[j]];
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < W; j += 2) add2(s[j], s[j + 1], __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+__device__ __forceinline__ void t2_mask_pad(float (&s)[W], int gc, const T2Row& r) {
   if (r.cf != nullptr) {
     float cfv[W];
 #pragma unroll
@@ -104,6 +128,11 @@ __device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& 
     for (int j = 0; j < W; ++j)
       if (gc + j >= r.N) s[j] = -INFINITY;
   }
+}
+
+template <int W>
+__device__ __forceinline__ void t2_exp_store(float (&s)[W], uint32_t ts_buf, int c, T2Row& r, bool o_acc, uint64_t* pv_done,
+                                             uint32_t pv_parity, uint32_t tmem_o) {
   if (r.first) {
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
@@ -115,17 +144,33 @@ __device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& 
     r.first = false;
   }
   float p[W];
-  float l0 = 0.f, l1 = 0.f;
+  float l0, l1;
   {
+    // three phases with no consumer next to its producer (a warp issues in order): arguments, W back-to-back MUFU.EX2 (the XU pipe
+    // takes one warp instruction per 8 cycles: the other warp of the SM sub-partition issues in the gaps), then a sum TREE and the packs
     const float nm = -r.m;
 #pragma unroll
     for (int j = 0; j < W; j += 2) {
-      float a0 = s[j], a1 = s[j + 1];
-      add2(a0, a1, nm, nm);
-      p[j] = ex2_ftz(a0);
-      p[j + 1] = ex2_ftz(a1);
-      add2(l0, l1, p[j], p[j + 1]);
+      p[j] = s[j];
+      p[j + 1] = s[j + 1];
+      add2(p[j], p[j + 1], nm, nm);
     }
+#pragma unroll
+    for (int j = 0; j < W; ++j) p[j] = ex2_ftz(p[j]);
+    float t0[W / 4 * 2];
+#pragma unroll
+    for (int j = 0; j < W / 4; ++j) {
+      t0[2 * j] = p[4 * j];
+      t0[2 * j + 1] = p[4 * j + 1];
+      add2(t0[2 * j], t0[2 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+    }
+#pragma unroll
+    for (int n = W / 4; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+      for (int j = 0; j < n / 2; ++j) add2(t0[2 * j], t0[2 * j + 1], t0[2 * (n - 1 - j)], t0[2 * (n - 1 - j) + 1]);
+    }
+    l0 = t0[0];
+    l1 = t0[1];
   }
   float ps = l0 + l1;
   if (__any_sync(0xffffffffu, !(ps <= T2_PSUM_LIMIT))) {
@@ -139,16 +184,16 @@ __device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& 
     const float m2 = fmaxf(m0, m1);
     const float f = ex2_ftz(r.m - m2);          // 1 for the lanes whose maximum did not move
     r.l *= f;
-    for (int pc = 0; pc < (c >> 1); pc += 8) {   // P columns of this chunk that were already written (bf16 pairs)
-      uint32_t w8[8];
-      tmem_ld_x8(ts_buf + pc, w8);
+    for (int pc = 0; pc < (c >> 1); pc += 2) {   // P columns of this chunk that were already written (bf16 pairs)
+      uint32_t w2[2];
+      tmem_ld_x2(ts_buf + pc, w2);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 t = unpack_bf16x2(w8[j]);
-        w8[j] = pack_bf16x2(t.x * f, t.y * f);
+      for (int j = 0; j < 2; ++j) {
+        const float2 t = unpack_bf16x2(w2[j]);
+        w2[j] = pack_bf16x2(t.x * f, t.y * f);
       }
-      tmem_st_x8(ts_buf + pc, w8);
+      tmem_st_x2(ts_buf + pc, w2);
     }
     if (o_acc) {
       mbar_wait(pv_done, pv_parity);             // every P.V issued so far into this accumulator has retired
@@ -179,7 +224,81 @@ __device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& 
   uint32_t pk[W / 2];
 #pragma unroll
   for (int j = 0; j < W; j += 2) pk[j >> 1] = pack_bf16x2(p[j], p[j + 1]);
-  tmem_st_w<W / 2>(ts_buf + (c >> 1), pk);
+  tmem_st_n<W / 2>(ts_buf + (c >> 1), pk);
+}
+
+// generic piece: any window geometry, one shared-memory index + one gather per score
+template <int W>
+__device__ __forceinline__ void t2_softmax_piece(float (&s)[W], uint32_t ts_buf, int c, int gc, T2Row& r, bool o_acc, uint64_t* pv_done,
+                                                 uint32_t pv_parity, uint32_t tmem_o) {
+  t2_mask_pad<W>(s, gc, r);
+  t2_exp_store<W>(s, ts_buf, c, r, o_acc, pv_done, pv_parity, tmem_o);
+}
+
+template <int W>
+__device__ __forceinline__ void t2_piece(uint32_t ts_buf, int c, int gc, T2Row& r, bool o_acc, uint64_t* pv_done, uint32_t pv_parity,
+                                         uint32_t tmem_o) {
+  uint32_t v[W];
+  tmem_ld_n<W>(ts_buf + c, v);
+  int no[W];
+#pragma unroll
+  for (int j = 0; j < W; j += 4) *reinterpret_cast<int4*>(&no[j]) = *reinterpret_cast<const int4*>(r.negoff + gc + j);
+  float s[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) s[j] = r.tabq[no[j]];
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < W; j += 2) add2(s[j], s[j + 1], __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+  t2_softmax_piece<W>(s, ts_buf, c, gc, r, o_acc, pv_done, pv_parity, tmem_o);
+}
+
+// run piece: NR runs of RW consecutive keys (RW = configured window width, so a run shares (d_j, h_j) and its bias entries are RW
+// consecutive table words): one address per run, the RW loads use immediate offsets -- no per-score index or address arithmetic.
+//   issue : tcgen05.ld of the scores + shared-memory loads of the bias        finish: wait::ld, s + bias, mask, padding
+// (a 28-column software-pipelined stream -- loads of piece k+1 in flight under the exponentials of piece k -- was measured slower than
+// these wider pieces: 302 vs 265 us at the stage-2 shape; per-piece bookkeeping and instruction-cache misses outweigh the overlap)
+template <int RW, int NR>
+__device__ __forceinline__ void t2_run_issue(uint32_t ts_buf, int c, int gc, const T2Row& r, uint32_t (&v)[RW * NR], float (&b)[RW * NR]) {
+  constexpr int W = RW * NR;
+  tmem_ld_n<W>(ts_buf + c, v);
+  int rcd[NR];
+  const int run0 = gc / RW;                      // gc is a multiple of W, so run0 is a multiple of NR
+  if constexpr (NR % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < NR; k += 4) *reinterpret_cast<int4*>(&rcd[k]) = *reinterpret_cast<const int4*>(r.runcode + run0 + k);
+  } else {
+    static_assert(NR % 2 == 0, "runs per piece must be even");
+#pragma unroll
+    for (int k = 0; k < NR; k += 2) *reinterpret_cast<int2*>(&rcd[k]) = *reinterpret_cast<const int2*>(r.runcode + run0 + k);
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const float* ar = r.tabq - rcd[k];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) b[k * RW + w] = *(ar - w);
+  }
+}
+template <int W>
+__device__ __forceinline__ void t2_run_finish(const uint32_t (&v)[W], const float (&b)[W], float (&x)[W], int gc, const T2Row& r) {
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < W; j += 2) {
+    float a0 = b[j], a1 = b[j + 1];
+    add2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+    x[j] = a0;
+    x[j + 1] = a1;
+  }
+  t2_mask_pad<W>(x, gc, r);
+}
+template <int RW, int NR>
+__device__ __forceinline__ void t2_piece_runs(uint32_t ts_buf, int c, int gc, T2Row& r, bool o_acc, uint64_t* pv_done, uint32_t pv_parity,
+                                              uint32_t tmem_o) {
+  constexpr int W = RW * NR;
+  uint32_t v[W];
+  float b[W], x[W];
+  t2_run_issue<RW, NR>(ts_buf, c, gc, r, v, b);
+  t2_run_finish<W>(v, b, x, gc, r);
+  t2_exp_store<W>(x, ts_buf, c, r, o_acc, pv_done, pv_parity, tmem_o);
 }
 
 template <int W>
@@ -187,9 +306,45 @@ __device__ __forceinline__ void t2_zero_piece(uint32_t ts_buf, int c) {
   uint32_t z[W / 2];
 #pragma unroll
   for (int j = 0; j < W / 2; ++j) z[j] = 0u;
-  tmem_st_w<W / 2>(ts_buf + (c >> 1), z);
+  tmem_st_n<W / 2>(ts_buf + (c >> 1), z);
 }
 
+// columns [cc, cl) of a chunk exist only to round the MMA N up to 16: P = 0 there
+__device__ __forceinline__ void t2_zero_tail(uint32_t ts_buf, int cc, int cl) {
+  const uint32_t z[2] = {0u, 0u};
+  for (int pc = cc >> 1; pc < (cl >> 1); pc += 2) tmem_st_x2(ts_buf + pc, z);
+}
+
+// all pieces of one chunk (cl columns starting at key cs) for this warp's 32 rows.  MODE 0: generic 32 / 16-column pieces;
+// MODE 1: 56-column pieces of 8 runs of 7 keys; MODE 2: 48-column pieces of 4 runs of 12 keys.  ``piece`` = running piece index of the
+// group within the tile (replicated tail tile: quadrant q owns every fourth piece, the others get P = 0).
+template <int MODE>
+__device__ __forceinline__ void t2_chunk(uint32_t ts_buf, int cs, int cl, T2Row& row, bool rep, int q, int& piece, bool o_acc,
+                                         uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
+  if constexpr (MODE == 0) {
+    int cc = 0;
+    for (; cc + 32 <= cl; cc += 32, ++piece) {
+      if (!rep || (piece & 3) == q) t2_piece<32>(ts_buf, cc, cs + cc, row, o_acc, pv_done, pvp, tmem_o);
+      else t2_zero_piece<32>(ts_buf, cc);
+    }
+    if (cc < cl) {
+      if (!rep || (piece & 3) == q) t2_piece<16>(ts_buf, cc, cs + cc, row, o_acc, pv_done, pvp, tmem_o);
+      else t2_zero_piece<16>(ts_buf, cc);
+      ++piece;
+    }
+  } else {
+    constexpr int RW = MODE == 1 ? 7 : 12, NR = MODE == 1 ? 8 : 4, W = RW * NR;
+    int cc = 0;
+#pragma unroll 1
+    for (; cc + W <= cl; cc += W, ++piece) {
+      if (!rep || (piece & 3) == q) t2_piece_runs<RW, NR>(ts_buf, cc, cs + cc, row, o_acc, pv_done, pvp, tmem_o);
+      else t2_zero_piece<W>(ts_buf, cc);
+    }
+    t2_zero_tail(ts_buf, cc, cl);
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 window_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmQT, const AttnParams p, const AttnTc2Args a) {
@@ -198,7 +353,7 @@ window_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint8_t* qring = smem + a.off_q;
   float* tab = reinterpret_cast<float*>(smem + a.off_tab);
   float* cfall = reinterpret_cast<float*>(smem + a.off_cf);       // [T2_G][NP]
-  int* negoff = reinterpret_cast<int*>(smem + a.off_negoff);
+  int* negoff = reinterpret_cast<int*>(smem + a.off_negoff);      // MODE 0: -code(j) per key; run modes: code(first key) per run
   float* pm = reinterpret_cast<float*>(smem + a.off_pm);          // [4][T2_G][128] group row max (tile index mod 4: with one chunk per
                                                                   // group and tile, group 0 runs up to three tiles ahead of the epilogue)
   float* ps = reinterpret_cast<float*>(smem + a.off_ps);          // [4][T2_G][128] group row sum
@@ -248,10 +403,18 @@ window_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   }
   if (warp == T2_TMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
   // per-launch table: -code(j) of the key tokens; zero the K / V pad rows of every stage
-  for (int j = threadIdx.x; j < NP; j += blockDim.x) {
-    int code = 0;
-    if (j < N) code = (j / (wg.Wh * wg.Ww)) * SD + ((j / wg.Ww) % wg.Wh) * SH + j % wg.Ww;
-    negoff[j] = -code;
+  if constexpr (MODE == 0) {
+    for (int j = threadIdx.x; j < NP; j += blockDim.x) {
+      int code = 0;
+      if (j < N) code = (j / (wg.Wh * wg.Ww)) * SD + ((j / wg.Ww) % wg.Wh) * SH + j % wg.Ww;
+      negoff[j] = -code;
+    }
+  } else {
+    constexpr int RW = MODE == 1 ? 7 : 12;
+    for (int rr = threadIdx.x; rr * RW < NP + RW; rr += blockDim.x) {
+      const int j = rr * RW;                       // first key of the run: w_j = 0 (RW == configured window width)
+      negoff[rr] = j < N ? (j / (wg.Wh * wg.Ww)) * SD + ((j / wg.Ww) % wg.Wh) * SH : 0;
+    }
   }
   {
     const int npad = NP - N;
@@ -511,6 +674,7 @@ window_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           const int code_i = (ic / (wg.Wh * wg.Ww)) * SD + ((ic / wg.Ww) % wg.Wh) * SH + ic % wg.Ww;
           row.tabq = tab + code_i + a.rc;
           row.negoff = negoff;
+          row.runcode = negoff;
           row.cf = nullptr;
           row.cif = 0.f;
           if (need_mask) {
@@ -527,37 +691,30 @@ window_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           row.first = true;
         }
         if (g == T2_EPI && cg == 0 && t >= 1) epilogue(t - 1);
-        int piece = 0;                                         // running piece index of this group within the tile
-        for (int j = 0; j < cg; ++j, ++n) {
-          const int c = g + j * T2_G;
-          const int cs = a.cstart[c], cl = a.clen[c];
-          const uint32_t ts_buf = tlane + (g * 2 + (n & 1)) * T2_CW;
-          mbar_wait(&s_full[g * 2 + (n & 1)], (n >> 1) & 1);
-          tc_fence_after();
-          if (wvalid) {
-            const uint32_t pvp = static_cast<uint32_t>((n - 1) & 1);
-            int cc = 0;
-            for (; cc + 32 <= cl; cc += 32, ++piece) {
-              if (!rep || (piece & 3) == q) t2_piece<32>(ts_buf, cc, cs + cc, row, j > 0, &pv_done[g], pvp, tmem_o);
-              else t2_zero_piece<32>(ts_buf, cc);
+        {
+          int piece = 0;                                         // running piece index of this group within the tile
+          for (int j = 0; j < cg; ++j, ++n) {
+            const int c = g + j * T2_G;
+            const int cs = a.cstart[c], cl = a.clen[c];
+            const uint32_t ts_buf = tlane + (g * 2 + (n & 1)) * T2_CW;
+            mbar_wait(&s_full[g * 2 + (n & 1)], (n >> 1) & 1);
+            tc_fence_after();
+            if (wvalid) {
+              const uint32_t pvp = static_cast<uint32_t>((n - 1) & 1);
+              t2_chunk<MODE>(ts_buf, cs, cl, row, rep, q, piece, j > 0, &pv_done[g], pvp, tmem_o);
+              tmem_st_wait();
+              if (j == cg - 1) {
+                pm[((t & 3) * T2_G + g) * 128 + r] = row.m;
+                ps[((t & 3) * T2_G + g) * 128 + r] = row.l;
+              }
             }
-            if (cc < cl) {
-              if (!rep || (piece & 3) == q) t2_piece<16>(ts_buf, cc, cs + cc, row, j > 0, &pv_done[g], pvp, tmem_o);
-              else t2_zero_piece<16>(ts_buf, cc);
-              ++piece;
-            }
-            tmem_st_wait();
-            if (j == cg - 1) {
-              pm[((t & 3) * T2_G + g) * 128 + r] = row.m;
-              ps[((t & 3) * T2_G + g) * 128 + r] = row.l;
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[g * 2 + (n & 1)]);
+            // group 1 drains the PREVIOUS tile's accumulators after its first chunk of this tile: by then both groups' last P.V of
+            // that tile retired long ago, and the first P.V of this tile (which overwrites O) waits for o_free
+            if (g == T2_EPI && j == 0 && t >= 1) epilogue(t - 1);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_ready[g * 2 + (n & 1)]);
-          // group 1 drains the PREVIOUS tile's accumulators after its first chunk of this tile: by then both groups' last P.V of
-          // that tile retired long ago, and the first P.V of this tile (which overwrites O) waits for o_free
-          if (g == T2_EPI && j == 0 && t >= 1) epilogue(t - 1);
         }
       }
     }
@@ -587,16 +744,22 @@ static bool t2_plan(const AttnParams& p, AttnTc2Args& a, int& smem_out) {
     if (g.N % nb == 0) { a.nb = nb; break; }
   if (a.nb == 0) return false;
   a.BR = g.N / a.nb;
-  // key chunks: an even number of <= 112 columns each (multiples of 16), balanced
-  const int n16 = a.NP / 16;
-  int nch = (n16 + 6) / 7;
-  if (nch < 2 && n16 >= 2) nch = 2;          // both softmax groups get work even for one small window
-  if (nch > 1 && (nch & 1)) ++nch;
-  if (nch > n16) nch = n16;
-  if (nch > T2_MAXCH) return false;
-  a.nchunks = nch;
-  a.ngact = nch >= 2 ? 2 : 1;
-  {
+  static int env_mode = -2;
+  if (env_mode == -2) {
+    const char* e = getenv("LAVT_ATTN_MODE");       // debugging / A-B runs: 0 forces the generic pieces
+    env_mode = e ? atoi(e) : -1;
+  }
+  a.mode = g.Ww == 7 ? 1 : g.Ww == 12 ? 2 : 0;
+  if (env_mode == 0) a.mode = 0;
+  if (a.mode == 0) {
+    // key chunks: an even number of <= 112 columns each (multiples of 16), balanced
+    const int n16 = a.NP / 16;
+    int nch = (n16 + 6) / 7;
+    if (nch < 2 && n16 >= 2) nch = 2;          // both softmax groups get work even for one small window
+    if (nch > 1 && (nch & 1)) ++nch;
+    if (nch > n16) nch = n16;
+    if (nch > T2_MAXCH) return false;
+    a.nchunks = nch;
     int pos = 0;
     for (int c = 0; c < nch; ++c) {
       const int blocks = n16 / nch + (c < n16 % nch ? 1 : 0);
@@ -604,8 +767,22 @@ static bool t2_plan(const AttnParams& p, AttnTc2Args& a, int& smem_out) {
       a.clen[c] = blocks * 16;
       pos += blocks * 16;
     }
-    for (int c = nch; c < T2_MAXCH; ++c) a.cstart[c] = a.clen[c] = 0;
+  } else {
+    // run pieces of 56 / 48 columns, two per chunk (112 / 96 columns); the last chunk may hold one, rounded up to the MMA's N granule
+    const int PW = a.mode == 1 ? 56 : 48;
+    const int npieces = (g.N + PW - 1) / PW;
+    const int nch = (npieces + 1) / 2;
+    if (nch > T2_MAXCH) return false;
+    a.nchunks = nch;
+    for (int c = 0; c < nch; ++c) {
+      const int pcs = c == nch - 1 ? npieces - 2 * (nch - 1) : 2;
+      a.cstart[c] = c * 2 * PW;
+      a.clen[c] = (pcs * PW + 15) & ~15;
+    }
+    a.NP = a.cstart[nch - 1] + a.clen[nch - 1];
   }
+  a.ngact = a.nchunks >= 2 ? 2 : 1;
+  for (int c = a.nchunks; c < T2_MAXCH; ++c) a.cstart[c] = a.clen[c] = 0;
   a.tail_rows = g.N - (a.ntiles - 1) * 128;
   a.r4 = (a.ntiles >= 2 && a.tail_rows <= T2_MAX_TAIL) ? 1 : 0;
   a.shifted = (g.sd | g.sh | g.sw) != 0;
@@ -675,12 +852,13 @@ int window_attn_tc2_dispatch(const AttnParams& p, cudaStream_t st) {
       sms = 148;
   }
   const int grid = a.units < sms ? a.units : sms;
-  static int configured = 0;
-  if (smem > configured) {
-    LAVT_CUDA(cudaFuncSetAttribute(window_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+  static int configured[3] = {0, 0, 0};
+  auto kfn = a.mode == 1 ? window_attn_tc2_kernel<1> : a.mode == 2 ? window_attn_tc2_kernel<2> : window_attn_tc2_kernel<0>;
+  if (smem > configured[a.mode]) {
+    LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[a.mode] = smem;
   }
-  window_attn_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
+  kfn<<<grid, T2_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
   LAVT_LAUNCH_CHECK("window_attn_tc2_kernel");
   return LAVT_OK;
 }

@@ -394,8 +394,10 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
     // LAVT_ATTN_IMPL=mma (or lavt_set_attention_impl(1)) forces the mma.sync kernels below
     const int impl = attn_impl_setting(-1);
     if (impl != 1) {
-      // auto: the one-pass chunked kernel (attn_tc2.cu, any window up to 1152 tokens); tc1 keeps the two-pass kernel (<= 400 tokens)
-      if (impl != 2 && window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
+      // auto: the resident two-pass kernel (attn_tc.cu) for windows of <= 400 tokens, where it is still the faster one (7.1 vs 8.0 ms
+      // per 8-clip step), the key-chunked one-pass kernel (attn_tc2.cu) for everything larger (8 x 12 x 12: 14.9 ms vs 21.8 ms for the
+      // mma.sync kernels); "tc2" forces the chunked kernel everywhere
+      if (impl == 3 && window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
       if (window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
       if (window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
     }
