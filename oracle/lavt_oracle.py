@@ -82,13 +82,13 @@ def _axis_region(p: Tensor, P: int, w: int, s: int) -> Tensor:
     return (p >= P - w).long() + (p >= P - s).long()
 
 
-def window_tokens(D, H, W, ws, ss, window_cfg):
+def window_tokens(D, H, W, ws, ss, window_cfg, device=None):
     """For every (window, token) of the padded+shifted grid: source coordinates, validity, relative
     position code and mask region id.  Returns tensors of shape (nW, N)."""
     nwd, nwh, nww = -(-D // ws[0]), -(-H // ws[1]), -(-W // ws[2])
     Dp, Hp, Wp = nwd * ws[0], nwh * ws[1], nww * ws[2]
-    a, b, c, td, th, tw = torch.meshgrid(torch.arange(nwd), torch.arange(nwh), torch.arange(nww),
-                                         torch.arange(ws[0]), torch.arange(ws[1]), torch.arange(ws[2]), indexing="ij")
+    ar = lambda n: torch.arange(n, device=device)          # noqa: E731  (index tensors live where the activations live)
+    a, b, c, td, th, tw = torch.meshgrid(ar(nwd), ar(nwh), ar(nww), ar(ws[0]), ar(ws[1]), ar(ws[2]), indexing="ij")
     pd, ph, pw = a * ws[0] + td, b * ws[1] + th, c * ws[2] + tw          # shifted-grid coordinates
     d, h, w = (pd + ss[0]) % Dp, (ph + ss[1]) % Hp, (pw + ss[2]) % Wp    # == roll(-ss) then partition (:228-234)
     valid = (d < D) & (h < H) & (w < W)                                   # pad rows are zeros AFTER norm1 (:218-224)
@@ -119,7 +119,7 @@ def swin_attention_half(x: Tensor, sd: Dict[str, Tensor], pre: str, num_heads: i
     B, D, H, W, C = x.shape
     shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
     ws, ss = effective_window((D, H, W), window, shift, clamp)
-    src, valid, code, rid = window_tokens(D, H, W, ws, ss, window)
+    src, valid, code, rid = window_tokens(D, H, W, ws, ss, window, device=x.device)
     nW, N = src.shape
     hd = C // num_heads
     xn = F.layer_norm(x, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5).reshape(B, D * H * W, C)
@@ -453,7 +453,7 @@ def decoder_forward(sd, x_c4, x_c3, x_c2, x_c1, capture: Optional[dict] = None, 
 
 def weighted_cross_entropy(logits: Tensor, target: Tensor) -> Tensor:
     """losses.py:7-11: F.cross_entropy with class weights [0.9, 1.1] (mean normalised by the summed weights)."""
-    return F.cross_entropy(logits, target, weight=torch.tensor([0.9, 1.1], dtype=logits.dtype))
+    return F.cross_entropy(logits, target, weight=torch.tensor([0.9, 1.1], dtype=logits.dtype, device=logits.device))
 
 
 def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Tensor, capture: Optional[dict] = None,
