@@ -27,7 +27,7 @@ extern "C" {
 #define LAVT_ERR_CUDA 2
 #define LAVT_ERR_ARCH 3
 
-enum { LAVT_ACT_NONE = 0, LAVT_ACT_GELU = 1, LAVT_ACT_RELU = 2, LAVT_ACT_TANH = 3 };
+enum { LAVT_ACT_NONE = 0, LAVT_ACT_GELU = 1, LAVT_ACT_RELU = 2, LAVT_ACT_TANH = 3, LAVT_ACT_SIGMOID = 4 };
 
 /* Window geometry of one Swin block on a (B,D,H,W,C) channels-last tensor.
  * (wd,wh,ww)/(sd,sh,sw) are the EFFECTIVE window/shift after get_window_size clamping
@@ -173,8 +173,33 @@ int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16,
 /* (B, Nl, C) fp32 -> (B, C, Nl) fp32: l_feats = last_hidden_state.permute(0, 2, 1) (lib/_utils.py:54) */
 int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream);
 
+/* ---- VLT fuse-and-classify head (lib/vlt.py:12-485; models vlt / lavt_vlt, lib/segmentation.py:299-433) ----
+ * The head's convolutions and Linear / Conv1d layers run on lavt_gemm_bf16 / lavt_conv3x3_bf16 (eval BatchNorm folded into the
+ * epilogue); these are the memory-bound pieces between them.
+ * lavt_rows_affine_act: out[r, c] = act((x[r, c] + add[r, c]) * v[r / rows_per_image, c] * s[c] + t[c]); add (bf16) / v / s / t may be NULL.
+ *   x bf16 or fp32 rows (pitch ldx), out bf16 and / or fp32 (pitch ldo).  x_c4 + vis_reduce_chann_1(x_c4), times the sentence vector,
+ *   joint_threshold BatchNorm + ReLU in one pass (:140-145), and the ReLU after lang_proj (:101-104).
+ * lavt_avgpool2_nhwc: nn.AvgPool2d(2) (:61, :151) over NHWC bf16 (pixel pitches ldi / ldo), even H and W.
+ * lavt_append_coords: vlt_concat_coords (:267-292): out NHWC bf16 [n,H,W,C+8] = in | x x x y y y 0 0 with x, y in [-1, 1].
+ * lavt_rows_add_table: out[r, :] = x[r, :] + table[r % period, :] -- PositionalEncoding (:204-222) on batch-major rows.
+ * lavt_mha_small: the attention core of nn.MultiheadAttention with head_dim 32 (:256, :262, :351): out[b, i, h*32:] =
+ *   softmax_j(q[b,i,h] . k[b,j,h] / sqrt(32) + (key_mask[b,j] == 0 ? -inf : 0)) v[b,j,h]; q [B,Lq] rows of pitch ldq etc., S <= 1024 keys.
+ * lavt_gate_transpose: out NHWC bf16 [B,S,Q] = gate[b*Q+q] * x[b*Q+q, s] -- gates * y of QueryBalancingModule (:405) and the
+ *   permute/view of q_to_spatial's output (:180-182) in one pass. */
+int lavt_rows_affine_act(const void* x, int32_t x_is_bf16, int64_t ldx, const void* add_bf16, int64_t lda, const float* v, int64_t rows_per_image,
+                         const float* s, const float* t, int32_t act, void* out_bf16, float* out_f32, int64_t ldo, int64_t rows, int32_t C,
+                         void* stream);
+int lavt_avgpool2_nhwc(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
+int lavt_append_coords(const void* in_bf16, int64_t ldi, void* out_bf16, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
+int lavt_rows_add_table(const void* x, int32_t x_is_bf16, int64_t ldx, const float* table, int64_t period, void* out_bf16, float* out_f32,
+                        int64_t ldo, int64_t rows, int32_t C, void* stream);
+int lavt_mha_small(const void* q_bf16, int64_t ldq, const void* k_bf16, int64_t ldk, const void* v_bf16, int64_t ldv, const float* key_mask,
+                   void* out_bf16, int64_t ldo, int32_t B, int32_t Lq, int32_t S, int32_t heads, void* stream);
+int lavt_gate_transpose(const float* x, int64_t ldx, const float* gate, int64_t ldg, void* out_bf16, int32_t B, int32_t Q, int32_t S, void* stream);
+
 /* ---- decoder glue (lib/mask_predictor.py:56-99, lib/_utils.py:106) ---- */
-/* out NHWC bf16 [n,H,W,C1+C2] = cat[bilinear(prev [n,ph,pw,C1] -> HxW, align_corners=True), skip [n,H,W,C2]] */
+/* out NHWC bf16 [n,H,W,C1+C2] = cat[bilinear(prev [n,ph,pw,C1] -> HxW, align_corners=True), skip [n,H,W,C2]];
+ * C2 = 0 (skip NULL) is a plain upsample: nn.Upsample(scale_factor=2, bilinear, align_corners=True) of lib/vlt.py:48,75,437-452 */
 int lavt_upsample_concat(const void* prev_bf16, int32_t ph, int32_t pw, int32_t C1, const void* skip_bf16, int32_t C2,
                          void* out_bf16, int32_t n_img, int32_t H, int32_t W, void* stream);
 /* conv1_1: logits[pix, 0:2] = y[pix, :] . w[0:2, :] + b */

@@ -15,7 +15,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "_lib", "liblavt_b200.so")
 
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 
 
 class WinGeom(C.Structure):
@@ -139,6 +139,12 @@ SIGNATURES = {
     "lavt_efn_norm_upsample": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_bcam_softmax_rows": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_bcam_transpose_pad": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp],
+    "lavt_rows_affine_act": [_vp, _i32, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp],
+    "lavt_avgpool2_nhwc": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+    "lavt_append_coords": [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_rows_add_table": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp],
+    "lavt_mha_small": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+    "lavt_gate_transpose": [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
 }
 EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
            "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
@@ -960,3 +966,105 @@ def efn_word_attend(score: torch.Tensor, mask: torch.Tensor, g: torch.Tensor, ou
         raise LavtError("efn_word_attend: shape mismatch")
     check(lib().lavt_efn_word_attend(score.data_ptr(), score.stride(0), _c(mask, torch.float32, "mask").data_ptr(), _c(g, torch.float32, "g").data_ptr(),
                                      g.shape[1], _c(out, torch.float32, "out").data_ptr(), B, rows // B, Nl, Cn, stream_ptr()), "lavt_efn_word_attend")
+
+
+# ---- VLT head glue (csrc/vlt_kernels.cu) ----
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise LavtError(f"{name} must be a 2-D CUDA tensor with contiguous rows (no CPU fallback)")
+    return t
+
+
+def rows_affine_act(x: torch.Tensor, *, add: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None, rows_per_image: int = 0,
+                    s: Optional[torch.Tensor] = None,
+                    t: Optional[torch.Tensor] = None, act: int = ACT_NONE, out_bf16: Optional[torch.Tensor] = None,
+                    out_f32: Optional[torch.Tensor] = None) -> None:
+    """out[r, c] = act((x[r, c] + add[r, c]) * v[r // rows_per_image, c] * s[c] + t[c]); x bf16 / fp32 [rows, C] (row pitch free), add bf16."""
+    _rows2d(x, "x")
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise LavtError("rows_affine_act: x must be bf16 or fp32")
+    rows, Cn = x.shape
+    out = out_bf16 if out_bf16 is not None else out_f32
+    if out is None:
+        raise LavtError("rows_affine_act needs an output")
+    for o, dt, nm in ((out_bf16, torch.bfloat16, "out_bf16"), (out_f32, torch.float32, "out_f32")):
+        if o is not None and (_rows2d(o, nm).dtype != dt or tuple(o.shape) != (rows, Cn) or o.stride(0) != out.stride(0)):
+            raise LavtError(f"rows_affine_act: {nm} has the wrong dtype / shape / pitch")
+    for vec, nm in ((s, "s"), (t, "t")):
+        if vec is not None:
+            _c(vec, torch.float32, nm)
+    if add is not None:
+        _req(_rows2d(add, "add"), torch.bfloat16, "add")
+        if tuple(add.shape) != (rows, Cn):
+            raise LavtError("rows_affine_act: addend shape mismatch")
+    check(lib().lavt_rows_affine_act(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), ptr(add), add.stride(0) if add is not None else 0,
+                                     _c(v, torch.float32, "v").data_ptr() if v is not None else None, int(rows_per_image), ptr(s), ptr(t), int(act),
+                                     ptr(out_bf16), ptr(out_f32), out.stride(0), rows, Cn, stream_ptr()), "lavt_rows_affine_act")
+
+
+def avgpool2_nhwc(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x bf16 [n,H,W,C] (pixel pitch x.stride(2)) -> out bf16 [n,H/2,W/2,C] (pixel pitch out.stride(2))."""
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    n, H, W, Cn = x.shape
+    if tuple(out.shape) != (n, H // 2, W // 2, Cn):
+        raise LavtError("avgpool2: shape mismatch")
+    check(lib().lavt_avgpool2_nhwc(x.data_ptr(), x.stride(2), out.data_ptr(), out.stride(2), n, H, W, Cn, stream_ptr()), "lavt_avgpool2_nhwc")
+
+
+def append_coords(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x bf16 [n,H,W,C] (pixel pitch free) -> out bf16 contiguous [n,H,W,C+8] = x | xxx yyy 00 (vlt_concat_coords)."""
+    _req(x, torch.bfloat16, "x")
+    n, H, W, Cn = x.shape
+    if tuple(out.shape) != (n, H, W, Cn + 8):
+        raise LavtError("append_coords: shape mismatch")
+    check(lib().lavt_append_coords(x.data_ptr(), x.stride(2), _c(out, torch.bfloat16, "out").data_ptr(), n, H, W, Cn, stream_ptr()),
+          "lavt_append_coords")
+
+
+def rows_add_table(x: torch.Tensor, table: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None) -> None:
+    """out[r, :] = x[r, :] + table[r % table.shape[0], :]."""
+    _rows2d(x, "x")
+    rows, Cn = x.shape
+    out = out_bf16 if out_bf16 is not None else out_f32
+    if out is None or table.shape[1] != Cn:
+        raise LavtError("rows_add_table: missing output / table width mismatch")
+    for o in (out_bf16, out_f32):
+        if o is not None and (tuple(o.shape) != (rows, Cn) or o.stride(0) != out.stride(0)):
+            raise LavtError("rows_add_table: output shape / pitch mismatch")
+    check(lib().lavt_rows_add_table(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _c(table, torch.float32, "table").data_ptr(),
+                                    table.shape[0], ptr(out_bf16), ptr(out_f32), out.stride(0), rows, Cn, stream_ptr()), "lavt_rows_add_table")
+
+
+def mha_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, heads: int, key_mask: Optional[torch.Tensor] = None) -> None:
+    """q bf16 [B*Lq, >= heads*32], k / v bf16 [B*S, >= heads*32] (column windows of packed projections are fine), out bf16 [B*Lq, heads*32];
+    key_mask fp32 [B, S] with 0 = ignore the key."""
+    for t_, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(_rows2d(t_, nm), torch.bfloat16, nm)
+    Lq, S = q.shape[0] // B, k.shape[0] // B
+    if q.shape[0] != B * Lq or k.shape[0] != B * S or v.shape[0] != B * S or out.shape[0] != B * Lq:
+        raise LavtError("mha_small: row counts are not multiples of the batch")
+    check(lib().lavt_mha_small(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                               _c(key_mask, torch.float32, "key_mask").data_ptr() if key_mask is not None else None, out.data_ptr(), out.stride(0),
+                               B, Lq, S, heads, stream_ptr()), "lavt_mha_small")
+
+
+def gate_transpose(x: torch.Tensor, gate: torch.Tensor, out: torch.Tensor, B: int) -> None:
+    """x fp32 [B*Q, S], gate fp32 [B*Q, >=1] (first column used) -> out bf16 [B, S, Q]."""
+    _req(_rows2d(x, "x"), torch.float32, "x")
+    _req(_rows2d(gate, "gate"), torch.float32, "gate")
+    Q, S = x.shape[0] // B, x.shape[1]
+    if tuple(out.shape) != (B, S, Q):
+        raise LavtError("gate_transpose: shape mismatch")
+    check(lib().lavt_gate_transpose(x.data_ptr(), x.stride(0), gate.data_ptr(), gate.stride(0), _c(out, torch.bfloat16, "out").data_ptr(), B, Q, S,
+                                    stream_ptr()), "lavt_gate_transpose")
+
+
+def upsample_nhwc(prev: torch.Tensor, out: torch.Tensor) -> None:
+    """Bilinear (align_corners=True) resize of prev bf16 [n,ph,pw,C] to out bf16 [n,H,W,C] (lavt_upsample_concat with no skip tensor)."""
+    _c(prev, torch.bfloat16, "prev")
+    n, ph, pw, C1 = prev.shape
+    if out.shape[0] != n or out.shape[3] != C1:
+        raise LavtError("upsample_nhwc: shape mismatch")
+    check(lib().lavt_upsample_concat(prev.data_ptr(), ph, pw, C1, None, 0, _c(out, torch.bfloat16, "out").data_ptr(), n, out.shape[1], out.shape[2],
+                                     stream_ptr()), "lavt_upsample_concat")

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(32) bcam_words_kernel(const float* __restrict_
       if (j0 + j < Nl) {
         f = acc[j] + bc;
         if (act == LAVT_ACT_GELU) f = gelu_erf(f);
+        else if (act == LAVT_ACT_RELU) f = fmaxf(f, 0.f);          // VLT project_lang (lib/vlt.py:320-322)
         if (mask) f *= mask[b * Nl + j0 + j];
       }
       const __nv_bfloat16 v = __float2bfloat16(f);
@@ -277,7 +278,7 @@ using namespace lavt;
 
 extern "C" int lavt_bcam_words(const float* l, const float* w, const float* bias, const float* mask, int32_t act, void* lr_bf16,
                                void* lrT_bf16, int32_t B, int32_t Nl, int32_t Nlp, int32_t Lin, int32_t C, void* stream) {
-  LAVT_REQUIRE(act == LAVT_ACT_NONE || act == LAVT_ACT_GELU, "bcam_words: activation %d not supported", act);
+  LAVT_REQUIRE(act == LAVT_ACT_NONE || act == LAVT_ACT_GELU || act == LAVT_ACT_RELU, "bcam_words: activation %d not supported", act);
   LAVT_REQUIRE(B > 0 && Nl > 0 && Nlp >= Nl && Lin > 0 && C > 0 && B < 65536, "bcam_words: bad sizes (B=%d Nl=%d Nlp=%d)", B, Nl, Nlp);
   LAVT_REQUIRE(l && w && bias && lr_bf16 && lrT_bf16, "bcam_words: missing buffers");
   bcam_words_kernel<<<dim3(C, (Nlp + BCAM_WCHUNK - 1) / BCAM_WCHUNK, B), 32, 0, static_cast<cudaStream_t>(stream)>>>(

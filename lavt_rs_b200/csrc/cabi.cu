@@ -27,7 +27,7 @@ static int fill_epilogue(GemmParams& p, const lavt_epilogue_t* e) {
   p.rscale = e->rscale;
   p.rs_rows = e->rscale_rows;
   LAVT_REQUIRE(!e->rscale || e->rscale_rows > 0, "epilogue: rscale needs rscale_rows > 0");
-  LAVT_REQUIRE(e->act >= 0 && e->act <= 3, "bad activation id %d", e->act);
+  LAVT_REQUIRE(e->act >= 0 && e->act <= 4, "bad activation id %d", e->act);
   if (e->win) {
     p.rowmap = ROWMAP_WINDOW;
     std::memcpy(&p.win, e->win, sizeof(WinGeom));

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat1
 
 int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,
                              __nv_bfloat16* out, int n_img, int H, int W, cudaStream_t st) {
-  LAVT_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 > 0, "upsample_concat: channels must be multiples of 8");
+  // C2 == 0 (skip may be NULL): plain bilinear upsample -- the nn.Upsample(x2) steps of ProgressiveDecoding (lib/vlt.py:437-452)
+  LAVT_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || skip != nullptr), "upsample_concat: channels must be multiples of 8");
   LAVT_REQUIRE(ph <= H && pw <= W && ph > 0 && pw > 0, "upsample_concat: prev (%dx%d) larger than skip (%dx%d)", ph, pw, H, W);
   LAVT_REQUIRE(n_img > 0 && n_img < 65536 && H > 0 && H < 65536 && W > 0, "upsample_concat: empty or too large input");
   const int per_row = W * ((C1 + C2) / 8);

@@ -418,6 +418,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (p.act == ACT_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
+        } else if (p.act == ACT_SIGMOID) {       // sigmoid(x) = 0.5 tanh(x / 2) + 0.5
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaf(0.5f, tanh_fast(0.5f * f[j]), 0.5f);
         }
         if (mul_row) {
 #pragma unroll

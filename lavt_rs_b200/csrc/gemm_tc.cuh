@@ -5,7 +5,7 @@
 
 namespace lavt {
 
-enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2, ROWMAP_WGCONV = 3 };
 
 // out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] * rscale[orow(m) / rs_rows] + resid[orow(m), n]

@@ -621,3 +621,247 @@ def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: 
         K.upsample_logits(lg, logits_nchw)      # same size: exact NHWC -> NCHW transposition
         _count(1)
     return lg
+
+
+# ------------------------------------------------------------------------------------------------
+# VLT fuse-and-classify head (reference VLTFuseAndClassify.forward, lib/vlt.py:129-199, and the modules it owns)
+# ------------------------------------------------------------------------------------------------
+def _fold_conv_bn(conv, bn, pad_cin: int = 0):
+    """Conv2d (no bias) weight as a GEMM / tap-major operand + the eval BatchNorm folded to (scale, shift)."""
+    w = conv.weight.detach()
+    if w.shape[-1] == 1:
+        wt = w.reshape(w.shape[0], -1)
+    else:                                          # [Cout, Cin, 3, 3] -> [Cout, (ky*3+kx)*Cin' + ci], input channels zero-padded to Cin'
+        cin = w.shape[1] + pad_cin
+        wp = torch.zeros(w.shape[0], 3, 3, cin, device=w.device, dtype=w.dtype)
+        wp[..., : w.shape[1]] = w.permute(0, 2, 3, 1)
+        wt = wp.reshape(w.shape[0], -1)
+    s, b = _bn_fold(bn)
+    return wt.to(torch.bfloat16).contiguous(), s, b
+
+
+def _pad_rows(w: torch.Tensor, rows: int) -> torch.Tensor:
+    out = torch.zeros(rows, w.shape[1], device=w.device, dtype=torch.bfloat16)
+    out[: w.shape[0]] = w.detach()
+    return out
+
+
+def _mha_layer(pw: PreparedWeights, tag: str, mha, xq_b: torch.Tensor, xkv_b: torch.Tensor, B: int, ws: Workspace, key_mask=None,
+               *, resid: torch.Tensor, out_f32: torch.Tensor, out_bf16: Optional[torch.Tensor] = None) -> None:
+    """nn.MultiheadAttention forward on batch-major rows: xq_b bf16 [B*Lq, E], xkv_b bf16 [B*S, E]; writes resid + attention output."""
+    Em = mha.embed_dim
+    dev = xq_b.device
+    w_in = pw.get(tag + "_win", [mha.in_proj_weight], lambda: _bf16(mha.in_proj_weight))
+    b_in = pw.get(tag + "_bin", [mha.in_proj_bias], lambda: _f32(mha.in_proj_bias))
+    w_out = pw.get(tag + "_wout", [mha.out_proj.weight], lambda: _bf16(mha.out_proj.weight))
+    nq, nk = xq_b.shape[0], xkv_b.shape[0]
+    if xq_b.data_ptr() == xkv_b.data_ptr():                 # self-attention: one packed projection
+        qkv = ws.get("vlt_qkv", (nq, 3 * Em), torch.bfloat16, dev)
+        K.gemm_bf16(xq_b, w_in, bias=b_in, out_bf16=qkv)
+        q, k, v = qkv[:, :Em], qkv[:, Em:2 * Em], qkv[:, 2 * Em:]
+        _count(1)
+    else:
+        qb = ws.get("vlt_q", (nq, Em), torch.bfloat16, dev)
+        kv = ws.get("vlt_kv", (nk, 2 * Em), torch.bfloat16, dev)
+        K.gemm_bf16(xq_b, w_in[:Em], bias=b_in[:Em], out_bf16=qb)
+        K.gemm_bf16(xkv_b, w_in[Em:], bias=b_in[Em:], out_bf16=kv)
+        q, k, v = qb, kv[:, :Em], kv[:, Em:]
+        _count(2)
+    att = ws.get("vlt_att", (nq, Em), torch.bfloat16, dev)
+    K.mha_small(q, k, v, att, B, mha.num_heads, key_mask=key_mask)
+    K.gemm_bf16(att, w_out, bias=mha.out_proj.bias.detach(), resid=resid, out_f32=out_f32, out_bf16=out_bf16)
+    _count(2)
+
+
+def _post_norm(x32: torch.Tensor, xb: torch.Tensor, ln) -> None:
+    K.layernorm_rows(x32, ln.weight, ln.bias, out_f32=x32, out_bf16=xb, eps=ln.eps)     # row-wise: safe in place
+    _count(1)
+
+
+def _ffn_layer(pw: PreparedWeights, tag: str, layer, x32: torch.Tensor, xb: torch.Tensor, ws: Workspace) -> None:
+    w1 = pw.get(tag + "_w1", [layer.linear1.weight], lambda: _bf16(layer.linear1.weight))
+    w2 = pw.get(tag + "_w2", [layer.linear2.weight], lambda: _bf16(layer.linear2.weight))
+    hid = ws.get("vlt_ffn", (x32.shape[0], w1.shape[0]), torch.bfloat16, x32.device)
+    K.gemm_bf16(xb, w1, bias=layer.linear1.bias.detach(), act=K.ACT_RELU, out_bf16=hid)
+    K.gemm_bf16(hid, w2, bias=layer.linear2.bias.detach(), resid=x32, out_f32=x32)
+    _count(2)
+
+
+def vlt_head(head, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, l: torch.Tensor, mask: torch.Tensor, ws: Workspace) -> torch.Tensor:
+    """c4 / c3 / c2 bf16 NHWC [B, s/2, s/2, 1024] / [B, s, s, 512] / [B, 2s, 2s, 256]; l fp32 [B,768,Nl]; mask fp32 [B,Nl].
+    Returns the logits as an NHWC fp32 workspace view [B, 8s, 8s, 2]."""
+    dev = c4.device
+    pw = head.prepared
+    B, s4, _, C4 = c4.shape
+    s = c3.shape[1]
+    if head.training:
+        raise K.LavtError("the VLT head on the B200 path is inference-only (BatchNorm must be in eval mode)")
+    if (s, 2 * s4, c2.shape[1]) != (head.size, s, 2 * s) or c3.shape[2] != s or (C4, c3.shape[3], c2.shape[3]) != (1024, 512, 256):
+        raise K.LavtError(f"VLT head built for img_size {16 * head.size}: needs {head.size // 2}^2 x 1024, {head.size}^2 x 512 and "
+                          f"{2 * head.size}^2 x 256 maps, got {tuple(c4.shape)}, {tuple(c3.shape)}, {tuple(c2.shape)}")
+    P4, P3, Q, Dm = B * s4 * s4, B * s * s, head.num_queries, head.d_model
+    Nl = l.shape[-1]
+
+    def cb(tag, seq, i=0, pad_cin=0):
+        return pw.get(tag, [seq[i].weight, seq[i + 1].weight, seq[i + 1].bias, seq[i + 1].running_mean, seq[i + 1].running_var],
+                      lambda: _fold_conv_bn(seq[i], seq[i + 1], pad_cin))
+
+    def conv1(x2d, tag, seq, out, i=0, **kw):              # 1x1 conv + BN + ReLU on rows
+        w, sc, bi = cb(tag, seq, i)
+        K.gemm_bf16(x2d, w, cscale=sc, bias=bi, act=K.ACT_RELU, out_bf16=out, **kw)
+        _count(1)
+
+    def conv3(x4d, tag, seq, out2d, i=0, pad_cin=0):       # 3x3 conv + BN + ReLU on NHWC
+        w, sc, bi = cb(tag, seq, i, pad_cin)
+        K.conv3x3_bf16(x4d, w, cscale=sc, bias=bi, act=K.ACT_RELU, out_bf16=out2d)
+        _count(1)
+
+    # ---- sentence vector: masked mean -> Linear -> BatchNorm1d -> ReLU  (:137-139)
+    lp, bn1 = head.lang_proj[0], head.lang_proj[1]
+
+    def _lang_fold():
+        sc, sh = _bn_fold(bn1)
+        return (_f32(lp.weight) * sc[:, None]).contiguous(), (_f32(lp.bias) * sc + sh).contiguous()
+    lw, lb = pw.get("lang_proj", [lp.weight, lp.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var], _lang_fold)
+    sent = ws.get("vlt_sent", (B, C4), torch.float32, dev)
+    K.efn_sentence_bias(l, mask, lw, lb, sent)
+    K.rows_affine_act(sent, act=K.ACT_RELU, out_f32=sent)
+    # ---- x_mm_c4 = ReLU(BN((x_c4 + bottleneck(x_c4)) * sentence))  (:140-145)
+    t1 = ws.get("vlt_t1", (B, s4, s4, C4 // 2), torch.bfloat16, dev)
+    conv1(c4.view(P4, C4), "vr1a", head.vis_reduce_chann_1, t1.view(P4, C4 // 2))
+    y4 = ws.get("vlt_y4", (P4, C4), torch.bfloat16, dev)
+    conv3(t1, "vr1b", head.vis_reduce_chann_1, y4, i=3)
+    jt_s, jt_b = pw.get("jt", [head.joint_threshold[0].weight, head.joint_threshold[0].bias, head.joint_threshold[0].running_mean,
+                               head.joint_threshold[0].running_var], lambda: _bn_fold(head.joint_threshold[0]))
+    mm4 = ws.get("vlt_mm4", (B, s4, s4, C4), torch.bfloat16, dev)
+    K.rows_affine_act(y4, add=c4.view(P4, C4), v=sent, rows_per_image=s4 * s4, s=jt_s, t=jt_b, act=K.ACT_RELU, out_bf16=mm4.view(P4, C4))
+    _count(4)
+    # ---- level-3 fusion.  BUF columns: temp3 | Fm_mid_query | reduced c2, so both concatenations (:155, :159) are column windows
+    u1 = ws.get("vlt_u1", (B, s, s, C4 + 512), torch.bfloat16, dev)            # up(x_mm_c4) | vis_reduce_chann_2(x_c3), later | project_again(..)
+    t2 = ws.get("vlt_t2", (B, s, s, 512), torch.bfloat16, dev)
+    conv1(c3.view(P3, 512), "vr2", head.vis_reduce_chann_2, t2.view(P3, 512))
+    K.upsample_concat(mm4, t2, u1)
+    buf = ws.get("vlt_buf", (P3, 1280), torch.bfloat16, dev)
+    u1r = u1.view(P3, C4 + 512)
+    conv1(u1r, "f12", head.fuse_1_2, buf[:, 512:1024])
+    c2p = ws.get("vlt_c2p", (B, s, s, 256), torch.bfloat16, dev)
+    K.avgpool2_nhwc(c2, c2p)
+    conv1(c2p.view(P3, 256), "vr3", head.vis_reduce_chann_3, buf[:, 1024:1280])
+    fmq = ws.get("vlt_fmq", (B, s, s, 512), torch.bfloat16, dev)
+    conv1(buf[:, 512:1280], "f23", head.fuse_2_3, fmq.view(P3, 512))
+    h0 = ws.get("vlt_h0", (B, s, s, 256), torch.bfloat16, dev)
+    conv1(fmq.view(P3, 512), "h23a", head.hallucinate_result_of_23, h0.view(P3, 256))
+    conv3(h0, "h23b", head.hallucinate_result_of_23, buf[:, 0:512], i=3)
+    conv1(buf[:, 0:1024], "pa", head.project_again, u1r[:, C4:])                # overwrites the dead vis_reduce_chann_2 columns
+    f1 = ws.get("vlt_f1", (P3, Dm), torch.bfloat16, dev)
+    conv1(u1r, "fa", head.fuse_again, f1)
+    ftf = ws.get("vlt_ftf", (P3, Dm), torch.bfloat16, dev)
+    conv1(f1, "lp", head.last_project, ftf)
+    _count(2)
+    # ---- query generation (:329-356)
+    qg = head.query_generation
+    yc = ws.get("vlt_yc", (B, s, s, 520), torch.bfloat16, dev)
+    K.append_coords(fmq, yc)
+    ya = ws.get("vlt_ya", (B, s, s, 512), torch.bfloat16, dev)
+    yb = ws.get("vlt_yb", (B, s, s, 512), torch.bfloat16, dev)
+    conv3(yc, "qg_p1a", qg.project_1, ya.view(P3, 512), i=0, pad_cin=2)
+    conv3(ya, "qg_p1b", qg.project_1, yb.view(P3, 512), i=3)
+    conv3(yb, "qg_p1c", qg.project_1, ya.view(P3, 512), i=6)
+    w_p2 = pw.get("qg_p2", [qg.project_2.weight], lambda: _pad_rows(qg.project_2.weight.reshape(Q, -1), 32))
+    y16 = ws.get("vlt_y16", (P3, 32), torch.bfloat16, dev)
+    K.gemm_bf16(ya.view(P3, 512), w_p2, out_bf16=y16)
+    n8 = (s * s + 7) // 8 * 8
+    yT = ws.get("vlt_yT", (B, 32, n8), torch.bfloat16, dev)
+    K.bcam_transpose_pad(y16, yT)
+
+    def _wq():
+        w = torch.zeros(Dm, n8, device=dev, dtype=torch.bfloat16)
+        w[:, : s * s] = qg.project_query[0].weight.detach()[:, :, 0]
+        return w
+    w_q = pw.get("qg_pq", [qg.project_query[0].weight], _wq)
+    vis32 = ws.get("vlt_vis32", (B * Q, Dm), torch.float32, dev)
+    for b in range(B):
+        K.gemm_bf16(yT[b, :Q], w_q, act=K.ACT_RELU, out_f32=vis32[b * Q:(b + 1) * Q])
+    xq = ws.get("vlt_xq", (B * Q, Dm), torch.bfloat16, dev)
+    pe_q = pw.get("qg_pe_q", [qg.pos_encoder.pe], lambda: qg.pos_encoder.table(Q))
+    K.rows_add_table(vis32, pe_q, out_bf16=xq)
+    w_pl = pw.get("qg_pl", [qg.project_lang[0].weight], lambda: _f32(qg.project_lang[0].weight[:, :, 0]))
+    zb = pw.get("qg_zb", [], lambda: torch.zeros(Dm, device=dev, dtype=torch.float32))
+    lr = ws.get("vlt_lr", (B, Nl, Dm), torch.bfloat16, dev)
+    lrT = ws.get("vlt_lrT", (B, Dm, Nl), torch.bfloat16, dev)
+    K.bcam_words(l, w_pl, zb, lr, lrT, act=K.ACT_RELU)
+    pe_l = pw.get("qg_pe_l%d" % Nl, [qg.pos_encoder.pe], lambda: qg.pos_encoder.table(Nl))
+    K.rows_add_table(lr.view(B * Nl, Dm), pe_l, out_bf16=lr.view(B * Nl, Dm))
+    nd32 = ws.get("vlt_nd32", (B * Q, Dm), torch.float32, dev)
+    ndb = ws.get("vlt_ndb", (B * Q, Dm), torch.bfloat16, dev)
+    _mha_layer(pw, "qg_mha", qg.query_gen, xq, lr.view(B * Nl, Dm), B, ws, key_mask=mask, resid=vis32, out_f32=nd32, out_bf16=ndb)
+    _count(8 + B)
+    # ---- transformer encoder over the s*s memory, decoder over the 16 queries (:244-264)
+    tf = head.transformer_fusion
+    mem32 = ws.get("vlt_mem32", (P3, Dm), torch.float32, dev)
+    memb = ws.get("vlt_memb", (P3, Dm), torch.bfloat16, dev)
+    pe_m = pw.get("tf_pe_m", [tf.pos_encoder.pe], lambda: tf.pos_encoder.table(s * s))
+    K.rows_add_table(ftf, pe_m, out_bf16=memb, out_f32=mem32)
+    for i, layer in enumerate(tf.transformer_encoder.layers):
+        _mha_layer(pw, "enc%d_sa" % i, layer.self_attn, memb, memb, B, ws, resid=mem32, out_f32=mem32)
+        _post_norm(mem32, memb, layer.norm1)
+        _ffn_layer(pw, "enc%d" % i, layer, mem32, memb, ws)
+        _post_norm(mem32, memb, layer.norm2)
+    out32 = ws.get("vlt_out32", (B * Q, Dm), torch.float32, dev)
+    outb = ws.get("vlt_outb", (B * Q, Dm), torch.bfloat16, dev)
+    pe_t = pw.get("tf_pe_q", [tf.pos_encoder.pe], lambda: tf.pos_encoder.table(Q))
+    K.rows_add_table(nd32, pe_t, out_bf16=outb, out_f32=out32)
+    for i, layer in enumerate(tf.transformer_decoder.layers):
+        _mha_layer(pw, "dec%d_sa" % i, layer.self_attn, outb, outb, B, ws, resid=out32, out_f32=out32)
+        _post_norm(out32, outb, layer.norm1)
+        _mha_layer(pw, "dec%d_ca" % i, layer.multihead_attn, outb, memb, B, ws, resid=out32, out_f32=out32)
+        _post_norm(out32, outb, layer.norm2)
+        _ffn_layer(pw, "dec%d" % i, layer, out32, outb, ws)
+        _post_norm(out32, outb, layer.norm3)
+    _count(2)
+    # ---- query balancing (:396-405) + q_to_spatial (:180-182): relu(W (g y)) = g relu(W y) because the gate is a sigmoid (> 0)
+    qb = head.query_balancing
+    cat2 = ws.get("vlt_cat2", (B * Q, 2 * Dm), torch.bfloat16, dev)            # y | x
+    wn = pw.get("qb_wn", [qb.not_decoded_query_proj[0].weight], lambda: _bf16(qb.not_decoded_query_proj[0].weight[:, :, 0]))
+    wd = pw.get("qb_wd", [qb.decoded_query_proj[0].weight], lambda: _bf16(qb.decoded_query_proj[0].weight[:, :, 0]))
+    K.gemm_bf16(ndb, wn, act=K.ACT_RELU, out_bf16=cat2[:, Dm:])
+    K.gemm_bf16(outb, wd, act=K.ACT_RELU, out_bf16=cat2[:, :Dm])
+    g0 = pw.get("qb_g0", [qb.gate_proj[0].weight], lambda: _bf16(qb.gate_proj[0].weight[:, :, 0]))
+    g2 = pw.get("qb_g2", [qb.gate_proj[2].weight], lambda: _pad_rows(qb.gate_proj[2].weight[:, :, 0], 32))
+    gh = ws.get("vlt_gh", (B * Q, Dm), torch.bfloat16, dev)
+    K.gemm_bf16(cat2, g0, act=K.ACT_RELU, out_bf16=gh)
+    gate = ws.get("vlt_gate", (B * Q, 32), torch.float32, dev)
+    K.gemm_bf16(gh, g2, act=K.ACT_SIGMOID, out_f32=gate)
+    ns = (s * s + 31) // 32 * 32
+    w_qs = pw.get("q2s", [head.q_to_spatial[0].weight], lambda: _pad_rows(head.q_to_spatial[0].weight[:, :, 0], ns))
+    sp = ws.get("vlt_sp", (B * Q, ns), torch.float32, dev)
+    K.gemm_bf16(cat2[:, :Dm], w_qs, act=K.ACT_RELU, out_f32=sp)
+    qmap = ws.get("vlt_qmap", (B, s * s, Q), torch.bfloat16, dev)
+    K.gate_transpose(sp[:, : s * s], gate, qmap, B)
+    _count(6)
+    # ---- spatial refinement + progressive decoding (:183-186, :459-485)
+    dec = head.decoding
+    cur = ws.get("vlt_d0", (B, s, s, Dm), torch.bfloat16, dev)
+    conv3(qmap.view(B, s, s, Q), "sr", head.spatial_refine, cur.view(P3, Dm))
+
+    def dconv(x4d, name):
+        conv, bn = getattr(dec, "conv" + name), getattr(dec, "bn" + name)
+        w, sc, bi = pw.get("dec" + name, [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: _fold_conv_bn(conv, bn))
+        n_, H_, W_, _ = x4d.shape
+        o = ws.get("vlt_dc_%s" % name, (n_, H_, W_, Dm), torch.bfloat16, dev)
+        K.conv3x3_bf16(x4d, w, cscale=sc, bias=bi, act=K.ACT_RELU, out_bf16=o.view(-1, Dm))
+        _count(1)
+        return o
+    cur = dconv(dconv(cur, "1_4"), "2_4")
+    for name in ("1_3", "1_2", "1_1"):
+        n_, H_, W_, _ = cur.shape
+        up = ws.get("vlt_up_%s" % name, (n_, 2 * H_, 2 * W_, Dm), torch.bfloat16, dev)
+        K.upsample_nhwc(cur, up)
+        _count(1)
+        cur = dconv(up, name)
+    n_, H_, W_, _ = cur.shape
+    w11 = pw.get("cls_w", [dec.classifier.weight], lambda: _f32(dec.classifier.weight.reshape(2, -1)))
+    lg = ws.get("vlt_logits", (n_, H_, W_, 2), torch.float32, dev)
+    K.conv1x1_logits(cur.view(-1, Dm), w11, dec.classifier.bias.detach(), lg.view(-1, 2))
+    _count(1)
+    return lg

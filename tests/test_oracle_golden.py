@@ -66,3 +66,16 @@ def test_oracle_autograd_reproduces_reference_training_step():
             if key.startswith("g:"):
                 a, b = leaf[key[2:]].grad.numpy(), gold[key]
                 assert np.linalg.norm(a - b) < 5e-3 * np.linalg.norm(b) + 1e-9, key
+
+
+def test_vlt_oracle_reproduces_reference_head():
+    """oracle/vlt_oracle.py vs the golden outputs of the unmodified reference VLTFuseAndClassify (oracle/make_golden_vlt.py)."""
+    from oracle import vlt_oracle as VO
+    from oracle.make_golden_vlt import VLT_CASES, vlt_case
+    for name, c in VLT_CASES.items():
+        gold = np.load(os.path.join(OUT, name + ".npz"))["logits"]
+        _, sd, (c4, c3, c2, l, mask) = vlt_case(c)
+        with torch.no_grad():
+            got = VO.vlt_fuse_and_classify(sd, c4, c3, c2, l, mask).numpy()
+        assert got.shape == gold.shape
+        assert np.abs(got - gold).max() < 2e-4 * max(1.0, np.abs(gold).max()), (name, np.abs(got - gold).max())
