@@ -101,6 +101,47 @@ class LAVTOne(_Segmenter):
         return self._segment(x5, l_feats, l_mask, x.shape[-2:], lang_ready=ev)
 
 
+class _VLTBase(_Segmenter):
+    """Encoder with three outputs (strides 8 / 16 / 32) + VLTFuseAndClassify + BERT (reference lib/_utils.py:279-343)."""
+    fused_backbone = True
+
+    def __init__(self, backbone, classifier, args=None, link=None):
+        super().__init__()
+        self.backbone, self.classifier, self.link = backbone, classifier, link
+        self.model = getattr(args, "model", None)
+        self.text_encoder = _build_text_encoder(args)
+
+    def forward(self, x, text, l_mask):
+        E.require_cuda(x, "x")
+        if self._train_mode():
+            raise NotImplementedError("the VLT head is inference-only on the B200 path")
+        l_feats, ev = self._encode_text_async(text, l_mask)
+        x5 = _planes(x).unsqueeze(2)
+        if self.fused_backbone:
+            _, nhwc = self.backbone.run(x5, _lang(l_feats), _mask(l_mask), want_nchw=False, want_nhwc_bf16=True, lang_ready=ev)
+        else:
+            _, nhwc = self.backbone.run(x5, None, None, want_nchw=False, want_nhwc_bf16=True)
+            torch.cuda.current_stream().wait_event(ev)
+        if len(nhwc) != 3:
+            raise K.LavtError("the VLT head reads three stage outputs: build the backbone with out_indices=(1, 2, 3)")
+        c2, c3, c4 = nhwc
+        ws = E.workspace(c4.device)
+        lg = E.vlt_head(self.classifier, c4, c3, c2, _lang(l_feats), _mask(l_mask), ws)
+        out = torch.empty(lg.shape[0], 2, x.shape[-2], x.shape[-1], device=lg.device, dtype=torch.float32)
+        K.upsample_logits(lg, out)                       # F.interpolate(..., size=input_shape, bilinear, align_corners=True) (:301, :336)
+        E._count(1)
+        return out
+
+
+class VLT(_VLTBase):
+    """Plain Swin encoder + VLT head (reference :279-307): the image branch never sees the language features."""
+    fused_backbone = False
+
+
+class LAVT_VLT(_VLTBase):
+    """LAVT encoder (PWAM + gates) + VLT head (reference :314-342)."""
+
+
 class LAVTVideo(_Segmenter):
     """Video model (reference :76-131): x (B,T,3,H,W) -> (B*T,2,H,W)."""
     video = True

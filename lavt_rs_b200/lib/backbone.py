@@ -258,3 +258,29 @@ class MultiModalSwinTransformer(V.MultiModalSwinTransformer3D):
         E.require_cuda(x, "x")
         nchw, _ = self.run(V._planes(x).unsqueeze(2), V._lang(l), V._mask(l_mask), want_nchw=True, want_nhwc_bf16=False)
         return tuple(nchw)
+
+
+class SwinTransformer(MultiModalSwinTransformer):
+    """Plain 2-D Swin backbone without language fusion (reference lib/backbone.py:1512-1650; the encoder of the ``vlt`` model,
+    lib/segmentation.py:299-352): ``forward(x[B,3,H,W])`` -> tuple of LayerNorm-ed stage outputs (B, C_i, H_i, W_i).  Same
+    state-dict keys as the reference class: ``patch_embed.*``, ``layers.{i}.blocks.*``, ``layers.{i}.downsample.*``, ``norm{i}.*``."""
+
+    def __init__(self, pretrain_img_size=224, patch_size=4, in_chans=3, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                 window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2,
+                 norm_layer=nn.LayerNorm, ape=False, patch_norm=True, out_indices=(0, 1, 2, 3), frozen_stages=-1, use_checkpoint=False):
+        super().__init__(pretrain_img_size=pretrain_img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim, depths=depths,
+                         num_heads=num_heads, window_size=window_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                         drop_rate=drop_rate, attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer, ape=ape,
+                         patch_norm=patch_norm, out_indices=out_indices, frozen_stages=frozen_stages, use_checkpoint=use_checkpoint,
+                         num_heads_fusion=[1, 1, 1, 1], fusion_drop=0.0, args=None)
+        for layer in self.layers:               # a BasicLayer owns blocks + downsample only
+            del layer.fusion
+            if hasattr(layer, "res_gate"):
+                del layer.res_gate
+            layer.has_gate = False
+            layer.version = "swin"
+
+    def forward(self, x: torch.Tensor):
+        E.require_cuda(x, "x")
+        nchw, _ = self.run(V._planes(x).unsqueeze(2), None, None, want_nchw=True, want_nhwc_bf16=False)
+        return tuple(nchw)

@@ -6,11 +6,11 @@ Returned modules expose ``.backbone``, ``.classifier`` and ``.text_encoder`` wit
 """
 from __future__ import annotations
 
-from ._utils import LAVT, LAVTOne, LAVTVideo
+from ._utils import LAVT, LAVT_VLT, LAVTOne, LAVTVideo, VLT
 from .mask_predictor import SimpleDecoding
 from .video_swin_transformer import MultiModalSwinTransformer3D
 
-__all__ = ["lavt", "lavt_one", "lavt_video"]
+__all__ = ["lavt", "lavt_one", "lavt_video", "vlt", "lavt_vlt"]
 
 # swin_type -> (embed_dim, depths, num_heads, drop_path_rate)   (reference :156-172; image model :100-123)
 _SWIN = {
@@ -78,3 +78,34 @@ def lavt(pretrained="", args=None):
     """Image model taking precomputed language features (reference _segm_lavt, :14-60)."""
     backbone, embed_dim = _image_backbone(pretrained, args)
     return LAVT(backbone, SimpleDecoding(8 * embed_dim, args))
+
+
+def _vlt_head(args, embed_dim):
+    from .vlt import VLTFuseAndClassify
+    if embed_dim != 128:
+        raise NotImplementedError("VLTFuseAndClassify hard-codes the Swin-B stage widths 256 / 512 / 1024 (reference lib/vlt.py:16-18): "
+                                  "use --swin_type base")
+    return VLTFuseAndClassify(args=args)
+
+
+def vlt(pretrained="", args=None):
+    """Swin encoder (no language fusion, stages 1-3) + VLT head (reference _vlt, :299-352)."""
+    from .backbone import SwinTransformer
+    embed_dim, depths, heads, dpr = _swin_cfg(args, "image")
+    w = 12 if (getattr(args, "window12", False) or "window12" in (pretrained or "")) else 7
+    backbone = SwinTransformer(embed_dim=embed_dim, depths=depths, num_heads=heads, window_size=w, ape=False, drop_path_rate=dpr,
+                               patch_norm=True, out_indices=(1, 2, 3), use_checkpoint=False)
+    backbone.init_weights(pretrained=pretrained if pretrained else None)
+    return VLT(backbone, _vlt_head(args, embed_dim), args=args)
+
+
+def lavt_vlt(pretrained="", args=None):
+    """LAVT encoder (stages 1-3) + VLT head (reference _lavt_vlt, :368-422)."""
+    from .backbone import MultiModalSwinTransformer
+    embed_dim, depths, heads, dpr = _swin_cfg(args, "image")
+    w = 12 if (getattr(args, "window12", False) or "window12" in (pretrained or "")) else 7
+    backbone = MultiModalSwinTransformer(embed_dim=embed_dim, depths=depths, num_heads=heads, window_size=w, ape=False, drop_path_rate=dpr,
+                                         patch_norm=True, out_indices=(1, 2, 3), use_checkpoint=False, num_heads_fusion=_fusion_heads(args),
+                                         fusion_drop=getattr(args, "fusion_drop", 0.0), args=args)
+    backbone.init_weights(pretrained=pretrained if pretrained else None)
+    return LAVT_VLT(backbone, _vlt_head(args, embed_dim), args=args)

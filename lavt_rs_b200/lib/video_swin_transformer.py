@@ -319,6 +319,13 @@ class MMBasicLayer(nn.Module):
                          xb_out=xb if i == self.depth - 1 else None)
         if pre_fusion is not None:
             pre_fusion(x)
+        if self.version == "swin":          # plain Swin stage (reference lib/backbone.py BasicLayer, :1409-1510): no language fusion at all
+            if self.downsample is not None:
+                H2, W2 = (H + 1) // 2, (W + 1) // 2
+                nxt = ws.get("stage_x_%d" % (2 * C), (B * D * H2 * W2, 2 * C), torch.float32, dev)
+                E.patch_merging(x, self.downsample, B, D, H, W, ws, nxt)
+                return nxt, H2, W2
+            return x, H, W
         if lang_ready is not None:          # first consumer of the language features
             torch.cuda.current_stream().wait_event(lang_ready)
         if self.sep_t_pwam:
@@ -506,7 +513,7 @@ class MultiModalSwinTransformer3D(nn.Module):
                                        pre_fusion=emit if early else None)
             if out_here and not early:
                 # stage output: the PWAM residual, or with --hs the gated features (x is not modified by the downsample)
-                emit(x if layer.hs else r)
+                emit(x if (layer.hs or layer.version == "swin") else r)
             x, Hc, Wc = x_next, H2, W2
         return (nchw if want_nchw else None), (nhwc if want_nhwc_bf16 else None)
 

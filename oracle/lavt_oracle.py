@@ -377,7 +377,9 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
                 capture[f"s{s}b{i}"] = x
         B, D, H, W, C = x.shape
         x_pre = x                                                          # V_i (:556-558)
-        if cfg.bcam:
+        if cfg.version == "swin":                                          # plain Swin stage (lib/backbone.py BasicLayer :1409-1510): no fusion
+            r = None
+        elif cfg.bcam:
             r = bcam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
         elif cfg.gacd:
             r = gacd(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.")
@@ -389,11 +391,13 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
             r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         if capture is not None:
             capture[f"s{s}.residual"] = r
-        if cfg.version == "no_gate":
+        if cfg.version == "swin":
+            pass
+        elif cfg.version == "no_gate":
             x = x + r.reshape(B, D, H, W, C)
         elif cfg.version == "default" and pre + "res_gate.0.weight" in sd:
             x = language_gate(x.reshape(B, D * H * W, C), r, sd, pre + "res_gate.", cfg.gate_act).reshape(B, D, H, W, C)
-        stage_out = x if cfg.hs else (x_pre if cfg.lazy_pred else r.reshape(B, D, H, W, C))          # (:579-587)
+        stage_out = x if (cfg.hs or cfg.version == "swin") else (x_pre if cfg.lazy_pred else r.reshape(B, D, H, W, C))   # (:579-587)
         if f"backbone.norm{s}.weight" in sd:                               # out_indices (lazy_pred: 1, 2, 3)
             o = F.layer_norm(stage_out, (C,), sd[f"backbone.norm{s}.weight"], sd[f"backbone.norm{s}.bias"], 1e-5)
             outs.append(o.permute(0, 1, 4, 2, 3).reshape(B * D, C, H, W))      # (:869-874)

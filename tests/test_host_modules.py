@@ -138,3 +138,22 @@ def test_relative_position_index_closed_form():
         rel[:, :, 0] *= (2 * Wh - 1) * (2 * Ww - 1)
         rel[:, :, 1] *= 2 * Ww - 1
         assert torch.equal(_relative_position_index(window), rel.sum(-1))
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("model", ["vlt", "lavt_vlt"])
+def test_vlt_builders_state_dict_matches_reference(model):
+    """``segmentation.vlt`` / ``segmentation.lavt_vlt`` (reference lib/segmentation.py:299-433): same classes of sub-modules, same
+    state-dict keys and shapes as the reference's own builders, so that its checkpoints load unchanged."""
+    from lavt_rs_b200.lib import segmentation
+    extra = ["--img_size", "480"]
+    ref, _ = ref_shims.build_reference(model, "base", extra=extra)
+    mine = segmentation.__dict__[model](pretrained="", args=default_args(["--model", model, "--swin_type", "base", *extra]))
+    ref_sd, my_sd = ref.state_dict(), mine.state_dict()
+    strip = lambda d: {k for k in d if not k.startswith("text_encoder.")}   # noqa: E731
+    assert strip(ref_sd) == strip(my_sd), (sorted(strip(ref_sd) - strip(my_sd))[:5], sorted(strip(my_sd) - strip(ref_sd))[:5])
+    for k in strip(ref_sd):
+        assert ref_sd[k].shape == my_sd[k].shape, k
+    assert type(mine).__name__ == type(ref).__name__
+    missing = mine.load_state_dict({k: v for k, v in ref_sd.items() if not k.startswith("text_encoder.")}, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("text_encoder.") for k in missing.missing_keys)

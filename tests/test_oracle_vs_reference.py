@@ -327,3 +327,27 @@ def test_vlt_head_matches_reference(monkeypatch):
         got = VO.vlt_fuse_and_classify(sd, c4, c3, c2, l, mask)
     assert got.shape == ref.shape == (B, 2, 64, 64)
     assert (got - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item()), (got - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("window,HW", [(7, (64, 80)), (12, (96, 72))])
+def test_plain_swin_backbone_matches_reference(window, HW):
+    """Plain Swin encoder of the ``vlt`` model (lib/backbone.py:1512-1650, no language fusion, out_indices (1, 2, 3)): the oracle's
+    ``version='swin'`` mode vs the unmodified reference SwinTransformer."""
+    ref_shims.install_shims()
+    from lib.backbone import SwinTransformer
+    torch.manual_seed(0)
+    bb = SwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=window, ape=False, drop_path_rate=0.0,
+                         patch_norm=True, out_indices=(1, 2, 3), use_checkpoint=False)
+    bb.init_weights()
+    bb.eval()
+    _randomise_norms([bb])
+    sd = {"backbone." + k: v.detach() for k, v in bb.state_dict().items()}
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, window, window), clamp_window=False, video=False, version="swin")
+    x, l, m = O.synthetic_inputs(2, 1, HW[0], HW[1], Nl=5, video=False)
+    with torch.no_grad():
+        ref = bb(x)
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+    assert len(ref) == len(got) == 3
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() < 2e-4, f"stage {i + 1}"

@@ -116,3 +116,44 @@ def test_vlt_head_matches_reference_golden(name):
     if clear.any():
         assert ((got[:, 1] > got[:, 0]).cpu().numpy() == (gold[:, 1] > gold[:, 0]))[clear].mean() >= 0.999
     assert agree > 0.97
+
+
+@pytest.mark.parametrize("model_name", ["lavt_vlt", "vlt"])
+def test_vlt_models_end_to_end_480(model_name):
+    """``segmentation.lavt_vlt`` / ``segmentation.vlt`` built through the reference's builder API at --img_size 480 (Swin-B, random init):
+    text encoder + encoder (stages 1-3) + VLT head + upsample on the CUDA path vs the CPU oracles on the same state dict."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib import segmentation
+    from oracle import bert_oracle as BO
+    from oracle import lavt_oracle as O
+    from oracle import vlt_oracle as VO
+    torch.manual_seed(3)
+    model = segmentation.__dict__[model_name](pretrained="", args=default_args(["--model", model_name, "--swin_type", "base", "--img_size", "480"]))
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for m in model.classifier.modules():                        # non-trivial eval statistics in the head
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(1.0 + 0.3 * torch.rand(m.running_var.shape, generator=g))
+    model = model.eval()
+    sd = {k: v.detach().float().clone() for k, v in model.state_dict().items()}
+    x = torch.randn(1, 3, 480, 480, generator=g)
+    ids = torch.randint(1000, 5000, (1, 20), generator=g)
+    mask = torch.zeros(1, 20, dtype=torch.int64)
+    mask[:, :13] = 1
+    cfg = O.OracleConfig.swin("base", video=False)
+    cfg.clamp_window = False
+    if model_name == "vlt":
+        cfg.version = "swin"
+    with torch.no_grad():
+        l = BO.bert_forward(sd, ids, mask).permute(0, 2, 1)
+        feats = O.backbone_forward(sd, cfg, x, l, mask.float().unsqueeze(-1))
+        c2, c3, c4 = feats[-3:]
+        ref = torch.nn.functional.interpolate(VO.vlt_fuse_and_classify(sd, c4, c3, c2, l, mask.float().unsqueeze(-1), pre="classifier."),
+                                              size=(480, 480), mode="bilinear", align_corners=True)
+        model = model.cuda()
+        got = model(x.cuda(), ids.cuda(), mask.cuda())
+    assert got.shape == ref.shape == (1, 2, 480, 480)
+    r = rel_l2(got, ref)
+    print(model_name, "logits rel-L2 vs oracle", r)
+    assert r < 3e-2, r
