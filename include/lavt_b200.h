@@ -173,6 +173,21 @@ int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16,
 /* (B, Nl, C) fp32 -> (B, C, Nl) fp32: l_feats = last_hidden_state.permute(0, 2, 1) (lib/_utils.py:54) */
 int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream);
 
+/* ---- fp32 validation twins (csrc/fp32_ref_kernels.cu) ----
+ * north_star tolerance: "1e-4 in fp32 with fp32 accumulate".  The production contractions take bf16 operands; these twins take fp32
+ * operands, accumulate in fp32 on the CUDA cores and share the production epilogue (lavt_epilogue_t, incl. the window-reverse scatter)
+ * and index math, so a Swin block replays at fp32 accuracy on the device (lavt_rs_b200.engine.set_precision("fp32")).  Validation only:
+ * slow, never selected by default.
+ * lavt_gemm_f32_ref: out = epilogue(A[M,K] Wt[N,K]^T), any M / N / K.
+ * lavt_window_attention_f32_ref: qkv fp32 [rows, 3C] (q pre-scaled by 32^-0.5 * log2 e, as in the bf16 path) -> out fp32 [rows, C].
+ * lavt_layernorm_window_gather_f32: lavt_layernorm_window_gather with an fp32 result. */
+int lavt_gemm_f32_ref(const float* A, int64_t lda, const float* Wt, int64_t ldw, int32_t M, int32_t N, int32_t K, const lavt_epilogue_t* epi,
+                      void* stream);
+int lavt_window_attention_f32_ref(const float* qkv, const float* table_t, int32_t L, int32_t nH, const lavt_win_geom_t* geom, float* out,
+                                  void* stream);
+int lavt_layernorm_window_gather_f32(const float* x, int32_t C, const lavt_win_geom_t* geom, const float* gamma, const float* beta, float eps,
+                                     float* out_f32, void* stream);
+
 /* ---- VLT fuse-and-classify head (lib/vlt.py:12-485; models vlt / lavt_vlt, lib/segmentation.py:299-433) ----
  * The head's convolutions and Linear / Conv1d layers run on lavt_gemm_bf16 / lavt_conv3x3_bf16 (eval BatchNorm folded into the
  * epilogue); these are the memory-bound pieces between them.

@@ -139,6 +139,9 @@ SIGNATURES = {
     "lavt_efn_norm_upsample": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_bcam_softmax_rows": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp],
     "lavt_bcam_transpose_pad": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp],
+    "lavt_gemm_f32_ref": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _EP, _vp],
+    "lavt_window_attention_f32_ref": [_vp, _vp, _i32, _i32, _WG, _vp, _vp],
+    "lavt_layernorm_window_gather_f32": [_vp, _i32, _WG, _vp, _vp, _f32, _vp, _vp],
     "lavt_rows_affine_act": [_vp, _i32, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp],
     "lavt_avgpool2_nhwc": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "lavt_append_coords": [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp],
@@ -1068,3 +1071,28 @@ def upsample_nhwc(prev: torch.Tensor, out: torch.Tensor) -> None:
         raise LavtError("upsample_nhwc: shape mismatch")
     check(lib().lavt_upsample_concat(prev.data_ptr(), ph, pw, C1, None, 0, _c(out, torch.bfloat16, "out").data_ptr(), n, out.shape[1], out.shape[2],
                                      stream_ptr()), "lavt_upsample_concat")
+
+
+# ---- fp32 validation twins (csrc/fp32_ref_kernels.cu): slow CUDA-core kernels with the production epilogue / index math ----
+def gemm_f32_ref(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
+    """out = epilogue(a @ w.T) with fp32 operands and fp32 accumulation; a [M,K] fp32, w [N,K] fp32."""
+    _req(a, torch.float32, "a")
+    _req(w, torch.float32, "w")
+    M, Kd = a.shape
+    N, K2 = w.shape
+    if Kd != K2:
+        raise LavtError(f"gemm_f32_ref: K mismatch {Kd} vs {K2}")
+    e = make_epilogue(**epi)
+    check(lib().lavt_gemm_f32_ref(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, Kd, C.byref(e), stream_ptr()), "lavt_gemm_f32_ref")
+
+
+def window_attention_f32_ref(qkv: torch.Tensor, table_t: torch.Tensor, geom: WinGeom, out: torch.Tensor) -> None:
+    nH, L = table_t.shape
+    check(lib().lavt_window_attention_f32_ref(_c(qkv, torch.float32, "qkv").data_ptr(), _c(table_t, torch.float32, "table_t").data_ptr(), L, nH,
+                                              C.byref(geom), _c(out, torch.float32, "out").data_ptr(), stream_ptr()), "lavt_window_attention_f32_ref")
+
+
+def layernorm_window_gather_f32(x: torch.Tensor, geom: WinGeom, gamma, beta, out_f32: torch.Tensor, eps: float = 1e-5) -> None:
+    check(lib().lavt_layernorm_window_gather_f32(_c(x, torch.float32, "x").data_ptr(), x.shape[-1], C.byref(geom), _c(gamma.detach(), torch.float32, "gamma").data_ptr(),
+                                                 _c(beta.detach(), torch.float32, "beta").data_ptr(), float(eps), _c(out_f32, torch.float32, "out").data_ptr(),
+                                                 stream_ptr()), "lavt_layernorm_window_gather_f32")

@@ -20,6 +20,17 @@ from . import _cabi as K
 from .geometry import window_geometry
 
 LAUNCHES = 0  # number of our kernel launches issued (bench.py reports it)
+PRECISION = "bf16"   # "fp32": the Swin block runs on the fp32 validation twins (csrc/fp32_ref_kernels.cu); see set_precision
+
+
+def set_precision(mode: str) -> str:
+    """'bf16' (production: bf16 operands on tcgen05, fp32 accumulation) or 'fp32' (validation: fp32 operands and activations through
+    the whole Swin block on the CUDA-core twins -- north_star's "1e-4 in fp32 with fp32 accumulate" mode).  Returns the previous mode."""
+    global PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    prev, PRECISION = PRECISION, mode
+    return prev
 
 
 def _count(n: int = 1) -> None:
@@ -106,6 +117,8 @@ def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shi
     nH = blk.num_heads
     pw = blk.prepared
     hd = C // nH
+    if PRECISION == "fp32":
+        return _swin_block_fp32(x, blk, geom, ws, xb_out)
 
     qkv_w = pw.get("qkv_w", [blk.attn.qkv.weight], lambda: _bf16(blk.attn.qkv.weight))
     # q columns are scaled by head_dim^-0.5 (:147) times log2(e) in the epilogue -- the attention kernel's softmax
@@ -136,6 +149,30 @@ def swin_block(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shi
     hid = ws.get("hid", (n, fc1_w.shape[0]), torch.bfloat16, dev)
     K.gemm_bf16(h1, fc1_w, bias=blk.mlp.fc1.bias.detach(), act=K.ACT_GELU, out_bf16=hid)
     K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x, out_f32=x, out_bf16=xb_out)
+    _count(7)
+
+
+def _swin_block_fp32(x: torch.Tensor, blk, geom, ws: Workspace, xb_out: Optional[torch.Tensor]) -> None:
+    """Same launch sequence as ``swin_block`` with fp32 operands / activations on the validation twins (no bf16 rounding anywhere)."""
+    n, C = x.shape
+    dev = x.device
+    rows, nH = geom.rows(), blk.num_heads
+    hd = C // nH
+    s = torch.ones(3 * C, device=dev, dtype=torch.float32)
+    s[:C] = hd ** -0.5 * 1.4426950408889634
+    qb = _f32(blk.attn.qkv.bias) * s if blk.attn.qkv.bias is not None else torch.zeros(3 * C, device=dev)
+    xw = ws.get("xw32", (rows, C), torch.float32, dev)
+    K.layernorm_window_gather_f32(x, geom, blk.norm1.weight, blk.norm1.bias, xw, eps=blk.norm1.eps)
+    qkv = ws.get("qkv32", (rows, 3 * C), torch.float32, dev)
+    K.gemm_f32_ref(xw, _f32(blk.attn.qkv.weight), cscale=s, bias=qb, out_f32=qkv)
+    att = ws.get("att32", (rows, C), torch.float32, dev)
+    K.window_attention_f32_ref(qkv, _f32(blk.attn.relative_position_bias_table.t()), geom, att)
+    K.gemm_f32_ref(att, _f32(blk.attn.proj.weight), bias=blk.attn.proj.bias.detach(), resid=x, out_f32=x, win=geom)
+    h1 = ws.get("ln2_32", (n, C), torch.float32, dev)
+    K.layernorm_rows(x, blk.norm2.weight, blk.norm2.bias, out_f32=h1, eps=blk.norm2.eps)
+    hid = ws.get("hid32", (n, blk.mlp.fc1.weight.shape[0]), torch.float32, dev)
+    K.gemm_f32_ref(h1, _f32(blk.mlp.fc1.weight), bias=blk.mlp.fc1.bias.detach(), act=K.ACT_GELU, out_f32=hid)
+    K.gemm_f32_ref(hid, _f32(blk.mlp.fc2.weight), bias=blk.mlp.fc2.bias.detach(), resid=x, out_f32=x, out_bf16=xb_out)
     _count(7)
 
 

@@ -20,13 +20,13 @@ def torch_window_attention(qkv, table, geom):
     nwin = rows // N
     _, code, rid = window_row_map(geom)
     code, rid = code.cuda().view(nwin, N), rid.cuda().view(nwin, N)
-    x = qkv.float().view(nwin, N, 3, nH, 32).permute(2, 0, 3, 1, 4)
+    x = (qkv if qkv.dtype == torch.float64 else qkv.float()).view(nwin, N, 3, nH, 32).permute(2, 0, 3, 1, 4)
     q, k, v = x[0] / math.log2(math.e), x[1], x[2]
     s = q @ k.transpose(-1, -2)
     idx = code[0][:, None] - code[0][None, :] + rel_const(geom)
     s = s + table[idx.reshape(-1)].view(N, N, nH).permute(2, 0, 1).unsqueeze(0)
     if geom.sd or geom.sh or geom.sw:
-        s = s + ((rid[:, :, None] != rid[:, None, :]).float() * -100.0).unsqueeze(1)
+        s = s + ((rid[:, :, None] != rid[:, None, :]).to(s.dtype) * -100.0).unsqueeze(1)
     return (s.softmax(-1) @ v).transpose(1, 2).reshape(rows, C)
 
 
