@@ -36,9 +36,12 @@ _STRUCTURE_FLAGS = [
     ("--conv3d_kernel_size_s", str, "1-1-1", "spatial-branch Conv3d kernel (B200 path: 1-1-1)"),
     ("--w_t3x3_s1x1", "store_true", False, "SepTPWAM: W = IN(conv_t) + IN(conv_s)"),
     ("--mm_t3x3_s1x1", "store_true", False, "SepTPWAM: project_mm = GELU(conv_t) + GELU(conv_s)"),
+    ("--interpolate_before_seg", "store_true", False, "decoder: one more conv3x3 level at 1/2 scale before the classifier (inference)"),
+    ("--seg_last", "store_true", False, "with --interpolate_before_seg: a further conv3x3 level at full scale; the video model then returns "
+                                        "the classifier output without the final interpolation (inference)"),
 ]
 _REJECTED_BOOL_FLAGS = ["ts_pwam", "t_pwam", "t_pwam_comp", "seq_t_pwam",
-                        "sep_t_pwam_inner", "sep_seq_t_pwam", "sep_seq_t_pwam_inner", "interpolate_before_seg", "seg_last"]
+                        "sep_t_pwam_inner", "sep_seq_t_pwam", "sep_seq_t_pwam_inner"]
 
 
 def get_parser() -> argparse.ArgumentParser:

@@ -184,6 +184,21 @@ def _conv1x1_w(conv) -> torch.Tensor:
     return conv.weight[:, :, 0]
 
 
+def _language_gate(x: torch.Tensor, rb: torch.Tensor, res_gate, pw: PreparedWeights, scratch: torch.Tensor, gate_act: str) -> None:
+    """LanguageGate (reference res_gate :519-525 applied at :570; 2-D lib/backbone.py:599-609): x += act(W2 relu(W1 r)) * r as two GEMMs
+    whose epilogues carry ReLU and tanh | sigmoid (--lg_act_layer), the elementwise product and the residual add.  ``scratch`` is a dead
+    bf16 [n, C] buffer of the caller."""
+    if res_gate is None:
+        return
+    if gate_act not in ("tanh", "sigmoid"):
+        raise K.LavtError(f"LanguageGate activation {gate_act!r}: the reference offers tanh and sigmoid (--lg_act_layer)")
+    g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+    g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+    K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=scratch)
+    K.gemm_bf16(scratch, g2, act=K.ACT_TANH if gate_act == "tanh" else K.ACT_SIGMOID, mul=rb, resid=x, out_f32=x)
+    _count(2)
+
+
 def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int,
               ws: Workspace, gate_act: str = "tanh", r_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x fp32 [B*n, C] (updated in place with the gated residual), xb = bf16 copy of x, l fp32 [B,768,Nl],
@@ -219,15 +234,7 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
         K.gemm_bf16(a2.view(N_, C), wprep("mm_w", fusion.project_mm[0]), bias=fusion.project_mm[0].bias.detach(), act=K.ACT_GELU, out_f32=r32,
                     out_bf16=rb)
         _count(6)
-        if res_gate is not None:
-            g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-            g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-            g1 = vis.view(N_, C)
-            K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
-            if gate_act != "tanh":
-                raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-            K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-            _count(2)
+        _language_gate(x, rb, res_gate, pw, vis.view(N_, C), gate_act)
         return r32
     heads = att.num_heads
 
@@ -241,33 +248,50 @@ def pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     vis = ws.get("pw_vis", (B, n, C), torch.bfloat16, dev)
     K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C))
     qpre = ws.get("pw_q", (B, n, C), torch.float32, dev)      # fp32: feeds InstanceNorm + SIMT attention, never an MMA operand
-    K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
     stats = ws.get("pw_stats", (B, 2, C), torch.float32, dev)
     stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), torch.float32, dev)
-    K.instnorm_stats(qpre, stats, stw)
+    # --att_norm_layer_type (2-D backbone, reference lib/backbone.py:1297-1316): IN = per-image statistics over the tokens (default);
+    # BN (eval) folds into the producing GEMM's column scale / bias; LN is a row LayerNorm of the GEMM result; none = identity.
+    # For the last three the consumers read "statistics" (mean 0, rstd 1).
+    norm_kind = getattr(att, "att_norm_layer_type", "IN")
+    ident = None
+    if norm_kind != "IN":
+        ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
+
+    def normed_gemm(a_rows, w, seq, tag, out32):
+        """out32 = norm(conv1x1(a_rows)) for BN / LN / none; for IN the plain projection (statistics computed by the caller)."""
+        bias = seq[0].bias.detach()
+        if norm_kind == "BN":
+            bn = seq[1]
+            if bn.training:
+                raise K.LavtError("--att_norm_layer_type BN is inference-only on the B200 path (BatchNorm must be in eval mode)")
+            sc, sh = pw.get(tag + "_bn", [bn.weight, bn.bias, bn.running_mean, bn.running_var, seq[0].bias],
+                            lambda: (lambda s_, t_: (s_, (_f32(seq[0].bias) * s_ + t_).contiguous()))(*_bn_fold(bn)))
+            K.gemm_bf16(a_rows, w, cscale=sc, bias=sh, out_f32=out32)
+        else:
+            K.gemm_bf16(a_rows, w, bias=bias, out_f32=out32)
+            if norm_kind == "LN":
+                K.layernorm_rows(out32, seq[1].weight, seq[1].bias, out_f32=out32, eps=seq[1].eps)
+                _count(1)
+    normed_gemm(xb, q_w, att.f_query, "fq", qpre.view(N_, C))
+    if norm_kind == "IN":
+        K.instnorm_stats(qpre, stats, stw)
     kk = ws.get("pw_k", (B, Nl, C), torch.float32, dev)
     vv = ws.get("pw_v", (B, Nl, C), torch.float32, dev)
     K.pwam_kv(l, mask, k_w, att.f_key[0].bias.detach(), v_w, att.f_value[0].bias.detach(), kk, vv)
     o = ws.get("pw_o", (B, n, C), torch.bfloat16, dev)
-    K.pwam_attend(qpre, stats, kk, vv, mask, o, heads)
+    K.pwam_attend(qpre, stats if norm_kind == "IN" else ident, kk, vv, mask, o, heads)
     lang = qpre  # q_pre is dead: reuse its buffer for lang_pre
-    K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_f32=lang.view(N_, C))
-    K.instnorm_stats(lang, stats, stw)
+    normed_gemm(o.view(N_, C), W_w, att.W, "W", lang.view(N_, C))
+    if norm_kind == "IN":
+        K.instnorm_stats(lang, stats, stw)
     a2 = o  # o is dead after the W projection
-    K.pwam_mul_norm(vis, lang, stats, a2)
+    K.pwam_mul_norm(vis, lang, stats if norm_kind == "IN" else ident, a2)
     r32 = r_f32 if r_f32 is not None else ws.get("pw_r32", (N_, C), torch.float32, dev)
     rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
     K.gemm_bf16(a2.view(N_, C), mm_w, bias=fusion.project_mm[0].bias.detach(), act=K.ACT_GELU, out_f32=r32, out_bf16=rb)
     _count(11)
-    if res_gate is not None:
-        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        g1 = vis.view(N_, C)  # vis is dead
-        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
-        if gate_act != "tanh":
-            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-        _count(2)
+    _language_gate(x, rb, res_gate, pw, vis.view(N_, C), gate_act)      # vis is dead: scratch
     return r32
 
 
@@ -294,15 +318,7 @@ def gacd_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
                 _f32(fusion.key_d.weight), _f32(fusion.key_d.bias), _f32(fusion.value.weight), _f32(fusion.value.bias),
                 lambda nfl: ws.get("gacd_ws", (nfl,), torch.float32, dev), out_f32=r32, out_bf16=rb)
     _count(10)
-    if res_gate is not None:
-        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        g1 = a.view(N_, C)           # the ls * x operand is dead
-        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
-        if gate_act != "tanh":
-            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-        _count(2)
+    _language_gate(x, rb, res_gate, pw, a.view(N_, C), gate_act)        # the ls * x operand is dead: scratch
     return r32
 
 
@@ -373,14 +389,7 @@ def bcam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tens
     rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
     K.gemm_bf16(cat[:, :2 * C], wb("o3_w", fusion.out3_proj[0]), bias=b_(fusion.out3_proj[0]), act=K.ACT_RELU, resid=q4, out_f32=r32, out_bf16=rb)
     _count(11 + 3 * B)
-    if res_gate is not None:
-        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=q)
-        if gate_act != "tanh":
-            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-        K.gemm_bf16(q, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-        _count(2)
+    _language_gate(x, rb, res_gate, pw, q, gate_act)
     return r32
 
 
@@ -468,14 +477,7 @@ def efn_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tenso
     rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
     K.efn_norm_upsample(o, stats, n, h, pooled, out_f32=r32, out_bf16=rb)
     _count(13 + 11 * B)
-    if res_gate is not None:
-        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=M)
-        if gate_act != "tanh":
-            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-        K.gemm_bf16(M, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-        _count(2)
+    _language_gate(x, rb, res_gate, pw, M, gate_act)
     return r32
 
 
@@ -544,15 +546,7 @@ def sep_t_pwam_gate(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torc
     rb = ws.get("pw_rb", (N_, C), torch.bfloat16, dev)
     K.gemm_bf16(a2.view(N_, C), w111("mm_s", ms), bias=b_(ms), act=K.ACT_GELU, resid=t32, out_f32=r32, out_bf16=rb)
     _count(19)
-    if res_gate is not None:
-        g0 = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2 = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        g1 = vis.view(N_, C)  # vis is dead
-        K.gemm_bf16(rb, g0, act=K.ACT_RELU, out_bf16=g1)
-        if gate_act != "tanh":
-            raise K.LavtError("only the tanh LanguageGate is implemented on the B200 path")
-        K.gemm_bf16(g1, g2, act=K.ACT_TANH, mul=rb, resid=x, out_f32=x)
-        _count(2)
+    _language_gate(x, rb, res_gate, pw, vis.view(N_, C), gate_act)      # vis is dead: scratch
     return r32
 
 
@@ -649,6 +643,17 @@ def decoder_nhwc(dec, c4: torch.Tensor, c3: torch.Tensor, c2: torch.Tensor, c1: 
         if feats is not None:
             feats.append(t2)
         _count(1)
+    if getattr(dec, "interpolate_before_seg", False):          # reference lib/mask_predictor.py:88-97
+        fine = c1
+        for on, (cname, bname, mul_) in ((True, ("conv2_1", "bn1_1", 2)), (getattr(dec, "seg_last", False), ("conv1_0", "bn1_0", 4))):
+            if not on:
+                continue
+            H, W = mul_ * fine.shape[1], mul_ * fine.shape[2]
+            up = ws.get("dec_up_%d" % mul_, (n_img, H, W, hid), torch.bfloat16, dev)
+            K.upsample_nhwc(y, up)
+            y = ws.get("dec_y_%d" % mul_, (n_img, H, W, hid), torch.bfloat16, dev)
+            _cbr(up, dec, cname, bname, y)
+            _count(1)
     _, H, W, _ = y.shape
     w11 = dec.prepared.get("w11", [dec.conv1_1.weight], lambda: _f32(dec.conv1_1.weight.reshape(2, -1)))
     lg = ws.get("dec_logits", (n_img, H, W, 2), torch.float32, dev)

@@ -60,6 +60,8 @@ class _Segmenter(nn.Module):
         c1, c2, c3, c4 = nhwc if len(nhwc) == 4 else (None, *nhwc)              # --lazy_pred: three maps (lib/_utils.py:101-105)
         ws = E.workspace(c4.device)
         lg = E.decoder_nhwc(self.classifier, c4, c3, c2, c1, ws, None)       # (n_img, H/4, W/4, 2) NHWC fp32 (H/8 under --lazy_pred)
+        if getattr(self, "seg_last", False):          # the video model skips the final interpolation (reference lib/_utils.py:105-106)
+            size = lg.shape[1:3]
         out = torch.empty(lg.shape[0], 2, size[0], size[1], device=lg.device, dtype=torch.float32)
         K.upsample_logits(lg, out)                                             # bilinear x4 (x8) + NCHW (lib/_utils.py:106)
         E._count(1)
@@ -151,7 +153,7 @@ class LAVTVideo(_Segmenter):
         self.backbone, self.classifier = backbone, classifier
         self.text_encoder = _build_text_encoder(args)
         self.lazy_pred = bool(getattr(args, "lazy_pred", False))
-        self.seg_last = False
+        self.seg_last = bool(getattr(args, "seg_last", False))
 
     def encode_text(self, text, l_mask):
         """BertModel(text, attention_mask=l_mask)[0].permute(0, 2, 1) on the sm_100a kernels (lavt_rs_b200/bert.py)."""

@@ -24,10 +24,10 @@ def _check_2d_args(args) -> None:
     for f in _REJECTED:
         if getattr(args, f, False):
             raise NotImplementedError(f"--{f} fusion (reference lib/bcam.py) is not implemented on the B200 path yet")
-    if getattr(args, "lg_act_layer", "tanh") != "tanh":
-        raise NotImplementedError("only the tanh LanguageGate is implemented on the B200 path")
-    if getattr(args, "att_norm_layer_type", "IN") != "IN":
-        raise NotImplementedError("only InstanceNorm PWAM attention norms are implemented on the B200 path")
+    if getattr(args, "lg_act_layer", "tanh") not in ("tanh", "sigmoid"):
+        raise ValueError("--lg_act_layer must be tanh or sigmoid (reference lib/backbone.py:552-554)")
+    if getattr(args, "att_norm_layer_type", "IN") not in ("IN", "BN", "LN", "none"):
+        raise ValueError("--att_norm_layer_type must be IN, BN, LN or none (reference lib/backbone.py:1297-1302)")
 
 
 class GACD(nn.Module):
@@ -163,6 +163,12 @@ class MMBasicLayer(V.MMBasicLayer):
             self.fusion = GACD(dim, dim, 768, num_heads=num_heads_fusion)
         elif getattr(args, "efn", False):     # reference lib/backbone.py:583-588
             self.fusion = EFN(dim, dim, 768)
+        elif getattr(args, "att_norm_layer_type", "IN") != "IN":          # reference lib/backbone.py:589-599
+            self.fusion = V.PWAM(dim, dim, 768, dim, dim, num_heads=num_heads_fusion, dropout=fusion_drop,
+                                 attention=getattr(args, "fuse", "default") != "simple", att_norm_layer_type=args.att_norm_layer_type)
+        self.gate_act = getattr(args, "lg_act_layer", "tanh")
+        if self.has_gate and self.gate_act == "sigmoid":
+            self.res_gate[3] = nn.Sigmoid()
         for blk in self.blocks:
             blk.clamp_window = False          # the 2-D reference always pads to a full window and always shifts
         self.use_checkpoint = use_checkpoint

@@ -120,19 +120,25 @@ class PatchMerging(nn.Module):
 class SpatialImageLanguageAttention(nn.Module):
     """Pixel-word attention parameters (reference :937-1009)."""
 
-    def __init__(self, v_in_channels, l_in_channels, key_channels, value_channels, out_channels=None, num_heads=1):
+    def __init__(self, v_in_channels, l_in_channels, key_channels, value_channels, out_channels=None, num_heads=1,
+                 att_norm_layer_type="IN"):
         super().__init__()
+        if att_norm_layer_type not in ("IN", "BN", "LN", "none"):
+            raise ValueError(f"unknown --att_norm_layer_type {att_norm_layer_type!r}")
+        self.att_norm_layer_type = att_norm_layer_type
+        norm = {"IN": nn.InstanceNorm1d, "BN": nn.BatchNorm1d, "LN": nn.LayerNorm, "none": lambda c: nn.Identity()}[att_norm_layer_type]
         self.v_in_channels, self.l_in_channels = v_in_channels, l_in_channels
         self.key_channels, self.value_channels = key_channels, value_channels
         self.out_channels = out_channels if out_channels is not None else value_channels
         self.num_heads = num_heads
         if not (v_in_channels == key_channels == value_channels == self.out_channels):
             raise NotImplementedError("PWAM with differing channel widths is not supported on the B200 path")
-        # index 1 of each Sequential is the (parameter-free) InstanceNorm1d of the reference
+        # index 1 of each Sequential is the norm of the reference: parameter-free InstanceNorm1d by default; the 2-D backbone's
+        # --att_norm_layer_type offers BatchNorm1d / LayerNorm / Identity (reference lib/backbone.py:1297-1316)
         self.f_key = nn.Sequential(nn.Conv1d(l_in_channels, key_channels, 1))
-        self.f_query = nn.Sequential(nn.Conv1d(v_in_channels, key_channels, 1), nn.InstanceNorm1d(key_channels))
+        self.f_query = nn.Sequential(nn.Conv1d(v_in_channels, key_channels, 1), norm(key_channels))
         self.f_value = nn.Sequential(nn.Conv1d(l_in_channels, value_channels, 1))
-        self.W = nn.Sequential(nn.Conv1d(value_channels, self.out_channels, 1), nn.InstanceNorm1d(self.out_channels))
+        self.W = nn.Sequential(nn.Conv1d(value_channels, self.out_channels, 1), norm(self.out_channels))
 
 
 class LangProject(nn.Module):
@@ -148,7 +154,7 @@ class PWAM(nn.Module):
     """Pixel-word attention module (reference :889-934); ``attention=False`` = the --fuse simple ablation (LangProject)."""
 
     def __init__(self, dim, v_in_channels, l_in_channels, key_channels, value_channels, num_heads=0, dropout=0.0,
-                 attention=True):
+                 attention=True, att_norm_layer_type="IN"):
         super().__init__()
         if dropout != 0.0:
             raise NotImplementedError("fusion dropout > 0 is not supported on the B200 path")
@@ -156,7 +162,8 @@ class PWAM(nn.Module):
         self.vis_project = nn.Sequential(nn.Conv1d(dim, dim, 1, 1), nn.GELU(), nn.Dropout(dropout))
         if attention:
             self.image_lang_att = SpatialImageLanguageAttention(v_in_channels, l_in_channels, key_channels, value_channels,
-                                                                out_channels=value_channels, num_heads=num_heads)
+                                                                out_channels=value_channels, num_heads=num_heads,
+                                                                att_norm_layer_type=att_norm_layer_type)
         else:
             if dim != value_channels:
                 raise NotImplementedError("--fuse simple with differing channel widths is not supported on the B200 path")
@@ -272,6 +279,7 @@ class MMBasicLayer(nn.Module):
         self.dim = dim
         self.use_checkpoint = use_checkpoint
         self.version = getattr(args, "version", "default")
+        self.gate_act = "tanh"                      # the 2-D backbone's --lg_act_layer may switch it to sigmoid (lib/backbone.py:552-554)
         self.is_last_layer = num_heads in (24, 32)
         self.blocks = nn.ModuleList([
             SwinTransformerBlock3D(dim=dim, num_heads=num_heads, window_size=self.window_size,
@@ -330,10 +338,10 @@ class MMBasicLayer(nn.Module):
             torch.cuda.current_stream().wait_event(lang_ready)
         if self.sep_t_pwam:
             def fuse(gate):
-                E.sep_t_pwam_gate(x, xb, self.fusion, gate, l, mask, B, D, H, W, ws, r_f32=r_out)
+                E.sep_t_pwam_gate(x, xb, self.fusion, gate, l, mask, B, D, H, W, ws, gate_act=self.gate_act, r_f32=r_out)
         else:
             def fuse(gate):
-                E.pwam_gate(x, xb, self.fusion, gate, l, mask, B, ws, r_f32=r_out)
+                E.pwam_gate(x, xb, self.fusion, gate, l, mask, B, ws, gate_act=self.gate_act, r_f32=r_out)
         if self.version == "none":      # fusion still produces the stage output; x is left untouched
             fuse(None)
         elif self.version == "no_gate":  # ablation flag: plain residual add (tensor-container op, not a hot path)

@@ -35,8 +35,14 @@ def _check_trainable(model) -> None:
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
         if not layer.sep_t_pwam and not layer.fusion.attention:
             raise NotImplementedError("--fuse simple is inference-only on the B200 path")
+        if getattr(layer, "gate_act", "tanh") != "tanh":
+            raise NotImplementedError("--lg_act_layer sigmoid is inference-only on the B200 path (the gate adjoint kernel is the tanh one)")
+        if getattr(getattr(layer.fusion, "image_lang_att", None), "att_norm_layer_type", "IN") != "IN":
+            raise NotImplementedError("--att_norm_layer_type BN / LN / none is inference-only on the B200 path")
         if layer.version not in ("default", "no_gate", "none"):
             raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
+    if getattr(model.classifier, "interpolate_before_seg", False):
+        raise NotImplementedError("--interpolate_before_seg / --seg_last are inference-only on the B200 path")
     if tuple(bb.out_indices) != (0, 1, 2, 3):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
 

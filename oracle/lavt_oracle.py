@@ -47,6 +47,9 @@ class OracleConfig:
     efn: bool = False                             # --efn (2-D image backbone): EFN fusion of lib/bcam.py:160-269 (co-attention over pooled pixels)
     gacd: bool = False                            # --gacd (2-D image backbone): GA-CD fusion of lib/bcam.py:78-127 instead of PWAM
     fuse_simple: bool = False                     # --fuse simple: LangProject (mean-pooled sentence vector) instead of pixel-word attention
+    att_norm: str = "IN"                          # --att_norm_layer_type of the 2-D backbone: IN | BN | LN | none (lib/backbone.py:1297-1302)
+    interpolate_before_seg: bool = False          # decoder level at 1/2 scale (lib/mask_predictor.py:40-43, 88-92)
+    seg_last: bool = False                        # decoder level at full scale, no final interpolation in the video model (:45-48, 93-97)
     version: str = "default"                      # --version: default = LanguageGate; no_gate = x + r; none = x (:561-575)
     sep_t_pwam: bool = False                      # README video flags: --sep_t_pwam --conv3d_kernel_size_t 3-3-3
                                                   # --conv3d_kernel_size_s 1-1-1 --w_t3x3_s1x1 --mm_t3x3_s1x1
@@ -184,7 +187,18 @@ def lang_project(l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
     return (h @ sd[pre + "project.2.weight"].t() + sd[pre + "project.2.bias"]).unsqueeze(1)
 
 
-def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, return_parts: bool = False):
+def _att_norm(t: Tensor, sd, name: str, kind: str) -> Tensor:
+    """The norm at index 1 of f_query / W (lib/backbone.py:1297-1316) on tokens-last tensors (B, n, C), eval mode."""
+    if kind == "IN":
+        return _instance_norm_tokens(t)
+    if kind == "BN":
+        return (t - sd[name + ".running_mean"]) / torch.sqrt(sd[name + ".running_var"] + 1e-5) * sd[name + ".weight"] + sd[name + ".bias"]
+    if kind == "LN":
+        return F.layer_norm(t, (t.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
+    return t
+
+
+def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, return_parts: bool = False, att_norm: str = "IN"):
     """x (B,n,C); l (B,768,Nl); l_mask (B,Nl,1) -> x_residual (B,n,C).  ``pre`` = 'backbone.layers.{s}.fusion.'"""
     B, n, C = x.shape
     m = l_mask.to(x.dtype)                                              # (B, Nl, 1)
@@ -192,7 +206,7 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     a = pre + "image_lang_att."
     if a + "project.0.weight" in sd:                                    # --fuse simple (:916-917, 929-930): broadcast sentence vector
         return F.gelu(_lin1x1(vis * lang_project(l, l_mask, sd, a), sd, pre + "project_mm.0"))
-    q = _instance_norm_tokens(_lin1x1(x, sd, a + "f_query.0"))          # (B, n, C)
+    q = _att_norm(_lin1x1(x, sd, a + "f_query.0"), sd, a + "f_query.1", att_norm)          # (B, n, C)
     lt = l.transpose(1, 2)                                              # (B, Nl, 768)
     k = _lin1x1(lt, sd, a + "f_key.0") * m                              # (B, Nl, C)
     v = _lin1x1(lt, sd, a + "f_value.0") * m
@@ -205,7 +219,7 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     s = s + (1e4 * m.transpose(1, 2) - 1e4).unsqueeze(1)                # (B,1,1,Nl): pads -> -1e4
     p = s.softmax(-1)
     o = (p @ vh).transpose(1, 2).reshape(B, n, C)
-    lang = _instance_norm_tokens(_lin1x1(o, sd, a + "W.0"))
+    lang = _att_norm(_lin1x1(o, sd, a + "W.0"), sd, a + "W.1", att_norm)
     r = F.gelu(_lin1x1(vis * lang, sd, pre + "project_mm.0"))
     if return_parts:
         return r, dict(vis=vis, q=q, k=k, v=v, o=o, lang=lang)
@@ -388,7 +402,7 @@ def backbone_forward(sd, cfg: OracleConfig, x: Tensor, l: Tensor, l_mask: Tensor
         elif cfg.sep_t_pwam:
             r = sep_t_pwam(x, l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
         else:
-            r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s])
+            r = pwam(x.reshape(B, D * H * W, C), l, l_mask, sd, pre + "fusion.", cfg.fusion_heads[s], att_norm=cfg.att_norm)
         if capture is not None:
             capture[f"s{s}.residual"] = r
         if cfg.version == "swin":
@@ -450,6 +464,12 @@ def decoder_forward(sd, x_c4, x_c3, x_c2, x_c1, capture: Optional[dict] = None, 
     if x_c1 is not None:                       # --lazy_pred stops at 1/8 scale (lib/mask_predictor.py:77)
         y = torch.cat([_up_to(y, x_c1), x_c1], 1)
         y = q(_cbr(_cbr(y, sd, "conv1_2", "bn1_2", tb, eb), sd, "conv2_2", "bn2_2", tb, eb))
+    if "classifier.conv2_1.weight" in sd:      # --interpolate_before_seg (lib/mask_predictor.py:88-92); conv2_1 is normalised by bn1_1
+        y = F.interpolate(y, size=(2 * x_c1.shape[-2], 2 * x_c1.shape[-1]), mode="bilinear", align_corners=True)
+        y = q(_cbr(y, sd, "conv2_1", "bn1_1", tb, eb))
+        if "classifier.conv1_0.weight" in sd:  # --seg_last (:93-97)
+            y = F.interpolate(y, size=(4 * x_c1.shape[-2], 4 * x_c1.shape[-1]), mode="bilinear", align_corners=True)
+            y = q(_cbr(y, sd, "conv1_0", "bn1_0", tb, eb))
     if capture is not None:
         capture["dec_feat"] = y
     return F.conv2d(y, sd["classifier.conv1_1.weight"], sd["classifier.conv1_1.bias"])
@@ -474,6 +494,8 @@ def model_forward(sd, cfg: OracleConfig, x: Tensor, l_feats: Tensor, l_mask: Ten
     logits = decoder_forward(sd, c4, c3, c2, c1, capture, train_bn)
     if capture is not None:
         capture["logits_lowres"] = logits
+    if cfg.seg_last and cfg.video:             # lib/_utils.py:105-106: the video model returns the classifier's own resolution
+        return logits
     return F.interpolate(logits, size=size, mode="bilinear", align_corners=True)
 
 
@@ -553,6 +575,12 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
                               ("image_lang_att.f_value.0", l_in), ("image_lang_att.W.0", C), ("project_mm.0", C)):
                 w, b = conv_default(C, cin, 1)
                 sd[f"{pre}fusion.{name}.weight"], sd[f"{pre}fusion.{name}.bias"] = w, b
+            if cfg.att_norm in ("BN", "LN"):            # drawn only for these variants: every other configuration keeps its random stream
+                for name in ("image_lang_att.f_query.1", "image_lang_att.W.1"):
+                    ln(f"{pre}fusion.{name}", C)
+                    if cfg.att_norm == "BN":
+                        sd[f"{pre}fusion.{name}.running_mean"] = 0.1 * torch.randn(C, generator=g)
+                        sd[f"{pre}fusion.{name}.running_var"] = 1 + 0.2 * torch.rand(C, generator=g)
         sd[pre + "res_gate.0.weight"], sd[pre + "res_gate.2.weight"] = tn(C, C), tn(C, C)
         if s < len(cfg.depths) - 1:
             sd[pre + "downsample.reduction.weight"] = tn(2 * C, 4 * C)
@@ -569,6 +597,13 @@ def random_state_dict(cfg: OracleConfig, seed: int = 0, l_in: int = 768) -> Dict
         sd[f"classifier.bn{name}.running_var"] = 1 + 0.2 * torch.rand(hid, generator=g)
     w, b = conv_default(2, hid, 1, 1)
     sd["classifier.conv1_1.weight"], sd["classifier.conv1_1.bias"] = w, b
+    extra = ([("conv2_1", "bn1_1")] if cfg.interpolate_before_seg else []) + ([("conv1_0", "bn1_0")] if cfg.seg_last else [])
+    for cname, bname in extra:                        # drawn last: the other configurations keep their random stream
+        sd[f"classifier.{cname}.weight"] = conv_default(hid, hid, 3, 3)[0]
+        sd[f"classifier.{bname}.weight"] = 1 + 0.1 * torch.randn(hid, generator=g)
+        sd[f"classifier.{bname}.bias"] = 0.1 * torch.randn(hid, generator=g)
+        sd[f"classifier.{bname}.running_mean"] = 0.1 * torch.randn(hid, generator=g)
+        sd[f"classifier.{bname}.running_var"] = 1 + 0.2 * torch.rand(hid, generator=g)
     return sd
 
 

@@ -71,7 +71,7 @@ def test_full_model_state_dict_round_trips_with_reference():
 
 def test_builders_reject_unimplemented_flags():
     from lavt_rs_b200.lib import segmentation
-    for flag in ("--sep_t_pwam", "--seg_last"):      # (--sep_t_pwam alone keeps the unsupported 3-1-1 temporal kernel)
+    for flag in ("--sep_t_pwam", "--ts_pwam"):       # (--sep_t_pwam alone keeps the unsupported 3-1-1 temporal kernel)
         with pytest.raises(NotImplementedError):
             segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "base", flag]))
     # Swin-T / Swin-S widths (96 channels) build: the README's video commands use --swin_type tiny
@@ -110,8 +110,9 @@ def test_inference_only_variants_refuse_training():
     """The lib/bcam.py fusions and --lazy_pred have no hand-written backward: the training entry point must refuse them up front."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in ("--bcam", "--efn", "--gacd", "--lazy_pred"):
-        m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", flag]))
+    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--lazy_pred"], ["--lg_act_layer", "sigmoid"], ["--att_norm_layer_type", "LN"],
+                 ["--interpolate_before_seg"]):
+        m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
@@ -157,3 +158,17 @@ def test_vlt_builders_state_dict_matches_reference(model):
     assert type(mine).__name__ == type(ref).__name__
     missing = mine.load_state_dict({k: v for k, v in ref_sd.items() if not k.startswith("text_encoder.")}, strict=False)
     assert not missing.unexpected_keys and all(k.startswith("text_encoder.") for k in missing.missing_keys)
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("extra", [["--att_norm_layer_type", "BN"], ["--att_norm_layer_type", "LN"], ["--att_norm_layer_type", "none"],
+                                   ["--lg_act_layer", "sigmoid"], ["--interpolate_before_seg"], ["--interpolate_before_seg", "--seg_last"]])
+def test_flag_variants_state_dict_matches_reference(extra):
+    """2-D gate / norm options and the extra decoder levels: same state-dict keys and shapes as the reference builder with the same flags."""
+    from lavt_rs_b200.lib import segmentation
+    ref, _ = ref_shims.build_reference("lavt_one", "tiny", extra=extra)
+    mine = segmentation.lavt_one(pretrained="", args=default_args(["--model", "lavt_one", "--swin_type", "tiny", *extra]))
+    strip = lambda d: {k: v.shape for k, v in d.items() if not k.startswith("text_encoder.")}   # noqa: E731
+    assert strip(ref.state_dict()) == strip(mine.state_dict())
+    if extra[0] == "--lg_act_layer":
+        assert type(mine.backbone.layers[0].res_gate[3]).__name__ == type(ref.backbone.layers[0].res_gate[3]).__name__ == "Sigmoid"

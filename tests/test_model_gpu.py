@@ -625,3 +625,38 @@ def test_lazy_pred_video_and_image_models():
                 for blk in bb.layers[1].blocks:
                     blocks_only = blk(blocks_only)
                 assert rel_l2(v_i, blocks_only.reshape(1, 96, 256)) < 1e-3
+
+
+@pytest.mark.parametrize("flags,cfgkw", [(["--att_norm_layer_type", "BN"], dict(att_norm="BN")), (["--att_norm_layer_type", "LN"], dict(att_norm="LN")),
+                                         (["--att_norm_layer_type", "none"], dict(att_norm="none")), (["--lg_act_layer", "sigmoid"], dict(gate_act="sigmoid")),
+                                         (["--interpolate_before_seg"], dict(interpolate_before_seg=True)),
+                                         (["--interpolate_before_seg", "--seg_last"], dict(interpolate_before_seg=True, seg_last=True))])
+def test_image_model_flag_variants(flags, cfgkw):
+    """--att_norm_layer_type BN | LN | none, --lg_act_layer sigmoid (2-D backbone, reference lib/backbone.py:552-554, 1297-1316) and the decoder
+    levels of --interpolate_before_seg / --seg_last (lib/mask_predictor.py:40-48, 88-97) on the CUDA path vs the oracle (pinned against the
+    reference with the same flags in tests/test_oracle_vs_reference.py)."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    args = default_args(flags)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, **cfgkw)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=args)
+    dec = SimpleDecoding(1024, args)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().eval()
+    x, l, m = O.synthetic_inputs(2, 1, 64, 96, Nl=17, video=False)
+    cap = {}
+    with torch.no_grad():
+        ref_logits = O.model_forward(sd, cfg, x, l, m, capture=cap)
+        feats = bb(x.cuda(), l.cuda(), m.unsqueeze(-1).cuda())
+        low = dec(feats[3], feats[2], feats[1], feats[0])
+        logits = model(x.cuda(), l.cuda(), m.cuda())
+    for i, name in enumerate(("c1", "c2", "c3", "c4")):
+        assert rel_l2(feats[i], cap[name]) < 3e-2, (name, rel_l2(feats[i], cap[name]))
+    assert low.shape == cap["logits_lowres"].shape and rel_l2(low, cap["logits_lowres"]) < 3e-2
+    assert logits.shape == ref_logits.shape and rel_l2(logits, ref_logits) < 3e-2

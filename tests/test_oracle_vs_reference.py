@@ -351,3 +351,34 @@ def test_plain_swin_backbone_matches_reference(window, HW):
     for i, (a, b) in enumerate(zip(got, ref)):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() < 2e-4, f"stage {i + 1}"
+
+
+@pytest.mark.parametrize("extra,cfgkw", [(("--att_norm_layer_type", "BN"), dict(att_norm="BN")), (("--att_norm_layer_type", "LN"), dict(att_norm="LN")),
+                                         (("--att_norm_layer_type", "none"), dict(att_norm="none")), (("--lg_act_layer", "sigmoid"), dict(gate_act="sigmoid")),
+                                         (("--interpolate_before_seg",), dict(interpolate_before_seg=True)),
+                                         (("--interpolate_before_seg", "--seg_last"), dict(interpolate_before_seg=True, seg_last=True))])
+def test_image_backbone_flag_variants_match_reference(extra, cfgkw):
+    """2-D backbone options --att_norm_layer_type BN | LN | none (lib/backbone.py:1297-1316), --lg_act_layer sigmoid (:552-554, :608) and the
+    decoder levels of --interpolate_before_seg / --seg_last (lib/mask_predictor.py:40-48, 88-97): oracle vs the unmodified reference modules."""
+    bb, dec, _ = ref_shims.build_reference_image_backbone_small(window=7, extra=extra)
+    _randomise_norms([bb, dec])
+    g = torch.Generator().manual_seed(3)
+    for m in bb.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.add_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.add_(0.2 * torch.rand(m.running_var.shape, generator=g))
+    sd = _sd(bb, dec)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, **cfgkw)
+    x, l, m = O.synthetic_inputs(2, 1, 64, 80, Nl=13, video=False)
+    with torch.no_grad():
+        ref = bb(x, l, m.unsqueeze(-1))
+        got = O.backbone_forward(sd, cfg, x, l, m.unsqueeze(-1))
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert (a - b).abs().max().item() < 2e-4, f"stage {i}"
+        rl = dec(ref[3], ref[2], ref[1], ref[0])
+        gl = O.decoder_forward(sd, got[3], got[2], got[1], got[0])
+        assert rl.shape == gl.shape and (rl - gl).abs().max().item() < 2e-4
+    # the oracle's random state dict carries the variant's extra keys with the reference's shapes
+    rsd = O.random_state_dict(cfg)
+    assert {k: tuple(v.shape) for k, v in rsd.items()} == {k: tuple(v.shape) for k, v in sd.items()
+                                                           if not k.endswith(("relative_position_index", "num_batches_tracked"))}
