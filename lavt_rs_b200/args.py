@@ -36,6 +36,10 @@ _STRUCTURE_FLAGS = [
     ("--conv3d_kernel_size_s", str, "1-1-1", "spatial-branch Conv3d kernel (B200 path: 1-1-1)"),
     ("--w_t3x3_s1x1", "store_true", False, "SepTPWAM: W = IN(conv_t) + IN(conv_s)"),
     ("--mm_t3x3_s1x1", "store_true", False, "SepTPWAM: project_mm = GELU(conv_t) + GELU(conv_s)"),
+    ("--loss", str, "ce", "training criterion: ce (weighted cross-entropy) | mc_dice | dice_focal | dice_boundary (lavt_rs_b200/losses.py)"),
+    ("--loss_focal_rate", float, 3.0, "weight of the focal term of --loss dice_focal"),
+    ("--loss_dice_rate", float, 1.0, "weight of the Dice term"),
+    ("--loss_boundary_rate", float, 0.05, "weight of the boundary term of --loss dice_boundary"),
     ("--interpolate_before_seg", "store_true", False, "decoder: one more conv3x3 level at 1/2 scale before the classifier (inference)"),
     ("--seg_last", "store_true", False, "with --interpolate_before_seg: a further conv3x3 level at full scale; the video model then returns "
                                         "the classifier output without the final interpolation (inference)"),

@@ -253,9 +253,13 @@ class MultiModalSwinTransformer(V.MultiModalSwinTransformer3D):
                 nn.init.constant_(m.bias, 0)
                 nn.init.constant_(m.weight, 1.0)
         if isinstance(pretrained, str) and pretrained:
-            raise NotImplementedError("initialising from an ImageNet Swin checkpoint is not implemented; "
-                                      "build with pretrained='' and load_state_dict() a LAVT checkpoint")
-        if pretrained is None or pretrained == "":
+            # reference :476-486: init, then load_checkpoint(self, pretrained, strict=False) -- the fusion / gate / per-stage norm
+            # parameters are not in an ImageNet Swin checkpoint and keep their initialisation
+            from ..weights import checkpoint_state_dict
+            self.apply(_init)
+            msg = self.load_state_dict(checkpoint_state_dict(pretrained), strict=False)
+            print(f"=> loaded '{pretrained}': {len(msg.missing_keys)} keys kept their initialisation, {len(msg.unexpected_keys)} unused")
+        elif pretrained is None or pretrained == "":
             self.apply(_init)
         else:
             raise TypeError("pretrained must be a str or None")

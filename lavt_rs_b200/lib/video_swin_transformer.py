@@ -454,6 +454,16 @@ class MultiModalSwinTransformer3D(nn.Module):
                 for p in m.parameters():
                     p.requires_grad = False
 
+    def inflate_weights(self):
+        """Initialise from an ImageNet 2-D Swin checkpoint at ``self.pretrained`` (reference :759-805; Kinetics-style inflation)."""
+        from ..weights import inflate_swin2d_state_dict
+        checkpoint = torch.load(self.pretrained, map_location="cpu", weights_only=False)
+        sd = inflate_swin2d_state_dict(checkpoint["model"], self.patch_size[0], self.window_size, self.state_dict())
+        msg = self.load_state_dict(sd, strict=False)
+        print(msg)
+        print(f"=> loaded successfully '{self.pretrained}'")
+        return msg
+
     def init_weights(self, pretrained=None):
         """trunc_normal(0.02) on Linear weights, zero biases, LayerNorm 1/0 (reference :811-852).  Loading a
         Video-Swin checkpoint follows the reference: keep ``backbone.*`` keys, sum the patch-embed kernel over time."""

@@ -56,3 +56,32 @@ def inflate_lavt2d_state_dict(sd: Dict[str, torch.Tensor], window_size, current:
             tab = grid.reshape(nH2, L2).permute(1, 0)
         out[k] = tab.repeat(2 * Wd - 1, 1)
     return out
+
+
+def inflate_swin2d_state_dict(sd: Dict[str, torch.Tensor], patch_t: int, window_size, current: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """ImageNet 2-D Swin checkpoint -> Video Swin backbone state dict (reference MultiModalSwinTransformer3D.inflate_weights,
+    lib/video_swin_transformer.py:759-805): index / mask buffers dropped, the patch-embedding kernel repeated ``patch_t`` times along a new
+    temporal axis and divided by ``patch_t``, every bias table bicubically resized to the video window when needed and tiled over the
+    2 Wd - 1 temporal offsets (a head-count mismatch leaves the tiled pretrained table as is, like the reference)."""
+    Wd, Wh, Ww = (int(w) for w in window_size)
+    out = {k: v for k, v in sd.items() if "relative_position_index" not in k and "attn_mask" not in k}
+    out["patch_embed.proj.weight"] = out["patch_embed.proj.weight"].unsqueeze(2).repeat(1, 1, patch_t, 1, 1) / patch_t
+    for k in [k for k in out if "relative_position_bias_table" in k]:
+        tab = out[k]
+        L1, nH1 = tab.shape
+        nH2 = current[k].shape[1]
+        L2 = (2 * Wh - 1) * (2 * Ww - 1)
+        if nH1 == nH2 and L1 != L2:
+            S1 = int(L1 ** 0.5)
+            grid = torch.nn.functional.interpolate(tab.permute(1, 0).reshape(1, nH1, S1, S1), size=(2 * Wh - 1, 2 * Ww - 1), mode="bicubic")
+            tab = grid.reshape(nH2, L2).permute(1, 0)
+        out[k] = tab.repeat(2 * Wd - 1, 1)
+    return out
+
+
+def checkpoint_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """What the OpenMMLab ``load_checkpoint`` the reference's 2-D backbone uses (lib/backbone.py:476-486) extracts from a file: the
+    ``state_dict`` / ``model`` entry if present (else the object itself), with a leading ``module.`` (DataParallel) stripped."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    sd = ck.get("state_dict", ck.get("model", ck)) if isinstance(ck, dict) else ck
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}

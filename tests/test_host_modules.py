@@ -172,3 +172,25 @@ def test_flag_variants_state_dict_matches_reference(extra):
     assert strip(ref.state_dict()) == strip(mine.state_dict())
     if extra[0] == "--lg_act_layer":
         assert type(mine.backbone.layers[0].res_gate[3]).__name__ == type(ref.backbone.layers[0].res_gate[3]).__name__ == "Sigmoid"
+
+
+def test_image_backbone_initialises_from_swin_checkpoint(tmp_path):
+    """``init_weights(pretrained=path)`` of the 2-D backbone (reference lib/backbone.py:476-486: OpenMMLab load_checkpoint, strict=False):
+    the Swin keys of the file are loaded ('module.' prefix stripped, 'state_dict' / 'model' wrappers accepted), fusion / gate / per-stage
+    norm parameters keep their initialisation."""
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    kw = dict(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0, patch_norm=True,
+              num_heads_fusion=[1, 1, 1, 1], args=None)
+    src = MultiModalSwinTransformer(**kw)
+    src.init_weights()
+    swin = {"module." + k: v + 0.5 for k, v in src.state_dict().items()
+            if v.is_floating_point() and "fusion" not in k and "res_gate" not in k and not k.startswith("norm")}
+    path = str(tmp_path / "swin_imagenet.pth")
+    torch.save({"model": swin}, path)
+    dst = MultiModalSwinTransformer(**kw)
+    torch.manual_seed(1)
+    dst.init_weights(pretrained=path)
+    got = dst.state_dict()
+    for k, v in swin.items():
+        assert torch.equal(got[k[len("module."):]], v), k
+    assert got["layers.0.fusion.vis_project.0.weight"].abs().sum() > 0 and torch.equal(got["norm0.weight"], torch.ones(128))

@@ -382,3 +382,70 @@ def test_image_backbone_flag_variants_match_reference(extra, cfgkw):
     rsd = O.random_state_dict(cfg)
     assert {k: tuple(v.shape) for k, v in rsd.items()} == {k: tuple(v.shape) for k, v in sd.items()
                                                            if not k.endswith(("relative_position_index", "num_batches_tracked"))}
+
+
+def test_losses_match_reference():
+    """lavt_rs_b200/losses.py vs the reference's losses.py (:38-243): value and gradient w.r.t. the logits for every --loss option."""
+    ref_shims.install_shims()
+    import importlib
+    ref_losses = importlib.import_module("losses")
+    from lavt_rs_b200 import losses as mine
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(3, 2, 24, 20, generator=g)
+    target = (torch.rand(3, 24, 20, generator=g) > 0.6).long()
+    target[:, 5:15, 4:12] = 1
+    pairs = [(ref_losses.MultiClassDiceLoss(), mine.MultiClassDiceLoss()), (ref_losses.DiceFocalLoss(3, 1), mine.DiceFocalLoss(3, 1)),
+             (ref_losses.DiceBoundaryLoss(0.05, 1), mine.DiceBoundaryLoss(0.05, 1)), (ref_losses.DiceFocalLoss(0.5, 2.0), mine.DiceFocalLoss(0.5, 2.0))]
+    for r, m in pairs:
+        a = logits.clone().requires_grad_()
+        b = logits.clone().requires_grad_()
+        lr, lm = r(a, target), m(b, target)
+        lr.backward()
+        lm.backward()
+        assert abs(lr.item() - lm.item()) < 1e-6 * max(1.0, abs(lr.item())), type(m).__name__
+        assert (a.grad - b.grad).abs().max().item() < 1e-7 + 1e-5 * a.grad.abs().max().item(), type(m).__name__
+    bl_r, bl_m = ref_losses.BoundaryLoss(), mine.BoundaryLoss()
+    prob, hot = logits.softmax(1), mine.one_hot(target, 2, dtype=torch.float32)
+    assert abs(bl_r(prob.clone(), hot.clone()).item() - bl_m(prob, hot).item()) < 1e-6
+    assert torch.equal(ref_losses.one_hot(target, 2, dtype=torch.float32), hot)
+    ce = torch.nn.functional.cross_entropy(logits, target, weight=torch.tensor([0.9, 1.1]))      # the reference's version calls .cuda()
+    assert abs(mine.cross_entropy_loss(logits, target).item() - ce.item()) < 1e-7
+    from lavt_rs_b200.args import default_args
+    assert isinstance(mine.build_criterion(default_args(["--loss", "dice_boundary"])), mine.DiceBoundaryLoss)
+    assert mine.build_criterion(default_args([])) is mine.cross_entropy_loss
+
+
+def test_swin2d_inflation_matches_reference(tmp_path):
+    """MultiModalSwinTransformer3D.inflate_weights (lib/video_swin_transformer.py:759-805): ImageNet 2-D Swin checkpoint -> video backbone,
+    this repo's method vs the unmodified reference method on the same synthetic checkpoint (window 7 tables into an 8 x 12 x 12 model)."""
+    import contextlib
+    import io
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D as Mine
+    bb, _, _ = ref_shims.build_reference_backbone_small(window=(8, 12, 12))
+    g = torch.Generator().manual_seed(2)
+    sd2d = {}
+    for k, v in bb.state_dict().items():
+        if "fusion" in k or "res_gate" in k or k.startswith("norm"):
+            continue
+        if "relative_position_bias_table" in k:
+            sd2d[k] = torch.randn(13 * 13, v.shape[1], generator=g)
+        elif k == "patch_embed.proj.weight":
+            sd2d[k] = torch.randn(v.shape[0], 3, 4, 4, generator=g)
+        elif "relative_position_index" in k:
+            sd2d[k] = torch.zeros(49, 49, dtype=torch.long)
+        else:
+            sd2d[k] = torch.randn(v.shape, generator=g)
+    path = str(tmp_path / "swin2d.pth")
+    torch.save({"model": sd2d}, path)
+    mine = Mine(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=(8, 12, 12), drop_path_rate=0.0,
+                patch_norm=True, args=None)
+    bb.pretrained, mine.pretrained = path, path
+    with contextlib.redirect_stdout(io.StringIO()):
+        bb.inflate_weights()
+        mine.inflate_weights()
+    rs, ms = bb.state_dict(), mine.state_dict()
+    for k in sd2d:
+        if "relative_position_index" in k:
+            continue
+        assert torch.equal(rs[k], ms[k]), k
+    assert ms["layers.0.blocks.0.attn.relative_position_bias_table"].shape == (15 * 23 * 23, 4)
