@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace lavt {
 
@@ -30,10 +31,12 @@ constexpr int GEMM_BK = 64;            // 64 bf16 = one 128-byte swizzle row
 
 // GEMM_BN columns per tile, GEMM_STAGES smem ring slots, EPI_WGS epilogue warpgroups (1 -> 256 threads, 2 CTAs/SM;
 // 2 -> 384 threads, 1 CTA/SM).  Two TMEM accumulators of GEMM_BN columns in every configuration.
-template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS>
+// CTA2: CTA-pair variant (tcgen05 cta_group::2): a pair of CTAs computes a 256 x GEMM_BN tile; each CTA holds its 128 rows of A and HALF
+// of the B rows, the leader issues the MMAs for both, every CTA drains its own 128 accumulator lanes.
+template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS, int CTA2 = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (CTA2 ? GEMM_BN / 2 : GEMM_BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = RING_BYTES;                  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
@@ -117,11 +120,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
 }
 
-template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS>
-__global__ void __launch_bounds__(GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::THREADS, GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>::MIN_CTAS)
+template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS, int CTA2 = 0>
+__global__ void __launch_bounds__(GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS, CTA2>::THREADS, GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS, CTA2>::MIN_CTAS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p, const int m_tiles, const int vec_all, long long* const trace_buf) {
-  using L = GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS>;
+  using L = GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS, CTA2>;
+  // CTA pair: rank 0 (leader) issues the MMAs; work items are handed to PAIRS (cluster index), the pair's CTA r owns m-tile 2 * mp + r
+  const int crank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int wid0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int wstep = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   // aligned as an OFFSET so the compiler keeps the shared address space (LDS, not generic LD)
@@ -142,7 +149,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // conv: each tap spans ceil(Cin / 64) k-blocks; a block's surplus channels are zero-filled on the A side, which makes the
   // (finite) next-tap weights the B box picks up there irrelevant.
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = (CTA2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;      // CTA pair: tiles of 256 rows
   const int conv_cpb = (p.cCin + GEMM_BK - 1) / GEMM_BK;
   const int num_kb = (p.rowmap == ROWMAP_CONV) ? p.taps * conv_cpb
                      : (p.rowmap == ROWMAP_WGCONV) ? (p.K / GEMM_BK) : (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -162,12 +169,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);      // one arrive per epilogue warp of the owning warpgroup
+      mbar_init(&tmem_empty_bar[a], CTA2 ? 8 : 4);      // one arrive per epilogue warp of the owning warpgroup (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, ACC * GEMM_BN);  // ACC fp32 accumulators of GEMM_BN columns
+    if constexpr (CTA2) tmem_alloc_2cta(tmem_ptr_smem, ACC * GEMM_BN);
+    else tmem_alloc(tmem_ptr_smem, ACC * GEMM_BN);  // ACC fp32 accumulators of GEMM_BN columns
   }
   if (vec_all) {
     // column scale / bias of ALL N columns staged once per CTA: the epilogue never waits on global memory for them
@@ -179,6 +187,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();        // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -188,11 +197,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool conv = (p.rowmap == ROWMAP_CONV);
       const int cpb = conv ? conv_cpb : 1;
       int it = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      for (int work = wid0; work < total_work; work += wstep) {
         const int ks = work / total_tiles, tile = work - ks * total_tiles;
         const int kb_lo = ks * kbs, kb_hi = min(num_kb, kb_lo + kbs);
-        const int mt = tile / n_tiles;
-        const int n0 = (tile - mt * n_tiles) * GEMM_BN;
+        const int mt = CTA2 ? 2 * (tile / n_tiles) + crank : tile / n_tiles;       // (a pair's odd m-tile may lie past the end: TMA zero-fills)
+        const int n0 = (tile - (tile / n_tiles) * n_tiles) * GEMM_BN;
+        const int nb0 = CTA2 ? n0 + crank * (GEMM_BN / 2) : n0;                    // this CTA's B rows
+        const uint32_t lbar_base = CTA2 ? leader_bar_addr(&full_bar[0]) : 0u;
         int img = 0, h0 = 0, w0 = 0, d0 = 0;
         if (conv) {
           const int tw = mt % p.cTilesW;
@@ -212,7 +223,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (kb == kb_lo) GEMM_TRACE(5, it / num_kb);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if constexpr (CTA2) {
+            // the leader's barrier counts the bytes of BOTH CTAs; each CTA's loads complete on it
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+          } else {
+            mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          }
+          const uint32_t lbar = lbar_base + s * 8;
           int bk0 = kb * GEMM_BK;                      // first K index of this block in the weight matrix
           if (conv) {
             const int tap = kb / cpb, cc = kb - tap * cpb;
@@ -220,11 +237,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.taps == 27) {
               // 3x3x3: tap = (kz * 3 + ky) * 3 + kx; frames outside the clip are zero-filled by TMA like the spatial border
               const int dz = tap / 9 - 1, r9 = tap % 9;
-              tma_load_5d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + r9 % 3 - 1, h0 + r9 / 3 - 1, d0 + dz, img);
+              if constexpr (CTA2) tma_load_5d_2sm(sa, &tmA, lbar, cc * GEMM_BK, w0 + r9 % 3 - 1, h0 + r9 / 3 - 1, d0 + dz, img);
+              else tma_load_5d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + r9 % 3 - 1, h0 + r9 / 3 - 1, d0 + dz, img);
             } else {
               const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
               const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-              tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
+              if constexpr (CTA2) tma_load_4d_2sm(sa, &tmA, lbar, cc * GEMM_BK, w0 + dx, h0 + dy, img);
+              else tma_load_4d(sa, &tmA, &full_bar[s], cc * GEMM_BK, w0 + dx, h0 + dy, img);
             }
           } else if (p.rowmap == ROWMAP_WGCONV) {
             // conv weight gradient: k-block = one 64-pixel tile of one image / frame; A = dz channels, B = x channels shifted by the tap
@@ -260,19 +279,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < GEMM_BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * GEMM_BK + p.b_koff);
             continue;
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
+            if constexpr (CTA2) tma_load_2d_2sm(sa, &tmA, lbar, kb * GEMM_BK, mt * GEMM_BM);
+            else tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], bk0 + p.b_koff, n0);
+          if constexpr (CTA2) tma_load_2d_2sm(sb, &tmB, lbar, bk0 + p.b_koff, nb0);
+          else tma_load_2d(sb, &tmB, &full_bar[s], bk0 + p.b_koff, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_k = make_idesc_bf16_f32(GEMM_BM, GEMM_BN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc_k = make_idesc_bf16_f32(CTA2 ? 2 * GEMM_BM : GEMM_BM, GEMM_BN);
       const uint32_t idesc = p.mnmajor ? (idesc_k | (1u << 15) | (1u << 16)) : idesc_k;      // bits 15 / 16: A / B are MN-major
       int it = 0, lt = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
+      for (int work = wid0; work < total_work; work += wstep, ++lt) {
         const int ks = work / total_tiles;
         const int kb_lo = ks * kbs, kb_hi = min(num_kb, kb_lo + kbs);
         const int acc = lt % ACC;
@@ -303,12 +324,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+              if constexpr (CTA2) umma_bf16_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+              else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
             }
           }
-          umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+          if constexpr (CTA2) umma_commit_2cta(&empty_bar[s]);     // frees the slot in BOTH CTAs
+          else umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
         }
-        umma_commit(&tmem_full_bar[acc]);      // accumulator complete
+        if constexpr (CTA2) umma_commit_2cta(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);      // accumulator complete
         GEMM_TRACE(2, lt);
       }
     }
@@ -322,13 +346,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float* s_bias = s_scale + GEMM_BN;
     const int r = ew * 32 + lane;              // row inside the tile
     int lt = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
+    for (int work = wid0; work < total_work; work += wstep, ++lt) {
       if ((lt % EPI_WGS) != wg) continue;
       const int ks = work / total_tiles, tile = work - ks * total_tiles;
       const int acc = lt % ACC;
       const uint32_t use = static_cast<uint32_t>(lt / ACC);
-      const int mt = tile / n_tiles;
-      const int n0 = (tile - mt * n_tiles) * GEMM_BN;
+      const int mt = CTA2 ? 2 * (tile / n_tiles) + crank : tile / n_tiles;
+      const int n0 = (tile - (tile / n_tiles) * n_tiles) * GEMM_BN;
 
       if (vec_all) {
         s_scale = vec + n0;
@@ -351,7 +375,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int th = (mt / p.cTilesW) % p.cTilesH;
         const int img = mt / (p.cTilesW * p.cTilesH);
         const int h = th * p.cTH + r / p.cTW, w = tw * p.cTW + r % p.cTW;
-        if (h < p.cH && w < p.cW) {
+        if (h < p.cH && w < p.cW && mt < m_tiles) {
           m = (static_cast<long long>(img) * p.cH + h) * p.cW + w;
           orow = m;
         }
@@ -394,7 +418,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // last read of this accumulator: hand it back to the MMA warp before finishing the math / stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_leader(&tmem_empty_bar[acc]);      // the leader's MMA thread waits for both CTAs' drains
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         if (!live || c >= nch) continue;
         float f[32];
@@ -468,9 +495,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();        // the peer may still be read by the leader's MMAs / signalled by its commits
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, ACC * GEMM_BN);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, ACC * GEMM_BN);
+    else tmem_dealloc(tmem_base, ACC * GEMM_BN);
   }
 }
 
@@ -487,10 +516,10 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI_WGS>
+template <int BN, int STAGES, int EPI_WGS, int CTA2 = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, EPI_WGS>;
-  auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS>;
+  using L = GemmSmem<BN, STAGES, EPI_WGS, CTA2>;
+  auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS, CTA2>;
   // stage scale / bias of all N columns when that fits next to the operand ring (per-CTA budget: the whole SM, or half of
   // it for the 2-CTAs/SM variant); otherwise the kernel refills a per-tile staging area
   const int budget = (L::MIN_CTAS == 1 ? 227 * 1024 : 113 * 1024) - (L::VEC_OFF + 1024);
@@ -501,17 +530,34 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const long long total = 1LL * m_tiles * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
+  const long long total = 1LL * (CTA2 ? (m_tiles + 1) / 2 : m_tiles) * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   LAVT_REQUIRE(total < (1LL << 30), "gemm: too many tiles (%lld)", total);
-  const long long slots = 1LL * sm_count() * L::MIN_CTAS;
-  const int grid = static_cast<int>(total < slots ? total : slots);
+  const long long slots = CTA2 ? sm_count() / 2 : 1LL * sm_count() * L::MIN_CTAS;      // CTA pairs: one pair per TPC
+  const int grid = static_cast<int>(total < slots ? total : slots) * (CTA2 ? 2 : 1);
   long long* trace = nullptr;
   const char* trace_path = getenv("LAVT_GEMM_TRACE");
   if (trace_path) {
     LAVT_CUDA(cudaMalloc(&trace, 6 * 32 * sizeof(long long)));
     LAVT_CUDA(cudaMemsetAsync(trace, 0, 6 * 32 * sizeof(long long), stream));
   }
-  kfn<<<grid, L::THREADS, smem, stream>>>(tmA, tmB, p, m_tiles, vec_all, trace);
+  if constexpr (CTA2) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(L::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LAVT_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, p, m_tiles, vec_all, trace));
+  } else {
+    kfn<<<grid, L::THREADS, smem, stream>>>(tmA, tmB, p, m_tiles, vec_all, trace);
+  }
   LAVT_LAUNCH_CHECK("gemm_bf16_tc_kernel");
   if (trace) {
     // debug only: synchronous dump of CTA 0's event clocks (rows: acc free, first operands, MMAs issued, acc ready, epilogue end, first TMA)
@@ -533,6 +579,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // 0: 128-wide tiles, 6 stages, two epilogue warpgroups, 1 CTA/SM
 // 1: 128-wide tiles, 3 stages, one epilogue warpgroup, 2 CTAs/SM
 // 2: 256-wide tiles, 4 stages, two epilogue warpgroups, 1 CTA/SM (N % 256 == 0)
+// 4: CTA PAIRS (cta_group::2): 256 x 256 tiles over two SMs, 6 stages of (A 128 x 64 | half of B 128 x 64) per CTA (N % 256 == 0,
+//    K-major operands, no split-K)
 static int gemm_variant(const GemmParams& p) {
   static int forced = -2;
   if (forced == -2) {
@@ -550,7 +598,14 @@ static int gemm_variant(const GemmParams& p) {
     const long long splits = p.ksplit > 1 ? p.ksplit : 1;                         // split-K work items fill the machine too
     if ((p.N % 256) == 0 && m_tiles * splits * (p.N / 256) >= sm_count() / 2) v = 2;      // (partial 256-wide tiles never pay off)
     else v = (p.K >= 1024) ? 1 : 0;
+    static int pair = -1;
+    if (pair < 0) {
+      const char* e = getenv("LAVT_GEMM_PAIR");
+      pair = e ? atoi(e) : 1;
+    }
+    if (v == 2 && pair && !p.mnmajor && p.ksplit <= 1 && p.rowmap != ROWMAP_WGCONV && (m_tiles + 1) / 2 * (p.N / 256) >= sm_count() / 4) v = 4;
   }
+  if (v == 4 && ((p.N % 256) != 0 || p.mnmajor || p.ksplit > 1 || p.rowmap == ROWMAP_WGCONV)) v = 2;
   if (v == 2 && (p.N % 256) != 0) v = 0;
   return v;
 }
@@ -640,13 +695,14 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
   if (!p.mnmajor) {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t strides[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {GEMM_BK, gemm_variant(p) == 2 ? 256u : 128u};
+    uint32_t box[2] = {GEMM_BK, gemm_variant(p) == 2 ? 256u : 128u};      // (CTA pairs: each CTA loads 128 of the tile's 256 B rows)
     int rc = make_tmap_bf16(&tmB, Bw, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   const int variant = gemm_variant(p);
   if (variant == 1) return launch_gemm<128, 3, 1>(tmA, tmB, p, m_tiles, stream);
   if (variant == 2) return launch_gemm<256, 4, 2>(tmA, tmB, p, m_tiles, stream);
+  if (variant == 4) return launch_gemm<256, 6, 2, 1>(tmA, tmB, p, m_tiles, stream);
   return launch_gemm<128, 6, 2>(tmA, tmB, p, m_tiles, stream);
 }
 

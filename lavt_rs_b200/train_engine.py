@@ -41,7 +41,7 @@ class GradStore:
         if params is not None:
             sizes: Dict[torch.device, int] = {}
             for p in params:
-                if not p.requires_grad or id(p) in self._slots or not p.is_cuda:
+                if not p.requires_grad or id(p) in self._slots:
                     continue
                 off = sizes.get(p.device, 0)
                 self._slots[id(p)] = (off, p)
@@ -117,6 +117,31 @@ class GradStore:
                     param.grad.add_(g)
                 done.append(param)
         return done
+
+    def flat_ranges(self, params) -> Tuple[List[torch.Tensor], List[torch.nn.Parameter]]:
+        """Contiguous slices of the flat allocation that cover the slots of ``params`` (adjacent slots merged; the 32-byte slot padding
+        between them holds zeros), plus the parameters that have no slot.  The gradient all-reduce runs IN PLACE on these slices --
+        ``param.grad`` of a slotted fp32 parameter is a view of the same memory -- so no flatten / copy-back pass exists."""
+        by_dev: Dict[torch.device, List[Tuple[int, int]]] = {}
+        loose = []
+        for p in params:
+            slot = self._slots.get(id(p))
+            if slot is None or p.dtype != torch.float32:
+                loose.append(p)
+                continue
+            by_dev.setdefault(p.device, []).append((slot[0], slot[0] + (p.numel() + 7) // 8 * 8))
+        views = []
+        for dev, spans in by_dev.items():
+            spans.sort()
+            lo, hi = spans[0]
+            for a, b in spans[1:]:
+                if a <= hi:
+                    hi = max(hi, b)
+                else:
+                    views.append(self._flat[dev][lo:hi])
+                    lo, hi = a, b
+            views.append(self._flat[dev][lo:hi])
+        return views, loose
 
     def buffers(self) -> List[Tuple[torch.nn.Parameter, torch.Tensor]]:
         """(parameter, fp32 gradient buffer) pairs after folding the alternate layouts (gradient all-reduce, tests)."""

@@ -203,49 +203,72 @@ class SegmentFunction(torch.autograd.Function):
 
 
 class GradReducer:
-    """Gradient all-reduce driven by ``segment_backward``'s ``on_ready`` callback: each finished parameter group (decoder, stages last
-    to first, patch embedding, text encoder) is handed to ``param.grad`` and flattened into one bucket.
+    """Gradient all-reduce driven by ``segment_backward``'s ``on_ready`` callback (replaces DistributedDataParallel, train.py:589-592):
+    each finished parameter group (decoder, stages last to first, patch embedding, text encoder) is handed to ``param.grad`` and averaged
+    over the ranks IN PLACE on the contiguous slices of the GradStore's flat fp32 allocation that hold the group (``param.grad`` are views
+    of it): no flatten, no copy-back, the division is NCCL's ReduceOp.AVG.  Parameters without a slot (the text encoder's, whose gradients
+    come from autograd) go through one coalesced all-reduce of their own tensors.
 
-    ``overlap=False`` (default): the buckets are all-reduced when ``wait()`` is called at the end of the backward.
-    ``overlap=True``: every bucket's all-reduce is launched asynchronously (NCCL's own stream) as soon as the group is finished, so it
-    runs under the backward kernels of the earlier stages.  Measured back to back on 2 x B200: 96.7 ms per step overlapped vs 97.4 ms
-    after the backward (1 GPU: 91.7 ms) -- within noise, i.e. the 226 M-gradient all-reduce over NVLink is not what the extra 5-6 ms of
-    the multi-GPU step are made of (SyncBN's 24 small blocking reductions and per-step skew are); kept as an option.
-    With one rank everything is a no-op except the hand-over to ``param.grad``."""
+    ``overlap=True`` (default): every group's all-reduce is launched asynchronously as soon as the group is finished, so it runs on NCCL's
+    stream under the backward kernels of the earlier stages; ``wait()`` joins them before the optimizer.  ``overlap=False`` defers all
+    launches to ``wait()``.  ``compress='bf16'`` halves the NVLink bytes (cast, all-reduce in bf16, cast back) at the price of two extra
+    passes over the bucket and bf16 rounding of the summed gradient; off by default -- 906 MB of fp32 gradients take ~3 ms of an 80 ms step
+    on NVSwitch and are hidden under the backward anyway.  With one rank everything is a no-op except the hand-over to ``param.grad``."""
 
-    def __init__(self, overlap: bool = False):
+    def __init__(self, overlap: bool = True, compress: Optional[str] = None):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
         self.overlap = overlap
-        self.pending = []
+        self.compress = compress
+        self.pending = []          # (handle or None, tensors, needs_division, bf16 staging or None)
+        self._avg = None
+        if self.dist is not None:
+            self._avg = self.dist.ReduceOp.AVG if self.dist.get_backend() == "nccl" else None     # gloo has no AVG: SUM, then divide
 
     def ready(self, grads: T.GradStore):
         def _cb(params):
-            self.reduce(grads.finalize(only=params))
+            done = grads.finalize(only=params)
+            self.reduce(done, grads)
         return _cb
 
-    def reduce(self, params) -> None:
-        gs = [p.grad for p in params if p.grad is not None]
-        if self.dist is None or not gs:
+    def _launch(self, tensors, async_op: bool):
+        """One all-reduce per contiguous slice (a handful per group); returns the entries to join."""
+        out = []
+        for t in tensors:
+            if self.compress == "bf16":
+                stage = t.to(torch.bfloat16)
+                h = self.dist.all_reduce(stage, op=self._avg or self.dist.ReduceOp.SUM, async_op=async_op)
+                out.append((h if async_op else None, t, self._avg is None, stage))
+            else:
+                h = self.dist.all_reduce(t, op=self._avg or self.dist.ReduceOp.SUM, async_op=async_op)
+                out.append((h if async_op else None, t, self._avg is None, None))
+        return out
+
+    def reduce(self, params, grads: Optional[T.GradStore] = None) -> None:
+        params = [p for p in params if p.grad is not None]
+        if self.dist is None or not params:
             return
-        if not self.overlap:
-            self.pending.append((None, None, gs))
-            return
-        flat = torch.cat([g.reshape(-1) for g in gs])
-        self.pending.append((self.dist.all_reduce(flat, async_op=True), flat, gs))
+        views, loose = grads.flat_ranges(params) if grads is not None else ([], params)
+        tensors = list(views) + [p.grad for p in loose]
+        if self.overlap:
+            self.pending += self._launch(tensors, async_op=True)
+        else:
+            self.pending += [("deferred", t, None, None) for t in tensors]
 
     def wait(self) -> None:
-        for handle, flat, gs in self.pending:
-            if handle is None:
-                flat = torch.cat([g.reshape(-1) for g in gs])
-                self.dist.all_reduce(flat)
-            else:
+        if self.dist is None:
+            self.pending = []
+            return
+        deferred = [t for h, t, _, _ in self.pending if isinstance(h, str)]
+        entries = [e for e in self.pending if not isinstance(e[0], str)] + (self._launch(deferred, async_op=False) if deferred else [])
+        world = self.dist.get_world_size()
+        for handle, t, divide, stage in entries:
+            if handle is not None:
                 handle.wait()
-            flat /= self.dist.get_world_size()
-            off = 0
-            for g in gs:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+            if stage is not None:
+                t.copy_(stage)
+            if divide:
+                t.div_(world)
         self.pending = []
 
 

@@ -90,15 +90,26 @@ def _reducer_worker(rank, world, port, q):
     g = torch.Generator().manual_seed(6)
     groups = [[torch.nn.Parameter(torch.zeros(s)) for s in shapes] for shapes in (((4, 3), (5,)), ((7, 2, 2),), ((1,), (9, 9)))]
     base = [[torch.randn(p.shape, generator=g) for p in grp] for grp in groups]
-    store = GradStore()
-    red = GradReducer(overlap=(rank >= 0) and bool(os.environ.get("LAVT_TEST_OVERLAP", "1") == "1"))
-    cb = red.ready(store)
-    for grp, bs in zip(groups, base):
-        for p, b in zip(grp, bs):
-            store.of(p).add_(b * (rank + 1))
-        cb(grp)                              # group finished: hand over + start its all-reduce
-    red.wait()
-    ok = all(torch.allclose(p.grad, 1.5 * b, rtol=1e-6, atol=1e-6) for grp, bs in zip(groups, base) for p, b in zip(grp, bs))
+    ok = True
+    # (slotted flat allocation | loose buffers) x (launch per group under the backward | deferred to wait()) x (fp32 | bf16 on the wire)
+    for slotted, overlap, compress in ((True, True, None), (True, False, None), (False, True, None), (True, True, "bf16")):
+        for grp in groups:
+            for p in grp:
+                p.grad = None
+        # interleave the slot order of the groups so that a group maps to several non-adjacent slices of the flat buffer
+        store = GradStore([groups[0][0], groups[2][0], groups[1][0], groups[0][1], groups[2][1]]) if slotted else GradStore()
+        red = GradReducer(overlap=overlap, compress=compress)
+        cb = red.ready(store)
+        for grp, bs in zip(groups, base):
+            for p, b in zip(grp, bs):
+                store.of(p).add_(b * (rank + 1))
+            cb(grp)                              # group finished: hand over + start its all-reduce
+        red.wait()
+        tol = 1e-2 if compress else 1e-6
+        ok = ok and all(torch.allclose(p.grad, 1.5 * b, rtol=tol, atol=tol) for grp, bs in zip(groups, base) for p, b in zip(grp, bs))
+        if slotted:      # param.grad aliases the flat allocation: the all-reduce ran in place, no copy-back exists
+            flat = store._flat[groups[0][0].device]
+            ok = ok and all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for grp in groups for p in grp)
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -32,6 +32,9 @@ def main():
         (1152, 3072, 1024, "s3 qkv"), (1152, 4096, 1024, "s3 fc1"), (1152, 1024, 4096, "s3 fc2"),
         (8192, 8192, 8192, "square 8k"), (36864, 2048, 512, "s2 fc1 B=8"),
     ]
+    if os.environ.get("LAVT_BENCH_SHAPES") == "big":     # the 8-clip bench shapes of stage 2 (18 of the 24 blocks) + the square reference
+        shapes = [(50176, 1536, 512, "s2 qkv B=8"), (50176, 512, 512, "s2 proj B=8"), (36864, 2048, 512, "s2 fc1 B=8"),
+                  (36864, 512, 2048, "s2 fc2 B=8"), (147456, 1024, 256, "s1 fc1 B=8"), (8192, 8192, 8192, "square 8k")]
     for M, N, K, tag in shapes:
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = torch.randn(N, K, device="cuda").bfloat16()
@@ -39,10 +42,16 @@ def main():
         bias = torch.zeros(N, device="cuda")
         t = timeit(lambda: _cabi.gemm_bf16(a, w, bias=bias, out_bf16=out))
         t_ref = timeit(lambda: torch.matmul(a, w.t()))
-        res.append(dict(tag=tag, M=M, N=N, K=K, us=t * 1e6, tflops=2 * M * N * K / t / 1e12,
-                        cublas_us=t_ref * 1e6, cublas_tflops=2 * M * N * K / t_ref / 1e12))
+        res.append(dict(tag=tag, M=M, N=N, K=K, us=round(t * 1e6, 1), tflops=round(2 * M * N * K / t / 1e12, 1),
+                        cublas_us=round(t_ref * 1e6, 1), cublas_tflops=round(2 * M * N * K / t_ref / 1e12, 1)))
         print(res[-1], flush=True)
-    for n_img, H, Cin, tag in [(8, 96, 640, "conv1_2"), (8, 96, 512, "conv2_2"), (8, 48, 768, "conv1_3"), (8, 24, 1536, "conv1_4")]:
+        if os.environ.get("LAVT_BENCH_SHAPES") == "big" and K == 512 and N >= 1536:     # the same shape with the GELU epilogue (fc1)
+            t = timeit(lambda: _cabi.gemm_bf16(a, w, bias=bias, act=_cabi.ACT_GELU, out_bf16=out))
+            print(dict(tag=tag + " +GELU", us=round(t * 1e6, 1), tflops=round(2 * M * N * K / t / 1e12, 1)), flush=True)
+    convs = [(8, 96, 640, "conv1_2"), (8, 96, 512, "conv2_2"), (8, 48, 768, "conv1_3"), (8, 24, 1536, "conv1_4")]
+    if os.environ.get("LAVT_BENCH_SHAPES") == "big":
+        convs = [(64, 96, 640, "conv1_2 B=8"), (64, 96, 512, "conv2_2 B=8"), (64, 48, 768, "conv1_3 B=8")]
+    for n_img, H, Cin, tag in convs:
         x = torch.randn(n_img, H, H, Cin, device="cuda").bfloat16()
         w = torch.randn(512, 9 * Cin, device="cuda").bfloat16()
         out = torch.empty(n_img * H * H, 512, device="cuda", dtype=torch.bfloat16)

@@ -36,7 +36,9 @@ def main():
     p.add_argument("--optimizer", action="store_true", help="include the AdamW update (FusedAdamW over the reference's parameter groups, "
                                                             "poly LR) in the timed step")
     p.add_argument("--sep-t-pwam", action="store_true", help="the reference README's video configuration (SepTPWAM fusion flags)")
-    p.add_argument("--overlap-allreduce", action="store_true", help="launch each stage's gradient all-reduce under the rest of the backward")
+    p.add_argument("--no-overlap-allreduce", dest="overlap_allreduce", action="store_false",
+                   help="all-reduce after the backward instead of launching each stage's all-reduce under the rest of the backward (default)")
+    p.add_argument("--bf16-allreduce", action="store_true", help="cast the gradient buckets to bf16 for the all-reduce")
     p.add_argument("--graph", action="store_true", help="capture forward + loss + backward of the hot path (everything after the text encoder) "
                                                         "in one CUDA graph (1 GPU only: SyncBN / gradient collectives stay eager)")
     p.add_argument("--eager-text", action="store_true", help="run the text encoder eagerly instead of as CUDA graphs")
@@ -143,12 +145,12 @@ def main():
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
         l_feats = text_fn(ids, m)
         grads = T.GradStore(params)
-        reducer = TR.GradReducer(overlap=a.overlap_allreduce)
+        reducer = TR.GradReducer(overlap=a.overlap_allreduce, compress="bf16" if a.bf16_allreduce else None)
         loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
         grads.finalize()
         if not a.frozen_text:
             l_feats.backward(dl)
-            reducer.reduce([prm for prm in text.parameters() if prm.requires_grad])
+            reducer.reduce([prm for prm in text.parameters() if prm.requires_grad], grads)
         reducer.wait()
         if opt is not None:
             opt.step()
