@@ -227,6 +227,75 @@ def gpu_eager_baseline(window12: bool, sd_cpu, dev, B: int):
     return out
 
 
+def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, steps: int = 3, warmup: int = 2):
+    """BASELINE configs[3] next to the headline: one training step (BERT + backbone + decoder forward, weighted CE, hand-written backward,
+    gradient all-reduce over NCCL launched per finished stage under the rest of the backward, SyncBN statistics) at ``clips`` clips per
+    GPU.  Runs on EVERY rank (it contains collectives); returns the dict rank 0 reports under ``extras.train_step``."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    from lavt_rs_b200 import training as TR
+    model.train()
+    for layer in model.backbone.layers:
+        for blk in layer.blocks:
+            blk.drop_path_rate = 0.0
+    text = model.text_encoder
+    text.eval()                                   # BERT dropout off: identical work, reproducible numbers
+    params = [p for p in model.parameters() if p.requires_grad]
+    seg_params = [p for p in list(model.backbone.parameters()) + list(model.classifier.parameters()) if p.requires_grad]
+    batches = []
+    for s_ in range(2):
+        x, ids, m = synth_batch(clips, 201 + s_ + 10 * rank)
+        g = torch.Generator().manual_seed(77 + s_ + 10 * rank)
+        tgt = torch.randint(0, 2, (clips * T_FRAMES, IMG, IMG), generator=g)
+        batches.append((x.to(dev), ids.to(dev), m.to(dev), tgt.to(dev)))
+    state = {}
+
+    def step(i):
+        x, ids, m, tgt = batches[i % 2]
+        for p in params:
+            p.grad = None
+        l_feats = text(ids, attention_mask=m)[0].permute(0, 2, 1)
+        grads = T.GradStore(seg_params)
+        reducer = TR.GradReducer(overlap=True)
+        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
+        grads.finalize()
+        l_feats.backward(dl)
+        reducer.reduce([p for p in text.parameters() if p.requires_grad], grads)
+        reducer.wait()
+        state["loss"] = loss
+
+    for i in range(warmup):
+        step(i)
+    E.LAUNCHES = 0
+    step(0)
+    launches = E.LAUNCHES
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    loss = float(state["loss"].item())
+    for p in params:
+        p.grad = None
+    model.eval()
+    return {"metric": "LAVT-RS train step clips/s (fwd+bwd, 8x384^2)", "clips_per_s": clips * world * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "n_gpus": world, "clips_per_gpu_per_step": clips, "steps": steps, "gpu_launches_per_step": launches, "loss": loss,
+            "config": "BASELINE configs[3]: fwd + [0.9,1.1]-weighted CE + bwd in bf16, window 8x7x7, DropPath off, no optimizer update; "
+                      + ("NCCL gradient all-reduce per finished stage under the rest of the backward (in place on the flat fp32 gradient "
+                         "buffer, ReduceOp.AVG) + SyncBN statistics" if world > 1 else "single GPU: no collectives"),
+            "peak_memory_bytes": torch.cuda.max_memory_allocated(dev)}
+
+
 def run_reference(a):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference cannot travel)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -410,6 +479,14 @@ def main():
             fam = K.TIMER.summary(_pk.get("bf16_tflops_sustained", 1400.0), _pk.get("hbm_gbs", 6550.0))
             K.TIMER.enabled = False
 
+    train_extra = None
+    if not a.no_extras and not a.window12 and not SEP_T_PWAM:
+        try:
+            train_extra = train_step_extra(model, dev, world, rank, dist)
+        except Exception as e:                               # noqa: BLE001  (reported, never fatal for the headline line)
+            train_extra = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -509,6 +586,8 @@ def main():
                 extras[key] = {"error": repr(e)[:200]}
         SEP_T_PWAM = keep
         res["extras"] = extras
+    if train_extra is not None:
+        res.setdefault("extras", {})["train_step"] = train_extra
     print(json.dumps(res))
     if dist is not None:
         dist.destroy_process_group()

@@ -603,7 +603,11 @@ static int gemm_variant(const GemmParams& p) {
       const char* e = getenv("LAVT_GEMM_PAIR");
       pair = e ? atoi(e) : 1;
     }
-    if (v == 2 && pair && !p.mnmajor && p.ksplit <= 1 && p.rowmap != ROWMAP_WGCONV && (m_tiles + 1) / 2 * (p.N / 256) >= sm_count() / 4) v = 4;
+    // CTA pairs (measured, tools/bench_gemm.py B = 8 shapes): qkv 942 -> 1004, fc1 932 -> 990, fc2 1129 -> 1207, 8192^3 1237 -> 1362 TFLOP/s;
+    // the implicit-GEMM convs do not gain (their A tiles are re-fetched tap by tap from L2, 1.20-1.37 PFLOP/s either way) and stay single-CTA
+    if (v == 2 && pair && !p.mnmajor && p.ksplit <= 1 && (p.rowmap == ROWMAP_IDENTITY || p.rowmap == ROWMAP_WINDOW || pair == 2) &&
+        p.rowmap != ROWMAP_WGCONV && (m_tiles + 1) / 2 * (p.N / 256) >= sm_count() / 4)
+      v = 4;
   }
   if (v == 4 && ((p.N % 256) != 0 || p.mnmajor || p.ksplit > 1 || p.rowmap == ROWMAP_WGCONV)) v = 2;
   if (v == 2 && (p.N % 256) != 0) v = 0;
