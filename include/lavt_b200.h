@@ -170,6 +170,12 @@ int lavt_bert_embed(const int64_t* ids, const float* word, const float* pos, con
  * qkv bf16 [B*Nl, 3H] = q | k | v with q pre-scaled by 64^-0.5 * log2(e); mask fp32 [B, Nl]; out bf16 [B*Nl, H] */
 int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16, int32_t B, int32_t Nl, int32_t H, int32_t heads,
                         void* stream);
+/* Split-precision operand of the text encoder's GEMMs: x fp32 [M,K] (pitch ldx) -> out bf16 [M,3K] = hi | lo | hi with hi = bf16(x),
+ * lo = bf16(x - hi).  Against weights stored [W_hi | W_hi | W_lo] one lavt_gemm_bf16 launch accumulates hi W_hi + lo W_hi + hi W_lo in
+ * fp32 on the tensor cores (relative error ~1e-5): BERT's 12 layers no longer dominate the logit error of the whole model. */
+int lavt_split3_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t M, int32_t K, void* stream);
+/* lavt_bert_attention with fp32 qkv [B*Nl, 3H] / out [B*Nl, H] (same pre-scaled q convention) */
+int lavt_bert_attention_f32(const float* qkv, const float* mask, float* out, int32_t B, int32_t Nl, int32_t H, int32_t heads, void* stream);
 /* (B, Nl, C) fp32 -> (B, C, Nl) fp32: l_feats = last_hidden_state.permute(0, 2, 1) (lib/_utils.py:54) */
 int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream);
 

@@ -94,6 +94,8 @@ SIGNATURES = {
     "lavt_bert_embed": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_bert_attention": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_rows_to_channels_first": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "lavt_split3_bf16": [_vp, _i64, _vp, _i64, _i32, _vp],
+    "lavt_bert_attention_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_upsample_concat": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp],
     "lavt_conv1x1_logits": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "lavt_upsample_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -1096,3 +1098,19 @@ def layernorm_window_gather_f32(x: torch.Tensor, geom: WinGeom, gamma, beta, out
     check(lib().lavt_layernorm_window_gather_f32(_c(x, torch.float32, "x").data_ptr(), x.shape[-1], C.byref(geom), _c(gamma.detach(), torch.float32, "gamma").data_ptr(),
                                                  _c(beta.detach(), torch.float32, "beta").data_ptr(), float(eps), _c(out_f32, torch.float32, "out").data_ptr(),
                                                  stream_ptr()), "lavt_layernorm_window_gather_f32")
+
+
+def split3_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x fp32 [M,K] -> out bf16 [M,3K] = hi | lo | hi (split-precision GEMM operand)."""
+    _req(_rows2d(x, "x"), torch.float32, "x")
+    M, Kd = x.shape
+    if tuple(out.shape) != (M, 3 * Kd):
+        raise LavtError("split3: shape mismatch")
+    check(lib().lavt_split3_bf16(x.data_ptr(), x.stride(0), _c(out, torch.bfloat16, "out").data_ptr(), M, Kd, stream_ptr()), "lavt_split3_bf16")
+
+
+def bert_attention_f32(qkv: torch.Tensor, mask: torch.Tensor, out: torch.Tensor, heads: int) -> None:
+    B, Nl = mask.shape
+    H = out.shape[-1]
+    check(lib().lavt_bert_attention_f32(_c(qkv, torch.float32, "qkv").data_ptr(), _c(mask, torch.float32, "mask").data_ptr(),
+                                        _c(out, torch.float32, "out").data_ptr(), B, Nl, H, heads, stream_ptr()), "lavt_bert_attention_f32")

@@ -228,6 +228,12 @@ int lavt_bert_attention(const void* qkv_bf16, const float* mask, void* out_bf16,
   return bert_attention_dispatch(CB(qkv_bf16), mask, MB(out_bf16), B, Nl, H, heads, S(stream));
 }
 
+int lavt_split3_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t M, int32_t K, void* stream) {
+  return split3_bf16_dispatch(x, ldx, MB(out_bf16), M, K, S(stream));
+}
+int lavt_bert_attention_f32(const float* qkv, const float* mask, float* out, int32_t B, int32_t Nl, int32_t H, int32_t heads, void* stream) {
+  return bert_attention_f32_dispatch(qkv, mask, out, B, Nl, H, heads, S(stream));
+}
 int lavt_rows_to_channels_first(const float* in, float* out, int32_t B, int32_t Nl, int32_t C, void* stream) {
   return rows_to_cf_dispatch(in, out, B, Nl, C, S(stream));
 }

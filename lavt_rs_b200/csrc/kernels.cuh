@@ -128,6 +128,8 @@ int bert_embed_dispatch(const long long* ids, const float* word, const float* po
                         int H, int vocab, cudaStream_t st);
 int bert_attention_dispatch(const __nv_bfloat16* qkv, const float* mask, __nv_bfloat16* out, int B, int Nl, int H, int heads,
                             cudaStream_t st);
+int split3_bf16_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int Kd, cudaStream_t st);
+int bert_attention_f32_dispatch(const float* qkv, const float* mask, float* out, int B, int Nl, int H, int heads, cudaStream_t st);
 int rows_to_cf_dispatch(const float* in, float* out, int B, int Nl, int C, cudaStream_t st);
 
 int upsample_concat_dispatch(const __nv_bfloat16* prev, int ph, int pw, int C1, const __nv_bfloat16* skip, int C2,
