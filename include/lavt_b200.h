@@ -132,7 +132,8 @@ int lavt_window_attention_has_lse(const lavt_win_geom_t* geom, int32_t L, int32_
  *   0 = auto: one-pass key-chunked tcgen05 / TMEM kernel (attn_tc2.cu) for windows of up to 1152 tokens
  *   1 = mma.sync kernels only
  *   2 = prefer the two-pass tcgen05 kernel (attn_tc.cu) for windows of <= 400 tokens
- *   3 = attn_tc2.cu (same as auto).  Returns the previous setting. */
+ *   3 = attn_tc2.cu (key-chunked one-pass kernel, any window up to 1152 tokens)
+ *   4 = attn_tc3.cu (7 x 7 windows: row-parallel warpgroups, run-padded keys; what auto picks for them).  Returns the previous setting. */
 int lavt_set_attention_impl(int32_t impl);
 
 /* ---- PWAM (lib/video_swin_transformer.py:919-1009) ---- */

@@ -393,9 +393,9 @@ def patch_embed_im2col(x: torch.Tensor, out_bf16: torch.Tensor) -> None:
 
 
 def set_attention_impl(impl: str) -> str:
-    """'auto' (tcgen05 kernels: the one-pass chunked kernel for every window size), 'tc1' (prefer the two-pass tcgen05 kernel for
-    windows of <= 400 tokens), 'tc2' (= auto today) or 'mma' (mma.sync kernels only); returns the previous setting."""
-    names = ["auto", "mma", "tc1", "tc2"]
+    """'auto' (tcgen05 kernels: attn_tc3.cu for 7 x 7 windows, else the two-pass kernel up to 400 tokens, else the chunked one-pass
+    kernel), 'tc1' / 'tc2' / 'tc3' (prefer that generation where it applies) or 'mma' (mma.sync kernels only); returns the previous setting."""
+    names = ["auto", "mma", "tc1", "tc2", "tc3"]
     prev = lib().lavt_set_attention_impl(names.index(impl))
     return names[prev] if 0 <= prev < len(names) else "auto"
 

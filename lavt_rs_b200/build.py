@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("LAVT_NVCC_EXTRA", "").split()      # debug builds, e.g. LAVT_NVCC_EXTRA=-DT3_WATCHDOG
 
 
 def _nvcc() -> str:

@@ -1,0 +1,635 @@
+// tcgen05 / TMEM shifted-window attention core, third generation: windows whose (h, w) extent is the configured 7 x 7
+// (N = 49 * wd tokens, wd <= 8: every window of the 8 x 7 x 7 video model and of the 7 x 7 image model).
+// (reference WindowAttention3D.forward, lib/video_swin_transformer.py:147-165; 2-D twin lib/backbone.py:127-138)
+//     S = q k^T + relative-position bias (+ shifted-window mask)  ->  softmax  ->  O = P v       per (window, head)
+//
+// What the profiles of the first two generations said (profiles/r2_ncu_attn_tc2_*): 12.6 issued instructions per score against 1
+// MUFU.EX2; one shared-memory gather + index arithmetic per score for the bias; ~15 % of the issue slots in mbarrier polling of
+// dedicated MMA-issuer warps; the key-split groups merge partial (m, l, O) per tile.  This kernel is built around the exponential:
+//   * KEY LAYOUT.  K and V of a unit arrive through ONE 4-D TMA box each, (32 ch, 8 of 7 w, 8 of 7 h, wd frames): the out-of-bounds
+//     w = 7 column and h = 7 row are zero-filled by TMA, so in shared memory (and therefore along the S columns) every run of 7 keys
+//     that share (frame, h) starts at a multiple of 8 and every frame at a multiple of 64.  A frame = one 64-column key chunk.
+//   * BIAS.  Along such a run the table index is contiguous, so with the w axis of the table flipped a run's 7 bias values are 7
+//     consecutive floats.  Four copies of the table, shifted by 0..3 floats, make the run start 16-byte aligned in one of them: the
+//     bias of a run is TWO LDS.128 at an immediate offset from one per-row base register -- 0.29 loads per score, no index math.
+//   * ROW-PARALLEL warpgroups.  Each of the three softmax warpgroups owns whole 128-row query tiles (thread = query row, all chunks of
+//     the tile, online softmax with a lazily re-based maximum like attn_tc2.cu) -- no cross-group merge of partial results -- with two
+//     64-column S buffers and one O accumulator in TMEM (3 x 160 columns).  The warpgroup's own elected thread issues its MMAs
+//     (P.V of chunk n, then Q.K^T of chunk n + 2 into the buffer P.V just read: tcgen05.mma of one thread execute in order), so there
+//     are no issuer warps polling barriers next to the softmax warps.
+//   * the tile epilogue (O / l -> bf16) is deferred until the first chunk of the warpgroup's next tile has been exponentiated, when
+//     the last P.V of the old tile has long retired.
+//   * a tail tile of <= 32 rows lands in a different TMEM lane quadrant for every unit, so its single active warp loads the four SM
+//     sub-partitions evenly.
+// Warp roles: warps 0-11 softmax (warpgroup = warp / 4, lane quadrant = warp % 4), warp 12 TMA producer + TMEM allocation.
+// q arrives pre-scaled by head_dim^-0.5 * log2(e) (qkv GEMM epilogue); the table is multiplied by log2(e) when it is staged.
+#include "kernels.cuh"
+#include "attn_tc_ptx.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace lavt {
+
+constexpr int T3_HD = 32;
+constexpr int T3_WGS = 3;
+constexpr int T3_SM_THREADS = 128 * T3_WGS;
+constexpr int T3_TMA_WARP = 4 * T3_WGS;
+constexpr int T3_THREADS = T3_SM_THREADS + 32;
+constexpr int T3_CW = 64;                   // S columns per chunk = one frame: 7 runs of 7 keys padded to 8 + one all-padding run
+constexpr int T3_WG_COLS = 2 * T3_CW + T3_HD;
+constexpr int T3_SH = 16;                   // bias-table strides (floats) in shared memory: w' in [0,13), h in [0,13), d in [0,2Wd-1)
+constexpr int T3_SD = 13 * T3_SH;
+constexpr int T3_NQ = 4;                    // Q-tile ring slots
+constexpr int T3_CHUNK_BYTES = T3_CW * 64;  // one frame of K (or V) rows in shared memory
+constexpr float T3_LOG2E = 1.4426950408889634f;
+constexpr float T3_MASKV = -100.0f * T3_LOG2E;
+constexpr float T3_PSUM_LIMIT = 1048576.0f;  // 2^20
+
+#ifdef T3_WATCHDOG
+// debug build (-DT3_WATCHDOG): a wait that does not complete within ~0.5 s reports where it is stuck and traps
+__device__ __noinline__ void t3_stuck(int tag, uint32_t parity) {
+  printf("[tc3 stuck] block %d warp %d lane %d tag %d parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, tag, parity);
+  __trap();
+}
+__device__ __forceinline__ void t3_wait(uint64_t* bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 1000000000LL) t3_stuck(tag, parity);
+}
+#else
+__device__ __forceinline__ void t3_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait(bar, parity); }
+#endif
+
+struct AttnTc3Args {
+  int N, nch, ntiles;       // tokens per window, frames per window (= key chunks), 128-row query tiles
+  int nwin, units;
+  int tail_rows, rot;       // rot: the last tile has <= 32 rows and rotates through the lane quadrants
+  int CS;                   // floats between the four shifted table copies
+  int kv_bytes;             // K | V of one stage
+  int off_q, off_tab, off_bar;
+  int shifted;
+};
+
+struct T3Row {
+  const float* tb;          // this row's bias address of (frame 0, run h_j = 6); run h_j: + (6 - h_j) * SH, frame t_j: - t_j * SD
+  float m, l;
+  float mw[8];              // masked windows: w-axis mask of the 7 keys of a run (0 or -100 log2 e)
+  uint32_t dm, hm;          // masked windows: bit t_j / h_j set = that frame / run lies in another region than this row
+};
+
+// One piece = NR runs of 8 columns (7 live) of the chunk in TMEM at ts (fp32 scores), written back as bf16 pairs at tp.
+//   fb  : bias address of run h_j = 6 of this frame for this row;   HJ0: first run of the piece
+//   pdone : P columns of this chunk already written (slow path rescales them), o_acc: the O accumulator holds earlier chunks
+template <int NR, int HJ0, bool MASKED, bool FIRST>
+__device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* fb, T3Row& r, uint32_t rmask, uint32_t tp_chunk, int pdone,
+                                         bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
+  constexpr int W = 8 * NR;
+  uint32_t v[W];
+  if constexpr (NR == 4) {
+    tmem_ld_x32(ts, v);
+  } else {
+    static_assert(NR == 3, "pieces are 4 or 3 runs");
+    tmem_ld_x16(ts, v);
+    tmem_ld_x8(ts + 16, v + 16);
+  }
+  float x[W];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const float4 b0 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH);
+    const float4 b1 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH + 4);
+    x[8 * k + 0] = b0.x; x[8 * k + 1] = b0.y; x[8 * k + 2] = b0.z; x[8 * k + 3] = b0.w;
+    x[8 * k + 4] = b1.x; x[8 * k + 5] = b1.y; x[8 * k + 6] = b1.z; x[8 * k + 7] = b1.w;
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < W; j += 2) add2(x[j], x[j + 1], __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+  if constexpr (MASKED) {
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const bool rm = (rmask >> (HJ0 + k)) & 1u;
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) add2(x[8 * k + e], x[8 * k + e + 1], rm ? T3_MASKV : r.mw[e], rm ? T3_MASKV : r.mw[e + 1]);
+    }
+  }
+  if constexpr (FIRST) {
+    float m0 = -1e30f, m1 = -1e30f;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      m0 = max3(m0, x[8 * k + 0], x[8 * k + 1]);
+      m1 = max3(m1, x[8 * k + 2], x[8 * k + 3]);
+      m0 = max3(m0, x[8 * k + 4], x[8 * k + 5]);
+      m1 = fmaxf(m1, x[8 * k + 6]);
+    }
+    r.m = fmaxf(m0, m1);
+  }
+  float p[W];
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  {
+    const float nm = -r.m;
+#pragma unroll
+    for (int j = 0; j < W; j += 2) {
+      p[j] = x[j];
+      p[j + 1] = x[j + 1];
+      add2(p[j], p[j + 1], nm, nm);
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+#pragma unroll
+      for (int e = 0; e < 7; ++e) p[8 * k + e] = ex2_ftz(p[8 * k + e]);
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      add2(l0, l1, p[8 * k + 0], p[8 * k + 1]);
+      add2(l2, l3, p[8 * k + 2], p[8 * k + 3]);
+      add2(l0, l1, p[8 * k + 4], p[8 * k + 5]);
+      l2 += p[8 * k + 6];
+    }
+  }
+  float ps = (l0 + l1) + (l2 + l3);
+  if constexpr (!FIRST) {
+    if (__any_sync(0xffffffffu, !(ps <= T3_PSUM_LIMIT))) {
+      // ---- slow path (rare): some score of this piece exceeds the running maximum by ~2^14: re-base the row ----
+      float m0 = r.m, m1 = r.m;
+#pragma unroll
+      for (int k = 0; k < NR; ++k) {
+        m0 = max3(m0, x[8 * k + 0], x[8 * k + 1]);
+        m1 = max3(m1, x[8 * k + 2], x[8 * k + 3]);
+        m0 = max3(m0, x[8 * k + 4], x[8 * k + 5]);
+        m1 = fmaxf(m1, x[8 * k + 6]);
+      }
+      const float m2 = fmaxf(m0, m1);
+      const float f = ex2_ftz(r.m - m2);          // 1 for the lanes whose maximum did not move
+      r.l *= f;
+      tmem_st_wait();                              // the P columns stored by the previous piece are read back below
+      for (int pc = 0; pc < pdone; pc += 2) {      // P columns of this chunk that were already written (bf16 pairs)
+        uint32_t w2[2];
+        tmem_ld_x2(tp_chunk + pc, w2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float2 t = unpack_bf16x2(w2[j]);
+          w2[j] = pack_bf16x2(t.x * f, t.y * f);
+        }
+        tmem_st_x2(tp_chunk + pc, w2);
+      }
+      if (o_acc) {
+        t3_wait(pv_done, pvp, 1);                  // every P.V issued so far into this accumulator has retired
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_x32(tmem_o, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+        tmem_st_x32(tmem_o, o);
+      }
+      tmem_st_wait();
+      r.m = m2;
+      ps = 0.f;
+      const float nm = -m2;
+#pragma unroll
+      for (int k = 0; k < NR; ++k) {
+#pragma unroll
+        for (int e = 0; e < 7; ++e) {
+          p[8 * k + e] = ex2_ftz(x[8 * k + e] + nm);
+          ps += p[8 * k + e];
+        }
+      }
+    }
+  }
+  r.l += ps;
+  uint32_t pk[16];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    pk[4 * k + 0] = pack_bf16x2(p[8 * k + 0], p[8 * k + 1]);
+    pk[4 * k + 1] = pack_bf16x2(p[8 * k + 2], p[8 * k + 3]);
+    pk[4 * k + 2] = pack_bf16x2(p[8 * k + 4], p[8 * k + 5]);
+    pk[4 * k + 3] = pack_bf16x2(p[8 * k + 6], 0.f);
+  }
+  if constexpr (NR == 3) {
+#pragma unroll
+    for (int j = 12; j < 16; ++j) pk[j] = 0u;          // the all-padding run of the frame
+  }
+  tmem_st_x16(tp, pk);
+}
+
+// one chunk (= frame t_j) for this thread's row
+template <bool MASKED, bool FIRST>
+__device__ __forceinline__ void t3_chunk(uint32_t ts_buf, int tj, T3Row& r, bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
+  const float* fb = r.tb - tj * T3_SD;
+  uint32_t rmask = 0;
+  if constexpr (MASKED) rmask = ((r.dm >> tj) & 1u) ? 0x7fu : r.hm;
+  t3_piece<4, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
+  t3_piece<3, 4, MASKED, false>(ts_buf + 32, ts_buf + 16, fb, r, rmask, ts_buf, 16, o_acc, pv_done, pvp, tmem_o);
+}
+
+// registers are granted per 4 warps: 13 warps count as 16, i.e. 128 registers per thread (144 fails to launch)
+__global__ void __launch_bounds__(T3_THREADS, 1)
+window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
+                       const __grid_constant__ CUtensorMap tmQT, const AttnParams p, const AttnTc3Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* qring = smem + a.off_q;
+  float* tab = reinterpret_cast<float*>(smem + a.off_tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+  uint64_t* kv_full = bars;                       // [2]
+  uint64_t* kv_free = bars + 2;                   // [2]   one arrival per tile of the unit (its last P.V retired)
+  uint64_t* q_full = bars + 4;                    // [T3_NQ]
+  uint64_t* q_free = bars + 4 + T3_NQ;            // [T3_NQ]
+  uint64_t* s_full = bars + 4 + 2 * T3_NQ;        // [T3_WGS][2]
+  uint64_t* pv_done = s_full + 2 * T3_WGS;        // [T3_WGS]
+  uint64_t* o_full = pv_done + T3_WGS;            // [T3_WGS]  the last P.V of a tile of that warpgroup retired
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + T3_WGS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, nch = a.nch, ntiles = a.ntiles;
+  const WinGeom& wg = p.win;
+#ifdef T3_WATCHDOG
+  volatile int* prog = reinterpret_cast<volatile int*>(smem + a.off_bar + 200);     // progress code per warp
+  if (threadIdx.x < 13) prog[threadIdx.x] = 0;
+#define T3_PROG(code) do { if (lane == 0) prog[warp] = (code); } while (0)
+#else
+#define T3_PROG(code) do { } while (0)
+#endif
+
+  // contiguous unit range of this CTA; unit u = head * nwin + window (head-major: the bias table is restaged rarely)
+  const int u_begin = static_cast<int>(1LL * a.units * blockIdx.x / gridDim.x);
+  const int u_end = static_cast<int>(1LL * a.units * (blockIdx.x + 1) / gridDim.x);
+  const int nunits = u_end - u_begin;
+  const int T = nunits * ntiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmQ);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_free[i], ntiles);
+    }
+    for (int i = 0; i < T3_NQ; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
+    }
+    for (int i = 0; i < 2 * T3_WGS; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < T3_WGS; ++i) {
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == T3_TMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == T3_TMA_WARP) {
+#ifdef T3_WATCHDOG
+    if (lane == 1) {
+      const long long t0 = clock64();
+      for (;;) {
+        bool all = true;
+        for (int w = 0; w < 12; ++w) all = all && prog[w] == 1000;
+        if (all) break;
+        if (clock64() - t0 > 4000000000LL) {
+          printf("[tc3 watchdog] block %d progress:", blockIdx.x);
+          for (int w = 0; w < 13; ++w) printf(" %d", prog[w]);
+          printf("\n bars:");
+          for (int w = 0; w < 24; ++w) printf(" %d:%llx", w, *reinterpret_cast<volatile unsigned long long*>(&bars[w]));
+          printf("\n");
+          __trap();
+        }
+      }
+    }
+#endif
+    // =============================== TMA producer (one thread) ===============================
+    if (lane == 0) {
+      for (int lu = 0; lu < nunits; ++lu) {
+        const int u = u_begin + lu, s = lu & 1;
+        const int head = u / a.nwin, win = u - head * a.nwin;
+        if (lu >= 2) t3_wait(&kv_free[s], ((lu >> 1) - 1) & 1, 2);           // every P.V of the unit that used this stage retired
+        uint8_t* st = smem + s * a.kv_bytes;
+        mbar_expect_tx(&kv_full[s], 2u * nch * T3_CHUNK_BYTES);
+        tma_load_4d(st, &tmKV, &kv_full[s], p.C + head * T3_HD, 0, 0, win * nch);
+        tma_load_4d(st + nch * T3_CHUNK_BYTES, &tmKV, &kv_full[s], 2 * p.C + head * T3_HD, 0, 0, win * nch);
+        T3_PROG(5 + lu * 100);
+        for (int qt = 0; qt < ntiles; ++qt) {
+          const int tq = lu * ntiles + qt, slot = tq & (T3_NQ - 1);
+          if (tq >= T3_NQ) t3_wait(&q_free[slot], ((tq >> 2) - 1) & 1, 3);
+          uint8_t* qs = qring + slot * (128 * 64);
+          mbar_expect_tx(&q_full[slot], 128u * 64u);
+          if (a.rot && qt == ntiles - 1) {
+            // tail query rows, one copy per TMEM lane quadrant (rows past the tensor end are zero-filled by TMA)
+            for (int qd = 0; qd < 4; ++qd) tma_load_2d(qs + qd * 32 * 64, &tmQT, &q_full[slot], head * T3_HD, win * N + qt * 128);
+          } else {
+            tma_load_2d(qs, &tmQ, &q_full[slot], head * T3_HD, win * N + qt * 128);
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== softmax warpgroups ===============================
+    const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * T3_WG_COLS;
+    const uint32_t tmem_o = tlane + 2 * T3_CW;
+    const uint32_t tmem_wg = tmem_base + g * T3_WG_COLS;      // lane 0 addresses for the MMA issue
+    uint64_t* const my_pv = &pv_done[g];
+    const int nW = wg.nwd * wg.nwh * wg.nww;
+    const uint32_t idesc_qk = make_idesc_bf16_f32(128, T3_CW);
+    const uint32_t idesc_pv = make_idesc_bf16_f32(128, T3_HD) | (1u << 16);     // B (= V) is MN-major
+    const int head_first = u_begin / a.nwin;
+    const int nevents = nunits > 0 ? (u_end - 1) / a.nwin - head_first + 1 : 0;
+
+    // ---- Q K^T issue cursor of this warpgroup (used by its warp 0 only) ----
+    int qk_tq = g, qk_c = 0, qk_n = 0;
+    auto issue_qk = [&](bool blocking) -> bool {
+      if (qk_tq >= T) return false;
+      const int lu = qk_tq / ntiles, s = lu & 1, slot = qk_tq & (T3_NQ - 1);
+      if (qk_c == 0) {
+        const uint32_t pk = (lu >> 1) & 1, pq = (qk_tq >> 2) & 1;
+        if (blocking) {
+          t3_wait(&kv_full[s], pk, 4);
+          t3_wait(&q_full[slot], pq, 5);
+        } else if (!(mbar_test(&kv_full[s], pk) && mbar_test(&q_full[slot], pq))) {
+          return false;
+        }
+      }
+      tc_fence_after();
+      const uint64_t dq = make_sw64_desc(smem_u32(qring + slot * (128 * 64)));
+      const uint64_t dk = make_sw64_desc(smem_u32(smem + s * a.kv_bytes) + qk_c * T3_CHUNK_BYTES);
+      const uint32_t ts = tmem_wg + (qk_n & 1) * T3_CW;
+      if (elect_one_sync()) {
+        umma_bf16_ss(ts, dq, dk, idesc_qk, 0);
+        umma_bf16_ss(ts, dq + 2, dk + 2, idesc_qk, 1);
+        umma_commit(&s_full[g * 2 + (qk_n & 1)]);
+        if (qk_c == nch - 1) umma_commit(&q_free[slot]);
+      }
+      __syncwarp();
+      ++qk_n;
+      if (++qk_c == nch) {
+        qk_c = 0;
+        qk_tq += T3_WGS;
+      }
+      return true;
+    };
+
+    // ---- bias table of one head: four copies shifted by 0..3 floats, w axis flipped, strides (SD, SH, 1) ----
+    auto stage_table = [&](int head) {
+      named_bar(4, T3_SM_THREADS);                 // every warpgroup is done with the previous head's tiles
+      const float* src = p.table_t + static_cast<long long>(head) * p.L;
+      const int nd = 2 * wg.Wd - 1;
+      for (int i = threadIdx.x; i < 4 * a.CS; i += T3_SM_THREADS) {
+        const int k = i / a.CS, xx = i - k * a.CS;
+        const int nat = xx + k;
+        const int aa = nat / T3_SD, rem = nat - aa * T3_SD;
+        const int bb = rem / T3_SH, cc = rem - bb * T3_SH;
+        float val = 0.f;
+        if (aa < nd && bb < 13 && cc < 13) val = __ldg(src + (aa * 13 + bb) * 13 + (12 - cc)) * T3_LOG2E;
+        tab[i] = val;
+      }
+      named_bar(4, T3_SM_THREADS);
+    };
+
+    int ev_done = 0;
+    int n = 0;                                      // chunk items processed by this warpgroup
+    int ntile_done = 0;                             // tiles whose chunks were all processed
+    // deferred epilogue state (previous tile of this warpgroup)
+    bool have_prev = false, prev_store = false, prev_wvalid = false;
+    float prev_m = 0.f, prev_l = 1.f;
+    long long prev_row = 0;
+    int prev_head = 0;
+
+    auto epilogue = [&]() {
+      // the last P.V of that tile retired (its own barrier: pv_done's parity only tells the current phase from the one before, and at
+      // the end of the warpgroup's work nothing guarantees that P.V(n - 2) is already complete when this wait starts)
+      t3_wait(&o_full[g], static_cast<uint32_t>((ntile_done - 1) & 1), 6);
+      tc_fence_after();
+      if (prev_wvalid) {                        // warp-uniform: tcgen05.ld is .sync.aligned
+        uint32_t o[32];
+        tmem_ld_x32(tmem_o, o);
+        tmem_ld_wait();
+        if (prev_store) {
+          const float inv = 1.0f / prev_l;
+          if (p.lse) p.lse[prev_row * p.nH + prev_head] = prev_m + __log2f(prev_l);
+          __nv_bfloat16* dst = p.out + prev_row * p.C + prev_head * T3_HD;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t w8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              w8[j] = pack_bf16x2(__uint_as_float(o[h * 16 + 2 * j]) * inv, __uint_as_float(o[h * 16 + 2 * j + 1]) * inv);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + h * 16), "r"(w8[0]), "r"(w8[1]),
+                         "r"(w8[2]), "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                         : "memory");
+          }
+        }
+        __syncwarp();
+      }
+    };
+
+    T3_PROG(1);
+    if (q == 0) {
+      // never block before the first table barrier: the data of this warpgroup's first tile may depend on units that other
+      // warpgroups can only finish once everybody has joined that barrier (single-tile units: tile 2 reuses the K/V stage of tile 0)
+      if (issue_qk(false)) issue_qk(false);
+    }
+    T3_PROG(2);
+    for (int tq = g; tq < T; tq += T3_WGS) {
+      const int lu = tq / ntiles, qt = tq - lu * ntiles;
+      const int u = u_begin + lu, s = lu & 1;
+      const int head = u / a.nwin, win = u - head * a.nwin;
+      T3_PROG(10 + tq * 100);
+      while (ev_done <= head - head_first) {
+        stage_table(head_first + ev_done);
+        ++ev_done;
+      }
+      T3_PROG(11 + tq * 100);
+      // ---- this thread's query row ----
+      const bool rot = a.rot && qt == ntiles - 1;
+      // a rotated tail tile is replicated into all four lane quadrants (see the producer); the warp of quadrant lu % 4 processes it
+      const int i = qt * 128 + (rot ? lane : r);
+      const bool wvalid = rot ? (q == (lu & 3)) : (qt * 128 + q * 32) < N;  // warp-uniform: does this warp own live query rows?
+      const int ic = i < N ? i : N - 1;
+      const int ti = ic / 49, hi = (ic / 7) % 7, wi = ic % 7;
+      T3Row row;
+      {
+        const int k = (6 - wi) & 3;
+        const int A = (ti + wg.Wd - 1) * T3_SD + (hi + 6) * T3_SH + (6 - wi);
+        row.tb = tab + k * a.CS + (A - k) - 6 * T3_SH;
+        row.m = -1e30f;
+        row.l = 0.f;
+        row.dm = 0u;
+        row.hm = 0u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) row.mw[e] = 0.f;
+      }
+      bool need_mask = false;
+      if (a.shifted) {
+        const int wi_ = win % nW;
+        const int wc = wi_ % wg.nww, wb = (wi_ / wg.nww) % wg.nwh, wa = wi_ / (wg.nww * wg.nwh);
+        // class boundary along an axis (local position): only the last window of a shifted axis holds two regions
+        const int bd = (wg.sd && wa == wg.nwd - 1) ? wg.wd - wg.sd : 64;
+        const int bh = (wg.sh && wb == wg.nwh - 1) ? wg.wh - wg.sh : 64;
+        const int bw = (wg.sw && wc == wg.nww - 1) ? wg.ww - wg.sw : 64;
+        need_mask = (bd < 64) || (bh < 64) || (bw < 64);
+        if (need_mask) {
+          const bool cd = ti >= bd, chh = hi >= bh, cw = wi >= bw;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (((e >= bd) != cd)) row.dm |= 1u << e;
+            if (e < 7 && ((e >= bh) != chh)) row.hm |= 1u << e;
+            row.mw[e] = (e < 7 && ((e >= bw) != cw)) ? T3_MASKV : 0.f;
+          }
+        }
+      }
+
+      for (int c = 0; c < nch; ++c, ++n) {
+        const int buf = n & 1;
+        if (q == 0) {
+          while (qk_n <= n) issue_qk(true);                         // normally issued long ago (look-ahead below)
+        }
+        T3_PROG(20 + c + tq * 100);
+        t3_wait(&s_full[g * 2 + buf], (n >> 1) & 1, 7);
+        tc_fence_after();
+        T3_PROG(30 + c + tq * 100);
+        if (wvalid) {
+          const uint32_t ts_buf = tlane + buf * T3_CW;
+          const uint32_t pvp = static_cast<uint32_t>((n - 1) & 1);
+          if (need_mask) {
+            if (c == 0) t3_chunk<true, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
+            else t3_chunk<true, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
+          } else {
+            if (c == 0) t3_chunk<false, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
+            else t3_chunk<false, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
+          }
+        }
+        T3_PROG(40 + c + tq * 100);
+        if (c == 0 && have_prev) epilogue();                       // previous tile of this warpgroup: its P.V retired long ago
+        tmem_st_wait();
+        tc_fence_before();
+        T3_PROG(50 + c + tq * 100);
+        named_bar(1 + g, 128);
+        T3_PROG(60 + c + tq * 100);
+        if (q == 0) {
+          // P.V of this chunk, then look ahead: Q K^T of item n + 2 goes into the S buffer the P.V reads (in-order execution)
+          tc_fence_after();
+          const uint64_t dv = make_sw64_desc(smem_u32(smem + s * a.kv_bytes) + (nch + c) * T3_CHUNK_BYTES);
+          const uint32_t tp = tmem_wg + buf * T3_CW;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int ks = 0; ks < T3_CW / 16; ++ks)               // 16 keys per step: 8 packed P columns, 16 V rows (1 KB)
+              umma_bf16_ts(tmem_wg + 2 * T3_CW, tp + 8 * ks, dv + 64 * ks, idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(my_pv);
+            if (c == nch - 1) {
+              umma_commit(&o_full[g]);
+              umma_commit(&kv_free[s]);
+            }
+          }
+          __syncwarp();
+          while (qk_n < n + 3 && issue_qk(false)) {
+          }
+        }
+      }
+      have_prev = true;
+      ++ntile_done;
+      prev_store = wvalid && i < N;
+      prev_wvalid = wvalid;
+      prev_m = row.m;
+      prev_l = row.l;
+      prev_row = static_cast<long long>(win) * N + ic;
+      prev_head = head;
+    }
+    T3_PROG(900);
+    if (have_prev) epilogue();
+    T3_PROG(901);
+    while (ev_done < nevents) {
+      stage_table(head_first + ev_done);
+      ++ev_done;
+    }
+    T3_PROG(1000);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T3_TMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static bool t3_plan(const AttnParams& p, AttnTc3Args& a, int& smem_out) {
+  const WinGeom& g = p.win;
+  if (g.Wh != 7 || g.Ww != 7 || g.wh != 7 || g.ww != 7) return false;
+  if (g.wd < 1 || g.wd > 8 || g.Wd < g.wd || g.Wd > 8 || g.N != 49 * g.wd) return false;
+  if ((3 * p.C * 2) % 16 != 0) return false;
+  a.N = g.N;
+  a.nch = g.wd;
+  a.ntiles = (g.N + 127) / 128;
+  a.tail_rows = g.N - (a.ntiles - 1) * 128;
+  a.rot = (a.ntiles >= 2 && a.tail_rows <= 32) ? 1 : 0;
+  a.shifted = (g.sd | g.sh | g.sw) != 0;
+  const int L2 = (2 * g.Wd - 1) * T3_SD + 16;
+  a.CS = L2 + ((8 - L2 % 32) + 32) % 32;          // CS = 8 (mod 32): the four copies start 2 sixteen-byte bank groups apart
+  a.kv_bytes = 2 * a.nch * T3_CHUNK_BYTES;
+  int off = 2 * a.kv_bytes;
+  a.off_q = off;          off += T3_NQ * 128 * 64;
+  a.off_tab = off;        off += ((4 * a.CS * 4 + 127) / 128) * 128;
+  a.off_bar = off;        off += 256;
+  smem_out = off + 1024;
+  return smem_out <= 227 * 1024;
+}
+
+bool window_attn_tc3_supported(const AttnParams& p) {
+  AttnTc3Args a;
+  int smem = 0;
+  return t3_plan(p, a, smem);
+}
+
+int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
+  const WinGeom& g = p.win;
+  AttnTc3Args a;
+  int smem = 0;
+  LAVT_REQUIRE(t3_plan(p, a, smem), "attention(tc3): unsupported window (N=%d, L=%d)", g.N, p.L);
+  const long long nwin = 1LL * g.B * g.nwd * g.nwh * g.nww;
+  LAVT_REQUIRE(nwin * p.nH < (1LL << 30), "attention(tc3): too many units");
+  a.nwin = static_cast<int>(nwin);
+  a.units = static_cast<int>(nwin * p.nH);
+
+  CUtensorMap tm_kv, tm_q, tm_tail;
+  {
+    // K / V: (channel, w, h, frame) with a box one larger than the 7 x 7 window: TMA zero-fills w = 7 and h = 7
+    const uint64_t rowb = static_cast<uint64_t>(3 * p.C) * 2;
+    uint64_t dims4[4] = {static_cast<uint64_t>(3 * p.C), 7, 7, static_cast<uint64_t>(nwin * a.nch)};
+    uint64_t str4[3] = {rowb, 7 * rowb, 49 * rowb};
+    uint32_t box4[4] = {T3_HD, 8, 8, static_cast<uint32_t>(a.nch)};
+    int rc = make_tmap_bf16(&tm_kv, p.qkv, 4, dims4, str4, box4, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    uint64_t dims[2] = {static_cast<uint64_t>(3 * p.C), static_cast<uint64_t>(nwin * g.N)};
+    uint64_t strides[1] = {rowb};
+    uint32_t box_q[2] = {T3_HD, 128};
+    rc = make_tmap_bf16(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    uint32_t box_t[2] = {T3_HD, 32};
+    rc = make_tmap_bf16(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  const int grid = a.units < sms ? a.units : sms;
+  static int configured = 0;
+  if (smem > configured) {
+    LAVT_CUDA(cudaFuncSetAttribute(window_attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  window_attn_tc3_kernel<<<grid, T3_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
+  LAVT_LAUNCH_CHECK("window_attn_tc3_kernel");
+  return LAVT_OK;
+}
+
+}  // namespace lavt

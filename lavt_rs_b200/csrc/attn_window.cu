@@ -373,10 +373,11 @@ int attn_impl_setting(int set) {
   if (impl < 0) {
     const char* e = getenv("LAVT_ATTN_IMPL");
     // default: auto (tcgen05 kernels where they apply); "mma" = mma.sync only, "tc1" / "tc2" = prefer the first / second generation
-    impl = !e ? 0 : e[0] == 'm' ? 1 : (e[0] == 't' && e[1] == 'c' && e[2] == '1') ? 2 : (e[0] == 't' && e[1] == 'c' && e[2] == '2') ? 3 : 0;
+    impl = !e ? 0 : e[0] == 'm' ? 1 : (e[0] == 't' && e[1] == 'c' && e[2] == '1') ? 2 : (e[0] == 't' && e[1] == 'c' && e[2] == '2') ? 3 :
+           (e[0] == 't' && e[1] == 'c' && e[2] == '3') ? 4 : 0;
   }
   const int prev = impl;
-  if (set >= 0) impl = set <= 3 ? set : 0;
+  if (set >= 0) impl = set <= 4 ? set : 0;
   return prev;
 }
 
@@ -398,6 +399,8 @@ int window_attn_dispatch(const AttnParams& p, cudaStream_t st) {
       // per 8-clip step), the key-chunked one-pass kernel (attn_tc2.cu) for everything larger (8 x 12 x 12: 14.9 ms vs 21.8 ms for the
       // mma.sync kernels); "tc2" forces the chunked kernel everywhere
       if (impl == 3 && window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
+      // 7 x 7 windows: the row-parallel kernel with vector bias loads (attn_tc3.cu); "tc1" / "tc2" keep the older generations for A/B runs
+      if ((impl == 0 || impl == 4) && window_attn_tc3_supported(p)) return window_attn_tc3_dispatch(p, st);
       if (window_attn_tc_supported(p)) return window_attn_tc_dispatch(p, st);
       if (window_attn_tc2_supported(p)) return window_attn_tc2_dispatch(p, st);
     }

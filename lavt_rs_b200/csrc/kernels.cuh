@@ -40,12 +40,15 @@ struct AttnParams {
 };
 int window_attn_dispatch(const AttnParams& p, cudaStream_t st);
 // tcgen05 / TMEM variant (attn_tc.cu): windows of up to 400 tokens
-int attn_impl_setting(int set);   // set < 0: query only; returns the previous value (0 = auto, 1 = mma.sync only, 2 = prefer attn_tc.cu, 3 = attn_tc2.cu)
+int attn_impl_setting(int set);   // set < 0: query only; returns the previous value (0 = auto, 1 = mma.sync only, 2 = prefer attn_tc.cu, 3 = attn_tc2.cu, 4 = attn_tc3.cu)
 bool window_attn_tc_supported(const AttnParams& p);
 int window_attn_tc_dispatch(const AttnParams& p, cudaStream_t st);
 // second generation (attn_tc2.cu): key-chunked, one-pass softmax, windows of up to 1152 tokens
 bool window_attn_tc2_supported(const AttnParams& p);
 int window_attn_tc2_dispatch(const AttnParams& p, cudaStream_t st);
+// third generation (attn_tc3.cu): 7 x 7 windows, row-parallel warpgroups, run-padded key layout with vector bias loads
+bool window_attn_tc3_supported(const AttnParams& p);
+int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st);
 
 // ---- backward pass (training step) ----
 struct AttnBwdParams {

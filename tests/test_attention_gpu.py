@@ -38,8 +38,9 @@ CASES = [  # (B, D, H, W), window, shifted, heads
 ]
 
 
-# auto / tc2 = one-pass chunked tcgen05 kernel (every N); tc1 = two-pass tcgen05 kernel where it applies (N <= 400); mma = mma.sync
-@pytest.mark.parametrize("impl", ["auto", "tc1", "mma"])
+# auto = attn_tc3.cu for 7 x 7 windows (row-parallel warpgroups, run-padded keys), else tc1 / tc2; tc2 = one-pass chunked tcgen05 kernel
+# (every N); tc1 = two-pass tcgen05 kernel where it applies (N <= 400); mma = mma.sync
+@pytest.mark.parametrize("impl", ["auto", "tc1", "tc2", "mma"])
 @pytest.mark.parametrize("dims,window,shifted,nH", CASES)
 def test_window_attention_matches_torch(dims, window, shifted, nH, impl):
     from lavt_rs_b200 import _cabi as K
@@ -73,7 +74,8 @@ def test_window_attention_matches_torch(dims, window, shifted, nH, impl):
 @pytest.mark.parametrize("dims,window,nH", [((1, 8, 14, 14), (8, 7, 7), 4), ((1, 8, 24, 24), (8, 12, 12), 4), ((1, 4, 24, 24), (8, 7, 7), 4),
                                             ((1, 8, 10, 10), (8, 12, 12), 4)])
 @pytest.mark.parametrize("pattern", ["ramp", "spike", "late_rows"])
-def test_one_pass_softmax_slow_path(dims, window, nH, pattern):
+@pytest.mark.parametrize("impl", ["tc2", "tc3"])
+def test_one_pass_softmax_slow_path(dims, window, nH, pattern, impl):
     """The one-pass kernel keeps the running maximum of the FIRST piece of a row and only re-bases when a later piece overflows
     sum 2^(s - m) <= 2^20.  These inputs force that slow path: scores that grow by hundreds of units along the key axis ('ramp'),
     a single huge key in the last chunk ('spike': rescale of the P columns already written AND of the O accumulator in TMEM), and
@@ -103,7 +105,7 @@ def test_one_pass_softmax_slow_path(dims, window, nH, pattern):
     table = torch.randn(L, nH, device="cuda", generator=g)
     out = torch.empty(rows, C, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(rows, nH, device="cuda", dtype=torch.float32)
-    prev = K.set_attention_impl("tc2")
+    prev = K.set_attention_impl(impl)       # tc3 falls through to the other generations for windows that are not 7 x 7
     try:
         K.window_attention(qkv, table.t().contiguous(), geom, out, lse=lse)
         torch.cuda.synchronize()
