@@ -14,14 +14,16 @@
 //     bias of a run is TWO LDS.128 at an immediate offset from one per-row base register -- 0.29 loads per score, no index math.
 //   * ROW-PARALLEL warpgroups.  Each of the three softmax warpgroups owns whole 128-row query tiles (thread = query row, all chunks of
 //     the tile, online softmax with a lazily re-based maximum like attn_tc2.cu) -- no cross-group merge of partial results -- with two
-//     64-column S buffers and one O accumulator in TMEM (3 x 160 columns).  The warpgroup's own elected thread issues its MMAs
-//     (P.V of chunk n, then Q.K^T of chunk n + 2 into the buffer P.V just read: tcgen05.mma of one thread execute in order), so there
-//     are no issuer warps polling barriers next to the softmax warps.
+//     64-column S buffers and one O accumulator in TMEM (3 x 160 columns).  One issuer warp per warpgroup: P.V of chunk n, then
+//     Q.K^T of chunk n + 2 into the buffer that P.V just read (tcgen05.mma of one thread execute in order).
 //   * the tile epilogue (O / l -> bf16) is deferred until the first chunk of the warpgroup's next tile has been exponentiated, when
 //     the last P.V of the old tile has long retired.
 //   * a tail tile of <= 32 rows lands in a different TMEM lane quadrant for every unit, so its single active warp loads the four SM
 //     sub-partitions evenly.
-// Warp roles: warps 0-11 softmax (warpgroup = warp / 4, lane quadrant = warp % 4), warp 12 TMA producer + TMEM allocation.
+// Warp roles: warps 0-11 softmax (warpgroup g = warp / 4, lane quadrant q = warp % 4), warps 12-14 MMA issuers of warpgroup 0 / 1 / 2
+// (the softmax warps only arrive on an mbarrier when their P rows are written and never wait for the issue: measured with the
+// in-kernel timeline, issuing from a softmax warp put ~900 cycles per chunk on that warp's critical path), warp 15 TMA producer + TMEM
+// allocation.
 // q arrives pre-scaled by head_dim^-0.5 * log2(e) (qkv GEMM epilogue); the table is multiplied by log2(e) when it is staged.
 #include "kernels.cuh"
 #include "attn_tc_ptx.cuh"
@@ -34,8 +36,8 @@ namespace lavt {
 constexpr int T3_HD = 32;
 constexpr int T3_WGS = 3;
 constexpr int T3_SM_THREADS = 128 * T3_WGS;
-constexpr int T3_TMA_WARP = 4 * T3_WGS;
-constexpr int T3_THREADS = T3_SM_THREADS + 32;
+constexpr int T3_TMA_WARP = 4 * T3_WGS + 3;   // warp 15: the SM sub-partition (warp % 4 = 3) that hosts no MMA-issuing softmax warp
+constexpr int T3_THREADS = 512;               // warps 12-14 only run to the final barrier (registers are granted per 4 warps anyway)
 constexpr int T3_CW = 64;                   // S columns per chunk = one frame: 7 runs of 7 keys padded to 8 + one all-padding run
 constexpr int T3_WG_COLS = 2 * T3_CW + T3_HD;
 constexpr int T3_SH = 16;                   // bias-table strides (floats) in shared memory: w' in [0,13), h in [0,13), d in [0,2Wd-1)
@@ -69,7 +71,9 @@ struct AttnTc3Args {
   int kv_bytes;             // K | V of one stage
   int off_q, off_tab, off_bar;
   int shifted;
+  long long* trace;         // -DT3_TRACE builds: clock64 stamps of CTA 0, [16 warps][8 events][T3_TRACE_ITEMS]
 };
+constexpr int T3_TRACE_ITEMS = 96;
 
 struct T3Row {
   const float* tb;          // this row's bias address of (frame 0, run h_j = 6); run h_j: + (6 - h_j) * SH, frame t_j: - t_j * SD
@@ -239,17 +243,23 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint64_t* s_full = bars + 4 + 2 * T3_NQ;        // [T3_WGS][2]
   uint64_t* pv_done = s_full + 2 * T3_WGS;        // [T3_WGS]
   uint64_t* o_full = pv_done + T3_WGS;            // [T3_WGS]  the last P.V of a tile of that warpgroup retired
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + T3_WGS);
+  uint64_t* p_ready = o_full + T3_WGS;            // [T3_WGS][2] the four warps of the warpgroup wrote their P rows of that S buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p_ready + 2 * T3_WGS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, nch = a.nch, ntiles = a.ntiles;
   const WinGeom& wg = p.win;
 #ifdef T3_WATCHDOG
-  volatile int* prog = reinterpret_cast<volatile int*>(smem + a.off_bar + 200);     // progress code per warp
-  if (threadIdx.x < 13) prog[threadIdx.x] = 0;
+  volatile int* prog = reinterpret_cast<volatile int*>(smem + a.off_bar + 256);     // progress code per warp
+  if (threadIdx.x < 16) prog[threadIdx.x] = 0;
 #define T3_PROG(code) do { if (lane == 0) prog[warp] = (code); } while (0)
 #else
 #define T3_PROG(code) do { } while (0)
+#endif
+#ifdef T3_TRACE
+#define T3_STAMP(ev, item) do { if (blockIdx.x == 0 && lane == 0 && a.trace && (item) < T3_TRACE_ITEMS) a.trace[(warp * 8 + (ev)) * T3_TRACE_ITEMS + (item)] = clock64(); } while (0)
+#else
+#define T3_STAMP(ev, item) do { } while (0)
 #endif
 
   // contiguous unit range of this CTA; unit u = head * nwin + window (head-major: the bias table is restaged rarely)
@@ -269,7 +279,10 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       mbar_init(&q_full[i], 1);
       mbar_init(&q_free[i], 1);
     }
-    for (int i = 0; i < 2 * T3_WGS; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2 * T3_WGS; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+    }
     for (int i = 0; i < T3_WGS; ++i) {
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
@@ -288,13 +301,13 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       const long long t0 = clock64();
       for (;;) {
         bool all = true;
-        for (int w = 0; w < 12; ++w) all = all && prog[w] == 1000;
+        for (int w = 0; w < 4 * T3_WGS; ++w) all = all && prog[w] == 1000;
         if (all) break;
         if (clock64() - t0 > 4000000000LL) {
           printf("[tc3 watchdog] block %d progress:", blockIdx.x);
-          for (int w = 0; w < 13; ++w) printf(" %d", prog[w]);
+          for (int w = 0; w < 16; ++w) printf(" %d", prog[w]);
           printf("\n bars:");
-          for (int w = 0; w < 24; ++w) printf(" %d:%llx", w, *reinterpret_cast<volatile unsigned long long*>(&bars[w]));
+          for (int w = 0; w < 30; ++w) printf(" %d:%llx", w, *reinterpret_cast<volatile unsigned long long*>(&bars[w]));
           printf("\n");
           __trap();
         }
@@ -326,36 +339,34 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         }
       }
     }
-  } else {
-    // =============================== softmax warpgroups ===============================
-    const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
-    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * T3_WG_COLS;
-    const uint32_t tmem_o = tlane + 2 * T3_CW;
-    const uint32_t tmem_wg = tmem_base + g * T3_WG_COLS;      // lane 0 addresses for the MMA issue
-    uint64_t* const my_pv = &pv_done[g];
-    const int nW = wg.nwd * wg.nwh * wg.nww;
+  } else if (warp >= 4 * T3_WGS) {
+    // =============================== MMA issuer of warpgroup g (warp-uniform loop, one elected lane issues) ===============================
+    // item n = (tile, chunk) of this warpgroup:  ... P(n) announced -> P.V(n) -> Q K^T(n + 2) into the S buffer that P.V(n) reads
+    // (tcgen05.mma of one thread execute in issue order) ...; Q K^T(n + 1) already sits in the other buffer.
+    const int g = warp - 4 * T3_WGS;
+    const uint32_t tmem_wg = tmem_base + g * T3_WG_COLS;
     const uint32_t idesc_qk = make_idesc_bf16_f32(128, T3_CW);
     const uint32_t idesc_pv = make_idesc_bf16_f32(128, T3_HD) | (1u << 16);     // B (= V) is MN-major
-    const int head_first = u_begin / a.nwin;
-    const int nevents = nunits > 0 ? (u_end - 1) / a.nwin - head_first + 1 : 0;
-
-    // ---- Q K^T issue cursor of this warpgroup (used by its warp 0 only) ----
-    int qk_tq = g, qk_c = 0, qk_n = 0;
+    const uint32_t kv_base = smem_u32(smem), q_base = smem_u32(qring);
+    int qk_tq = g, qk_lu = g / ntiles, qk_c = 0, qk_n = 0;
+    int qk_qt = g - qk_lu * ntiles;
+    // Look-ahead issues never block: the K/V stage of a unit two ahead is only released by P.V's this warp has not issued yet
+    // (units of one or two tiles); the issue for the item that is due next may block -- it only depends on earlier tiles.
     auto issue_qk = [&](bool blocking) -> bool {
       if (qk_tq >= T) return false;
-      const int lu = qk_tq / ntiles, s = lu & 1, slot = qk_tq & (T3_NQ - 1);
+      const int s = qk_lu & 1, slot = qk_tq & (T3_NQ - 1);
       if (qk_c == 0) {
-        const uint32_t pk = (lu >> 1) & 1, pq = (qk_tq >> 2) & 1;
+        const uint32_t pk = (qk_lu >> 1) & 1, pq = (qk_tq >> 2) & 1;
         if (blocking) {
           t3_wait(&kv_full[s], pk, 4);
           t3_wait(&q_full[slot], pq, 5);
         } else if (!(mbar_test(&kv_full[s], pk) && mbar_test(&q_full[slot], pq))) {
           return false;
         }
+        tc_fence_after();
       }
-      tc_fence_after();
-      const uint64_t dq = make_sw64_desc(smem_u32(qring + slot * (128 * 64)));
-      const uint64_t dk = make_sw64_desc(smem_u32(smem + s * a.kv_bytes) + qk_c * T3_CHUNK_BYTES);
+      const uint64_t dq = make_sw64_desc(q_base + slot * (128 * 64));
+      const uint64_t dk = make_sw64_desc(kv_base + s * a.kv_bytes + qk_c * T3_CHUNK_BYTES);
       const uint32_t ts = tmem_wg + (qk_n & 1) * T3_CW;
       if (elect_one_sync()) {
         umma_bf16_ss(ts, dq, dk, idesc_qk, 0);
@@ -368,9 +379,58 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       if (++qk_c == nch) {
         qk_c = 0;
         qk_tq += T3_WGS;
+        qk_qt += T3_WGS;
+        while (qk_qt >= ntiles) {
+          qk_qt -= ntiles;
+          ++qk_lu;
+        }
       }
       return true;
     };
+    if (issue_qk(false)) issue_qk(false);
+    int n = 0, lu = g / ntiles, qt = g - lu * ntiles;
+    for (int tq = g; tq < T; tq += T3_WGS) {
+      const int s = lu & 1;
+      for (int c = 0; c < nch; ++c, ++n) {
+        const int buf = n & 1;
+        while (qk_n <= n) issue_qk(true);                         // normally issued long ago
+        T3_STAMP(3, n);
+        t3_wait(&p_ready[g * 2 + buf], (n >> 1) & 1, 8);           // the four softmax warps wrote their P rows of this chunk
+        T3_STAMP(4, n);
+        tc_fence_after();
+        const uint64_t dv = make_sw64_desc(kv_base + s * a.kv_bytes + (nch + c) * T3_CHUNK_BYTES);
+        const uint32_t tp = tmem_wg + buf * T3_CW;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int ks = 0; ks < T3_CW / 16; ++ks)               // 16 keys per step: 8 packed P columns, 16 V rows (1 KB)
+            umma_bf16_ts(tmem_wg + 2 * T3_CW, tp + 8 * ks, dv + 64 * ks, idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&pv_done[g]);
+          if (c == nch - 1) {
+            umma_commit(&o_full[g]);
+            umma_commit(&kv_free[s]);
+          }
+        }
+        __syncwarp();
+        T3_STAMP(5, n);
+        while (qk_n < n + 3 && issue_qk(false)) {
+        }
+        T3_STAMP(6, n);
+      }
+      qt += T3_WGS;
+      while (qt >= ntiles) {
+        qt -= ntiles;
+        ++lu;
+      }
+    }
+  } else {
+    // =============================== softmax warpgroups ===============================
+    const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * T3_WG_COLS;
+    const uint32_t tmem_o = tlane + 2 * T3_CW;
+    uint64_t* const my_pv = &pv_done[g];
+    const int nW = wg.nwd * wg.nwh * wg.nww;
+    const int head_first = u_begin / a.nwin;
+    const int nevents = nunits > 0 ? (u_end - 1) / a.nwin - head_first + 1 : 0;
 
     // ---- bias table of one head: four copies shifted by 0..3 floats, w axis flipped, strides (SD, SH, 1) ----
     auto stage_table = [&](int head) {
@@ -427,15 +487,10 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     };
 
     T3_PROG(1);
-    if (q == 0) {
-      // never block before the first table barrier: the data of this warpgroup's first tile may depend on units that other
-      // warpgroups can only finish once everybody has joined that barrier (single-tile units: tile 2 reuses the K/V stage of tile 0)
-      if (issue_qk(false)) issue_qk(false);
-    }
     T3_PROG(2);
     for (int tq = g; tq < T; tq += T3_WGS) {
       const int lu = tq / ntiles, qt = tq - lu * ntiles;
-      const int u = u_begin + lu, s = lu & 1;
+      const int u = u_begin + lu;
       const int head = u / a.nwin, win = u - head * a.nwin;
       T3_PROG(10 + tq * 100);
       while (ev_done <= head - head_first) {
@@ -484,12 +539,11 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 
       for (int c = 0; c < nch; ++c, ++n) {
         const int buf = n & 1;
-        if (q == 0) {
-          while (qk_n <= n) issue_qk(true);                         // normally issued long ago (look-ahead below)
-        }
         T3_PROG(20 + c + tq * 100);
+        T3_STAMP(0, n);
         t3_wait(&s_full[g * 2 + buf], (n >> 1) & 1, 7);
         tc_fence_after();
+        T3_STAMP(1, n);
         T3_PROG(30 + c + tq * 100);
         if (wvalid) {
           const uint32_t ts_buf = tlane + buf * T3_CW;
@@ -503,31 +557,15 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           }
         }
         T3_PROG(40 + c + tq * 100);
+        T3_STAMP(2, n);
         if (c == 0 && have_prev) epilogue();                       // previous tile of this warpgroup: its P.V retired long ago
         tmem_st_wait();
         tc_fence_before();
+        __syncwarp();
+        T3_STAMP(3, n);
         T3_PROG(50 + c + tq * 100);
-        named_bar(1 + g, 128);
-        T3_PROG(60 + c + tq * 100);
-        if (q == 0) {
-          // P.V of this chunk, then look ahead: Q K^T of item n + 2 goes into the S buffer the P.V reads (in-order execution)
-          tc_fence_after();
-          const uint64_t dv = make_sw64_desc(smem_u32(smem + s * a.kv_bytes) + (nch + c) * T3_CHUNK_BYTES);
-          const uint32_t tp = tmem_wg + buf * T3_CW;
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int ks = 0; ks < T3_CW / 16; ++ks)               // 16 keys per step: 8 packed P columns, 16 V rows (1 KB)
-              umma_bf16_ts(tmem_wg + 2 * T3_CW, tp + 8 * ks, dv + 64 * ks, idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(my_pv);
-            if (c == nch - 1) {
-              umma_commit(&o_full[g]);
-              umma_commit(&kv_free[s]);
-            }
-          }
-          __syncwarp();
-          while (qk_n < n + 3 && issue_qk(false)) {
-          }
-        }
+        // announce this warp's P rows to the warpgroup's MMA-issuing warp and move on to the next chunk
+        if (lane == 0) mbar_arrive(&p_ready[g * 2 + buf]);
       }
       have_prev = true;
       ++ntile_done;
@@ -576,7 +614,7 @@ static bool t3_plan(const AttnParams& p, AttnTc3Args& a, int& smem_out) {
   int off = 2 * a.kv_bytes;
   a.off_q = off;          off += T3_NQ * 128 * 64;
   a.off_tab = off;        off += ((4 * a.CS * 4 + 127) / 128) * 128;
-  a.off_bar = off;        off += 256;
+  a.off_bar = off;        off += 384;
   smem_out = off + 1024;
   return smem_out <= 227 * 1024;
 }
@@ -627,8 +665,33 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
     LAVT_CUDA(cudaFuncSetAttribute(window_attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
+  a.trace = nullptr;
+#ifdef T3_TRACE
+  const char* trace_path = getenv("LAVT_ATTN_TRACE");
+  const size_t trace_n = 16 * 8 * T3_TRACE_ITEMS;
+  if (trace_path) {
+    LAVT_CUDA(cudaMalloc(&a.trace, trace_n * sizeof(long long)));
+    LAVT_CUDA(cudaMemsetAsync(a.trace, 0, trace_n * sizeof(long long), st));
+  }
+#endif
   window_attn_tc3_kernel<<<grid, T3_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
   LAVT_LAUNCH_CHECK("window_attn_tc3_kernel");
+#ifdef T3_TRACE
+  if (a.trace) {
+    // debug only: synchronous dump of CTA 0's event clocks, one line per (warp, event)
+    static long long host[16 * 8 * T3_TRACE_ITEMS];
+    LAVT_CUDA(cudaStreamSynchronize(st));
+    LAVT_CUDA(cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(a.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int e = 0; e < 16 * 8; ++e) {
+        for (int t = 0; t < T3_TRACE_ITEMS; ++t) fprintf(f, "%lld ", host[e * T3_TRACE_ITEMS + t]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#endif
   return LAVT_OK;
 }
 
