@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "liblavt_b200.so")
+LIB_PATH = os.environ.get("LAVT_LIB_PATH") or os.path.join(_PKG, "_lib", "liblavt_b200.so")   # LAVT_LIB_PATH: A/B runs of debug builds
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 

@@ -90,18 +90,31 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
                                          bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
   constexpr int W = 8 * NR;
   uint32_t v[W];
+#ifdef T3_X_NOLD
+#pragma unroll
+  for (int j = 0; j < W; ++j) v[j] = ts + j;
+#else
   if constexpr (NR == 4) {
     tmem_ld_x32(ts, v);
-  } else {
-    static_assert(NR == 3, "pieces are 4 or 3 runs");
+  } else if constexpr (NR == 3) {
     tmem_ld_x16(ts, v);
     tmem_ld_x8(ts + 16, v + 16);
+  } else {
+    static_assert(NR == 7, "pieces are 7, 4 or 3 runs");
+    tmem_ld_x32(ts, v);
+    tmem_ld_x16(ts + 32, v + 32);
+    tmem_ld_x8(ts + 48, v + 48);
   }
+#endif
   float x[W];
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
+#ifdef T3_X_NOBIAS
+    const float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+#else
     const float4 b0 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH);
     const float4 b1 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH + 4);
+#endif
     x[8 * k + 0] = b0.x; x[8 * k + 1] = b0.y; x[8 * k + 2] = b0.z; x[8 * k + 3] = b0.w;
     x[8 * k + 4] = b1.x; x[8 * k + 5] = b1.y; x[8 * k + 6] = b1.z; x[8 * k + 7] = b1.w;
   }
@@ -137,11 +150,13 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
       p[j + 1] = x[j + 1];
       add2(p[j], p[j + 1], nm, nm);
     }
+#ifndef T3_X_NOMUFU
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
 #pragma unroll
       for (int e = 0; e < 7; ++e) p[8 * k + e] = ex2_ftz(p[8 * k + e]);
     }
+#endif
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
       add2(l0, l1, p[8 * k + 0], p[8 * k + 1]);
@@ -202,7 +217,7 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
     }
   }
   r.l += ps;
-  uint32_t pk[16];
+  uint32_t pk[NR == 7 ? 32 : 16];
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
     pk[4 * k + 0] = pack_bf16x2(p[8 * k + 0], p[8 * k + 1]);
@@ -214,7 +229,18 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
 #pragma unroll
     for (int j = 12; j < 16; ++j) pk[j] = 0u;          // the all-padding run of the frame
   }
-  tmem_st_x16(tp, pk);
+  if constexpr (NR == 7) {
+#pragma unroll
+    for (int j = 28; j < 32; ++j) pk[j] = 0u;
+  }
+#ifdef T3_X_NOST
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc ^= pk[j];
+  if (acc == 0x12345678u) tmem_st_x16(tp, pk);
+#else
+  if constexpr (NR == 7) tmem_st_x32(tp, pk); else tmem_st_x16(tp, pk);
+#endif
 }
 
 // one chunk (= frame t_j) for this thread's row
@@ -223,11 +249,15 @@ __device__ __forceinline__ void t3_chunk(uint32_t ts_buf, int tj, T3Row& r, bool
   const float* fb = r.tb - tj * T3_SD;
   uint32_t rmask = 0;
   if constexpr (MASKED) rmask = ((r.dm >> tj) & 1u) ? 0x7fu : r.hm;
+#ifndef T3_ONE_PIECE
   t3_piece<4, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
   t3_piece<3, 4, MASKED, false>(ts_buf + 32, ts_buf + 16, fb, r, rmask, ts_buf, 16, o_acc, pv_done, pvp, tmem_o);
+#else
+  // the whole frame as one piece: one TMEM load / wait / store per chunk and one large basic block for the instruction scheduler
+  t3_piece<7, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
+#endif
 }
 
-// registers are granted per 4 warps: 13 warps count as 16, i.e. 128 registers per thread (144 fails to launch)
 __global__ void __launch_bounds__(T3_THREADS, 1)
 window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmQT, const AttnParams p, const AttnTc3Args a) {
@@ -290,11 +320,19 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     fence_mbar_init();
   }
   if (warp == T3_TMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  for (int i = threadIdx.x; i < 4 * a.CS; i += blockDim.x) tab[i] = 0.f;      // padding entries of the table copies: any finite value
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Register split (the launch grants 128 per thread): the control warpgroup (issuers + producer) keeps 56, each softmax warpgroup
+  // grows to 152:  3 x 128 x 152 + 128 x 56 = 65 536.
+  if (warp >= 4 * T3_WGS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+  }
   if (warp == T3_TMA_WARP) {
 #ifdef T3_WATCHDOG
     if (lane == 1) {
@@ -434,17 +472,27 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 
     // ---- bias table of one head: four copies shifted by 0..3 floats, w axis flipped, strides (SD, SH, 1) ----
     auto stage_table = [&](int head) {
-      named_bar(4, T3_SM_THREADS);                 // every warpgroup is done with the previous head's tiles
+      // the compact table (L <= 2535 floats) is read once with independent coalesced loads (a dependent load per expanded entry cost
+      // 20 000 cycles per head: ncu showed the softmax warps parked on it) and every entry is scattered into the four shifted copies
       const float* src = p.table_t + static_cast<long long>(head) * p.L;
-      const int nd = 2 * wg.Wd - 1;
-      for (int i = threadIdx.x; i < 4 * a.CS; i += T3_SM_THREADS) {
-        const int k = i / a.CS, xx = i - k * a.CS;
-        const int nat = xx + k;
-        const int aa = nat / T3_SD, rem = nat - aa * T3_SD;
-        const int bb = rem / T3_SH, cc = rem - bb * T3_SH;
-        float val = 0.f;
-        if (aa < nd && bb < 13 && cc < 13) val = __ldg(src + (aa * 13 + bb) * 13 + (12 - cc)) * T3_LOG2E;
-        tab[i] = val;
+      float vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = threadIdx.x + j * T3_SM_THREADS;
+        vals[j] = i < p.L ? __ldg(src + i) * T3_LOG2E : 0.f;
+      }
+      named_bar(4, T3_SM_THREADS);                 // every warpgroup is done with the previous head's tiles
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = threadIdx.x + j * T3_SM_THREADS;
+        if (i < p.L) {
+          const int aa = i / 169, rem = i - aa * 169;
+          const int bb = rem / 13, co = rem - bb * 13;
+          const int nat = aa * T3_SD + bb * T3_SH + (12 - co);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (nat >= k) tab[k * a.CS + nat - k] = vals[j];
+        }
       }
       named_bar(4, T3_SM_THREADS);
     };
@@ -488,10 +536,10 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 
     T3_PROG(1);
     T3_PROG(2);
+    // (unit, tile, head, window) of this warpgroup's tiles advance incrementally: no runtime divisions per tile
+    int lu = g / ntiles, qt = g - lu * ntiles;
+    int head = (u_begin + lu) / a.nwin, win = (u_begin + lu) - head * a.nwin;
     for (int tq = g; tq < T; tq += T3_WGS) {
-      const int lu = tq / ntiles, qt = tq - lu * ntiles;
-      const int u = u_begin + lu;
-      const int head = u / a.nwin, win = u - head * a.nwin;
       T3_PROG(10 + tq * 100);
       while (ev_done <= head - head_first) {
         stage_table(head_first + ev_done);
@@ -545,7 +593,11 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         tc_fence_after();
         T3_STAMP(1, n);
         T3_PROG(30 + c + tq * 100);
+#ifdef T3_X_NOSOFTMAX
+        if (wvalid && n < 0) {
+#else
         if (wvalid) {
+#endif
           const uint32_t ts_buf = tlane + buf * T3_CW;
           const uint32_t pvp = static_cast<uint32_t>((n - 1) & 1);
           if (need_mask) {
@@ -575,6 +627,15 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       prev_l = row.l;
       prev_row = static_cast<long long>(win) * N + ic;
       prev_head = head;
+      qt += T3_WGS;
+      while (qt >= ntiles) {
+        qt -= ntiles;
+        ++lu;
+        if (++win == a.nwin) {
+          win = 0;
+          ++head;
+        }
+      }
     }
     T3_PROG(900);
     if (have_prev) epilogue();
