@@ -234,6 +234,10 @@ def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, st
     from lavt_rs_b200 import engine as E
     from lavt_rs_b200 import train_engine as T
     from lavt_rs_b200 import training as TR
+    # the steps below move the decoder's BatchNorm running statistics; they are put back afterwards so that the parity leg (which runs
+    # later on the same model) still compares the model the headline number was measured on
+    buffers = {k: v.detach().clone() for k, v in model.named_buffers()}
+    drop_rates = [blk.drop_path_rate for layer in model.backbone.layers for blk in layer.blocks]
     model.train()
     for layer in model.backbone.layers:
         for blk in layer.blocks:
@@ -288,6 +292,11 @@ def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, st
     for p in params:
         p.grad = None
     model.eval()
+    with torch.no_grad():
+        for k, v in model.named_buffers():
+            v.copy_(buffers[k])
+    for blk, r in zip([blk for layer in model.backbone.layers for blk in layer.blocks], drop_rates):
+        blk.drop_path_rate = r
     return {"metric": "LAVT-RS train step clips/s (fwd+bwd, 8x384^2)", "clips_per_s": clips * world * steps / (ms * 1e-3), "ms_per_step": ms / steps,
             "n_gpus": world, "clips_per_gpu_per_step": clips, "steps": steps, "gpu_launches_per_step": launches, "loss": loss,
             "config": "BASELINE configs[3]: fwd + [0.9,1.1]-weighted CE + bwd in bf16, window 8x7x7, DropPath off, no optimizer update; "
