@@ -528,7 +528,7 @@ def main():
                 # per launch the binding roof is max(FLOPs / tensor peak, algorithmic bytes / HBM peak): short-K Swin
                 # GEMMs (K = 128..256) are HBM-bound; this is sum(ideal) / sum(measured) over the step's launches
                 "alg_bytes_per_step": g.get("bytes"), "frac_vs_binding_roof": (g["ideal_ms"] / g["ms"]) if g["ms"] > 0 else None,
-                "attention_core": {"kernel": "window_attn_tc_kernel (tcgen05/TMEM two-pass, windows <= 400 tokens) / window_attn_tc2_kernel (tcgen05/TMEM key-chunked one-pass, larger windows)",
+                "attention_core": {"kernel": "window_attn_tc3_kernel (tcgen05/TMEM, 7x7 windows: row-parallel warpgroups, run-padded keys) / window_attn_tc2_kernel (tcgen05/TMEM key-chunked one-pass, other windows)",
                                    "impl": os.environ.get("LAVT_ATTN_IMPL", "auto"), "launches": at["launches"], "ms_per_step": at["ms"],
                                    "tflops": at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0},
                 "whole_step_tflops": flops_per_clip(a.window12) * value / world / 1e12}
