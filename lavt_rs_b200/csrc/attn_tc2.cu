@@ -814,13 +814,13 @@ int window_attn_tc2_dispatch(const AttnParams& p, cudaStream_t st) {
     uint64_t dims[2] = {static_cast<uint64_t>(3 * p.C), static_cast<uint64_t>(nwin * g.N)};
     uint64_t strides[1] = {static_cast<uint64_t>(3 * p.C) * 2};
     uint32_t box[2] = {T2_HD, static_cast<uint32_t>(a.BR)};
-    int rc = make_tmap_bf16(&tm_kv, p.qkv, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = make_tmap_bf16_l2_64b(&tm_kv, p.qkv, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     uint32_t box_q[2] = {T2_HD, 128};
-    rc = make_tmap_bf16(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_bf16_l2_64b(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     uint32_t box_t[2] = {T2_HD, 32};
-    rc = make_tmap_bf16(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_bf16_l2_64b(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   static int sms = 0;

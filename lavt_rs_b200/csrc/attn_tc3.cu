@@ -703,15 +703,15 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
     uint64_t dims4[4] = {static_cast<uint64_t>(3 * p.C), 7, 7, static_cast<uint64_t>(nwin * a.nch)};
     uint64_t str4[3] = {rowb, 7 * rowb, 49 * rowb};
     uint32_t box4[4] = {T3_HD, 8, 8, static_cast<uint32_t>(a.nch)};
-    int rc = make_tmap_bf16(&tm_kv, p.qkv, 4, dims4, str4, box4, CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = make_tmap_bf16_l2_64b(&tm_kv, p.qkv, 4, dims4, str4, box4, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     uint64_t dims[2] = {static_cast<uint64_t>(3 * p.C), static_cast<uint64_t>(nwin * g.N)};
     uint64_t strides[1] = {rowb};
     uint32_t box_q[2] = {T3_HD, 128};
-    rc = make_tmap_bf16(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_bf16_l2_64b(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     uint32_t box_t[2] = {T3_HD, 32};
-    rc = make_tmap_bf16(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_bf16_l2_64b(&tm_tail, p.qkv, 2, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   static int sms = 0;

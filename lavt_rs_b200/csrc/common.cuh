@@ -47,6 +47,8 @@ int check_cuda(cudaError_t e, const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
+int make_tmap_bf16_l2_64b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, CUtensorMapSwizzle swz);
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 

@@ -42,7 +42,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                           CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -62,7 +63,7 @@ static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void*
     return LAVT_ERR_SHAPE;
   }
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
-                  gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: CUresult=%d (rank=%d dims0=%llu box0=%u)", (int)r, rank,
@@ -75,6 +76,12 @@ static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void*
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
+}
+// boxes whose inner extent is 64 bytes (one attention head of a [rows, 3C] tensor): no promotion, so the other half of the 128-byte
+// line (the neighbouring head, consumed by another CTA much later) is not dragged through DRAM twice
+int make_tmap_bf16_l2_64b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
 }
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
