@@ -35,6 +35,9 @@ CASES = [  # (B, D, H, W), window, shifted, heads
     ((1, 16, 14, 14), (8, 7, 7), True, 8), ((1, 8, 24, 24), (8, 12, 12), True, 16), ((1, 4, 48, 48), (8, 12, 12), True, 8),
     ((1, 8, 12, 12), (8, 12, 12), True, 32), ((1, 16, 24, 24), (8, 12, 12), True, 16), ((2, 1, 30, 30), (1, 12, 12), True, 8),
     ((2, 1, 15, 15), (1, 7, 7), True, 32), ((1, 8, 10, 10), (8, 12, 12), True, 4), ((3, 8, 14, 21), (8, 7, 7), False, 4),
+    # attn_tc3.cu corner cases: a two-frame window (N = 98, one partial tile), a single (window, head) unit, and enough units per CTA that the
+    # K / V stages, the Q ring and the bias table (several heads per CTA) all wrap around
+    ((1, 2, 14, 14), (8, 7, 7), True, 4), ((1, 8, 7, 7), (8, 7, 7), False, 1), ((4, 8, 24, 24), (8, 7, 7), True, 16),
 ]
 
 
