@@ -1,5 +1,8 @@
-// tcgen05 / TMEM shifted-window attention core, third generation: windows whose (h, w) extent is the configured 7 x 7
-// (N = 49 * wd tokens, wd <= 8: every window of the 8 x 7 x 7 video model and of the 7 x 7 image model).
+// tcgen05 / TMEM shifted-window attention core, third generation: windows whose (h, w) extent is the configured 7 x 7 or 12 x 12
+// (N = 49 * wd or 144 * wd tokens, wd <= 8: every unclamped window of the 8 x 7 x 7 / 8 x 12 x 12 video models and of the 2-D image models).
+// The description below is written for 7 x 7; the 12 x 12 instantiation (T3G<12>) differs in the numbers only: runs of 12 keys need no
+// padding, a chunk is 4 runs = 48 columns (three chunks per frame), and the 33 KB table exists once (scalar bias loads at immediate
+// offsets: four shifted copies do not fit next to 147 KB of K / V, which is also why that shape has a single K / V stage).
 // (reference WindowAttention3D.forward, lib/video_swin_transformer.py:147-165; 2-D twin lib/backbone.py:127-138)
 //     S = q k^T + relative-position bias (+ shifted-window mask)  ->  softmax  ->  O = P v       per (window, head)
 //
@@ -38,12 +41,17 @@ constexpr int T3_WGS = 3;
 constexpr int T3_SM_THREADS = 128 * T3_WGS;
 constexpr int T3_TMA_WARP = 4 * T3_WGS + 3;   // warp 15: the SM sub-partition (warp % 4 = 3) that hosts no MMA-issuing softmax warp
 constexpr int T3_THREADS = 512;               // warps 12-14 only run to the final barrier (registers are granted per 4 warps anyway)
-constexpr int T3_CW = 64;                   // S columns per chunk = one frame: 7 runs of 7 keys padded to 8 + one all-padding run
-constexpr int T3_WG_COLS = 2 * T3_CW + T3_HD;
-constexpr int T3_SH = 16;                   // bias-table strides (floats) in shared memory: w' in [0,13), h in [0,13), d in [0,2Wd-1)
-constexpr int T3_SD = 13 * T3_SH;
+// Window-shape traits.  RW keys per run (= window width), RP S columns per run, WH runs per frame, RC runs per chunk (incl. the all-padding
+// run of a 7 x 7 frame), CPF chunks per frame, CW S columns per chunk, SH / EH / EW bias-table geometry in shared memory (w' in [0, EW),
+// h in [0, EH), row stride SH, frame stride SD), NCOPY shifted table copies, NR0 + NR1 runs in the two pieces of a chunk.
+template <int RW_> struct T3G;
+template <> struct T3G<7> {
+  static constexpr int RW = 7, RP = 8, WH = 7, RC = 8, CPF = 1, CW = 64, SH = 16, EH = 13, EW = 13, NCOPY = 4, NR0 = 4, NR1 = 3;
+};
+template <> struct T3G<12> {
+  static constexpr int RW = 12, RP = 12, WH = 12, RC = 4, CPF = 3, CW = 48, SH = 24, EH = 23, EW = 23, NCOPY = 1, NR0 = 2, NR1 = 2;
+};
 constexpr int T3_NQ = 4;                    // Q-tile ring slots
-constexpr int T3_CHUNK_BYTES = T3_CW * 64;  // one frame of K (or V) rows in shared memory
 constexpr float T3_LOG2E = 1.4426950408889634f;
 constexpr float T3_MASKV = -100.0f * T3_LOG2E;
 constexpr float T3_PSUM_LIMIT = 1048576.0f;  // 2^20
@@ -64,7 +72,9 @@ __device__ __forceinline__ void t3_wait(uint64_t* bar, uint32_t parity, int) { m
 #endif
 
 struct AttnTc3Args {
-  int N, nch, ntiles;       // tokens per window, frames per window (= key chunks), 128-row query tiles
+  int N, nch, ntiles;       // tokens per window, key chunks per window, 128-row query tiles
+  int nkv;                  // K | V stages (2, or 1 when a unit's K / V fill most of the shared memory)
+  int BR, nb;               // 12 x 12 windows: K / V arrive as nb plain 2-D boxes of BR rows
   int nwin, units;
   int tail_rows, rot;       // rot: the last tile has <= 32 rows and rotates through the lane quadrants
   int CS;                   // floats between the four shifted table copies
@@ -78,45 +88,59 @@ constexpr int T3_TRACE_ITEMS = 96;
 struct T3Row {
   const float* tb;          // this row's bias address of (frame 0, run h_j = 6); run h_j: + (6 - h_j) * SH, frame t_j: - t_j * SD
   float m, l;
-  float mw[8];              // masked windows: w-axis mask of the 7 keys of a run (0 or -100 log2 e)
+  float mw[12];             // masked windows: w-axis mask of the keys of a run (0 or -100 log2 e)
   uint32_t dm, hm;          // masked windows: bit t_j / h_j set = that frame / run lies in another region than this row
 };
 
-// One piece = NR runs of 8 columns (7 live) of the chunk in TMEM at ts (fp32 scores), written back as bf16 pairs at tp.
-//   fb  : bias address of run h_j = 6 of this frame for this row;   HJ0: first run of the piece
+// running maximum / sum helpers over the RW live values of a run
+template <int RW>
+__device__ __forceinline__ void t3_run_max(const float* x, float& m0, float& m1) {
+#pragma unroll
+  for (int e = 0; e + 1 < RW; e += 2) {
+    if ((e >> 1) & 1) m1 = max3(m1, x[e], x[e + 1]); else m0 = max3(m0, x[e], x[e + 1]);
+  }
+  if (RW & 1) m1 = fmaxf(m1, x[RW - 1]);
+}
+
+// One piece = NR runs of RP columns (RW live) of the chunk in TMEM at ts (fp32 scores), written back as bf16 pairs at tp.
+//   fb  : bias address of run h_j = WH - 1 of this frame for this row, moved back by the chunk's first run;   HJ0: first run of the piece
 //   pdone : P columns of this chunk already written (slow path rescales them), o_acc: the O accumulator holds earlier chunks
-template <int NR, int HJ0, bool MASKED, bool FIRST>
+template <typename G, int NR, int HJ0, bool MASKED, bool FIRST>
 __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* fb, T3Row& r, uint32_t rmask, uint32_t tp_chunk, int pdone,
                                          bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
-  constexpr int W = 8 * NR;
+  constexpr int RW = G::RW, RP = G::RP;
+  constexpr int W = RP * NR;
+  static_assert(W == 32 || W == 24, "pieces are 32 or 24 columns");
   uint32_t v[W];
 #ifdef T3_X_NOLD
 #pragma unroll
   for (int j = 0; j < W; ++j) v[j] = ts + j;
 #else
-  if constexpr (NR == 4) {
+  if constexpr (W == 32) {
     tmem_ld_x32(ts, v);
-  } else if constexpr (NR == 3) {
+  } else {
     tmem_ld_x16(ts, v);
     tmem_ld_x8(ts + 16, v + 16);
-  } else {
-    static_assert(NR == 7, "pieces are 7, 4 or 3 runs");
-    tmem_ld_x32(ts, v);
-    tmem_ld_x16(ts + 32, v + 32);
-    tmem_ld_x8(ts + 48, v + 48);
   }
 #endif
   float x[W];
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
+    const float* rb = fb + (G::WH - 1 - HJ0 - k) * G::SH;
 #ifdef T3_X_NOBIAS
-    const float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+#pragma unroll
+    for (int e = 0; e < RP; ++e) x[RP * k + e] = 0.f;
 #else
-    const float4 b0 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH);
-    const float4 b1 = *reinterpret_cast<const float4*>(fb + (6 - HJ0 - k) * T3_SH + 4);
+    if constexpr (G::NCOPY == 4) {          // 16-byte aligned run start in this row's table copy: two LDS.128 (the 8th value is unused)
+      const float4 b0 = *reinterpret_cast<const float4*>(rb);
+      const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
+      x[8 * k + 0] = b0.x; x[8 * k + 1] = b0.y; x[8 * k + 2] = b0.z; x[8 * k + 3] = b0.w;
+      x[8 * k + 4] = b1.x; x[8 * k + 5] = b1.y; x[8 * k + 6] = b1.z; x[8 * k + 7] = b1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < RP; ++e) x[RP * k + e] = rb[e];
+    }
 #endif
-    x[8 * k + 0] = b0.x; x[8 * k + 1] = b0.y; x[8 * k + 2] = b0.z; x[8 * k + 3] = b0.w;
-    x[8 * k + 4] = b1.x; x[8 * k + 5] = b1.y; x[8 * k + 6] = b1.z; x[8 * k + 7] = b1.w;
   }
   tmem_ld_wait();
 #pragma unroll
@@ -126,18 +150,13 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
     for (int k = 0; k < NR; ++k) {
       const bool rm = (rmask >> (HJ0 + k)) & 1u;
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) add2(x[8 * k + e], x[8 * k + e + 1], rm ? T3_MASKV : r.mw[e], rm ? T3_MASKV : r.mw[e + 1]);
+      for (int e = 0; e < RP; e += 2) add2(x[RP * k + e], x[RP * k + e + 1], rm ? T3_MASKV : r.mw[e], rm ? T3_MASKV : r.mw[e + 1]);
     }
   }
   if constexpr (FIRST) {
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      m0 = max3(m0, x[8 * k + 0], x[8 * k + 1]);
-      m1 = max3(m1, x[8 * k + 2], x[8 * k + 3]);
-      m0 = max3(m0, x[8 * k + 4], x[8 * k + 5]);
-      m1 = fmaxf(m1, x[8 * k + 6]);
-    }
+    for (int k = 0; k < NR; ++k) t3_run_max<RW>(x + RP * k, m0, m1);
     r.m = fmaxf(m0, m1);
   }
   float p[W];
@@ -154,15 +173,16 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
 #pragma unroll
-      for (int e = 0; e < 7; ++e) p[8 * k + e] = ex2_ftz(p[8 * k + e]);
+      for (int e = 0; e < RW; ++e) p[RP * k + e] = ex2_ftz(p[RP * k + e]);
     }
 #endif
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-      add2(l0, l1, p[8 * k + 0], p[8 * k + 1]);
-      add2(l2, l3, p[8 * k + 2], p[8 * k + 3]);
-      add2(l0, l1, p[8 * k + 4], p[8 * k + 5]);
-      l2 += p[8 * k + 6];
+#pragma unroll
+      for (int e = 0; e + 1 < RW; e += 2) {
+        if ((e >> 1) & 1) add2(l2, l3, p[RP * k + e], p[RP * k + e + 1]); else add2(l0, l1, p[RP * k + e], p[RP * k + e + 1]);
+      }
+      if (RW & 1) l2 += p[RP * k + RW - 1];
     }
   }
   float ps = (l0 + l1) + (l2 + l3);
@@ -171,12 +191,7 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
       // ---- slow path (rare): some score of this piece exceeds the running maximum by ~2^14: re-base the row ----
       float m0 = r.m, m1 = r.m;
 #pragma unroll
-      for (int k = 0; k < NR; ++k) {
-        m0 = max3(m0, x[8 * k + 0], x[8 * k + 1]);
-        m1 = max3(m1, x[8 * k + 2], x[8 * k + 3]);
-        m0 = max3(m0, x[8 * k + 4], x[8 * k + 5]);
-        m1 = fmaxf(m1, x[8 * k + 6]);
-      }
+      for (int k = 0; k < NR; ++k) t3_run_max<RW>(x + RP * k, m0, m1);
       const float m2 = fmaxf(m0, m1);
       const float f = ex2_ftz(r.m - m2);          // 1 for the lanes whose maximum did not move
       r.l *= f;
@@ -209,55 +224,51 @@ __device__ __forceinline__ void t3_piece(uint32_t ts, uint32_t tp, const float* 
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
 #pragma unroll
-        for (int e = 0; e < 7; ++e) {
-          p[8 * k + e] = ex2_ftz(x[8 * k + e] + nm);
-          ps += p[8 * k + e];
+        for (int e = 0; e < RW; ++e) {
+          p[RP * k + e] = ex2_ftz(x[RP * k + e] + nm);
+          ps += p[RP * k + e];
         }
       }
     }
   }
   r.l += ps;
-  uint32_t pk[NR == 7 ? 32 : 16];
+  uint32_t pk[16];
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
-    pk[4 * k + 0] = pack_bf16x2(p[8 * k + 0], p[8 * k + 1]);
-    pk[4 * k + 1] = pack_bf16x2(p[8 * k + 2], p[8 * k + 3]);
-    pk[4 * k + 2] = pack_bf16x2(p[8 * k + 4], p[8 * k + 5]);
-    pk[4 * k + 3] = pack_bf16x2(p[8 * k + 6], 0.f);
-  }
-  if constexpr (NR == 3) {
 #pragma unroll
-    for (int j = 12; j < 16; ++j) pk[j] = 0u;          // the all-padding run of the frame
+    for (int e = 0; e < RP; e += 2) pk[(RP / 2) * k + (e >> 1)] = pack_bf16x2(p[RP * k + e], (e + 1 < RW) ? p[RP * k + e + 1] : 0.f);
   }
-  if constexpr (NR == 7) {
 #pragma unroll
-    for (int j = 28; j < 32; ++j) pk[j] = 0u;
-  }
+  for (int j = NR * RP / 2; j < 16; ++j) pk[j] = 0u;          // 7 x 7: the all-padding run that ends the frame
 #ifdef T3_X_NOST
   uint32_t acc = 0;
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc ^= pk[j];
   if (acc == 0x12345678u) tmem_st_x16(tp, pk);
 #else
-  if constexpr (NR == 7) tmem_st_x32(tp, pk); else tmem_st_x16(tp, pk);
+  if constexpr (G::RP == 8) {
+    tmem_st_x16(tp, pk);                         // 4 runs (or 3 + the padding run) x 4 words
+  } else {
+    tmem_st_x8(tp, pk);                          // 2 runs x 6 words
+    tmem_st_x4(tp + 8, pk + 8);
+  }
 #endif
 }
 
-// one chunk (= frame t_j) for this thread's row
-template <bool MASKED, bool FIRST>
-__device__ __forceinline__ void t3_chunk(uint32_t ts_buf, int tj, T3Row& r, bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
-  const float* fb = r.tb - tj * T3_SD;
+// one chunk (chunk index c of the window) for this thread's row
+template <typename G, bool MASKED, bool FIRST>
+__device__ __forceinline__ void t3_chunk(uint32_t ts_buf, int c, T3Row& r, bool o_acc, uint64_t* pv_done, uint32_t pvp, uint32_t tmem_o) {
+  const int tj = G::CPF == 1 ? c : c / G::CPF;
+  const int run0 = G::CPF == 1 ? 0 : (c - tj * G::CPF) * G::RC;
+  const float* fb = r.tb - tj * (G::EH * G::SH) - run0 * G::SH;
   uint32_t rmask = 0;
-  if constexpr (MASKED) rmask = ((r.dm >> tj) & 1u) ? 0x7fu : r.hm;
-#ifndef T3_ONE_PIECE
-  t3_piece<4, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
-  t3_piece<3, 4, MASKED, false>(ts_buf + 32, ts_buf + 16, fb, r, rmask, ts_buf, 16, o_acc, pv_done, pvp, tmem_o);
-#else
-  // the whole frame as one piece: one TMEM load / wait / store per chunk and one large basic block for the instruction scheduler
-  t3_piece<7, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
-#endif
+  if constexpr (MASKED) rmask = (((r.dm >> tj) & 1u) ? 0xfffu : r.hm) >> run0;
+  constexpr int P0 = G::NR0 * G::RP;             // S columns of the first piece (its P takes half as many)
+  t3_piece<G, G::NR0, 0, MASKED, FIRST>(ts_buf, ts_buf, fb, r, rmask, ts_buf, 0, o_acc, pv_done, pvp, tmem_o);
+  t3_piece<G, G::NR1, G::NR0, MASKED, false>(ts_buf + P0, ts_buf + P0 / 2, fb, r, rmask, ts_buf, P0 / 2, o_acc, pv_done, pvp, tmem_o);
 }
 
+template <int RW>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmQT, const AttnParams p, const AttnTc3Args a) {
@@ -276,8 +287,10 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint64_t* p_ready = o_full + T3_WGS;            // [T3_WGS][2] the four warps of the warpgroup wrote their P rows of that S buffer
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p_ready + 2 * T3_WGS);
 
+  using G = T3G<RW>;
+  constexpr int T3_CW = G::CW, T3_WG_COLS = 2 * G::CW + T3_HD, T3_CHUNK_BYTES = G::CW * 64, T3_SH = G::SH, T3_SD = G::EH * G::SH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.N, nch = a.nch, ntiles = a.ntiles;
+  const int N = a.N, nch = a.nch, ntiles = a.ntiles, nkv = a.nkv;
   const WinGeom& wg = p.win;
 #ifdef T3_WATCHDOG
   volatile int* prog = reinterpret_cast<volatile int*>(smem + a.off_bar + 256);     // progress code per warp
@@ -320,7 +333,7 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     fence_mbar_init();
   }
   if (warp == T3_TMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
-  for (int i = threadIdx.x; i < 4 * a.CS; i += blockDim.x) tab[i] = 0.f;      // padding entries of the table copies: any finite value
+  for (int i = threadIdx.x; i < G::NCOPY * a.CS; i += blockDim.x) tab[i] = 0.f;      // padding entries of the table copies: any finite value
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -355,13 +368,20 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     // =============================== TMA producer (one thread) ===============================
     if (lane == 0) {
       for (int lu = 0; lu < nunits; ++lu) {
-        const int u = u_begin + lu, s = lu & 1;
+        const int u = u_begin + lu;
+        const int s = nkv == 2 ? (lu & 1) : 0, use = nkv == 2 ? (lu >> 1) : lu;      // stage and how often it was used before
         const int head = u / a.nwin, win = u - head * a.nwin;
-        if (lu >= 2) t3_wait(&kv_free[s], ((lu >> 1) - 1) & 1, 2);           // every P.V of the unit that used this stage retired
+        if (use >= 1) t3_wait(&kv_free[s], (use - 1) & 1, 2);                        // every P.V of the unit that used this stage retired
         uint8_t* st = smem + s * a.kv_bytes;
         mbar_expect_tx(&kv_full[s], 2u * nch * T3_CHUNK_BYTES);
-        tma_load_4d(st, &tmKV, &kv_full[s], p.C + head * T3_HD, 0, 0, win * nch);
-        tma_load_4d(st + nch * T3_CHUNK_BYTES, &tmKV, &kv_full[s], 2 * p.C + head * T3_HD, 0, 0, win * nch);
+        if constexpr (RW == 7) {
+          tma_load_4d(st, &tmKV, &kv_full[s], p.C + head * T3_HD, 0, 0, win * nch);
+          tma_load_4d(st + nch * T3_CHUNK_BYTES, &tmKV, &kv_full[s], 2 * p.C + head * T3_HD, 0, 0, win * nch);
+        } else {
+          for (int op = 0; op < 2; ++op)
+            for (int b = 0; b < a.nb; ++b)
+              tma_load_2d(st + op * nch * T3_CHUNK_BYTES + b * a.BR * 64, &tmKV, &kv_full[s], (1 + op) * p.C + head * T3_HD, win * N + b * a.BR);
+        }
         T3_PROG(5 + lu * 100);
         for (int qt = 0; qt < ntiles; ++qt) {
           const int tq = lu * ntiles + qt, slot = tq & (T3_NQ - 1);
@@ -392,9 +412,9 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     // (units of one or two tiles); the issue for the item that is due next may block -- it only depends on earlier tiles.
     auto issue_qk = [&](bool blocking) -> bool {
       if (qk_tq >= T) return false;
-      const int s = qk_lu & 1, slot = qk_tq & (T3_NQ - 1);
+      const int s = nkv == 2 ? (qk_lu & 1) : 0, slot = qk_tq & (T3_NQ - 1);
       if (qk_c == 0) {
-        const uint32_t pk = (qk_lu >> 1) & 1, pq = (qk_tq >> 2) & 1;
+        const uint32_t pk = (nkv == 2 ? (qk_lu >> 1) : qk_lu) & 1, pq = (qk_tq >> 2) & 1;
         if (blocking) {
           t3_wait(&kv_full[s], pk, 4);
           t3_wait(&q_full[slot], pq, 5);
@@ -428,7 +448,7 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     if (issue_qk(false)) issue_qk(false);
     int n = 0, lu = g / ntiles, qt = g - lu * ntiles;
     for (int tq = g; tq < T; tq += T3_WGS) {
-      const int s = lu & 1;
+      const int s = nkv == 2 ? (lu & 1) : 0;
       for (int c = 0; c < nch; ++c, ++n) {
         const int buf = n & 1;
         while (qk_n <= n) issue_qk(true);                         // normally issued long ago
@@ -472,26 +492,28 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 
     // ---- bias table of one head: four copies shifted by 0..3 floats, w axis flipped, strides (SD, SH, 1) ----
     auto stage_table = [&](int head) {
-      // the compact table (L <= 2535 floats) is read once with independent coalesced loads (a dependent load per expanded entry cost
-      // 20 000 cycles per head: ncu showed the softmax warps parked on it) and every entry is scattered into the four shifted copies
+      // the compact table is read with independent coalesced loads (a dependent load per expanded entry cost 20 000 cycles per head: ncu
+      // showed the softmax warps parked on it) and every entry is scattered into the shifted copies; w axis flipped, strides (SD, SH, 1)
       const float* src = p.table_t + static_cast<long long>(head) * p.L;
-      float vals[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = threadIdx.x + j * T3_SM_THREADS;
-        vals[j] = i < p.L ? __ldg(src + i) * T3_LOG2E : 0.f;
-      }
       named_bar(4, T3_SM_THREADS);                 // every warpgroup is done with the previous head's tiles
+      for (int base = 0; base < p.L; base += 8 * T3_SM_THREADS) {
+        float vals[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = threadIdx.x + j * T3_SM_THREADS;
-        if (i < p.L) {
-          const int aa = i / 169, rem = i - aa * 169;
-          const int bb = rem / 13, co = rem - bb * 13;
-          const int nat = aa * T3_SD + bb * T3_SH + (12 - co);
+        for (int j = 0; j < 8; ++j) {
+          const int i = base + threadIdx.x + j * T3_SM_THREADS;
+          vals[j] = i < p.L ? __ldg(src + i) * T3_LOG2E : 0.f;
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (nat >= k) tab[k * a.CS + nat - k] = vals[j];
+        for (int j = 0; j < 8; ++j) {
+          const int i = base + threadIdx.x + j * T3_SM_THREADS;
+          if (i < p.L) {
+            const int aa = i / (G::EH * G::EW), rem = i - aa * (G::EH * G::EW);
+            const int bb = rem / G::EW, co = rem - bb * G::EW;
+            const int nat = aa * T3_SD + bb * T3_SH + (G::EW - 1 - co);
+#pragma unroll
+            for (int k = 0; k < G::NCOPY; ++k)
+              if (nat >= k) tab[k * a.CS + nat - k] = vals[j];
+          }
         }
       }
       named_bar(4, T3_SM_THREADS);
@@ -552,18 +574,18 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       const int i = qt * 128 + (rot ? lane : r);
       const bool wvalid = rot ? (q == (lu & 3)) : (qt * 128 + q * 32) < N;  // warp-uniform: does this warp own live query rows?
       const int ic = i < N ? i : N - 1;
-      const int ti = ic / 49, hi = (ic / 7) % 7, wi = ic % 7;
+      const int ti = ic / (G::WH * RW), hi = (ic / RW) % G::WH, wi = ic % RW;
       T3Row row;
       {
-        const int k = (6 - wi) & 3;
-        const int A = (ti + wg.Wd - 1) * T3_SD + (hi + 6) * T3_SH + (6 - wi);
-        row.tb = tab + k * a.CS + (A - k) - 6 * T3_SH;
+        const int k = G::NCOPY == 4 ? ((RW - 1 - wi) & 3) : 0;
+        const int A = (ti + wg.Wd - 1) * T3_SD + (hi + G::WH - 1) * T3_SH + (RW - 1 - wi);
+        row.tb = tab + k * a.CS + (A - k) - (G::WH - 1) * T3_SH;
         row.m = -1e30f;
         row.l = 0.f;
         row.dm = 0u;
         row.hm = 0u;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) row.mw[e] = 0.f;
+        for (int e = 0; e < 12; ++e) row.mw[e] = 0.f;
       }
       bool need_mask = false;
       if (a.shifted) {
@@ -577,10 +599,10 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         if (need_mask) {
           const bool cd = ti >= bd, chh = hi >= bh, cw = wi >= bw;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (((e >= bd) != cd)) row.dm |= 1u << e;
-            if (e < 7 && ((e >= bh) != chh)) row.hm |= 1u << e;
-            row.mw[e] = (e < 7 && ((e >= bw) != cw)) ? T3_MASKV : 0.f;
+          for (int e = 0; e < 12; ++e) {
+            if (e < 8 && ((e >= bd) != cd)) row.dm |= 1u << e;
+            if (e < G::WH && ((e >= bh) != chh)) row.hm |= 1u << e;
+            row.mw[e] = (e < RW && ((e >= bw) != cw)) ? T3_MASKV : 0.f;
           }
         }
       }
@@ -601,11 +623,11 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           const uint32_t ts_buf = tlane + buf * T3_CW;
           const uint32_t pvp = static_cast<uint32_t>((n - 1) & 1);
           if (need_mask) {
-            if (c == 0) t3_chunk<true, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
-            else t3_chunk<true, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
+            if (c == 0) t3_chunk<G, true, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
+            else t3_chunk<G, true, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
           } else {
-            if (c == 0) t3_chunk<false, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
-            else t3_chunk<false, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
+            if (c == 0) t3_chunk<G, false, true>(ts_buf, c, row, false, my_pv, pvp, tmem_o);
+            else t3_chunk<G, false, false>(ts_buf, c, row, true, my_pv, pvp, tmem_o);
           }
         }
         T3_PROG(40 + c + tq * 100);
@@ -658,26 +680,42 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static bool t3_plan(const AttnParams& p, AttnTc3Args& a, int& smem_out) {
+template <int RW>
+static bool t3_plan_rw(const AttnParams& p, AttnTc3Args& a, int& smem_out) {
+  using G = T3G<RW>;
   const WinGeom& g = p.win;
-  if (g.Wh != 7 || g.Ww != 7 || g.wh != 7 || g.ww != 7) return false;
-  if (g.wd < 1 || g.wd > 8 || g.Wd < g.wd || g.Wd > 8 || g.N != 49 * g.wd) return false;
-  if ((3 * p.C * 2) % 16 != 0) return false;
+  if (g.Wh != RW || g.Ww != RW || g.wh != RW || g.ww != RW) return false;
+  if (g.wd < 1 || g.wd > 8 || g.Wd < g.wd || g.Wd > 8 || g.N != RW * RW * g.wd) return false;
+  if ((3 * p.C * 2) % 16 != 0 || p.L != (2 * g.Wd - 1) * G::EH * G::EW) return false;
   a.N = g.N;
-  a.nch = g.wd;
+  a.nch = g.wd * G::CPF;
   a.ntiles = (g.N + 127) / 128;
   a.tail_rows = g.N - (a.ntiles - 1) * 128;
   a.rot = (a.ntiles >= 2 && a.tail_rows <= 32) ? 1 : 0;
   a.shifted = (g.sd | g.sh | g.sw) != 0;
-  const int L2 = (2 * g.Wd - 1) * T3_SD + 16;
+  a.nb = a.BR = 0;
+  if (RW != 7) {          // plain 2-D K / V boxes: the fewest boxes of <= 256 rows that tile N exactly
+    for (int nb = (g.N + 255) / 256; nb <= 16; ++nb)
+      if (g.N % nb == 0) { a.nb = nb; break; }
+    if (a.nb == 0) return false;
+    a.BR = g.N / a.nb;
+  }
+  const int L2 = (2 * g.Wd - 1) * G::EH * G::SH + 32;
   a.CS = L2 + ((8 - L2 % 32) + 32) % 32;          // CS = 8 (mod 32): the four copies start 2 sixteen-byte bank groups apart
-  a.kv_bytes = 2 * a.nch * T3_CHUNK_BYTES;
-  int off = 2 * a.kv_bytes;
-  a.off_q = off;          off += T3_NQ * 128 * 64;
-  a.off_tab = off;        off += ((4 * a.CS * 4 + 127) / 128) * 128;
-  a.off_bar = off;        off += 384;
-  smem_out = off + 1024;
-  return smem_out <= 227 * 1024;
+  a.kv_bytes = 2 * a.nch * G::CW * 64;
+  for (a.nkv = 2; a.nkv >= 1; --a.nkv) {
+    int off = a.nkv * a.kv_bytes;
+    a.off_q = off;          off += T3_NQ * 128 * 64;
+    a.off_tab = off;        off += ((G::NCOPY * a.CS * 4 + 127) / 128) * 128;
+    a.off_bar = off;        off += 384;
+    smem_out = off + 1024;
+    if (smem_out <= 227 * 1024) return true;
+  }
+  return false;
+}
+
+static bool t3_plan(const AttnParams& p, AttnTc3Args& a, int& smem_out) {
+  return p.win.Ww == 12 ? t3_plan_rw<12>(p, a, smem_out) : t3_plan_rw<7>(p, a, smem_out);
 }
 
 bool window_attn_tc3_supported(const AttnParams& p) {
@@ -698,15 +736,21 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
 
   CUtensorMap tm_kv, tm_q, tm_tail;
   {
-    // K / V: (channel, w, h, frame) with a box one larger than the 7 x 7 window: TMA zero-fills w = 7 and h = 7
     const uint64_t rowb = static_cast<uint64_t>(3 * p.C) * 2;
-    uint64_t dims4[4] = {static_cast<uint64_t>(3 * p.C), 7, 7, static_cast<uint64_t>(nwin * a.nch)};
-    uint64_t str4[3] = {rowb, 7 * rowb, 49 * rowb};
-    uint32_t box4[4] = {T3_HD, 8, 8, static_cast<uint32_t>(a.nch)};
-    int rc = make_tmap_bf16_l2_64b(&tm_kv, p.qkv, 4, dims4, str4, box4, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
     uint64_t dims[2] = {static_cast<uint64_t>(3 * p.C), static_cast<uint64_t>(nwin * g.N)};
     uint64_t strides[1] = {rowb};
+    int rc;
+    if (g.Ww == 7) {
+      // K / V: (channel, w, h, frame) with a box one larger than the 7 x 7 window: TMA zero-fills w = 7 and h = 7
+      uint64_t dims4[4] = {static_cast<uint64_t>(3 * p.C), 7, 7, static_cast<uint64_t>(nwin * a.nch)};
+      uint64_t str4[3] = {rowb, 7 * rowb, 49 * rowb};
+      uint32_t box4[4] = {T3_HD, 8, 8, static_cast<uint32_t>(a.nch)};
+      rc = make_tmap_bf16_l2_64b(&tm_kv, p.qkv, 4, dims4, str4, box4, CU_TENSOR_MAP_SWIZZLE_64B);
+    } else {
+      uint32_t box_kv[2] = {T3_HD, static_cast<uint32_t>(a.BR)};
+      rc = make_tmap_bf16_l2_64b(&tm_kv, p.qkv, 2, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
+    if (rc) return rc;
     uint32_t box_q[2] = {T3_HD, 128};
     rc = make_tmap_bf16_l2_64b(&tm_q, p.qkv, 2, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
@@ -721,10 +765,12 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
       sms = 148;
   }
   const int grid = a.units < sms ? a.units : sms;
-  static int configured = 0;
-  if (smem > configured) {
-    LAVT_CUDA(cudaFuncSetAttribute(window_attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+  const int ki = g.Ww == 12 ? 1 : 0;
+  auto kfn = ki ? window_attn_tc3_kernel<12> : window_attn_tc3_kernel<7>;
+  static int configured[2] = {0, 0};
+  if (smem > configured[ki]) {
+    LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[ki] = smem;
   }
   a.trace = nullptr;
 #ifdef T3_TRACE
@@ -735,7 +781,7 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
     LAVT_CUDA(cudaMemsetAsync(a.trace, 0, trace_n * sizeof(long long), st));
   }
 #endif
-  window_attn_tc3_kernel<<<grid, T3_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
+  kfn<<<grid, T3_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
   LAVT_LAUNCH_CHECK("window_attn_tc3_kernel");
 #ifdef T3_TRACE
   if (a.trace) {
