@@ -641,6 +641,7 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         // announce this warp's P rows to the warpgroup's MMA-issuing warp and move on to the next chunk
         if (lane == 0) mbar_arrive(&p_ready[g * 2 + buf]);
       }
+      T3_STAMP(7, n - 1);
       have_prev = true;
       ++ntile_done;
       prev_store = wvalid && i < N;

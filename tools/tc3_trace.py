@@ -14,7 +14,8 @@ for w in range(4 * g, 4 * g + 4):
         if ev[0, n] == 0: break
         e = ev[:, n]
         nxt = ev[0, n + 1] if n + 1 < ev.shape[1] and ev[0, n + 1] else 0
-        print(f"   {n:3d} {e[0]-t0:8d} | {e[1]-e[0]:6d} | {e[2]-e[1]:6d} | {e[3]-e[2]:6d} | {(nxt - e[0]) if nxt else 0:6d}")
+        tail = f" | tile end -> next item {nxt - e[7]:6d}" if e[7] and nxt else ""
+        print(f"   {n:3d} {e[0]-t0:8d} | {e[1]-e[0]:6d} | {e[2]-e[1]:6d} | {e[3]-e[2]:6d} | {(nxt - e[0]) if nxt else 0:6d}{tail}")
 ev = a[12 + g]
 print(f"issuer warp {12 + g}:  item | P wait begins | wait P | P.V issue | look-ahead Q.K^T issue | S(n+2) ready after P(n) ready (softmax warp {4*g} view)")
 for n in range(8, min(40, ev.shape[1])):
