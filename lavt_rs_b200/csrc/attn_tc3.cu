@@ -338,6 +338,8 @@ window_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                      // barriers, TMEM and the zeroed table are set up under the previous kernel's tail
+  pdl_launch_dependents();
 
   // Register split (the launch grants 128 per thread): the control warpgroup (issuers + producer) keeps 56, each softmax warpgroup
   // grows to 152:  3 x 128 x 152 + 128 x 56 = 65 536.
@@ -782,7 +784,7 @@ int window_attn_tc3_dispatch(const AttnParams& p, cudaStream_t st) {
     LAVT_CUDA(cudaMemsetAsync(a.trace, 0, trace_n * sizeof(long long), st));
   }
 #endif
-  kfn<<<grid, T3_THREADS, smem, st>>>(tm_kv, tm_q, tm_tail, p, a);
+  LAVT_CUDA(launch_pdl(kfn, dim3(grid), dim3(T3_THREADS), smem, st, 1, tm_kv, tm_q, tm_tail, p, a));
   LAVT_LAUNCH_CHECK("window_attn_tc3_kernel");
 #ifdef T3_TRACE
   if (a.trace) {

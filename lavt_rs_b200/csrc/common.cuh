@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define LAVT_OK 0
 #define LAVT_ERR_SHAPE 1    // unsupported shape / argument
@@ -53,6 +54,44 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may START (CTAs become
+// resident, barriers / TMEM / descriptors are set up) while the previous kernel of the stream is still draining its last tiles; it must
+// execute griddepcontrol.wait before it touches anything that kernel produced.  Every kernel below orders it as
+//     prologue that reads no global data  ->  pdl_wait()  ->  pdl_launch_dependents()  ->  work
+// (signalling only AFTER the own wait keeps the chain transitive: the next kernel never starts before the one before this one finished).
+// Both instructions are no-ops in a launch without the attribute, which is the default: LAVT_PDL=1 turns it on (measured slower, runtime.cu).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------

@@ -177,6 +177,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (CTA2) tmem_alloc_2cta(tmem_ptr_smem, ACC * GEMM_BN);
     else tmem_alloc(tmem_ptr_smem, ACC * GEMM_BN);  // ACC fp32 accumulators of GEMM_BN columns
   }
+  pdl_wait();                      // everything above touched no global data: it overlaps the previous kernel's tail
+  pdl_launch_dependents();
   if (vec_all) {
     // column scale / bias of ALL N columns staged once per CTA: the epilogue never waits on global memory for them
     float* vec = reinterpret_cast<float*>(smem + L::VEC_OFF);
@@ -540,24 +542,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     LAVT_CUDA(cudaMalloc(&trace, 6 * 32 * sizeof(long long)));
     LAVT_CUDA(cudaMemsetAsync(trace, 0, 6 * 32 * sizeof(long long), stream));
   }
-  if constexpr (CTA2) {
-    cudaLaunchConfig_t cfg;
-    std::memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(L::THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LAVT_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, p, m_tiles, vec_all, trace));
-  } else {
-    kfn<<<grid, L::THREADS, smem, stream>>>(tmA, tmB, p, m_tiles, vec_all, trace);
-  }
+  LAVT_CUDA(launch_pdl(kfn, dim3(grid), dim3(L::THREADS), smem, stream, CTA2 ? 2 : 1, tmA, tmB, p, m_tiles, vec_all, trace));
   LAVT_LAUNCH_CHECK("gemm_bf16_tc_kernel");
   if (trace) {
     // debug only: synchronous dump of CTA 0's event clocks (rows: acc free, first operands, MMAs issued, acc ready, epilogue end, first TMA)

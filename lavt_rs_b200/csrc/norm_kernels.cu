@@ -19,6 +19,8 @@ namespace lavt {
 // 32 lanes of a one-row warp (at C = 128 that index arithmetic, not memory, bounded the gather kernel).
 template <int MODE, int NV, int RPW>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long m0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (m0 >= p.M) return;
@@ -118,7 +120,7 @@ static void launch_ln_nv(const LnParams& p, cudaStream_t st) {
   const int warps = 8;
   const long long rows_per_block = static_cast<long long>(warps) * RPW;
   const long long blocks = (p.M + rows_per_block - 1) / rows_per_block;
-  ln_rows_kernel<MODE, NV, RPW><<<dim3(static_cast<unsigned>(blocks)), 256, 0, st>>>(p);
+  launch_pdl(ln_rows_kernel<MODE, NV, RPW>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, 1, p);
 }
 
 template <int MODE>
