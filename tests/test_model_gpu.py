@@ -671,3 +671,22 @@ def test_image_model_flag_variants(flags, cfgkw):
         assert rel_l2(feats[i], cap[name]) < 3e-2, (name, rel_l2(feats[i], cap[name]))
     assert low.shape == cap["logits_lowres"].shape and rel_l2(low, cap["logits_lowres"]) < 3e-2
     assert logits.shape == ref_logits.shape and rel_l2(logits, ref_logits) < 3e-2
+
+
+@pytest.mark.parametrize("n,ph,pw,H,W,C1,C2", [(3, 12, 12, 24, 24, 64, 32), (2, 6, 9, 12, 18, 128, 8), (2, 2, 2, 4, 4, 8, 8), (2, 5, 7, 12, 15, 64, 16),
+                                               (1, 24, 24, 24, 24, 32, 16)])
+def test_upsample_concat_matches_torch(n, ph, pw, H, W, C1, C2):
+    """cat[bilinear(prev -> (H, W), align_corners=True), skip] (reference lib/mask_predictor.py:58-61) -- the exact-x2 kernel (2 x 2 outputs per
+    thread, 3 x 3 shared taps), the general per-pixel kernel (non-integer ratios) and the same-size copy path, against F.interpolate on the
+    same bf16 inputs.  Tolerance: one bf16 rounding of the blended value."""
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(n * 100 + H)
+    prev = torch.randn(n, ph, pw, C1, generator=g).cuda().to(torch.bfloat16)
+    skip = torch.randn(n, H, W, C2, generator=g).cuda().to(torch.bfloat16)
+    out = torch.empty(n, H, W, C1 + C2, device="cuda", dtype=torch.bfloat16)
+    K.upsample_concat(prev, skip, out)
+    up = torch.nn.functional.interpolate(prev.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = torch.cat([up, skip.float()], -1)
+    assert torch.equal(out[..., C1:], skip)
+    err = (out.float() - ref).abs()
+    assert (err <= 8e-3 * ref.abs() + 1e-3).all(), err.max().item()

@@ -15,3 +15,7 @@ for (n,H,ph,C1,C2) in [(64,96,48,512,128),(64,48,24,512,256),(64,24,12,1024,512)
     us=t(lambda: K.upsample_concat(prev,skip,out))
     byt=out.numel()*2+skip.numel()*2+prev.numel()*2
     print(f"upsample_concat {H}x{H} C{C1}+{C2}: {us:.1f} us  {byt/us/1e3:.0f} GB/s")
+# reference points on the same buffers: a plain device copy of the output-sized tensor (read + write) and a fill (write only)
+    src = torch.empty_like(out)
+    us_c = t(lambda: out.copy_(src)); us_f = t(lambda: out.zero_())
+    print(f"   copy of the output tensor: {us_c:.1f} us  {2*out.numel()*2/us_c/1e3:.0f} GB/s   fill: {us_f:.1f} us  {out.numel()*2/us_f/1e3:.0f} GB/s")
