@@ -10,6 +10,8 @@
 //   pwam_mul           vis * InstanceNorm(lang_pre)  -> bf16 A operand of project_mm (:929-930)
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace lavt {
 
 // NV = float4 slots per lane: Cn <= NV * 128 (a lane's slot i covers channels [(i*32+lane)*4, +4); slots past Cn are
@@ -115,6 +117,84 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnParams p) {
   }
 }
 
+// Narrow rows (C = 128 / 256, stages 0 / 1: 590 K / 147 K rows per 8-clip step): LPR = C / 16 lanes share a row (4 float4 per lane), a warp
+// works on 32 / LPR rows at once and G such row sets per warp.  A row's two reductions cost log2(LPR) shuffle steps that serve 32 / LPR rows
+// per instruction: 1.5 (C = 128) / 4 (C = 256) warp shuffles per row instead of 10.  ncu on the one-row-per-warp kernel at C = 128: issue
+// slots 59 %, short-scoreboard (shuffle) stalls 33 %, DRAM 50 % -- as much shuffle- as bandwidth-bound.
+template <int MODE, int LPR, int G>
+__global__ void __launch_bounds__(256) ln_rows_narrow_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int RPS = 32 / LPR;                     // rows per set
+  const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
+  const long long m0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPS * G);
+  if (m0 >= p.M) return;
+  const int Cn = p.C;                               // == 16 * LPR
+  const float inv_cn = 1.0f / static_cast<float>(Cn);
+  float4 v[G][4];
+  bool live[G], inrange[G];
+  long long myrow = -1;                              // closed-form window gather: lane l evaluates row m0 + l once, the sub-groups fetch theirs
+  if (MODE == MODE_WINDOW) {
+    if (lane < RPS * G && m0 + lane < p.M) myrow = win_token(p.win, m0 + lane).row;
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const long long m = m0 + g * RPS + sr;
+    inrange[g] = m < p.M;
+    long long row = inrange[g] ? m : p.M - 1;
+    if (MODE == MODE_WINDOW) row = __shfl_sync(0xffffffffu, myrow, g * RPS + sr);
+    live[g] = inrange[g] && row >= 0;
+    const float4* src = reinterpret_cast<const float4*>(p.x + (row < 0 ? 0 : row) * p.ldx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[g][i] = live[g] ? __ldg(src + i * LPR + sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 gm[4], bt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + i * LPR + sl);
+    bt[i] = __ldg(reinterpret_cast<const float4*>(p.beta) + i * LPR + sl);
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += (v[g][i].x + v[g][i].y) + (v[g][i].z + v[g][i].w);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_cn;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[g][i].x - mean, b = v[g][i].y - mean, c = v[g][i].z - mean, d = v[g][i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_cn + p.eps);
+    const long long m = m0 + g * RPS + sr;
+    if (!inrange[g]) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);             // window pad row: zeros AFTER the norm
+      if (live[g]) {
+        y.x = (v[g][i].x - mean) * rstd * gm[i].x + bt[i].x;
+        y.y = (v[g][i].y - mean) * rstd * gm[i].y + bt[i].y;
+        y.z = (v[g][i].z - mean) * rstd * gm[i].z + bt[i].z;
+        y.w = (v[g][i].w - mean) * rstd * gm[i].w + bt[i].w;
+      }
+      if (p.out_bf16) reinterpret_cast<uint2*>(p.out_bf16 + m * Cn)[i * LPR + sl] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+      if (p.out_f32) reinterpret_cast<float4*>(p.out_f32 + m * Cn)[i * LPR + sl] = y;
+    }
+  }
+}
+
+template <int MODE, int LPR, int G>
+static void launch_ln_narrow(const LnParams& p, cudaStream_t st) {
+  const long long rows_per_block = 8LL * (32 / LPR) * G;
+  const long long blocks = (p.M + rows_per_block - 1) / rows_per_block;
+  launch_pdl(ln_rows_narrow_kernel<MODE, LPR, G>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, 1, p);
+}
+
 template <int MODE, int NV, int RPW>
 static void launch_ln_nv(const LnParams& p, cudaStream_t st) {
   const int warps = 8;
@@ -126,6 +206,18 @@ static void launch_ln_nv(const LnParams& p, cudaStream_t st) {
 template <int MODE>
 static int launch_ln(const LnParams& p, int Cn, cudaStream_t st) {
   LAVT_REQUIRE((p.M + 7) / 8 < (1LL << 31), "layernorm: too many rows");
+  if constexpr (MODE != MODE_MERGE) {
+    static int narrow = -1;
+    if (narrow < 0) {
+      const char* e = getenv("LAVT_LN_NARROW");       // A/B runs: 0 = one row per warp everywhere
+      narrow = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (narrow && (Cn == 128 || Cn == 256)) {
+      if (Cn == 128) launch_ln_narrow<MODE, 8, 2>(p, st); else launch_ln_narrow<MODE, 16, 4>(p, st);
+      LAVT_LAUNCH_CHECK("ln_rows_narrow_kernel");
+      return LAVT_OK;
+    }
+  }
   switch ((Cn + 127) / 128) {   // rows per warp chosen so that the row data of a warp stays in registers (<= 16 float4 per lane)
     case 1: launch_ln_nv<MODE, 1, 8>(p, st); break;
     case 2: launch_ln_nv<MODE, 2, 8>(p, st); break;
