@@ -346,22 +346,37 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __re
   }
 }
 
+// grid (C / 32, B), 256 threads = 8 chunk slices x 32 channels: slice s sums the partials of chunks s, s + 8, ... in double, the slices are
+// combined in a fixed order (deterministic).  (One thread per channel walking all chunks serially took 43 us for 288 chunks per clip.)
 __global__ void __launch_bounds__(256) colstats_final_kernel(const float* __restrict__ x, const float* __restrict__ part,
                                                              float* __restrict__ stats, int n, int C, int chunks, float eps) {
+  __shared__ double sa[8][32], sq[8][32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float pivot = x[static_cast<long long>(b) * n * C + c];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double a = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    const float* o = part + ((static_cast<long long>(b) * chunks + k) * 2) * C;
-    a += o[c];
-    q += o[C + c];
+  if (c < C) {
+    for (int k = sl; k < chunks; k += 8) {
+      const float* o = part + ((static_cast<long long>(b) * chunks + k) * 2) * C;
+      a += o[c];
+      q += o[C + c];
+    }
   }
-  const double m1 = a / n;
-  const double var = fmax(q / n - m1 * m1, 0.0);
-  stats[(static_cast<long long>(b) * 2 + 0) * C + c] = pivot + static_cast<float>(m1);
-  stats[(static_cast<long long>(b) * 2 + 1) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  sa[sl][cl] = a;
+  sq[sl][cl] = q;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      a += sa[k][cl];
+      q += sq[k][cl];
+    }
+    const float pivot = x[static_cast<long long>(b) * n * C + c];
+    const double m1 = a / n;
+    const double var = fmax(q / n - m1 * m1, 0.0);
+    stats[(static_cast<long long>(b) * 2 + 0) * C + c] = pivot + static_cast<float>(m1);
+    stats[(static_cast<long long>(b) * 2 + 1) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 long long colstats_workspace_floats(int B, long long n, int C) {
@@ -380,7 +395,7 @@ int colstats_dispatch(const float* x, float* stats, float* workspace, int B, lon
   const size_t smem = static_cast<size_t>(rg) * C * 2 * sizeof(float);   // <= 8 KB
   colstats_partial_kernel<<<dim3(chunks, B), 256, smem, st>>>(x, workspace, n, C, chunks);
   LAVT_LAUNCH_CHECK("colstats_partial_kernel");
-  colstats_final_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(x, workspace, stats, n, C, chunks, eps);
+  colstats_final_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(x, workspace, stats, n, C, chunks, eps);
   LAVT_LAUNCH_CHECK("colstats_final_kernel");
   return LAVT_OK;
 }

@@ -690,3 +690,22 @@ def test_upsample_concat_matches_torch(n, ph, pw, H, W, C1, C2):
     assert torch.equal(out[..., C1:], skip)
     err = (out.float() - ref).abs()
     assert (err <= 8e-3 * ref.abs() + 1e-3).all(), err.max().item()
+
+
+@pytest.mark.parametrize("B,n,C", [(2, 1000, 128), (3, 73, 96), (1, 5000, 1024), (8, 2304, 256)])
+def test_instnorm_stats_matches_torch(B, n, C):
+    """InstanceNorm1d statistics over the tokens of a clip (reference lib/video_swin_transformer.py:959-962): mean and 1 / sqrt(var + eps) per
+    (clip, channel), two deterministic stages (pivot-shifted per-chunk sums, then a sliced reduction in double)."""
+    from lavt_rs_b200 import _cabi as K
+    g = torch.Generator().manual_seed(B * 7 + C)
+    x = (torch.randn(B, n, C, generator=g) * 1.7 + torch.randn(1, 1, C, generator=g) * 5).cuda()
+    stats = torch.empty(B, 2, C, device="cuda")
+    ws = torch.empty(K.instnorm_workspace_floats(B, n, C), device="cuda")
+    K.instnorm_stats(x, stats, ws)
+    mean = x.double().mean(1)
+    rstd = 1.0 / torch.sqrt(x.double().var(1, unbiased=False) + 1e-5)
+    assert (stats[:, 0].double() - mean).abs().max().item() < 1e-4
+    assert ((stats[:, 1].double() - rstd).abs() / rstd).max().item() < 1e-4
+    stats2 = torch.empty_like(stats)
+    K.instnorm_stats(x, stats2, ws)
+    assert torch.equal(stats, stats2)           # deterministic: no atomics
