@@ -225,9 +225,44 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(const float* __res
   o[plane] = w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
 }
 
+// four consecutive output pixels of a row per thread (W % 4 == 0): the row taps are shared and each class is written with one 16-byte store
+// (one 4-byte store per pixel and class ran at 1.1 TB/s: 74 us for the 75 MB of full-resolution logits of 8 clips)
+__global__ void __launch_bounds__(256) upsample_logits4_kernel(const float* __restrict__ in, float* __restrict__ out, int n_img,
+                                                               int h, int w, int H, int W) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int W4 = W >> 2;
+  const long long total = static_cast<long long>(n_img) * H * W4;
+  if (idx >= total) return;
+  const int x4 = static_cast<int>(idx % W4) * 4, y = static_cast<int>((idx / W4) % H);
+  const long long img = idx / (static_cast<long long>(W4) * H);
+  int y0, y1; float fy;
+  bilinear_taps(y, h, H, y0, y1, fy);
+  const float2* r0 = reinterpret_cast<const float2*>(in) + (img * h + y0) * w;
+  const float2* r1 = reinterpret_cast<const float2*>(in) + (img * h + y1) * w;
+  float o0[4], o1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int x0, x1; float fx;
+    bilinear_taps(x4 + k, w, W, x0, x1, fx);
+    const float2 a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    o0[k] = w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+    o1[k] = w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+  }
+  const long long plane = static_cast<long long>(H) * W;
+  float* o = out + img * 2 * plane + static_cast<long long>(y) * W + x4;
+  *reinterpret_cast<float4*>(o) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+  *reinterpret_cast<float4*>(o + plane) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+}
+
 int upsample_logits_dispatch(const float* in, float* out, int n_img, int h, int w, int H, int W, cudaStream_t st) {
   const long long total = static_cast<long long>(n_img) * H * W;
   LAVT_REQUIRE(total > 0 && h > 0 && w > 0, "upsample_logits: empty input");
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    upsample_logits4_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(in, out, n_img, h, w, H, W);
+    LAVT_LAUNCH_CHECK("upsample_logits4_kernel");
+    return LAVT_OK;
+  }
   upsample_logits_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, n_img, h, w, H, W);
   LAVT_LAUNCH_CHECK("upsample_logits_kernel");
   return LAVT_OK;

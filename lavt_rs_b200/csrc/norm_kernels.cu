@@ -297,9 +297,16 @@ int im2col_patch4_dispatch(const float* x, long long sB, long long sC, long long
 //         E[x^2]-E[x]^2 cancellation);  pass 2: deterministic reduction over chunks -> mean, rstd.
 // ---------------------------------------------------------------------------------------------
 constexpr int CS_ROWS_PER_BLOCK = 256;
+// rows per block: 256 while that still gives every SM several blocks, fewer for short clips (stage 2 / 3 of the bench have 4608 / 1152 tokens
+// per clip: with 256-row chunks those launches ran 144 / 40 blocks and took 41 / 76 us for 75 / 38 MB)
+static int cs_rows_per_block(int B, long long n) {
+  int rows = CS_ROWS_PER_BLOCK;
+  while (rows > 16 && static_cast<long long>(B) * ((n + rows - 1) / rows) < 592) rows >>= 1;
+  return rows;
+}
 
 __global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __restrict__ x, float* __restrict__ part,
-                                                               int n, int C, int chunks) {
+                                                               int n, int C, int chunks, int rows_per_block) {
   // grid: (chunks, B).  thread -> 4 channels (one float4); row groups stride over the chunk's rows
   extern __shared__ float sm[];   // [rowgroups][C][2]
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -309,8 +316,8 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const float* __re
   const float* base = x + static_cast<long long>(b) * n * C;
   const float4 pv = __ldg(reinterpret_cast<const float4*>(base) + tc);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  const int r0 = chunk * CS_ROWS_PER_BLOCK;
-  const int r1 = min(n, r0 + CS_ROWS_PER_BLOCK);
+  const int r0 = chunk * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
   if (tr < rg) {
     int r = r0 + tr;
     for (; r + 3 * rg < r1; r += 4 * rg) {      // 4 independent 16-byte loads in flight per thread
@@ -380,7 +387,8 @@ __global__ void __launch_bounds__(256) colstats_final_kernel(const float* __rest
 }
 
 long long colstats_workspace_floats(int B, long long n, int C) {
-  const long long chunks = (n + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  const int rows = cs_rows_per_block(B, n);
+  const long long chunks = (n + rows - 1) / rows;
   return static_cast<long long>(B) * chunks * 2 * C;
 }
 
@@ -389,11 +397,12 @@ int colstats_dispatch(const float* x, float* stats, float* workspace, int B, lon
   const int n = static_cast<int>(n_ll);
   LAVT_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "instance-norm stats: C=%d unsupported", C);
   LAVT_REQUIRE(B > 0 && n > 0, "instance-norm stats: empty input");
-  const int chunks = (n + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  const int rows = cs_rows_per_block(B, n);
+  const int chunks = (n + rows - 1) / rows;
   const int tpr = C / 4;
   const int rg = 256 / tpr;
   const size_t smem = static_cast<size_t>(rg) * C * 2 * sizeof(float);   // <= 8 KB
-  colstats_partial_kernel<<<dim3(chunks, B), 256, smem, st>>>(x, workspace, n, C, chunks);
+  colstats_partial_kernel<<<dim3(chunks, B), 256, smem, st>>>(x, workspace, n, C, chunks, rows);
   LAVT_LAUNCH_CHECK("colstats_partial_kernel");
   colstats_final_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(x, workspace, stats, n, C, chunks, eps);
   LAVT_LAUNCH_CHECK("colstats_final_kernel");

@@ -8,30 +8,47 @@
 
 namespace lavt {
 
-// grid (Nl, B, ceil(2C / 64)), block 256: smem holds the word vector l[b, :, j]; each warp produces 8 of the block's 64
-// outputs (k channels first, then v channels)
+// grid (ceil(B * Nl / 8), ceil(2C / 64)), block 256: smem holds the word vectors l[b, :, j] of EIGHT (clip, word) pairs; each warp produces
+// 8 of the block's 64 outputs (k channels first, then v channels) for all eight pairs, so a weight row is read once per 8 pairs (one pair per
+// block re-read the 2C x 768 weights 160 times: 121 us at C = 1024).
+constexpr int KV_PAIRS = 8;
 __global__ void __launch_bounds__(256) pwam_kv_kernel(const float* __restrict__ l, const float* __restrict__ mask,
                                                       const float* __restrict__ wk, const float* __restrict__ bk,
                                                       const float* __restrict__ wv, const float* __restrict__ bv,
-                                                      float* __restrict__ k, float* __restrict__ v, int Nl, int Lin, int C) {
-  extern __shared__ float lv[];
-  const int j = blockIdx.x, b = blockIdx.y;
-  for (int i = threadIdx.x; i < Lin; i += blockDim.x) lv[i] = l[(static_cast<long long>(b) * Lin + i) * Nl + j];
+                                                      float* __restrict__ k, float* __restrict__ v, int B, int Nl, int Lin, int C) {
+  extern __shared__ float lv[];                 // [KV_PAIRS][Lin]
+  const int p0 = blockIdx.x * KV_PAIRS, npairs = B * Nl;
+  for (int i = threadIdx.x; i < KV_PAIRS * Lin; i += blockDim.x) {
+    const int q = i / Lin, ii = i - q * Lin;
+    const int pr = min(p0 + q, npairs - 1);
+    const int b = pr / Nl, j = pr - b * Nl;
+    lv[i] = l[(static_cast<long long>(b) * Lin + ii) * Nl + j];
+  }
   __syncthreads();
-  const float m = mask[b * Nl + j];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int cbeg = blockIdx.z * 64;
+  const int cbeg = blockIdx.y * 64;
   const int cend = min(2 * C, cbeg + 64);
   for (int c = cbeg + warp; c < cend; c += nw) {
     const bool is_v = c >= C;
     const int cc = is_v ? c - C : c;
     const float* w = (is_v ? wv : wk) + static_cast<long long>(cc) * Lin;
-    float acc = 0.f;
-    for (int i = lane; i < Lin; i += 32) acc = fmaf(__ldg(w + i), lv[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
+    float acc[KV_PAIRS];
+#pragma unroll
+    for (int q = 0; q < KV_PAIRS; ++q) acc[q] = 0.f;
+    for (int i = lane; i < Lin; i += 32) {
+      const float wi = __ldg(w + i);
+#pragma unroll
+      for (int q = 0; q < KV_PAIRS; ++q) acc[q] = fmaf(wi, lv[q * Lin + i], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < KV_PAIRS; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane < KV_PAIRS && p0 + lane < npairs) {
+      float a = acc[0];
+#pragma unroll
+      for (int q = 1; q < KV_PAIRS; ++q) a = lane == q ? acc[q] : a;
+      const int pr = p0 + lane;
       const float bias = is_v ? bv[cc] : bk[cc];
-      (is_v ? v : k)[(static_cast<long long>(b) * Nl + j) * C + cc] = (acc + bias) * m;
+      (is_v ? v : k)[static_cast<long long>(pr) * C + cc] = (a + bias) * mask[pr];
     }
   }
 }
@@ -39,8 +56,9 @@ __global__ void __launch_bounds__(256) pwam_kv_kernel(const float* __restrict__ 
 int pwam_kv_dispatch(const float* l, const float* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                      float* k, float* v, int B, int Nl, int Lin, int C, cudaStream_t st) {
   LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0, "pwam_kv: empty input");
-  LAVT_REQUIRE(Lin * sizeof(float) <= 48 * 1024, "pwam_kv: language width %d too large", Lin);
-  pwam_kv_kernel<<<dim3(Nl, B, (2 * C + 63) / 64), 256, Lin * sizeof(float), st>>>(l, mask, wk, bk, wv, bv, k, v, Nl, Lin, C);
+  LAVT_REQUIRE(KV_PAIRS * Lin * sizeof(float) <= 48 * 1024, "pwam_kv: language width %d too large", Lin);
+  pwam_kv_kernel<<<dim3((B * Nl + KV_PAIRS - 1) / KV_PAIRS, (2 * C + 63) / 64), 256, KV_PAIRS * Lin * sizeof(float), st>>>(l, mask, wk, bk, wv, bv,
+                                                                                                                     k, v, B, Nl, Lin, C);
   LAVT_LAUNCH_CHECK("pwam_kv_kernel");
   return LAVT_OK;
 }
