@@ -360,8 +360,12 @@ static int launch_pwam_mma(const float* qpre, const float* stats, const float* k
     LAVT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  const long long blocks = (n + 127) / 128;
-  kfn<<<dim3(static_cast<unsigned>(blocks), B), 256, smem, st>>>(qpre, stats, k, v, mask, o, n, C, Nl, heads, scale);
+  // 16 pixels per warp; 8 warps per block while that still gives every SM two blocks, fewer for short clips (stage 3 of the bench: 1152
+  // tokens per clip ran as 72 blocks of 128 pixels, 77 us)
+  int warps = 8;
+  while (warps > 2 && static_cast<long long>(B) * ((n + 16 * warps - 1) / (16 * warps)) < 296) warps >>= 1;
+  const long long blocks = (n + 16 * warps - 1) / (16 * warps);
+  kfn<<<dim3(static_cast<unsigned>(blocks), B), 32 * warps, smem, st>>>(qpre, stats, k, v, mask, o, n, C, Nl, heads, scale);
   LAVT_LAUNCH_CHECK("pwam_core_mma_kernel");
   return LAVT_OK;
 }
