@@ -320,7 +320,8 @@ int lavt_pwam_kv_bwd(const float* dkbuf, const float* dvbuf, const float* mask, 
  *   mode 3: out_bf16 = GELU(a), out_f32 = the same                (a = bf16 pre-activation)
  *   mode 4: out_bf16 = f * GELU'(a)                               (f = fp32 gradient)
  *   mode 5: out_bf16 = out_f32 = GELU(a) + f                      (SepTPWAM: sum of the temporal and spatial GELU'd branches)
- *   mode 6: out_f32 = f + f2                                      (--version no_gate: x' = x + r; a = any bf16 tensor of that size) */
+ *   mode 6: out_f32 = f + f2                                      (--version no_gate: x' = x + r; a = any bf16 tensor of that size)
+ *   mode 7 / 8: modes 0 / 1 with a sigmoid instead of a tanh gate (--lg_act_layer sigmoid, reference lib/backbone.py:552-554) */
 int lavt_gate_elementwise(int32_t mode, const void* a_bf16, const void* b_bf16, const float* f, const float* f2, void* out_bf16,
                           float* out_f32, int64_t count, void* stream);
 

@@ -444,6 +444,7 @@ int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* ma
 // mode 4: out_bf16 = f * GELU'(a)                                        (GELU backward with an fp32 gradient)
 // mode 5: out_bf16 = out_f32 = GELU(a) + f                               (SepTPWAM: sum of the two GELU'd branches)
 // mode 6: out_f32 = f + f2                                               (--version no_gate: x' = x + r, and its adjoint dr += dx')
+// mode 7 / 8: modes 0 / 1 with a sigmoid gate (--lg_act_layer sigmoid, reference lib/backbone.py:552-554): g = sigmoid(a), g' = g (1 - g)
 template <int MODE>
 __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ f,
                                                         const float4* __restrict__ f2, uint4* __restrict__ out_bf16,
@@ -457,19 +458,19 @@ __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w[j]); av[2 * j] = t.x; av[2 * j + 1] = t.y; }
   }
-  if (MODE <= 2) {
+  if (MODE <= 2 || MODE == 7 || MODE == 8) {
     const uint4 u = __ldg(b + i);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w[j]); bv[2 * j] = t.x; bv[2 * j + 1] = t.y; }
   }
-  if (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5 || MODE == 6) {
+  if (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5 || MODE == 6 || MODE == 7 || MODE == 8) {
     const float4 x0 = __ldg(f + 2 * i), x1 = __ldg(f + 2 * i + 1);
     fv[0] = x0.x; fv[1] = x0.y; fv[2] = x0.z; fv[3] = x0.w; fv[4] = x1.x; fv[5] = x1.y; fv[6] = x1.z; fv[7] = x1.w;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) gv[j] = 0.f;
-  if ((MODE == 1 || MODE == 6) && f2) {
+  if ((MODE == 1 || MODE == 6 || MODE == 8) && f2) {
     const float4 x0 = __ldg(f2 + 2 * i), x1 = __ldg(f2 + 2 * i + 1);
     gv[0] = x0.x; gv[1] = x0.y; gv[2] = x0.z; gv[3] = x0.w; gv[4] = x1.x; gv[5] = x1.y; gv[6] = x1.z; gv[7] = x1.w;
   }
@@ -484,9 +485,11 @@ __global__ void __launch_bounds__(256) gate_elem_kernel(const uint4* __restrict_
     if (MODE == 4) ob[j] = fv[j] * gelu_grad(av[j]);
     if (MODE == 5) { ob[j] = gelu_erf(av[j]) + fv[j]; of[j] = ob[j]; }
     if (MODE == 6) of[j] = fv[j] + gv[j];
+    if (MODE == 7) of[j] = fv[j] + bv[j] / (1.0f + __expf(-av[j]));
+    if (MODE == 8) { const float t = 1.0f / (1.0f + __expf(-av[j])); ob[j] = fv[j] * bv[j] * t * (1.0f - t); of[j] = gv[j] + fv[j] * t; }
   }
-  if (MODE != 0 && MODE != 6) out_bf16[i] = make_uint4(pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]), pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
-  if (MODE == 0 || MODE == 1 || MODE == 3 || MODE == 5 || MODE == 6) {
+  if (MODE != 0 && MODE != 6 && MODE != 7) out_bf16[i] = make_uint4(pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]), pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
+  if (MODE == 0 || MODE == 1 || MODE == 3 || MODE == 5 || MODE == 6 || MODE == 7 || MODE == 8) {
     out_f32[2 * i] = make_float4(of[0], of[1], of[2], of[3]);
     out_f32[2 * i + 1] = make_float4(of[4], of[5], of[6], of[7]);
   }
@@ -511,6 +514,8 @@ int gate_elem_dispatch(int mode, const __nv_bfloat16* a, const __nv_bfloat16* b,
     case 4: LAVT_REQUIRE(a && f && out_bf16, "gelu backward: missing tensor"); gate_elem_kernel<4><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     case 5: LAVT_REQUIRE(a && f && out_bf16 && out_f32, "gelu sum: missing tensor"); gate_elem_kernel<5><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     case 6: LAVT_REQUIRE(a && f && g4 && out_f32, "add: missing tensor"); gate_elem_kernel<6><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 7: LAVT_REQUIRE(a && b && f && out_f32, "sigmoid gate apply: missing tensor"); gate_elem_kernel<7><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
+    case 8: LAVT_REQUIRE(a && b && f && out_bf16 && out_f32, "sigmoid gate backward: missing tensor"); gate_elem_kernel<8><<<grid, 256, 0, st>>>(a4, b4, f4, g4, ob, of, c8); break;
     default: set_last_error("gate kernels: bad mode %d", mode); return LAVT_ERR_SHAPE;
   }
   LAVT_LAUNCH_CHECK("gate_elem_kernel");

@@ -336,7 +336,8 @@ def _nl_pad(Nl: int) -> int:
     return (Nl + 7) // 8 * 8
 
 
-def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace):
+def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace,
+                  gate_act: str = "tanh"):
     """x fp32 [B*n, C] (not modified), xb = its bf16 copy, l fp32 [B,768,Nl], mask fp32 [B,Nl].
     Returns (r fp32 [B*n, C] = x_residual, x' fp32 = gated x or None without a gate, saved)."""
     N_, C = x.shape
@@ -388,12 +389,12 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         g1 = torch.empty(N_, C, device=dev, dtype=bf)
         K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
         g2 = torch.empty(N_, C, device=dev, dtype=bf)
-        K.gemm_bf16(g1, g2w, out_bf16=g2)       # PRE-activation of the tanh (saved); tanh is applied by the elementwise kernel
+        K.gemm_bf16(g1, g2w, out_bf16=g2)       # PRE-activation of the tanh / sigmoid (saved); the gate is applied by the elementwise kernel
         xg = torch.empty(N_, C, device=dev, dtype=f32)
-        K.gate_elementwise(0, g2, rb, f=x, out_f32=xg)
+        K.gate_elementwise(0 if gate_act == "tanh" else 7, g2, rb, f=x, out_f32=xg)
         _count(3)
     saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
-                 a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w)
+                 a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act)
     return r32, xg, saved
 
 
@@ -416,11 +417,12 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     dr = dr_out
     if res_gate is not None and dxg is not None:
         dg2pre = ws.get("bw_pw_a", (N_, C), bf, dev)
+        gmode = 1 if s.get("gate_act", "tanh") == "tanh" else 8
         if dr is None:
             dr = ws.get("bw_pw_dr", (N_, C), f32, dev)
-            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
+            K.gate_elementwise(gmode, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
         else:
-            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
+            K.gate_elementwise(gmode, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
         dg1 = ws.get("bw_pw_b", (N_, C), bf, dev)
         linear_bwd(dg2pre, s["g1"], res_gate[2].weight, None, grads, ws, pw, "g2", dx_bf16=dg1)
         K.gate_elementwise(2, dg1, s["g1"], out_bf16=dg1)

@@ -35,8 +35,8 @@ def _check_trainable(model) -> None:
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
         if not layer.sep_t_pwam and not layer.fusion.attention:
             raise NotImplementedError("--fuse simple is inference-only on the B200 path")
-        if getattr(layer, "gate_act", "tanh") != "tanh":
-            raise NotImplementedError("--lg_act_layer sigmoid is inference-only on the B200 path (the gate adjoint kernel is the tanh one)")
+        if getattr(layer, "gate_act", "tanh") != "tanh" and layer.sep_t_pwam:
+            raise NotImplementedError("--lg_act_layer sigmoid with SepTPWAM is inference-only on the B200 path")
         if getattr(getattr(layer.fusion, "image_lang_att", None), "att_norm_layer_type", "IN") != "IN":
             raise NotImplementedError("--att_norm_layer_type BN / LN / none is inference-only on the B200 path")
         if layer.version not in ("default", "no_gate", "none"):
@@ -79,7 +79,7 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
         if layer.sep_t_pwam:
             r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
         else:
-            r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws)
+            r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws, gate_act=getattr(layer, "gate_act", "tanh"))
         if layer.version == "no_gate" and (not last or layer.hs):       # ablation: plain residual add x' = x + r (:570-575)
             xg = torch.empty_like(r32)
             K.gate_elementwise(6, pw_saved["rb"], f=feat, f2=r32, out_f32=xg)

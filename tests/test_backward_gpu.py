@@ -248,8 +248,10 @@ def test_patch_merging_backward():
     check_grads(grads.named(ds), pg_ref, "patch merging")
 
 
-@pytest.mark.parametrize("stage,heads,Nl,gate", [(0, 1, 20, True), (1, 4, 13, True), (3, 1, 22, False)])
+@pytest.mark.parametrize("stage,heads,Nl,gate", [(0, 1, 20, True), (1, 4, 13, True), (3, 1, 22, False), (1, 1, 17, "sigmoid")])
 def test_pwam_gate_backward(stage, heads, Nl, gate):
+    gate_act = "sigmoid" if gate == "sigmoid" else "tanh"          # --lg_act_layer sigmoid (reference lib/backbone.py:552-554)
+    gate = bool(gate)
     from lavt_rs_b200 import engine as E
     from lavt_rs_b200 import train_engine as T
     mha = tuple(heads if i == stage else 1 for i in range(4))
@@ -278,7 +280,7 @@ def test_pwam_gate_backward(stage, heads, Nl, gate):
         r = O.pwam(xx, ll, m, sd2, pre + "fusion.", heads)
         if not gate:
             return r
-        return torch.cat([r, O.language_gate(xx, r, sd2, pre + "res_gate.")], 0)
+        return torch.cat([r, O.language_gate(xx, r, sd2, pre + "res_gate.", act=gate_act)], 0)
     gout = torch.cat([gr, gx], 0) if gate else gr
     (dx_ref, dl_ref), pg_ref = _oracle_grads(fn, sd, pre, [x, l], gout)
     pg_ref = {k: v for k, v in pg_ref.items() if k.startswith("fusion.") or (gate and k.startswith("res_gate."))}
@@ -287,7 +289,7 @@ def test_pwam_gate_backward(stage, heads, Nl, gate):
     grads = T.GradStore()
     xf = x.cuda().reshape(-1, C).contiguous()
     r32, xg, saved = T.pwam_gate_fwd(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate if gate else None, l.cuda(),
-                                     m.squeeze(-1).cuda(), B, ws)
+                                     m.squeeze(-1).cuda(), B, ws, gate_act=gate_act)
     ref = fn(sd, x, l)
     assert rel_l2(r32, ref[:B].reshape(-1, C)) < 1.5e-2
     if gate:

@@ -110,12 +110,13 @@ def test_inference_only_variants_refuse_training():
     """The lib/bcam.py fusions and --lazy_pred have no hand-written backward: the training entry point must refuse them up front."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--lazy_pred"], ["--lg_act_layer", "sigmoid"], ["--att_norm_layer_type", "LN"],
-                 ["--interpolate_before_seg"]):
+    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--lazy_pred"], ["--att_norm_layer_type", "LN"], ["--interpolate_before_seg"]):
         m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
+    # the sigmoid gate trains (gate adjoint modes 7 / 8 of lavt_gate_elementwise)
+    training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lg_act_layer", "sigmoid"])))
 
 
 def test_forward_refuses_cpu_tensors():
