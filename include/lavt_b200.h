@@ -246,6 +246,13 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
 int64_t lavt_gemm_splitk_workspace_floats(int32_t M, int32_t N, int32_t K);
 int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t b_koff,
                           float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream);
+/* Small-M forward GEMM (the text encoder's dense layers, bert/modeling_bert.py: 160 rows at 8 clips x 20 tokens): the same product as
+ * lavt_gemm_bf16 computed as a split-K launch that fills the GPU (work item = (tile, k range), fp32 partials in ``workspace``, size from
+ * lavt_gemm_splitk_workspace_floats) followed by one reduce + epilogue kernel (column scale, bias, GELU, fp32 residual; bf16 and / or fp32 out).
+ * Identity row map only. */
+int lavt_gemm_bf16_smallm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                          const lavt_epilogue_t* epi, float* workspace, int64_t workspace_floats, void* stream);
+
 /* dst[n_out, n_in] (+)= dy[tokens, n_out]^T x[tokens, n_in] straight from the ROW-MAJOR activations: TMA boxes of 64 tokens x 64
  * channels land in shared memory as MN-major tcgen05 operands, so no transposed copies are made (split-K over the token axis,
  * workspace as for lavt_gemm_bf16_splitk with M = n_out, N = n_in, K = tokens).  n_out % 8 == 0, n_in % 32 == 0. */

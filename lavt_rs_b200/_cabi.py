@@ -77,6 +77,7 @@ _WG = C.POINTER(WinGeom)
 SIGNATURES = {
     "lavt_check_device": [],
     "lavt_gemm_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _EP, _vp],
+    "lavt_gemm_bf16_smallm": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _EP, _vp, _i64, _vp],
     "lavt_conv3x3_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _EP, _vp],
     "lavt_conv3d_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _EP, _vp],
     "lavt_layernorm_rows": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp],
@@ -151,7 +152,7 @@ SIGNATURES = {
     "lavt_mha_small": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "lavt_gate_transpose": [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
 }
-EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
+EXPORTS = ["lavt_last_error", "lavt_gemm_bf16_smallm", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
            "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
@@ -300,6 +301,21 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, **epi) -> None:
         nbytes = 2.0 * (M * K + N * K) + M * N * ((4.0 if e.out_f32 else 0.0) + (2.0 if e.out_bf16 else 0.0)
                                                    + (4.0 if e.resid else 0.0) + (2.0 if e.mul else 0.0))
         TIMER.end(t0, "gemm_bf16_tc_kernel", 2.0 * M * N * K, nbytes, f"M{M} N{N} K{K} act{e.act}")
+
+
+def gemm_bf16_smallm(a: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, **epi) -> None:
+    """gemm_bf16 for a few rows (the text encoder: M = clips x words): split-K launch that fills the GPU + one reduce / epilogue kernel.
+    ``workspace`` fp32 with at least splitk_workspace_floats(M, N, K) elements; epilogue: cscale, bias, act (none / GELU), resid, out_f32, out_bf16."""
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise LavtError(f"gemm: K mismatch {K} vs {K2}")
+    e = make_epilogue(**epi)
+    check(lib().lavt_gemm_bf16_smallm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(e),
+                                      _c(workspace, torch.float32, "workspace").data_ptr(), workspace.numel(), stream_ptr()),
+          "lavt_gemm_bf16_smallm")
 
 
 def conv3x3_bf16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, **epi) -> None:

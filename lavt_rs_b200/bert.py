@@ -24,6 +24,8 @@ _LOG2E = 1.4426950408889634
 # error is made of (the 24 Swin blocks' bf16 operands are: stage outputs c3 / c4 sit at 1.4e-2 / 1.8e-2 with exact language features),
 # and its 145 launches on the side stream cost 4 % of throughput; so it is an option (validation of the text side), not the default.
 PRECISION = "bf16"
+import os as _os
+SMALL_M = int(_os.environ.get("LAVT_BERT_SMALLM", "512"))          # rows up to which the dense layers run as split-K launches (gemm_bf16_smallm)
 
 
 def set_precision(mode: str) -> str:
@@ -127,25 +129,38 @@ def bert_forward(enc, ids: torch.Tensor, mask: torch.Tensor, out_cf: torch.Tenso
     ctx = ws.get("bert_ctx", (M, H), torch.bfloat16, dev)
     hid = ws.get("bert_hid", (M, cfg.intermediate_size), torch.bfloat16, dev)
     qs = pw.get("qscale", [], lambda: torch.cat([torch.full((H,), 64 ** -0.5 * _LOG2E), torch.ones(2 * H)]).to(dev))
+    # A sentence batch is a few rows (M = clips x words = 160 at 8 clips): as plain launches these GEMMs are 2 x 3..12 output tiles that each
+    # walk up to 48 k-blocks alone (26-43 us per launch, on SMs the backbone's persistent kernels are waiting for); split over K they fill the
+    # GPU and a reduce kernel applies the epilogue.
+    small = M <= SMALL_M
+    I = cfg.intermediate_size
+    skw = ws.get("bert_splitk", (max(K.splitk_workspace_floats(M, n_, k_) for n_, k_ in ((3 * H, H), (H, H), (I, H), (H, I))),),
+                 torch.float32, dev) if small else None
+
+    def gemm(a_, w_, **epi):
+        if small:
+            K.gemm_bf16_smallm(a_, w_, skw, **epi)
+        else:
+            K.gemm_bf16(a_, w_, **epi)
     for i, layer in enumerate(enc.encoder.layer):
         sa, so = layer.attention.self, layer.attention.output
         w_qkv = pw.get(f"qkv_w{i}", [sa.query.weight, sa.key.weight, sa.value.weight],
                        lambda: torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0).detach().to(torch.bfloat16).contiguous())
         b_qkv = pw.get(f"qkv_b{i}", [sa.query.bias, sa.key.bias, sa.value.bias],
                        lambda: (torch.cat([sa.query.bias, sa.key.bias, sa.value.bias]).detach().float() * qs).contiguous())
-        K.gemm_bf16(xb, w_qkv, cscale=qs, bias=b_qkv, out_bf16=qkv)         # q pre-scaled by 64^-0.5 * log2(e)
+        gemm(xb, w_qkv, cscale=qs, bias=b_qkv, out_bf16=qkv)         # q pre-scaled by 64^-0.5 * log2(e)
         K.bert_attention(qkv, maskf, ctx, heads)
         w_o = pw.get(f"o_w{i}", [so.dense.weight], lambda: so.dense.weight.detach().to(torch.bfloat16).contiguous())
-        K.gemm_bf16(ctx, w_o, bias=so.dense.bias.detach(), resid=x, out_f32=x)
+        gemm(ctx, w_o, bias=so.dense.bias.detach(), resid=x, out_f32=x)
         K.layernorm_rows(x, so.LayerNorm.weight.detach(), so.LayerNorm.bias.detach(), out_bf16=xb, out_f32=x, eps=eps)
         w_1 = pw.get(f"fc1_w{i}", [layer.intermediate.dense.weight],
                      lambda: layer.intermediate.dense.weight.detach().to(torch.bfloat16).contiguous())
-        K.gemm_bf16(xb, w_1, bias=layer.intermediate.dense.bias.detach(), act=K.ACT_GELU, out_bf16=hid)
+        gemm(xb, w_1, bias=layer.intermediate.dense.bias.detach(), act=K.ACT_GELU, out_bf16=hid)
         w_2 = pw.get(f"fc2_w{i}", [layer.output.dense.weight], lambda: layer.output.dense.weight.detach().to(torch.bfloat16).contiguous())
-        K.gemm_bf16(hid, w_2, bias=layer.output.dense.bias.detach(), resid=x, out_f32=x)
+        gemm(hid, w_2, bias=layer.output.dense.bias.detach(), resid=x, out_f32=x)
         K.layernorm_rows(x, layer.output.LayerNorm.weight.detach(), layer.output.LayerNorm.bias.detach(), out_bf16=xb, out_f32=x, eps=eps)
     if out_cf is None:
         out_cf = torch.empty(B, H, Nl, device=dev, dtype=torch.float32)
     K.rows_to_channels_first(x.view(B, Nl, H), out_cf)
-    E._count(3 + 7 * layers)
+    E._count(3 + (11 if small else 7) * layers)
     return out_cf

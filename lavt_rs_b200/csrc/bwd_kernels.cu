@@ -35,6 +35,42 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __rest
   *d = a;
 }
 
+// out = act((sum_s partial[s]) * cscale[col] + bias[col]) (+ resid): the epilogue of a split-K forward GEMM (small-M GEMMs of the text encoder:
+// 160 rows give 2 x 3..12 output tiles, each walking up to 48 k-blocks alone -- 26-43 us per launch; split over K they fill the machine)
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float4* __restrict__ part, int splits, long long count4, int ncols4,
+                                                              const float4* __restrict__ cscale, const float4* __restrict__ bias, int act,
+                                                              const float* __restrict__ resid, float* __restrict__ out_f32,
+                                                              __nv_bfloat16* __restrict__ out_bf16, long long ldo) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  float4 a = __ldg(part + i);
+  for (int s2 = 1; s2 < splits; ++s2) {
+    const float4 b = __ldg(part + s2 * count4 + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  const long long row = i / ncols4;
+  const int c4 = static_cast<int>(i - row * ncols4);
+  if (cscale) { const float4 sc = __ldg(cscale + c4); a.x *= sc.x; a.y *= sc.y; a.z *= sc.z; a.w *= sc.w; }
+  if (bias) { const float4 b = __ldg(bias + c4); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+  const long long o = row * ldo + c4 * 4;
+  if (resid) { const float4 r = *reinterpret_cast<const float4*>(resid + o); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = a;
+  if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+}
+
+int splitk_epilogue_dispatch(const float* partials, int splits, long long M, int N, const float* cscale, const float* bias, int act,
+                             const float* resid, float* out_f32, __nv_bfloat16* out_bf16, long long ldo, cudaStream_t st) {
+  LAVT_REQUIRE(N % 4 == 0 && ldo % 4 == 0 && splits >= 1 && (act == 0 || act == 1), "split-K epilogue: bad arguments");
+  const long long c4 = M * N / 4;
+  splitk_epilogue_kernel<<<static_cast<unsigned>((c4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, c4, N / 4,
+                                                                                 reinterpret_cast<const float4*>(cscale),
+                                                                                 reinterpret_cast<const float4*>(bias), act, resid, out_f32,
+                                                                                 out_bf16, ldo);
+  LAVT_LAUNCH_CHECK("splitk_epilogue_kernel");
+  return LAVT_OK;
+}
+
 int splitk_reduce_dispatch(const float* partials, int splits, long long count, int ncols, float* dst, long long ldd, int accumulate,
                            cudaStream_t st) {
   LAVT_REQUIRE(count % 4 == 0 && ncols % 4 == 0 && ldd % 4 == 0, "splitk reduce: sizes must be multiples of 4");

@@ -306,6 +306,31 @@ int lavt_gemm_bf16_splitk(const void* A, int64_t lda, const void* Bt, int64_t ld
   return splitk_reduce_dispatch(workspace, ks, 1LL * M * N, N, dst, ldd, accumulate, S(stream));
 }
 
+int lavt_gemm_bf16_smallm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                          const lavt_epilogue_t* epi, float* workspace, int64_t workspace_floats, void* stream) {
+  GemmParams e;
+  std::memset(&e, 0, sizeof(e));
+  int rc = fill_epilogue(e, epi);
+  if (rc) return rc;
+  LAVT_REQUIRE(e.rowmap == ROWMAP_IDENTITY && !e.mul && !e.rscale && (e.act == 0 || e.act == 1), "small-M gemm: epilogue not supported");
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  int ks, kbs;
+  splitk_plan(M, N, K, &ks, &kbs);
+  LAVT_REQUIRE(workspace && workspace_floats >= 1LL * ks * M * N, "small-M gemm: workspace too small (%lld < %lld floats)",
+               static_cast<long long>(workspace_floats), 1LL * ks * M * N);
+  p.out_f32 = workspace;
+  p.ldo = N;
+  p.rowmap = ROWMAP_IDENTITY;
+  p.ksplit = ks;
+  p.kbs = kbs;
+  p.split_stride = 1LL * M * N;
+  rc = gemm_dispatch(A, lda, Wt, ldw, p, S(stream));
+  if (rc) return rc;
+  return splitk_epilogue_dispatch(workspace, ks, M, N, e.cscale, e.bias, e.act, e.resid, e.out_f32, e.out_bf16, e.ldo, S(stream));
+}
+
 int lavt_gemm_bf16_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t tokens, int32_t n_out, int32_t n_in,
                          float* workspace, int64_t workspace_floats, float* dst, int64_t ldd, int32_t accumulate, void* stream) {
   LAVT_REQUIRE(tokens > 0 && tokens < (1LL << 31), "wgrad gemm: token count out of range");

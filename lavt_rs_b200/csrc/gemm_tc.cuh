@@ -43,6 +43,8 @@ struct GemmParams {
                              //    TMA boxes of 64 k-rows x 64 MN-elements, MN-major shared-memory descriptors, no transposed copies
   int b_koff;                // added to the K coordinate of the B operand (conv weight gradient: tap offset in the padded pixel axis)
 };
+int splitk_epilogue_dispatch(const float* partials, int splits, long long M, int N, const float* cscale, const float* bias, int act,
+                             const float* resid, float* out_f32, __nv_bfloat16* out_bf16, long long ldo, cudaStream_t st);
 int splitk_reduce_dispatch(const float* partials, int splits, long long count, int ncols, float* dst, long long ldd, int accumulate,
                            cudaStream_t st);
 

@@ -140,3 +140,27 @@ def test_gemm_rejects_bad_shapes(cabi):
         cabi.gemm_bf16(a, w, out_bf16=out)          # K % 8 != 0 (TMA needs 16-byte row pitches)
     with pytest.raises(cabi.LavtError):
         cabi.gemm_bf16(a.cpu(), w, out_bf16=out)    # no CPU fallback
+
+
+@pytest.mark.parametrize("M,N,K", [(160, 2304, 768), (160, 768, 3072), (20, 3072, 768), (77, 768, 768)])
+def test_small_m_splitk_gemm_matches_torch(M, N, K):
+    """lavt_gemm_bf16_smallm (the text encoder's dense layers): split-K launch + reduce / epilogue kernel against the fp32 product of the same
+    bf16 operands, with the epilogues BERT uses (column scale + bias -> bf16; bias + GELU -> bf16; bias + fp32 residual in place)."""
+    from lavt_rs_b200 import _cabi as Kx
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).cuda().to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    cs = (torch.rand(N, generator=g) + 0.5).cuda()
+    ws = torch.empty(Kx.splitk_workspace_floats(M, N, K), device="cuda")
+    ref = a.float() @ w.float().t()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    Kx.gemm_bf16_smallm(a, w, ws, cscale=cs, bias=bias, out_bf16=out)
+    assert ((out.float() - (ref * cs + bias)).norm() / (ref * cs + bias).norm()).item() < 4e-3
+    Kx.gemm_bf16_smallm(a, w, ws, bias=bias, act=Kx.ACT_GELU, out_bf16=out)
+    want = torch.nn.functional.gelu(ref + bias)
+    assert ((out.float() - want).norm() / want.norm()).item() < 4e-3
+    x = torch.randn(M, N, generator=g).cuda()
+    x0 = x.clone()
+    Kx.gemm_bf16_smallm(a, w, ws, bias=bias, resid=x, out_f32=x)
+    assert ((x - (x0 + ref + bias)).norm() / (x0 + ref + bias).norm()).item() < 1e-4
