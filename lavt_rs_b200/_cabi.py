@@ -152,7 +152,7 @@ SIGNATURES = {
     "lavt_mha_small": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "lavt_gate_transpose": [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
 }
-EXPORTS = ["lavt_last_error", "lavt_gemm_bf16_smallm", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
+EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
            "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
