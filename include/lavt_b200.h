@@ -297,6 +297,10 @@ int lavt_patch_merge_layernorm_bwd(const float* x, int32_t B, int32_t D, int32_t
  * Windows of up to ~400 tokens (shared-memory resident). */
 int lavt_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* table_t, int32_t L, int32_t nH,
                               const lavt_win_geom_t* geom, const float* lse, void* dqkv, float* dtable_t, void* stream);
+/* Kernel selection for lavt_window_attention_bwd (process-wide; initial value from LAVT_ATTN_BWD_IMPL = mma | tc):
+ *   0 = auto: the tcgen05 / TMEM kernel (attn_bwd_tc.cu) for 7 x 7 windows with an even number of frames when lse is given, else mma.sync
+ *   1 = mma.sync kernel only (attn_bwd.cu)      2 = same as auto.   Returns the previous setting. */
+int lavt_set_attention_bwd_impl(int32_t impl);
 
 /* ---- PWAM + LanguageGate backward (adjoints of lavt_pwam_* above; reference lib/video_swin_transformer.py:919-1009, 519-525) ---- */
 /* Per pixel: recompute q^ = IN(q_pre) and the masked word softmax P, dP = dO v^T, dS = P (dP - sum P dP).  Outputs:

@@ -152,7 +152,7 @@ SIGNATURES = {
     "lavt_mha_small": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "lavt_gate_transpose": [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
 }
-EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl",
+EXPORTS = ["lavt_last_error", "lavt_abi_version", "lavt_instnorm_workspace_floats", "lavt_set_attention_impl", "lavt_set_attention_bwd_impl",
            "lavt_gemm_splitk_workspace_floats", "lavt_conv3x3_wgrad_workspace_floats", "lavt_gacd_workspace_floats", "lavt_conv3d_wgrad_workspace_floats", "lavt_adamw_chunk_elems", "lavt_window_attention_has_lse",
            *SIGNATURES.keys()]
 
@@ -175,6 +175,8 @@ def _declare(l: C.CDLL) -> None:
     l.lavt_adamw_chunk_elems.restype = C.c_int
     l.lavt_set_attention_impl.argtypes = [_i32]
     l.lavt_set_attention_impl.restype = C.c_int
+    l.lavt_set_attention_bwd_impl.argtypes = [_i32]
+    l.lavt_set_attention_bwd_impl.restype = C.c_int
     for name, argtypes in SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = argtypes
@@ -413,6 +415,13 @@ def set_attention_impl(impl: str) -> str:
     kernel), 'tc1' / 'tc2' / 'tc3' (prefer that generation where it applies) or 'mma' (mma.sync kernels only); returns the previous setting."""
     names = ["auto", "mma", "tc1", "tc2", "tc3"]
     prev = lib().lavt_set_attention_impl(names.index(impl))
+    return names[prev] if 0 <= prev < len(names) else "auto"
+
+
+def set_attention_bwd_impl(impl: str) -> str:
+    """'auto' / 'tc' (tcgen05 kernel attn_bwd_tc.cu where it applies) or 'mma' (mma.sync kernel only); returns the previous setting."""
+    names = ["auto", "mma", "tc"]
+    prev = lib().lavt_set_attention_bwd_impl(names.index(impl))
     return names[prev] if 0 <= prev < len(names) else "auto"
 
 

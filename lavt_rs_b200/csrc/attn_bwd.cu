@@ -16,6 +16,8 @@
 // atomics are CAS loops) and per CTA in an fp32 table copy that is flushed when the head changes.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace lavt {
 
 constexpr int AB_HD = 32;
@@ -372,10 +374,22 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) window_attn_bwd_kernel(const
     for (int i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(p.dtable_t + static_cast<long long>(cur_head) * L + i, dtab[i]);
 }
 
+int attn_bwd_impl_setting(int set) {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("LAVT_ATTN_BWD_IMPL");      // "mma" = mma.sync kernel only, "tc" = tcgen05 kernel where it applies (= auto)
+    impl = !e ? 0 : e[0] == 'm' ? 1 : e[0] == 't' ? 2 : 0;
+  }
+  const int prev = impl;
+  if (set >= 0) impl = set <= 2 ? set : 0;
+  return prev;
+}
+
 int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st) {
   const WinGeom& w = p.win;
   LAVT_REQUIRE(p.C == p.nH * AB_HD, "attention backward: head_dim must be 32 (C=%d, heads=%d)", p.C, p.nH);
   LAVT_REQUIRE(w.N > 0 && w.N == w.wd * w.wh * w.ww, "attention backward: bad window geometry");
+  if (attn_bwd_impl_setting(-1) != 1 && window_attn_bwd_tc_supported(p)) return window_attn_bwd_tc_dispatch(p, st);
   const int NP = (w.N + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(NP) * 64 * 4 + static_cast<size_t>(NP) * sizeof(AbTok) + static_cast<size_t>(p.L) * 12 + 32;
   LAVT_REQUIRE(smem <= 227 * 1024, "attention backward: window of %d tokens (table %d) needs %zu B of shared memory; windows above ~400 "

@@ -64,6 +64,10 @@ struct AttnBwdParams {
   WinGeom win;
 };
 int window_attn_bwd_dispatch(const AttnBwdParams& p, cudaStream_t st);
+// tcgen05 / TMEM variant (attn_bwd_tc.cu): 7 x 7 windows with an even number of frames and the forward's saved row statistics
+int attn_bwd_impl_setting(int set);   // set < 0: query only; returns the previous value (0 = auto, 1 = mma.sync only, 2 = tcgen05 where it applies)
+bool window_attn_bwd_tc_supported(const AttnBwdParams& p);
+int window_attn_bwd_tc_dispatch(const AttnBwdParams& p, cudaStream_t st);
 
 struct LnBwdParams {
   const float* x;              // LN input rows (fp32, pitch ldx), gathered like the forward
