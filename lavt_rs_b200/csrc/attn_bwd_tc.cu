@@ -45,8 +45,16 @@ struct AttnBwdTcArgs {
   int tab_floats;           // (2 Wd - 1) * BT_SD
   int off_q, off_do, off_k, off_v, off_dz, off_tab, off_itab, off_lse, off_del, off_bar;
   unsigned ld_bytes;        // TMA bytes per unit
+  long long* trace;         // -DBT_DEBUG builds: clock64 stamps of CTA 0 ([2 roles][BT_TRACE_N])
+  int dbg;                  // -DBT_DEBUG builds: elimination switches (LAVT_BT_DBG bit mask), timing experiments only
 };
 
+constexpr int BT_TRACE_N = 512;
+#ifdef BT_DEBUG
+#define BT_STAMP(role, idx) do { if (blockIdx.x == 0 && a.trace && (idx) < BT_TRACE_N) a.trace[(role) * BT_TRACE_N + (idx)] = clock64(); } while (0)
+#else
+#define BT_STAMP(role, idx) do { } while (0)
+#endif
 #ifdef BT_WATCHDOG
 __device__ __noinline__ void bt_stuck(int tag, uint32_t parity) {
   printf("[bwd_tc stuck] block %d warp %d lane %d tag %d parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, tag, parity);
@@ -59,6 +67,10 @@ __device__ __forceinline__ void bt_wait(uint64_t* bar, uint32_t parity, int tag)
 }
 #else
 __device__ __forceinline__ void bt_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void bt_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {
+  }
+}
 #endif
 
 __device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
@@ -68,6 +80,12 @@ __device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(r));
 }
+
+#ifdef BT_DEBUG
+#define BT_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define BT_DBG(bit) false
+#endif
 
 struct BtKey {              // per-thread state of this thread's key row in the current key tile
   const float* tb;          // bias address of query (frame 0, run 2 g, w 0) for this key
@@ -83,7 +101,7 @@ struct BtKey {              // per-thread state of this thread's key row in the 
 //   dzrow   : this key's 128-byte row in the MN-major dZ tile of the chunk;  r7 = row & 7 (swizzle phase)
 template <bool MASKED, bool TAIL>
 __device__ __forceinline__ void bt_chunk(uint32_t ts, uint32_t td, int c, int g, const BtKey& k, const float* nl, const float* nd,
-                                         uint8_t* dzrow, int r7, float fix, bool do_tab, bool kvalid) {
+                                         uint8_t* dzrow, int r7, float fix, bool do_tab, bool kvalid, int dbg) {
   uint32_t sv[16], dv[16];
   tmem_ld_x16(ts, sv);
   tmem_ld_x16(td, dv);
@@ -111,7 +129,7 @@ __device__ __forceinline__ void bt_chunk(uint32_t ts, uint32_t td, int c, int g,
     }
     float b[8];
 #pragma unroll
-    for (int e = 0; e < 7; ++e) b[e] = fb[kk * BT_SH + e];
+    for (int e = 0; e < 7; ++e) b[e] = BT_DBG(32) ? 0.f : fb[kk * BT_SH + e];
     b[7] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; e += 2) add2(t[e], t[e + 1], b[e], b[e + 1]);
@@ -137,7 +155,7 @@ __device__ __forceinline__ void bt_chunk(uint32_t ts, uint32_t td, int c, int g,
       add2(dz[e], dz[e + 1], d[e], d[e + 1]);
     }
 #pragma unroll
-    for (int e = 0; e < 7; ++e) pr[e] = ex2_ftz(pr[e]);
+    for (int e = 0; e < 7; ++e) pr[e] = BT_DBG(4) ? pr[e] : ex2_ftz(pr[e]);
     pr[7] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; e += 2) mul2(dz[e], dz[e + 1], pr[e], pr[e + 1]);
@@ -151,10 +169,14 @@ __device__ __forceinline__ void bt_chunk(uint32_t ts, uint32_t td, int c, int g,
       for (int e = 0; e < 7; ++e) atomicAdd(ib + kk * BT_SH + e, __float2int_rn(dz[e] * fix));
     }
   }
-  tmem_st_x8(ts, pw);
-  tmem_st_x8(td, zw);
-  *reinterpret_cast<uint4*>(dzrow + (((2 * g) ^ r7) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-  *reinterpret_cast<uint4*>(dzrow + (((2 * g + 1) ^ r7) << 4)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+  if (!BT_DBG(8)) {
+    tmem_st_x8(ts, pw);
+    tmem_st_x8(td, zw);
+  }
+  if (!BT_DBG(16)) {
+    *reinterpret_cast<uint4*>(dzrow + (((2 * g) ^ r7) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+    *reinterpret_cast<uint4*>(dzrow + (((2 * g + 1) ^ r7) << 4)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+  }
 }
 
 __global__ void __launch_bounds__(BT_THREADS, 1)
@@ -246,34 +268,53 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const uint32_t dz_base = sbase + a.off_dz;
       int n = 0, kt = 0;
       for (int lu = 0; lu < nunits; ++lu) {
+        int tr = lu * 40;
+        BT_STAMP(0, tr); ++tr;
         bt_wait(ld_full, lu & 1, 2);
         tc_fence_after();
+        BT_STAMP(0, tr); ++tr;
         auto issue_sdp = [&](int nl, int ng) {
           const int j = nl / nch, c = nl - j * nch, buf = ng & 1;
           const uint64_t dk = make_sw64_desc(k_base + j * 8192), dv = make_sw64_desc(v_base + j * 8192);
           const uint64_t dq = make_sw64_desc(q_base + c * 4096), dd = make_sw64_desc(do_base + c * 4096);
           const uint32_t ts = tmem_base + BT_COL_ST + buf * 64, td = tmem_base + BT_COL_DP + buf * 64;
+#ifdef BT_DEBUG
+          if (!(a.dbg & 256)) {
+#endif
           umma_bf16_ss(ts, dk, dq, idesc_s, 0);
           umma_bf16_ss(ts, dk + 2, dq + 2, idesc_s, 1);
           umma_bf16_ss(td, dv, dd, idesc_s, 0);
           umma_bf16_ss(td, dv + 2, dd + 2, idesc_s, 1);
+#ifdef BT_DEBUG
+          }
+#endif
           umma_commit(&s_full[buf]);
         };
         issue_sdp(0, n);
         if (NT > 1) issue_sdp(1, n + 1);
         for (int nl = 0; nl < NT; ++nl, ++n) {
           const int j = nl / nch, c = nl - j * nch, buf = n & 1;
+#ifdef BT_DEBUG
+          if (a.dbg & 512) bt_spin(&p_ready[buf], (n >> 1) & 1); else
+#endif
           bt_wait(&p_ready[buf], (n >> 1) & 1, 3);
+          BT_STAMP(0, tr); ++tr;
           if (c == 0 && kt >= 2) bt_wait(&dkv_free[kt & 1], ((kt >> 1) - 1) & 1, 4);
           tc_fence_after();
           {
             const uint32_t tdk = tmem_base + BT_COL_DKV + (kt & 1) * 64, tdv = tdk + BT_HD;
             const uint32_t tp = tmem_base + BT_COL_ST + buf * 64, tz = tmem_base + BT_COL_DP + buf * 64;
             const uint64_t bq = make_sw64_desc(q_base + c * 4096), bd = make_sw64_desc(do_base + c * 4096);
+#ifdef BT_DEBUG
+            if (!(a.dbg & 128)) {
+#endif
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_bf16_ts(tdv, tp + 16 * ks, bd + 64 * ks, idesc_kv, (c > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_bf16_ts(tdk, tz + 16 * ks, bq + 64 * ks, idesc_kv, (c > 0 || ks > 0) ? 1u : 0u);
+#ifdef BT_DEBUG
+            }
+#endif
           }
           if (c & 1) {
             if (nl == 1 && lu >= 1) {
@@ -285,6 +326,9 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const uint64_t da = make_mnmajor_sw128_desc(dz_base + slot * 32768, 16384);
             const uint64_t db = make_sw64_desc(k_base + j * 8192);
             const uint32_t tq = tmem_base + BT_COL_DQ + (c >> 1) * BT_HD;
+#ifdef BT_DEBUG
+            if (!(a.dbg & 64))
+#endif
             for (int ks = 0; ks < nks; ++ks) umma_bf16_ss(tq, da + 128 * ks, db + 64 * ks, idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&dz_free[slot]);
           }
@@ -343,6 +387,8 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const int u = u_begin + lu;
       const int head = u / a.nwin, win = u - head * a.nwin;
       const long long row0 = static_cast<long long>(win) * N;
+      int tr = lu * 80;
+      if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
       // ---- unit prologue: fold the previous unit's table gradient, (re)stage the bias table, -lse / -delta of every query, scale ----
       if (lu >= 1 && do_tab) {
         for (int pos = tid; pos < a.tab_floats; pos += BT_SM_THREADS) {
@@ -409,6 +455,7 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         if (tid == 0) umax[((lu + 1) & 1) * 2] = umax[((lu + 1) & 1) * 2 + 1] = 0;
       }
       named_bar(2, BT_SM_THREADS);
+      if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
       // |dZ| <= |dP| + |delta| <= 2 max||dO_i|| max||V_j|| (Cauchy-Schwarz; O is a convex combination of V rows), <= N terms per entry:
       // scale = 2^30 / (2.5 N bound) cannot overflow int32
       const float bound = 2.5f * static_cast<float>(N) * sqrtf(__int_as_float(umax[(lu & 1) * 2]) * __int_as_float(umax[(lu & 1) * 2 + 1]));
@@ -455,33 +502,53 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         }
         for (int c = 0; c < nch; ++c, ++n) {
           const int buf = n & 1;
+#ifdef BT_DEBUG
+          if (a.dbg & 1024) {
+            if (lane == 0) bt_spin(&s_full[buf], (n >> 1) & 1);
+            __syncwarp();
+          } else if (a.dbg & 2048) {
+            if (lane == 0) bt_wait(&s_full[buf], (n >> 1) & 1, 7);
+            __syncwarp();
+          } else
+#endif
           bt_wait(&s_full[buf], (n >> 1) & 1, 7);
+          if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
           if ((n & 1) == 0 && (n >> 1) >= 2) bt_wait(&dz_free[(n >> 1) & 1], (((n >> 1) >> 1) - 1) & 1, 8);
           tc_fence_after();
+#ifdef BT_DEBUG
+          if (wvalid && !(a.dbg & 1)) {
+#else
           if (wvalid) {
+#endif
             const uint32_t ts = tlane + BT_COL_ST + buf * 64 + 16 * g, td = tlane + BT_COL_DP + buf * 64 + 16 * g;
             uint8_t* dzrow = smem + a.off_dz + ((n >> 1) & 1) * 32768 + (c & 1) * 16384 + r * 128;
             const float* nl = nlse_s + c * 64 + 16 * g;
             const float* nd = ndel_s + c * 64 + 16 * g;
             if (need_mask) {
-              if (tail) bt_chunk<true, true>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid);
-              else bt_chunk<true, false>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid);
+              if (tail) bt_chunk<true, true>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid, a.dbg);
+              else bt_chunk<true, false>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid, a.dbg);
             } else {
-              if (tail) bt_chunk<false, true>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid);
-              else bt_chunk<false, false>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid);
+              if (tail) bt_chunk<false, true>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid, a.dbg);
+              else bt_chunk<false, false>(ts, td, c, g, key, nl, nd, dzrow, r & 7, fix, do_tab, kvalid, a.dbg);
             }
           }
           tmem_st_wait();
           tc_fence_before();
+#ifdef BT_DEBUG
+          if (!(a.dbg & 2))
+#endif
           fence_proxy_async_smem();                          // the dZ rows are read by the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_ready[buf]);
+          if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
           if (c == 0 && j > 0) drain_dkv(kt - 1, j - 1, row0, head);    // previous key tile: its last MMAs retired long ago
         }
       }
       // ---- unit epilogue: last key tile, dQ, and everybody's atomics before the table is folded ----
+      if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
       drain_dkv(kt - 1, ntk - 1, row0, head);
       bt_wait(dq_full, lu & 1, 9);
+      if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
       tc_fence_after();
       if (g < a.nqt) {
         uint32_t v[32];
@@ -508,6 +575,7 @@ window_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       prev_inv_fix = 1.0f / fix;
       prev_head = head;
       named_bar(1, BT_SM_THREADS);
+      if (threadIdx.x == 0) { BT_STAMP(1, tr); } ++tr;
     }
     if (nunits > 0 && do_tab) {
       for (int pos = tid; pos < a.tab_floats; pos += BT_SM_THREADS) {
@@ -574,6 +642,16 @@ int window_attn_bwd_tc_dispatch(const AttnBwdParams& p, cudaStream_t st) {
   LAVT_REQUIRE(nwin * p.nH < (1LL << 30), "attention backward (tcgen05): too many units");
   a.nwin = static_cast<int>(nwin);
   a.units = static_cast<int>(nwin * p.nH);
+  a.dbg = 0;
+  a.trace = nullptr;
+#ifdef BT_DEBUG
+  if (const char* e = getenv("LAVT_BT_DBG")) a.dbg = atoi(e);
+  const char* trace_path = getenv("LAVT_BT_TRACE");
+  if (trace_path) {
+    LAVT_CUDA(cudaMalloc(&a.trace, 2 * BT_TRACE_N * sizeof(long long)));
+    LAVT_CUDA(cudaMemsetAsync(a.trace, 0, 2 * BT_TRACE_N * sizeof(long long), st));
+  }
+#endif
 
   CUtensorMap tm_q, tm_do, tm_kv;
   {
@@ -608,6 +686,21 @@ int window_attn_bwd_tc_dispatch(const AttnBwdParams& p, cudaStream_t st) {
   }
   window_attn_bwd_tc_kernel<<<grid, BT_THREADS, smem, st>>>(tm_q, tm_do, tm_kv, p, a);
   LAVT_LAUNCH_CHECK("window_attn_bwd_tc_kernel");
+#ifdef BT_DEBUG
+  if (a.trace) {            // debug only: synchronous dump of CTA 0's event clocks, one line per role
+    static long long host[2 * BT_TRACE_N];
+    LAVT_CUDA(cudaStreamSynchronize(st));
+    LAVT_CUDA(cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(a.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 2; ++r) {
+        for (int t = 0; t < BT_TRACE_N; ++t) fprintf(f, "%lld ", host[r * BT_TRACE_N + t]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#endif
   return LAVT_OK;
 }
 

@@ -186,11 +186,25 @@ def test_swin_block_backward(stage, shifted, dims):
     check_grads(grads.named(blk), pg_ref, f"swin block stage {stage} shifted={shifted}")
     # the forward kernel saved the row log-sum-exp for the attention backward; without it the backward recomputes it in a first pass
     assert saved[-1] is not None and saved[-1].shape == (saved[8].rows(), nH)
+    # (without the statistics the mma.sync kernel runs; with them the tcgen05 kernel attn_bwd_tc.cu where it applies: two implementations,
+    # each held to the oracle above -- their mutual distance is bounded by twice their own bf16 error)
     grads2 = T.GradStore()
     dx2 = T.swin_block_bwd(blk, saved[:-1] + (None,), gout.cuda().reshape(-1, C).contiguous(), grads2, ws)
-    assert rel_l2(dx2, dx) < 5e-3
+    assert rel_l2(dx2, dx) < 1e-2
     n1, n2 = grads.named(blk), grads2.named(blk)
-    assert all(rel_l2(n2[k], n1[k]) < 5e-3 for k in ("attn.qkv.weight", "attn.relative_position_bias_table"))
+    errs = {k: rel_l2(n2[k], n1[k]) for k in ("attn.qkv.weight", "attn.relative_position_bias_table")}
+    assert all(e < 1e-2 for e in errs.values()), errs
+    # the mma.sync kernel with and without the saved statistics
+    from lavt_rs_b200 import _cabi as K
+    prev = K.set_attention_bwd_impl("mma")
+    try:
+        grads3 = T.GradStore()
+        dx3 = T.swin_block_bwd(blk, saved, gout.cuda().reshape(-1, C).contiguous(), grads3, ws)
+        torch.cuda.synchronize()
+    finally:
+        K.set_attention_bwd_impl(prev)
+    n3 = grads3.named(blk)
+    assert rel_l2(dx3, dx2) < 5e-3 and all(rel_l2(n3[k], n2[k]) < 5e-3 for k in ("attn.qkv.weight", "attn.relative_position_bias_table"))
 
 
 def test_swin_block_drop_path():

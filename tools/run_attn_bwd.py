@@ -87,7 +87,7 @@ def main():
             geom, qkv, table, dout, out, lse = setup(dims, shifted, nH)
             tt = table.t().contiguous()
             dqkv = torch.zeros_like(qkv)
-            dtab = torch.zeros(nH, table.shape[0], device="cuda")
+            dtab = None if "--notab" in sys.argv else torch.zeros(nH, table.shape[0], device="cuda")
             res = {}
             for impl in ("mma", "tc"):
                 prev = K.set_attention_bwd_impl(impl)
