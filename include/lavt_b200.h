@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LAVT_ABI_VERSION 2
+#define LAVT_ABI_VERSION 3
 
 #define LAVT_ERR_SHAPE 1
 #define LAVT_ERR_CUDA 2
@@ -43,7 +43,11 @@ typedef struct lavt_win_geom {
 } lavt_win_geom_t;
 
 /* Fused GEMM epilogue:
- *   out[orow(m), n] = act(acc[m,n] * cscale[n] + bias[n]) * mul[m,n] * rscale[orow(m) / rscale_rows] + resid[orow(m), n]
+ *   pre = acc[m,n] * cscale[n] + bias[n]
+ *   out[orow(m), n] = act(pre) * mul'[m,n] * rscale[orow(m) / rscale_rows] + resid[orow(m), n],   out_pre[orow(m), n] = pre
+ * mul' = mul, or GELU'(mul) with mul_act = LAVT_ACT_GELU: the fc2 input gradient times the derivative of the saved fc1
+ * pre-activation in one launch (adjoint of Mlp, lib/video_swin_transformer.py:30-36); out_pre keeps the pre-activation of a
+ * training-mode forward next to the activated output (fc1: both tensors from one launch).
  * orow = m, or (win != NULL) the token row that window-row m maps back to (window_reverse +
  * reverse cyclic shift + crop, lib/video_swin_transformer.py:238-247); pad rows are dropped. */
 typedef struct lavt_epilogue {
@@ -55,13 +59,14 @@ typedef struct lavt_epilogue {
   const float* resid;    /* fp32 [rows_out, ldo] or NULL */
   float* out_f32;        /* fp32 [rows_out, ldo] or NULL */
   void* out_bf16;        /* bf16 [rows_out, ldo] or NULL */
-  int32_t ldo;           /* row pitch of resid / out (elements) */
-  int32_t _pad;
+  int32_t ldo;           /* row pitch of resid / out / out_pre (elements) */
+  int32_t mul_act;       /* 0: multiply by mul; LAVT_ACT_GELU: multiply by GELU'(mul) */
   const lavt_win_geom_t* win; /* HOST pointer or NULL */
   const float* rscale;   /* fp32 per-sample scale of the whole branch, or NULL: DropPath in training (timm drop_path as used at
                             lib/video_swin_transformer.py:266,271: 0 or 1/keep_prob per clip); sample = output row / rscale_rows */
   int32_t rscale_rows;
-  int32_t _pad2;
+  int32_t pre_mode;      /* 0: out_pre = pre;  1 (act = LAVT_ACT_GELU only): out_pre = GELU'(pre), the factor the backward of fc1 needs */
+  void* out_pre;         /* bf16 [rows_out, ldo] or NULL: the value BEFORE the activation (tcgen05 GEMM / conv entry points only) */
 } lavt_epilogue_t;
 
 const char* lavt_last_error(void);

@@ -36,9 +36,10 @@ class Epilogue(C.Structure):
         ("act", C.c_int32), ("ldm", C.c_int32),
         ("mul", C.c_void_p), ("resid", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
-        ("ldo", C.c_int32), ("_pad", C.c_int32),
+        ("ldo", C.c_int32), ("mul_act", C.c_int32),
         ("win", C.POINTER(WinGeom)),
-        ("rscale", C.c_void_p), ("rscale_rows", C.c_int32), ("_pad2", C.c_int32),
+        ("rscale", C.c_void_p), ("rscale_rows", C.c_int32), ("pre_mode", C.c_int32),
+        ("out_pre", C.c_void_p),
     ]
 
 
@@ -67,7 +68,7 @@ def lib() -> C.CDLL:
     return l
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 _EP = C.POINTER(Epilogue)
@@ -207,27 +208,33 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def make_epilogue(*, cscale=None, bias=None, act=ACT_NONE, mul=None, resid=None,
-                  out_f32=None, out_bf16=None, ldo=None, win: Optional[WinGeom] = None, rscale=None, rscale_rows: int = 0) -> Epilogue:
+                  out_f32=None, out_bf16=None, ldo=None, win: Optional[WinGeom] = None, rscale=None, rscale_rows: int = 0,
+                  mul_act=ACT_NONE, out_pre=None, pre_mode: int = 0) -> Epilogue:
+    """``mul_act=ACT_GELU``: the result is multiplied by GELU'(mul) instead of mul; ``out_pre`` (bf16): the value before the activation,
+    or with ``pre_mode=1`` (act = GELU) the derivative GELU'(pre)."""
     e = Epilogue()
     for name, t in (("cscale", cscale), ("bias", bias), ("resid", resid), ("out_f32", out_f32)):
         if t is not None:
             _req(t, torch.float32, name)
-    for name, t in (("mul", mul), ("out_bf16", out_bf16)):
+    for name, t in (("mul", mul), ("out_bf16", out_bf16), ("out_pre", out_pre)):
         if t is not None:
             _req(t, torch.bfloat16, name)
     e.cscale, e.bias = ptr(cscale), ptr(bias)
     e.act = act
     e.mul = ptr(mul)
     e.ldm = mul.stride(-2) if mul is not None else 0
+    e.mul_act = mul_act
+    e.out_pre = ptr(out_pre)
+    e.pre_mode = int(pre_mode)
     e.resid = ptr(resid)
     e.out_f32, e.out_bf16 = ptr(out_f32), ptr(out_bf16)
     out = out_f32 if out_f32 is not None else out_bf16
     if out is None:
         raise LavtError("epilogue needs out_f32 or out_bf16")
     e.ldo = int(ldo if ldo is not None else out.stride(-2))
-    for t in (resid, out_f32, out_bf16):
+    for t in (resid, out_f32, out_bf16, out_pre):
         if t is not None and t.stride(-2) != e.ldo:
-            raise LavtError("resid / out_f32 / out_bf16 must share one row pitch")
+            raise LavtError("resid / out_f32 / out_bf16 / out_pre must share one row pitch")
     e.win = C.pointer(win) if win is not None else None
     if rscale is not None:
         _req(rscale, torch.float32, "rscale")

@@ -35,6 +35,40 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __rest
   *d = a;
 }
 
+// Many splits (single-tile weight gradients split 100-300 ways): one thread walking all partials of its element is a chain of `splits`
+// L2 round trips on a handful of SMs (272 splits of a 128 x 128 output: ~40 us).  Here 8 thread groups of a block sum every 8th split
+// of 32 consecutive float4 elements and combine through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float4* __restrict__ part, int splits, long long count4, int ncols4,
+                                                                 float* __restrict__ dst, long long ldd, int accumulate) {
+  __shared__ float4 sm[8][32];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long long i = static_cast<long long>(blockIdx.x) * 32 + e;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < count4) {
+#pragma unroll 4
+    for (int s = g; s < splits; s += 8) {
+      const float4 b = __ldg(part + s * count4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+  }
+  sm[g][e] = a;
+  __syncthreads();
+  if (g != 0 || i >= count4) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    const float4 b = sm[q][e];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  const long long m = i / ncols4;
+  const int n = static_cast<int>(i - m * ncols4) * 4;
+  float4* d = reinterpret_cast<float4*>(dst + m * ldd + n);
+  if (accumulate) {
+    const float4 o = *d;
+    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+  }
+  *d = a;
+}
+
 // out = act((sum_s partial[s]) * cscale[col] + bias[col]) (+ resid): the epilogue of a split-K forward GEMM (small-M GEMMs of the text encoder:
 // 160 rows give 2 x 3..12 output tiles, each walking up to 48 k-blocks alone -- 26-43 us per launch; split over K they fill the machine)
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float4* __restrict__ part, int splits, long long count4, int ncols4,
@@ -75,6 +109,12 @@ int splitk_reduce_dispatch(const float* partials, int splits, long long count, i
                            cudaStream_t st) {
   LAVT_REQUIRE(count % 4 == 0 && ncols % 4 == 0 && ldd % 4 == 0, "splitk reduce: sizes must be multiples of 4");
   const long long c4 = count / 4;
+  if (splits >= 16 && (c4 + 255) / 256 < 4 * 148) {
+    splitk_reduce_wide_kernel<<<static_cast<unsigned>((c4 + 31) / 32), 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, c4,
+                                                                                  ncols / 4, dst, ldd, accumulate);
+    LAVT_LAUNCH_CHECK("splitk_reduce_wide_kernel");
+    return LAVT_OK;
+  }
   splitk_reduce_kernel<<<static_cast<unsigned>((c4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, c4,
                                                                               ncols / 4, dst, ldd, accumulate);
   LAVT_LAUNCH_CHECK("splitk_reduce_kernel");

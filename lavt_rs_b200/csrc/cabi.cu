@@ -20,6 +20,12 @@ static int fill_epilogue(GemmParams& p, const lavt_epilogue_t* e) {
   p.act = e->act;
   p.mul = static_cast<const __nv_bfloat16*>(e->mul);
   p.ldm = e->ldm;
+  p.mul_act = e->mul_act;
+  p.out_pre = static_cast<__nv_bfloat16*>(e->out_pre);
+  p.pre_mode = e->pre_mode;
+  LAVT_REQUIRE(e->pre_mode == 0 || (e->pre_mode == 1 && e->out_pre && e->act == LAVT_ACT_GELU),
+               "epilogue: pre_mode 1 (out_pre = GELU'(pre)) needs out_pre and act = LAVT_ACT_GELU");
+  LAVT_REQUIRE(e->mul_act == 0 || (e->mul_act == LAVT_ACT_GELU && e->mul), "epilogue: mul_act must be 0 or LAVT_ACT_GELU with a mul operand");
   p.resid = e->resid;
   p.out_f32 = e->out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(e->out_bf16);
@@ -264,17 +270,34 @@ int lavt_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int32_t n_img, int32
  * backward pass (training step)
  * ------------------------------------------------------------------------------------------------ */
 static void splitk_plan(int M, int N, int K, int* ksplit, int* kbs) {
-  // One wave of work items: (tile, split) pairs should fill the CTA slots of the variant gemm_variant() will pick, not overflow
-  // them (tiles x 5 = 320 items on 296 slots ran as two waves, the second one 8 % full: ncu showed the tensor pipe at 30 %).
+  // (tile, split) work items over the CTA slots of the variant gemm_variant() will pick.  The first planner filled at most ONE wave
+  // (tiles x 5 = 320 items on 296 slots had run as two waves, the second one 8 % full: ncu showed the tensor pipe at 30 %), which
+  // left 92 tiles of the Cin = 640 conv weight gradient on 148 SMs unsplit (62 % of the machine) and capped single-tile problems at
+  // 64 items.  Now: the split count with the lowest modelled time, in units of one k-block of one tile --
+  //   waves(s) * (k-blocks per item + per-item overhead) + s * (write + read of one fp32 partial of the whole output)
+  // so that several FULL waves (92 x 8 = 736 items = 4.97 waves) are as good as one.
   const int num_kb = (K + 63) / 64;
   const bool wide = (N % 256) == 0;                       // 128 x 256 tiles, one CTA per SM
   const long long tiles = 1LL * ((M + 127) / 128) * (wide ? N / 256 : (N + 127) / 128);
   const long long slots = wide ? 148 : (K >= 1024 ? 296 : 148);
-  long long want = slots / tiles;
-  if (want > num_kb) want = num_kb;
-  if (want > 64) want = 64;
-  if (want < 1) want = 1;
-  *kbs = static_cast<int>((num_kb + want - 1) / want);
+  const double part = 1.0 * M * N * (wide ? 1.6e-6 : 3.2e-6);          // partial traffic of one split / time of one k-block
+  const double ovh = 6.0;                                 // pipeline fill + the part of the drain the next item cannot hide
+  long long smax = num_kb < 512 ? num_kb : 512;
+  const long long ws_cap = (64LL << 20) / (1LL * M * N);  // <= 256 MB of fp32 partials
+  if (smax > ws_cap) smax = ws_cap < 1 ? 1 : ws_cap;
+  double best = 0.0;
+  int best_kbs = num_kb;
+  for (long long s = 1; s <= smax; ++s) {
+    const long long kb = (num_kb + s - 1) / s;
+    const long long sp = (num_kb + kb - 1) / kb;          // splits that actually own k-blocks
+    const long long waves = (tiles * sp + slots - 1) / slots;
+    const double cost = waves * (kb + ovh) + (sp > 1 ? sp * part : 0.0);
+    if (s == 1 || cost < best * 0.98) {                   // a finer split has to win by 2 % to be taken
+      best = cost;
+      best_kbs = static_cast<int>(kb);
+    }
+  }
+  *kbs = best_kbs;
   *ksplit = (num_kb + *kbs - 1) / *kbs;
 }
 
@@ -313,7 +336,7 @@ int lavt_gemm_bf16_smallm(const void* A, int64_t lda, const void* Wt, int64_t ld
   std::memset(&e, 0, sizeof(e));
   int rc = fill_epilogue(e, epi);
   if (rc) return rc;
-  LAVT_REQUIRE(e.rowmap == ROWMAP_IDENTITY && !e.mul && !e.rscale && (e.act == 0 || e.act == 1), "small-M gemm: epilogue not supported");
+  LAVT_REQUIRE(e.rowmap == ROWMAP_IDENTITY && !e.mul && !e.out_pre && !e.pre_mode && !e.rscale && (e.act == 0 || e.act == 1), "small-M gemm: epilogue not supported");
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;

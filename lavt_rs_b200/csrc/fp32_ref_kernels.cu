@@ -161,6 +161,7 @@ extern "C" int lavt_gemm_f32_ref(const float* A, int64_t lda, const float* Wt, i
   LAVT_REQUIRE(A && Wt && e && M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K, "gemm_f32_ref: bad arguments");
   LAVT_REQUIRE(e->out_f32 || e->out_bf16, "gemm_f32_ref: no output");
   LAVT_REQUIRE(e->act >= 0 && e->act <= 4, "gemm_f32_ref: bad activation id %d", e->act);
+  LAVT_REQUIRE(e->mul_act == 0 && !e->out_pre && e->pre_mode == 0, "gemm_f32_ref: mul_act / out_pre are training-path epilogues of the tcgen05 kernel only");
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;

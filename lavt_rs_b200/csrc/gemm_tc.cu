@@ -103,6 +103,41 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
   upk2(fma2(hx, e, hx), x0, x1);
 }
+// GELU and GELU'(x) = Phi(x) + x phi(x) for two values: Phi from the same erf polynomial as gelu_erf2, phi from one ex2.
+// x0 / x1 become GELU(x), d0 / d1 the derivative.
+__device__ __forceinline__ void gelu_both2(float& x0, float& x1, float& d0, float& d1) {
+  const uint64_t x = pk2(x0, x1);
+  float z0, z1;
+  upk2(mul2(x, pk2(0.70710678118654752f, 0.70710678118654752f)), z0, z1);
+  const uint64_t zz = pk2(z0, z1);
+  float q0, q1;
+  upk2(mul2(zz, zz), q0, q1);                  // x^2 / 2
+  const float e0 = ex2_approx(-1.4426950408889634f * q0), e1 = ex2_approx(-1.4426950408889634f * q1);
+  z0 = fminf(fmaxf(z0, -3.0f), 3.0f);
+  z1 = fminf(fmaxf(z1, -3.0f), 3.0f);
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t t = mul2(z, z);
+  constexpr float K = 1.0000220904f;
+  uint64_t p = pk2(4.0742095563e-08f * K, 4.0742095563e-08f * K);
+  p = fma2(p, t, pk2(-1.9448222676e-06f * K, -1.9448222676e-06f * K));
+  p = fma2(p, t, pk2(4.1060515983e-05f * K, 4.1060515983e-05f * K));
+  p = fma2(p, t, pk2(-5.1103678896e-04f * K, -5.1103678896e-04f * K));
+  p = fma2(p, t, pk2(4.2354270142e-03f * K, 4.2354270142e-03f * K));
+  p = fma2(p, t, pk2(-2.5102860078e-02f * K, -2.5102860078e-02f * K));
+  p = fma2(p, t, pk2(1.1107933337e-01f * K, 1.1107933337e-01f * K));
+  p = fma2(p, t, pk2(-3.7531487405e-01f * K, -3.7531487405e-01f * K));
+  p = fma2(p, t, pk2(1.1282684285e+00f * K, 1.1282684285e+00f * K));
+  const uint64_t Phi = fma2(mul2(z, p), pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));                    // 0.5 + 0.5 erf(x / sqrt 2)
+  const uint64_t xs = mul2(x, pk2(0.3989422804014327f, 0.3989422804014327f));
+  upk2(fma2(xs, pk2(e0, e1), Phi), d0, d1);
+  upk2(mul2(x, Phi), x0, x1);
+}
+__device__ __forceinline__ void gelu_grad2(float& x0, float& x1) {
+  float d0, d1;
+  gelu_both2(x0, x1, d0, d1);
+  x0 = d0;
+  x1 = d1;
+}
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
 __device__ __forceinline__ void ldg_v8(uint32_t* r, const void* p) {
   asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -394,6 +429,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
       float* of_row = (p.out_f32 && live) ? p.out_f32 + ks * p.split_stride + orow * p.ldo + n0 : nullptr;
       __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
+      __nv_bfloat16* op_row = (p.out_pre && live) ? p.out_pre + orow * p.ldo + n0 : nullptr;
 
       const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
       bool acc_ready = false;
@@ -438,7 +474,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                  f[4 * q + 3]);
           }
         }
-        if (p.act == ACT_GELU) {
+        if (op_row && p.pre_mode == 1) {     // training forward of fc1: GELU(pre) and GELU'(pre) from one polynomial
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float d0, d1;
+              gelu_both2(f[q * 16 + 2 * j], f[q * 16 + 2 * j + 1], d0, d1);
+              u[j] = pack_bf16x2(d0, d1);
+            }
+            stg_v8(op_row + c * 32 + q * 16, u);
+          }
+        } else if (op_row) {                 // training forward: the pre-activation is saved next to the activated output
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(f[q * 16 + 2 * j], f[q * 16 + 2 * j + 1]);
+            stg_v8(op_row + c * 32 + q * 16, u);
+          }
+        }
+        if (op_row && p.pre_mode == 1) {
+          // activation already applied above
+        } else if (p.act == ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
         } else if (p.act == ACT_RELU) {
@@ -458,7 +517,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ldg_v8(u, mul_row + c * 32 + q * 16);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float2 a = unpack_bf16x2(u[j]);
+              float2 a = unpack_bf16x2(u[j]);
+              if (p.mul_act == ACT_GELU) gelu_grad2(a.x, a.y);
               f[q * 16 + 2 * j] *= a.x;
               f[q * 16 + 2 * j + 1] *= a.y;
             }

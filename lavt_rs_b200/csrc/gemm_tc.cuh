@@ -8,7 +8,8 @@ namespace lavt {
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 enum GemmRowMap { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1, ROWMAP_CONV = 2, ROWMAP_WGCONV = 3 };
 
-// out[orow(m), n] = act( acc[m,n] * cscale[n] + bias[n] ) * mul[m,n] * rscale[orow(m) / rs_rows] + resid[orow(m), n]
+// pre = acc[m,n] * cscale[n] + bias[n];  out_pre[orow(m), n] = pre
+// out[orow(m), n] = act(pre) * mul'[m,n] * rscale[orow(m) / rs_rows] + resid[orow(m), n],  mul' = mul or GELU'(mul) (mul_act)
 struct GemmParams {
   int M, N, K;               // logical problem (conv: M = pixels, K = taps*Cin)
   // ---- epilogue ----
@@ -17,6 +18,9 @@ struct GemmParams {
   int act;                   // GemmAct
   const __nv_bfloat16* mul;  // [M, ldm] or nullptr (indexed by the GEMM row m)
   int ldm;
+  int mul_act;               // 0: multiply by mul; ACT_GELU: multiply by GELU'(mul) (fc2 input gradient x derivative of the fc1 pre-activation)
+  __nv_bfloat16* out_pre;    // [rows_out, ldo] or nullptr: the value before the activation (training forward)
+  int pre_mode;              // 1 (with act = ACT_GELU): out_pre receives GELU'(pre) instead of pre -- what the backward of fc1 multiplies by
   const float* resid;        // [rows_out, ldo] or nullptr (indexed by the OUTPUT row)
   float* out_f32;            // [rows_out, ldo] or nullptr
   __nv_bfloat16* out_bf16;   // [rows_out, ldo] or nullptr

@@ -370,66 +370,161 @@ int instnorm_bwd_dispatch(const float* g32, const __nv_bfloat16* ga, const __nv_
 
 // ---------------------------------------------------------------------------------------------------------------
 // k, v = (W l + b) * mask.  dkbuf / dvbuf fp32 [(b * heads + h) * NlPad + j, C]: the row of head h = channel's head is the valid one.
-// grid.x covers C * Lin weight elements (both matrices), then B * Lin * Nl language elements.
-__global__ void __launch_bounds__(256) pwam_kv_bwd_kernel(const float* __restrict__ dkbuf, const float* __restrict__ dvbuf,
-                                                          const float* __restrict__ mask, const float* __restrict__ l,
-                                                          const float* __restrict__ wk, const float* __restrict__ wv,
-                                                          float* __restrict__ dwk, float* __restrict__ dbk, float* __restrict__ dwv,
-                                                          float* __restrict__ dbv, float* __restrict__ dl, int B, int Nl, int NlPad,
-                                                          int Lin, int C, int heads) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long nW = static_cast<long long>(C) * Lin;
+// Two small tiled contractions over G[(b, j), c] = mask[b, j] * d{k,v}[b, head(c), j, c]  (the first version walked all (clip, word)
+// pairs / all channels in ONE thread per output element with strided loads: 330 us per launch for 60-250 MFLOP):
+//   pwam_kv_wgrad_kernel   dW{k,v}[c, i] += sum_(b,j) G[(b,j), c] * l[b, i, j],  db{k,v}[c] += sum_(b,j) G[(b,j), c]
+//                          block = 64 channels x 64 language channels, (b, j) staged 32 words at a time
+//   pwam_kv_dl_kernel      dl[b, i, j] += mask[b, j] * sum_c (dk[.., c] * Wk[c, i] + dv[.., c] * Wv[c, i])
+//                          block = 16 (b, j) rows x 64 language channels; the 2C-long contraction is split over gridDim.z
+//                          (fp32 atomic adds into dl, like the LayerNorm gamma / beta gradients)
+__global__ void __launch_bounds__(256) pwam_kv_wgrad_kernel(const float* __restrict__ dkbuf, const float* __restrict__ dvbuf,
+                                                            const float* __restrict__ mask, const float* __restrict__ l,
+                                                            float* __restrict__ dwk, float* __restrict__ dbk, float* __restrict__ dwv,
+                                                            float* __restrict__ dbv, int B, int Nl, int NlPad, int Lin, int C, int heads) {
+  __shared__ float sGk[32][64], sGv[32][64], sL[32][65];
+  const int t = threadIdx.x;
+  const int i0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tc = t & 15, ti = t >> 4;           // 4 channels x 4 language channels per thread
   const int ch = C / heads;
-  if (idx < nW) {
-    const int c = static_cast<int>(idx / Lin), i = static_cast<int>(idx - static_cast<long long>(c) * Lin);
-    const int h = c / ch;
-    float ak = 0.f, av = 0.f, bk = 0.f, bv = 0.f;
-    for (int b = 0; b < B; ++b) {
-      for (int j = 0; j < Nl; ++j) {
-        const float m = __ldg(mask + b * Nl + j);
-        if (m == 0.f) continue;
-        const long long r = (static_cast<long long>(b) * heads + h) * NlPad + j;
-        const float gk = __ldg(dkbuf + r * C + c) * m, gv = __ldg(dvbuf + r * C + c) * m;
-        const float lv = __ldg(l + (static_cast<long long>(b) * Lin + i) * Nl + j);
-        ak = fmaf(gk, lv, ak);
-        av = fmaf(gv, lv, av);
-        bk += gk;
-        bv += gv;
+  float ak[4][4], av[4][4], bk[4], bv[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    bk[a] = 0.f;
+    bv[a] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ak[a][q] = 0.f; av[a][q] = 0.f; }
+  }
+  for (int b = 0; b < B; ++b) {
+    for (int j0 = 0; j0 < Nl; j0 += 32) {
+      const int jn = min(32, Nl - j0);
+      __syncthreads();
+      for (int e = t; e < 32 * 64; e += 256) {
+        const int kk = e >> 6, c = c0 + (e & 63);
+        float gk = 0.f, gv = 0.f;
+        if (kk < jn && c < C) {
+          const float m = __ldg(mask + b * Nl + j0 + kk);
+          if (m != 0.f) {
+            const long long r = (static_cast<long long>(b) * heads + c / ch) * NlPad + j0 + kk;
+            gk = __ldg(dkbuf + r * C + c) * m;
+            gv = __ldg(dvbuf + r * C + c) * m;
+          }
+        }
+        sGk[kk][e & 63] = gk;
+        sGv[kk][e & 63] = gv;
+      }
+      for (int e = t; e < 64 * jn; e += 256) {        // l[b, i0 + i, j0 + kk]: runs of jn consecutive floats
+        const int i = e / jn, kk = e - i * jn;
+        sL[kk][i] = (i0 + i < Lin) ? __ldg(l + (static_cast<long long>(b) * Lin + i0 + i) * Nl + j0 + kk) : 0.f;
+      }
+      __syncthreads();
+      for (int kk = 0; kk < jn; ++kk) {
+        const float4 gk = *reinterpret_cast<const float4*>(&sGk[kk][tc * 4]);
+        const float4 gv = *reinterpret_cast<const float4*>(&sGv[kk][tc * 4]);
+        const float g1[4] = {gk.x, gk.y, gk.z, gk.w}, g2[4] = {gv.x, gv.y, gv.z, gv.w};
+        float lv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lv[q] = sL[kk][ti * 4 + q];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          bk[a] += g1[a];
+          bv[a] += g2[a];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ak[a][q] = fmaf(g1[a], lv[q], ak[a][q]);
+            av[a][q] = fmaf(g2[a], lv[q], av[a][q]);
+          }
+        }
       }
     }
-    if (dwk) dwk[idx] += ak;
-    if (dwv) dwv[idx] += av;
-    if (i == 0) {
-      if (dbk) dbk[c] += bk;
-      if (dbv) dbv[c] += bv;
-    }
-    return;
   }
-  const long long e = idx - nW;
-  if (!dl || e >= static_cast<long long>(B) * Lin * Nl) return;
-  const int j = static_cast<int>(e % Nl);
-  const int i = static_cast<int>((e / Nl) % Lin);
-  const int b = static_cast<int>(e / (static_cast<long long>(Nl) * Lin));
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int c = c0 + tc * 4 + a;
+    if (c >= C) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + ti * 4 + q;
+      if (i >= Lin) continue;
+      if (dwk) dwk[static_cast<long long>(c) * Lin + i] += ak[a][q];
+      if (dwv) dwv[static_cast<long long>(c) * Lin + i] += av[a][q];
+    }
+    if (blockIdx.x == 0 && ti == 0) {
+      if (dbk) dbk[c] += bk[a];
+      if (dbv) dbv[c] += bv[a];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pwam_kv_dl_kernel(const float* __restrict__ dkbuf, const float* __restrict__ dvbuf,
+                                                         const float* __restrict__ mask, const float* __restrict__ wk,
+                                                         const float* __restrict__ wv, float* __restrict__ dl, int B, int Nl, int NlPad,
+                                                         int Lin, int C, int heads) {
+  __shared__ float sG[16][65];
+  __shared__ __align__(16) float sW[64][64];
+  const int t = threadIdx.x;
+  const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 16;
+  const int ti = t & 15, tk = t >> 4;           // one (b, j) row x 4 language channels per thread
+  const int ch = C / heads;
+  const int KR = B * Nl;
+  const int cchunks = (C + 63) / 64;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int cc = blockIdx.z; cc < 2 * cchunks; cc += gridDim.z) {
+    const bool isv = cc >= cchunks;
+    const int c0 = (isv ? cc - cchunks : cc) * 64;
+    const float* g = isv ? dvbuf : dkbuf;
+    const float* w = isv ? wv : wk;
+    __syncthreads();
+    for (int e = t; e < 16 * 64; e += 256) {
+      const int kr = e >> 6, c = c0 + (e & 63), k = k0 + kr;
+      float v = 0.f;
+      if (k < KR && c < C) {
+        const int b = k / Nl, j = k - b * Nl;
+        v = __ldg(g + ((static_cast<long long>(b) * heads + c / ch) * NlPad + j) * C + c);
+      }
+      sG[kr][e & 63] = v;
+    }
+    for (int e = t; e < 64 * 64; e += 256) {
+      const int cr = e >> 6, i = i0 + (e & 63), c = c0 + cr;
+      sW[cr][e & 63] = (c < C && i < Lin) ? __ldg(w + static_cast<long long>(c) * Lin + i) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float gv = sG[tk][c];
+      const float4 w4 = *reinterpret_cast<const float4*>(&sW[c][ti * 4]);
+      acc[0] = fmaf(gv, w4.x, acc[0]);
+      acc[1] = fmaf(gv, w4.y, acc[1]);
+      acc[2] = fmaf(gv, w4.z, acc[2]);
+      acc[3] = fmaf(gv, w4.w, acc[3]);
+    }
+  }
+  const int k = k0 + tk;
+  if (k >= KR) return;
+  const int b = k / Nl, j = k - b * Nl;
   const float m = __ldg(mask + b * Nl + j);
-  float acc = 0.f;
-  if (m != 0.f) {
-    for (int c = 0; c < C; ++c) {
-      const long long r = (static_cast<long long>(b) * heads + c / ch) * NlPad + j;
-      acc = fmaf(__ldg(dkbuf + r * C + c), __ldg(wk + static_cast<long long>(c) * Lin + i), acc);
-      acc = fmaf(__ldg(dvbuf + r * C + c), __ldg(wv + static_cast<long long>(c) * Lin + i), acc);
-    }
+  if (m == 0.f) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + ti * 4 + q;
+    if (i < Lin) atomicAdd(dl + (static_cast<long long>(b) * Lin + i) * Nl + j, acc[q] * m);
   }
-  dl[e] += acc * m;
 }
 
 int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* mask, const float* l, const float* wk, const float* wv,
                          float* dwk, float* dbk, float* dwv, float* dbv, float* dl, int B, int Nl, int NlPad, int Lin, int C, int heads,
                          cudaStream_t st) {
   LAVT_REQUIRE(B > 0 && Nl > 0 && Lin > 0 && C > 0 && heads > 0 && C % heads == 0, "pwam kv backward: bad sizes");
-  const long long total = static_cast<long long>(C) * Lin + static_cast<long long>(B) * Lin * Nl;
-  pwam_kv_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dkbuf, dvbuf, mask, l, wk, wv, dwk, dbk, dwv, dbv, dl, B,
-                                                                              Nl, NlPad, Lin, C, heads);
-  LAVT_LAUNCH_CHECK("pwam_kv_bwd_kernel");
+  if (dwk || dwv || dbk || dbv) {
+    dim3 grid(static_cast<unsigned>((Lin + 63) / 64), static_cast<unsigned>((C + 63) / 64));
+    pwam_kv_wgrad_kernel<<<grid, 256, 0, st>>>(dkbuf, dvbuf, mask, l, dwk, dbk, dwv, dbv, B, Nl, NlPad, Lin, C, heads);
+    LAVT_LAUNCH_CHECK("pwam_kv_wgrad_kernel");
+  }
+  if (dl) {
+    const int cchunks = (C + 63) / 64;
+    dim3 grid(static_cast<unsigned>((Lin + 63) / 64), static_cast<unsigned>((B * Nl + 15) / 16), static_cast<unsigned>(min(4, 2 * cchunks)));
+    pwam_kv_dl_kernel<<<grid, 256, 0, st>>>(dkbuf, dvbuf, mask, wk, wv, dl, B, Nl, NlPad, Lin, C, heads);
+    LAVT_LAUNCH_CHECK("pwam_kv_dl_kernel");
+  }
   return LAVT_OK;
 }
 

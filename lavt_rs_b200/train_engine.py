@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import _cabi as K
@@ -209,10 +211,17 @@ def draw_drop_path(rate: float, B: int, device) -> Optional[torch.Tensor]:
     return torch.empty(B, device=device, dtype=torch.float32).bernoulli_(keep).div_(keep)
 
 
+# 0 (default): fc1 saves its pre-activation and the fc2 input-gradient epilogue evaluates GELU' of it; 1: fc1 saves GELU'(pre) in bf16 and
+# the backward multiplies by it.  Same launches and the same time (148 us per stage-2 block for both GEMMs, 218 us with the two GELU
+# kernels of the first version), but the bf16-rounded derivative moved one cancellation-heavy gradient (layers.0.blocks.0.norm1.bias)
+# below the end-to-end direction criterion (cosine 0.934 < 0.95), so the derivative is evaluated in fp32 from the saved pre-activation.
+_GELU_PRE_MODE = int(os.environ.get("LAVT_TRAIN_GELU_PRE_MODE", "0"))
+
+
 def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shifted: bool, clamp: bool, ws: Workspace,
                    xb_out: Optional[torch.Tensor] = None, drop_scales=None):
-    """x fp32 [B*D*H*W, C] (not modified) -> (x_out, saved).  Same kernels as ``engine.swin_block`` except that fc1 stores
-    its pre-activation (GELU runs as its own kernel) and nothing is overwritten.  ``drop_scales`` = (attention-branch scale,
+    """x fp32 [B*D*H*W, C] (not modified) -> (x_out, saved).  Same kernels as ``engine.swin_block`` except that fc1 also stores
+    its pre-activation (second output of the same epilogue; ``hpre`` below) and nothing is overwritten.  ``drop_scales`` = (attention-branch scale,
     MLP-branch scale), fp32 [B] each or None (stochastic depth; drawn here from the block's rate when not given)."""
     n, C = x.shape
     dev = x.device
@@ -253,12 +262,12 @@ def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window,
     h1 = torch.empty(n, C, device=dev, dtype=torch.bfloat16)
     K.layernorm_rows(x1, blk.norm2.weight, blk.norm2.bias, out_bf16=h1, eps=blk.norm2.eps)
     hpre = torch.empty(n, hidden, device=dev, dtype=torch.bfloat16)
-    K.gemm_bf16(h1, fc1_w, bias=blk.mlp.fc1.bias.detach(), out_bf16=hpre)
     hid = torch.empty(n, hidden, device=dev, dtype=torch.bfloat16)
-    K.gelu_fwd(hpre, hid)
+    # one epilogue writes GELU(pre) and the pre-activation (or GELU'(pre), see _GELU_PRE_MODE)
+    K.gemm_bf16(h1, fc1_w, bias=blk.mlp.fc1.bias.detach(), act=K.ACT_GELU, out_bf16=hid, out_pre=hpre, pre_mode=_GELU_PRE_MODE)
     x2 = torch.empty_like(x)
     K.gemm_bf16(hid, fc2_w, bias=blk.mlp.fc2.bias.detach(), resid=x1, out_f32=x2, out_bf16=xb_out, rscale=s_mlp, rscale_rows=tok)
-    _count(8)
+    _count(7)
     return x2, (x, xw, qkv, att, x1, h1, hpre, hid, geom, table_t, s_attn, s_mlp, tok, lse)
 
 
@@ -274,8 +283,9 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
     dyb = ws.get("bw_dyb", (n, C), torch.bfloat16, dev)
     K.cast_rows_bf16(dx, dyb, rscale=s_mlp, rscale_rows=tok)         # DropPath: the branch sees the gradient times its sample's scale
     dhid = ws.get("bw_dhid", (n, hidden), torch.bfloat16, dev)
-    linear_bwd(dyb, hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, grads, ws, pw, "fc2", dx_bf16=dhid)
-    K.gelu_bwd(dhid, hpre, dhid)
+    # d pre = (dy W2) * GELU'(pre) in the epilogue of the input-gradient GEMM (`mul` operand = the saved pre-activation)
+    linear_bwd(dyb, hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, grads, ws, pw, "fc2", dx_bf16=dhid, mul=hpre,
+               mul_act=K.ACT_NONE if _GELU_PRE_MODE else K.ACT_GELU)
     dh1 = ws.get("bw_dh1", (n, C), torch.bfloat16, dev)
     linear_bwd(dhid, h1, blk.mlp.fc1.weight, blk.mlp.fc1.bias, grads, ws, pw, "fc1", dx_bf16=dh1)
     K.layernorm_rows_bwd(x1, dh1, blk.norm2.weight, dx, grads.of(blk.norm2.weight), grads.of(blk.norm2.bias), dres=dx,
@@ -292,7 +302,7 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
     linear_bwd(dqkv, xw, blk.attn.qkv.weight, blk.attn.qkv.bias, grads, ws, pw, "qkv", dx_bf16=dxw)
     K.layernorm_window_gather_bwd(x0, geom, dxw, blk.norm1.weight, dx, grads.of(blk.norm1.weight), grads.of(blk.norm1.bias),
                                   dres=dx, eps=blk.norm1.eps)
-    _count(7)
+    _count(6)
     return dx
 
 
@@ -357,9 +367,8 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     v_w = pw.get("v_w", [att.f_value[0].weight], lambda: _f32(att.f_value[0].weight[:, :, 0]))
 
     vispre = torch.empty(N_, C, device=dev, dtype=bf)
-    K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), out_bf16=vispre)
     vis = torch.empty(B, n, C, device=dev, dtype=bf)
-    K.gelu_fwd(vispre, vis)
+    K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C), out_pre=vispre)
     qpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
     stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
@@ -381,7 +390,7 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     rb = torch.empty(N_, C, device=dev, dtype=bf)
     r32 = torch.empty(N_, C, device=dev, dtype=f32)
     K.gate_elementwise(3, rpre, out_bf16=rb, out_f32=r32)
-    _count(13)
+    _count(12)
     g1 = g2 = xg = None
     if res_gate is not None:
         g0w = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))

@@ -34,7 +34,8 @@ def test_ctypes_binding_covers_header():
 def test_struct_layouts_match_header():
     from lavt_rs_b200 import _cabi
     assert ctypes.sizeof(_cabi.WinGeom) == 17 * 4
-    assert ctypes.sizeof(_cabi.Epilogue) == 8 * 8 + 6 * 4      # 6 data pointers + win + rscale pointers, act/ldm/ldo/_pad/rscale_rows/_pad2
+    assert ctypes.sizeof(_cabi.Epilogue) == 9 * 8 + 6 * 4      # 6 data pointers + win + rscale + out_pre pointers, act/ldm/ldo/mul_act/rscale_rows/pre_mode
+    assert _cabi.Epilogue.mul_act.offset == 60 and _cabi.Epilogue.out_pre.offset == 88
     assert _cabi.Epilogue.win.offset == 64 and _cabi.Epilogue.rscale.offset == 72 and _cabi.Epilogue.rscale_rows.offset == 80
     from lavt_rs_b200.optim import _Tensor
     assert ctypes.sizeof(_Tensor) == 56                         # lavt_adamw_tensor_t: 5 pointers, int64 n, two floats

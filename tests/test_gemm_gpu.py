@@ -38,6 +38,41 @@ def test_gemm_bias_gelu(cabi, M, N, K):
     _close(out, ref, 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 256, 192), (4608, 2048, 512), (1000, 384, 128), (520, 512, 1024)])
+def test_gemm_training_epilogues(cabi, M, N, K):
+    """Training-path epilogues: (1) out_pre = the pre-activation next to the GELU'd output (fc1 forward), (2) mul_act = GELU:
+    the result times GELU'(mul) (fc2 input gradient x derivative of the saved pre-activation; exact-erf GELU, reference :30-36)."""
+    g = torch.Generator(device="cuda").manual_seed(3 * M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, bias=bias, act=cabi.ACT_GELU, out_bf16=out, out_pre=pre)
+    ref_pre = a.float() @ w.float().t() + bias
+    _close(pre, ref_pre, 2e-2)
+    _close(out, F.gelu(ref_pre), 2e-2)
+    # (2): the derivative of GELU at the saved (bf16) pre-activation, spread over [-6, 6]
+    hpre = (3.0 * torch.randn(M, N, device="cuda", generator=g)).bfloat16()
+    x = hpre.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    dgelu = x.grad
+    dh = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, out_bf16=dh, mul=hpre, mul_act=cabi.ACT_GELU)
+    ref = (a.float() @ w.float().t()) * dgelu
+    _close(dh, ref, 2e-2)
+    # (3) pre_mode = 1: the same launch writes GELU(pre) and GELU'(pre)
+    dpre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, bias=bias, act=cabi.ACT_GELU, out_bf16=out, out_pre=dpre, pre_mode=1)
+    x = ref_pre.clone().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    _close(out, F.gelu(ref_pre), 2e-2)
+    _close(dpre, x.grad, 2e-2)
+    # and the plain mul epilogue is unchanged
+    cabi.gemm_bf16(a, w, out_bf16=dh, mul=hpre)
+    _close(dh, (a.float() @ w.float().t()) * hpre.float(), 2e-2)
+
+
 def test_gemm_scale_mul_tanh_resid(cabi):
     M, N, K = 513, 256, 256
     g = torch.Generator(device="cuda").manual_seed(7)
