@@ -11,6 +11,8 @@
 //   gate kernels      x' = x + tanh(.) * r: elementwise adjoints (tanh', relu mask), GELU with an fp32 copy / fp32 gradient in
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace lavt {
 
 __device__ __forceinline__ float gelu_grad(float x) {
@@ -186,6 +188,143 @@ __global__ void __launch_bounds__(256) pwam_attend_bwd_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same adjoint for ONE fusion head and at most 32 (padded) words -- the default configuration (20-token expressions, --mha unset).
+// The kernel above reduces every one of the Nl scores / dP values across the warp separately (2 x Nl x 5 shuffle steps per pixel: at
+// C = 128 the shuffles and the per-word scalar code were 2/3 of its instructions).  Here every lane accumulates the partial dot
+// products of ALL words over its own channels, and one transposing butterfly (31 shuffles for 32 values) leaves the total of word j
+// in lane j; softmax, D = sum_j P_j dP_j and dS then are one value per lane with a warp max / sum.
+template <int CPL>
+__device__ __forceinline__ float words_to_lanes(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+template <int CPL, int NLP>
+__global__ void __launch_bounds__(256, 2) pwam_attend_bwd_h1_kernel(const float* __restrict__ qpre, const float* __restrict__ stats,
+                                                                 const float* __restrict__ k, const float* __restrict__ v,
+                                                                 const float* __restrict__ mask, const __nv_bfloat16* __restrict__ dO,
+                                                                 float* __restrict__ dqhat, __nv_bfloat16* __restrict__ qs_out,
+                                                                 __nv_bfloat16* __restrict__ P_bd, __nv_bfloat16* __restrict__ dS_bd,
+                                                                 float* __restrict__ sums, int B, long long n, int Nl, int NlPad,
+                                                                 float scale) {
+  __shared__ float sPZ[8][2][32];
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int c0 = lane * CPL;
+  const int Wd = B * NlPad;
+  float mu[CPL], rs[CPL], s1[CPL], s2[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    mu[i] = __ldg(stats + (static_cast<long long>(b) * 2) * C + c0 + i);
+    rs[i] = __ldg(stats + (static_cast<long long>(b) * 2 + 1) * C + c0 + i);
+    s1[i] = 0.f;
+    s2[i] = 0.f;
+  }
+  const float* kb = k + static_cast<long long>(b) * Nl * C + c0;
+  const float* vb = v + static_cast<long long>(b) * Nl * C + c0;
+  const float mterm = (lane < Nl) ? (1e4f * __ldg(mask + b * Nl + lane) - 1e4f) : -INFINITY;      // lanes past the last word drop out
+  float* sP = sPZ[warp][0];
+  float* sZ = sPZ[warp][1];
+  const long long total_warps = static_cast<long long>(gridDim.x) * 8;
+  for (long long p = static_cast<long long>(blockIdx.x) * 8 + warp; p < n; p += total_warps) {
+    const long long row = static_cast<long long>(b) * n + p;
+    float qh[CPL], d[CPL], dq[CPL];
+    ld_f32<CPL>(qh, qpre + row * C + c0);
+    ld_bf16<CPL>(d, dO + row * C + c0);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      qh[i] = (qh[i] - mu[i]) * rs[i];
+      dq[i] = 0.f;
+    }
+    float sj, dpj;
+    {
+      float ps[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ps[j] = (j < NLP && j < Nl) ? dot_row<CPL>(qh, kb + static_cast<long long>(j) * C) : 0.f;
+      sj = words_to_lanes<CPL>(ps, lane) * scale + mterm;       // score of word `lane`
+    }
+    {
+      float pd[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pd[j] = (j < NLP && j < Nl) ? dot_row<CPL>(d, vb + static_cast<long long>(j) * C) : 0.f;
+      dpj = words_to_lanes<CPL>(pd, lane);                      // dP of word `lane`
+    }
+    float mx = sj;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float e = (lane < Nl) ? __expf(sj - mx) : 0.f;
+    const float pj = e / warp_sum(e);
+    const float Dsum = warp_sum(pj * dpj);
+    const float dsj = pj * (dpj - Dsum);
+    sP[lane] = pj;
+    sZ[lane] = dsj;
+    // d q^ = scale * sum_j dS_j k_j
+#pragma unroll
+    for (int j = 0; j < NLP; ++j) {
+      if (j < Nl) {
+        const float ds = __shfl_sync(0xffffffffu, dsj, j);
+        float kk[CPL];
+        ld_f32<CPL>(kk, kb + static_cast<long long>(j) * C);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) dq[i] = fmaf(ds, kk[i], dq[i]);
+      }
+    }
+    {
+      float* dst = dqhat + row * C + c0;
+      __nv_bfloat16* qdst = qs_out + row * C + c0;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const float o = dq[i] * scale;
+        dq[i] = o;
+        s1[i] += o;
+        s2[i] = fmaf(o, qh[i], s2[i]);
+      }
+      if constexpr (CPL % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < CPL; i += 4) {
+          *reinterpret_cast<float4*>(dst + i) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+          *reinterpret_cast<uint2*>(qdst + i) = make_uint2(pack_bf16x2(qh[i] * scale, qh[i + 1] * scale), pack_bf16x2(qh[i + 2] * scale, qh[i + 3] * scale));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          dst[i] = dq[i];
+          qdst[i] = __float2bfloat16(qh[i] * scale);
+        }
+      }
+    }
+    __syncwarp();
+    // block-diagonal rows: columns of clip b carry P / dS, all other clips (and the padded words) zero
+    for (int c2 = lane * 2; c2 < Wd; c2 += 64) {
+      const int blk = c2 / NlPad, w = c2 - blk * NlPad;
+      uint32_t pv = 0u, zv = 0u;
+      if (blk == b) {
+        pv = pack_bf16x2(sP[w], sP[w + 1]);
+        zv = pack_bf16x2(sZ[w], sZ[w + 1]);
+      }
+      *reinterpret_cast<uint32_t*>(P_bd + row * Wd + c2) = pv;
+      *reinterpret_cast<uint32_t*>(dS_bd + row * Wd + c2) = zv;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    atomicAdd(sums + (static_cast<long long>(b) * 2) * C + c0 + i, s1[i]);
+    atomicAdd(sums + (static_cast<long long>(b) * 2 + 1) * C + c0 + i, s2[i]);
+  }
+}
+
 int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float* k, const float* v, const float* mask,
                              const __nv_bfloat16* dO, float* dqhat, __nv_bfloat16* qs_out, __nv_bfloat16* P_bd, __nv_bfloat16* dS_bd,
                              float* sums, int B, long long n, int C, int Nl, int NlPad, int heads, cudaStream_t st) {
@@ -198,6 +337,21 @@ int pwam_attend_bwd_dispatch(const float* qpre, const float* stats, const float*
   long long gx = (n + 7) / 8;
   if (gx > 148 * 2) gx = 148 * 2;
   dim3 grid(static_cast<unsigned>(gx), B);
+  // one fusion head, <= 32 words, C = 128: word-per-lane kernel (measured per 4-clip step: stage 0 7.69 -> 7.11 ms; at C = 256 the
+  // 128-register budget spills and stage 1 went 4.70 -> 5.10 ms, at C >= 512 the dot products dominate either way)
+  static const bool h1_off = getenv("LAVT_PWAM_BWD_H1") && atoi(getenv("LAVT_PWAM_BWD_H1")) == 0;
+  static const bool h1_wide = getenv("LAVT_PWAM_BWD_H1") && atoi(getenv("LAVT_PWAM_BWD_H1")) == 2;
+  if (heads == 1 && NlPad <= 32 && (C == 128 || (C == 256 && h1_wide)) && !h1_off) {
+    long long g1 = (n + 7) / 8;
+    if (g1 > 148 * 4) g1 = 148 * 4;
+    dim3 grid1(static_cast<unsigned>(g1), B);
+#define LAVT_PAB_H1(cpl, nlp) pwam_attend_bwd_h1_kernel<cpl, nlp><<<grid1, 256, 0, st>>>(qpre, stats, k, v, mask, dO, dqhat, qs_out, P_bd, dS_bd, sums, B, n, Nl, NlPad, scale)
+    if (C == 128) { if (NlPad <= 24) LAVT_PAB_H1(4, 24); else LAVT_PAB_H1(4, 32); }
+    else { if (NlPad <= 24) LAVT_PAB_H1(8, 24); else LAVT_PAB_H1(8, 32); }
+#undef LAVT_PAB_H1
+    LAVT_LAUNCH_CHECK("pwam_attend_bwd_h1_kernel");
+    return LAVT_OK;
+  }
 #define LAVT_PAB_CASE(cpl)                                                                                             \
   case cpl * 32: {                                                                                                     \
     if (smem > 48 * 1024)                                                                                              \
