@@ -635,14 +635,19 @@ def _cbr_bwd(dec, saved, dt: torch.Tensor, grads: GradStore, ws: Workspace, sync
 
 
 def decoder_fwd(dec, c4, c3, c2, c1, ws: Workspace, sync_bn: bool = False):
-    """NHWC bf16 maps (coarse -> fine) -> (low-resolution logits fp32 [n, H1, W1, 2], saved)."""
-    dev = c1.device
-    n_img = c1.shape[0]
+    """NHWC bf16 maps (coarse -> fine) -> (low-resolution logits fp32 [n, H1, W1, 2], saved).  ``c1`` is None under --lazy_pred: the
+    decoder stops at the 1/8-scale level (reference lib/mask_predictor.py:77)."""
+    dev = c2.device
+    n_img = c2.shape[0]
     hid = dec.conv1_4.weight.shape[0]
+    if (c1 is None) != bool(getattr(dec, "lazy_pred", False)):
+        raise K.LavtError("decoder: the 1/4-scale map is omitted exactly when the decoder was built with --lazy_pred")
     y = c4
     levels = []
-    for skip, (ca, ba, cb, bb) in ((c3, ("conv1_4", "bn1_4", "conv2_4", "bn2_4")), (c2, ("conv1_3", "bn1_3", "conv2_3", "bn2_3")),
-                                   (c1, ("conv1_2", "bn1_2", "conv2_2", "bn2_2"))):
+    plan = [(c3, ("conv1_4", "bn1_4", "conv2_4", "bn2_4")), (c2, ("conv1_3", "bn1_3", "conv2_3", "bn2_3"))]
+    if c1 is not None:
+        plan.append((c1, ("conv1_2", "bn1_2", "conv2_2", "bn2_2")))
+    for skip, (ca, ba, cb, bb) in plan:
         _, H, W, Cs = skip.shape
         if y.shape[1] > H or y.shape[2] > W:
             raise K.LavtError("decoder: coarser map is larger than the skip connection")
@@ -663,7 +668,7 @@ def decoder_fwd(dec, c4, c3, c2, c1, ws: Workspace, sync_bn: bool = False):
 
 def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, sync_bn: bool = False):
     """dlg fp32 [n, H1, W1, 2] -> gradients of (c4, c3, c2, c1) as bf16 row views [n*H_i*W_i, C_i] (c3..c1 are column slices of the
-    concatenated-input gradient, i.e. have a row pitch larger than C_i)."""
+    concatenated-input gradient, i.e. have a row pitch larger than C_i); dc1 is None under --lazy_pred."""
     levels, y, w11 = saved
     dev = dlg.device
     hid = y.shape[-1]
@@ -672,7 +677,7 @@ def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, 
     K.conv1x1_logits_bwd(dlg.view(-1, 2), y.view(-1, hid), w11, dy, grads.of(dec.conv1_1.weight).view(2, hid), grads.of(dec.conv1_1.bias))
     _count(1)
     dskips = []
-    for li in (2, 1, 0):
+    for li in range(len(levels) - 1, -1, -1):
         yshape, s1, s2 = levels[li]
         cat = s1[0]
         n, H, W, Ct = cat.shape
@@ -686,7 +691,8 @@ def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, 
         K.upsample_concat_bwd(dcat, dprev)
         _count(1)
         dy = dprev.view(-1, C1)
-    return (dy, dskips[2], dskips[1], dskips[0])       # dc4, dc3, dc2, dc1
+    dskips = dskips[::-1]                               # coarse -> fine: dc3, dc2(, dc1)
+    return (dy, dskips[0], dskips[1], dskips[2] if len(dskips) > 2 else None)       # dc4, dc3, dc2, dc1
 
 
 # ------------------------------------------------------------------------------------------------

@@ -43,8 +43,11 @@ def _check_trainable(model) -> None:
             raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
     if getattr(model.classifier, "interpolate_before_seg", False):
         raise NotImplementedError("--interpolate_before_seg / --seg_last are inference-only on the B200 path")
-    if tuple(bb.out_indices) != (0, 1, 2, 3):
-        raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3)")
+    lazy = any(getattr(layer, "lazy_pred", False) for layer in bb.layers)
+    if tuple(bb.out_indices) != ((1, 2, 3) if lazy else (0, 1, 2, 3)):
+        raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3), or (1, 2, 3) with --lazy_pred")
+    if lazy != bool(getattr(model.classifier, "lazy_pred", False)):
+        raise NotImplementedError("--lazy_pred: backbone and decoder must both be built with the flag")
 
 
 def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, sync_bn: bool = False):
@@ -84,17 +87,24 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
             xg = torch.empty_like(r32)
             K.gate_elementwise(6, pw_saved["rb"], f=feat, f2=r32, out_f32=xg)
             E._count(1)
-        norm = getattr(bb, f"norm{i}")
-        ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
-        out_src = ((xg if xg is not None else feat) if layer.hs else r32)      # --hs: stage output = gated features instead of the residual
-        K.layernorm_rows(out_src, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
-        E._count(1)
-        maps.append(ob)
+        # --hs: stage output = gated features instead of the residual; --lazy_pred: the features BEFORE fusion (V_i, reference :556-558),
+        # stages 1-3 only (no norm0, no 1/4-scale map)
+        lazy = bool(getattr(layer, "lazy_pred", False))
+        out_src = ((xg if xg is not None else feat) if layer.hs else (feat if lazy else r32))
+        if i in bb.out_indices:
+            norm = getattr(bb, f"norm{i}")
+            ob = torch.empty(B * D, Hc, Wc, C, device=dev, dtype=torch.bfloat16)
+            K.layernorm_rows(out_src, norm.weight, norm.bias, out_bf16=ob.view(n, C), eps=norm.eps)
+            E._count(1)
+            maps.append(ob)
+        else:
+            maps.append(None)
         merge_saved = None
         if not last:
             src = xg if xg is not None else feat
             feat, merge_saved = T.patch_merging_fwd(src, layer.downsample, B, D, Hc, Wc, ws)
-        stages.append((blocks, pw_saved, out_src, merge_saved, gate is not None, bool(layer.hs), layer.version == "no_gate" and xg is not None))
+        stages.append((blocks, pw_saved, out_src, merge_saved, gate is not None, bool(layer.hs), layer.version == "no_gate" and xg is not None,
+                       lazy))
         if not last:
             Hc, Wc = (Hc + 1) // 2, (Wc + 1) // 2
     c1, c2, c3, c4 = maps
@@ -124,8 +134,9 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_
     dx_next: Optional[torch.Tensor] = None
     for i in range(len(bb.layers) - 1, -1, -1):
         layer = bb.layers[i]
-        blocks, pw_saved, out_src, merge_saved, has_gate, hs, plain_add = tape["stages"][i]
-        norm = getattr(bb, f"norm{i}")
+        blocks, pw_saved, out_src, merge_saved, has_gate, hs, plain_add, lazy = tape["stages"][i]
+        norm = getattr(bb, f"norm{i}", None)
+        has_out = i in bb.out_indices
         dxg = None
         if merge_saved is not None:
             dxg = T.patch_merging_bwd(layer.downsample, merge_saved, dx_next, grads, ws)
@@ -136,6 +147,8 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_
                 K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dxg, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
             else:
                 K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dxg, grads.of(norm.weight), grads.of(norm.bias), dres=dxg, eps=norm.eps)
+        elif lazy:
+            dr = None      # the stage output is V_i: its gradient joins the stream gradient AFTER the fusion's adjoint (below)
         else:
             dr = torch.empty_like(out_src)
             K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dr, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
@@ -146,17 +159,25 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_
             else:
                 K.gate_elementwise(6, pw_saved["rb"], f=dr, f2=dxg, out_f32=dr)
             E._count(1)
-        if dr is None and not has_gate:
-            dx = dxg        # --hs without a gate: x' = x and the fusion output is unused (no gradient for its parameters)
+        if dr is None and (not has_gate or dxg is None):
+            dx = dxg        # --hs without a gate: x' = x and the fusion output is unused (no gradient for its parameters);
+                            # --lazy_pred at the last stage: nothing downstream reads the fusion (dxg is None)
         else:
             fuse_bwd = T.sep_t_pwam_gate_bwd if layer.sep_t_pwam else T.pwam_gate_bwd
             # without a gate on this stage x feeds the next stage directly, so dxg is the residual-stream gradient itself
             dx = fuse_bwd(layer.fusion, layer.res_gate if has_gate else None, pw_saved, dr, dxg, grads, ws, dl)
+        if lazy and has_out:       # d V_i: LayerNorm adjoint of the stage output, added to the gradient that came back through the fusion
+            if dx is None:
+                dx = torch.empty_like(out_src)
+                K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dx, grads.of(norm.weight), grads.of(norm.bias), eps=norm.eps)
+            else:
+                K.layernorm_rows_bwd(out_src, dcs[3 - i], norm.weight, dx, grads.of(norm.weight), grads.of(norm.bias), dres=dx, eps=norm.eps)
+            E._count(1)
         for bi in range(layer.depth - 1, -1, -1):
             dx = T.swin_block_bwd(layer.blocks[bi], blocks[bi], dx, grads, ws)
         dx_next = dx
         if on_ready is not None:
-            on_ready(list(layer.parameters()) + list(norm.parameters()))
+            on_ready(list(layer.parameters()) + (list(norm.parameters()) if norm is not None else []))
     T.patch_embed_bwd(bb.patch_embed, tape["pe"], dx_next, grads, ws)
     if on_ready is not None:
         on_ready(list(bb.patch_embed.parameters()))

@@ -878,6 +878,53 @@ def test_version_ablation_training_step(version):
     check_direction(got, {k: v.grad for k, v in leaf.items() if v.grad is not None}, f"--version {version} training step")
 
 
+def test_lazy_pred_training_step():
+    """--lazy_pred in training mode (reference lib/video_swin_transformer.py:556-558, lib/mask_predictor.py:77): the decoder reads
+    norm_i(V_i) of stages 1-3 (features BEFORE fusion), the fusion residual only feeds the gate, the last stage's fusion is dead code
+    and the logits come from the 1/8-scale level.  Loss, every parameter gradient and d l_feats vs autograd through the oracle."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    args = default_args(["--lazy_pred"])
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), lazy_pred=True)
+    sd = O.random_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(5)
+    for k in list(sd):      # a zero-initialised gate passes no gradient to the fusion: random gate weights (as in the unit test)
+        if "res_gate" in k and k.endswith("weight"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * sd[k].shape[1] ** -0.5
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, out_indices=(1, 2, 3), args=args)
+    dec = SimpleDecoding(1024, args)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    B, Tn, H, W, Nl = 2, 4, 64, 96, 10
+    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    m[1, Nl - 3:] = 0
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    lq = l.clone().requires_grad_(True)
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, lq, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, dl = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    dead = [k for k in ref if k.startswith("backbone.layers.3.fusion") and ref[k].abs().max() > 0]
+    assert not dead, f"the last stage's fusion is unused under --lazy_pred, yet the oracle has gradients for {dead[:3]}"
+    check_direction(got, ref, "--lazy_pred training step")
+    c, ratio = cos_and_ratio(dl, lq.grad)
+    assert c > 0.95 and 0.85 < ratio < 1.18, ("d l_feats", c, ratio)
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""
