@@ -269,10 +269,11 @@ class KernelTimer:
         torch.cuda.synchronize()
         out = {}
         for fam, fl, nb, s, e, tag in self.records:
-            d = out.setdefault((fam, tag), {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d = out.setdefault((fam, tag), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
+            d["bytes"] += nb
         return out
 
     def summary(self, peak_tflops: float = 0.0, peak_gbs: float = 0.0):

@@ -31,5 +31,5 @@ with torch.no_grad():
     rows = K.TIMER.by_tag()
 tot = sum(v["ms"] for v in rows.values())
 for (fam, tag), v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"]):
-    print(f"{fam[:12]:12s} {tag:38s} x{v['launches']:3d} {v['ms']:8.3f} ms {100*v['ms']/tot:5.1f}%  {v['flops']/max(v['ms'],1e-9)/1e9:8.1f} TF")
+    print(f"{fam[:12]:12s} {tag:38s} x{v['launches']:3d} {v['ms']:8.3f} ms {100*v['ms']/tot:5.1f}%  {v['flops']/max(v['ms'],1e-9)/1e9:8.1f} TF {v['bytes']/max(v['ms'],1e-9)/1e6:7.0f} GB/s")
 print("timed kernels total ms", tot)
