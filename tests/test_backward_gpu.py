@@ -878,7 +878,8 @@ def test_version_ablation_training_step(version):
     check_direction(got, {k: v.grad for k, v in leaf.items() if v.grad is not None}, f"--version {version} training step")
 
 
-def test_lazy_pred_training_step():
+@pytest.mark.parametrize("video", [True, False])
+def test_lazy_pred_training_step(video):
     """--lazy_pred in training mode (reference lib/video_swin_transformer.py:556-558, lib/mask_predictor.py:77): the decoder reads
     norm_i(V_i) of stages 1-3 (features BEFORE fusion), the fusion residual only feeds the gate, the last stage's fusion is dead code
     and the logits come from the 1/8-scale level.  Loss, every parameter gradient and d l_feats vs autograd through the oracle."""
@@ -889,21 +890,24 @@ def test_lazy_pred_training_step():
     from lavt_rs_b200.args import default_args
     from lavt_rs_b200 import training as TR
     from lavt_rs_b200 import train_engine as T
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
     args = default_args(["--lazy_pred"])
-    cfg = O.OracleConfig(depths=(2, 2, 2, 2), lazy_pred=True)
+    cfg = (O.OracleConfig(depths=(2, 2, 2, 2), lazy_pred=True) if video else
+           O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, lazy_pred=True))
     sd = O.random_state_dict(cfg, seed=0)
     g = torch.Generator().manual_seed(5)
     for k in list(sd):      # a zero-initialised gate passes no gradient to the fusion: random gate weights (as in the unit test)
         if "res_gate" in k and k.endswith("weight"):
             sd[k] = torch.randn(sd[k].shape, generator=g) * sd[k].shape[1] ** -0.5
-    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
-                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, out_indices=(1, 2, 3), args=args)
+    kw = dict(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], drop_path_rate=0.0, patch_norm=True, out_indices=(1, 2, 3), args=args)
+    bb = (MultiModalSwinTransformer3D(patch_size=(1, 4, 4), window_size=(8, 7, 7), **kw) if video
+          else MultiModalSwinTransformer(window_size=7, num_heads_fusion=[1, 1, 1, 1], **kw))
     dec = SimpleDecoding(1024, args)
     load_reference_state_dict(bb, sd, "backbone.")
     load_reference_state_dict(dec, sd, "classifier.")
     model = LAVT(bb, dec).cuda().train()
-    B, Tn, H, W, Nl = 2, 4, 64, 96, 10
-    x = torch.randn(B, Tn, 3, H, W, generator=g)
+    B, Tn, H, W, Nl = (2, 4, 64, 96, 10) if video else (3, 1, 160, 128, 10)
+    x = torch.randn(B, Tn, 3, H, W, generator=g) if video else torch.randn(B, 3, H, W, generator=g)
     l = torch.randn(B, 768, Nl, generator=g)
     m = torch.ones(B, Nl)
     m[1, Nl - 3:] = 0

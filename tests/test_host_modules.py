@@ -107,14 +107,16 @@ def test_lazy_pred_state_dict_matches_oracle_contract():
 
 
 def test_inference_only_variants_refuse_training():
-    """The lib/bcam.py fusions and --lazy_pred have no hand-written backward: the training entry point must refuse them up front."""
+    """The lib/bcam.py fusions, the BN / LN / none attention norms and the decoder tails have no hand-written backward: the training
+    entry point must refuse them up front.  --lazy_pred trains (tests/test_backward_gpu.py::test_lazy_pred_training_step)."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--lazy_pred"], ["--att_norm_layer_type", "LN"], ["--interpolate_before_seg"]):
+    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "LN"], ["--interpolate_before_seg"]):
         m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
+    training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lazy_pred"])))
     # the sigmoid gate trains (gate adjoint modes 7 / 8 of lavt_gate_elementwise)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lg_act_layer", "sigmoid"])))
 
