@@ -463,7 +463,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (!live || c >= nch) continue;
         float f[32];
-        {
+        if (p.cscale) {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
           const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
@@ -473,6 +473,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             upk2(fma2(pk2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), pk2(sc.z, sc.w), pk2(bi.z, bi.w)), f[4 * q + 2],
                  f[4 * q + 3]);
           }
+        } else if (p.bias) {       // no column scale (most launches): half the shared-memory loads of the staged vectors
+          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bi = bi4[q];
+            f[4 * q] = __uint_as_float(v[4 * q]) + bi.x;
+            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bi.y;
+            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bi.z;
+            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bi.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
         if (op_row && p.pre_mode == 1) {     // training forward of fc1: GELU(pre) and GELU'(pre) from one polynomial
 #pragma unroll
