@@ -274,7 +274,7 @@ def main():
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None, "launches": g["launches"], "ms_per_step": g["ms"],
                      "alg_flops_per_step": g["flops"],
-                     "attention_bwd": {"kernel": "window_attn_bwd_kernel (mma.sync)", "launches": ab["launches"], "ms_per_step": ab["ms"],
+                     "attention_bwd": {"kernel": "window_attn_bwd_tc_kernel (tcgen05 / TMEM; 7 x 7 windows with saved row statistics) / window_attn_bwd_kernel (mma.sync, other windows)", "launches": ab["launches"], "ms_per_step": ab["ms"],
                                        "tflops": ab["flops"] / (ab["ms"] * 1e-3) / 1e12 if ab["ms"] > 0 else 0.0},
                      "attention_fwd": {"launches": af["launches"], "ms_per_step": af["ms"]},
                      "whole_step_tflops": flops_clip * value / world / 1e12},
