@@ -155,7 +155,11 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
 }
 
-template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS, int CTA2 = 0>
+// SIMPLE = 1: the epilogue is compiled for bias / column scale + activation + bf16 output in GEMM-row order only (no mul, residual, DropPath
+// scale, fp32 or pre-activation output, no row map), which leaves room for FOUR epilogue warpgroups (640 threads, <= 102 registers): the
+// epilogue of the short-K launches is a flat chain of dependent-issue latencies at 2 warps per scheduler (ncu: issue slots 28 %, no dominant
+// stall), so it needs warps, not bandwidth.
+template <int GEMM_BN, int GEMM_STAGES, int EPI_WGS, int CTA2 = 0, int SIMPLE = 0>
 __global__ void __launch_bounds__(GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS, CTA2>::THREADS, GemmSmem<GEMM_BN, GEMM_STAGES, EPI_WGS, CTA2>::MIN_CTAS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p, const int m_tiles, const int vec_all, long long* const trace_buf) {
@@ -407,7 +411,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
 
       long long m = -1, orow = -1;
-      if (p.rowmap == ROWMAP_CONV) {
+      if (!SIMPLE && p.rowmap == ROWMAP_CONV) {
         const int tw = mt % p.cTilesW;
         const int th = (mt / p.cTilesW) % p.cTilesH;
         const int img = mt / (p.cTilesW * p.cTilesH);
@@ -420,16 +424,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long mm = static_cast<long long>(mt) * GEMM_BM + r;
         if (mm < p.M) {
           m = mm;
-          orow = (p.rowmap == ROWMAP_WINDOW) ? win_token(p.win, mm).row : mm;
+          orow = (!SIMPLE && p.rowmap == ROWMAP_WINDOW) ? win_token(p.win, mm).row : mm;
         }
       }
       const bool live = (orow >= 0);
-      const float row_scale = (p.rscale && live) ? __ldg(p.rscale + orow / p.rs_rows) : 1.0f;
-      const __nv_bfloat16* mul_row = (p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
-      const float* res_row = (p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
-      float* of_row = (p.out_f32 && live) ? p.out_f32 + ks * p.split_stride + orow * p.ldo + n0 : nullptr;
+      const float row_scale = (!SIMPLE && p.rscale && live) ? __ldg(p.rscale + orow / p.rs_rows) : 1.0f;
+      const __nv_bfloat16* mul_row = (!SIMPLE && p.mul && live) ? p.mul + m * p.ldm + n0 : nullptr;
+      const float* res_row = (!SIMPLE && p.resid && live) ? p.resid + orow * p.ldo + n0 : nullptr;
+      float* of_row = (!SIMPLE && p.out_f32 && live) ? p.out_f32 + ks * p.split_stride + orow * p.ldo + n0 : nullptr;
       __nv_bfloat16* ob_row = (p.out_bf16 && live) ? p.out_bf16 + orow * p.ldo + n0 : nullptr;
-      __nv_bfloat16* op_row = (p.out_pre && live) ? p.out_pre + orow * p.ldo + n0 : nullptr;
+      __nv_bfloat16* op_row = (!SIMPLE && p.out_pre && live) ? p.out_pre + orow * p.ldo + n0 : nullptr;
 
       const uint32_t tbase = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(ew * 32) << 16);
       bool acc_ready = false;
@@ -516,10 +520,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (p.act == ACT_TANH) {
+        } else if (!SIMPLE && p.act == ACT_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
-        } else if (p.act == ACT_SIGMOID) {       // sigmoid(x) = 0.5 tanh(x / 2) + 0.5
+        } else if (!SIMPLE && p.act == ACT_SIGMOID) {       // sigmoid(x) = 0.5 tanh(x / 2) + 0.5
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaf(0.5f, tanh_fast(0.5f * f[j]), 0.5f);
         }
@@ -537,7 +541,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (p.rscale) {       // DropPath: the whole branch of a dropped sample is scaled (0 or 1 / keep_prob) before the shortcut add
+        if (!SIMPLE && p.rscale) {       // DropPath: the whole branch of a dropped sample is scaled (0 or 1 / keep_prob) before the shortcut add
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= row_scale;
         }
@@ -591,10 +595,10 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI_WGS, int CTA2 = 0>
+template <int BN, int STAGES, int EPI_WGS, int CTA2 = 0, int SIMPLE = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI_WGS, CTA2>;
-  auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS, CTA2>;
+  auto kfn = gemm_bf16_tc_kernel<BN, STAGES, EPI_WGS, CTA2, SIMPLE>;
   // stage scale / bias of all N columns when that fits next to the operand ring (per-CTA budget: the whole SM, or half of
   // it for the 2-CTAs/SM variant); otherwise the kernel refills a per-tile staging area
   const int budget = (L::MIN_CTAS == 1 ? 227 * 1024 : 113 * 1024) - (L::VEC_OFF + 1024);
@@ -669,6 +673,18 @@ static int gemm_variant(const GemmParams& p) {
   }
   if (v == 4 && ((p.N % 256) != 0 || p.mnmajor || p.ksplit > 1 || p.rowmap == ROWMAP_WGCONV)) v = 2;
   if (v == 2 && (p.N % 256) != 0) v = 0;
+  // 6: four epilogue warpgroups with the plain bf16-output epilogue for the short-K, output-bound launches of stages 0 / 1 (measured:
+  //    qkv M 614656 x N 384 x K 128: 185 -> 138 us, fc1 + GELU M 589824 x N 512 x K 128: 294 -> 236 us; at K = 512 the 128-wide tiles lose:
+  //    fc1 104 -> 115 us).  A TMA-store epilogue (64-column halves staged in 128-byte-swizzled shared memory, parity-green) did NOT help
+  //    these launches (185 -> 185 us): their L1 store wavefronts (ncu: LSU data pipe 68 %) were never what the epilogue warps waited for.
+  static int simple_kmax = -1;
+  if (simple_kmax < 0) {
+    const char* e = getenv("LAVT_GEMM_SIMPLE_KMAX");
+    simple_kmax = e ? atoi(e) : 256;
+  }
+  if (forced < 0 && p.rowmap == ROWMAP_IDENTITY && !p.mnmajor && p.ksplit <= 1 && p.K <= simple_kmax && p.out_bf16 && !p.out_f32 && !p.out_pre &&
+      !p.mul && !p.resid && !p.rscale && p.act <= ACT_RELU && p.M >= 32768)
+    v = 6;
   return v;
 }
 
@@ -762,6 +778,7 @@ int gemm_dispatch(const void* A, long long lda, const void* Bw, long long ldb, c
     if (rc) return rc;
   }
   const int variant = gemm_variant(p);
+  if (variant == 6) return launch_gemm<128, 6, 4, 0, 1>(tmA, tmB, p, m_tiles, stream);
   if (variant == 1) return launch_gemm<128, 3, 1>(tmA, tmB, p, m_tiles, stream);
   if (variant == 2) return launch_gemm<256, 4, 2>(tmA, tmB, p, m_tiles, stream);
   if (variant == 4) return launch_gemm<256, 6, 2, 1>(tmA, tmB, p, m_tiles, stream);

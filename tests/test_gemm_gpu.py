@@ -73,6 +73,35 @@ def test_gemm_training_epilogues(cabi, M, N, K):
     _close(dh, (a.float() @ w.float().t()) * hpre.float(), 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(40000, 384, 128, 0), (32768, 512, 128, 1), (33000, 192, 256, 0), (36864, 1024, 256, 1), (50000, 64, 64, 2)])
+def test_gemm_short_k_four_warpgroup_epilogue(cabi, M, N, K, act):
+    """Short-K launches with a plain bf16 output in GEMM-row order (M >= 32768, K <= 256; bias / scale / GELU / ReLU only) run the
+    four-epilogue-warpgroup instantiation of the GEMM: partial row tiles, partial column tiles (N = 192: one and a half 128-wide tiles),
+    bit-identical to the general epilogue; launches with mul / a wider output pitch stay on the general path."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M + 8, N), 7.0, device="cuda", dtype=torch.bfloat16)     # rows past M must stay untouched
+    cabi.gemm_bf16(a, w, bias=bias, act=act, out_bf16=out[:M])
+    pre = a.float() @ w.float().t() + bias
+    ref = F.gelu(pre) if act == 1 else torch.relu(pre) if act == 2 else pre
+    _close(out[:M], ref, 2e-2)
+    assert (out[M:] == 7.0).all()
+    # scale + mul + residual, output pitch larger than N (column window of a wider buffer)
+    cs = torch.rand(N, device="cuda", generator=g) + 0.5
+    mul = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    wide = torch.full((M, N + 64), 3.0, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, cscale=cs, mul=mul, out_bf16=wide[:, :N])
+    _close(wide[:, :N], (a.float() @ w.float().t()) * cs * mul.float(), 2e-2)
+    assert (wide[:, N:] == 3.0).all()
+    # the general epilogue gives the same bits (compared through a launch the variant does not take: an fp32 + bf16 dual output)
+    o32 = torch.empty(M, N, device="cuda")
+    ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.gemm_bf16(a, w, bias=bias, act=act, out_f32=o32, out_bf16=ob)
+    assert torch.equal(ob, out[:M])
+
+
 def test_gemm_scale_mul_tanh_resid(cabi):
     M, N, K = 513, 256, 256
     g = torch.Generator(device="cuda").manual_seed(7)
