@@ -50,8 +50,10 @@ def _check_trainable(model) -> None:
         raise NotImplementedError("--lazy_pred: backbone and decoder must both be built with the flag")
 
 
-def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, sync_bn: bool = False):
+def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch.Tensor, sync_bn: bool = False, lang_ready=None):
     """Forward of the hot path with saved activations.  x (B,T,3,H,W) fp32 (video) or (B,3,H,W) (image); l_feats (B,768,Nl); l_mask (B,Nl[,1]).
+    ``lang_ready``: optional CUDA event after which ``l_feats`` is valid (a text encoder running on a side stream): the stream waits for
+    it right before the first fusion, i.e. the patch embedding and the Swin blocks of stage 0 run under the text encoder.
     Returns (logits fp32 (B*T,2,H,W), tape)."""
     from .lib.video_swin_transformer import _lang, _mask, _planes
     _check_trainable(model)
@@ -59,7 +61,7 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
     bb, dec = model.backbone, model.classifier
     dev = x.device
     ws = E.workspace(dev)
-    l = _lang(l_feats)
+    l = None               # read at the first fusion (after ``lang_ready``)
     mask = _mask(l_mask)
     # video: (B,T,3,H,W) -> (B,3,T,H,W) view; image models (lavt / lavt_one): (B,3,H,W) -> one frame, windows (1,w,w) never clamped
     x5 = _planes(x).permute(0, 2, 1, 3, 4) if x.dim() == 5 else _planes(x).unsqueeze(2)
@@ -79,6 +81,10 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
         last = layer.downsample is None
         # the last stage's gated features are unused (:570-587) unless --hs makes them the stage output (:579-587)
         gate = layer.res_gate if (layer.has_gate and (not last or layer.hs)) else None
+        if l is None:
+            if lang_ready is not None:
+                torch.cuda.current_stream().wait_event(lang_ready)
+            l = _lang(l_feats)
         if layer.sep_t_pwam:
             r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
         else:
@@ -116,10 +122,12 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
     return logits, tape
 
 
-def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_ready=None) -> torch.Tensor:
+def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_ready=None, on_dl_ready=None) -> torch.Tensor:
     """dlogits fp32 (B*T,2,H,W) -> parameter gradients in ``grads``; returns the gradient of l_feats (B,768,Nl).
     ``on_ready(params)`` is called as soon as the gradients of a group of parameters are complete (decoder, then each stage from the
-    last to the first, then the patch embedding) so that their all-reduce can overlap the rest of the backward (``GradReducer``)."""
+    last to the first, then the patch embedding) so that their all-reduce can overlap the rest of the backward (``GradReducer``).
+    ``on_dl_ready(dl)`` is called as soon as the gradient of l_feats is final (after the adjoint of stage 0's fusion): the text encoder's
+    backward can then run on a side stream under the backward of stage 0's Swin blocks and of the patch embedding."""
     bb, dec = model.backbone, model.classifier
     dev = dlogits.device
     ws = E.workspace(dev)
@@ -166,6 +174,8 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_
             fuse_bwd = T.sep_t_pwam_gate_bwd if layer.sep_t_pwam else T.pwam_gate_bwd
             # without a gate on this stage x feeds the next stage directly, so dxg is the residual-stream gradient itself
             dx = fuse_bwd(layer.fusion, layer.res_gate if has_gate else None, pw_saved, dr, dxg, grads, ws, dl)
+        if i == 0 and on_dl_ready is not None:
+            on_dl_ready(dl)
         if lazy and has_out:       # d V_i: LayerNorm adjoint of the stage output, added to the gradient that came back through the fusion
             if dx is None:
                 dx = torch.empty_like(out_src)
@@ -185,16 +195,58 @@ def segment_backward(model, tape, dlogits: torch.Tensor, grads: T.GradStore, on_
 
 
 def segment_forward_backward(model, x, l_feats, l_mask, target: torch.Tensor, grads: T.GradStore, sync_bn: bool = False,
-                             loss_scale: float = 1.0, on_ready=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One fused fwd + loss + bwd of the hot path.  target int64 (B*T,H,W) in {0,1}.  Returns (loss as a 0-d CUDA tensor, dl_feats)."""
-    logits, tape = segment_forward(model, x, l_feats, l_mask, sync_bn)
+                             loss_scale: float = 1.0, on_ready=None, lang_ready=None, on_dl_ready=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One fused fwd + loss + bwd of the hot path.  target int64 (B*T,H,W) in {0,1}.  Returns (loss as a 0-d CUDA tensor, dl_feats).
+    ``lang_ready`` / ``on_dl_ready``: see ``segment_forward`` / ``segment_backward`` (``SideStreamText`` provides both)."""
+    logits, tape = segment_forward(model, x, l_feats, l_mask, sync_bn, lang_ready)
     acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
     K.cross_entropy(logits, target, acc, phase=0)
     dlogits = torch.empty_like(logits)
     K.cross_entropy(logits, target, acc, dlogits, gscale=loss_scale, phase=1)
     E._count(2)
-    dl = segment_backward(model, tape, dlogits, grads, on_ready)
+    dl = segment_backward(model, tape, dlogits, grads, on_ready, on_dl_ready)
     return acc[0] / acc[1], dl
+
+
+class SideStreamText:
+    """The text encoder's forward and backward on a side stream around ``segment_forward_backward``.  BERT-base on a few sentences is
+    ~600 tiny launches in each direction (2.5 + 3.2 ms per step even as CUDA graphs) that use a handful of SMs: the forward hides under the
+    patch embedding and the Swin blocks of stage 0 (the hot path needs l_feats at the first fusion), the backward under the backward of
+    stage 0's Swin blocks and of the patch embedding (d l_feats is final after the adjoint of stage 0's fusion).
+
+        side = SideStreamText(device)
+        l_feats, ready = side.forward(text_fn, ids, mask)
+        loss, dl = segment_forward_backward(model, x, l_feats.detach(), mask, target, grads, lang_ready=ready, on_dl_ready=side.backward_hook())
+        side.join()                      # before the optimizer / the text encoder's gradient all-reduce
+    """
+
+    def __init__(self, device):
+        self.side = torch.cuda.Stream(device=device, priority=-1)      # its tiny kernels go first whenever SMs free up
+        self.l_feats = None
+        self._keep = []
+
+    def forward(self, text_fn, ids, mask):
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.l_feats = text_fn(ids, mask)
+            ready = torch.cuda.Event()
+            ready.record(self.side)
+        return self.l_feats, ready
+
+    def backward_hook(self):
+        def hook(dl):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.side.wait_event(ev)
+            self._keep.append(dl)                 # allocated on the main stream, read on the side stream: alive until join()
+            with torch.cuda.stream(self.side):
+                self.l_feats.backward(dl)
+        return hook
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.l_feats = None
+        self._keep.clear()
 
 
 class SegmentFunction(torch.autograd.Function):

@@ -929,6 +929,88 @@ def test_lazy_pred_training_step(video):
     assert c > 0.95 and 0.85 < ratio < 1.18, ("d l_feats", c, ratio)
 
 
+def test_text_encoder_on_side_stream():
+    """``training.SideStreamText``: the text encoder's forward runs on a side stream under patch embedding + stage 0 (the hot path waits for
+    its event at the first fusion) and its backward under the backward of stage 0's Swin blocks (``on_dl_ready``).  Same loss, d l_feats,
+    hot-path gradients and text-encoder gradients as the serial order (a small autograd module stands in for BERT)."""
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2))
+    sd = O.random_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(3)
+    for k in list(sd):
+        if "res_gate" in k and k.endswith("weight"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * sd[k].shape[1] ** -0.5
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=None)
+    dec = SimpleDecoding(1024, None)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    B, Tn, H, W, Nl = 2, 4, 64, 96, 12
+    x = torch.randn(B, Tn, 3, H, W, generator=g).cuda()
+    m = torch.ones(B, Nl).cuda()
+    target = torch.randint(0, 2, (B * Tn, H, W), generator=g).cuda()
+    ids = torch.randint(0, 100, (B, Nl), generator=g).cuda()
+    torch.manual_seed(0)
+    emb = torch.nn.Embedding(100, 768).cuda()
+    lin = torch.nn.Linear(768, 768).cuda()
+    text_params = list(emb.parameters()) + list(lin.parameters())
+
+    def text_fn(ids_, mask_):
+        h = torch.tanh(lin(emb(ids_)))
+        for _ in range(20):                       # a few hundred small launches, like the real encoder
+            h = torch.tanh(lin(h)) + h
+        return h.permute(0, 2, 1)
+
+    def run(side_stream: bool):
+        for prm in text_params:
+            prm.grad = None
+        bn = {k: v.clone() for k, v in model.named_buffers()}
+        grads = T.GradStore()
+        if side_stream:
+            side = TR.SideStreamText(x.device)
+            l_feats, ready = side.forward(text_fn, ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, target, grads, lang_ready=ready, on_dl_ready=side.backward_hook())
+            side.join()
+        else:
+            l_feats = text_fn(ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, target, grads)
+            l_feats.backward(dl)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for k, v in model.named_buffers():     # BatchNorm running statistics moved: both runs start from the same model
+                v.copy_(bn[k])
+        got = {k: v.clone() for k, v in grads.named(bb).items()}
+        return loss.item(), dl.clone(), got, [prm.grad.clone() for prm in text_params]
+
+    # Two serial runs differ too: fp32 atomics (InstanceNorm / LayerNorm reductions) sum in a different order and bf16 roundings downstream
+    # of them flip.  That run-to-run noise is the yardstick: the side-stream runs must stay within 3x of it.
+    loss0, dl0, g0, t0 = run(False)
+    loss0b, dl0b, g0b, t0b = run(False)
+    big = max(v.float().norm().item() for v in g0.values())
+
+    def dist(ga, gb):
+        return {k: (ga[k].float() - gb[k].float()).norm().item() for k in ga}
+    noise_dl = rel_l2(dl0b, dl0)
+    noise_t = max(rel_l2(a_, b_) for a_, b_ in zip(t0b, t0))
+    noise_g = dist(g0b, g0)
+    assert noise_dl < 2e-2 and noise_t < 2e-2, (noise_dl, noise_t)
+    for _ in range(3):                             # repeated: a missing stream dependency shows up as a flaky mismatch
+        loss1, dl1, g1, t1 = run(True)
+        assert abs(loss0 - loss1) < 1e-5 * abs(loss0)
+        assert rel_l2(dl1, dl0) < 3 * noise_dl + 1e-4, (rel_l2(dl1, dl0), noise_dl)
+        for a_, b_ in zip(t1, t0):
+            assert rel_l2(a_, b_) < 3 * noise_t + 1e-4, (rel_l2(a_, b_), noise_t)
+        d1 = dist(g1, g0)
+        for k in g0:
+            assert d1[k] <= 3 * noise_g[k] + 1e-3 * g0[k].float().norm().item() + 1e-5 * big, (k, d1[k], noise_g[k])
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""

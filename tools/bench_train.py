@@ -41,6 +41,8 @@ def main():
     p.add_argument("--bf16-allreduce", action="store_true", help="cast the gradient buckets to bf16 for the all-reduce")
     p.add_argument("--graph", action="store_true", help="capture forward + loss + backward of the hot path (everything after the text encoder) "
                                                         "in one CUDA graph (1 GPU only: SyncBN / gradient collectives stay eager)")
+    p.add_argument("--serial-text", action="store_true", help="text encoder forward / backward on the main stream, before / after the hot path, "
+                   "instead of on a side stream under stage 0 (default)")
     p.add_argument("--eager-text", action="store_true", help="run the text encoder eagerly instead of as CUDA graphs")
     p.add_argument("--phases", action="store_true", help="print CUDA-event times of the phases of one step to stderr")
     p.add_argument("--by-tag", action="store_true", help="print the CUDA-event time of every GEMM / attention shape of one step to stderr")
@@ -143,13 +145,23 @@ def main():
         x, ids, m, tgt = batches[i % 2]
         for prm in params:
             prm.grad = None                                                    # optimizer.zero_grad(set_to_none=True)
-        l_feats = text_fn(ids, m)
         grads = T.GradStore(params)
         reducer = TR.GradReducer(overlap=a.overlap_allreduce, compress="bf16" if a.bf16_allreduce else None)
-        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
-        grads.finalize()
+        if a.serial_text or a.frozen_text or K.TIMER.enabled:
+            l_feats = text_fn(ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
+            grads.finalize()
+            if not a.frozen_text:
+                l_feats.backward(dl)
+        else:
+            # text encoder forward / backward on a side stream, under stage 0 of the hot path (TR.SideStreamText)
+            side = state.setdefault("side", TR.SideStreamText(dev))
+            l_feats, ready = side.forward(text_fn, ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads),
+                                                   lang_ready=ready, on_dl_ready=side.backward_hook())
+            grads.finalize()
+            side.join()
         if not a.frozen_text:
-            l_feats.backward(dl)
             reducer.reduce([prm for prm in text.parameters() if prm.requires_grad], grads)
         reducer.wait()
         if opt is not None:
