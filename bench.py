@@ -254,16 +254,33 @@ def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, st
         batches.append((x.to(dev), ids.to(dev), m.to(dev), tgt.to(dev)))
     state = {}
 
+    # the text encoder (stock transformers module under autograd, ~600 tiny launches per direction) replays as two CUDA graphs on a side
+    # stream under stage 0 of the hot path, like tools/bench_train.py; eager on the main stream if the capture is not possible
+    text_fn = lambda ids_, m_: text(ids_, attention_mask=m_)[0].permute(0, 2, 1)       # noqa: E731  lib/_utils.py:98-100
+    side = None
+    try:
+        text_fn = TR.GraphedTextEncoder(text, batches[0][1], batches[0][2])
+        side = TR.SideStreamText(dev)
+    except Exception as exc:       # noqa: BLE001
+        print(f"train_step extra: text encoder not graph-captured ({type(exc).__name__}: {exc}); running it eagerly", file=sys.stderr)
+
     def step(i):
         x, ids, m, tgt = batches[i % 2]
         for p in params:
             p.grad = None
-        l_feats = text(ids, attention_mask=m)[0].permute(0, 2, 1)
         grads = T.GradStore(seg_params)
         reducer = TR.GradReducer(overlap=True)
-        loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
-        grads.finalize()
-        l_feats.backward(dl)
+        if side is not None:
+            l_feats, ready = side.forward(text_fn, ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads),
+                                                   lang_ready=ready, on_dl_ready=side.backward_hook())
+            grads.finalize()
+            side.join()
+        else:
+            l_feats = text_fn(ids, m)
+            loss, dl = TR.segment_forward_backward(model, x, l_feats.detach(), m, tgt, grads, sync_bn=world > 1, on_ready=reducer.ready(grads))
+            grads.finalize()
+            l_feats.backward(dl)
         reducer.reduce([p for p in text.parameters() if p.requires_grad], grads)
         reducer.wait()
         state["loss"] = loss
