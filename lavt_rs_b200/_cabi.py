@@ -190,7 +190,13 @@ def check(rc: int, what: str) -> None:
         raise LavtError(f"{what} failed (code {rc}): {msg}")
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream (the raw getter skips the Stream object ``torch.cuda.current_stream()`` builds on every call)."""
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
