@@ -227,7 +227,7 @@ def gpu_eager_baseline(window12: bool, sd_cpu, dev, B: int):
     return out
 
 
-def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, steps: int = 3, warmup: int = 2):
+def train_step_extra(model, dev, world: int, rank: int, dist, clips: int = 4, steps: int = 5, warmup: int = 3):
     """BASELINE configs[3] next to the headline: one training step (BERT + backbone + decoder forward, weighted CE, hand-written backward,
     gradient all-reduce over NCCL launched per finished stage under the rest of the backward, SyncBN statistics) at ``clips`` clips per
     GPU.  Runs on EVERY rank (it contains collectives); returns the dict rank 0 reports under ``extras.train_step``."""
