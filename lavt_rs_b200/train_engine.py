@@ -371,9 +371,20 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C), out_pre=vispre)
     qpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
-    stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
+    # --att_norm_layer_type none (2-D backbone, reference lib/backbone.py:1297-1316): Identity instead of InstanceNorm1d -- the consumers
+    # read identity "statistics" (mean 0, rstd 1) and the backward's InstanceNorm reductions are zeroed, which turns its adjoint into a pass-through
+    norm_kind = getattr(att, "att_norm_layer_type", "IN")
+    if norm_kind not in ("IN", "none"):
+        raise NotImplementedError("--att_norm_layer_type %s is inference-only on the B200 path" % norm_kind)
+    ident = None
+    if norm_kind == "none":
+        ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
     stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), f32, dev)
-    K.instnorm_stats(qpre, stats_q, stw)
+    if ident is None:
+        stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
+        K.instnorm_stats(qpre, stats_q, stw)
+    else:
+        stats_q = ident
     kk = torch.empty(B, Nl, C, device=dev, dtype=f32)
     vv = torch.empty(B, Nl, C, device=dev, dtype=f32)
     K.pwam_kv(l, mask, k_w, att.f_key[0].bias.detach(), v_w, att.f_value[0].bias.detach(), kk, vv)
@@ -381,8 +392,11 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     K.pwam_attend(qpre, stats_q, kk, vv, mask, o, heads)
     langpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_f32=langpre.view(N_, C))
-    stats_l = torch.empty(B, 2, C, device=dev, dtype=f32)
-    K.instnorm_stats(langpre, stats_l, stw)
+    if ident is None:
+        stats_l = torch.empty(B, 2, C, device=dev, dtype=f32)
+        K.instnorm_stats(langpre, stats_l, stw)
+    else:
+        stats_l = ident
     a2 = torch.empty(B, n, C, device=dev, dtype=bf)
     K.pwam_mul_norm(vis, langpre, stats_l, a2)
     rpre = torch.empty(N_, C, device=dev, dtype=bf)
@@ -403,7 +417,8 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         K.gate_elementwise(0 if gate_act == "tanh" else 7, g2, rb, f=x, out_f32=xg)
         _count(3)
     saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
-                 a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act)
+                 a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act,
+                 no_norm=ident is not None)
     return r32, xg, saved
 
 
@@ -446,6 +461,8 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     sums = torch.zeros(2, B, 2, C, device=dev, dtype=f32)
     dvispre = ws.get("bw_pw_c", (N_, C), bf, dev)
     K.pwam_mul_norm_bwd(da2, s["vis"], s["vispre"], s["langpre"], s["stats_l"], dvispre, sums[0])
+    if s.get("no_norm"):
+        sums[0].zero_()         # Identity instead of InstanceNorm: with zero reductions and rstd = 1 the adjoint below is the pass-through
     dlangpre = ws.get("bw_pw_a", (N_, C), bf, dev)
     K.instnorm_bwd(s["langpre"], s["stats_l"], sums[0], dlangpre, ga=da2, gb=s["vis"].view(N_, C))
     do = ws.get("bw_pw_b", (N_, C), bf, dev)
@@ -466,6 +483,8 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
                   grads.of(fk.weight) if fk.weight.requires_grad else None, grads.of(fk.bias) if fk.bias.requires_grad else None,
                   grads.of(fv.weight) if fv.weight.requires_grad else None, grads.of(fv.bias) if fv.bias.requires_grad else None,
                   dl, heads, nlp)
+    if s.get("no_norm"):
+        sums[1].zero_()
     dqpre = ws.get("bw_pw_b", (N_, C), bf, dev)
     K.instnorm_bwd(s["qpre"], s["stats_q"], sums[1], dqpre, g_f32=dqhat)
     # both projections of x: dx (+)= dvispre Wvis + dqpre Wq

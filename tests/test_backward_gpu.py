@@ -262,9 +262,11 @@ def test_patch_merging_backward():
     check_grads(grads.named(ds), pg_ref, "patch merging")
 
 
-@pytest.mark.parametrize("stage,heads,Nl,gate", [(0, 1, 20, True), (1, 4, 13, True), (3, 1, 22, False), (1, 1, 17, "sigmoid")])
+@pytest.mark.parametrize("stage,heads,Nl,gate", [(0, 1, 20, True), (1, 4, 13, True), (3, 1, 22, False), (1, 1, 17, "sigmoid"), (0, 1, 20, "no_norm"),
+                                                 (2, 2, 9, "no_norm")])
 def test_pwam_gate_backward(stage, heads, Nl, gate):
     gate_act = "sigmoid" if gate == "sigmoid" else "tanh"          # --lg_act_layer sigmoid (reference lib/backbone.py:552-554)
+    att_norm = "none" if gate == "no_norm" else "IN"               # --att_norm_layer_type none (reference lib/backbone.py:1297-1316): Identity
     gate = bool(gate)
     from lavt_rs_b200 import engine as E
     from lavt_rs_b200 import train_engine as T
@@ -290,8 +292,10 @@ def test_pwam_gate_backward(stage, heads, Nl, gate):
         layer.res_gate[0].weight.copy_(sd[pre + "res_gate.0.weight"])
         layer.res_gate[2].weight.copy_(sd[pre + "res_gate.2.weight"])
 
+    layer.fusion.image_lang_att.att_norm_layer_type = att_norm      # InstanceNorm1d has no parameters: the same module, other statistics
+
     def fn(sd2, xx, ll):
-        r = O.pwam(xx, ll, m, sd2, pre + "fusion.", heads)
+        r = O.pwam(xx, ll, m, sd2, pre + "fusion.", heads, att_norm=att_norm)
         if not gate:
             return r
         return torch.cat([r, O.language_gate(xx, r, sd2, pre + "res_gate.", act=gate_act)], 0)
