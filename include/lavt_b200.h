@@ -286,6 +286,12 @@ int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const
 int lavt_cast_rows_scaled_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
                                int32_t rscale_rows, void* out_bf16, void* stream);
 /* exact-erf GELU on a saved bf16 pre-activation and its derivative (Mlp.act, lib/video_swin_transformer.py:33) */
+/* Adjoint of lavt_lang_project (--fuse simple in training mode; reference lib/video_swin_transformer.py:1012-1039 under autograd):
+ * ds fp32 [B,C] = gradient of the sentence vector (sum over the pixels of d a2 * vis: row 0 of lavt_pwam_mul_norm_bwd's reductions);
+ * dw0 [C,Lin], db0 [C], dw2 [C,C], db2 [C] and dl [B,Lin,Nl] accumulate (+=; any may be NULL except the workspace of
+ * B * (2 C + 2 Lin) floats). */
+int lavt_lang_project_bwd(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* ds, float* dw0,
+                          float* db0, float* dw2, float* db2, float* dl, float* workspace, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream);
 int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream);
 int lavt_gelu_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int64_t count, void* stream);
 /* LayerNorm backward, adjoints of lavt_layernorm_rows / _window_gather / lavt_patch_merge_layernorm:

@@ -90,6 +90,7 @@ SIGNATURES = {
     "lavt_instnorm_stats": [_vp, _i32, _i64, _i32, _f32, _vp, _vp, _vp],
     "lavt_pwam_kv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_lang_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "lavt_lang_project_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "lavt_pwam_attend": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "lavt_pwam_mul_norm": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "lavt_instnorm_sum2": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
@@ -497,6 +498,19 @@ def lang_project(l, mask, w0, b0, w2, b2, stats) -> None:
         _c(t, torch.float32, nm)
     check(lib().lavt_lang_project(l.data_ptr(), mask.data_ptr(), w0.data_ptr(), b0.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                   stats.data_ptr(), B, Nl, Lin, Cn, stream_ptr()), "lavt_lang_project")
+
+
+def lang_project_bwd(l, mask, w0, b0, w2, ds, dw0, db0, dw2, db2, dl, workspace) -> None:
+    """Adjoint of lang_project: ds fp32 [B,C]; dw0 / db0 / dw2 / db2 / dl accumulate (None = not needed)."""
+    B, Lin, Nl = l.shape
+    Cn = w0.shape[0]
+    if workspace.numel() < B * (2 * Cn + 2 * Lin):
+        raise LavtError("lang_project_bwd: workspace too small")
+    check(lib().lavt_lang_project_bwd(_c(l, torch.float32, "l").data_ptr(), _c(mask, torch.float32, "mask").data_ptr(),
+                                      _c(w0, torch.float32, "w0").data_ptr(), _c(b0, torch.float32, "b0").data_ptr(),
+                                      _c(w2, torch.float32, "w2").data_ptr(), _c(ds, torch.float32, "ds").data_ptr(), ptr(dw0), ptr(db0),
+                                      ptr(dw2), ptr(db2), ptr(dl), _c(workspace, torch.float32, "workspace").data_ptr(), B, Nl, Lin, Cn,
+                                      stream_ptr()), "lavt_lang_project_bwd")
 
 
 def pwam_attend(qpre, stats, k, v, mask, out, heads: int) -> None:

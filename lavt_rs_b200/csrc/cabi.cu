@@ -457,6 +457,10 @@ int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const
   return lavt_cast_rows_scaled_bf16(x, ldx, M, C, geom, nullptr, 0, out_bf16, stream);
 }
 
+int lavt_lang_project_bwd(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* ds, float* dw0,
+                          float* db0, float* dw2, float* db2, float* dl, float* workspace, int32_t B, int32_t Nl, int32_t Lin, int32_t C, void* stream) {
+  return lang_project_bwd_dispatch(l, mask, w0, b0, w2, ds, dw0, db0, dw2, db2, dl, workspace, B, Nl, Lin, C, S(stream));
+}
 int lavt_gelu_fwd(const void* x_bf16, void* y_bf16, int64_t count, void* stream) {
   return gelu_fwd_dispatch(CB(x_bf16), MB(y_bf16), count, S(stream));
 }

@@ -683,6 +683,99 @@ int pwam_kv_bwd_dispatch(const float* dkbuf, const float* dvbuf, const float* ma
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LangProject backward (--fuse simple, reference lib/video_swin_transformer.py:1012-1039): s = W2 relu(W0 mean + b0) + b2 with
+// mean[b, :] = sum_j l[b, :, j] m[b, j] / sum_j m[b, j].  ds fp32 [B, C] arrives as the first row of pwam_mul_bwd's reductions
+// (sum over the pixels of d a2 * vis).  Everything here is clip-sized (B x C, B x Lin): four small launches, the forward's mean / hidden
+// vectors are recomputed.  workspace fp32: h [B, C] | dh [B, C] | mean [B, Lin] | dmean [B, Lin].
+__global__ void __launch_bounds__(256) lang_project_bwd_hidden_kernel(const float* __restrict__ l, const float* __restrict__ mask,
+                                                                      const float* __restrict__ w0, const float* __restrict__ b0,
+                                                                      float* __restrict__ h, float* __restrict__ mean, int Nl, int Lin, int C) {
+  extern __shared__ float lpb_sm[];      // [Lin] pooled sentence vector
+  const int b = blockIdx.y;
+  float cnt = 0.f;
+  for (int j = 0; j < Nl; ++j) cnt += mask[b * Nl + j];
+  for (int i = threadIdx.x; i < Lin; i += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Nl; ++j) s += l[(static_cast<long long>(b) * Lin + i) * Nl + j] * mask[b * Nl + j];
+    lpb_sm[i] = s / cnt;
+    if (blockIdx.x == 0) mean[static_cast<long long>(b) * Lin + i] = s / cnt;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int i = lane; i < Lin; i += 32) acc = fmaf(__ldg(w0 + static_cast<long long>(c) * Lin + i), lpb_sm[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) h[static_cast<long long>(b) * C + c] = fmaxf(acc + b0[c], 0.f);
+}
+// dW[r, q] += sum_b u[b, r] * v[b, q];  dbias[r] += sum_b u[b, r]        (u [B, R], v [B, Q])
+__global__ void __launch_bounds__(256) outer_accumulate_kernel(const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ dW,
+                                                               float* __restrict__ dbias, int B, int R, int Q) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(R) * Q) return;
+  const int r = static_cast<int>(idx / Q), q = static_cast<int>(idx - static_cast<long long>(r) * Q);
+  float acc = 0.f, bs = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float uv = __ldg(u + static_cast<long long>(b) * R + r);
+    acc = fmaf(uv, __ldg(v + static_cast<long long>(b) * Q + q), acc);
+    bs += uv;
+  }
+  if (dW) dW[idx] += acc;
+  if (dbias && q == 0) dbias[r] += bs;
+}
+// out[b, q] = (sum_r W[r, q] * u[b, r]) * (gate == nullptr || gate[b, q] > 0)        (W [R, Q])
+__global__ void __launch_bounds__(256) matvec_t_kernel(const float* __restrict__ W, const float* __restrict__ u, const float* __restrict__ gate,
+                                                       float* __restrict__ out, int B, int R, int Q) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (q >= Q) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) acc = fmaf(__ldg(W + static_cast<long long>(r) * Q + q), __ldg(u + static_cast<long long>(b) * R + r), acc);
+  if (gate && !(gate[static_cast<long long>(b) * Q + q] > 0.f)) acc = 0.f;
+  out[static_cast<long long>(b) * Q + q] = acc;
+}
+// dl[b, i, j] += dmean[b, i] * m[b, j] / sum_j m[b, j]
+__global__ void __launch_bounds__(256) lang_mean_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ mask, float* __restrict__ dl,
+                                                            int Nl, int Lin, long long total) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int j = static_cast<int>(e % Nl);
+  const long long bi = e / Nl;
+  const int b = static_cast<int>(bi / Lin);
+  float cnt = 0.f;
+  for (int t = 0; t < Nl; ++t) cnt += mask[b * Nl + t];
+  dl[e] += dmean[bi] * mask[b * Nl + j] / cnt;
+}
+
+int lang_project_bwd_dispatch(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* ds, float* dw0,
+                              float* db0, float* dw2, float* db2, float* dl, float* workspace, int B, int Nl, int Lin, int C, cudaStream_t st) {
+  LAVT_REQUIRE(B > 0 && B < 65536 && Nl > 0 && Lin > 0 && C > 0 && workspace, "lang_project backward: bad arguments");
+  LAVT_REQUIRE(static_cast<size_t>(Lin) * sizeof(float) <= 48 * 1024, "lang_project backward: language width %d too large", Lin);
+  float* h = workspace;
+  float* dh = h + static_cast<long long>(B) * C;
+  float* mean = dh + static_cast<long long>(B) * C;
+  float* dmean = mean + static_cast<long long>(B) * Lin;
+  lang_project_bwd_hidden_kernel<<<dim3((C + 7) / 8, B), 256, static_cast<size_t>(Lin) * sizeof(float), st>>>(l, mask, w0, b0, h, mean, Nl, Lin, C);
+  LAVT_LAUNCH_CHECK("lang_project_bwd_hidden_kernel");
+  // s = W2 h + b2
+  outer_accumulate_kernel<<<static_cast<unsigned>((1LL * C * C + 255) / 256), 256, 0, st>>>(ds, h, dw2, db2, B, C, C);
+  LAVT_LAUNCH_CHECK("outer_accumulate_kernel");
+  matvec_t_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(w2, ds, h, dh, B, C, C);            // dh = (W2^T ds) * [h > 0]
+  LAVT_LAUNCH_CHECK("matvec_t_kernel");
+  // hpre = W0 mean + b0
+  outer_accumulate_kernel<<<static_cast<unsigned>((1LL * C * Lin + 255) / 256), 256, 0, st>>>(dh, mean, dw0, db0, B, C, Lin);
+  LAVT_LAUNCH_CHECK("outer_accumulate_kernel");
+  if (dl) {
+    matvec_t_kernel<<<dim3((Lin + 255) / 256, B), 256, 0, st>>>(w0, dh, nullptr, dmean, B, C, Lin);
+    LAVT_LAUNCH_CHECK("matvec_t_kernel");
+    const long long total = 1LL * B * Lin * Nl;
+    lang_mean_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dmean, mask, dl, Nl, Lin, total);
+    LAVT_LAUNCH_CHECK("lang_mean_bwd_kernel");
+  }
+  return LAVT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LanguageGate elementwise pieces (x' = x + g2 * r, g2 = tanh(g1 G2^T), g1 = relu(r G0^T)); 8 elements per thread
 // (the tanh PRE-activation is what is saved: 1 - tanh^2 recomputed from a bf16-rounded tanh output loses all precision near
 //  saturation)

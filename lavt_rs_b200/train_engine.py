@@ -346,6 +346,52 @@ def _nl_pad(Nl: int) -> int:
     return (Nl + 7) // 8 * 8
 
 
+def _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act):
+    """r = GELU(project_mm(a2)) (:930) and the LanguageGate (:519-525) with what their adjoints need."""
+    N_, C = x.shape
+    dev = x.device
+    pw = fusion.prepared
+    bf, f32 = torch.bfloat16, torch.float32
+    rpre = torch.empty(N_, C, device=dev, dtype=bf)
+    K.gemm_bf16(a2.view(N_, C), mm_w, bias=fusion.project_mm[0].bias.detach(), out_bf16=rpre)
+    rb = torch.empty(N_, C, device=dev, dtype=bf)
+    r32 = torch.empty(N_, C, device=dev, dtype=f32)
+    K.gate_elementwise(3, rpre, out_bf16=rb, out_f32=r32)
+    _count(12)
+    g1 = g2 = xg = None
+    if res_gate is not None:
+        g0w = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
+        g2w = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
+        g1 = torch.empty(N_, C, device=dev, dtype=bf)
+        K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
+        g2 = torch.empty(N_, C, device=dev, dtype=bf)
+        K.gemm_bf16(g1, g2w, out_bf16=g2)       # PRE-activation of the tanh / sigmoid (saved); the gate is applied by the elementwise kernel
+        xg = torch.empty(N_, C, device=dev, dtype=f32)
+        K.gate_elementwise(0 if gate_act == "tanh" else 7, g2, rb, f=x, out_f32=xg)
+        _count(3)
+    return rpre, rb, r32, g1, g2, xg
+
+
+def _simple_fuse_fwd(x, xb, fusion, res_gate, l, mask, B, ws, gate_act, vispre, vis, mm_w):
+    """--fuse simple in training mode: a2 = vis * LangProject(l) (one sentence vector per clip, reference :916-917, :929-930, :1012-1039).
+    The sentence vector sits in an InstanceNorm-statistics block as (mean = -s, rstd = 1) over an all-zero lang_pre tensor, so the PWAM
+    product kernel and ITS ADJOINT are reused: row 0 of the adjoint's reductions is sum_pixels d a2 * vis = d s."""
+    N_, C = x.shape
+    n = N_ // B
+    dev = x.device
+    pw = fusion.prepared
+    pr = fusion.image_lang_att.project
+    stats = torch.empty(B, 2, C, device=dev, dtype=torch.float32)
+    K.lang_project(l, mask, _f32(pr[0].weight), _f32(pr[0].bias), _f32(pr[2].weight), _f32(pr[2].bias), stats)
+    zeros = pw.get("zeros_%d_%d" % (B, n), [], lambda: torch.zeros(B, n, C, device=dev, dtype=torch.float32))
+    a2 = torch.empty(B, n, C, device=dev, dtype=torch.bfloat16)
+    K.pwam_mul_norm(vis, zeros, stats, a2)
+    rpre, rb, r32, g1, g2, xg = _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act)
+    saved = dict(xb=xb, vispre=vispre, vis=vis, langpre=zeros, stats_l=stats, a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B,
+                 heads=1, gate_act=gate_act, no_norm=False, simple=True)
+    return r32, xg, saved
+
+
 def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, ws: Workspace,
                   gate_act: str = "tanh"):
     """x fp32 [B*n, C] (not modified), xb = its bf16 copy, l fp32 [B,768,Nl], mask fp32 [B,Nl].
@@ -355,20 +401,26 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     dev = x.device
     pw = fusion.prepared
     att = fusion.image_lang_att
-    heads = att.num_heads
+    heads = getattr(att, "num_heads", 1)
     Nl = l.shape[-1]
     bf, f32 = torch.bfloat16, torch.float32
 
     def wprep(name, conv):
         return pw.get(name, [conv.weight], lambda: _bf16(conv.weight[:, :, 0]))
-    vis_w, q_w, W_w, mm_w = (wprep("vis_w", fusion.vis_project[0]), wprep("q_w", att.f_query[0]), wprep("W_w", att.W[0]),
-                             wprep("mm_w", fusion.project_mm[0]))
-    k_w = pw.get("k_w", [att.f_key[0].weight], lambda: _f32(att.f_key[0].weight[:, :, 0]))
-    v_w = pw.get("v_w", [att.f_value[0].weight], lambda: _f32(att.f_value[0].weight[:, :, 0]))
+    simple = not fusion.attention          # --fuse simple (reference :916-917, :929-930): lang = LangProject(mean-pooled words), one vector per clip
+    vis_w, mm_w = wprep("vis_w", fusion.vis_project[0]), wprep("mm_w", fusion.project_mm[0])
+    if not simple:
+        q_w, W_w = wprep("q_w", att.f_query[0]), wprep("W_w", att.W[0])
+        k_w = pw.get("k_w", [att.f_key[0].weight], lambda: _f32(att.f_key[0].weight[:, :, 0]))
+        v_w = pw.get("v_w", [att.f_value[0].weight], lambda: _f32(att.f_value[0].weight[:, :, 0]))
+    else:
+        k_w = v_w = None
 
     vispre = torch.empty(N_, C, device=dev, dtype=bf)
     vis = torch.empty(B, n, C, device=dev, dtype=bf)
     K.gemm_bf16(xb, vis_w, bias=fusion.vis_project[0].bias.detach(), act=K.ACT_GELU, out_bf16=vis.view(N_, C), out_pre=vispre)
+    if simple:
+        return _simple_fuse_fwd(x, xb, fusion, res_gate, l, mask, B, ws, gate_act, vispre, vis, mm_w)
     qpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
     # --att_norm_layer_type none (2-D backbone, reference lib/backbone.py:1297-1316): Identity instead of InstanceNorm1d -- the consumers
@@ -399,26 +451,10 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         stats_l = ident
     a2 = torch.empty(B, n, C, device=dev, dtype=bf)
     K.pwam_mul_norm(vis, langpre, stats_l, a2)
-    rpre = torch.empty(N_, C, device=dev, dtype=bf)
-    K.gemm_bf16(a2.view(N_, C), mm_w, bias=fusion.project_mm[0].bias.detach(), out_bf16=rpre)
-    rb = torch.empty(N_, C, device=dev, dtype=bf)
-    r32 = torch.empty(N_, C, device=dev, dtype=f32)
-    K.gate_elementwise(3, rpre, out_bf16=rb, out_f32=r32)
-    _count(12)
-    g1 = g2 = xg = None
-    if res_gate is not None:
-        g0w = pw.get("g0", [res_gate[0].weight], lambda: _bf16(res_gate[0].weight))
-        g2w = pw.get("g2", [res_gate[2].weight], lambda: _bf16(res_gate[2].weight))
-        g1 = torch.empty(N_, C, device=dev, dtype=bf)
-        K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
-        g2 = torch.empty(N_, C, device=dev, dtype=bf)
-        K.gemm_bf16(g1, g2w, out_bf16=g2)       # PRE-activation of the tanh / sigmoid (saved); the gate is applied by the elementwise kernel
-        xg = torch.empty(N_, C, device=dev, dtype=f32)
-        K.gate_elementwise(0 if gate_act == "tanh" else 7, g2, rb, f=x, out_f32=xg)
-        _count(3)
+    rpre, rb, r32, g1, g2, xg = _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act)
     saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
                  a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act,
-                 no_norm=ident is not None)
+                 no_norm=ident is not None, simple=False)
     return r32, xg, saved
 
 
@@ -461,6 +497,24 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     sums = torch.zeros(2, B, 2, C, device=dev, dtype=f32)
     dvispre = ws.get("bw_pw_c", (N_, C), bf, dev)
     K.pwam_mul_norm_bwd(da2, s["vis"], s["vispre"], s["langpre"], s["stats_l"], dvispre, sums[0])
+    if s.get("simple"):
+        # --fuse simple: d s = sum_pixels d a2 * vis (row 0 of the reductions) -> LangProject adjoint; the only projection of x is vis_project
+        pr = att.project
+        ds = sums[0][:, 0, :].contiguous()
+        Lin = s["l"].shape[1]
+        wsp = ws.get("bw_langproj", (B * (2 * C + 2 * Lin),), f32, dev)
+
+        def gof(prm):
+            return grads.of(prm) if prm.requires_grad else None
+        K.lang_project_bwd(s["l"], s["mask"], _f32(pr[0].weight), _f32(pr[0].bias), _f32(pr[2].weight), ds, gof(pr[0].weight), gof(pr[0].bias),
+                           gof(pr[2].weight), gof(pr[2].bias), dl, wsp)
+        if dxg is not None:
+            dx, first_resid = dxg, dxg
+        else:
+            dx, first_resid = torch.empty(N_, C, device=dev, dtype=f32), None
+        linear_bwd(dvispre, xb, fusion.vis_project[0].weight, fusion.vis_project[0].bias, grads, ws, pw, "vis", dx_f32=dx, dx_resid=first_resid)
+        _count(12)
+        return dx
     if s.get("no_norm"):
         sums[0].zero_()         # Identity instead of InstanceNorm: with zero reductions and rstd = 1 the adjoint below is the pass-through
     dlangpre = ws.get("bw_pw_a", (N_, C), bf, dev)

@@ -33,8 +33,6 @@ def _check_trainable(model) -> None:
     for layer in bb.layers:
         if getattr(layer.fusion, "kind", "pwam") in ("gacd", "bcam", "efn"):
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
-        if not layer.sep_t_pwam and not layer.fusion.attention:
-            raise NotImplementedError("--fuse simple is inference-only on the B200 path")
         if getattr(layer, "gate_act", "tanh") != "tanh" and layer.sep_t_pwam:
             raise NotImplementedError("--lg_act_layer sigmoid with SepTPWAM is inference-only on the B200 path")
         if getattr(getattr(layer.fusion, "image_lang_att", None), "att_norm_layer_type", "IN") not in ("IN", "none"):

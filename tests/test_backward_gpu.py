@@ -1015,6 +1015,60 @@ def test_text_encoder_on_side_stream():
             assert d1[k] <= 3 * noise_g[k] + 1e-3 * g0[k].float().norm().item() + 1e-5 * big, (k, d1[k], noise_g[k])
 
 
+@pytest.mark.parametrize("stage,gate", [(0, True), (2, False)])
+def test_simple_fusion_backward(stage, gate):
+    """--fuse simple in training mode (reference lib/video_swin_transformer.py:916-917, 929-930, LangProject :1012-1039): r = GELU(project_mm(
+    GELU(vis_project(x)) * LangProject(l))) + LanguageGate; every parameter gradient, dx and d l_feats vs autograd through the oracle."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib.video_swin_transformer import MultiModalSwinTransformer3D
+    from lavt_rs_b200.weights import load_reference_state_dict
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(8, 7, 7), fuse_simple=True)
+    sd = dict(O.random_state_dict(cfg, seed=0))
+    bb = MultiModalSwinTransformer3D(patch_size=(1, 4, 4), embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32],
+                                     window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True, args=default_args(["--fuse", "simple"]))
+    C = 128 * 2 ** stage
+    pre = f"backbone.layers.{stage}."
+    g = torch.Generator().manual_seed(17)
+    for k in ("res_gate.0.weight", "res_gate.2.weight"):       # a zero-initialised gate has no gradient signal
+        sd[pre + k] = torch.randn(C, C, generator=g) * C ** -0.5
+    load_reference_state_dict(bb, sd, "backbone.")
+    bb = bb.cuda().train()
+    layer = bb.layers[stage]
+    B, n, Nl = 3, 520, 11
+    x = torch.randn(B, n, C, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl, 1)
+    m[0, Nl - 4:] = 0
+    m[2, Nl - 1:] = 0
+    gr = torch.randn(B, n, C, generator=g)
+    gx = torch.randn(B, n, C, generator=g)
+
+    def fn(sd2, xx, ll):
+        r = O.pwam(xx, ll, m, sd2, pre + "fusion.", 1)
+        if not gate:
+            return r
+        return torch.cat([r, O.language_gate(xx, r, sd2, pre + "res_gate.")], 0)
+    gout = torch.cat([gr, gx], 0) if gate else gr
+    (dx_ref, dl_ref), pg_ref = _oracle_grads(fn, sd, pre, [x, l], gout)
+    pg_ref = {k: v for k, v in pg_ref.items() if k.startswith("fusion.") or (gate and k.startswith("res_gate."))}
+    assert any(k.startswith("fusion.image_lang_att.project.") for k in pg_ref)
+    ws = E.workspace("cuda")
+    grads = T.GradStore()
+    xf = x.cuda().reshape(-1, C).contiguous()
+    r32, xg, saved = T.pwam_gate_fwd(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate if gate else None, l.cuda(), m.squeeze(-1).cuda(), B, ws)
+    ref = fn(sd, x, l)
+    assert rel_l2(r32, ref[:B].reshape(-1, C)) < 1.5e-2
+    dl = torch.zeros(B, 768, Nl, device="cuda")
+    dx = T.pwam_gate_bwd(layer.fusion, layer.res_gate if gate else None, saved, gr.cuda().reshape(-1, C).contiguous(),
+                         gx.cuda().reshape(-1, C).contiguous() if gate else None, grads, ws, dl)
+    torch.cuda.synchronize()
+    assert rel_l2(dx, dx_ref.reshape(-1, C)) < GRAD_L2, ("dx", rel_l2(dx, dx_ref.reshape(-1, C)))
+    assert rel_l2(dl, dl_ref) < GRAD_L2, ("dl", rel_l2(dl, dl_ref))
+    check_grads(grads.named(layer), pg_ref, f"simple fusion stage {stage}")
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""

@@ -118,6 +118,7 @@ def test_inference_only_variants_refuse_training():
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lazy_pred"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--att_norm_layer_type", "none"])))
+    training._check_trainable(segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny", "--fuse", "simple"])))
     # the sigmoid gate trains (gate adjoint modes 7 / 8 of lavt_gate_elementwise)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lg_act_layer", "sigmoid"])))
 
