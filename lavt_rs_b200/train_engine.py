@@ -346,6 +346,19 @@ def _nl_pad(Nl: int) -> int:
     return (Nl + 7) // 8 * 8
 
 
+def _att_ln_bwd(x_raw: torch.Tensor, dy: torch.Tensor, ln, grads: GradStore, ws: Workspace, name: str) -> torch.Tensor:
+    """Adjoint of the row LayerNorm that --att_norm_layer_type LN puts behind f_query / W: x_raw fp32 [B,n,C] = its input, dy bf16 [B*n, C] =
+    gradient of its output -> bf16 gradient of its input (LayerNorm backward kernel + the bf16 cast the next weight-gradient GEMM reads)."""
+    N_, C = dy.shape
+    dev = dy.device
+    dx32 = ws.get(name + "_f32", (N_, C), torch.float32, dev)
+    K.layernorm_rows_bwd(x_raw.view(N_, C), dy, ln.weight, dx32, grads.of(ln.weight), grads.of(ln.bias), eps=ln.eps)
+    out = ws.get(name + "_bf16", (N_, C), torch.bfloat16, dev)
+    K.cast_rows_bf16(dx32, out)
+    _count(2)
+    return out
+
+
 def _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act):
     """r = GELU(project_mm(a2)) (:930) and the LanguageGate (:519-525) with what their adjoints need."""
     N_, C = x.shape
@@ -423,14 +436,21 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         return _simple_fuse_fwd(x, xb, fusion, res_gate, l, mask, B, ws, gate_act, vispre, vis, mm_w)
     qpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(xb, q_w, bias=att.f_query[0].bias.detach(), out_f32=qpre.view(N_, C))
-    # --att_norm_layer_type none (2-D backbone, reference lib/backbone.py:1297-1316): Identity instead of InstanceNorm1d -- the consumers
-    # read identity "statistics" (mean 0, rstd 1) and the backward's InstanceNorm reductions are zeroed, which turns its adjoint into a pass-through
+    # --att_norm_layer_type none / LN (2-D backbone, reference lib/backbone.py:1297-1316): Identity or a row LayerNorm instead of
+    # InstanceNorm1d -- the consumers read identity "statistics" (mean 0, rstd 1) of the (LayerNorm'd) projection and the backward's
+    # InstanceNorm reductions are zeroed, which turns its adjoint into a pass-through; LN adds the LayerNorm adjoint behind it
     norm_kind = getattr(att, "att_norm_layer_type", "IN")
-    if norm_kind not in ("IN", "none"):
+    if norm_kind not in ("IN", "none", "LN"):
         raise NotImplementedError("--att_norm_layer_type %s is inference-only on the B200 path" % norm_kind)
     ident = None
-    if norm_kind == "none":
+    q_raw = l_raw = None
+    if norm_kind != "IN":
         ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
+    if norm_kind == "LN":
+        q_raw = qpre                                            # LayerNorm input, kept for its adjoint
+        qpre = torch.empty(B, n, C, device=dev, dtype=f32)
+        K.layernorm_rows(q_raw.view(N_, C), att.f_query[1].weight, att.f_query[1].bias, out_f32=qpre.view(N_, C), eps=att.f_query[1].eps)
+        _count(1)
     stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), f32, dev)
     if ident is None:
         stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
@@ -444,6 +464,11 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     K.pwam_attend(qpre, stats_q, kk, vv, mask, o, heads)
     langpre = torch.empty(B, n, C, device=dev, dtype=f32)
     K.gemm_bf16(o.view(N_, C), W_w, bias=att.W[0].bias.detach(), out_f32=langpre.view(N_, C))
+    if norm_kind == "LN":
+        l_raw = langpre
+        langpre = torch.empty(B, n, C, device=dev, dtype=f32)
+        K.layernorm_rows(l_raw.view(N_, C), att.W[1].weight, att.W[1].bias, out_f32=langpre.view(N_, C), eps=att.W[1].eps)
+        _count(1)
     if ident is None:
         stats_l = torch.empty(B, 2, C, device=dev, dtype=f32)
         K.instnorm_stats(langpre, stats_l, stw)
@@ -454,7 +479,7 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     rpre, rb, r32, g1, g2, xg = _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act)
     saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
                  a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act,
-                 no_norm=ident is not None, simple=False)
+                 no_norm=ident is not None, simple=False, q_raw=q_raw, l_raw=l_raw)
     return r32, xg, saved
 
 
@@ -519,6 +544,8 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
         sums[0].zero_()         # Identity instead of InstanceNorm: with zero reductions and rstd = 1 the adjoint below is the pass-through
     dlangpre = ws.get("bw_pw_a", (N_, C), bf, dev)
     K.instnorm_bwd(s["langpre"], s["stats_l"], sums[0], dlangpre, ga=da2, gb=s["vis"].view(N_, C))
+    if s.get("l_raw") is not None:          # --att_norm_layer_type LN: dlangpre is the gradient of the LayerNorm OUTPUT
+        dlangpre = _att_ln_bwd(s["l_raw"], dlangpre, att.W[1], grads, ws, "bw_pw_ln")
     do = ws.get("bw_pw_b", (N_, C), bf, dev)
     linear_bwd(dlangpre, s["o"].view(N_, C), att.W[0].weight, att.W[0].bias, grads, ws, pw, "W", dx_bf16=do)
     # pixel-word attention core
@@ -541,6 +568,8 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
         sums[1].zero_()
     dqpre = ws.get("bw_pw_b", (N_, C), bf, dev)
     K.instnorm_bwd(s["qpre"], s["stats_q"], sums[1], dqpre, g_f32=dqhat)
+    if s.get("q_raw") is not None:
+        dqpre = _att_ln_bwd(s["q_raw"], dqpre, att.f_query[1], grads, ws, "bw_pw_ln")
     # both projections of x: dx (+)= dvispre Wvis + dqpre Wq
     if dxg is not None:
         dx = dxg

@@ -111,13 +111,14 @@ def test_inference_only_variants_refuse_training():
     entry point must refuse them up front.  --lazy_pred trains (tests/test_backward_gpu.py::test_lazy_pred_training_step)."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "LN"], ["--interpolate_before_seg"]):
+    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "BN"], ["--interpolate_before_seg"]):
         m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lazy_pred"])))
-    training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--att_norm_layer_type", "none"])))
+    for kind in ("none", "LN"):
+        training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--att_norm_layer_type", kind])))
     training._check_trainable(segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny", "--fuse", "simple"])))
     # the sigmoid gate trains (gate adjoint modes 7 / 8 of lavt_gate_elementwise)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lg_act_layer", "sigmoid"])))
