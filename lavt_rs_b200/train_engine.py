@@ -760,24 +760,46 @@ def decoder_fwd(dec, c4, c3, c2, c1, ws: Workspace, sync_bn: bool = False):
         levels.append((tuple(y.shape), s1, s2))
         y = t2
         _count(1)
+    # --interpolate_before_seg / --seg_last (reference lib/mask_predictor.py:40-48, 88-97): bilinear x2 + conv3x3 + BN + ReLU at 1/2 scale,
+    # and once more at full scale, before the 1x1 classifier
+    tails = []
+    if getattr(dec, "interpolate_before_seg", False):
+        fine = c1
+        for on, (cname, bname, mul_) in ((True, ("conv2_1", "bn1_1", 2)), (getattr(dec, "seg_last", False), ("conv1_0", "bn1_0", 4))):
+            if not on:
+                continue
+            up = torch.empty(n_img, mul_ * fine.shape[1], mul_ * fine.shape[2], hid, device=dev, dtype=torch.bfloat16)
+            K.upsample_nhwc(y, up)
+            t, sv = _cbr_fwd(up, dec, cname, bname, ws, sync_bn)
+            tails.append((tuple(y.shape), sv))
+            y = t
+            _count(1)
     _, H, W, _ = y.shape
     w11 = dec.prepared.get("w11", [dec.conv1_1.weight], lambda: _f32(dec.conv1_1.weight.reshape(2, -1)))
     lg = torch.empty(n_img, H, W, 2, device=dev, dtype=torch.float32)
     K.conv1x1_logits(y.view(-1, hid), w11, dec.conv1_1.bias.detach(), lg.view(-1, 2))
     _count(1)
-    return lg, (levels, y, w11)
+    return lg, (levels, y, w11, tails)
 
 
 def decoder_bwd(dec, saved, dlg: torch.Tensor, grads: GradStore, ws: Workspace, sync_bn: bool = False):
     """dlg fp32 [n, H1, W1, 2] -> gradients of (c4, c3, c2, c1) as bf16 row views [n*H_i*W_i, C_i] (c3..c1 are column slices of the
     concatenated-input gradient, i.e. have a row pitch larger than C_i); dc1 is None under --lazy_pred."""
-    levels, y, w11 = saved
+    levels, y, w11, tails = saved
     dev = dlg.device
     hid = y.shape[-1]
     npix = y.shape[0] * y.shape[1] * y.shape[2]
     dy = ws.get("bw_dec_dy", (npix, hid), torch.bfloat16, dev)
     K.conv1x1_logits_bwd(dlg.view(-1, 2), y.view(-1, hid), w11, dy, grads.of(dec.conv1_1.weight).view(2, hid), grads.of(dec.conv1_1.bias))
     _count(1)
+    for yshape, sv in reversed(tails):          # adjoint of (bilinear upsample -> conv3x3 + BN + ReLU), finest level first
+        up = sv[0]
+        dup = torch.empty(up.shape, device=dev, dtype=torch.bfloat16)
+        _cbr_bwd(dec, sv, dy, grads, ws, sync_bn, dup)
+        dprev = torch.empty(yshape, device=dev, dtype=torch.bfloat16)
+        K.upsample_concat_bwd(dup, dprev)
+        _count(1)
+        dy = dprev.view(-1, hid)
     dskips = []
     for li in range(len(levels) - 1, -1, -1):
         yshape, s1, s2 = levels[li]

@@ -39,8 +39,6 @@ def _check_trainable(model) -> None:
             raise NotImplementedError("--att_norm_layer_type BN is inference-only on the B200 path (IN, LN and none train)")
         if layer.version not in ("default", "no_gate", "none"):
             raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
-    if getattr(model.classifier, "interpolate_before_seg", False):
-        raise NotImplementedError("--interpolate_before_seg / --seg_last are inference-only on the B200 path")
     lazy = any(getattr(layer, "lazy_pred", False) for layer in bb.layers)
     if tuple(bb.out_indices) != ((1, 2, 3) if lazy else (0, 1, 2, 3)):
         raise NotImplementedError("training on the B200 path needs out_indices (0, 1, 2, 3), or (1, 2, 3) with --lazy_pred")

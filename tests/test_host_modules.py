@@ -107,16 +107,17 @@ def test_lazy_pred_state_dict_matches_oracle_contract():
 
 
 def test_inference_only_variants_refuse_training():
-    """The lib/bcam.py fusions, the BN / LN / none attention norms and the decoder tails have no hand-written backward: the training
-    entry point must refuse them up front.  --lazy_pred trains (tests/test_backward_gpu.py::test_lazy_pred_training_step)."""
+    """The lib/bcam.py fusions and the BatchNorm attention norm have no hand-written backward: the training entry point must refuse them up
+    front.  --lazy_pred, --fuse simple, the none / LN attention norms and the decoder tails train (tests/test_backward_gpu.py)."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "BN"], ["--interpolate_before_seg"]):
+    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "BN"]):
         m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lazy_pred"])))
+    training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--interpolate_before_seg", "--seg_last"])))
     for kind in ("none", "LN"):
         training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--att_norm_layer_type", kind])))
     training._check_trainable(segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny", "--fuse", "simple"])))
