@@ -285,6 +285,10 @@ int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const
 /* same with a per-sample scale: out = x[src(m)] * rscale[src(m) / rscale_rows] (adjoint of the epilogue's rscale: DropPath backward) */
 int lavt_cast_rows_scaled_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
                                int32_t rscale_rows, void* out_bf16, void* stream);
+/* The same cast with the column sums of the (scaled, fp32) values added into colsum[C] (+=): the bias gradient of the Linear layer whose
+ * output gradient the rows are (Mlp.fc2 / WindowAttention3D.proj of a Swin block under autograd) without a second pass; C <= 1024. */
+int lavt_cast_rows_colsum_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
+                               int32_t rscale_rows, void* out_bf16, float* colsum, void* stream);
 /* exact-erf GELU on a saved bf16 pre-activation and its derivative (Mlp.act, lib/video_swin_transformer.py:33) */
 /* Adjoint of lavt_lang_project (--fuse simple in training mode; reference lib/video_swin_transformer.py:1012-1039 under autograd):
  * ds fp32 [B,C] = gradient of the sentence vector (sum over the pixels of d a2 * vis: row 0 of lavt_pwam_mul_norm_bwd's reductions);

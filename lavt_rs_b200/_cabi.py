@@ -113,6 +113,7 @@ SIGNATURES = {
     "lavt_colsum_accumulate": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "lavt_cast_rows_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _vp],
     "lavt_cast_rows_scaled_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _i32, _vp, _vp],
+    "lavt_cast_rows_colsum_bf16": [_vp, _i64, _i64, _i32, _WG, _vp, _i32, _vp, _vp, _vp],
     "lavt_gelu_fwd": [_vp, _vp, _i64, _vp],
     "lavt_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "lavt_layernorm_rows_bwd": [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp],
@@ -713,11 +714,17 @@ def colsum_accumulate(x: torch.Tensor, dst: torch.Tensor) -> None:
 
 
 def cast_rows_bf16(x: torch.Tensor, out: torch.Tensor, geom: Optional[WinGeom] = None, rscale: Optional[torch.Tensor] = None,
-                   rscale_rows: int = 0) -> None:
+                   rscale_rows: int = 0, colsum: Optional[torch.Tensor] = None) -> None:
     """out bf16 [M, C] = x fp32 rows (identity) or gathered into window order (pad rows zero), optionally times a per-sample scale
-    rscale[source row // rscale_rows] (DropPath backward)."""
+    rscale[source row // rscale_rows] (DropPath backward).  ``colsum`` fp32 [C]: the column sums of the written values are added
+    into it by the same pass (the bias gradient of the layer whose output gradient this is)."""
     _req(x, torch.float32, "x")
     M, Cn = out.shape
+    if colsum is not None:
+        check(lib().lavt_cast_rows_colsum_bf16(x.data_ptr(), x.stride(0), M, Cn, C.byref(geom) if geom is not None else None,
+                                               ptr(rscale), int(rscale_rows), _c(out, torch.bfloat16, "out").data_ptr(),
+                                               _c(colsum, torch.float32, "colsum").data_ptr(), stream_ptr()), "lavt_cast_rows_colsum_bf16")
+        return
     check(lib().lavt_cast_rows_scaled_bf16(x.data_ptr(), x.stride(0), M, Cn, C.byref(geom) if geom is not None else None,
                                            ptr(rscale), int(rscale_rows), _c(out, torch.bfloat16, "out").data_ptr(), stream_ptr()),
           "lavt_cast_rows_scaled_bf16")

@@ -242,6 +242,91 @@ int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long l
   return LAVT_OK;
 }
 
+// The same cast with the COLUMN SUMS of what it writes (fp32, before the bf16 rounding) added into colsum[C]: the bias gradient of the Linear
+// layer whose output gradient this is (fc2 / proj of a Swin block) comes out of the pass that already reads every element, instead of a
+// second pass over the bf16 copy.  A warp takes groups of 32 output rows (closed-form gather evaluated one row per lane), keeps its column
+// sums in registers over all its groups, the block combines them in shared memory and issues one atomicAdd per column.
+template <int NV>
+__global__ void __launch_bounds__(256) cast_rows_colsum_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
+                                                               long long M, int C, const WinGeom win, const int use_win,
+                                                               const float* __restrict__ rscale, const int rs_rows, float* __restrict__ colsum) {
+  extern __shared__ float crc_red[];      // [8][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long groups = (M + 31) / 32;
+  for (long long g = static_cast<long long>(blockIdx.x) * 8 + warp; g < groups; g += static_cast<long long>(gridDim.x) * 8) {
+    const long long m0 = g * 32;
+    long long myrow = (m0 + lane < M) ? m0 + lane : -1;
+    if (use_win && myrow >= 0) myrow = win_token(win, m0 + lane).row;
+    const int rows = static_cast<int>((M - m0 < 32) ? M - m0 : 32);
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      const long long row = __shfl_sync(0xffffffffu, myrow, r);
+      const float sc = (rscale && row >= 0) ? __ldg(rscale + row / rs_rows) : 1.0f;
+      uint2* dst = reinterpret_cast<uint2*>(out + (m0 + r) * C);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 * 4 >= C) continue;
+        uint2 o = make_uint2(0u, 0u);
+        if (row >= 0) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c4);
+          v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+          o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+        dst[c4] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 * 4 < C) *reinterpret_cast<float4*>(&crc_red[warp * C + c4 * 4]) = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += crc_red[w * C + c];
+    atomicAdd(colsum + c, s);
+  }
+}
+
+int cast_rows_colsum_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, const float* rscale,
+                              int rs_rows, float* colsum, cudaStream_t st) {
+  LAVT_REQUIRE(M > 0 && C % 4 == 0 && ldx % 4 == 0 && colsum, "cast rows + column sums: channels / pitch must be multiples of 4");
+  LAVT_REQUIRE(C <= 1024, "cast rows + column sums: at most 1024 channels (got %d)", C);
+  WinGeom g{};
+  if (win) g = *win;
+  long long blocks = ((M + 31) / 32 + 7) / 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;       // every block ends with C atomics onto the same C words: few, long-running blocks
+  const size_t smem = static_cast<size_t>(8) * C * sizeof(float);
+#define LAVT_CRC_CASE(nv)                                                                                                           \
+  case nv: {                                                                                                                          \
+    cast_rows_colsum_kernel<nv><<<static_cast<unsigned>(blocks), 256, smem, st>>>(x, ldx, out, M, C, g, win ? 1 : 0, rscale, rs_rows, colsum); \
+    break;                                                                                                                            \
+  }
+  switch ((C + 127) / 128) {
+    LAVT_CRC_CASE(1)
+    LAVT_CRC_CASE(2)
+    LAVT_CRC_CASE(3)
+    LAVT_CRC_CASE(4)
+    LAVT_CRC_CASE(5)
+    LAVT_CRC_CASE(6)
+    LAVT_CRC_CASE(7)
+    LAVT_CRC_CASE(8)
+    default:
+      set_last_error("cast rows + column sums: %d channels unsupported", C);
+      return LAVT_ERR_SHAPE;
+  }
+#undef LAVT_CRC_CASE
+  LAVT_LAUNCH_CHECK("cast_rows_colsum_kernel");
+  return LAVT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
 __global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ out,

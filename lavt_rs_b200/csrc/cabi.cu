@@ -453,6 +453,16 @@ int lavt_cast_rows_scaled_bf16(const float* x, int64_t ldx, int64_t M, int32_t C
   LAVT_REQUIRE(!rscale || rscale_rows > 0, "cast rows: rscale needs rscale_rows > 0");
   return cast_rows_dispatch(x, ldx, MB(out_bf16), M, C, geom ? &g : nullptr, rscale, rscale_rows, S(stream));
 }
+int lavt_cast_rows_colsum_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, const float* rscale,
+                               int32_t rscale_rows, void* out_bf16, float* colsum, void* stream) {
+  WinGeom g;
+  if (geom) {
+    std::memcpy(&g, geom, sizeof(g));
+    LAVT_REQUIRE(M == 1LL * g.B * g.nwd * g.nwh * g.nww * g.N, "cast rows: M does not match the window geometry");
+  }
+  LAVT_REQUIRE(!rscale || rscale_rows > 0, "cast rows: rscale needs rscale_rows > 0");
+  return cast_rows_colsum_dispatch(x, ldx, MB(out_bf16), M, C, geom ? &g : nullptr, rscale, rscale_rows, colsum, S(stream));
+}
 int lavt_cast_rows_bf16(const float* x, int64_t ldx, int64_t M, int32_t C, const lavt_win_geom_t* geom, void* out_bf16, void* stream) {
   return lavt_cast_rows_scaled_bf16(x, ldx, M, C, geom, nullptr, 0, out_bf16, stream);
 }

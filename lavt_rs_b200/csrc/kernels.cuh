@@ -91,6 +91,8 @@ int transpose_bf16_dispatch(const __nv_bfloat16* in, long long ldi, __nv_bfloat1
 int colsum_dispatch(const void* x, int is_bf16, long long ldx, long long M, int N, float* dst, cudaStream_t st);
 int cast_rows_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, const float* rscale,
                        int rs_rows, cudaStream_t st);
+int cast_rows_colsum_dispatch(const float* x, long long ldx, __nv_bfloat16* out, long long M, int C, const WinGeom* win, const float* rscale,
+                              int rs_rows, float* colsum, cudaStream_t st);
 int lang_project_bwd_dispatch(const float* l, const float* mask, const float* w0, const float* b0, const float* w2, const float* ds, float* dw0,
                               float* db0, float* dw2, float* db2, float* dl, float* workspace, int B, int Nl, int Lin, int C, cudaStream_t st);
 int gelu_fwd_dispatch(const __nv_bfloat16* x, __nv_bfloat16* y, long long count, cudaStream_t st);

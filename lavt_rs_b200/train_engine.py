@@ -176,7 +176,7 @@ def _transposed(ws: Workspace, name: str, x: torch.Tensor) -> torch.Tensor:
 def linear_bwd(dy: torch.Tensor, x: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], grads: GradStore,
                ws: Workspace, prepared: E.PreparedWeights, key: str, *, dx_bf16: Optional[torch.Tensor] = None,
                dx_f32: Optional[torch.Tensor] = None, dx_resid: Optional[torch.Tensor] = None, x_t: Optional[torch.Tensor] = None,
-               **dx_epi) -> Optional[torch.Tensor]:
+               bias_done: bool = False, **dx_epi) -> Optional[torch.Tensor]:
     """Adjoint of y = x W^T + b for bf16 rows dy [M, out], x [M, in]; ``weight`` is the [out, in(,1)] parameter.
     dW += dy^T x, db += colsum(dy); if a dx buffer is given: dx = dy W (through the GEMM epilogue options in ``dx_epi``).
     (``x_t`` is accepted for callers written against the transposed-operand version and ignored.)"""
@@ -189,7 +189,7 @@ def linear_bwd(dy: torch.Tensor, x: Optional[torch.Tensor], weight: torch.Tensor
         part = ws.get("bw_splitk", (K.splitk_workspace_floats(Nout, Kin, M),), torch.float32, dev)
         K.gemm_bf16_wgrad(dy, x, grads.of(weight).view(Nout, Kin), part, accumulate=True)
         _count(2)
-    if bias is not None and bias.requires_grad:
+    if bias is not None and bias.requires_grad and not bias_done:      # (bias_done: the kernel that produced dy already summed its columns)
         K.colsum_accumulate(dy, grads.of(bias))
         _count(1)
     if dx_bf16 is not None or dx_f32 is not None:
@@ -216,6 +216,11 @@ def draw_drop_path(rate: float, B: int, device) -> Optional[torch.Tensor]:
 # kernels of the first version), but the bf16-rounded derivative moved one cancellation-heavy gradient (layers.0.blocks.0.norm1.bias)
 # below the end-to-end direction criterion (cosine 0.934 < 0.95), so the derivative is evaluated in fp32 from the saved pre-activation.
 _GELU_PRE_MODE = int(os.environ.get("LAVT_TRAIN_GELU_PRE_MODE", "0"))
+# 1: the casts of a block's output gradient also sum its columns (d fc2.bias, d proj.bias; lavt_cast_rows_colsum_bf16), 48 launches fewer per
+# step; 0 (default): separate column-sum launches.  Measured on one box, twice each: 65.5 / 65.8 ms fused vs 64.2 / 64.6 ms separate -- the
+# column sums read the bf16 copy out of L2 right after the cast wrote it, and the fused kernel's register accumulators + per-block atomics cost
+# more than that second pass, so the fusion stays an option.
+_FUSE_COLSUM = int(os.environ.get("LAVT_TRAIN_FUSE_COLSUM", "0"))
 
 
 def swin_block_fwd(x: torch.Tensor, blk, B: int, D: int, H: int, W: int, window, shifted: bool, clamp: bool, ws: Workspace,
@@ -281,20 +286,25 @@ def swin_block_bwd(blk, saved, dx: torch.Tensor, grads: GradStore, ws: Workspace
     pw = blk.prepared
     # ---- MLP half: x2 = x1 + fc2(GELU(fc1(LN2(x1))))
     dyb = ws.get("bw_dyb", (n, C), torch.bfloat16, dev)
-    K.cast_rows_bf16(dx, dyb, rscale=s_mlp, rscale_rows=tok)         # DropPath: the branch sees the gradient times its sample's scale
+    # DropPath: the branch sees the gradient times its sample's scale; the same pass sums the columns = d fc2.bias
+    b2 = blk.mlp.fc2.bias
+    fuse2 = bool(_FUSE_COLSUM) and b2 is not None and b2.requires_grad and C <= 1024
+    K.cast_rows_bf16(dx, dyb, rscale=s_mlp, rscale_rows=tok, colsum=grads.of(b2) if fuse2 else None)
     dhid = ws.get("bw_dhid", (n, hidden), torch.bfloat16, dev)
     # d pre = (dy W2) * GELU'(pre) in the epilogue of the input-gradient GEMM (`mul` operand = the saved pre-activation)
     linear_bwd(dyb, hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, grads, ws, pw, "fc2", dx_bf16=dhid, mul=hpre,
-               mul_act=K.ACT_NONE if _GELU_PRE_MODE else K.ACT_GELU)
+               mul_act=K.ACT_NONE if _GELU_PRE_MODE else K.ACT_GELU, bias_done=fuse2)
     dh1 = ws.get("bw_dh1", (n, C), torch.bfloat16, dev)
     linear_bwd(dhid, h1, blk.mlp.fc1.weight, blk.mlp.fc1.bias, grads, ws, pw, "fc1", dx_bf16=dh1)
     K.layernorm_rows_bwd(x1, dh1, blk.norm2.weight, dx, grads.of(blk.norm2.weight), grads.of(blk.norm2.bias), dres=dx,
                          eps=blk.norm2.eps)
     # ---- attention half: x1 = x0 + scatter(proj(attn(qkv(gather(LN1(x0))))))
     dyw = ws.get("bw_dyw", (rows, C), torch.bfloat16, dev)
-    K.cast_rows_bf16(dx, dyw, geom, rscale=s_attn, rscale_rows=tok)
+    bp = blk.attn.proj.bias
+    fusep = bool(_FUSE_COLSUM) and bp is not None and bp.requires_grad and C <= 1024
+    K.cast_rows_bf16(dx, dyw, geom, rscale=s_attn, rscale_rows=tok, colsum=grads.of(bp) if fusep else None)
     datt = ws.get("bw_datt", (rows, C), torch.bfloat16, dev)
-    linear_bwd(dyw, att, blk.attn.proj.weight, blk.attn.proj.bias, grads, ws, pw, "proj", dx_bf16=datt)
+    linear_bwd(dyw, att, blk.attn.proj.weight, blk.attn.proj.bias, grads, ws, pw, "proj", dx_bf16=datt, bias_done=fusep)
     dqkv = ws.get("bw_dqkv", (rows, 3 * C), torch.bfloat16, dev)
     tbl = blk.attn.relative_position_bias_table
     K.window_attention_bwd(qkv, att, datt, table_t, geom, dqkv, grads.table_t(tbl) if tbl.requires_grad else None, lse=lse)

@@ -1164,6 +1164,45 @@ def test_decoder_tails_training_step(flags, cfgkw):
     check_direction(got, ref, f"{flags} training step", min_cos=0.93 if cfgkw.get("seg_last") else 0.95)
 
 
+def test_cast_rows_with_column_sums():
+    """lavt_cast_rows_colsum_bf16: the fp32 -> bf16 cast of a gradient (identity rows, or gathered into window order with zero pad rows,
+    optionally times the DropPath scale of each row's sample) that also adds the column sums of what it writes into the bias gradient."""
+    from lavt_rs_b200 import _cabi as K
+    from lavt_rs_b200.geometry import window_geometry, window_row_map
+    g = torch.Generator().manual_seed(31)
+    for C, dims, shifted in ((128, (2, 8, 14, 14), True), (512, (1, 4, 10, 13), True), (96, (2, 8, 7, 7), False), (1024, (3, 2, 7, 9), True)):
+        B, D, H, W = dims
+        geom = window_geometry(B, D, H, W, (8, 7, 7), shifted)
+        n = geom.tokens()
+        tok = n // B
+        x = torch.randn(n, C, generator=g).cuda()
+        sc = (torch.rand(B, generator=g) + 0.5).cuda()
+        acc0 = torch.randn(C, generator=g).cuda()
+        # identity rows
+        out = torch.empty(n, C, device="cuda", dtype=torch.bfloat16)
+        cs = acc0.clone()
+        K.cast_rows_bf16(x, out, rscale=sc, rscale_rows=tok, colsum=cs)
+        ref = x * sc.repeat_interleave(tok)[:, None]
+        assert torch.equal(out, ref.to(torch.bfloat16))
+        assert rel_l2(cs - acc0, ref.sum(0)) < 1e-5
+        # window order: pad rows are zeros and add nothing
+        rows, _, _ = window_row_map(geom)
+        rows = rows.cuda()
+        M = geom.rows()
+        outw = torch.full((M, C), 7.0, device="cuda", dtype=torch.bfloat16)
+        cs = acc0.clone()
+        K.cast_rows_bf16(x, outw, geom, colsum=cs)
+        refw = torch.zeros(M, C, device="cuda")
+        live = rows >= 0
+        refw[live] = x[rows[live]]
+        assert torch.equal(outw, refw.to(torch.bfloat16))
+        assert rel_l2(cs - acc0, refw.sum(0)) < 1e-5
+        # and the plain cast gives the same rows
+        outp = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+        K.cast_rows_bf16(x, outp, geom)
+        assert torch.equal(outp, outw)
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""
