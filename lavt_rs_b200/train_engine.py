@@ -369,6 +369,55 @@ def _att_ln_bwd(x_raw: torch.Tensor, dy: torch.Tensor, ln, grads: GradStore, ws:
     return out
 
 
+def _att_bn_fwd(raw: torch.Tensor, bn, B: int, ws: Workspace):
+    """--att_norm_layer_type BN in training mode (nn.BatchNorm1d in train(), reference lib/backbone.py:1297-1316): batch statistics over all
+    clips and tokens of ``raw`` fp32 [B,n,C].  Nothing is materialised: the affine normalisation y = (x - mean) rstd gamma + beta is handed to
+    the consumers as FOLDED statistics (mean' = mean - beta / (rstd gamma), rstd' = rstd gamma), which they already apply per element.
+    Returns (folded statistics [B,2,C], true statistics [2,C])."""
+    Bq, n, C = raw.shape
+    dev = raw.device
+    if _world() is not None:
+        raise NotImplementedError("--att_norm_layer_type BN under SyncBatchNorm (multi-GPU training) is not implemented on the B200 path")
+    N_ = Bq * n
+    stats = torch.empty(1, 2, C, device=dev, dtype=torch.float32)
+    stw = ws.get("pw_statw1", (K.instnorm_workspace_floats(1, N_, C),), torch.float32, dev)
+    K.instnorm_stats(raw.view(1, N_, C), stats, stw, eps=bn.eps)
+    _count(2)
+    with torch.no_grad():       # [C]-sized bookkeeping: folded statistics and the running buffers
+        mean, rstd = stats[0, 0], stats[0, 1]
+        if bn.track_running_stats:
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            var = 1.0 / rstd ** 2 - bn.eps
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var * (N_ / max(N_ - 1, 1)), alpha=mom)
+            bn.num_batches_tracked += 1
+        gam = bn.weight.detach().float()
+        gam = torch.where(gam.abs() < 1e-12, torch.full_like(gam, 1e-12), gam)
+        rs2 = rstd * gam
+        folded = torch.stack([mean - bn.bias.detach().float() / rs2, rs2]).unsqueeze(0).expand(B, 2, C).contiguous()
+    return folded, stats.view(2, C)
+
+
+def _att_bn_bwd(raw: torch.Tensor, stats: torch.Tensor, g: torch.Tensor, bn, grads: GradStore, ws: Workspace, pw, name: str) -> torch.Tensor:
+    """Adjoint of the BatchNorm above: raw fp32 [B,n,C], true statistics [2,C], g bf16 [B*n, C] = gradient of the BatchNorm output.
+    The decoder's BatchNorm + ReLU adjoint kernels are reused with an all-ones ReLU mask.  Returns the bf16 gradient of ``raw``."""
+    N_, C = g.shape
+    dev = g.device
+    ones = pw.get("bn_ones_%d_%d" % (N_, C), [], lambda: torch.ones(N_, C, device=dev, dtype=torch.bfloat16))
+    sums = torch.zeros(2, C, device=dev, dtype=torch.float32)
+    z = raw.view(N_, C)
+    K.bn_relu_bwd_reduce(g, ones, z, stats, sums)
+    with torch.no_grad():
+        if bn.weight.requires_grad:
+            grads.of(bn.weight).add_(sums[1])
+        if bn.bias.requires_grad:
+            grads.of(bn.bias).add_(sums[0])
+    out = ws.get(name, (N_, C), torch.bfloat16, dev)
+    K.bn_relu_bwd_apply(g, ones, z, stats, bn.weight, sums, out, N_)
+    _count(2)
+    return out
+
+
 def _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act):
     """r = GELU(project_mm(a2)) (:930) and the LanguageGate (:519-525) with what their adjoints need."""
     N_, C = x.shape
@@ -450,10 +499,11 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     # InstanceNorm1d -- the consumers read identity "statistics" (mean 0, rstd 1) of the (LayerNorm'd) projection and the backward's
     # InstanceNorm reductions are zeroed, which turns its adjoint into a pass-through; LN adds the LayerNorm adjoint behind it
     norm_kind = getattr(att, "att_norm_layer_type", "IN")
-    if norm_kind not in ("IN", "none", "LN"):
-        raise NotImplementedError("--att_norm_layer_type %s is inference-only on the B200 path" % norm_kind)
+    if norm_kind not in ("IN", "none", "LN", "BN"):
+        raise NotImplementedError("--att_norm_layer_type %s is not known" % norm_kind)
     ident = None
     q_raw = l_raw = None
+    bn_q = bn_l = None            # BN: (folded statistics [B,2,C], true statistics [2,C])
     if norm_kind != "IN":
         ident = pw.get("ident_%d_%s" % (B, dev), [], lambda: torch.stack([torch.zeros(B, C), torch.ones(B, C)], 1).to(dev).contiguous())
     if norm_kind == "LN":
@@ -462,7 +512,10 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         K.layernorm_rows(q_raw.view(N_, C), att.f_query[1].weight, att.f_query[1].bias, out_f32=qpre.view(N_, C), eps=att.f_query[1].eps)
         _count(1)
     stw = ws.get("pw_statw", (K.instnorm_workspace_floats(B, n, C),), f32, dev)
-    if ident is None:
+    if norm_kind == "BN":
+        bn_q = _att_bn_fwd(qpre, att.f_query[1], B, ws)
+        stats_q = bn_q[0]
+    elif ident is None:
         stats_q = torch.empty(B, 2, C, device=dev, dtype=f32)
         K.instnorm_stats(qpre, stats_q, stw)
     else:
@@ -479,7 +532,10 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
         langpre = torch.empty(B, n, C, device=dev, dtype=f32)
         K.layernorm_rows(l_raw.view(N_, C), att.W[1].weight, att.W[1].bias, out_f32=langpre.view(N_, C), eps=att.W[1].eps)
         _count(1)
-    if ident is None:
+    if norm_kind == "BN":
+        bn_l = _att_bn_fwd(langpre, att.W[1], B, ws)
+        stats_l = bn_l[0]
+    elif ident is None:
         stats_l = torch.empty(B, 2, C, device=dev, dtype=f32)
         K.instnorm_stats(langpre, stats_l, stw)
     else:
@@ -489,7 +545,7 @@ def pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.
     rpre, rb, r32, g1, g2, xg = _mm_and_gate_fwd(x, a2, fusion, res_gate, mm_w, gate_act)
     saved = dict(xb=xb, vispre=vispre, vis=vis, qpre=qpre, stats_q=stats_q, kk=kk, vv=vv, o=o, langpre=langpre, stats_l=stats_l,
                  a2=a2, rpre=rpre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B, heads=heads, k_w=k_w, v_w=v_w, gate_act=gate_act,
-                 no_norm=ident is not None, simple=False, q_raw=q_raw, l_raw=l_raw)
+                 no_norm=ident is not None, simple=False, q_raw=q_raw, l_raw=l_raw, bn_q=bn_q, bn_l=bn_l, ident=ident)
     return r32, xg, saved
 
 
@@ -553,7 +609,10 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     if s.get("no_norm"):
         sums[0].zero_()         # Identity instead of InstanceNorm: with zero reductions and rstd = 1 the adjoint below is the pass-through
     dlangpre = ws.get("bw_pw_a", (N_, C), bf, dev)
-    K.instnorm_bwd(s["langpre"], s["stats_l"], sums[0], dlangpre, ga=da2, gb=s["vis"].view(N_, C))
+    # (BN: the kernels above normalised with the FOLDED statistics; the gradient of the BatchNorm OUTPUT is the pass-through of g = d a2 * vis)
+    K.instnorm_bwd(s["langpre"], s["ident"] if s.get("bn_l") is not None else s["stats_l"], sums[0], dlangpre, ga=da2, gb=s["vis"].view(N_, C))
+    if s.get("bn_l") is not None:
+        dlangpre = _att_bn_bwd(s["langpre"], s["bn_l"][1], dlangpre, att.W[1], grads, ws, pw, "bw_pw_bn")
     if s.get("l_raw") is not None:          # --att_norm_layer_type LN: dlangpre is the gradient of the LayerNorm OUTPUT
         dlangpre = _att_ln_bwd(s["l_raw"], dlangpre, att.W[1], grads, ws, "bw_pw_ln")
     do = ws.get("bw_pw_b", (N_, C), bf, dev)
@@ -577,7 +636,9 @@ def pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor], dxg: 
     if s.get("no_norm"):
         sums[1].zero_()
     dqpre = ws.get("bw_pw_b", (N_, C), bf, dev)
-    K.instnorm_bwd(s["qpre"], s["stats_q"], sums[1], dqpre, g_f32=dqhat)
+    K.instnorm_bwd(s["qpre"], s["ident"] if s.get("bn_q") is not None else s["stats_q"], sums[1], dqpre, g_f32=dqhat)
+    if s.get("bn_q") is not None:
+        dqpre = _att_bn_bwd(s["qpre"], s["bn_q"][1], dqpre, att.f_query[1], grads, ws, pw, "bw_pw_bn")
     if s.get("q_raw") is not None:
         dqpre = _att_ln_bwd(s["q_raw"], dqpre, att.f_query[1], grads, ws, "bw_pw_ln")
     # both projections of x: dx (+)= dvispre Wvis + dqpre Wq

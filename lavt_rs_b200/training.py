@@ -35,8 +35,6 @@ def _check_trainable(model) -> None:
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
         if getattr(layer, "gate_act", "tanh") != "tanh" and layer.sep_t_pwam:
             raise NotImplementedError("--lg_act_layer sigmoid with SepTPWAM is inference-only on the B200 path")
-        if getattr(getattr(layer.fusion, "image_lang_att", None), "att_norm_layer_type", "IN") not in ("IN", "none", "LN"):
-            raise NotImplementedError("--att_norm_layer_type BN is inference-only on the B200 path (IN, LN and none train)")
         if layer.version not in ("default", "no_gate", "none"):
             raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
     lazy = any(getattr(layer, "lazy_pred", False) for layer in bb.layers)

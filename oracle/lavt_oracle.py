@@ -187,10 +187,15 @@ def lang_project(l: Tensor, l_mask: Tensor, sd, pre: str) -> Tensor:
     return (h @ sd[pre + "project.2.weight"].t() + sd[pre + "project.2.bias"]).unsqueeze(1)
 
 
-def _att_norm(t: Tensor, sd, name: str, kind: str) -> Tensor:
-    """The norm at index 1 of f_query / W (lib/backbone.py:1297-1316) on tokens-last tensors (B, n, C), eval mode."""
+def _att_norm(t: Tensor, sd, name: str, kind: str, train: bool = False) -> Tensor:
+    """The norm at index 1 of f_query / W (lib/backbone.py:1297-1316) on tokens-last tensors (B, n, C); eval mode unless ``train``
+    (nn.BatchNorm1d in train(): batch statistics over all clips and tokens, biased variance)."""
     if kind == "IN":
         return _instance_norm_tokens(t)
+    if kind == "BN" and train:
+        mean = t.mean((0, 1))
+        var = t.var((0, 1), unbiased=False)
+        return (t - mean) / torch.sqrt(var + 1e-5) * sd[name + ".weight"] + sd[name + ".bias"]
     if kind == "BN":
         return (t - sd[name + ".running_mean"]) / torch.sqrt(sd[name + ".running_var"] + 1e-5) * sd[name + ".weight"] + sd[name + ".bias"]
     if kind == "LN":
@@ -198,7 +203,8 @@ def _att_norm(t: Tensor, sd, name: str, kind: str) -> Tensor:
     return t
 
 
-def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, return_parts: bool = False, att_norm: str = "IN"):
+def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, return_parts: bool = False, att_norm: str = "IN",
+         train_norm: bool = False):
     """x (B,n,C); l (B,768,Nl); l_mask (B,Nl,1) -> x_residual (B,n,C).  ``pre`` = 'backbone.layers.{s}.fusion.'"""
     B, n, C = x.shape
     m = l_mask.to(x.dtype)                                              # (B, Nl, 1)
@@ -206,7 +212,7 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     a = pre + "image_lang_att."
     if a + "project.0.weight" in sd:                                    # --fuse simple (:916-917, 929-930): broadcast sentence vector
         return F.gelu(_lin1x1(vis * lang_project(l, l_mask, sd, a), sd, pre + "project_mm.0"))
-    q = _att_norm(_lin1x1(x, sd, a + "f_query.0"), sd, a + "f_query.1", att_norm)          # (B, n, C)
+    q = _att_norm(_lin1x1(x, sd, a + "f_query.0"), sd, a + "f_query.1", att_norm, train_norm)          # (B, n, C)
     lt = l.transpose(1, 2)                                              # (B, Nl, 768)
     k = _lin1x1(lt, sd, a + "f_key.0") * m                              # (B, Nl, C)
     v = _lin1x1(lt, sd, a + "f_value.0") * m
@@ -219,7 +225,7 @@ def pwam(x: Tensor, l: Tensor, l_mask: Tensor, sd, pre: str, heads: int = 1, ret
     s = s + (1e4 * m.transpose(1, 2) - 1e4).unsqueeze(1)                # (B,1,1,Nl): pads -> -1e4
     p = s.softmax(-1)
     o = (p @ vh).transpose(1, 2).reshape(B, n, C)
-    lang = _att_norm(_lin1x1(o, sd, a + "W.0"), sd, a + "W.1", att_norm)
+    lang = _att_norm(_lin1x1(o, sd, a + "W.0"), sd, a + "W.1", att_norm, train_norm)
     r = F.gelu(_lin1x1(vis * lang, sd, pre + "project_mm.0"))
     if return_parts:
         return r, dict(vis=vis, q=q, k=k, v=v, o=o, lang=lang)

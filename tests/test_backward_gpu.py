@@ -1203,6 +1203,64 @@ def test_cast_rows_with_column_sums():
         assert torch.equal(outp, outw)
 
 
+@pytest.mark.parametrize("stage,heads", [(0, 1), (1, 2)])
+def test_pwam_batchnorm_att_norm_backward(stage, heads):
+    """--att_norm_layer_type BN in training mode (2-D backbone, reference lib/backbone.py:1297-1316: nn.BatchNorm1d in train(), batch statistics
+    over all clips and tokens): the normalisation reaches the PWAM kernels as folded statistics, its adjoint reuses the decoder's BatchNorm
+    kernels.  PWAM + gate gradients (incl. the BatchNorm weights / biases), dx, d l_feats and the running statistics vs the oracle."""
+    from lavt_rs_b200 import engine as E
+    from lavt_rs_b200 import train_engine as T
+    from lavt_rs_b200.args import default_args
+    from lavt_rs_b200.lib.backbone import MultiModalSwinTransformer
+    from lavt_rs_b200.weights import load_reference_state_dict
+    fh = [heads if i == stage else 1 for i in range(4)]
+    cfg = O.OracleConfig(depths=(2, 2, 2, 2), window=(1, 7, 7), clamp_window=False, video=False, att_norm="BN", fusion_heads=tuple(fh))
+    sd = dict(O.random_state_dict(cfg, seed=0))
+    bb = MultiModalSwinTransformer(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.0,
+                                   patch_norm=True, num_heads_fusion=fh, args=default_args(["--att_norm_layer_type", "BN"]))
+    C = 128 * 2 ** stage
+    pre = f"backbone.layers.{stage}."
+    g = torch.Generator().manual_seed(37)
+    for k in ("res_gate.0.weight", "res_gate.2.weight"):
+        sd[pre + k] = torch.randn(C, C, generator=g) * C ** -0.5
+    load_reference_state_dict(bb, sd, "backbone.")
+    bb = bb.cuda().train()
+    layer = bb.layers[stage]
+    B, n, Nl = 3, 520, 12
+    x = torch.randn(B, n, C, generator=g)
+    l = torch.randn(B, 768, Nl, generator=g)
+    m = torch.ones(B, Nl, 1)
+    m[1, Nl - 3:] = 0
+    gr = torch.randn(B, n, C, generator=g)
+    gx = torch.randn(B, n, C, generator=g)
+
+    def fn(sd2, xx, ll):
+        r = O.pwam(xx, ll, m, sd2, pre + "fusion.", heads, att_norm="BN", train_norm=True)
+        return torch.cat([r, O.language_gate(xx, r, sd2, pre + "res_gate.")], 0)
+    (dx_ref, dl_ref), pg_ref = _oracle_grads(fn, sd, pre, [x, l], torch.cat([gr, gx], 0))
+    pg_ref = {k: v for k, v in pg_ref.items() if k.startswith("fusion.") or k.startswith("res_gate.")}
+    assert "fusion.image_lang_att.f_query.1.weight" in pg_ref and "fusion.image_lang_att.W.1.bias" in pg_ref
+    ws = E.workspace("cuda")
+    grads = T.GradStore()
+    xf = x.cuda().reshape(-1, C).contiguous()
+    bnq = layer.fusion.image_lang_att.f_query[1]
+    rm0 = bnq.running_mean.clone()
+    r32, xg, saved = T.pwam_gate_fwd(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate, l.cuda(), m.squeeze(-1).cuda(), B, ws)
+    ref = fn(sd, x, l)
+    assert rel_l2(r32, ref[:B].reshape(-1, C)) < 1.5e-2
+    assert rel_l2(xg, ref[B:].reshape(-1, C)) < 1.5e-2
+    # running statistics moved like nn.BatchNorm1d (momentum 0.1) towards the batch mean of f_query's projection
+    qraw = torch.nn.functional.conv1d(x.transpose(1, 2), sd[pre + "fusion.image_lang_att.f_query.0.weight"], sd[pre + "fusion.image_lang_att.f_query.0.bias"])
+    want = 0.9 * rm0.cpu() + 0.1 * qraw.mean((0, 2))
+    assert rel_l2(bnq.running_mean, want) < 2e-2 and int(bnq.num_batches_tracked) == 1
+    dl = torch.zeros(B, 768, Nl, device="cuda")
+    dx = T.pwam_gate_bwd(layer.fusion, layer.res_gate, saved, gr.cuda().reshape(-1, C).contiguous(), gx.cuda().reshape(-1, C).contiguous(), grads, ws, dl)
+    torch.cuda.synchronize()
+    assert rel_l2(dx, dx_ref.reshape(-1, C)) < GRAD_L2, ("dx", rel_l2(dx, dx_ref.reshape(-1, C)))
+    assert rel_l2(dl, dl_ref) < GRAD_L2, ("dl", rel_l2(dl, dl_ref))
+    check_grads(grads.named(layer), pg_ref, f"PWAM with BatchNorm attention norms, stage {stage}")
+
+
 def test_conv_weight_gradient_tma():
     """lavt_conv3x3_wgrad / lavt_conv3d_wgrad (one launch, 4-D / 5-D TMA boxes as MN-major operands, taps as box offsets, zero padding
     from out-of-bounds fill) vs autograd of F.conv2d / F.conv3d, including sizes with partial pixel tiles."""

@@ -107,18 +107,18 @@ def test_lazy_pred_state_dict_matches_oracle_contract():
 
 
 def test_inference_only_variants_refuse_training():
-    """The lib/bcam.py fusions and the BatchNorm attention norm have no hand-written backward: the training entry point must refuse them up
-    front.  --lazy_pred, --fuse simple, the none / LN attention norms and the decoder tails train (tests/test_backward_gpu.py)."""
+    """The lib/bcam.py fusions have no hand-written backward: the training entry point must refuse them up front.  --lazy_pred,
+    --fuse simple, the BN / LN / none attention norms and the decoder tails train (tests/test_backward_gpu.py)."""
     from lavt_rs_b200 import training
     from lavt_rs_b200.lib import segmentation
-    for flag in (["--bcam"], ["--efn"], ["--gacd"], ["--att_norm_layer_type", "BN"]):
+    for flag in (["--bcam"], ["--efn"], ["--gacd"]):
         m = segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", *flag]))
         with pytest.raises(NotImplementedError):
             training._check_trainable(m)
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "tiny"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--lazy_pred"])))
     training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--interpolate_before_seg", "--seg_last"])))
-    for kind in ("none", "LN"):
+    for kind in ("none", "LN", "BN"):
         training._check_trainable(segmentation.lavt(pretrained="", args=default_args(["--swin_type", "base", "--att_norm_layer_type", kind])))
     training._check_trainable(segmentation.lavt_video(pretrained="", args=default_args(["--swin_type", "tiny", "--fuse", "simple"])))
     # the sigmoid gate trains (gate adjoint modes 7 / 8 of lavt_gate_elementwise)
