@@ -938,7 +938,7 @@ def conv3d_bwd(dy: torch.Tensor, x5: torch.Tensor, conv, grads: GradStore, ws: W
 
 
 def sep_t_pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: torch.Tensor, mask: torch.Tensor, B: int, D: int, H: int,
-                        W: int, ws: Workspace):
+                        W: int, ws: Workspace, gate_act: str = "tanh"):
     """Training twin of ``engine.sep_t_pwam_gate``: returns (r fp32 [B*n, C], gated x or None, saved)."""
     N_, C = x.shape
     n = N_ // B
@@ -1015,11 +1015,11 @@ def sep_t_pwam_gate_fwd(x: torch.Tensor, xb: torch.Tensor, fusion, res_gate, l: 
         K.gemm_bf16(rb, g0w, act=K.ACT_RELU, out_bf16=g1)
         K.gemm_bf16(g1, g2w, out_bf16=g2)
         xg = rows(f32)
-        K.gate_elementwise(0, g2, rb, f=x, out_f32=xg)
+        K.gate_elementwise(0 if gate_act == "tanh" else 7, g2, rb, f=x, out_f32=xg)      # --lg_act_layer sigmoid: modes 7 / 8
         _count(3)
     saved = dict(xb=xb, vt_pre=vt_pre, vs_pre=vs_pre, vis=vis, qa=qa, qb=qb, qhat=qhat, sa_q=sa_q, sb_q=sb_q, kk=kk, vv=vv, o=o, la=la,
                  lb=lb, lang=lang, sa_l=sa_l, sb_l=sb_l, a2=a2, rt_pre=rt_pre, rs_pre=rs_pre, rb=rb, g1=g1, g2=g2, l=l, mask=mask, B=B,
-                 dims=(D, H, W), heads=heads, k_w=k_w, v_w=v_w, ident=ident)
+                 dims=(D, H, W), heads=heads, k_w=k_w, v_w=v_w, ident=ident, gate_act=gate_act)
     return r32, xg, saved
 
 
@@ -1044,11 +1044,12 @@ def sep_t_pwam_gate_bwd(fusion, res_gate, saved, dr_out: Optional[torch.Tensor],
     dr = dr_out
     if res_gate is not None and dxg is not None:
         dg2pre = wsb("a")
+        gmode = 1 if s.get("gate_act", "tanh") == "tanh" else 8
         if dr is None:
             dr = wsb("dr", f32)
-            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
+            K.gate_elementwise(gmode, s["g2"], s["rb"], f=dxg, f2=None, out_bf16=dg2pre, out_f32=dr)
         else:
-            K.gate_elementwise(1, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
+            K.gate_elementwise(gmode, s["g2"], s["rb"], f=dxg, f2=dr, out_bf16=dg2pre, out_f32=dr)
         dg1 = wsb("b")
         linear_bwd(dg2pre, s["g1"], res_gate[2].weight, None, grads, ws, pw, "g2", dx_bf16=dg1)
         K.gate_elementwise(2, dg1, s["g1"], out_bf16=dg1)

@@ -33,8 +33,6 @@ def _check_trainable(model) -> None:
     for layer in bb.layers:
         if getattr(layer.fusion, "kind", "pwam") in ("gacd", "bcam", "efn"):
             raise NotImplementedError("--%s is inference-only on the B200 path" % layer.fusion.kind)
-        if getattr(layer, "gate_act", "tanh") != "tanh" and layer.sep_t_pwam:
-            raise NotImplementedError("--lg_act_layer sigmoid with SepTPWAM is inference-only on the B200 path")
         if layer.version not in ("default", "no_gate", "none"):
             raise NotImplementedError(f"--version {layer.version} is not implemented on the B200 training path")
     lazy = any(getattr(layer, "lazy_pred", False) for layer in bb.layers)
@@ -80,7 +78,8 @@ def segment_forward(model, x: torch.Tensor, l_feats: torch.Tensor, l_mask: torch
                 torch.cuda.current_stream().wait_event(lang_ready)
             l = _lang(l_feats)
         if layer.sep_t_pwam:
-            r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws)
+            r32, xg, pw_saved = T.sep_t_pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, D, Hc, Wc, ws,
+                                                      gate_act=getattr(layer, "gate_act", "tanh"))
         else:
             r32, xg, pw_saved = T.pwam_gate_fwd(feat, xb, layer.fusion, gate, l, mask, B, ws, gate_act=getattr(layer, "gate_act", "tanh"))
         if layer.version == "no_gate" and (not last or layer.hs):       # ablation: plain residual add x' = x + r (:570-575)

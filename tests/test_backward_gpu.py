@@ -724,12 +724,14 @@ def _sep_setup(embed=128, heads=(4, 8, 16, 32)):
     return cfg, sd, bb.cuda().train()
 
 
-@pytest.mark.parametrize("stage,gate", [(0, True), (2, False)])
+@pytest.mark.parametrize("stage,gate", [(0, True), (2, False), (1, "sigmoid")])
 def test_sep_t_pwam_gate_backward(stage, gate):
-    """SepTPWAM under the README video flags (Conv3d(3,3,3) + Conv3d(1,1,1) branches, summed InstanceNorms) + LanguageGate:
-    every gradient vs autograd through the oracle."""
+    """SepTPWAM under the README video flags (Conv3d(3,3,3) + Conv3d(1,1,1) branches, summed InstanceNorms) + LanguageGate (tanh, or the
+    sigmoid of --lg_act_layer sigmoid): every gradient vs autograd through the oracle."""
     from lavt_rs_b200 import engine as E
     from lavt_rs_b200 import train_engine as T
+    gate_act = "sigmoid" if gate == "sigmoid" else "tanh"
+    gate = bool(gate)
     cfg, sd, bb = _sep_setup()
     layer = bb.layers[stage]
     C = 128 * 2 ** stage
@@ -754,7 +756,7 @@ def test_sep_t_pwam_gate_backward(stage, gate):
         r = O.sep_t_pwam(xx, ll, m, sd2, pre + "fusion.", 1)
         if not gate:
             return r
-        return torch.cat([r, O.language_gate(xx.reshape(B, n, C), r, sd2, pre + "res_gate.")], 0)
+        return torch.cat([r, O.language_gate(xx.reshape(B, n, C), r, sd2, pre + "res_gate.", act=gate_act)], 0)
     gout = torch.cat([gr, gx], 0) if gate else gr
     (dx_ref, dl_ref), pg_ref = _oracle_grads(fn, sd, pre, [x, l], gout)
     pg_ref = {k: v for k, v in pg_ref.items() if k.startswith("fusion.") or (gate and k.startswith("res_gate."))}
@@ -762,7 +764,9 @@ def test_sep_t_pwam_gate_backward(stage, gate):
     grads = T.GradStore()
     xf = x.cuda().reshape(-1, C).contiguous()
     r32, xg, saved = T.sep_t_pwam_gate_fwd(xf, xf.to(torch.bfloat16), layer.fusion, layer.res_gate if gate else None, l.cuda(),
-                                           m.squeeze(-1).cuda(), B, D, H, W, ws)
+                                           m.squeeze(-1).cuda(), B, D, H, W, ws, gate_act=gate_act)
+    if gate:
+        assert rel_l2(xg, fn(sd, x, l)[B:].reshape(-1, C)) < 1.5e-2
     ref = fn(sd, x, l)
     assert rel_l2(r32, ref[:B].reshape(-1, C)) < 1.5e-2
     dl = torch.zeros(B, 768, Nl, device="cuda")
